@@ -1,0 +1,89 @@
+"""Synthetic nuScenes-shaped scenes for tests and bench.
+
+Shapes follow the reference's trajdata batch as parsed by `parse_node_centric`
+(src/tbsim/utils/trajdata_utils.py:346-475): agent-centric frames, 224x224 raster at 0.5 m/px with
+`raster_from_agent = [[2,0,56],[0,2,112],[0,0,1]]` (trajdata_utils.py:385-389, config.yaml:73-86).
+All tensors are CPU fp32/bool; callers move them to the device.
+"""
+import math
+
+import torch
+
+
+def make_scenes(num_scenes, agents_per_scene, horizon=52, seed=123, cond_dim=256, dense=False):
+    """Returns (aux_info, batch).  B = num_scenes * agents_per_scene agent rows, scene-major.
+
+    dense=True packs the agents of a scene within ~12 m so that agent-agent collisions and
+    off-road events actually occur (used by the guidance tests)."""
+    g = torch.Generator().manual_seed(seed)
+    S, A, T = num_scenes, agents_per_scene, horizon
+    B = S * A
+    cond = torch.randn(B, cond_dim, generator=g)
+    v = torch.rand(B, generator=g) * 15.0
+    stationary = torch.rand(B, generator=g) < 0.2
+    v = torch.where(stationary, torch.rand(B, generator=g) * 0.4, v)
+    curr = torch.stack([torch.zeros(B), torch.zeros(B), v, torch.zeros(B)], dim=1)
+    extent = torch.stack([4.0 + 1.5 * torch.rand(B, generator=g),
+                          1.8 + 0.4 * torch.rand(B, generator=g),
+                          torch.full((B,), 1.6)], dim=1)
+    spread = 12.0 if dense else 50.0
+    pos = (torch.rand(B, 2, generator=g) * 2 - 1) * spread
+    if dense:
+        yaw = (torch.rand(B, generator=g) * 2 - 1) * 0.3 + \
+            math.pi * (torch.rand(B, generator=g) < 0.5).float()
+    else:
+        yaw = (torch.rand(B, generator=g) * 2 - 1) * math.pi
+    c, s = torch.cos(yaw), torch.sin(yaw)
+    wfa = torch.zeros(B, 3, 3)
+    wfa[:, 0, 0], wfa[:, 0, 1], wfa[:, 0, 2] = c, -s, pos[:, 0]
+    wfa[:, 1, 0], wfa[:, 1, 1], wfa[:, 1, 2] = s, c, pos[:, 1]
+    wfa[:, 2, 2] = 1.0
+    rfa = torch.tensor([[2., 0., 56.], [0., 2., 112.], [0., 0., 1.]]).repeat(B, 1, 1)
+    # drivable map: a road band around the agent's heading axis + random rectangles
+    dmap = torch.zeros(B, 224, 224, dtype=torch.bool)
+    half = torch.randint(6, 22, (B,), generator=g)          # band half-width in px (3..11 m)
+    off = torch.randint(-6, 7, (B,), generator=g)
+    rows = torch.arange(224)[None, :]
+    band = (rows >= (112 + off - half)[:, None]) & (rows <= (112 + off + half)[:, None])
+    dmap |= band[:, :, None]
+    nrect = 3
+    r0 = torch.randint(0, 200, (B, nrect), generator=g)
+    c0 = torch.randint(0, 200, (B, nrect), generator=g)
+    rh = torch.randint(8, 60, (B, nrect), generator=g)
+    cw = torch.randint(8, 60, (B, nrect), generator=g)
+    cols = torch.arange(224)[None, :]
+    for k in range(nrect):
+        rm = (rows >= r0[:, k:k + 1]) & (rows < (r0[:, k:k + 1] + rh[:, k:k + 1]))
+        cm = (cols >= c0[:, k:k + 1]) & (cols < (c0[:, k:k + 1] + cw[:, k:k + 1]))
+        dmap |= rm[:, :, None] & cm[:, None, :]
+    # other agents' futures in each ego frame: straight-line constant-velocity motion
+    tt = (torch.arange(1, T + 1).float() * 0.1)
+    fut_local = torch.stack([v[:, None] * tt[None, :], torch.zeros(B, T)], dim=-1)          # [B,T,2]
+    fut_world = torch.einsum('bij,btj->bti', wfa[:, :2, :2], fut_local) + wfa[:, None, :2, 2]
+    fw = fut_world.view(S, A, T, 2)
+    So = max(A - 1, 1)
+    others = torch.zeros(S, A, So, T, 2)
+    for a in range(A):
+        idx = [j for j in range(A) if j != a] or [a]
+        others[:, a] = fw[:, idx]
+    others = others.view(B, So, T, 2)
+    Rinv = wfa[:, :2, :2].transpose(1, 2)
+    others = torch.einsum('bij,bstj->bsti', Rinv, others - wfa[:, None, None, :2, 2])
+    avail = torch.rand(B, So, T, generator=g) < 0.7
+    if A == 1:
+        avail[:] = False
+    target = torch.stack([v * 5.2, (torch.rand(B, generator=g) * 2 - 1) * 3.0], dim=1)
+    aux = {'cond_feat': cond, 'curr_states': curr}
+    batch = {
+        'history_positions': torch.zeros(B, 31, 2),
+        'curr_speed': v.clone(),
+        'extent': extent,
+        'world_from_agent': wfa,
+        'raster_from_agent': rfa,
+        'scene_index': torch.arange(S).repeat_interleave(A),
+        'drivable_map': dmap,
+        'all_other_agents_future_positions': others.contiguous(),
+        'all_other_agents_future_availability': avail,
+        'target_pos': target,
+    }
+    return aux, batch

@@ -1,0 +1,242 @@
+"""Pin the oracle against the REAL reference and write tests/golden/*.npz  (container-only).
+
+Run:  python oracle/make_golden.py          (needs /root/reference; prints every comparison)
+The .npz files hold seeded inputs + the REFERENCE's outputs (not the oracle's); tests/test_oracle.py
+re-checks the oracle against them anywhere, tests/test_gpu_*.py check the CUDA path against them on
+the B200.  Weights are not stored (17 MB): they are regenerated from `torch.manual_seed(0)` through
+cld_b200's parameter containers, whose construction order mirrors the reference so the init is
+bit-identical; weight checksums are stored to detect drift.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [ROOT, HERE]
+import cld_oracle as O          # noqa: E402
+import ref_harness as RH        # noqa: E402
+from cld_b200.synthetic import make_scenes   # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+torch.set_num_threads(8)
+
+
+def rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def check(name, a, b, tol):
+    r = rel(a.double(), b.double())
+    print("%-40s rel=%.3e  max|d|=%.3e  %s" % (name, r, (a - b).abs().max().item(), "OK" if r <= tol else "FAIL"))
+    assert r <= tol, name
+
+
+def sd_np(sd):
+    return {k: v.detach().numpy() for k, v in sd.items()}
+
+
+def main():
+    RH.install()
+    from tbsim.utils.guidance_loss import PerturbationGuidance
+    out = {}
+    # ---------------- schedule --------------------------------------------------------------
+    for n in (10, 16, 100):
+        dm, vae, algo = RH.build_models(n_timesteps=n)
+        sch = O.make_schedule(n)
+        for k, v in sch.items():
+            assert torch.equal(v, getattr(dm, k)), (n, k)
+        print("schedule n=%d: 14 buffers bit-identical" % n)
+    dm, vae, algo = RH.build_models(n_timesteps=10)
+    unet_sd = {k: v.detach() for k, v in dm.model.state_dict().items()}
+    dec_sd = {k: v.detach() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    wsum = {
+        'unet_sum': float(sum(v.double().sum() for v in unet_sd.values())),
+        'unet_abs': float(sum(v.double().abs().sum() for v in unet_sd.values())),
+        'dec_sum': float(sum(v.double().sum() for v in dec_sd.values())),
+        'dec_abs': float(sum(v.double().abs().sum() for v in dec_sd.values())),
+    }
+    print("weight checksums", wsum)
+
+    # ---------------- unet forward -----------------------------------------------------------
+    torch.manual_seed(11)
+    R = 6
+    x = torch.randn(R, 52, 4)
+    cond = torch.randn(R, 256)
+    t = torch.tensor([0, 1, 3, 5, 8, 9])
+    with torch.no_grad():
+        eps_ref = dm.model(x, {'cond_feat': cond}, t)
+        eps_or = O.unet_forward(unet_sd, x, cond, t)
+    check("unet_forward T=52", eps_or, eps_ref, 2e-6)
+    x104 = torch.randn(3, 104, 4)
+    with torch.no_grad():
+        e104_ref = dm.model(x104, {'cond_feat': cond[:3]}, t[:3])
+        e104_or = O.unet_forward(unet_sd, x104, cond[:3], t[:3])
+    check("unet_forward T=104", e104_or, e104_ref, 2e-6)
+    np.savez_compressed(os.path.join(GOLD, "unet.npz"), x=x.numpy(), cond=cond.numpy(), t=t.numpy(),
+                        eps=eps_ref.numpy(), x104=x104.numpy(), eps104=e104_ref.numpy(), **wsum)
+
+    # ---------------- cfg0 sampler: 1 scene x 16 agents, DDPM-10 (Appendix A recipe) ------------
+    torch.manual_seed(123)
+    cond16 = torch.randn(16, 256)
+    curr16 = torch.cat([torch.zeros(16, 2), torch.rand(16, 1) * 10, torch.zeros(16, 1)], 1)
+    torch.manual_seed(7)
+    with torch.no_grad():
+        o = dm({'history_positions': torch.zeros(16, 31, 2)}, {'cond_feat': cond16, 'curr_states': curr16}, algo)
+    # replay the same RNG stream to capture x_init and the per-step noises the reference drew
+    torch.manual_seed(7)
+    x_init = torch.randn(16, 1, 52, 4).reshape(16, 52, 4)
+    # the reference draws randn_like at EVERY step (also t=0 where it is multiplied by 0)
+    sch = O.make_schedule(10)
+    steps = O.step_indices(10, 1)
+    xs = x_init.clone()
+    noises = []
+    with torch.no_grad():
+        for i in steps:
+            tt = torch.full((16,), i, dtype=torch.long)
+            eps = dm.model(xs, {'cond_feat': cond16}, tt)
+            mean, sig = O.ddpm_mean_sigma(sch, xs, eps, i)
+            nz = torch.randn_like(mean)
+            noises.append(nz)
+            xs = mean + (0.0 if i == 0 else 1.0) * sig * nz
+    noises = torch.stack(noises)
+    check("replay == reference DmModel.forward", xs, o['pred_traj'], 1e-6)
+    with torch.no_grad():
+        so = O.sample(unet_sd, sch, cond16, x_init, noises, 10, 1, 'ddpm')
+    check("oracle sample cfg0 pred_traj", so['pred_traj'], o['pred_traj'], 1e-5)
+    check("oracle sample cfg0 x1", so['x1'], o['x1'], 1e-5)
+    check("oracle sample cfg0 log_prob_final", so['log_prob_final'], o['log_prob_final'], 1e-6)
+    with torch.no_grad():
+        act_ref = vae.lstmvae.lstm_dec(o['pred_traj'], cond16)
+        traj_ref = vae.convert_action_to_state_and_action(act_ref, curr16, descaled_output=True)
+        traj_or, act_or = O.decode_rollout(dec_sd, o['pred_traj'], cond16, curr16)
+        traj_scaled_ref = vae.convert_action_to_state_and_action(act_ref, curr16)
+    check("lstm_decode", act_or, act_ref, 1e-5)
+    check("decode_rollout traj", traj_or, traj_ref, 1e-5)
+    check("scale_traj", O.scale_traj(traj_or), traj_scaled_ref, 1e-5)
+    np.savez_compressed(os.path.join(GOLD, "cfg0_sample.npz"), cond=cond16.numpy(), curr=curr16.numpy(),
+                        x_init=x_init.numpy(), noises=noises.numpy(), pred_traj=o['pred_traj'].numpy(),
+                        x1=o['x1'].numpy(), log_prob_final=o['log_prob_final'].numpy(),
+                        act=act_ref.numpy(), traj=traj_ref.numpy(), **wsum)
+
+    # ---------------- strided DDPM (n=100, stride 2) through the reference ------------------------
+    dm100, _, _ = RH.build_models(n_timesteps=100)
+    assert all(torch.equal(a, b) for a, b in zip(dm100.model.state_dict().values(), unet_sd.values()))
+    dm100.stride = 2
+    torch.manual_seed(5)
+    with torch.no_grad():
+        o2 = dm100({'history_positions': torch.zeros(4, 31, 2)}, {'cond_feat': cond16[:4], 'curr_states': curr16[:4]}, algo)
+    torch.manual_seed(5)
+    xi2 = torch.randn(4, 1, 52, 4).reshape(4, 52, 4)
+    sch100 = O.make_schedule(100)
+    xs = xi2.clone(); nz2 = []
+    with torch.no_grad():
+        for i in O.step_indices(100, 2):
+            eps = dm100.model(xs, {'cond_feat': cond16[:4]}, torch.full((4,), i, dtype=torch.long))
+            mean, sig = O.ddpm_mean_sigma(sch100, xs, eps, i)
+            n_ = torch.randn_like(mean); nz2.append(n_)
+            xs = mean + (0.0 if i == 0 else 1.0) * sig * n_
+    nz2 = torch.stack(nz2)
+    check("replay stride2 == reference", xs, o2['pred_traj'], 1e-6)
+    assert o2['x1'] is None
+    with torch.no_grad():
+        so2 = O.sample(unet_sd, sch100, cond16[:4], xi2, nz2, 100, 2, 'ddpm')
+    check("oracle sample n=100 stride=2", so2['pred_traj'], o2['pred_traj'], 2e-5)
+    np.savez_compressed(os.path.join(GOLD, "stride2_sample.npz"), cond=cond16[:4].numpy(), x_init=xi2.numpy(),
+                        noises=nz2.numpy(), pred_traj=o2['pred_traj'].numpy(), **wsum)
+
+    # ---------------- rollout with saturating actions vs the reference ------------------------------
+    torch.manual_seed(21)
+    u = torch.randn(32, 52, 2) * torch.tensor([6.0, 1.5])
+    c0 = torch.cat([torch.randn(32, 2), torch.rand(32, 1) * 28 - 2, torch.randn(32, 1)], 1)
+    from tbsim.models.diffuser_helpers import unicyle_forward_dynamics
+    st_ref = unicyle_forward_dynamics(dm.dyn, c0, u, 0.1, mode='parallel')
+    check("unicycle (saturating)", O.unicycle_rollout(c0, u), st_ref, 1e-5)
+    np.savez_compressed(os.path.join(GOLD, "unicycle.npz"), u=u.numpy(), curr=c0.numpy(), state=st_ref.numpy())
+
+    # ---------------- indicators / failure rates -----------------------------------------------------
+    from models.rl.criticmodel import failure_rate_compute, compute_collision_reward
+    aux, batch = make_scenes(2, 8, seed=31, dense=True)
+    torch.manual_seed(32)
+    ui = torch.randn(16, 52, 2) * torch.tensor([3.0, 0.6])
+    with torch.no_grad():
+        st = O.unicycle_rollout(aux['curr_states'], ui)
+        tr = torch.cat([st, ui], -1)
+        # make some rows hit another agent's future so the collision indicator is exercised
+        oth = batch['all_other_agents_future_positions']
+        tr[3, :, :2] = oth[3, 1] + 0.3
+        tr[9, 10:20, :2] = oth[9, 4, 10:20] - 0.5
+    fr_ref = failure_rate_compute(tr, batch)
+    fr_or = O.failure_rates(tr[..., :2], batch)
+    print("failure rates ref", fr_ref, "oracle", fr_or)
+    assert all(abs(fr_ref[k] - fr_or[k]) < 1e-9 for k in fr_ref)
+    offroad, coll = O.indicators(tr[..., :2], batch)
+    cr = compute_collision_reward(tr[..., :2], batch)
+    assert torch.equal(-cr.view(-1), coll)
+    np.savez_compressed(os.path.join(GOLD, "indicators.npz"), traj=tr.numpy(), offroad=offroad.numpy(),
+                        coll=coll.numpy(), **{k: np.float64(v) for k, v in fr_ref.items()})
+
+    # ---------------- guidance: real PerturbationGuidance.perturb, one scene per call -----------------
+    def ref_perturb(z_mean, aux_s, batch_s, N, cfg_list, opt):
+        def transform(x_dec, data_batch, params, bsize=None, num_samp=1):
+            cs = aux_s['curr_states'].unsqueeze(1).expand(bsize, num_samp, 4).reshape(bsize * num_samp, 4)
+            return vae.convert_action_to_state_and_action(x_dec, cs, scaled_input=True, descaled_output=True)
+        pg = PerturbationGuidance(transform, {})
+        pg.set_guidance([cfg_list])
+        condN = aux_s['cond_feat'].repeat_interleave(N, 0)
+        xg = z_mean.clone().detach().requires_grad_()
+        x_out, per = pg.perturb(xg, batch_s, opt, num_samp=N, decoder=lambda zz: vae.lstmvae.lstm_dec(zz, condN))
+        return x_out.detach(), per
+
+    cfg_list = [
+        {'name': 'agent_collision', 'weight': 50.0, 'agents': None,
+         'params': {'num_disks': 2, 'buffer_dist': 0.2, 'decay_rate': 0.9, 'excluded_agents': None}},
+        {'name': 'map_collision', 'weight': 1.0, 'agents': None,
+         'params': {'num_points_lw': (10, 10), 'decay_rate': 0.9}},
+    ]
+    S, A, N = 3, 6, 2
+    aux, batch = make_scenes(S, A, seed=41, dense=True)
+    torch.manual_seed(42)
+    zg = torch.randn(S * A * N, 52, 4)
+    z_ref, loss_ref = [], {'agent_collision': [], 'map_collision': []}
+    grads_ref = []
+    for s in range(S):
+        aux_s = {k: v[s * A:(s + 1) * A] for k, v in aux.items()}
+        batch_s = O.slice_scene(batch, s * A, (s + 1) * A)
+        batch_s = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch_s.items()}
+        zs = zg[s * A * N:(s + 1) * A * N]
+        # SGD lr=1 exposes the raw gradient:  z' = z - g
+        zo_sgd, _ = ref_perturb(zs, aux_s, batch_s, N, cfg_list, {'optimizer': 'sgd', 'lr': 1.0, 'grad_steps': 1, 'perturb_th': None})
+        grads_ref.append(zs - zo_sgd)
+        zo, per = ref_perturb(zs, aux_s, batch_s, N, cfg_list, {'optimizer': 'adam', 'lr': 0.3, 'grad_steps': 1, 'perturb_th': None})
+        z_ref.append(zo)
+        loss_ref['agent_collision'].append(per['agent_collision_scene_000_00'])
+        loss_ref['map_collision'].append(per['map_collision_scene_000_01'])
+    z_ref = torch.cat(z_ref); grads_ref = torch.cat(grads_ref)
+    loss_ref = {k: torch.cat(v) for k, v in loss_ref.items()}
+    g_or, per_or = O.guidance_grad(dec_sd, zg, aux['cond_feat'], aux['curr_states'], batch, A, N)
+    z_or = O.apply_guidance_update(zg, g_or)
+    lo_ac = torch.cat([p['agent_collision'] for p in per_or]); lo_mc = torch.cat([p['map_collision'] for p in per_or])
+    print("guidance: |g|max %.3e  nonzero frac %.3f  losses ac %.4e mc %.4e" % (
+        grads_ref.abs().max(), (grads_ref != 0).float().mean(), loss_ref['agent_collision'].sum(), loss_ref['map_collision'].sum()))
+    check("guidance loss agent_collision", lo_ac, loss_ref['agent_collision'], 1e-5)
+    check("guidance loss map_collision", lo_mc, loss_ref['map_collision'], 1e-5)
+    # the SGD-extracted reference gradient carries fp32 rounding of (z - (z - g)); compare loosely
+    big = grads_ref.abs() > 1e-4 * grads_ref.abs().max()
+    check("guidance grad (sgd-extracted)", g_or[big], grads_ref[big], 5e-3)
+    sign_agree = (torch.sign(g_or) == torch.sign(z_ref.sub(zg).neg())).float().mean().item()
+    print("sign agreement oracle-grad vs reference adam step: %.6f" % sign_agree)
+    check("guidance adam update z'", z_or, z_ref, 2e-3)
+    np.savez_compressed(os.path.join(GOLD, "guidance.npz"), S=S, A=A, N=N, seed=41, z=zg.numpy(), z_out=z_ref.numpy(),
+                        grad_sgd=grads_ref.numpy(), loss_ac=loss_ref['agent_collision'].numpy(),
+                        loss_mc=loss_ref['map_collision'].numpy(), **wsum)
+    print("golden files written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
