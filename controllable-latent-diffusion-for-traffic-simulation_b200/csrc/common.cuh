@@ -1,0 +1,143 @@
+// Shared declarations of libcld_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cld_b200.h"
+
+#define CLD_MAX_T 128          // horizon upper bound baked into per-thread scan arrays
+#define CLD_TB_TOTAL_MAX 4096  // upper bound of the concatenated time-bias width
+
+namespace cld {
+
+// ------------------------------------------------------------------------------------------------
+// U-Net plan (src/tbsim/models/temporal.py:49-120): 12 residual blocks, 2 down convs, 2 up convs,
+// final block.  Weights are re-packed at load time; fp32 packing: conv taps as [tap][cin][cout].
+// ------------------------------------------------------------------------------------------------
+struct ConvW {
+  float* w = nullptr;   // fp32 [ntaps][cin][cout]
+  float* b = nullptr;   // [cout]
+  int cin = 0, cout = 0, ntaps = 0;
+};
+struct GnW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct ResBlockW {
+  ConvW c0, c1, res;    // res.w == nullptr -> identity
+  GnW n0, n1;
+  int tb_off = 0;       // offset of this block's slice inside the concatenated time-bias
+  int cin = 0, cout = 0;
+};
+
+struct UnetW {
+  // time embedding MLP
+  float *t1_w = nullptr, *t1_b = nullptr, *t2_w = nullptr, *t2_b = nullptr;   // [4d,d],[4d],[d,4d],[d]
+  float* freqs = nullptr;   // [d/2] sinusoid frequencies (diffuser_helpers.py:27-29)
+  // concatenated per-block Linear(288->cout): packed [288][tb_total] + bias[tb_total]
+  float* tb_w = nullptr;
+  float* tb_b = nullptr;
+  int tb_total = 0;
+  ResBlockW rb[12];     // downs.0.0 .. ups.1.1 in execution order
+  ConvW down[2];        // k3 s2 p1
+  ConvW up[2][2];       // transposed conv split in 2 output phases, 2 taps each
+  float* up_b[2] = {nullptr, nullptr};
+  ConvW fin0;           // final Conv1dBlock conv
+  GnW fin0n;
+  ConvW fin1;           // 1x1 conv to latent dim
+  bool loaded = false;
+};
+
+struct DecoderW {
+  // transposed copies [in][4H] for the forward kernel (coalesced register loads)
+  float *wih0 = nullptr, *whh0 = nullptr, *b0 = nullptr;   // [4,256],[64,256],[256] (b_ih+b_hh)
+  float *wih1 = nullptr, *whh1 = nullptr, *b1 = nullptr;   // [64,256],[64,256],[256]
+  // original nn.LSTM layouts [4H][in] for the backward kernel
+  float *wih0_raw = nullptr, *whh0_raw = nullptr, *wih1_raw = nullptr, *whh1_raw = nullptr;
+  float *c2h_w = nullptr, *c2h_b = nullptr;                // transposed [C,64], [64]
+  float *h2a_w = nullptr, *h2a_b = nullptr;                // [2,64],[2]
+  bool loaded = false;
+};
+
+struct Schedule {
+  std::vector<float> x_t_cof, noise_cof, logvar, sqrt_recip, sqrt_recipm1, sqrt_acp, sqrt_1macp;
+  bool loaded = false;
+};
+
+}  // namespace cld
+
+struct CldHandle {
+  CldConfig cfg;
+  int device = 0;
+  int num_sms = 0;
+  std::string err;
+  cld::UnetW unet;
+  cld::DecoderW dec;
+  cld::Schedule sched;
+  std::vector<void*> allocs;       // everything cudaMalloc'ed by the handle
+  // fp32 denoiser workspace (sized for cfg.max_rows)
+  float* act[8] = {nullptr};       // activation buffers, each max_rows * act_elems floats
+  size_t act_elems = 0;            // per-row elements of one activation buffer
+  float* tcm = nullptr;            // [max_rows, 32+cond] Mish([t_emb, cond])
+  float* tbias = nullptr;          // [max_rows, tb_total]
+  // guidance / decode workspace
+  float* stash = nullptr;          // LSTM forward stash [2][T][max_rows][5*H]
+  float* ws_act = nullptr;         // [max_rows, T, 2]
+  float* ws_traj = nullptr;        // [max_rows, T, 6]
+  float* ws_dtraj = nullptr;       // [max_rows, T, 4]
+  float* ws_loss = nullptr;        // [3, max_rows]
+  float* ws_eps = nullptr;         // [max_rows, T, D]
+  float* ws_mean = nullptr;        // [max_rows, T, D]
+  float* ws_x = nullptr;           // [max_rows, T, D]
+  int64_t* ws_t = nullptr;         // [max_rows]
+  // debug tap
+  int dbg_stage = -1;
+  float* dbg_out = nullptr;
+  // bf16 tensor-core path (opaque, owned by unet_tc.cu)
+  void* tc = nullptr;
+};
+
+namespace cld {
+int fail(CldHandle* h, int code, const char* fmt, ...);
+#define CLD_CUDA_OK(h, expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return cld::fail(h, CLD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                       __FILE__, __LINE__);                                                    \
+  } while (0)
+#define CLD_LAUNCH_OK(h, name)                                                             \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return cld::fail(h, CLD_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- kernels_unet_fp32.cu
+int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps,
+                      int R, cudaStream_t s);
+int unet_stage_elems(const CldHandle* h, int stage);
+// ---- kernels_step.cu
+int posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise, uint64_t seed,
+                   uint64_t seq, int t, int t_next, int sampler, float* x_out, float* mean_out, int R,
+                   cudaStream_t s);
+int add_noise(CldHandle* h, const float* mean, const float* noise, uint64_t seed, uint64_t seq, int t,
+              float* x_out, int R, cudaStream_t s);
+int fill_t(CldHandle* h, int64_t* t, int value, int R, cudaStream_t s);
+// ---- kernels_decode.cu
+int decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr, float* act_out,
+                   float* traj_out, bool save, int R, cudaStream_t s);
+int unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, int R, cudaStream_t s);
+int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,
+               float* reward, int R, cudaStream_t s);
+// ---- kernels_guidance.cu
+int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g,
+                       float* dtraj, float* loss, int R, cudaStream_t s);
+int decode_backward_update(CldHandle* h, const float* z_mean, const float* act, const float* curr,
+                           const float* dtraj, const CldGuidanceConfig* g, float* z_out, float* grad_out,
+                           int R, cudaStream_t s);
+}  // namespace cld

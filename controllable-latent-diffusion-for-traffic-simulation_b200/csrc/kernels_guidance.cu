@@ -1,0 +1,588 @@
+// Guidance gradient with an ANALYTIC backward (replaces autograd through
+// PerturbationGuidance.perturb, reference src/tbsim/utils/guidance_loss.py:2221-2282):
+//   guidance_loss_grad      d(loss)/d(trajectory) of AgentCollisionLoss (:505-626), MapCollisionLoss (:772-870)
+//                           and TargetPosLoss (:693-712), one (scene, sample) per CTA, warp-shuffle reductions
+//                           over time / sample points; normalisation = "one scene per reference call"
+//                           (DiffuserGuidance.compute_guidance_loss :2143-2174).
+//   decode_backward_update  unicycle backward (reverse scans, clip masks) -> hid2act^T -> LSTM BPTT
+//                           (two layers, stash written by the forward kernel) -> dz, fused with the first
+//                           Adam / SGD step of perturb (:2250-2278).
+// All arithmetic fp32 (the update is sign-sensitive: SURVEY.md section 7, hard part 3).
+#include "common.cuh"
+
+namespace cld {
+
+__device__ __forceinline__ float clipg(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+struct LossArgs {
+  const float* traj;     // [R,T,6]
+  float* dtraj;          // [R,T,4]  d/d(x, y, v, yaw)
+  float* loss;           // [3,R] or nullptr
+  const float *extent, *wfa, *rfa, *speed, *target;
+  const uint8_t* dmap; int H, W;
+  int S, A, N, T, R;
+  float w_ac, w_mc, w_tp;
+  int D; float buffer, decay, speed_th, min_target_time;
+  int nl, nw;
+  float lwise[16], wwise[16];
+};
+
+// torch.linspace(lo, hi, n)[i] in fp32 (symmetric evaluation, as ATen does)
+__device__ __forceinline__ float linspace_at(float lo, float hi, int n, int i) {
+  if (n == 1) return lo;
+  float step = (hi - lo) / (float)(n - 1);
+  return (i < n / 2) ? lo + step * (float)i : hi - step * (float)(n - 1 - i);
+}
+
+__global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int A = a.A, T = a.T, N = a.N;
+  float* pose = sm;                         // [A][T][4] world Px, Py, cos(Psi), sin(Psi)
+  float* agt = pose + (size_t)A * T * 4;    // [A][8]: rad, cmin, cmax, moving, R00, R01, R10, R11
+  float* wts = agt + A * 8;                 // [T] decay weights
+  const int s = blockIdx.x / N, n = blockIdx.x % N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ag0 = s * A;
+  const float inv_AN = 1.0f / (float)(A * N);
+
+  if (tid < A) {
+    const int g = ag0 + tid;
+    float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
+    float rad = Wd / 2.f;
+    float* q = agt + tid * 8;
+    q[0] = rad; q[1] = -(L / 2.f) + rad; q[2] = (L / 2.f) - rad;
+    q[3] = (fabsf(a.speed[g]) > a.speed_th) ? 1.f : 0.f;
+    q[4] = a.wfa[g * 9 + 0]; q[5] = a.wfa[g * 9 + 1]; q[6] = a.wfa[g * 9 + 3]; q[7] = a.wfa[g * 9 + 4];
+  }
+  if (tid == 0) {
+    // exp_weights = decay^t / sum (guidance_loss.py:607-608)
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) { float w = powf(a.decay, (float)t); wts[t] = w; sum += w; }
+    for (int t = 0; t < T; ++t) wts[t] /= sum;
+  }
+  for (int it = tid; it < A * T; it += 256) {
+    int i = it / T, t = it - i * T, g = ag0 + i;
+    const float* tr = a.traj + (((size_t)g * N + n) * T + t) * 6;
+    float px = tr[0], py = tr[1], psi = tr[3];
+    const float* M = a.wfa + (size_t)g * 9;
+    // transform_agents_to_world (geometry_utils.py:458-483)
+    float Px = M[0] * px + M[1] * py + M[2], Py = M[3] * px + M[4] * py + M[5];
+    float c = cosf(psi), sn = sinf(psi);
+    float hx = M[0] * c + M[1] * sn, hy = M[3] * c + M[4] * sn;
+    float Psi = atan2f(hy, hx);
+    float* p = pose + (size_t)it * 4;
+    p[0] = Px; p[1] = Py; p[2] = cosf(Psi); p[3] = sinf(Psi);
+  }
+  __syncthreads();
+
+  // ---------------- agent-agent collision: warp per agent, lanes over time ---------------------
+  for (int i = warp; i < A; i += 8) {
+    const int g = ag0 + i;
+    const size_t row = (size_t)g * N + n;
+    const float* qi = agt + i * 8;
+    const float rad_i = qi[0], mov_i = qi[3];
+    float loss_i = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      float gPx = 0.f, gPy = 0.f, gPsi = 0.f, pen_sum = 0.f;
+      if (a.w_ac != 0.f) {
+        const float* pi = pose + ((size_t)i * T + t) * 4;
+        const float Pix = pi[0], Piy = pi[1], ci = pi[2], si = pi[3];
+        for (int j = 0; j < A; ++j) {
+          if (j == i) continue;
+          const float* qj = agt + j * 8;
+          const float* pj = pose + ((size_t)j * T + t) * 4;
+          float best = 3.4e38f, bdx = 0.f, bdy = 0.f, bxi = 0.f;
+          for (int d = 0; d < a.D; ++d) {
+            float xi = linspace_at(qi[1], qi[2], a.D, d);
+            float cx = Pix + xi * ci, cy = Piy + xi * si;
+            for (int e = 0; e < a.D; ++e) {
+              float xj = linspace_at(qj[1], qj[2], a.D, e);
+              float dx = cx - (pj[0] + xj * pj[2]), dy = cy - (pj[1] + xj * pj[3]);
+              float dist = sqrtf(dx * dx + dy * dy);
+              if (dist < best) { best = dist; bdx = dx; bdy = dy; bxi = xi; }
+            }
+          }
+          float pd = rad_i + qj[0] + a.buffer;
+          if (best <= pd) {
+            pen_sum += 1.0f - best / pd;
+            if (mov_i != 0.f && best > 0.f) {
+              // pair (i,j) is in l_i; pair (j,i) is in l_j when j moves (guidance_loss.py:617-620)
+              float f = (1.0f + qj[3]) / (best * pd);
+              float gx = -bdx * f, gy = -bdy * f;
+              gPx += gx; gPy += gy; gPsi += bxi * (-si * gx + ci * gy);
+            }
+          }
+        }
+      }
+      const float wt = wts[t];
+      float kk = a.w_ac * inv_AN * (1.0f / (float)A) * wt;
+      gPx *= kk; gPy *= kk; gPsi *= kk;
+      // back to the agent frame: p = R^T P ; dPsi/dpsi through atan2(R [cos, sin])
+      const float* tr = a.traj + ((size_t)row * T + t) * 6;
+      float psi = tr[3], c = cosf(psi), sn = sinf(psi);
+      float hx = qi[4] * c + qi[5] * sn, hy = qi[6] * c + qi[7] * sn;
+      float dhx = -qi[4] * sn + qi[5] * c, dhy = -qi[6] * sn + qi[7] * c;
+      float dPsi_dpsi = (hx * dhy - hy * dhx) / (hx * hx + hy * hy);
+      float* o = a.dtraj + ((size_t)row * T + t) * 4;
+      o[0] = qi[4] * gPx + qi[6] * gPy;
+      o[1] = qi[5] * gPx + qi[7] * gPy;
+      o[2] = 0.f;
+      o[3] = gPsi * dPsi_dpsi;
+      loss_i += wt * pen_sum;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) loss_i += __shfl_xor_sync(0xffffffffu, loss_i, o);
+    if (lane == 0 && a.loss) a.loss[row] = (mov_i != 0.f) ? loss_i / (float)A : 0.f;
+  }
+  __syncthreads();
+
+  // ---------------- map collision: warp per (agent, step), lanes over the sample points ----------
+  if (a.w_mc != 0.f) {
+    const int P = a.nl * a.nw;
+    for (int i = warp; i < A; i += 8) {
+      const int g = ag0 + i;
+      const size_t row = (size_t)g * N + n;
+      const float mov_i = agt[i * 8 + 3];
+      const float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
+      const float diag = sqrtf(L * L + Wd * Wd);
+      const float* M = a.rfa + (size_t)g * 9;
+      const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
+      float loss_i = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float* tr = a.traj + ((size_t)row * T + t) * 6;
+        const float px = tr[0], py = tr[1], psi = tr[3];
+        const float c = cosf(psi), sn = sinf(psi);
+        uint32_t offm[4] = {0u, 0u, 0u, 0u};
+        int n_off = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int p = lane + 32 * q;
+          bool off = false;
+          if (p < P) {
+            float lx = a.lwise[p / a.nw] * L, ly = a.wwise[p % a.nw] * Wd;
+            float qx = lx * c - ly * sn + px, qy = lx * sn + ly * c + py;
+            float rx = M[0] * qx + M[1] * qy + M[2], ry = M[3] * qx + M[4] * qy + M[5];
+            long long cx = (long long)rx, cy = (long long)ry;      // .long(): truncation (guidance_loss.py:796)
+            cx = cx < 0 ? 0 : (cx > a.W - 1 ? a.W - 1 : cx);
+            cy = cy < 0 ? 0 : (cy > a.H - 1 ? a.H - 1 : cy);
+            off = dm[cy * a.W + cx] == 0;
+          }
+          offm[q] = __ballot_sync(0xffffffffu, off);
+          n_off += __popc(offm[q]);
+        }
+        float gx = 0.f, gy = 0.f, gpsi = 0.f, lsum = 0.f;
+        if (n_off > 0 && n_off < P && mov_i != 0.f) {
+          for (int q = 0; q < 4; ++q) {
+            int p = lane + 32 * q;
+            if (p >= P || !((offm[q] >> lane) & 1u)) continue;
+            float plx = a.lwise[p / a.nw] * L, ply = a.wwise[p % a.nw] * Wd;
+            float pxw = plx * c - ply * sn + px, pyw = plx * sn + ply * c + py;
+            float best = 3.4e38f;
+            int cnt = 0;
+            for (int k = 0; k < P; ++k) {
+              if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
+              float lx = a.lwise[k / a.nw] * L, ly = a.wwise[k % a.nw] * Wd;
+              float dx = (lx * c - ly * sn + px) - pxw, dy = (lx * sn + ly * c + py) - pyw;
+              float dist = sqrtf(dx * dx + dy * dy);
+              if (dist < best) { best = dist; cnt = 1; } else if (dist == best) { ++cnt; }
+            }
+            lsum += 1.0f - best / diag;
+            if (best > 0.f) {
+              // torch.amin splits the gradient evenly over tied minima
+              float f = -1.0f / (best * diag * (float)cnt);
+              for (int k = 0; k < P; ++k) {
+                if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
+                float lx = a.lwise[k / a.nw] * L, ly = a.wwise[k % a.nw] * Wd;
+                float dx = (lx * c - ly * sn + px) - pxw, dy = (lx * sn + ly * c + py) - pyw;
+                float dist = sqrtf(dx * dx + dy * dy);
+                if (dist == best) {
+                  float ggx = dx * f, ggy = dy * f;
+                  gx += ggx; gy += ggy;
+                  gpsi += ggx * (-lx * sn - ly * c) + ggy * (lx * c - ly * sn);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          gx += __shfl_xor_sync(0xffffffffu, gx, o);
+          gy += __shfl_xor_sync(0xffffffffu, gy, o);
+          gpsi += __shfl_xor_sync(0xffffffffu, gpsi, o);
+          lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        }
+        if (lane == 0) {
+          float kk = a.w_mc * inv_AN * wts[t];
+          float* o = a.dtraj + ((size_t)row * T + t) * 4;
+          o[0] += kk * gx; o[1] += kk * gy; o[3] += kk * gpsi;
+          loss_i += wts[t] * lsum;
+        }
+      }
+      if (lane == 0 && a.loss) a.loss[(size_t)a.R + row] = loss_i;
+    }
+  } else if (a.loss) {
+    for (int i = tid; i < A; i += 256) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
+  }
+
+  // ---------------- target position (softmin-weighted squared distance): warp per agent ------------
+  if (a.w_tp != 0.f && a.target) {
+    const int t0 = (int)(a.min_target_time * (float)T);
+    const int Tn = T - t0;
+    for (int i = warp; i < A; i += 8) {
+      const int g = ag0 + i;
+      const size_t row = (size_t)g * N + n;
+      const float tx = a.target[g * 2 + 0], ty = a.target[g * 2 + 1];
+      // stationary agents were detached in place by the agent-collision term (guidance_loss.py:511-515)
+      const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);
+      const float* tr = a.traj + (size_t)row * T * 6;
+      float dmin = 3.4e38f;
+      for (int t = t0 + lane; t < T; t += 32) {
+        float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+        dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+      float Z = 0.f, E = 0.f;
+      for (int t = t0 + lane; t < T; t += 32) {
+        float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+        float d2 = dx * dx + dy * dy, d = sqrtf(d2);
+        float e = expf(-(d - dmin));
+        Z += e; E += e * d2;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        Z += __shfl_xor_sync(0xffffffffu, Z, o);
+        E += __shfl_xor_sync(0xffffffffu, E, o);
+      }
+      E /= Z;
+      if (lane == 0 && a.loss) a.loss[2 * (size_t)a.R + row] = E / (float)Tn;
+      if (has_grad) {
+        float kk = a.w_tp * inv_AN / (float)Tn;
+        for (int t = t0 + lane; t < T; t += 32) {
+          float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+          float d2 = dx * dx + dy * dy, d = sqrtf(d2);
+          float sw = expf(-(d - dmin)) / Z;
+          float f = 2.f * sw + ((d > 0.f) ? sw * (E - d2) / d : 0.f);
+          float* o = a.dtraj + ((size_t)row * T + t) * 4;
+          o[0] += kk * f * dx; o[1] += kk * f * dy;
+        }
+      }
+    }
+  } else if (a.loss) {
+    for (int i = tid; i < A; i += 256) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
+  }
+}
+
+static float host_linspace(float lo, float hi, int n, int i) {
+  if (n == 1) return lo;
+  float step = (hi - lo) / (float)(n - 1);
+  return (i < n / 2) ? lo + step * (float)i : hi - step * (float)(n - 1 - i);
+}
+
+int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g, float* dtraj,
+                       float* loss, int R, cudaStream_t s) {
+  if (!sc || !g) return fail(h, CLD_ERR_ARG, "scene / guidance config missing");
+  const int S = sc->num_scenes, A = sc->agents_per_scene, N = sc->num_samp, T = h->cfg.horizon;
+  if (R != S * A * N) return fail(h, CLD_ERR_ARG, "R=%d does not match S*A*N=%d*%d*%d", R, S, A, N);
+  if (A < 1 || A > 64) return fail(h, CLD_ERR_UNSUPPORTED, "agents_per_scene must be in [1,64]");
+  if (g->num_disks < 1 || g->num_disks > 5) return fail(h, CLD_ERR_UNSUPPORTED, "num_disks must be in [1,5]");
+  if (g->num_points_l < 1 || g->num_points_l > 16 || g->num_points_w < 1 || g->num_points_w > 16 ||
+      g->num_points_l * g->num_points_w > 128)
+    return fail(h, CLD_ERR_UNSUPPORTED, "num_points_lw must be <=16 each and <=128 points in total");
+  if (!sc->extent || !sc->world_from_agent || !sc->curr_speed) return fail(h, CLD_ERR_ARG, "scene tensors missing");
+  if (g->w_map_collision != 0.f && (!sc->drivable_map || !sc->raster_from_agent))
+    return fail(h, CLD_ERR_ARG, "map_collision needs drivable_map and raster_from_agent");
+  LossArgs a;
+  a.traj = traj; a.dtraj = dtraj; a.loss = loss;
+  a.extent = sc->extent; a.wfa = sc->world_from_agent; a.rfa = sc->raster_from_agent; a.speed = sc->curr_speed;
+  a.target = sc->target_pos; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w;
+  a.S = S; a.A = A; a.N = N; a.T = T; a.R = R;
+  a.w_ac = g->w_agent_collision; a.w_mc = g->w_map_collision; a.w_tp = g->w_target_pos;
+  a.D = g->num_disks; a.buffer = g->buffer_dist; a.decay = g->decay_rate; a.speed_th = g->speed_th;
+  a.min_target_time = g->min_target_time; a.nl = g->num_points_l; a.nw = g->num_points_w;
+  for (int i = 0; i < 16; ++i) {
+    a.lwise[i] = i < a.nl ? host_linspace(-0.5f, 0.5f, a.nl, i) : 0.f;
+    a.wwise[i] = i < a.nw ? host_linspace(-0.5f, 0.5f, a.nw, i) : 0.f;
+  }
+  size_t smem = ((size_t)A * T * 4 + (size_t)A * 8 + T) * sizeof(float);
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(guidance_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  guidance_loss_grad_kernel<<<S * N, 256, smem, s>>>(a);
+  CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: d(traj) -> d(scaled actions) -> BPTT -> dz -> optimizer step
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float *z_mean, *act, *curr, *dtraj, *stash;
+  const float *wih0, *whh0, *wih1, *whh1, *h2a_w;   // original [4H][in] layouts
+  float *z_out, *grad_out;
+  int R, T;
+  float dt, acce_lo, acce_hi, v_lo, v_hi, max_steer, max_yawvel, a_mean, a_std, w_mean, w_std;
+  int optimizer; float lr;
+};
+
+// reverse of unicycle_row for one row; writes d(scaled action) [T][2]
+__device__ void unicycle_row_backward(const float* act, const float* curr, const float* dtr, int T, const BwdArgs& a,
+                                      float* scr /*[4][T+1]*/, float* dact) {
+  float* sk = scr;                 // raw cumulative speed s_k, k=0..T
+  float* psik = scr + (T + 1);     // yaw psi_k, k=0..T
+  float* vbar = scr + 2 * (T + 1); // k=0..T-1
+  float* msk = scr + 3 * (T + 1);  // bit0: acc clip passes, bit1: yaw-rate clip passes
+  float s = curr[2], psi = curr[3];
+  float vprev = clipg(s, a.v_lo, a.v_hi);
+  sk[0] = s; psik[0] = psi;
+  for (int k = 0; k < T; ++k) {
+    float a_raw = __fadd_rn(__fmul_rn(act[k * 2 + 0], a.a_std), a.a_mean);
+    float w_raw = __fadd_rn(__fmul_rn(act[k * 2 + 1], a.w_std), a.w_mean);
+    float ac = clipg(a_raw, a.acce_lo, a.acce_hi);
+    s = __fadd_rn(s, __fmul_rn(ac, a.dt));
+    float vnext = clipg(s, a.v_lo, a.v_hi);
+    vbar[k] = __fmul_rn(0.5f, __fadd_rn(vprev, vnext));
+    float ve = fabsf(vprev);
+    float yb = fmaxf(fminf(__fmul_rn(a.max_steer, ve), __fdiv_rn(a.max_yawvel, fmaxf(ve, 0.1f))), 0.1f);
+    float w = clipg(w_raw, -yb, yb);
+    psi = __fadd_rn(psi, __fmul_rn(w, a.dt));
+    int m = ((a_raw >= a.acce_lo && a_raw <= a.acce_hi) ? 1 : 0) | ((w_raw >= -yb && w_raw <= yb) ? 2 : 0);
+    msk[k] = __int_as_float(m);
+    sk[k + 1] = s; psik[k + 1] = psi;
+    vprev = vnext;
+  }
+  float Gx = 0.f, Gy = 0.f, Spsi = 0.f, Ss = 0.f, dvbar_next = 0.f, direct_next = 0.f;
+  for (int m = T - 1; m >= 0; --m) {
+    const float gx = dtr[m * 4 + 0], gy = dtr[m * 4 + 1], gv = dtr[m * 4 + 2], gpsi = dtr[m * 4 + 3];
+    Gx += a.dt * gx; Gy += a.dt * gy;
+    float c = cosf(psik[m]), sn = sinf(psik[m]);
+    float dvbar = Gx * c + Gy * sn;
+    float direct = vbar[m] * (-Gx * sn + Gy * c);
+    Spsi += ((m + 1 <= T - 1) ? direct_next : 0.f) + gpsi;
+    float dvhat = 0.5f * (((m + 1 <= T - 1) ? dvbar_next : 0.f) + dvbar) + gv;
+    float s1 = sk[m + 1];
+    if (s1 >= a.v_lo && s1 <= a.v_hi) Ss += dvhat;
+    int mk = __float_as_int(msk[m]);
+    float du0 = (mk & 1) ? a.dt * Ss : 0.f;
+    float du1 = (mk & 2) ? a.dt * Spsi : 0.f;
+    dact[m * 2 + 0] = a.a_std * du0;
+    dact[m * 2 + 1] = a.w_std * du1;
+    dvbar_next = dvbar; direct_next = direct;
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(256, 1) lstm_backward_update_kernel(BwdArgs a) {
+  constexpr int H = 64, PPT = RB * H / 256;
+  extern __shared__ __align__(16) float sm[];
+  const int T = a.T, R = a.R;
+  float* acts = sm;                                  // [RB][T][2]
+  float* dtr = acts + RB * T * 2;                    // [RB][T][4]
+  float* dact = dtr + RB * T * 4;                    // [RB][T][2]
+  float* scr = dact + RB * T * 2;                    // [RB][4][T+1]
+  float* dh0seq = scr + RB * 4 * (T + 1);            // [T][RB][H]
+  float* dzb = dh0seq + (size_t)T * RB * H;          // [RB][256] gate pre-activation grads
+  float* part = dzb + RB * 256;                      // [4][RB][H] partial transposed mat-vecs
+  float* dhrec = part + 4 * RB * H;                  // [RB][H]
+  float* dzout = dhrec + RB * H;                     // [RB][T][4]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row0 = blockIdx.x * RB;
+
+  for (int i = tid; i < RB * T * 2; i += 256) {
+    int b = i / (T * 2);
+    acts[i] = (row0 + b < R) ? a.act[(size_t)row0 * T * 2 + i] : 0.f;
+  }
+  for (int i = tid; i < RB * T * 4; i += 256) {
+    int b = i / (T * 4);
+    dtr[i] = (row0 + b < R) ? a.dtraj[(size_t)row0 * T * 4 + i] : 0.f;
+  }
+  __syncthreads();
+  if (tid < RB) {
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row0 + tid < R)
+      for (int i = 0; i < 4; ++i) cs[i] = a.curr[(size_t)(row0 + tid) * 4 + i];
+    unicycle_row_backward(acts + tid * T * 2, cs, dtr + tid * T * 4, T, a, scr + tid * 4 * (T + 1), dact + tid * T * 2);
+  }
+  for (int p = tid; p < RB * H; p += 256) dhrec[p] = 0.f;
+  __syncthreads();
+
+  // ------------------------------ layer 1 (top) -------------------------------------------------
+  {
+    const int which = tid >> 7, jh = (tid >> 6) & 1, k = tid & 63;
+    const float* Wsrc = which ? a.wih1 : a.whh1;
+    float w[128];
+#pragma unroll
+    for (int jj = 0; jj < 128; ++jj) w[jj] = Wsrc[(size_t)(jh * 128 + jj) * H + k];
+    float dcrec[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) dcrec[i] = 0.f;
+    const float* st1 = a.stash + (size_t)T * R * 5 * H;
+    for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        int p = tid + i * 256, b = p >> 6, u = p & 63;
+        float dz_i = 0.f, dz_f = 0.f, dz_g = 0.f, dz_o = 0.f;
+        if (row0 + b < R) {
+          const float* st = st1 + ((size_t)t * R + row0 + b) * (5 * H) + u;
+          float ig = st[0], fg = st[H], gg = st[2 * H], og = st[3 * H], c = st[4 * H];
+          float cprev = (t > 0) ? *(st + 4 * H - (ptrdiff_t)R * 5 * H) : 0.f;
+          float dh = a.h2a_w[u] * dact[(b * T + t) * 2] + a.h2a_w[H + u] * dact[(b * T + t) * 2 + 1] + dhrec[b * H + u];
+          float tc = tanhf(c);
+          float dc = dcrec[i] + dh * og * (1.f - tc * tc);
+          dz_i = dc * gg * ig * (1.f - ig);
+          dz_f = dc * cprev * fg * (1.f - fg);
+          dz_g = dc * ig * (1.f - gg * gg);
+          dz_o = dh * tc * og * (1.f - og);
+          dcrec[i] = dc * fg;
+        }
+        float* d = dzb + b * 256 + u;
+        d[0] = dz_i; d[64] = dz_f; d[128] = dz_g; d[192] = dz_o;
+      }
+      __syncthreads();
+      float acc[RB];
+#pragma unroll
+      for (int b = 0; b < RB; ++b) acc[b] = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; ++j4) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          float4 dv = *reinterpret_cast<const float4*>(dzb + b * 256 + jh * 128 + j4 * 4);
+          acc[b] = fmaf(w[j4 * 4 + 0], dv.x, acc[b]); acc[b] = fmaf(w[j4 * 4 + 1], dv.y, acc[b]);
+          acc[b] = fmaf(w[j4 * 4 + 2], dv.z, acc[b]); acc[b] = fmaf(w[j4 * 4 + 3], dv.w, acc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < RB; ++b) part[((which * 2 + jh) * RB + b) * H + k] = acc[b];
+      __syncthreads();
+      for (int p = tid; p < RB * H; p += 256) {
+        dhrec[p] = part[p] + part[RB * H + p];
+        dh0seq[(size_t)t * RB * H + p] = part[2 * RB * H + p] + part[3 * RB * H + p];
+      }
+      __syncthreads();
+    }
+  }
+  // ------------------------------ layer 0 --------------------------------------------------------
+  {
+    for (int p = tid; p < RB * H; p += 256) dhrec[p] = 0.f;
+    __syncthreads();
+    const int jq = tid >> 6, k = tid & 63;
+    float w[64];
+#pragma unroll
+    for (int jj = 0; jj < 64; ++jj) w[jj] = a.whh0[(size_t)(jq * 64 + jj) * H + k];
+    float4 wi[8];   // weight_ih_l0 rows j = lane*8 .. lane*8+7 (for dz = W_ih^T dgates)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) wi[jj] = *reinterpret_cast<const float4*>(a.wih0 + (size_t)(lane * 8 + jj) * 4);
+    float dcrec[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) dcrec[i] = 0.f;
+    const float* st0 = a.stash;
+    for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        int p = tid + i * 256, b = p >> 6, u = p & 63;
+        float dz_i = 0.f, dz_f = 0.f, dz_g = 0.f, dz_o = 0.f;
+        if (row0 + b < R) {
+          const float* st = st0 + ((size_t)t * R + row0 + b) * (5 * H) + u;
+          float ig = st[0], fg = st[H], gg = st[2 * H], og = st[3 * H], c = st[4 * H];
+          float cprev = (t > 0) ? *(st + 4 * H - (ptrdiff_t)R * 5 * H) : 0.f;
+          float dh = dh0seq[(size_t)t * RB * H + p] + dhrec[p];
+          float tc = tanhf(c);
+          float dc = dcrec[i] + dh * og * (1.f - tc * tc);
+          dz_i = dc * gg * ig * (1.f - ig);
+          dz_f = dc * cprev * fg * (1.f - fg);
+          dz_g = dc * ig * (1.f - gg * gg);
+          dz_o = dh * tc * og * (1.f - og);
+          dcrec[i] = dc * fg;
+        }
+        float* d = dzb + b * 256 + u;
+        d[0] = dz_i; d[64] = dz_f; d[128] = dz_g; d[192] = dz_o;
+      }
+      __syncthreads();
+      float acc[RB];
+#pragma unroll
+      for (int b = 0; b < RB; ++b) acc[b] = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          float4 dv = *reinterpret_cast<const float4*>(dzb + b * 256 + jq * 64 + j4 * 4);
+          acc[b] = fmaf(w[j4 * 4 + 0], dv.x, acc[b]); acc[b] = fmaf(w[j4 * 4 + 1], dv.y, acc[b]);
+          acc[b] = fmaf(w[j4 * 4 + 2], dv.z, acc[b]); acc[b] = fmaf(w[j4 * 4 + 3], dv.w, acc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < RB; ++b) part[(jq * RB + b) * H + k] = acc[b];
+      // dz_t = W_ih_l0^T dgates : warp b handles row b (RB <= 8 warps)
+      if (warp < RB) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float dv = dzb[warp * 256 + lane * 8 + jj];
+          s4.x = fmaf(wi[jj].x, dv, s4.x); s4.y = fmaf(wi[jj].y, dv, s4.y);
+          s4.z = fmaf(wi[jj].z, dv, s4.z); s4.w = fmaf(wi[jj].w, dv, s4.w);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+          s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+        }
+        if (lane == 0) *reinterpret_cast<float4*>(dzout + (warp * T + t) * 4) = s4;
+      }
+      __syncthreads();
+      for (int p = tid; p < RB * H; p += 256)
+        dhrec[p] = part[p] + part[RB * H + p] + part[2 * RB * H + p] + part[3 * RB * H + p];
+      __syncthreads();
+    }
+  }
+  // ------------------------------ optimizer step (guidance_loss.py:2250-2278) --------------------
+  for (int i = tid; i < RB * T * 4; i += 256) {
+    int b = i / (T * 4);
+    if (row0 + b >= R) continue;
+    size_t gi = (size_t)row0 * T * 4 + i;
+    float g = dzout[i], z = a.z_mean[gi], zn;
+    if (a.optimizer == CLD_OPT_ADAM) {
+      // first torch.optim.Adam step: m = 0.1 g, v = 0.001 g^2, bias corrections 0.1 / 0.001, eps 1e-8
+      float m = 0.1f * g;
+      float v = (0.001f * g) * g;
+      float denom = sqrtf(v) / 0.03162277660168379f + 1e-8f;
+      float step = a.lr / 0.1f;
+      zn = z - step * (m / denom);
+    } else {
+      zn = z - a.lr * g;
+    }
+    a.z_out[gi] = zn;
+    if (a.grad_out) a.grad_out[gi] = g;
+  }
+}
+
+template <int RB>
+static size_t bwd_smem_bytes(int T) {
+  size_t f = (size_t)RB * T * 2 + (size_t)RB * T * 4 + (size_t)RB * T * 2 + (size_t)RB * 4 * (T + 1) +
+             (size_t)T * RB * 64 + (size_t)RB * 256 + 4 * (size_t)RB * 64 + (size_t)RB * 64 + (size_t)RB * T * 4;
+  return f * sizeof(float);
+}
+
+template <int RB>
+static int launch_bwd(CldHandle* h, const BwdArgs& a, cudaStream_t s) {
+  size_t smem = bwd_smem_bytes<RB>(a.T);
+  auto kern = lstm_backward_update_kernel<RB>;
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(a.R + RB - 1) / RB, 256, smem, s>>>(a);
+  CLD_LAUNCH_OK(h, "lstm_backward_update_kernel");
+  return 0;
+}
+
+int decode_backward_update(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
+                           const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+  const CldConfig& c = h->cfg;
+  BwdArgs a;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash;
+  a.wih0 = h->dec.wih0_raw; a.whh0 = h->dec.whh0_raw; a.wih1 = h->dec.wih1_raw; a.whh1 = h->dec.whh1_raw;
+  a.h2a_w = h->dec.h2a_w;
+  a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = c.horizon;
+  a.dt = c.dt; a.acce_lo = c.acce_lo; a.acce_hi = c.acce_hi; a.v_lo = c.v_lo; a.v_hi = c.v_hi;
+  a.max_steer = c.max_steer; a.max_yawvel = c.max_yawvel;
+  a.a_mean = c.norm_mean[4]; a.a_std = c.norm_std[4]; a.w_mean = c.norm_mean[5]; a.w_std = c.norm_std[5];
+  a.optimizer = g->optimizer; a.lr = g->lr;
+  if (a.T <= 64) return launch_bwd<8>(h, a, s);
+  return launch_bwd<4>(h, a, s);
+}
+
+}  // namespace cld

@@ -1,0 +1,192 @@
+/*
+ * cld_b200.h -- C ABI of libcld_b200.so: the B200 (sm_100a) implementation of CLD's guided
+ * latent-diffusion SAMPLING path.
+ *
+ * The reference (RoboSafe-Lab/Controllable-Latent-Diffusion-for-Traffic-Simulation) is pure
+ * Python/PyTorch and has no FFI; each entry point below names the reference function it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add to models/dm/dm_model.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()), contiguous, fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, no
+ *     implicit synchronisation, no allocation in the step path (CUDA-graph capturable);
+ *   - return 0 on success, a negative CldStatus otherwise; cld_last_error() gives the message;
+ *   - a handle belongs to one device and is not thread-safe;
+ *   - there is NO CPU fallback and no other-architecture dispatch: cld_create fails on a device
+ *     that is not compute capability 10.x.
+ *   - row layout: R = S*A*N rows, row = (scene*A + agent)*N + sample  (the reference's
+ *     TensorUtils.join_dimensions of [B,N,...], models/dm/dm_model.py:110).
+ */
+#ifndef CLD_B200_H_
+#define CLD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CldHandle CldHandle;
+
+typedef enum {
+  CLD_OK = 0,
+  CLD_ERR_ARG = -1,        /* bad argument / shape */
+  CLD_ERR_ARCH = -2,       /* device is not sm_100 */
+  CLD_ERR_CUDA = -3,       /* CUDA runtime error (message in cld_last_error) */
+  CLD_ERR_STATE = -4,      /* weights / schedule not loaded */
+  CLD_ERR_UNSUPPORTED = -5 /* configuration outside what the kernels implement */
+} CldStatus;
+
+enum { CLD_PREC_FP32 = 0, CLD_PREC_BF16 = 1 };   /* denoiser arithmetic: fp32 SIMT | bf16 tcgen05 */
+enum { CLD_SAMPLER_DDPM = 0, CLD_SAMPLER_DDIM = 1 };
+enum { CLD_OPT_ADAM = 0, CLD_OPT_SGD = 1 };
+
+/* Mirrors the algo_config keys the reference's hot path reads (SURVEY.md sec. 5 "Config/flags"). */
+typedef struct {
+  int32_t horizon;          /* algo.horizon (T, multiple of 4)                                   */
+  int32_t latent_dim;       /* algo.vae.latent_size (4)                                          */
+  int32_t cond_dim;         /* algo.cond_feat_dim (256)                                          */
+  int32_t base_dim;         /* algo.base_dim (32): time-embedding width                          */
+  int32_t dims[3];          /* base_dim * dim_mults = (64,128,256)                               */
+  int32_t hidden;           /* algo.vae.hidden_size (64)                                         */
+  int32_t n_timesteps;      /* DmModel(n_timesteps)                                              */
+  int32_t max_rows;         /* workspace is sized for this many rows per call                    */
+  int32_t precision;        /* CLD_PREC_*                                                        */
+  float dt;                 /* algo.step_time (0.1)                                              */
+  float acce_lo, acce_hi;   /* algo.dynamics.acce_bound                                          */
+  float v_lo, v_hi;         /* Unicycle.vbound default [-10,30] (src/tbsim/dynamics/unicycle.py:9) */
+  float max_steer;          /* algo.dynamics.max_steer                                           */
+  float max_yawvel;         /* algo.dynamics.max_yawvel                                          */
+  float norm_mean[6];       /* algo.nusc_norm_info.diffuser[0]                                   */
+  float norm_std[6];        /* algo.nusc_norm_info.diffuser[1]                                   */
+} CldConfig;
+
+/* Guidance terms (src/tbsim/utils/guidance_loss.py; defaults src/tbsim/configs/scene_edit_config.py:73-92,302-325). */
+typedef struct {
+  float w_agent_collision;  /* 50.0 ; 0 disables the term                                        */
+  float w_map_collision;    /* 1.0                                                               */
+  float w_target_pos;       /* 0.0                                                               */
+  int32_t num_disks;        /* 2  (<= 5)                                                         */
+  float buffer_dist;        /* 0.2                                                               */
+  float decay_rate;         /* 0.9                                                               */
+  int32_t num_points_l;     /* 10                                                                */
+  int32_t num_points_w;     /* 10                                                                */
+  float speed_th;           /* 0.5 (guide_moving_speed_th)                                       */
+  float min_target_time;    /* 0.0                                                               */
+  int32_t optimizer;        /* CLD_OPT_ADAM                                                      */
+  float lr;                 /* 0.3                                                               */
+} CldGuidanceConfig;
+
+/* Per-agent scene tensors (the reference's data_batch entries), B = S*A agent rows, scene-major. */
+typedef struct {
+  int32_t num_scenes;               /* S */
+  int32_t agents_per_scene;         /* A (<= 64) */
+  int32_t num_samp;                 /* N */
+  const float* extent;              /* [B,3]  data_batch['extent']                               */
+  const float* world_from_agent;    /* [B,3,3]                                                   */
+  const float* raster_from_agent;   /* [B,3,3]                                                   */
+  const float* curr_speed;          /* [B]                                                       */
+  const uint8_t* drivable_map;      /* [B,H,W] bool as bytes                                     */
+  int32_t map_h, map_w;
+  const float* target_pos;          /* [B,2] or NULL                                             */
+  const float* others_pos;          /* [B,So,T,2] all_other_agents_future_positions or NULL      */
+  const uint8_t* others_avail;      /* [B,So,T]   all_other_agents_future_availability or NULL   */
+  int32_t num_others;               /* So */
+} CldScene;
+
+int cld_version(void);
+int cld_create(const CldConfig* cfg, CldHandle** out);
+void cld_destroy(CldHandle* h);
+const char* cld_last_error(const CldHandle* h);   /* h may be NULL: last create() error */
+
+/* Denoiser weights: the 148 tensors of DmModel.model.state_dict() in state-dict order
+ * (SURVEY.md sec. 8b), fp32 device pointers; numels[i] (optional, may be NULL) is checked against
+ * the element count the layout expects.  Packs them into the kernels' layouts.
+ * Replaces: TemporalMapUnet.__init__/load_state_dict (src/tbsim/models/temporal.py:49-120). */
+int cld_load_unet(CldHandle* h, const float* const* dev_ptrs, const int64_t* numels, int n, void* stream);
+
+/* LSTM decoder weights, fp32 device pointers in this order:
+ * lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
+ * lstm.weight_ih_l1, lstm.weight_hh_l1, lstm.bias_ih_l1, lstm.bias_hh_l1,
+ * cond2hidden.weight, cond2hidden.bias, hid2act.weight, hid2act.bias
+ * Replaces: Decoder.__init__ (models/vae/lstm_vae.py:28-43). */
+int cld_load_decoder(CldHandle* h, const float* const* dev_ptrs, int n, void* stream);
+
+/* Schedule buffers (HOST fp32 arrays of length n_timesteps), computed by the caller exactly as the
+ * reference registers them (models/dm/dm_model.py:29-56). */
+int cld_set_schedule(CldHandle* h, const float* x_t_cof, const float* noise_cof,
+                     const float* posterior_log_variance_clipped,
+                     const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                     const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
+                     int n);
+
+/* eps = TemporalMapUnet.forward(x, {'cond_feat': cond}, t)   (src/tbsim/models/temporal.py:122-180)
+ * x [R,T,D], cond [R,C], t [R] int64, eps_out [R,T,D]. */
+int cld_unet_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t,
+                     float* eps_out, int R, void* stream);
+
+/* Debug/verification hook: registers a tap; the NEXT cld_unet_forward calls copy the channels-last
+ * activation [R,T',C] produced by stage `stage_index` (0..16: downs.0.0, downs.0.1, downs.0.2, ...,
+ * mid_block1, mid_block2, ups.0.0, ..., ups.1.2, final_conv.0) into `out` (fp32).  out == NULL
+ * removes the tap.  Returns elements per row of that stage (negative on error). */
+int cld_unet_debug_stage(CldHandle* h, int stage_index, float* out, int R, void* stream);
+
+/* One posterior step (models/dm/dm_model.py:144-163):
+ *   DDPM: mean = x_t_cof[t]*x - noise_cof[t]*eps ; x' = mean + 1[t!=0]*exp(.5*logvar[t])*noise
+ *   DDIM (eta=0, t_next<0 means final): x0 = sqrt_recip[t]*x - sqrt_recipm1[t]*eps ;
+ *         x' = mean = sqrt_acp[t_next]*x0 + sqrt(1-acp[t_next])*eps
+ * noise may be NULL (treated as 0).  mean_out may be NULL.  x_out may alias x. */
+int cld_posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise,
+                       int t, int t_next, int sampler, float* x_out, float* mean_out, int R,
+                       void* stream);
+
+/* x' = mean + 1[t!=0]*sigma[t]*noise (the noise injection applied after guidance). */
+int cld_add_noise(CldHandle* h, const float* mean, const float* noise, int t, float* x_out, int R,
+                  void* stream);
+
+/* act = Decoder.forward(z, cond) (models/vae/lstm_vae.py:44-52) fused with
+ * VaeModel.convert_action_to_state_and_action(act, curr, descaled_output=True)
+ * (models/vae/vae_model.py:100-129; unicycle: src/tbsim/models/diffuser_helpers.py:573-639).
+ * z [R,T,4], cond [R,C], curr [R,4] -> act_out [R,T,2] scaled actions (may be NULL),
+ * traj_out [R,T,6] metric (x,y,v,yaw,acc,yawvel). */
+int cld_decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr,
+                       float* act_out, float* traj_out, int R, void* stream);
+
+/* Unicycle rollout alone (diffuser_helpers.py:573-639): u [R,T,2] metric actions -> [R,T,4]. */
+int cld_unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, int R,
+                 void* stream);
+
+/* failure_rate_compute / compute_reward indicators (models/rl/criticmodel.py:7-64,114-145).
+ * traj [R,T,6] metric, rows map to agents by row / num_samp.
+ * offroad_out [R,T] bytes (1 = off the drivable area), coll_out [R] fp32 collision counts,
+ * reward_out [R] fp32 (may be NULL). */
+int cld_indicators(CldHandle* h, const float* traj, const CldScene* scene, uint8_t* offroad_out,
+                   float* coll_out, float* reward_out, int R, void* stream);
+
+/* One guidance update of PerturbationGuidance.perturb (guidance_loss.py:2221-2282) with
+ * decoder = lstm_dec and transform = convert_action_to_state_and_action, one scene per reference
+ * call: z_out = z_mean - lr*g/(|g|+1e-8) (Adam step 1) or z_mean - lr*g (SGD), g = dL/dz by an
+ * analytic backward.  cond/curr are per ROW ([R,C], [R,4]).  grad_out [R,T,4] and
+ * loss_out [3,R] (agent_collision, map_collision, target_pos per row) may be NULL. */
+int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr,
+                      const CldScene* scene, const CldGuidanceConfig* g, float* z_out,
+                      float* grad_out, float* loss_out, int R, void* stream);
+
+/* Whole sampler: DmModel.sample_traj (models/dm/dm_model.py:103-142) + optional guidance
+ * (template src/tbsim/models/diffuser.py:843-929) + decode/rollout + indicators.
+ *   x_init [R,T,D]; noises [K,R,T,D] or NULL with seed!=0 for in-kernel Philox noise;
+ *   cond [R,C], curr [R,4] per row; scene/g may be NULL (unguided, no indicators).
+ * Outputs (any may be NULL): x0 [R,T,D], x1 [R,T,D] (written only if step index 1 is visited;
+ * *x1_valid says so), traj [R,T,6], offroad [R,T], coll [R]. */
+int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t seed,
+               const float* cond, const float* curr, const CldScene* scene,
+               const CldGuidanceConfig* g, int stride, int sampler, float* x0_out, float* x1_out,
+               int* x1_valid, float* traj_out, uint8_t* offroad_out, float* coll_out, int R,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLD_B200_H_ */

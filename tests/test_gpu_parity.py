@@ -1,0 +1,299 @@
+"""GPU (-m gpu): the CUDA path (through the C ABI) against the reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cld_oracle as O
+from cld_b200.synthetic import make_scenes
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4          # north_star: denoiser outputs and trajectories within 1e-4 relative under fp32
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def gpu_models(models_cpu):
+    cache = {}
+
+    def build(n):
+        if n not in cache:
+            dm, vae, algo = models_cpu(n)
+            dm = dm.cuda()
+            vae.bind(dm)
+            cache[n] = (dm, vae, algo)
+        return cache[n]
+    return build
+
+
+def cpu_sd(m):
+    return {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+def test_library_loaded_and_arch():
+    from cld_b200 import _lib
+    assert _lib.lib.cld_version() == 100
+    assert torch.cuda.get_device_capability()[0] == 10
+
+
+def test_unet_fp32_vs_reference_golden(gpu_models, gold):
+    g = gold("unet")
+    dm, _, _ = gpu_models(10)
+    eps = dm.denoise(torch.tensor(g["x"]).cuda(), {"cond_feat": torch.tensor(g["cond"]).cuda()}, torch.tensor(g["t"]).cuda())
+    assert rel(eps, g["eps"]) < FP32_TOL
+    assert rel(eps, g["eps"]) < 2e-5
+
+
+def test_unet_fp32_every_stage_vs_oracle(gpu_models, gold):
+    g = gold("unet")
+    dm, _, _ = gpu_models(10)
+    x, cond, t = torch.tensor(g["x"]), torch.tensor(g["cond"]), torch.tensor(g["t"])
+    taps = {}
+    with torch.no_grad():
+        O.unet_forward(cpu_sd(dm.model), x, cond, t, taps=taps)
+    names = ["downs.0.0", "downs.0.1", "downs.0.2", "downs.1.0", "downs.1.1", "downs.1.2", "downs.2.0", "downs.2.1",
+             "mid_block1", "mid_block2", "ups.0.0", "ups.0.1", "ups.0.2", "ups.1.0", "ups.1.1", "ups.1.2", "final_conv.0"]
+    eng = dm.engine(x.shape[0])
+    for i, nm in enumerate(names):
+        _, dbg = eng.unet_forward(x.cuda(), cond.cuda(), t.cuda(), debug_stage=i)
+        want = taps[nm].reshape(x.shape[0], -1)
+        assert dbg.shape == want.shape, nm
+        assert rel(dbg, want) < 2e-5, nm
+
+
+def test_unet_fp32_ragged_rows_and_T104(models_cpu, gold):
+    # R not a multiple of any tile, and the long-horizon config (T=104)
+    g = gold("unet")
+    from cld_b200 import default_algo_config
+    from cld_b200.dm_model import DmModel
+    algo = default_algo_config(horizon=104)
+    torch.manual_seed(0)
+    dm = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=10).cuda()
+    eps = dm.denoise(torch.tensor(g["x104"]).cuda(), {"cond_feat": torch.tensor(g["cond"][:3]).cuda()},
+                     torch.tensor(g["t"][:3]).cuda())
+    assert rel(eps, g["eps104"]) < 2e-5
+
+
+def test_posterior_step_vs_oracle(gpu_models):
+    dm, _, _ = gpu_models(100)
+    eng = dm.engine(64)
+    sch = O.make_schedule(100)
+    torch.manual_seed(1)
+    x, eps, nz = torch.randn(37, 52, 4), torch.randn(37, 52, 4), torch.randn(37, 52, 4)
+    for i in (99, 50, 1, 0):
+        mean, sig = O.ddpm_mean_sigma(sch, x, eps, i)
+        want = mean + (0.0 if i == 0 else 1.0) * sig * nz
+        got, gmean = eng.posterior_step(x.cuda(), eps.cuda(), nz.cuda(), i, want_mean=True)
+        assert rel(got, want) < 1e-6 and rel(gmean, mean) < 1e-6
+    for i, nxt in ((98, 96), (2, 0), (0, -1)):
+        want = O.ddim_next(sch, x, eps, i, nxt)
+        got = eng.posterior_step(x.cuda(), eps.cuda(), None, i, nxt, sampler="ddim")
+        assert rel(got, want) < 1e-6
+
+
+def test_cfg0_sampler_vs_reference_golden(gpu_models, gold):
+    """BASELINE config 0: 1 scene x 16 agents, 10-step DDPM, same x_init / noise tensors / weights."""
+    g = gold("cfg0_sample")
+    dm, vae, algo = gpu_models(10)
+    out = dm({"history_positions": torch.zeros(16, 31, 2)},
+             {"cond_feat": torch.tensor(g["cond"]).cuda(), "curr_states": torch.tensor(g["curr"]).cuda()}, algo,
+             noise=torch.tensor(g["noises"]).cuda(), x_init=torch.tensor(g["x_init"]).cuda())
+    assert rel(out["pred_traj"], g["pred_traj"]) < FP32_TOL
+    assert rel(out["x1"], g["x1"]) < FP32_TOL
+    assert rel(out["log_prob_final"], g["log_prob_final"]) < 1e-6
+    assert out["aux_info"]["cond_feat"].shape == (16, 256)
+    # decode + rollout of the reference's own latent
+    act = vae.lstmvae.lstm_dec(torch.tensor(g["pred_traj"]).cuda(), torch.tensor(g["cond"]).cuda())
+    traj, act2 = vae.decode_to_trajectory(torch.tensor(g["pred_traj"]).cuda(), torch.tensor(g["cond"]).cuda(),
+                                          torch.tensor(g["curr"]).cuda())
+    assert rel(act, g["act"]) < 1e-5 and rel(act2, g["act"]) < 1e-5
+    assert rel(traj, g["traj"]) < 1e-5
+    t2 = vae.convert_action_to_state_and_action(torch.tensor(g["act"]).cuda(), torch.tensor(g["curr"]).cuda(),
+                                                descaled_output=True)
+    assert rel(t2, g["traj"]) < 1e-5
+
+
+def test_strided_ddpm_vs_reference_golden(gpu_models, gold):
+    g = gold("stride2_sample")
+    dm, _, algo = gpu_models(100)
+    dm.stride = 2
+    try:
+        out = dm({"history_positions": torch.zeros(4, 31, 2)}, {"cond_feat": torch.tensor(g["cond"]).cuda()}, algo,
+                 noise=torch.tensor(g["noises"]).cuda(), x_init=torch.tensor(g["x_init"]).cuda())
+    finally:
+        dm.stride = 1
+    assert out["x1"] is None
+    assert rel(out["pred_traj"], g["pred_traj"]) < FP32_TOL
+
+
+def test_ddim_sampler_vs_oracle(gpu_models):
+    dm, _, algo = gpu_models(100)
+    aux, _ = make_scenes(1, 8, seed=5)
+    torch.manual_seed(2)
+    x_init = torch.randn(8, 52, 4)
+    dm.stride = 10
+    try:
+        out = dm({"history_positions": torch.zeros(8, 31, 2)}, {"cond_feat": aux["cond_feat"].cuda()}, algo,
+                 x_init=x_init.cuda(), sampler="ddim")
+    finally:
+        dm.stride = 1
+    with torch.no_grad():
+        want = O.sample(cpu_sd(dm.model), O.make_schedule(100), aux["cond_feat"], x_init, None, 100, 10, "ddim")
+    assert rel(out["pred_traj"], want["pred_traj"]) < FP32_TOL
+
+
+def test_unicycle_vs_reference_golden(gpu_models, gold):
+    g = gold("unicycle")
+    dm, _, _ = gpu_models(10)
+    st = dm.engine(32).unicycle(torch.tensor(g["curr"]).cuda(), torch.tensor(g["u"]).cuda())
+    assert rel(st, g["state"]) < 1e-5
+
+
+def test_indicators_bit_exact_vs_reference_golden(gpu_models, gold):
+    g = gold("indicators")
+    dm, _, _ = gpu_models(10)
+    _, batch = make_scenes(2, 8, seed=31, dense=True)
+    from cld_b200.critic import failure_rate_compute, indicators
+    tr = torch.tensor(g["traj"]).cuda()
+    off, coll, rew = indicators(dm, tr, batch)
+    assert np.array_equal(off.cpu().numpy(), g["offroad"])
+    assert np.array_equal(coll.cpu().numpy(), g["coll"])
+    fr = failure_rate_compute(dm, tr, batch)
+    for k in fr:
+        assert abs(fr[k] - float(g[k])) < 1e-12
+    want_rew = O.reward(torch.tensor(g["traj"]), batch)
+    assert rel(rew, want_rew) < 1e-5
+
+
+def test_indicators_with_samples_and_edge_maps(gpu_models):
+    dm, vae, _ = gpu_models(10)
+    S, A, N = 2, 5, 3
+    aux, batch = make_scenes(S, A, seed=77, dense=True)
+    batch["drivable_map"][0] = False                 # everything off-road
+    batch["drivable_map"][1] = True                  # nothing off-road
+    torch.manual_seed(8)
+    u = torch.randn(S * A * N, 52, 2) * torch.tensor([4.0, 0.8])
+    curr = aux["curr_states"].repeat_interleave(N, 0)
+    st = O.unicycle_rollout(curr, u)
+    st[4] = 1e4                                       # far outside the raster: clamps to the edge
+    tr6 = torch.cat([st, u], -1)
+    from cld_b200.critic import indicators
+    off, coll, _ = indicators(dm, tr6.cuda(), batch, num_samp=N)
+    rep = {k: (v.repeat_interleave(N, 0) if torch.is_tensor(v) and v.shape[0] == S * A else v) for k, v in batch.items()}
+    woff, wcoll = O.indicators(tr6[..., :2], rep)
+    assert torch.equal(off.cpu(), woff) and torch.equal(coll.cpu(), wcoll)
+    assert off[:N].all() and not off[N:2 * N].any()
+
+
+def test_guidance_step_vs_reference_golden(gpu_models, gold):
+    g = gold("guidance")
+    dm, vae, _ = gpu_models(10)
+    S, A, N = int(g["S"]), int(g["A"]), int(g["N"])
+    aux, batch = make_scenes(S, A, seed=int(g["seed"]), dense=True)
+    from cld_b200.engine import default_guidance
+    eng = dm.engine(S * A * N)
+    scene = eng.make_scene(batch, S, A, N)
+    z = torch.tensor(g["z"]).cuda()
+    cond = aux["cond_feat"].repeat_interleave(N, 0).cuda()
+    curr = aux["curr_states"].repeat_interleave(N, 0).cuda()
+    z_out, grad, loss = eng.guidance_step(z, cond, curr, scene, default_guidance())
+    assert rel(loss[0], g["loss_ac"].reshape(-1)) < 1e-4
+    assert rel(loss[1], g["loss_mc"].reshape(-1)) < 1e-4
+    # gradient level: oracle autograd (fp32, CPU)
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    g_or, _ = O.guidance_grad(dec_sd, torch.tensor(g["z"]), aux["cond_feat"], aux["curr_states"], batch, A, N)
+    assert rel(grad, g_or) < 1e-3
+    zero_agree = ((grad.cpu() == 0) == (g_or == 0)).float().mean().item()
+    nz = g_or != 0
+    sign_agree = (torch.sign(grad.cpu())[nz] == torch.sign(g_or)[nz]).float().mean().item()
+    print("guidance: rel(grad)=%.3e sign agreement %.6f zero-set agreement %.6f" % (rel(grad, g_or), sign_agree, zero_agree))
+    assert sign_agree > 0.999 and zero_agree > 0.999
+    # the reference's own Adam step
+    assert rel(z_out, g["z_out"]) < 5e-3
+    frac_bad = ((z_out.cpu() - torch.tensor(g["z_out"])).abs() > 1e-3).float().mean().item()
+    assert frac_bad < 1e-3
+
+
+def test_guidance_target_pos_and_sgd_vs_oracle(gpu_models):
+    dm, vae, _ = gpu_models(10)
+    S, A, N = 2, 4, 2
+    aux, batch = make_scenes(S, A, seed=91, dense=True)
+    from cld_b200.engine import default_guidance
+    cfg = default_guidance(target_pos=2.0, optimizer="sgd", lr=1.0)
+    eng = dm.engine(S * A * N)
+    scene = eng.make_scene(batch, S, A, N)
+    torch.manual_seed(92)
+    z = torch.randn(S * A * N, 52, 4)
+    cond = aux["cond_feat"].repeat_interleave(N, 0)
+    curr = aux["curr_states"].repeat_interleave(N, 0)
+    z_out, grad, loss = eng.guidance_step(z.cuda(), cond.cuda(), curr.cuda(), scene, cfg)
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    ocfg = dict(O.DEFAULT_GUIDANCE, target_pos=2.0, optimizer="sgd", lr=1.0)
+    g_or, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], batch, A, N, ocfg)
+    assert rel(loss[2], torch.cat([p["target_pos"] for p in per]).reshape(-1)) < 1e-4
+    assert rel(grad, g_or) < 1e-3
+    assert rel(z_out, O.apply_guidance_update(z, g_or, ocfg)) < 1e-5
+
+
+def test_guided_sampler_vs_oracle(gpu_models):
+    """Guided strided-DDPM (cfg1-shaped, small): CUDA loop vs the composed oracle on identical noise."""
+    dm, vae, algo = gpu_models(10)
+    S, A, N = 2, 4, 1
+    aux, batch = make_scenes(S, A, seed=55, dense=True)
+    from cld_b200.engine import default_guidance
+    torch.manual_seed(56)
+    R = S * A * N
+    x_init, noises = torch.randn(R, 52, 4), torch.randn(10, R, 52, 4)
+    out = dm({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()},
+             {k: v.cuda() for k, v in aux.items()}, algo, noise=noises.cuda(), x_init=x_init.cuda(),
+             guidance=default_guidance(), want_indicators=True)
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    gd = dict(dec_sd=dec_sd, cond=aux["cond_feat"], curr=aux["curr_states"], batch=batch, A=A, N=N, cfg=O.DEFAULT_GUIDANCE)
+    want = O.sample(cpu_sd(dm.model), O.make_schedule(10), aux["cond_feat"], x_init, noises, 10, 1, "ddpm", guidance=gd)
+    r = rel(out["pred_traj"], want["pred_traj"])
+    frac = ((out["pred_traj"].cpu() - want["pred_traj"]).abs() > 1e-2 * want["pred_traj"].abs().max()).float().mean().item()
+    print("guided sampler: rel %.3e, fraction of elements off by >1%% of max: %.5f" % (r, frac))
+    assert frac < 0.02
+    wtraj, _ = O.decode_rollout(dec_sd, out["pred_traj"].cpu(), aux["cond_feat"], aux["curr_states"])
+    assert rel(out["traj"], wtraj) < 1e-4
+    woff, wcoll = O.indicators(out["traj"].cpu()[..., :2], batch)
+    assert torch.equal(out["offroad"].cpu(), woff) and torch.equal(out["coll"].cpu(), wcoll)
+
+
+def test_sampler_chunking_and_device_rng(gpu_models):
+    """R > max_rows is processed in whole-scene chunks with identical results; Philox noise is N(0,1)."""
+    from cld_b200 import default_algo_config
+    from cld_b200.dm_model import DmModel
+    dm, _, algo = gpu_models(10)
+    torch.manual_seed(0)
+    dm_small = DmModel(default_algo_config(), {"image": (34, 224, 224)}, n_timesteps=10, max_rows=8).cuda()
+    aux, _ = make_scenes(3, 4, seed=3)
+    torch.manual_seed(4)
+    x_init, noises = torch.randn(12, 52, 4).cuda(), torch.randn(10, 12, 52, 4).cuda()
+    eng_small = dm_small.engine(1)
+    assert eng_small.max_rows == 8
+    a = eng_small.sample(x_init, aux["cond_feat"].cuda(), noises=noises)
+    b = dm.engine(12).sample(x_init, aux["cond_feat"].cuda(), noises=noises)
+    assert torch.equal(a["x0"], b["x0"])
+    eng = dm.engine(12)
+    zero = torch.zeros(4096, 52, 4).cuda()
+    c = eng.sample(zero[:12], aux["cond_feat"].cuda(), seed=1234)
+    d = eng.sample(zero[:12], aux["cond_feat"].cuda(), seed=1234)
+    e = eng.sample(zero[:12], aux["cond_feat"].cuda(), seed=1235)
+    assert torch.equal(c["x0"], d["x0"]) and not torch.equal(c["x0"], e["x0"])
+
+
+def test_error_paths(gpu_models):
+    dm, _, _ = gpu_models(10)
+    eng = dm.engine(16)
+    with pytest.raises(RuntimeError):
+        eng.posterior_step(torch.zeros(2, 52, 4).cuda(), torch.zeros(2, 52, 4).cuda(), None, 99)   # t out of range
+    from cld_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(horizon=50)                       # horizon must be a multiple of 4
+    e2 = Engine(n_timesteps=10, max_rows=4)
+    with pytest.raises(RuntimeError):
+        e2.unet_forward(torch.zeros(2, 52, 4).cuda(), torch.zeros(2, 256).cuda(), torch.zeros(2).long().cuda())  # no weights

@@ -1,0 +1,131 @@
+"""CPU: the oracle (oracle/cld_oracle.py) against the golden vectors produced by the REAL reference
+(oracle/make_golden.py).  No GPU, no reference needed."""
+import numpy as np
+import torch
+
+import cld_oracle as O
+from cld_b200.synthetic import make_scenes
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _sds(models_cpu, n):
+    dm, vae, algo = models_cpu(n)
+    unet_sd = {k: v.detach() for k, v in dm.model.state_dict().items()}
+    dec_sd = {k: v.detach() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    return dm, unet_sd, dec_sd
+
+
+def test_weight_init_matches_reference(models_cpu, gold):
+    g = gold("unet")
+    dm, unet_sd, dec_sd = _sds(models_cpu, 10)
+    assert abs(float(sum(v.double().sum() for v in unet_sd.values())) - float(g["unet_sum"])) < 1e-9
+    assert abs(float(sum(v.double().abs().sum() for v in unet_sd.values())) - float(g["unet_abs"])) < 1e-9
+    assert abs(float(sum(v.double().sum() for v in dec_sd.values())) - float(g["dec_sum"])) < 1e-9
+
+
+def test_schedule_known_answers():
+    # betas(n=10) of the reference
+    want = [0.027907, 0.075494, 0.124396, 0.17719, 0.237282, 0.309883, 0.404003, 0.536998, 0.743829, 0.999]
+    s = O.make_schedule(10)
+    assert np.allclose(s["betas"].numpy(), want, atol=1e-6)
+    assert len(s) == 14
+    assert abs((-torch.log((0.5 * s["posterior_log_variance_clipped"][0]).exp()) - 0.5 * np.log(2 * np.pi)).item() - 22.106915) < 1e-4
+
+
+def test_unet_oracle_vs_reference_golden(models_cpu, gold):
+    g = gold("unet")
+    _, unet_sd, _ = _sds(models_cpu, 10)
+    with torch.no_grad():
+        eps = O.unet_forward(unet_sd, torch.tensor(g["x"]), torch.tensor(g["cond"]), torch.tensor(g["t"]))
+        e104 = O.unet_forward(unet_sd, torch.tensor(g["x104"]), torch.tensor(g["cond"][:3]), torch.tensor(g["t"][:3]))
+    assert rel(eps, g["eps"]) < 5e-6
+    assert rel(e104, g["eps104"]) < 5e-6
+
+
+def test_sampler_oracle_vs_reference_golden(models_cpu, gold):
+    g = gold("cfg0_sample")
+    _, unet_sd, dec_sd = _sds(models_cpu, 10)
+    with torch.no_grad():
+        out = O.sample(unet_sd, O.make_schedule(10), torch.tensor(g["cond"]), torch.tensor(g["x_init"]),
+                       torch.tensor(g["noises"]), 10, 1, "ddpm")
+        traj, act = O.decode_rollout(dec_sd, torch.tensor(g["pred_traj"]), torch.tensor(g["cond"]), torch.tensor(g["curr"]))
+    assert rel(out["pred_traj"], g["pred_traj"]) < 1e-4
+    assert rel(out["x1"], g["x1"]) < 1e-4
+    assert rel(out["log_prob_final"], g["log_prob_final"]) < 1e-6
+    assert rel(act, g["act"]) < 1e-5
+    assert rel(traj, g["traj"]) < 1e-5
+
+
+def test_strided_sampler_oracle_vs_reference_golden(models_cpu, gold):
+    g = gold("stride2_sample")
+    _, unet_sd, _ = _sds(models_cpu, 100)
+    with torch.no_grad():
+        out = O.sample(unet_sd, O.make_schedule(100), torch.tensor(g["cond"]), torch.tensor(g["x_init"]),
+                       torch.tensor(g["noises"]), 100, 2, "ddpm")
+    assert out["x1"] is None            # step index 1 is never visited with stride 2 (dm_model.py:126-127)
+    assert rel(out["pred_traj"], g["pred_traj"]) < 1e-4
+
+
+def test_unicycle_oracle_vs_reference_golden(gold):
+    g = gold("unicycle")
+    st = O.unicycle_rollout(torch.tensor(g["curr"]), torch.tensor(g["u"]))
+    assert rel(st, g["state"]) < 1e-5
+
+
+def test_unicycle_closed_form_matches_chain_in_bounds():
+    # property: inside the bounds the closed form equals the step-by-step integrator
+    torch.manual_seed(3)
+    u = torch.randn(8, 52, 2) * torch.tensor([0.5, 0.05])
+    c0 = torch.cat([torch.zeros(8, 2), 5 + torch.rand(8, 1) * 5, torch.zeros(8, 1)], 1)
+    st = O.unicycle_rollout(c0, u)
+    x = c0.clone()
+    outs = []
+    for k in range(52):
+        v, th = x[:, 2], x[:, 3]
+        vm = v + u[:, k, 0] * 0.1 * 0.5
+        x = torch.stack([x[:, 0] + vm * torch.cos(th) * 0.1, x[:, 1] + vm * torch.sin(th) * 0.1,
+                         v + u[:, k, 0] * 0.1, th + u[:, k, 1] * 0.1], 1)
+        outs.append(x)
+    assert rel(st, torch.stack(outs, 1)) < 1e-5
+
+
+def test_indicators_oracle_vs_reference_golden(gold):
+    g = gold("indicators")
+    _, batch = make_scenes(2, 8, seed=31, dense=True)
+    tr = torch.tensor(g["traj"])
+    off, coll = O.indicators(tr[..., :2], batch)
+    assert np.array_equal(off.numpy(), g["offroad"])
+    assert np.array_equal(coll.numpy(), g["coll"])
+    fr = O.failure_rates(tr[..., :2], batch)
+    for k in fr:
+        assert abs(fr[k] - float(g[k])) < 1e-12
+    assert float(g["offroad_failure_rate"]) > 0 and float(g["collision_failure_rate"]) > 0
+
+
+def test_guidance_oracle_vs_reference_golden(models_cpu, gold):
+    g = gold("guidance")
+    _, _, dec_sd = _sds(models_cpu, 10)
+    S, A, N = int(g["S"]), int(g["A"]), int(g["N"])
+    aux, batch = make_scenes(S, A, seed=int(g["seed"]), dense=True)
+    z = torch.tensor(g["z"])
+    grad, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], batch, A, N)
+    z_out = O.apply_guidance_update(z, grad)
+    lo_ac = torch.cat([p["agent_collision"] for p in per])
+    lo_mc = torch.cat([p["map_collision"] for p in per])
+    assert rel(lo_ac.reshape(-1), g["loss_ac"].reshape(-1)) < 1e-5
+    assert rel(lo_mc.reshape(-1), g["loss_mc"].reshape(-1)) < 1e-5
+    assert rel(z_out, g["z_out"]) < 1e-4
+    moved = torch.tensor(g["z_out"]) - z
+    assert (torch.sign(grad) == torch.sign(-moved)).float().mean().item() > 0.9999
+    assert float(lo_ac.sum()) > 0 and float(lo_mc.sum()) > 0
+
+
+def test_ddim_final_step_is_x0_prediction():
+    s = O.make_schedule(100)
+    x, eps = torch.randn(2, 52, 4), torch.randn(2, 52, 4)
+    x0 = O.ddim_next(s, x, eps, 0, -1)
+    assert torch.allclose(x0, s["sqrt_recip_alphas_cumprod"][0] * x - s["sqrt_recipm1_alphas_cumprod"][0] * eps)
