@@ -20,6 +20,27 @@ int fail(CldHandle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+int prof_begin(CldHandle* h, int kind, cudaStream_t s) {
+  if (!h->profiling) return 0;
+  if (h->ev_used + 2 > h->ev_pool.size()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      CLD_CUDA_OK(h, cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+  }
+  h->ev_kind.resize(h->ev_pool.size() / 2);
+  h->ev_kind[h->ev_used / 2] = kind;
+  CLD_CUDA_OK(h, cudaEventRecord(h->ev_pool[h->ev_used], s));
+  return 0;
+}
+int prof_end(CldHandle* h, cudaStream_t s) {
+  if (!h->profiling) return 0;
+  CLD_CUDA_OK(h, cudaEventRecord(h->ev_pool[h->ev_used + 1], s));
+  h->ev_used += 2;
+  return 0;
+}
+
 template <typename T>
 static int dev_alloc(CldHandle* h, T** p, size_t n) {
   void* q = nullptr;
@@ -144,6 +165,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
 void cld_destroy(CldHandle* h) {
   if (!h) return;
   tc_destroy(h);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -456,15 +478,25 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
       if (!noises && seed == 0 && sampler == CLD_SAMPLER_DDPM && i != 0)
         return fail(h, CLD_ERR_ARG, "either a noise tensor or a non-zero seed is required");
       if ((rc = fill_t(h, h->ws_t, i, Rc, s))) return rc;
+      if ((rc = prof_begin(h, 0, s))) return rc;
       if ((rc = unet_dispatch(h, x, condc, h->ws_t, h->ws_eps, Rc, s))) return rc;
+      if ((rc = prof_end(h, s))) return rc;
       const bool guided = (g != nullptr) && i != 0;
       const uint64_t seq = ((uint64_t)k << 32) ^ (uint64_t)r0;
       if (!guided) {
+        if ((rc = prof_begin(h, 1, s))) return rc;
         if ((rc = posterior_step(h, x, h->ws_eps, nz, seed, seq, i, i_next, sampler, x, nullptr, Rc, s))) return rc;
+        if ((rc = prof_end(h, s))) return rc;
       } else {
+        if ((rc = prof_begin(h, 1, s))) return rc;
         if ((rc = posterior_step(h, x, h->ws_eps, nullptr, 0, 0, i, i_next, sampler, nullptr, h->ws_mean, Rc, s))) return rc;
+        if ((rc = prof_end(h, s))) return rc;
+        if ((rc = prof_begin(h, 2, s))) return rc;
         if ((rc = guidance_step_impl(h, h->ws_mean, condc, currc, sc, g, h->ws_mean, nullptr, nullptr, Rc, s))) return rc;
+        if ((rc = prof_end(h, s))) return rc;
+        if ((rc = prof_begin(h, 1, s))) return rc;
         if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, sampler == CLD_SAMPLER_DDPM ? i : 0, x, Rc, s))) return rc;
+        if ((rc = prof_end(h, s))) return rc;
       }
       if (i == 1 && x1_out) {
         CLD_CUDA_OK(h, cudaMemcpyAsync(x1_out + r0 * row_e, x, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -475,14 +507,40 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
       CLD_CUDA_OK(h, cudaMemcpyAsync(x0_out + r0 * row_e, x, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (traj_out || offroad_out || coll_out) {
       float* tr = traj_out ? traj_out + (size_t)r0 * T * 6 : h->ws_traj;
+      if ((rc = prof_begin(h, 3, s))) return rc;
       if ((rc = decode_rollout(h, x, condc, currc, nullptr, tr, false, Rc, s))) return rc;
       if (offroad_out || coll_out) {
         if ((rc = indicators(h, tr, sc, offroad_out ? offroad_out + (size_t)r0 * T : nullptr,
                              coll_out ? coll_out + r0 : nullptr, nullptr, Rc, s)))
           return rc;
       }
+      if ((rc = prof_end(h, s))) return rc;
     }
   }
+  return CLD_OK;
+}
+
+unsigned long long cld_launch_count(const CldHandle* h) { return h ? h->launches : 0ull; }
+
+int cld_profile_begin(CldHandle* h) {
+  if (!h) return CLD_ERR_ARG;
+  h->profiling = true;
+  h->ev_used = 0;
+  return CLD_OK;
+}
+
+int cld_profile_end(CldHandle* h, double* ms_by_kind, int* count_by_kind, int nkinds) {
+  if (!h || !ms_by_kind || !count_by_kind) return fail(h, CLD_ERR_ARG, "null argument");
+  for (int k = 0; k < nkinds; ++k) { ms_by_kind[k] = 0.0; count_by_kind[k] = 0; }
+  if (h->ev_used) CLD_CUDA_OK(h, cudaEventSynchronize(h->ev_pool[h->ev_used - 1]));
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CLD_CUDA_OK(h, cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+    int k = h->ev_kind[i / 2];
+    if (k >= 0 && k < nkinds) { ms_by_kind[k] += ms; count_by_kind[k] += 1; }
+  }
+  h->profiling = false;
+  h->ev_used = 0;
   return CLD_OK;
 }
 

@@ -97,6 +97,13 @@ struct CldHandle {
   // debug tap
   int dbg_stage = -1;
   float* dbg_out = nullptr;
+  // measurement: kernels launched by this handle; optional CUDA-event brackets around the phases of
+  // cld_sample (0 denoiser, 1 posterior/noise, 2 guidance, 3 decode+indicators)
+  unsigned long long launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;      // kind of bracket i (events 2i, 2i+1)
+  size_t ev_used = 0;
   // bf16 tensor-core path (opaque, owned by unet_tc.cu)
   void* tc = nullptr;
 };
@@ -115,8 +122,12 @@ int fail(CldHandle* h, int code, const char* fmt, ...);
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess)                                                                 \
       return cld::fail(h, CLD_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    if (h) ++(h)->launches;                                                                \
   } while (0)
 
+// event brackets for cld_sample phases (no-ops unless h->profiling)
+int prof_begin(CldHandle* h, int kind, cudaStream_t s);
+int prof_end(CldHandle* h, cudaStream_t s);
 // ---- kernels_unet_fp32.cu
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps,
                       int R, cudaStream_t s);

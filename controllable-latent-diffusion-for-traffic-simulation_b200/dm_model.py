@@ -215,7 +215,8 @@ class DmModel(nn.Module):
         return self.sample_traj(data_batch, algo_config, aux_info, **kw)
 
     def sample_traj(self, data_batch, algo_config, aux_info, *, noise=None, x_init=None, sampler="ddpm",
-                    guidance=None, seed=None, use_device_rng=False, want_traj=False, want_indicators=False):
+                    guidance=None, seed=None, use_device_rng=False, want_traj=False, want_indicators=False,
+                    agents_per_scene=None):
         B = data_batch['history_positions'].size()[0]
         N = algo_config.num_samp
         T, D = algo_config.horizon, algo_config.vae.latent_size
@@ -235,7 +236,7 @@ class DmModel(nn.Module):
         curr_rows = rep(aux_info['curr_states']) if 'curr_states' in aux_info else None
         scene = None
         if guidance is not None or want_indicators:
-            A = guidance.get('agents_per_scene') if guidance is not None and 'agents_per_scene' in guidance else None
+            A = agents_per_scene
             if A is None:
                 sidx = data_batch['scene_index']
                 A = int((sidx == sidx[0]).sum().item())

@@ -94,6 +94,20 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ------------------------------------------------------------------ measurement
+    def launch_count(self):
+        return int(lib.cld_launch_count(self._h))
+
+    def profile_begin(self):
+        self._check(lib.cld_profile_begin(self._h), "cld_profile_begin")
+
+    def profile_end(self):
+        """-> {kind: (total_ms, brackets)} for kinds denoiser / step / guidance / decode."""
+        ms, cnt = (C.c_double * 4)(), (C.c_int * 4)()
+        self._check(lib.cld_profile_end(self._h, ms, cnt, 4), "cld_profile_end")
+        names = ["denoiser", "step", "guidance", "decode"]
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
     # ------------------------------------------------------------------ weights / schedule
     def load_unet(self, state_dict):
         """state_dict: DmModel.model.state_dict() (reference key order)."""

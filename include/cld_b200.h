@@ -186,6 +186,14 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
                int* x1_valid, float* traj_out, uint8_t* offroad_out, float* coll_out, int R,
                void* stream);
 
+/* Measurement hooks (bench.py): number of kernels this handle has launched, and CUDA-event brackets
+ * around the phases of cld_sample on the caller's stream (kind 0 denoiser forward, 1 posterior /
+ * noise step, 2 guidance step, 3 decode + rollout + indicators).  cld_profile_end synchronises on the
+ * last recorded event and returns summed milliseconds and bracket counts per kind. */
+unsigned long long cld_launch_count(const CldHandle* h);
+int cld_profile_begin(CldHandle* h);
+int cld_profile_end(CldHandle* h, double* ms_by_kind, int* count_by_kind, int nkinds);
+
 #ifdef __cplusplus
 }
 #endif
