@@ -17,7 +17,7 @@ EXPORTS = [
     "cld_version", "cld_create", "cld_destroy", "cld_last_error", "cld_load_unet", "cld_load_decoder",
     "cld_set_schedule", "cld_unet_forward", "cld_unet_debug_stage", "cld_posterior_step", "cld_add_noise",
     "cld_decode_rollout", "cld_unicycle", "cld_indicators", "cld_guidance_step", "cld_sample",
-    "cld_launch_count", "cld_profile_begin", "cld_profile_end",
+    "cld_launch_count", "cld_profile_begin", "cld_profile_end", "cld_tc_selftest",
 ]
 
 
@@ -77,6 +77,7 @@ def _load():
                                       i32, vp]
     lib.cld_sample.argtypes = [vp, vp, vp, u64, vp, vp, C.POINTER(CldScene), C.POINTER(CldGuidanceConfig), i32, i32,
                                vp, vp, C.POINTER(C.c_int), vp, vp, vp, i32, vp]
+    lib.cld_tc_selftest.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.cld_launch_count.argtypes = [vp]
     lib.cld_profile_begin.argtypes = [vp]
     lib.cld_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int), i32]

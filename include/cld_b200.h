@@ -186,6 +186,12 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
                int* x1_valid, float* traj_out, uint8_t* offroad_out, float* coll_out, int R,
                void* stream);
 
+/* Hardware self-test of the tcgen05 building blocks (no handle): stages a 128B-swizzled A image and
+ * B image (device pointers) in shared memory, issues nk16 UMMAs (M=128, N, K=16) whose A descriptor starts
+ * a_start_off bytes into the image with sbo_a bytes between 8-row groups, returns D [128][N] fp32. */
+int cld_tc_selftest(const void* a_img, int a_bytes, const void* b_img, int b_bytes, int a_start_off,
+                    int sbo_a, int N, int nk16, int base_offset, float* d_out, void* stream);
+
 /* Measurement hooks (bench.py): number of kernels this handle has launched, and CUDA-event brackets
  * around the phases of cld_sample on the caller's stream (kind 0 denoiser forward, 1 posterior /
  * noise step, 2 guidance step, 3 decode + rollout + indicators).  cld_profile_end synchronises on the
