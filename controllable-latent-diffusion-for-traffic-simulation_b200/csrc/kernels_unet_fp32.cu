@@ -238,6 +238,16 @@ static int tap(CldHandle* h, int stage, const float* buf, int R, cudaStream_t s)
   return 0;
 }
 
+// time / cond projections of all 12 blocks at once: tbias[R, tb_total] = Mish([t_emb, cond]) @ Wtb + btb
+int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s) {
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  time_cond_mish<<<R, 128, 0, s>>>(t, cond, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, h->tcm, c.base_dim, c.cond_dim);
+  CLD_LAUNCH_OK(h, "time_cond_mish");
+  ConvW tb; tb.w = u.tb_w; tb.b = u.tb_b; tb.cin = c.base_dim + c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;
+  return launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s);
+}
+
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R,
                       cudaStream_t s) {
   const UnetW& u = h->unet;
@@ -247,13 +257,7 @@ int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int
   float *a0 = h->act[0], *a1 = h->act[1], *sk1 = h->act[2], *sk2 = h->act[3];
   float *tA = h->act[4], *tB = h->act[5], *tR = h->act[6];
   int rc;
-  // time / cond projections of all 12 blocks at once: tbias = Mish([t_emb, cond]) @ Wtb + btb
-  time_cond_mish<<<R, 128, 0, s>>>(t, cond, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, h->tcm, c.base_dim, c.cond_dim);
-  CLD_LAUNCH_OK(h, "time_cond_mish");
-  {
-    ConvW tb; tb.w = u.tb_w; tb.b = u.tb_b; tb.cin = c.base_dim + c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;
-    if ((rc = launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s))) return rc;
-  }
+  if ((rc = unet_time_bias(h, cond, t, R, s))) return rc;
 #define RB(i, in0, c0, in1, c1, TT, out, stage)                                                     \
   if ((rc = run_resblock(h, u.rb[i], in0, c0, in1, c1, TT, tA, tB, tR, out, R, s))) return rc;       \
   if ((rc = tap(h, stage, out, R, s))) return rc;
