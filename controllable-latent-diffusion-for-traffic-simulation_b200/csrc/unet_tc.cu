@@ -22,7 +22,7 @@ constexpr int TC_UNIT = 8192;
 constexpr int TC_UNITS = 8;
 constexpr int TC_THREADS = 320;
 constexpr int TC_ARENA = 128 * 1024;
-constexpr int TC_SMEM = TC_ARENA + TC_UNITS * TC_UNIT + 4096 + 8192 + 2048 + 256 + 1024;
+constexpr int TC_SMEM = TC_ARENA + TC_UNITS * TC_UNIT + 4096 + 8192 + 8192 + 256 + 1024;
 
 enum { EPI_GN_TB = 0, EPI_GN_RES_ACC = 1, EPI_GN_RES_ID = 2, EPI_BIAS = 3, EPI_UP = 4, EPI_GN = 5, EPI_OUT = 6 };
 
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
   uint8_t* ring = arena + TC_ARENA;
   float* par_s = reinterpret_cast<float*>(ring + TC_UNITS * TC_UNIT);   // [4][256]
   float* tb_s = par_s + 1024;                                           // [8][256]
-  float* st_s = tb_s + 2048;                                            // [8][32][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + 512);             // full[8], empty[8], act_ready, acc_ready
+  float* st_s = tb_s + 2048;                                            // [4 quadrants][8][32][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + 2048);            // full[8], empty[8], act_ready, acc_ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
               tb_s[bb * 256 + c] = (r < P.R) ? P.tbias[(size_t)r * P.tb_stride + o->tb_off + c] : 0.f;
             }
           }
-          if (is_gn) for (int i = etid; i < 512; i += 256) st_s[i] = 0.f;
+          if (is_gn) for (int i = etid; i < 2048; i += 256) st_s[i] = 0.f;
         }
         epi_bar();
         mbar_wait(bar_acc, acc_par);
@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
                 s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
                 if (lane < 8) {
-                  atomicAdd(&st_s[(b * 32 + (c0 >> 3) + sb) * 2 + 0], s);
-                  atomicAdd(&st_s[(b * 32 + (c0 >> 3) + sb) * 2 + 1], ss);
+                  // slot owned by (quadrant, b, sub-block): only this lane of this warp touches it -> deterministic
+                  float* sp = &st_s[((q * 8 + b) * 32 + (c0 >> 3) + sb) * 2];
+                  sp[0] += s; sp[1] += ss;
                 }
               }
             }
@@ -305,7 +306,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
                 if (is_gn) {
                   const int gsb = ((c >> 3) / sbpg) * sbpg;
                   float S = 0.f, SS = 0.f;
-                  for (int k = 0; k < sbpg; ++k) { S += st_s[(b * 32 + gsb + k) * 2]; SS += st_s[(b * 32 + gsb + k) * 2 + 1]; }
+                  for (int k = 0; k < sbpg; ++k) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                      S += st_s[((qq * 8 + b) * 32 + gsb + k) * 2];
+                      SS += st_s[((qq * 8 + b) * 32 + gsb + k) * 2 + 1];
+                    }
+                  }
                   mean = S * inv_n;
                   float var = fmaxf(SS * inv_n - mean * mean, 0.f);
                   rstd = rsqrtf(var + 1e-5f);
