@@ -8,6 +8,8 @@
 //                           (two layers, stash written by the forward kernel) -> dz, fused with the first
 //                           Adam / SGD step of perturb (:2250-2278).
 // All arithmetic fp32 (the update is sign-sensitive: SURVEY.md section 7, hard part 3).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace cld {
@@ -25,6 +27,7 @@ struct LossArgs {
   int D; float buffer, decay, speed_th, min_target_time;
   int nl, nw;
   float lwise[16], wwise[16];
+  float wts[CLD_MAX_T];   // decay^t / sum_t decay^t  (guidance_loss.py:607-608)
 };
 
 // torch.linspace(lo, hi, n)[i] in fp32 (symmetric evaluation, as ATen does)
@@ -54,12 +57,7 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
     q[3] = (fabsf(a.speed[g]) > a.speed_th) ? 1.f : 0.f;
     q[4] = a.wfa[g * 9 + 0]; q[5] = a.wfa[g * 9 + 1]; q[6] = a.wfa[g * 9 + 3]; q[7] = a.wfa[g * 9 + 4];
   }
-  if (tid == 0) {
-    // exp_weights = decay^t / sum (guidance_loss.py:607-608)
-    float sum = 0.f;
-    for (int t = 0; t < T; ++t) { float w = powf(a.decay, (float)t); wts[t] = w; sum += w; }
-    for (int t = 0; t < T; ++t) wts[t] /= sum;
-  }
+  for (int t = tid; t < T; t += 256) wts[t] = a.wts[t];
   for (int it = tid; it < A * T; it += 256) {
     int i = it / T, t = it - i * T, g = ag0 + i;
     const float* tr = a.traj + (((size_t)g * N + n) * T + t) * 6;
@@ -136,93 +134,8 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   }
   __syncthreads();
 
-  // ---------------- map collision: warp per (agent, step), lanes over the sample points ----------
-  if (a.w_mc != 0.f) {
-    const int P = a.nl * a.nw;
-    for (int i = warp; i < A; i += 8) {
-      const int g = ag0 + i;
-      const size_t row = (size_t)g * N + n;
-      const float mov_i = agt[i * 8 + 3];
-      const float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
-      const float diag = sqrtf(L * L + Wd * Wd);
-      const float* M = a.rfa + (size_t)g * 9;
-      const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
-      float loss_i = 0.f;
-      for (int t = 0; t < T; ++t) {
-        const float* tr = a.traj + ((size_t)row * T + t) * 6;
-        const float px = tr[0], py = tr[1], psi = tr[3];
-        const float c = cosf(psi), sn = sinf(psi);
-        uint32_t offm[4] = {0u, 0u, 0u, 0u};
-        int n_off = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int p = lane + 32 * q;
-          bool off = false;
-          if (p < P) {
-            float lx = a.lwise[p / a.nw] * L, ly = a.wwise[p % a.nw] * Wd;
-            float qx = lx * c - ly * sn + px, qy = lx * sn + ly * c + py;
-            float rx = M[0] * qx + M[1] * qy + M[2], ry = M[3] * qx + M[4] * qy + M[5];
-            long long cx = (long long)rx, cy = (long long)ry;      // .long(): truncation (guidance_loss.py:796)
-            cx = cx < 0 ? 0 : (cx > a.W - 1 ? a.W - 1 : cx);
-            cy = cy < 0 ? 0 : (cy > a.H - 1 ? a.H - 1 : cy);
-            off = dm[cy * a.W + cx] == 0;
-          }
-          offm[q] = __ballot_sync(0xffffffffu, off);
-          n_off += __popc(offm[q]);
-        }
-        float gx = 0.f, gy = 0.f, gpsi = 0.f, lsum = 0.f;
-        if (n_off > 0 && n_off < P && mov_i != 0.f) {
-          for (int q = 0; q < 4; ++q) {
-            int p = lane + 32 * q;
-            if (p >= P || !((offm[q] >> lane) & 1u)) continue;
-            float plx = a.lwise[p / a.nw] * L, ply = a.wwise[p % a.nw] * Wd;
-            float pxw = plx * c - ply * sn + px, pyw = plx * sn + ply * c + py;
-            float best = 3.4e38f;
-            int cnt = 0;
-            for (int k = 0; k < P; ++k) {
-              if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
-              float lx = a.lwise[k / a.nw] * L, ly = a.wwise[k % a.nw] * Wd;
-              float dx = (lx * c - ly * sn + px) - pxw, dy = (lx * sn + ly * c + py) - pyw;
-              float dist = sqrtf(dx * dx + dy * dy);
-              if (dist < best) { best = dist; cnt = 1; } else if (dist == best) { ++cnt; }
-            }
-            lsum += 1.0f - best / diag;
-            if (best > 0.f) {
-              // torch.amin splits the gradient evenly over tied minima
-              float f = -1.0f / (best * diag * (float)cnt);
-              for (int k = 0; k < P; ++k) {
-                if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
-                float lx = a.lwise[k / a.nw] * L, ly = a.wwise[k % a.nw] * Wd;
-                float dx = (lx * c - ly * sn + px) - pxw, dy = (lx * sn + ly * c + py) - pyw;
-                float dist = sqrtf(dx * dx + dy * dy);
-                if (dist == best) {
-                  float ggx = dx * f, ggy = dy * f;
-                  gx += ggx; gy += ggy;
-                  gpsi += ggx * (-lx * sn - ly * c) + ggy * (lx * c - ly * sn);
-                }
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          gx += __shfl_xor_sync(0xffffffffu, gx, o);
-          gy += __shfl_xor_sync(0xffffffffu, gy, o);
-          gpsi += __shfl_xor_sync(0xffffffffu, gpsi, o);
-          lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-        }
-        if (lane == 0) {
-          float kk = a.w_mc * inv_AN * wts[t];
-          float* o = a.dtraj + ((size_t)row * T + t) * 4;
-          o[0] += kk * gx; o[1] += kk * gy; o[3] += kk * gpsi;
-          loss_i += wts[t] * lsum;
-        }
-      }
-      if (lane == 0 && a.loss) a.loss[(size_t)a.R + row] = loss_i;
-    }
-  } else if (a.loss) {
-    for (int i = tid; i < A; i += 256) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
-  }
+  if (a.loss)
+    for (int i = tid; i < A; i += 256) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;   // map term: own kernel
 
   // ---------------- target position (softmin-weighted squared distance): warp per agent ------------
   if (a.w_tp != 0.f && a.target) {
@@ -273,6 +186,100 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   }
 }
 
+
+// ---------------- map collision: one warp per (row, step), lanes over the 10x10 sample points ----------
+// MapCollisionLoss.forward (guidance_loss.py:772-870).  Runs after guidance_loss_grad_kernel and
+// accumulates into dtraj.
+__global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
+  __shared__ float qxs[8][128], qys[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 8 + warp;
+  const int T = a.T, N = a.N;
+  if (item >= (long long)a.R * T) return;
+  const int row = (int)(item / T), t = (int)(item - (long long)row * T);
+  const int g = row / N;
+  if (!(fabsf(a.speed[g]) > a.speed_th)) return;       // loss and gradient are zero for non-moving agents
+  const int P = a.nl * a.nw;
+  const float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
+  const float* M = a.rfa + (size_t)g * 9;
+  const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
+  const float* tr = a.traj + ((size_t)row * T + t) * 6;
+  const float px = tr[0], py = tr[1], psi = tr[3];
+  const float c = cosf(psi), sn = sinf(psi);
+  uint32_t offm[4];
+  int n_off = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int p = lane + 32 * q;
+    bool off = false;
+    if (p < P) {
+      float lx = a.lwise[p / a.nw] * L, ly = a.wwise[p % a.nw] * Wd;
+      float qx = lx * c - ly * sn + px, qy = lx * sn + ly * c + py;
+      qxs[warp][p] = qx; qys[warp][p] = qy;
+      float rx = M[0] * qx + M[1] * qy + M[2], ry = M[3] * qx + M[4] * qy + M[5];
+      long long cx = (long long)rx, cy = (long long)ry;      // .long(): truncation (guidance_loss.py:796)
+      cx = cx < 0 ? 0 : (cx > a.W - 1 ? a.W - 1 : cx);
+      cy = cy < 0 ? 0 : (cy > a.H - 1 ? a.H - 1 : cy);
+      off = dm[cy * a.W + cx] == 0;
+    }
+    offm[q] = __ballot_sync(0xffffffffu, off);
+    n_off += __popc(offm[q]);
+  }
+  if (n_off == 0 || n_off == P) return;                 // only partially overlapping steps contribute
+  __syncwarp();
+  const float diag = sqrtf(L * L + Wd * Wd);
+  float gx = 0.f, gy = 0.f, gpsi = 0.f, lsum = 0.f;
+  for (int q = 0; q < 4; ++q) {
+    int p = lane + 32 * q;
+    if (p >= P || !((offm[q] >> lane) & 1u)) continue;
+    const float pxw = qxs[warp][p], pyw = qys[warp][p];
+    float best = 3.4e38f, bx = 0.f, by = 0.f;
+    int cnt = 0;
+    for (int k = 0; k < P; ++k) {
+      if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
+      float dx = qxs[warp][k] - pxw, dy = qys[warp][k] - pyw;
+      float dist = sqrtf(dx * dx + dy * dy);
+      if (dist < best) { best = dist; bx = qxs[warp][k]; by = qys[warp][k]; cnt = 1; }
+      else if (dist == best) ++cnt;
+    }
+    lsum += 1.0f - best / diag;
+    if (best > 0.f) {
+      if (cnt == 1) {
+        float f = -1.0f / (best * diag);
+        float ggx = (bx - pxw) * f, ggy = (by - pyw) * f;
+        gx += ggx; gy += ggy;
+        gpsi += ggx * (-(by - py)) + ggy * (bx - px);
+      } else {
+        // torch.amin splits the gradient evenly over tied minima
+        float f = -1.0f / (best * diag * (float)cnt);
+        for (int k = 0; k < P; ++k) {
+          if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
+          float dx = qxs[warp][k] - pxw, dy = qys[warp][k] - pyw;
+          if (sqrtf(dx * dx + dy * dy) == best) {
+            float ggx = dx * f, ggy = dy * f;
+            gx += ggx; gy += ggy;
+            gpsi += ggx * (-(qys[warp][k] - py)) + ggy * (qxs[warp][k] - px);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    gy += __shfl_xor_sync(0xffffffffu, gy, o);
+    gpsi += __shfl_xor_sync(0xffffffffu, gpsi, o);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  }
+  if (lane == 0) {
+    const float wt = a.wts[t];
+    float kk = a.w_mc * (1.0f / (float)(a.A * N)) * wt;
+    float* o = a.dtraj + ((size_t)row * T + t) * 4;
+    o[0] += kk * gx; o[1] += kk * gy; o[3] += kk * gpsi;
+    if (a.loss) atomicAdd(&a.loss[(size_t)a.R + row], wt * lsum);
+  }
+}
+
 static float host_linspace(float lo, float hi, int n, int i) {
   if (n == 1) return lo;
   float step = (hi - lo) / (float)(n - 1);
@@ -304,10 +311,22 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
     a.lwise[i] = i < a.nl ? host_linspace(-0.5f, 0.5f, a.nl, i) : 0.f;
     a.wwise[i] = i < a.nw ? host_linspace(-0.5f, 0.5f, a.nw, i) : 0.f;
   }
+  {
+    // exp_weights: python-double powers cast to fp32, fp32 sum, fp32 divide (guidance_loss.py:607-608)
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) { a.wts[t] = (float)pow((double)g->decay_rate, (double)t); sum += a.wts[t]; }
+    for (int t = 0; t < T; ++t) a.wts[t] /= sum;
+    for (int t = T; t < CLD_MAX_T; ++t) a.wts[t] = 0.f;
+  }
   size_t smem = ((size_t)A * T * 4 + (size_t)A * 8 + T) * sizeof(float);
   CLD_CUDA_OK(h, cudaFuncSetAttribute(guidance_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   guidance_loss_grad_kernel<<<S * N, 256, smem, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
+  if (a.w_mc != 0.f) {
+    long long items = (long long)R * T;
+    guidance_map_grad_kernel<<<(unsigned)((items + 7) / 8), 256, 0, s>>>(a);
+    CLD_LAUNCH_OK(h, "guidance_map_grad_kernel");
+  }
   return 0;
 }
 

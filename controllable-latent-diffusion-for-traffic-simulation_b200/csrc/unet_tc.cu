@@ -22,7 +22,9 @@ constexpr int TC_UNIT = 8192;
 constexpr int TC_UNITS = 8;
 constexpr int TC_THREADS = 320;
 constexpr int TC_ARENA = 128 * 1024;
-constexpr int TC_SMEM = TC_ARENA + TC_UNITS * TC_UNIT + 4096 + 8192 + 8192 + 256 + 1024;
+constexpr int TB_LD = 260;            // padded row stride of the time-bias tile (bank-conflict free float4 reads)
+constexpr int TC_MAX_OPS = 32;
+constexpr int TC_MAX_KBS = 640;
 
 enum { EPI_GN_TB = 0, EPI_GN_RES_ACC = 1, EPI_GN_RES_ID = 2, EPI_BIAS = 3, EPI_UP = 4, EPI_GN = 5, EPI_OUT = 6 };
 
@@ -30,7 +32,7 @@ struct TcOp {
   int n, n_tiles;
   int tile_slot0[4], tile_lo[4], tile_hi[4];
   int sbo, slot_stride;
-  int kb_first, n_kb, units, kb_bytes;
+  int kb_first, n_kb, units, kb_bytes, w_first;
   int epi, cout, cpg, t_out, n_vt;
   int dst_off, dst_pitch;
   int par_off, tb_off, res_col;
@@ -39,10 +41,12 @@ struct TcOp {
   int load_skip, load_off, load_pitch, load_npanels, load_T;   // load_skip: -1 or byte offset in the skip buffer
   int dbg_stage;
 };
-struct TcKb { int a_base, shift, w_off, acc_col, nk16, first; };
+struct TcKb { int a_base, shift, w_off, acc_col, nk16, first; };   // host-side record; the device gets it packed in 32 bits
+constexpr int TC_SMEM = TC_ARENA + TC_UNITS * TC_UNIT + 4096 + TC_G * TB_LD * 4 + 8192 + 512 + TC_MAX_OPS * (int)sizeof(TcOp) +
+                        TC_MAX_KBS * 4 + 256 + 1024;
 
 struct TcParams {
-  const TcOp* ops; int n_ops; const TcKb* kbs;
+  const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
   const uint8_t* wblob; const float* par; const float* tbias; int tb_stride;
   const float* x; float* eps; int R, T, n_groups;
   uint8_t* skipbuf; int skip_stride;
@@ -53,7 +57,7 @@ struct TcParams {
 struct TcState {
   std::vector<TcOp> ops;
   std::vector<TcKb> kbs;
-  TcOp* d_ops = nullptr; TcKb* d_kbs = nullptr;
+  TcOp* d_ops = nullptr; uint32_t* d_kbs = nullptr;
   uint8_t* wblob = nullptr; size_t wblob_bytes = 0;
   float* par = nullptr; size_t par_floats = 0;
   uint8_t* skipbuf = nullptr; int skip_stride = 0; int grid = 0;
@@ -102,15 +106,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* arena = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = arena + TC_ARENA;
-  float* par_s = reinterpret_cast<float*>(ring + TC_UNITS * TC_UNIT);   // [4][256]
-  float* tb_s = par_s + 1024;                                           // [8][256]
-  float* st_s = tb_s + 2048;                                            // [4 quadrants][8][32][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(st_s + 2048);            // full[8], empty[8], act_ready, acc_ready
+  float* par_s = reinterpret_cast<float*>(ring + TC_UNITS * TC_UNIT);   // [4][256] bias, gamma, beta, res bias
+  float* tb_s = par_s + 1024;                                           // [8][TB_LD] time/cond bias per row
+  float* st_s = tb_s + TC_G * TB_LD;                                    // [4 quadrants][8][32][2] partial sums
+  float* mr_s = st_s + 2048;                                            // [8][8][2] mean, rstd per (row, group)
+  TcOp* ops_s = reinterpret_cast<TcOp*>(mr_s + 128);                    // [TC_MAX_OPS]
+  uint32_t* kbs_s = reinterpret_cast<uint32_t*>(ops_s + TC_MAX_OPS);    // [TC_MAX_KBS] packed k-block records
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kbs_s + TC_MAX_KBS);     // full[8], empty[8], act_ready, acc_ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8);
   const uint32_t bar_act = smem_u32(bars + 16), bar_acc = smem_u32(bars + 17);
 
+  for (int i = tid; i < P.n_ops * (int)(sizeof(TcOp) / 4); i += TC_THREADS)
+    reinterpret_cast<uint32_t*>(ops_s)[i] = reinterpret_cast<const uint32_t*>(P.ops)[i];
+  for (int i = tid; i < P.n_kbs; i += TC_THREADS) kbs_s[i] = P.kbs[i];
   if (tid == 0) {
     for (int i = 0; i < TC_UNITS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_act, 1);
@@ -130,8 +140,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       int pos = 0;
       for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
         for (int oi = 0; oi < P.n_ops; ++oi) {
-          const TcOp* o = P.ops + oi;
-          const int u = o->units, nkb = o->n_kb, bytes = o->kb_bytes, kb0 = o->kb_first;
+          const TcOp* o = ops_s + oi;
+          const int u = o->units, nkb = o->n_kb, bytes = o->kb_bytes;
+          const uint8_t* src = P.wblob + (size_t)(unsigned)o->w_first;
           for (int k = 0; k < nkb; ++k) {
             pos = (pos + u - 1) & ~(u - 1);
             if (pos + u > TC_UNITS) pos = 0;
@@ -140,8 +151,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
               par_empty ^= 1u << uu;
             }
             mbar_arrive_expect_tx(bar_full + 8 * pos, bytes);
-            bulk_g2s(smem_u32(ring + pos * TC_UNIT), P.wblob + (size_t)(unsigned)P.kbs[kb0 + k].w_off, bytes,
-                     bar_full + 8 * pos);
+            bulk_g2s(smem_u32(ring + pos * TC_UNIT), src, bytes, bar_full + 8 * pos);
+            src += (size_t)u * TC_UNIT;
             pos += u;
             if (pos >= TC_UNITS) pos = 0;
           }
@@ -154,32 +165,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       uint32_t par_full = 0, act_par = 0;
       int pos = 0;
       const uint32_t arena_u = smem_u32(arena), ring_u = smem_u32(ring);
+      const uint64_t b_const = make_desc_sw128(0, 1024);
       for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
         for (int oi = 0; oi < P.n_ops; ++oi) {
-          const TcOp* o = P.ops + oi;
+          const TcOp* o = ops_s + oi;
           const int u = o->units, nkb = o->n_kb, kb0 = o->kb_first, N = o->n, nt = o->n_tiles;
-          const uint32_t sbo = o->sbo, sstride = o->slot_stride;
           const uint32_t idesc = make_idesc_bf16(128, N);
-          int ts0[4];
-          for (int i = 0; i < 4; ++i) ts0[i] = o->tile_slot0[i];
+          const uint64_t a_const = make_desc_sw128(0, (uint32_t)o->sbo);
+          uint32_t ts_off[4];
+          for (int i = 0; i < 4; ++i) ts_off[i] = (arena_u >> 4) + (uint32_t)(o->tile_slot0[i] * o->slot_stride) * 64u;
           mbar_wait(bar_act, act_par);          // A operand of this op is in shared memory
           act_par ^= 1u;
           tc_fence_after();
           for (int k = 0; k < nkb; ++k) {
-            const TcKb kb = P.kbs[kb0 + k];
+            const uint32_t kb = kbs_s[kb0 + k];
+            // packed: [0,8) (a_base/1024 + shift) , [8,13) acc_col/16 , [13,16) nk16 , [16] first
+            const uint32_t a_slots = kb & 0xFFu, acc_col = ((kb >> 8) & 0x1Fu) << 4, nk16 = (kb >> 13) & 7u;
+            uint32_t accum = ((kb >> 16) & 1u) ^ 1u;
             pos = (pos + u - 1) & ~(u - 1);
             if (pos + u > TC_UNITS) pos = 0;
             mbar_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
             par_full ^= 1u << pos;
             tc_fence_after();
-            const uint32_t b_addr = ring_u + pos * TC_UNIT;
+            const uint64_t bd0 = b_const + ((ring_u + pos * TC_UNIT) >> 4);
             for (int mt = 0; mt < nt; ++mt) {
-              const uint32_t a_addr = arena_u + kb.a_base + (ts0[mt] * sstride + kb.shift) * 1024u;
-              const uint32_t d_addr = tmem_base + kb.acc_col + mt * N;
-              for (int kk = 0; kk < kb.nk16; ++kk) {
-                umma_bf16(d_addr, make_desc_sw128(a_addr + kk * 32, sbo), make_desc_sw128(b_addr + kk * 32, 1024), idesc,
-                          (kb.first && kk == 0) ? 0u : 1u);
-              }
+              const uint64_t ad0 = a_const + (ts_off[mt] + a_slots * 64u);
+              const uint32_t d_addr = tmem_base + acc_col + mt * N;
+              umma_bf16(d_addr, ad0, bd0, idesc, accum);
+              for (uint32_t kk = 1; kk < nk16; ++kk) umma_bf16(d_addr, ad0 + 2 * kk, bd0 + 2 * kk, idesc, 1u);
             }
             for (int uu = pos; uu < pos + u; ++uu) umma_commit(bar_empty + 8 * uu);
             pos += u;
@@ -216,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       if (etid == 0) mbar_arrive(bar_act);
 
       for (int oi = 0; oi < P.n_ops; ++oi) {
-        const TcOp* o = P.ops + oi;
+        const TcOp* o = ops_s + oi;
         const int epi = o->epi, N = o->n, cout = o->cout, nt = o->n_tiles, n_vt = o->n_vt, t_out = o->t_out;
         const int halfN = N >> 1;
         const bool is_gn = (epi == EPI_GN_TB || epi == EPI_GN_RES_ACC || epi == EPI_GN_RES_ID || epi == EPI_GN);
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           if (epi == EPI_GN_TB) {
             for (int i = etid; i < TC_G * cout; i += 256) {
               int bb = i / cout, c = i - bb * cout, r = g * TC_G + bb;
-              tb_s[bb * 256 + c] = (r < P.R) ? P.tbias[(size_t)r * P.tb_stride + o->tb_off + c] : 0.f;
+              tb_s[bb * TB_LD + c] = (r < P.R) ? P.tbias[(size_t)r * P.tb_stride + o->tb_off + c] : 0.f;
             }
           }
           if (is_gn) for (int i = etid; i < 2048; i += 256) st_s[i] = 0.f;
@@ -238,9 +251,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         tc_fence_after();
 
         // ---- pass 1: GroupNorm statistics over (time, channels of the group) per batch row
+        float2 mr[4];   // (mean, rstd) of the 4 groups inside this thread's column half
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mr[i] = make_float2(0.f, 1.f);
         if (is_gn) {
           for (int vt = 0; vt < n_vt; ++vt) {
-            const bool valid = sl >= o->tile_lo[vt] && sl < o->tile_hi[vt];
+            const int lo = o->tile_lo[vt], hi = o->tile_hi[vt];
+            if (q * 4 + 4 <= lo || q * 4 >= hi) continue;          // no valid row in this warp's 4 slots
+            const bool valid = sl >= lo && sl < hi;
             const int col0 = vt * N + half * halfN;
             for (int ch = 0; ch < halfN; ch += 32) {
               uint32_t r[32];
@@ -249,10 +267,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
               const int c0 = half * halfN + ch;
 #pragma unroll
               for (int sb = 0; sb < 4; ++sb) {
+                const float4 b0 = *reinterpret_cast<const float4*>(par_s + c0 + sb * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(par_s + c0 + sb * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float s = 0.f, ss = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  float v = __uint_as_float(r[sb * 8 + j]) + par_s[c0 + sb * 8 + j];
+                  float v = __uint_as_float(r[sb * 8 + j]) + bb[j];
                   s += v; ss = fmaf(v, v, ss);
                 }
                 if (!valid) { s = 0.f; ss = 0.f; }
@@ -260,18 +281,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
                 s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
                 if (lane < 8) {
                   // slot owned by (quadrant, b, sub-block): only this lane of this warp touches it -> deterministic
-                  float* sp = &st_s[((q * 8 + b) * 32 + (c0 >> 3) + sb) * 2];
-                  sp[0] += s; sp[1] += ss;
+                  float2* sp = reinterpret_cast<float2*>(&st_s[((q * 8 + b) * 32 + (c0 >> 3) + sb) * 2]);
+                  float2 cur = *sp;
+                  cur.x += s; cur.y += ss;
+                  *sp = cur;
                 }
               }
             }
           }
           epi_bar();
+          // (row, group) mean / rstd: 64 threads, fixed summation order
+          if (etid < 64) {
+            const int bb = etid >> 3, gg = etid & 7, sbpg = o->cpg >> 3;
+            float S = 0.f, SS = 0.f;
+            for (int k = 0; k < sbpg; ++k)
+              for (int qq = 0; qq < 4; ++qq) {
+                S += st_s[((qq * 8 + bb) * 32 + gg * sbpg + k) * 2];
+                SS += st_s[((qq * 8 + bb) * 32 + gg * sbpg + k) * 2 + 1];
+              }
+            const float inv_n = 1.0f / (float)(t_out * o->cpg);
+            const float mean = S * inv_n;
+            const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
+            mr_s[(bb * 8 + gg) * 2] = mean;
+            mr_s[(bb * 8 + gg) * 2 + 1] = rsqrtf(var + 1e-5f);
+          }
+          epi_bar();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mr[i] = *reinterpret_cast<const float2*>(&mr_s[(b * 8 + half * 4 + i) * 2]);
         }
 
         // ---- pass 2: normalise / activate / add, write the next A operand (or eps)
-        const int cpg = o->cpg, sbpg = cpg >> 3;
-        const float inv_n = is_gn ? 1.0f / (float)(t_out * cpg) : 0.f;
+        const int cpg_shift = 31 - __clz(o->cpg);
         const bool dbg = (o->dbg_stage >= 0 && o->dbg_stage == P.dbg_stage && P.dbg_out != nullptr);
         if (epi == EPI_OUT) {
           if (half == 0) {
@@ -290,9 +330,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         } else {
           for (int vt = 0; vt < n_vt; ++vt) {
             const int mt = vt % nt, ph = vt / nt;
-            const bool valid = sl >= o->tile_lo[mt] && sl < o->tile_hi[mt];
+            const int lo = o->tile_lo[mt], hi = o->tile_hi[mt];
+            if (q * 4 + 4 <= lo || q * 4 >= hi) continue;
+            const bool valid = sl >= lo && sl < hi;
             const int slot = (epi == EPI_UP) ? 2 * (o->tile_slot0[mt] + sl) + ph : o->tile_slot0[mt] + sl;
             const int col0 = vt * N + half * halfN;
+            uint8_t* rowp = arena + o->dst_off + (slot + 2) * 1024 + b * 128;
             for (int ch = 0; ch < halfN; ch += 32) {
               uint32_t r[32], rr[32];
               tmem_ld32(lane_addr + col0 + ch, r);
@@ -302,39 +345,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
 #pragma unroll
               for (int sb = 0; sb < 4; ++sb) {
                 const int c = c0 + sb * 8;
-                float mean = 0.f, rstd = 1.f;
-                if (is_gn) {
-                  const int gsb = ((c >> 3) / sbpg) * sbpg;
-                  float S = 0.f, SS = 0.f;
-                  for (int k = 0; k < sbpg; ++k) {
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                      S += st_s[((qq * 8 + b) * 32 + gsb + k) * 2];
-                      SS += st_s[((qq * 8 + b) * 32 + gsb + k) * 2 + 1];
-                    }
-                  }
-                  mean = S * inv_n;
-                  float var = fmaxf(SS * inv_n - mean * mean, 0.f);
-                  rstd = rsqrtf(var + 1e-5f);
-                }
-                uint8_t* dstp = arena + o->dst_off + (c >> 6) * o->dst_pitch + (slot + 2) * 1024 + b * 128 +
-                                ((((c >> 3) & 7) ^ b) << 4);
+                const float2 m2 = mr[((c >> cpg_shift) & 3)];
+                uint8_t* dstp = rowp + (c >> 6) * o->dst_pitch + ((((c >> 3) & 7) ^ b) << 4);
                 float y[8];
+                {
+                  const float4 b0 = *reinterpret_cast<const float4*>(par_s + c), b1 = *reinterpret_cast<const float4*>(par_s + c + 4);
+                  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float v = __uint_as_float(r[sb * 8 + j]) + par_s[c + j];
-                  if (is_gn) {
-                    v = (v - mean) * rstd * par_s[256 + c + j] + par_s[512 + c + j];
-                    v = mish_fast(v);
+                  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[sb * 8 + j]) + bb[j];
+                }
+                if (is_gn) {
+                  const float4 g0 = *reinterpret_cast<const float4*>(par_s + 256 + c), g1 = *reinterpret_cast<const float4*>(par_s + 256 + c + 4);
+                  const float4 e0 = *reinterpret_cast<const float4*>(par_s + 512 + c), e1 = *reinterpret_cast<const float4*>(par_s + 512 + c + 4);
+                  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                  const float bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float sc = m2.y * gm[j];
+                    y[j] = mish_fast(fmaf(y[j] - m2.x, sc, bt[j]));
                   }
-                  y[j] = v;
                 }
                 if (epi == EPI_GN_TB) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] += tb_s[b * 256 + c + j];
+                  const float4 t0 = *reinterpret_cast<const float4*>(tb_s + b * TB_LD + c), t1 = *reinterpret_cast<const float4*>(tb_s + b * TB_LD + c + 4);
+                  y[0] += t0.x; y[1] += t0.y; y[2] += t0.z; y[3] += t0.w; y[4] += t1.x; y[5] += t1.y; y[6] += t1.z; y[7] += t1.w;
                 } else if (epi == EPI_GN_RES_ACC) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(par_s + 768 + c), s1 = *reinterpret_cast<const float4*>(par_s + 768 + c + 4);
+                  const float rb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] += __uint_as_float(rr[sb * 8 + j]) + par_s[768 + c + j];
+                  for (int j = 0; j < 8; ++j) y[j] += __uint_as_float(rr[sb * 8 + j]) + rb[j];
                 } else if (epi == EPI_GN_RES_ID) {
                   if (valid) {
                     uint4 old = *reinterpret_cast<const uint4*>(dstp);
@@ -655,9 +693,24 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   for (const auto& j : B.pars)
     CLD_CUDA_OK(h, cudaMemcpyAsync(s->par + j.off, j.src, j.n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   if ((rc = alloc((void**)&s->d_ops, s->ops.size() * sizeof(TcOp)))) return rc;
-  if ((rc = alloc((void**)&s->d_kbs, s->kbs.size() * sizeof(TcKb)))) return rc;
+  if (s->ops.size() > (size_t)TC_MAX_OPS || s->kbs.size() > (size_t)TC_MAX_KBS)
+    return fail(h, CLD_ERR_UNSUPPORTED, "op table too large (%zu ops, %zu k-blocks)", s->ops.size(), s->kbs.size());
+  std::vector<uint32_t> packed(s->kbs.size());
+  for (TcOp& o : s->ops) {
+    o.w_first = s->kbs[o.kb_first].w_off;
+    for (int k = 0; k < o.n_kb; ++k) {
+      const TcKb& kb = s->kbs[o.kb_first + k];
+      if (kb.w_off != o.w_first + k * o.units * TC_UNIT || kb.a_base % 1024 || kb.acc_col % 16)
+        return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block record not packable");
+      uint32_t a_slots = (uint32_t)(kb.a_base / 1024 + kb.shift);
+      if (a_slots > 255u || kb.acc_col > 496 || kb.nk16 > 4) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block field overflow");
+      packed[o.kb_first + k] = a_slots | ((uint32_t)(kb.acc_col / 16) << 8) | ((uint32_t)kb.nk16 << 13) | ((uint32_t)kb.first << 16);
+    }
+  }
+  if ((rc = alloc((void**)&s->d_kbs, packed.size() * sizeof(uint32_t)))) return rc;
   CLD_CUDA_OK(h, cudaMemcpyAsync(s->d_ops, s->ops.data(), s->ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice, stream));
-  CLD_CUDA_OK(h, cudaMemcpyAsync(s->d_kbs, s->kbs.data(), s->kbs.size() * sizeof(TcKb), cudaMemcpyHostToDevice, stream));
+  CLD_CUDA_OK(h, cudaMemcpyAsync(s->d_kbs, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  CLD_CUDA_OK(h, cudaStreamSynchronize(stream));
   s->grid = h->num_sms;
   s->skip_stride = ((skip1_bytes + skip2_bytes + 1023) / 1024) * 1024;
   if ((rc = alloc((void**)&s->skipbuf, (size_t)s->grid * s->skip_stride))) return rc;
@@ -677,7 +730,7 @@ int tc_unet_forward(CldHandle* h, const float* x, const float* cond, const int64
   int rc;
   if ((rc = unet_time_bias(h, cond, t, R, stream))) return rc;
   TcParams P;
-  P.ops = s->d_ops; P.n_ops = (int)s->ops.size(); P.kbs = s->d_kbs; P.wblob = s->wblob; P.par = s->par;
+  P.ops = s->d_ops; P.n_ops = (int)s->ops.size(); P.kbs = s->d_kbs; P.n_kbs = (int)s->kbs.size(); P.wblob = s->wblob; P.par = s->par;
   P.tbias = h->tbias; P.tb_stride = h->unet.tb_total; P.x = x; P.eps = eps; P.R = R; P.T = h->cfg.horizon;
   P.n_groups = (R + TC_G - 1) / TC_G; P.skipbuf = s->skipbuf; P.skip_stride = s->skip_stride;
   const int T = h->cfg.horizon;
