@@ -72,11 +72,12 @@ struct TcState {
 // device helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float mish_fast(float x) {
-  // x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2)
-  float e = __expf(fminf(x, 20.f));
-  float n = e * (e + 2.f);
-  float y = x * __fdividef(n, n + 2.f);
-  return x > 20.f ? x : y;
+  // x * tanh(softplus(x)) = x * n / (n + 2) = x * (1 - 2 / (n + 2)),  n = e^x (e^x + 2); inf-safe (1/inf = 0)
+  float e = __expf(x);
+  float d = fmaf(e, e + 2.f, 2.f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return x * fmaf(r, -2.f, 1.f);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -104,7 +105,8 @@ __device__ __forceinline__ void zero_halos(uint8_t* arena, int offB, int pitch, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* arena = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* arena = smem_raw;   // kept as a __shared__-space pointer so that ptxas emits LDS/STS, not generic LD/ST
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();   // the swizzle atoms need 1024-byte alignment
   uint8_t* ring = arena + TC_ARENA;
   float* par_s = reinterpret_cast<float*>(ring + TC_UNITS * TC_UNIT);   // [4][256] bias, gamma, beta, res bias
   float* tb_s = par_s + 1024;                                           // [8][TB_LD] time/cond bias per row
