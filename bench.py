@@ -201,6 +201,7 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     x_init = torch.randn(R, T, 4, device=dev, generator=gen)
     noise = torch.randn(K_d, R, T, 4, device=dev, generator=gen) if a.sampler == "ddpm" else None
+    from cld_b200.distributed import gather_results
     gathered = None
     if world > 1:
         gathered = torch.empty(world * R, T * 6 + T + 1, device=dev)
@@ -210,8 +211,8 @@ def main():
                  agents_per_scene=A)
         if world > 1:
             # the path's one exchange: trajectories + indicator flags + collision counts of every rank
-            pack = torch.cat([out["traj"].reshape(R, -1), out["offroad"].float(), out["coll"][:, None]], dim=1)
-            dist.all_gather_into_tensor(gathered, pack)
+            out["all_traj"], out["all_offroad"], out["all_coll"] = gather_results(
+                out["traj"], out["offroad"], out["coll"], out=gathered)
         return out
 
     def barrier():

@@ -144,6 +144,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   for (int i = 0; i < 7 && !rc; ++i) rc = dev_alloc(h, &h->act[i], MR * ae);
   if (!rc) rc = dev_alloc(h, &h->tcm, MR * (cfg->base_dim + cfg->cond_dim));
   if (!rc) rc = dev_alloc(h, &h->tbias, MR * tb_total);
+  if (!rc) rc = dev_alloc(h, &h->tvec, tb_total);
   if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * MR * 5 * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_act, MR * T * 2);
   if (!rc) rc = dev_alloc(h, &h->ws_traj, MR * T * 6);
@@ -471,15 +472,23 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     const float* currc = curr ? curr + (size_t)r0 * 4 : nullptr;
     float* x = h->ws_x;
     CLD_CUDA_OK(h, cudaMemcpyAsync(x, x_init + r0 * row_e, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // bf16 path: the cond half of every block's time/cond projection is step-invariant -> once per chunk
+    const bool split_bias = (c.precision == CLD_PREC_BF16);
+    if (split_bias && (rc = unet_cond_bias(h, condc, Rc, s))) return rc;
     for (int k = 0; k < K; ++k) {
       const int i = steps[K - 1 - k];
       const int i_next = (k + 1 < K) ? steps[K - 2 - k] : -1;
       const float* nz = noises ? noises + ((size_t)k * R + r0) * row_e : nullptr;
       if (!noises && seed == 0 && sampler == CLD_SAMPLER_DDPM && i != 0)
         return fail(h, CLD_ERR_ARG, "either a noise tensor or a non-zero seed is required");
-      if ((rc = fill_t(h, h->ws_t, i, Rc, s))) return rc;
       if ((rc = prof_begin(h, 0, s))) return rc;
-      if ((rc = unet_dispatch(h, x, condc, h->ws_t, h->ws_eps, Rc, s))) return rc;
+      if (split_bias) {
+        if ((rc = unet_time_vec(h, i, s))) return rc;
+        if ((rc = tc_unet_forward_prepared(h, x, h->ws_eps, Rc, s))) return rc;
+      } else {
+        if ((rc = fill_t(h, h->ws_t, i, Rc, s))) return rc;
+        if ((rc = unet_dispatch(h, x, condc, h->ws_t, h->ws_eps, Rc, s))) return rc;
+      }
       if ((rc = prof_end(h, s))) return rc;
       const bool guided = (g != nullptr) && i != 0;
       const uint64_t seq = ((uint64_t)k << 32) ^ (uint64_t)r0;

@@ -84,6 +84,7 @@ struct CldHandle {
   size_t act_elems = 0;            // per-row elements of one activation buffer
   float* tcm = nullptr;            // [max_rows, 32+cond] Mish([t_emb, cond])
   float* tbias = nullptr;          // [max_rows, tb_total]
+  float* tvec = nullptr;           // [tb_total] per-step time part of the bias (sampler: uniform t)
   // guidance / decode workspace
   float* stash = nullptr;          // LSTM forward stash [2][T][max_rows][5*H]
   float* ws_act = nullptr;         // [max_rows, T, 2]
@@ -132,6 +133,8 @@ int prof_end(CldHandle* h, cudaStream_t s);
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps,
                       int R, cudaStream_t s);
 int unet_stage_elems(const CldHandle* h, int stage);
+int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s);   // -> h->tbias (cond part + bias)
+int unet_time_vec(CldHandle* h, int t, cudaStream_t s);                        // -> h->tvec
 // ---- kernels_step.cu
 int posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise, uint64_t seed,
                    uint64_t seq, int t, int t_next, int sampler, float* x_out, float* mean_out, int R,

@@ -248,6 +248,70 @@ int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cud
   return launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s);
 }
 
+// ---- split form used by the sampler (every row shares the same step index t):
+//   tbias[r, c] = cond_bias[r, c] + time_vec[c]
+//   cond_bias = Mish(cond) @ Wtb[d:, :] + btb      (step-invariant: computed once per cld_sample call)
+//   time_vec  = Mish(t_emb(t)) @ Wtb[:d, :]        (one vector per step, shared by all rows)
+// Linear(Mish([t_emb, cond])) of temporal.py:21-25 splits exactly because Mish is elementwise.
+__global__ void __launch_bounds__(256) cond_mish_kernel(const float* __restrict__ cond, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = mish_f(cond[i]);
+}
+
+__global__ void __launch_bounds__(256) time_vec_kernel(int t, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       const float* __restrict__ freqs, const float* __restrict__ tb_w,
+                                                       float* __restrict__ tvec, int d, int tb_total) {
+  __shared__ float emb[64];
+  __shared__ float hid[256];
+  __shared__ float tm[64];
+  const int tid = threadIdx.x;
+  const float tv = (float)t;
+  const int half = d >> 1;
+  if (tid < d) {
+    float a = tv * freqs[tid % half];
+    emb[tid] = (tid < half) ? sinf(a) : cosf(a);
+  }
+  __syncthreads();
+  for (int o = tid; o < 4 * d; o += blockDim.x) {
+    float acc = b1[o];
+    for (int k = 0; k < d; ++k) acc = fmaf(w1[o * d + k], emb[k], acc);
+    hid[o] = mish_f(acc);
+  }
+  __syncthreads();
+  if (tid < d) {
+    float acc = b2[tid];
+    for (int k = 0; k < 4 * d; ++k) acc = fmaf(w2[tid * 4 * d + k], hid[k], acc);
+    tm[tid] = mish_f(acc);
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + tid;
+  if (c < tb_total) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(tb_w[(size_t)k * tb_total + c], tm[k], acc);
+    tvec[c] = acc;
+  }
+}
+
+int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s) {
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  const size_t n = (size_t)R * c.cond_dim;
+  cond_mish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cond, h->tcm, n);
+  CLD_LAUNCH_OK(h, "cond_mish_kernel");
+  ConvW tb; tb.w = u.tb_w + (size_t)c.base_dim * u.tb_total; tb.b = u.tb_b; tb.cin = c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;
+  return launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s);
+}
+
+int unet_time_vec(CldHandle* h, int t, cudaStream_t s) {
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  time_vec_kernel<<<(u.tb_total + 255) / 256, 256, 0, s>>>(t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, u.tb_w, h->tvec,
+                                                            c.base_dim, u.tb_total);
+  CLD_LAUNCH_OK(h, "time_vec_kernel");
+  return 0;
+}
+
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R,
                       cudaStream_t s) {
   const UnetW& u = h->unet;

@@ -47,7 +47,7 @@ constexpr int TC_SMEM = TC_ARENA + TC_UNITS * TC_UNIT + 4096 + TC_G * TB_LD * 4 
 
 struct TcParams {
   const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
-  const uint8_t* wblob; const float* par; const float* tbias; int tb_stride;
+  const uint8_t* wblob; const float* par; const float* tbias; const float* tvec; int tb_stride;
   const float* x; float* eps; int R, T, n_groups;
   uint8_t* skipbuf; int skip_stride;
   int zero0_pitch, zero0_npanels, zero0_offB;
@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           if (epi == EPI_GN_TB) {
             for (int i = etid; i < TC_G * cout; i += 256) {
               int bb = i / cout, c = i - bb * cout, r = g * TC_G + bb;
-              tb_s[bb * TB_LD + c] = (r < P.R) ? P.tbias[(size_t)r * P.tb_stride + o->tb_off + c] : 0.f;
+              float tv = (r < P.R) ? P.tbias[(size_t)r * P.tb_stride + o->tb_off + c] : 0.f;
+              if (P.tvec) tv += P.tvec[o->tb_off + c];
+              tb_s[bb * TB_LD + c] = tv;
             }
           }
           if (is_gn) for (int i = etid; i < 2048; i += 256) st_s[i] = 0.f;
@@ -726,12 +728,26 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
 // time / cond projection shared with the fp32 path (kernels_unet_fp32.cu)
 int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s);
 
+static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const float* tvec, cudaStream_t stream);
+
 int tc_unet_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R, cudaStream_t stream) {
   TcState* s = st_of(h);
   if (!s || !s->ready) return fail(h, CLD_ERR_STATE, "bf16 denoiser weights not packed");
   int rc;
   if ((rc = unet_time_bias(h, cond, t, R, stream))) return rc;
+  return tc_launch(h, x, eps, R, nullptr, stream);
+}
+
+int tc_unet_forward_prepared(CldHandle* h, const float* x, float* eps, int R, cudaStream_t stream) {
+  TcState* s = st_of(h);
+  if (!s || !s->ready) return fail(h, CLD_ERR_STATE, "bf16 denoiser weights not packed");
+  return tc_launch(h, x, eps, R, h->tvec, stream);
+}
+
+static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const float* tvec, cudaStream_t stream) {
+  TcState* s = st_of(h);
   TcParams P;
+  P.tvec = tvec;
   P.ops = s->d_ops; P.n_ops = (int)s->ops.size(); P.kbs = s->d_kbs; P.n_kbs = (int)s->kbs.size(); P.wblob = s->wblob; P.par = s->par;
   P.tbias = h->tbias; P.tb_stride = h->unet.tb_total; P.x = x; P.eps = eps; P.R = R; P.T = h->cfg.horizon;
   P.n_groups = (R + TC_G - 1) / TC_G; P.skipbuf = s->skipbuf; P.skip_stride = s->skip_stride;
