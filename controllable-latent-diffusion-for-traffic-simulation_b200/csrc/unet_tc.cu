@@ -147,6 +147,7 @@ struct EpiCtx {
   uint8_t* arena; const float* par; const float* tb_s; float2* st; uint32_t lane_addr;
   int q, cq, lane, etid, g;
   uint8_t* skip_cta; float* dbg_out; int dbg_stage; int R;
+  long long* tl;   // profiling build only: per-item phase timestamps
 };
 
 // store 8 consecutive channels of one (slot, batch row) as bf16: next layer's A operand (+ skip buffer, + debug tap)
@@ -187,18 +188,49 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(uint8_t* smem, const float* par) 
   const TcShared* gs = reinterpret_cast<const TcShared*>(smem + SM_GLOB);
   cx.lane_addr = gs->tmem_base + ((uint32_t)(cx.q * 32) << 16);
   cx.skip_cta = gs->skip_cta;
-  cx.g = 0; cx.dbg_out = nullptr; cx.dbg_stage = -1; cx.R = 0;
+  cx.g = 0; cx.dbg_out = nullptr; cx.dbg_stage = -1; cx.R = 0; cx.tl = nullptr;
   return cx;
 }
 
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2): half the issue slots of the scalar forms
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t pack_bf16_2(uint64_t p) { float a, b; upk2(p, a, b); return pack_bf16(a, b); }
+
+// Mish on a packed pair whose input is ALREADY scaled by log2(e):  t' = log2e * x  ->  x * tanh(softplus(x))
+//   e = 2^t' = exp(x); n = e (e + 2); tanh(softplus(x)) = n / (n + 2) = 1 - 2 / (n + 2); x = ln2 * t'
+__device__ __forceinline__ uint64_t mish2_log2(uint64_t t) {
+  float tx, ty;
+  upk2(t, tx, ty);
+  const uint64_t e = pk2(ex2_ftz(tx), ex2_ftz(ty));
+  const uint64_t two = pk2(2.f, 2.f);
+  const uint64_t d = fma2(e, add2(e, two), two);
+  float dx, dy;
+  upk2(d, dx, dy);
+  const uint64_t w = fma2(pk2(rcp_ftz(dx), rcp_ftz(dy)), pk2(-1.3862943611198906f, -1.3862943611198906f),
+                          pk2(0.6931471805599453f, 0.6931471805599453f));
+  return mul2(t, w);
+}
+
+// GroupNorm + Mish (+ time bias | + residual) for ONE GroupNorm group (cpg channels) of one half of the op, over the
+// warp's 32 GEMM rows.  The thread's values are `nch` chunks of 8 channels held in registers between the statistics
+// pass and the normalise pass; chunk k belongs to m-tile k / cpt and covers channels c0 + (k % cpt) * 8.
+// (n_vt, cpg) = (4,8) (2,16) (1,32): 4 chunks; (2,8) (1,16): 2.  gamma / beta arrive pre-scaled by log2(e).
+#define TC_SCHED_FENCE() asm volatile("" ::: "memory")
 __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
   const int EPI = o->epi;
-  // generic in the tile class: the thread's values are `nch` chunks of 8 channels; chunk k belongs to m-tile
-  // k / cpt and covers channels c0 + (k % cpt) * 8.  (n_vt, cpg) = (4,8) (2,16) (1,32): 4 chunks; (2,8) (1,16): 2.
   const int q = cx.q, lane = cx.lane, b = lane & 7, sl = q * 4 + (lane >> 3);
   const int N = o->n, cpg = o->cpg, cpt = cpg >> 3, nch = o->n_vt * cpt;
   const int c0 = (h * 4 + cx.cq) * cpg;
-  uint32_t v[4][8];
+  const int dst_pitch = o->dst_pitch, save_skip = o->save_skip, t_out = o->t_out;
+  uint8_t* const dst_row = cx.arena + o->dst_off + 2048 + b * 128;     // + slot * 1024 + panel * pitch + swizzled chunk
+  uint64_t v[4][4];
   uint32_t actm = 0, validm = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -207,46 +239,53 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
       const int lo = o->tile_lo[vt], hi = o->tile_hi[vt];
       if (!(q * 4 + 4 <= lo || q * 4 >= hi)) {           // warp-uniform: some row of this warp is valid
         actm |= 1u << k;
-        tmem_ld8(cx.lane_addr + vt * N + c0 + (k & (cpt - 1)) * 8, v[k]);
+        uint32_t r[8];
+        tmem_ld8(cx.lane_addr + vt * N + c0 + (k & (cpt - 1)) * 8, r);
+        v[k][0] = pk2u(r[0], r[1]); v[k][1] = pk2u(r[2], r[3]); v[k][2] = pk2u(r[4], r[5]); v[k][3] = pk2u(r[6], r[7]);
       }
       if (sl >= lo && sl < hi) validm |= 1u << k;
     }
   }
   tmem_wait_ld();
+  if (cx.tl) cx.tl[0] = clock64();
   // ---- pass 1: conv bias, statistics over (time, channels of the group) per batch row
-  float s = 0.f, ss = 0.f;
+  uint64_t s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (!((actm >> k) & 1u)) continue;
     const int c = c0 + (k & (cpt - 1)) * 8;
-    const bool valid = (validm >> k) & 1u;
-#pragma unroll
-    for (int j4 = 0; j4 < 2; ++j4) {
-      const float4 bb = *reinterpret_cast<const float4*>(cx.par + c + j4 * 4);
-      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float u = __uint_as_float(v[k][j4 * 4 + j]) + bv[j];
-        v[k][j4 * 4 + j] = __float_as_uint(u);
-        float uu = valid ? u : 0.f;
-        s += uu; ss = fmaf(uu, uu, ss);
-      }
+    const float4 b0 = *reinterpret_cast<const float4*>(cx.par + c), b1 = *reinterpret_cast<const float4*>(cx.par + c + 4);
+    const uint64_t u0 = add2(v[k][0], pk2(b0.x, b0.y)), u1 = add2(v[k][1], pk2(b0.z, b0.w));
+    const uint64_t u2 = add2(v[k][2], pk2(b1.x, b1.y)), u3 = add2(v[k][3], pk2(b1.z, b1.w));
+    v[k][0] = u0; v[k][1] = u1; v[k][2] = u2; v[k][3] = u3;
+    if ((validm >> k) & 1u) {
+      s2 = add2(s2, add2(add2(u0, u1), add2(u2, u3)));
+      ss2 = add2(ss2, fma2(u0, u0, fma2(u1, u1, fma2(u2, u2, mul2(u3, u3)))));
     }
     TC_SCHED_FENCE();
+  }
+  float s, ss;
+  {
+    float a0, a1, q0, q1;
+    upk2(s2, a0, a1); upk2(ss2, q0, q1);
+    s = a0 + a1; ss = q0 + q1;
   }
   s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
   s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
   float2* st = cx.st + (h & 1) * 128 + cx.cq * 32;          // [cq][quadrant][batch row]
   if (lane < 8) st[q * 8 + b] = make_float2(s, ss);
+  if (cx.tl) cx.tl[1] = clock64();
   named_bar(2 + cx.cq, 128);                                // the 4 quadrant warps of this group
-  float mean, rstd;
+  if (cx.tl) cx.tl[2] = clock64();
+  uint64_t rstd2, nmean2;
   {
     const float2 p0 = st[b], p1 = st[8 + b], p2 = st[16 + b], p3 = st[24 + b];   // fixed order: deterministic
     const float S = ((p0.x + p1.x) + p2.x) + p3.x, SS = ((p0.y + p1.y) + p2.y) + p3.y;
-    const float inv_n = 1.0f / (float)(o->t_out * cpg);
-    mean = S * inv_n;
+    const float inv_n = __frcp_rn((float)(t_out * cpg));
+    const float mean = S * inv_n;
     const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
-    rstd = rsqrtf(var + 1e-5f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    rstd2 = pk2(rstd, rstd); nmean2 = pk2(-mean, -mean);
   }
   // ---- pass 2: normalise / activate / add, write the next A operand
 #pragma unroll
@@ -256,43 +295,44 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
     const int c = c0 + (k & (cpt - 1)) * 8;
     const bool valid = (validm >> k) & 1u;
     const int slot = o->tile_slot0[vt] + sl;
-    float y[8];
+    uint64_t y[4];
+    {
+      const float4 g0 = *reinterpret_cast<const float4*>(cx.par + 256 + c), g1 = *reinterpret_cast<const float4*>(cx.par + 256 + c + 4);
+      const float4 e0 = *reinterpret_cast<const float4*>(cx.par + 512 + c), e1 = *reinterpret_cast<const float4*>(cx.par + 512 + c + 4);
+      const uint64_t gp[4] = {pk2(g0.x, g0.y), pk2(g0.z, g0.w), pk2(g1.x, g1.y), pk2(g1.z, g1.w)};
+      const uint64_t ep[4] = {pk2(e0.x, e0.y), pk2(e0.z, e0.w), pk2(e1.x, e1.y), pk2(e1.z, e1.w)};
 #pragma unroll
-    for (int j4 = 0; j4 < 2; ++j4) {
-      const float4 gm = *reinterpret_cast<const float4*>(cx.par + 256 + c + j4 * 4);
-      const float4 bt = *reinterpret_cast<const float4*>(cx.par + 512 + c + j4 * 4);
-      y[j4 * 4 + 0] = mish_fast(fmaf(__uint_as_float(v[k][j4 * 4 + 0]) - mean, rstd * gm.x, bt.x));
-      y[j4 * 4 + 1] = mish_fast(fmaf(__uint_as_float(v[k][j4 * 4 + 1]) - mean, rstd * gm.y, bt.y));
-      y[j4 * 4 + 2] = mish_fast(fmaf(__uint_as_float(v[k][j4 * 4 + 2]) - mean, rstd * gm.z, bt.z));
-      y[j4 * 4 + 3] = mish_fast(fmaf(__uint_as_float(v[k][j4 * 4 + 3]) - mean, rstd * gm.w, bt.w));
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t A = mul2(rstd2, gp[j]);
+        const uint64_t B = fma2(nmean2, A, ep[j]);
+        y[j] = mish2_log2(fma2(v[k][j], A, B));
+      }
     }
     if (EPI == EPI_GN_TB) {
-#pragma unroll
-      for (int j4 = 0; j4 < 2; ++j4) {
-        const float4 t0 = *reinterpret_cast<const float4*>(cx.tb_s + b * TB_LD + c + j4 * 4);
-        const float4 u0 = *reinterpret_cast<const float4*>(cx.par + 1024 + c + j4 * 4);
-        y[j4 * 4 + 0] += t0.x + u0.x; y[j4 * 4 + 1] += t0.y + u0.y; y[j4 * 4 + 2] += t0.z + u0.z; y[j4 * 4 + 3] += t0.w + u0.w;
-      }
+      const float4 t0 = *reinterpret_cast<const float4*>(cx.tb_s + b * TB_LD + c), t1 = *reinterpret_cast<const float4*>(cx.tb_s + b * TB_LD + c + 4);
+      y[0] = add2(y[0], pk2(t0.x, t0.y)); y[1] = add2(y[1], pk2(t0.z, t0.w));
+      y[2] = add2(y[2], pk2(t1.x, t1.y)); y[3] = add2(y[3], pk2(t1.z, t1.w));
     } else if (EPI == EPI_GN_RES_ACC) {
       uint32_t rr[8];
       tmem_ld8(cx.lane_addr + TC_RES_COL + vt * N + c, rr);
       tmem_wait_ld();
-#pragma unroll
-      for (int j4 = 0; j4 < 2; ++j4) {
-        const float4 s0 = *reinterpret_cast<const float4*>(cx.par + 768 + c + j4 * 4);
-        y[j4 * 4 + 0] += __uint_as_float(rr[j4 * 4 + 0]) + s0.x; y[j4 * 4 + 1] += __uint_as_float(rr[j4 * 4 + 1]) + s0.y;
-        y[j4 * 4 + 2] += __uint_as_float(rr[j4 * 4 + 2]) + s0.z; y[j4 * 4 + 3] += __uint_as_float(rr[j4 * 4 + 3]) + s0.w;
-      }
-    } else if (EPI == EPI_GN_RES_ID) {
-      if (valid) {
-        const uint4 old = *reinterpret_cast<const uint4*>(cx.arena + o->dst_off + (slot + 2) * 1024 + b * 128 +
-                                                          (c >> 6) * o->dst_pitch + ((((c >> 3) & 7) ^ b) << 4));
-        float2 f0 = unpack_bf16(old.x), f1 = unpack_bf16(old.y), f2 = unpack_bf16(old.z), f3 = unpack_bf16(old.w);
-        y[0] += f0.x; y[1] += f0.y; y[2] += f1.x; y[3] += f1.y;
-        y[4] += f2.x; y[5] += f2.y; y[6] += f3.x; y[7] += f3.y;
-      }
+      const float4 s0 = *reinterpret_cast<const float4*>(cx.par + 768 + c), s1 = *reinterpret_cast<const float4*>(cx.par + 768 + c + 4);
+      y[0] = add2(y[0], add2(pk2u(rr[0], rr[1]), pk2(s0.x, s0.y))); y[1] = add2(y[1], add2(pk2u(rr[2], rr[3]), pk2(s0.z, s0.w)));
+      y[2] = add2(y[2], add2(pk2u(rr[4], rr[5]), pk2(s1.x, s1.y))); y[3] = add2(y[3], add2(pk2u(rr[6], rr[7]), pk2(s1.z, s1.w)));
     }
-    store_chunk(o, cx, y, c, slot, b, valid);
+    if (valid) {
+      const int sw = ((((c >> 3) & 7) ^ b) << 4);
+      uint8_t* dp = dst_row + slot * 1024 + (c >> 6) * dst_pitch + sw;
+      if (EPI == EPI_GN_RES_ID) {
+        const uint4 old = *reinterpret_cast<const uint4*>(dp);
+        y[0] = add2(y[0], pk2u(old.x << 16, old.x & 0xffff0000u)); y[1] = add2(y[1], pk2u(old.y << 16, old.y & 0xffff0000u));
+        y[2] = add2(y[2], pk2u(old.z << 16, old.z & 0xffff0000u)); y[3] = add2(y[3], pk2u(old.w << 16, old.w & 0xffff0000u));
+      }
+      const uint4 pk = make_uint4(pack_bf16_2(y[0]), pack_bf16_2(y[1]), pack_bf16_2(y[2]), pack_bf16_2(y[3]));
+      *reinterpret_cast<uint4*>(dp) = pk;
+      if (save_skip >= 0)
+        *reinterpret_cast<uint4*>(cx.skip_cta + save_skip + ((size_t)(c >> 6) * t_out + slot) * 1024 + b * 128 + sw) = pk;
+    }
     TC_SCHED_FENCE();
   }
 }
@@ -365,6 +405,7 @@ __device__ __forceinline__ void prefetch_params(const TcOp* o, const TcParams& P
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+template <bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* arena = smem_raw;   // kept as a __shared__-space pointer so that ptxas emits LDS/STS, not generic LD/ST
@@ -409,10 +450,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       for (int k = 0; k < P.n_kbs; ++k) {
         const uint32_t kb = kbs_s[k];
         const uint32_t bytes = ((kb >> 14) & 0x3Fu) * (8u * 128u);
-        const long long tw0 = P.prof ? clock64() : 0;
+        const long long tw0 = PROF ? clock64() : 0;
         mbar_wait(bar_empty + 8 * pos, ((par_empty >> pos) & 1u) ^ 1u);
         par_empty ^= 1u << pos;
-        if (P.prof) t_empty += clock64() - tw0;
+        if (PROF) t_empty += clock64() - tw0;
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * pos, bytes);
           bulk_g2s(smem_u32(ring + pos * TC_SLOT), src, bytes, bar_full + 8 * pos);
@@ -422,19 +463,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         pos = (pos + 1) & (TC_SLOTS - 1);
       }
     }
-    if (P.prof && lane == 0) { P.prof[blockIdx.x * 8 + 0] = t_empty; }
+    if (PROF && lane == 0) { P.prof[blockIdx.x * 8 + 0] = t_empty; }
   } else if (warp == TC_EW + 1) {
     // ===================== MMA issuer =====================
     // all lanes walk the (warp-uniform) loop so that descriptors are computed on the uniform datapath; one elected
     // lane issues the tcgen05 instructions
     uint32_t par_full = 0, opn = 0;
     int pos = 0;
+    bool ready = false;
+    uint32_t kb_next = kbs_s[0];
     long long t_full = 0, t_act = 0, t_issue = 0, t_commit = 0;
-    const long long t_start = P.prof ? clock64() : 0;
+    const long long t_start = PROF ? clock64() : 0;
     const uint32_t arena_u = smem_u32(arena), ring_u = smem_u32(ring);
     const uint64_t b_const = make_desc_sw128(0, 1024);
     constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
+      kb_next = kbs_s[0];
       for (int oi = 0; oi < P.n_ops; ++oi, ++opn) {
         const TcOp* o = ops_s + oi;
         const int N = o->n, nt = o->n_tiles, flags = o->flags;
@@ -447,18 +491,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         int kbi = o->kb_first;
         auto issue = [&](int count) {
           for (int k = 0; k < count; ++k, ++kbi) {
-            const uint32_t kb = kbs_s[kbi];
+            const uint32_t kb = kb_next;
+            kb_next = kbs_s[kbi + 1];                         // next record (the table has slack past the end)
             const uint32_t a_slots = kb & 0xFFu, acc_col = ((kb >> 8) & 0x3Fu) << 3, nk16 = (kb >> 20) & 7u;
             const uint32_t idesc = IDESC0 | (((kb >> 14) & 0x3Fu) << 17);
             const uint32_t accum = ((kb >> 23) & 1u) ^ 1u;
-            const long long tw0 = P.prof ? clock64() : 0;
-            mbar_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
-            if (P.prof) t_full += clock64() - tw0;
+            const long long tw0 = PROF ? clock64() : 0;
+            while (!ready) ready = mbar_try_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
+            if (PROF) t_full += clock64() - tw0;
             par_full ^= 1u << pos;
             tc_fence_after();
+            // probe the next slot now; the answer is consumed after this k-block's MMAs have been issued
+            const int pos_n = (pos + 1) & (TC_SLOTS - 1);
+            const bool ready_n = mbar_try_wait(bar_full + 8 * pos_n, (par_full >> pos_n) & 1u);
             const uint64_t bd0 = b_const + ((ring_u + pos * TC_SLOT) >> 4);
             const uint64_t a_kb = a_const + a_slots * 64u;
-            const long long ti0 = P.prof ? clock64() : 0;
+            const long long ti0 = PROF ? clock64() : 0;
             if (elect_one()) {
 #pragma unroll
               for (int mt = 0; mt < 4; ++mt) {
@@ -476,8 +524,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
               umma_commit(bar_empty + 8 * pos);
             }
             __syncwarp();
-            if (P.prof) t_issue += clock64() - ti0;
-            pos = (pos + 1) & (TC_SLOTS - 1);
+            if (PROF) t_issue += clock64() - ti0;
+            pos = pos_n;
+            ready = ready_n;
           }
         };
         auto commit = [&](uint32_t bar) {
@@ -485,16 +534,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           __syncwarp();
         };
         const uint32_t ph = opn & 1u;
-        long long tw1 = P.prof ? clock64() : 0;
+        long long* tl = (PROF && blockIdx.x == 0 && g == blockIdx.x && lane == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
+        if (tl) tl[0] = clock64();
+        long long tw1 = PROF ? clock64() : 0;
         mbar_wait(bar_act, ph);                                  // inputs written by half 0 of the previous epilogue
         if (!(flags & F_SPLIT_K)) mbar_wait(bar_act + 8, ph);
-        if (P.prof) t_act += clock64() - tw1;
+        if (PROF) t_act += clock64() - tw1;
+        if (tl) tl[1] = clock64();
         tc_fence_after();
         issue(o->n_g0);
         if (flags & F_SPLIT_K) {
-          tw1 = P.prof ? clock64() : 0;
+          tw1 = PROF ? clock64() : 0;
           mbar_wait(bar_act + 8, ph);
-          if (P.prof) t_act += clock64() - tw1;
+          if (PROF) t_act += clock64() - tw1;
           tc_fence_after();
         }
         issue(o->n_g1);
@@ -502,9 +554,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         issue(o->n_g2);
         if (!(flags & F_COMMIT_SPLIT)) commit(bar_acc);
         commit(bar_acc + 8);
+        if (tl) tl[2] = clock64();
       }
     }
-    if (P.prof && lane == 0) { P.prof[blockIdx.x * 8 + 2] = t_full; P.prof[blockIdx.x * 8 + 3] = t_act; P.prof[blockIdx.x * 8 + 4] = clock64() - t_start; P.prof[blockIdx.x * 8 + 7] = t_issue; P.prof[blockIdx.x * 8 + 1] = t_commit; }
+    if (PROF && lane == 0) { P.prof[blockIdx.x * 8 + 2] = t_full; P.prof[blockIdx.x * 8 + 3] = t_act; P.prof[blockIdx.x * 8 + 4] = clock64() - t_start; P.prof[blockIdx.x * 8 + 7] = t_issue; P.prof[blockIdx.x * 8 + 1] = t_commit; }
   } else {
     // ===================== epilogue warps =====================
     EpiCtx cx;
@@ -512,11 +565,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
     cx.arena = arena; cx.tb_s = tb_s; cx.st = st_s;
     cx.lane_addr = tmem_base + ((uint32_t)(cx.q * 32) << 16);
     cx.skip_cta = P.skipbuf + (size_t)blockIdx.x * P.skip_stride;
-    cx.dbg_out = P.dbg_out; cx.dbg_stage = P.dbg_stage; cx.R = P.R;
+    cx.dbg_out = P.dbg_out; cx.dbg_stage = P.dbg_stage; cx.R = P.R; cx.tl = nullptr;
     const int etid = cx.etid;
     uint32_t opn = 0;
     long long t_acc = 0;
-    const long long t_start = P.prof ? clock64() : 0;
+    const long long t_start = PROF ? clock64() : 0;
     for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
       cx.g = g;
       // ---- stage the latent x [8,T,4] fp32 as bf16 hi/lo channels 0..7 of panel 0 (region A, level 0)
@@ -541,15 +594,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
         const TcOp* o = ops_s + oi;
         cp_async_wait_all();
         epi_bar();                                   // parameters of this op are visible to every epilogue thread
+        if (o->epi == EPI_GN_TB) {
+          // fold the per-step time vector into the per-row cond bias: tb_s[b][c] += tvec[c]
+          const float* tv = par_s + (oi & 1) * (PAR_ROWS * 256) + 1024;
+          for (int i = etid; i < TC_G * o->cout; i += TC_ETHREADS) {
+            const int bb = i / o->cout, c = i - bb * o->cout;
+            tb_s[bb * TB_LD + c] += tv[c];
+          }
+          epi_bar();
+        }
         if (oi + 1 < P.n_ops) prefetch_params(o + 1, P, par_s + ((oi + 1) & 1) * (PAR_ROWS * 256), tb_s, g, etid);
         cx.par = par_s + (oi & 1) * (PAR_ROWS * 256);
         const int epi = o->epi;
         const bool is_gn = (epi == EPI_GN_TB || epi == EPI_GN_RES_ACC || epi == EPI_GN_RES_ID || epi == EPI_GN);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const long long tw0 = P.prof ? clock64() : 0;
+          const long long tw0 = PROF ? clock64() : 0;
           mbar_wait(bar_acc + 8 * h, opn & 1u);
-          if (P.prof) t_acc += clock64() - tw0;
+          if (PROF) t_acc += clock64() - tw0;
+          long long* tl = (PROF && blockIdx.x == 0 && g == blockIdx.x && etid == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
+          if (tl) tl[3 + 2 * h] = clock64();
+          cx.tl = (tl && h == 0) ? P.prof + (gridDim.x + TC_MAX_OPS) * 8 + oi * 4 : nullptr;
           tc_fence_after();
           if (is_gn) {
             epi_gn(o, cx, h);
@@ -578,10 +643,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && oi + 1 < P.n_ops) mbar_arrive(bar_act + 8 * h);
+          if (tl) tl[4 + 2 * h] = clock64();
         }
       }
     }
-    if (P.prof && etid == 0) { P.prof[blockIdx.x * 8 + 5] = t_acc; P.prof[blockIdx.x * 8 + 6] = clock64() - t_start; }
+    if (PROF && etid == 0) { P.prof[blockIdx.x * 8 + 5] = t_acc; P.prof[blockIdx.x * 8 + 6] = clock64() - t_start; }
   }
   tc_fence_before();
   __syncthreads();
@@ -602,6 +668,11 @@ __global__ void tc_pack_tile_kernel(uint8_t* __restrict__ dst, const float* __re
   if (n < cout && ci < cin) v = transposed ? w[((size_t)ci * cout + n) * K + tap] : w[((size_t)n * cin + ci) * K + tap];
   __nv_bfloat16 hv = __float2bfloat16_rn(v);
   *reinterpret_cast<__nv_bfloat16*>(dst + sw128_off(nr, k >> 3) + (k & 7) * 2) = hv;
+}
+
+__global__ void tc_copy_scale_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, float scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
 }
 
 static TcState* st_of(CldHandle* h) { return reinterpret_cast<TcState*>(h->tc); }
@@ -650,13 +721,15 @@ struct Builder {
   TcState* s;
   size_t w_bytes = 0; size_t par_floats = 0;
   struct PackJob { size_t off; const float* w; int cout, cin, K, transposed, tap, ci0, n0, rows, dup4; };
-  struct ParJob { size_t off; const float* src; int n; };
+  struct ParJob { size_t off; const float* src; int n; float scale; };
   std::vector<PackJob> packs; std::vector<ParJob> pars;
 
   int add_par(const float* bias, const float* gamma, const float* beta, const float* resb, int cout) {
     size_t off = par_floats;
+    // GroupNorm gamma / beta are stored pre-scaled by log2(e): the epilogue evaluates Mish through 2^x
     const float* srcs[4] = {bias, gamma, beta, resb};
-    for (int i = 0; i < 4; ++i) if (srcs[i]) pars.push_back({off + (size_t)i * cout, srcs[i], cout});
+    const float scl[4] = {1.f, 1.4426950408889634f, 1.4426950408889634f, 1.f};
+    for (int i = 0; i < 4; ++i) if (srcs[i]) pars.push_back({off + (size_t)i * cout, srcs[i], cout, scl[i]});
     par_floats += 4 * (size_t)((cout + 3) / 4 * 4);
     return (int)off;
   }
@@ -734,7 +807,8 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     const ConvSpec resc{bk.rw, N, bk.cin, 1, 0, k1, o1, 1, e == 0};
     const ConvSpec conv1{bk.c1w, N, N, 5, 0, k5, o5, 5, false};
     // ---- op A: conv0 (+ residual 1x1 conv into the second accumulator set), GroupNorm + Mish + time bias
-    const bool csA = (N >= 128) && !concat;          // concat blocks write h over x: the epilogue must wait for all MMAs
+    // an M=128 MMA costs >= 64 cycles whatever its N (A-operand fetch), so only N = 256 layers are split into halves
+    const bool csA = (N >= 256) && !concat;          // concat blocks write h over x: the epilogue must wait for all MMAs
     const bool skA = csA && prev_commit_split && (n_in % 2 == 0);
     TcOp a = blank_op();
     a.n = N; set_tiles(a, lv); a.kb_first = (int)s->kbs.size();
@@ -762,7 +836,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     }
     s->ops.push_back(a);
     // ---- op B: conv1, GroupNorm + Mish + residual
-    const bool csB = (N >= 128) && !concat;           // concat blocks run conv1 in place (h and the output share region A)
+    const bool csB = (N >= 256) && !concat;           // concat blocks run conv1 in place (h and the output share region A)
     const bool skB = csB && csA;                      // h has N/64 >= 2 panels
     TcOp b = blank_op();
     b.n = N; set_tiles(b, lv); b.kb_first = (int)s->kbs.size();
@@ -901,8 +975,8 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   CLD_LAUNCH_OK(h, "tc_pack_tile_kernel");
   for (int cpy = 1; cpy < s->wcopies; ++cpy)
     CLD_CUDA_OK(h, cudaMemcpyAsync(s->wblob + (size_t)cpy * B.w_bytes, s->wblob, B.w_bytes, cudaMemcpyDeviceToDevice, stream));
-  for (const auto& j : B.pars)
-    CLD_CUDA_OK(h, cudaMemcpyAsync(s->par + j.off, j.src, j.n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  for (const auto& j : B.pars) tc_copy_scale_kernel<<<(j.n + 255) / 256, 256, 0, stream>>>(s->par + j.off, j.src, j.n, j.scale);
+  CLD_LAUNCH_OK(h, "tc_copy_scale_kernel");
   std::vector<uint32_t> packed(s->kbs.size());
   size_t expect_off = 0;
   for (size_t k = 0; k < s->kbs.size(); ++k) {
@@ -930,10 +1004,11 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   s->skip_stride = ((skip1_bytes + skip2_bytes + 1023) / 1024) * 1024;
   if ((rc = alloc((void**)&s->skipbuf, (size_t)s->grid * s->skip_stride))) return rc;
   if (getenv("CLD_TC_PROF")) {
-    if ((rc = alloc((void**)&s->prof, (size_t)s->grid * 8 * sizeof(long long)))) return rc;
-    CLD_CUDA_OK(h, cudaMemsetAsync(s->prof, 0, (size_t)s->grid * 8 * sizeof(long long), stream));
+    if ((rc = alloc((void**)&s->prof, (size_t)(s->grid + 2 * TC_MAX_OPS) * 8 * sizeof(long long)))) return rc;
+    CLD_CUDA_OK(h, cudaMemsetAsync(s->prof, 0, (size_t)(s->grid + 2 * TC_MAX_OPS) * 8 * sizeof(long long), stream));
   }
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   CLD_CUDA_OK(h, cudaStreamSynchronize(stream));
   s->ready = true;
   (void)skip2_off;
@@ -971,17 +1046,31 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
   P.dbg_stage = h->dbg_out ? h->dbg_stage : -1; P.dbg_out = h->dbg_out;
   P.prof = s->prof;
   int grid = P.n_groups < s->grid ? P.n_groups : s->grid;
-  unet_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(P);
+  if (s->prof) unet_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, stream>>>(P);
+  else unet_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, stream>>>(P);
   CLD_LAUNCH_OK(h, "unet_tc_kernel");
   if (s->prof) {
     // debug only (CLD_TC_PROF=1): per-CTA cycle counters of the three roles, printed for CTA 0 and averaged
-    std::vector<long long> hp((size_t)grid * 8);
+    std::vector<long long> hp((size_t)(grid + 2 * TC_MAX_OPS) * 8);
     CLD_CUDA_OK(h, cudaStreamSynchronize(stream));
     CLD_CUDA_OK(h, cudaMemcpy(hp.data(), s->prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     double avg[8] = {0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) avg[i] += (double)hp[(size_t)b * 8 + i] / grid;
     fprintf(stderr, "[tc prof] producer: wait_empty %.0f | mma: wait_full %.0f wait_act %.0f issue %.0f commit %.0f of %.0f | epilogue: wait_acc %.0f of %.0f cycles\n",
             avg[0], avg[2], avg[3], avg[7], avg[1], avg[4], avg[5], avg[6]);
+    if (getenv("CLD_TC_TIMELINE")) {
+      const long long* tl = hp.data() + (size_t)grid * 8;
+      const long long t0 = tl[0];
+      for (size_t oi = 0; oi < s->ops.size(); ++oi) {
+        const long long* r = tl + oi * 8;
+        const TcOp& o = s->ops[oi];
+        fprintf(stderr, "[tc op %2zu epi %d N %3d nvt %d kb %3d fl %d] mma: start %7lld act_ok %7lld done %7lld (issue %6lld) | epi h0: acc %7lld end %7lld (%6lld) h1: acc %7lld end %7lld (%6lld)\n",
+                oi, o.epi, o.n, o.n_vt, o.n_g0 + o.n_g1 + o.n_g2, o.flags, r[0] - t0, r[1] - t0, r[2] - t0, r[2] - r[1], r[3] - t0, r[4] - t0, r[4] - r[3],
+                r[5] - t0, r[6] - t0, r[6] - r[5]);
+        const long long* e = hp.data() + (size_t)(grid + TC_MAX_OPS) * 8 + oi * 4;
+        if (e[0]) fprintf(stderr, "      item h0 warp0: acc->loaded %lld | pass1 %lld | bar %lld | pass2+store %lld\n", e[0] - r[3], e[1] - e[0], e[2] - e[1], r[4] - e[2]);
+      }
+    }
   }
   return 0;
 }
