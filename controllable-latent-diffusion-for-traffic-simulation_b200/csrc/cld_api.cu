@@ -147,6 +147,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->tvec, tb_total);
   if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * MR * 5 * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_act, MR * T * 2);
+  if (!rc) rc = dev_alloc(h, &h->ws_h0, MR * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_traj, MR * T * 6);
   if (!rc) rc = dev_alloc(h, &h->ws_dtraj, MR * T * 4);
   if (!rc) rc = dev_alloc(h, &h->ws_loss, 3 * MR);
@@ -406,11 +407,16 @@ int cld_indicators(CldHandle* h, const float* traj, const CldScene* scene, uint8
   return indicators(h, traj, scene, offroad_out, coll_out, reward_out, R, (cudaStream_t)stream);
 }
 
-static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* cond, const float* curr,
+// h0 == nullptr: compute cond2hidden(cond) first; otherwise cond is unused
+static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* cond, const float* h0, const float* curr,
                               const CldScene* scene, const CldGuidanceConfig* g, float* z_out, float* grad_out,
                               float* loss_out, int R, cudaStream_t s) {
   int rc;
-  if ((rc = decode_rollout(h, z_mean, cond, curr, h->ws_act, h->ws_traj, true, R, s))) return rc;
+  if (!h0) {
+    if ((rc = decode_h0(h, cond, h->ws_h0, R, s))) return rc;
+    h0 = h->ws_h0;
+  }
+  if ((rc = decode_rollout_h0(h, z_mean, h0, curr, h->ws_act, h->ws_traj, true, R, s))) return rc;
   if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, loss_out, R, s))) return rc;
   return decode_backward_update(h, z_mean, h->ws_act, curr, h->ws_dtraj, g, z_out, grad_out, R, s);
 }
@@ -420,7 +426,7 @@ int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, cons
   int rc = check_rows(h, R);
   if (rc) return rc;
   if (!z_mean || !cond || !curr || !scene || !g || !z_out) return fail(h, CLD_ERR_ARG, "null argument");
-  return guidance_step_impl(h, z_mean, cond, curr, scene, g, z_out, grad_out, loss_out, R, (cudaStream_t)stream);
+  return guidance_step_impl(h, z_mean, cond, nullptr, curr, scene, g, z_out, grad_out, loss_out, R, (cudaStream_t)stream);
 }
 
 int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t seed, const float* cond,
@@ -475,6 +481,8 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     // bf16 path: the cond half of every block's time/cond projection is step-invariant -> once per chunk
     const bool split_bias = (c.precision == CLD_PREC_BF16);
     if (split_bias && (rc = unet_cond_bias(h, condc, Rc, s))) return rc;
+    // LSTM initial state (cond2hidden) is step-invariant as well
+    if ((g || traj_out || offroad_out || coll_out) && (rc = decode_h0(h, condc, h->ws_h0, Rc, s))) return rc;
     for (int k = 0; k < K; ++k) {
       const int i = steps[K - 1 - k];
       const int i_next = (k + 1 < K) ? steps[K - 2 - k] : -1;
@@ -501,7 +509,7 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
         if ((rc = posterior_step(h, x, h->ws_eps, nullptr, 0, 0, i, i_next, sampler, nullptr, h->ws_mean, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
         if ((rc = prof_begin(h, 2, s))) return rc;
-        if ((rc = guidance_step_impl(h, h->ws_mean, condc, currc, sc, g, h->ws_mean, nullptr, nullptr, Rc, s))) return rc;
+        if ((rc = guidance_step_impl(h, h->ws_mean, condc, h->ws_h0, currc, sc, g, h->ws_mean, nullptr, nullptr, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
         if ((rc = prof_begin(h, 1, s))) return rc;
         if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, sampler == CLD_SAMPLER_DDPM ? i : 0, x, Rc, s))) return rc;
@@ -517,7 +525,7 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     if (traj_out || offroad_out || coll_out) {
       float* tr = traj_out ? traj_out + (size_t)r0 * T * 6 : h->ws_traj;
       if ((rc = prof_begin(h, 3, s))) return rc;
-      if ((rc = decode_rollout(h, x, condc, currc, nullptr, tr, false, Rc, s))) return rc;
+      if ((rc = decode_rollout_h0(h, x, h->ws_h0, currc, h->ws_act, tr, false, Rc, s))) return rc;
       if (offroad_out || coll_out) {
         if ((rc = indicators(h, tr, sc, offroad_out ? offroad_out + (size_t)r0 * T : nullptr,
                              coll_out ? coll_out + r0 : nullptr, nullptr, Rc, s)))

@@ -60,6 +60,7 @@ struct DecoderW {
   float *wih0_raw = nullptr, *whh0_raw = nullptr, *wih1_raw = nullptr, *whh1_raw = nullptr;
   float *c2h_w = nullptr, *c2h_b = nullptr;                // transposed [C,64], [64]
   float *h2a_w = nullptr, *h2a_b = nullptr;                // [2,64],[2]
+  float *w0p = nullptr, *w1p = nullptr;                    // packed [k pair][unit][gate][2] for kernels_lstm.cu
   bool loaded = false;
 };
 
@@ -88,6 +89,7 @@ struct CldHandle {
   // guidance / decode workspace
   float* stash = nullptr;          // LSTM forward stash [2][T][max_rows][5*H]
   float* ws_act = nullptr;         // [max_rows, T, 2]
+  float* ws_h0 = nullptr;          // [max_rows, H] cond2hidden(cond): LSTM initial state
   float* ws_traj = nullptr;        // [max_rows, T, 6]
   float* ws_dtraj = nullptr;       // [max_rows, T, 4]
   float* ws_loss = nullptr;        // [3, max_rows]
@@ -146,6 +148,10 @@ int fill_t(CldHandle* h, int64_t* t, int value, int R, cudaStream_t s);
 int decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr, float* act_out,
                    float* traj_out, bool save, int R, cudaStream_t s);
 int unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, int R, cudaStream_t s);
+// ---- kernels_lstm.cu
+int decode_h0(CldHandle* h, const float* cond, float* h0, int R, cudaStream_t s);
+int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
+                      bool save, int R, cudaStream_t s);
 int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,
                float* reward, int R, cudaStream_t s);
 // ---- kernels_guidance.cu

@@ -231,18 +231,9 @@ static int launch_dec(CldHandle* h, const DecArgs& a, cudaStream_t s) {
 
 int decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr, float* act_out,
                    float* traj_out, bool save, int R, cudaStream_t s) {
-  const DecoderW& w = h->dec;
-  if (!w.loaded) return fail(h, CLD_ERR_STATE, "decoder weights not loaded");
-  if (h->cfg.hidden != 64 || h->cfg.latent_dim != 4 || h->cfg.cond_dim > 256)
-    return fail(h, CLD_ERR_UNSUPPORTED, "decoder kernel is specialised for hidden=64, latent=4, cond<=256");
-  DecArgs a;
-  a.z = z; a.cond = cond; a.curr = curr;
-  a.wih0T = w.wih0; a.whh0T = w.whh0; a.b0 = w.b0; a.wih1T = w.wih1; a.whh1T = w.whh1; a.b1 = w.b1;
-  a.c2hT = w.c2h_w; a.c2h_b = w.c2h_b; a.h2a_w = w.h2a_w; a.h2a_b = w.h2a_b;
-  a.act_out = act_out; a.traj_out = traj_out; a.stash = save ? h->stash : nullptr;
-  a.R = R; a.T = h->cfg.horizon; a.C = h->cfg.cond_dim; a.dyn = dyn_of(h->cfg);
-  if (a.T <= 64) return save ? launch_dec<8, true>(h, a, s) : launch_dec<8, false>(h, a, s);
-  return save ? launch_dec<4, true>(h, a, s) : launch_dec<4, false>(h, a, s);
+  int rc;
+  if ((rc = decode_h0(h, cond, h->ws_h0, R, s))) return rc;
+  return decode_rollout_h0(h, z, h->ws_h0, curr, act_out ? act_out : h->ws_act, traj_out, save, R, s);
 }
 
 __global__ void unicycle_kernel(const float* __restrict__ curr, const float* __restrict__ u, float* __restrict__ out,
