@@ -148,6 +148,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * MR * 5 * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_act, MR * T * 2);
   if (!rc) rc = dev_alloc(h, &h->ws_h0, MR * cfg->hidden);
+  if (!rc) rc = dev_alloc(h, &h->ws_dh0, (size_t)T * MR * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_traj, MR * T * 6);
   if (!rc) rc = dev_alloc(h, &h->ws_dtraj, MR * T * 4);
   if (!rc) rc = dev_alloc(h, &h->ws_loss, 3 * MR);
@@ -418,7 +419,7 @@ static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* co
   }
   if ((rc = decode_rollout_h0(h, z_mean, h0, curr, h->ws_act, h->ws_traj, true, R, s))) return rc;
   if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, loss_out, R, s))) return rc;
-  return decode_backward_update(h, z_mean, h->ws_act, curr, h->ws_dtraj, g, z_out, grad_out, R, s);
+  return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, g, z_out, grad_out, R, s);
 }
 
 int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr, const CldScene* scene,

@@ -60,7 +60,8 @@ struct DecoderW {
   float *wih0_raw = nullptr, *whh0_raw = nullptr, *wih1_raw = nullptr, *whh1_raw = nullptr;
   float *c2h_w = nullptr, *c2h_b = nullptr;                // transposed [C,64], [64]
   float *h2a_w = nullptr, *h2a_b = nullptr;                // [2,64],[2]
-  float *w0p = nullptr, *w1p = nullptr;                    // packed [k pair][unit][gate][2] for kernels_lstm.cu
+  float *w0p = nullptr, *w1p = nullptr;                    // packed forward weights for kernels_lstm.cu
+  float *w1t = nullptr, *w0t = nullptr;                    // packed transposed weights for the backward
   bool loaded = false;
 };
 
@@ -90,6 +91,7 @@ struct CldHandle {
   float* stash = nullptr;          // LSTM forward stash [2][T][max_rows][5*H]
   float* ws_act = nullptr;         // [max_rows, T, 2]
   float* ws_h0 = nullptr;          // [max_rows, H] cond2hidden(cond): LSTM initial state
+  float* ws_dh0 = nullptr;         // [T, max_rows, H] d(loss)/d(h0_t) coming down from layer 1 (backward)
   float* ws_traj = nullptr;        // [max_rows, T, 6]
   float* ws_dtraj = nullptr;       // [max_rows, T, 4]
   float* ws_loss = nullptr;        // [3, max_rows]
@@ -150,6 +152,8 @@ int decode_rollout(CldHandle* h, const float* z, const float* cond, const float*
 int unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, int R, cudaStream_t s);
 // ---- kernels_lstm.cu
 int decode_h0(CldHandle* h, const float* cond, float* h0, int R, cudaStream_t s);
+int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
+                            const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
 int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
                       bool save, int R, cudaStream_t s);
 int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,

@@ -94,18 +94,17 @@ __device__ __forceinline__ float clip2(float x, float lo, float hi) { return fmi
 __device__ __forceinline__ void lstm_kloop(const float* __restrict__ wp, const float* __restrict__ hsrc, int nkp, uint64_t (&acc)[8][4]) {
 #pragma unroll 2
   for (int kp = 0; kp < nkp; ++kp) {
-    const float4 wa = *reinterpret_cast<const float4*>(wp + kp * (LS_H * 8));
-    const float4 wb = *reinterpret_cast<const float4*>(wp + kp * (LS_H * 8) + LS_H * 4);
-    const uint64_t wi = pk2(wa.x, wa.y), wf = pk2(wa.z, wa.w), wg = pk2(wb.x, wb.y), wo = pk2(wb.z, wb.w);
-    const float4* hp = reinterpret_cast<const float4*>(hsrc + (size_t)kp * (LS_RP * 2));
+    // 64-bit register pairs straight from LDS.128: (k0, k1) of one gate / one row -- no repacking moves
+    const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wp + kp * (LS_H * 8));               // (i, f)
+    const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wp + kp * (LS_H * 8) + LS_H * 4);    // (g, o)
+    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hsrc + (size_t)kp * (LS_RP * 2));
 #pragma unroll
     for (int r2 = 0; r2 < 4; ++r2) {
-      const float4 hv = hp[r2];                    // two rows: (k0, k1) pairs
-      const uint64_t ha = pk2(hv.x, hv.y), hb = pk2(hv.z, hv.w);
-      acc[2 * r2][0] = fma2(ha, wi, acc[2 * r2][0]); acc[2 * r2][1] = fma2(ha, wf, acc[2 * r2][1]);
-      acc[2 * r2][2] = fma2(ha, wg, acc[2 * r2][2]); acc[2 * r2][3] = fma2(ha, wo, acc[2 * r2][3]);
-      acc[2 * r2 + 1][0] = fma2(hb, wi, acc[2 * r2 + 1][0]); acc[2 * r2 + 1][1] = fma2(hb, wf, acc[2 * r2 + 1][1]);
-      acc[2 * r2 + 1][2] = fma2(hb, wg, acc[2 * r2 + 1][2]); acc[2 * r2 + 1][3] = fma2(hb, wo, acc[2 * r2 + 1][3]);
+      const ulonglong2 hv = hp[r2];                // two rows
+      acc[2 * r2][0] = fma2(hv.x, wa.x, acc[2 * r2][0]); acc[2 * r2][1] = fma2(hv.x, wa.y, acc[2 * r2][1]);
+      acc[2 * r2][2] = fma2(hv.x, wb.x, acc[2 * r2][2]); acc[2 * r2][3] = fma2(hv.x, wb.y, acc[2 * r2][3]);
+      acc[2 * r2 + 1][0] = fma2(hv.y, wa.x, acc[2 * r2 + 1][0]); acc[2 * r2 + 1][1] = fma2(hv.y, wa.y, acc[2 * r2 + 1][1]);
+      acc[2 * r2 + 1][2] = fma2(hv.y, wb.x, acc[2 * r2 + 1][2]); acc[2 * r2 + 1][3] = fma2(hv.y, wb.y, acc[2 * r2 + 1][3]);
     }
   }
 }
@@ -262,6 +261,285 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_decode2_kernel(const Lstm2
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward: d(traj) -> d(scaled actions) -> BPTT through both layers -> dz -> first optimizer step
+// (PerturbationGuidance.perturb, reference src/tbsim/utils/guidance_loss.py:2250-2278).  Same tiling as the
+// forward: one CTA owns 32 rows; pass 1 walks layer 1 backwards in time with [W_hh1 | W_ih1]^T in shared memory
+// (per step: gate gradients [32 x 256] x [256 x 128] -> recurrent dh1 (kept in registers by the thread that needs it
+// next) and dh0 (to a global workspace)), pass 2 does the same for layer 0 with [W_hh0 | W_ih0]^T and emits dz.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int LB_W = 0;                                   // [128 jp][128 col][2] (pass 2: [128 jp][68 col][2])
+constexpr int LB_DG = LB_W + 128 * 128 * 2;               // [128 jp][LS_RP rows][2] gate gradients
+constexpr int LB_HW = LB_DG + 128 * LS_RP * 2;            // hid2act weights [2][64]
+constexpr int LB_DACT = LB_HW + 2 * LS_H;                 // [32 rows][T][4]: d(action) in pass 1, dz in pass 2
+static size_t lb_smem(int T) { return (size_t)(LB_DACT + LS_RB * T * 4) * sizeof(float); }
+static_assert(128 * 128 * 2 >= LS_RB * 4 * (CLD_MAX_T + 1), "unicycle scratch aliases the weight tile");
+}  // namespace
+
+struct Bwd2Args {
+  const float *z_mean, *act, *curr, *dtraj, *stash;
+  const float *w1t, *w0t, *h2a_w;
+  float *z_out, *grad_out, *dh0f;
+  int R, T;
+  DynParams2 dyn;
+  int optimizer; float lr;
+};
+
+// packs W_hh [256][64] | W_ih [256][in] (nn.LSTM layouts) into [j pair][col][2], col < 64: W_hh[j][col], else W_ih[j][col-64]
+__global__ void lstm_pack_t_kernel(const float* __restrict__ whh, const float* __restrict__ wih, int in_dim, float* __restrict__ out) {
+  const int ncol = 64 + in_dim;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * ncol * 2) return;
+  int jj = idx & 1, col = (idx >> 1) % ncol, jp = (idx >> 1) / ncol;
+  int j = 2 * jp + jj;
+  out[idx] = (col < 64) ? whh[(size_t)j * 64 + col] : wih[(size_t)j * in_dim + (col - 64)];
+}
+
+// reverse of the unicycle closed form for one row; writes d(scaled action) [T][2]
+__device__ void unicycle_row_backward2(const float* act, const float* curr, const float* dtr, int T, const DynParams2& a,
+                                       float* scr /*[4][T+1]*/, float* dact) {
+  float* sk = scr; float* psik = scr + (T + 1); float* vbar = scr + 2 * (T + 1); float* msk = scr + 3 * (T + 1);
+  float s = curr[2], psi = curr[3];
+  float vprev = clip2(s, a.v_lo, a.v_hi);
+  sk[0] = s; psik[0] = psi;
+  for (int k = 0; k < T; ++k) {
+    float a_raw = __fadd_rn(__fmul_rn(act[k * 2 + 0], a.a_std), a.a_mean);
+    float w_raw = __fadd_rn(__fmul_rn(act[k * 2 + 1], a.w_std), a.w_mean);
+    float ac = clip2(a_raw, a.acce_lo, a.acce_hi);
+    s = __fadd_rn(s, __fmul_rn(ac, a.dt));
+    float vnext = clip2(s, a.v_lo, a.v_hi);
+    vbar[k] = __fmul_rn(0.5f, __fadd_rn(vprev, vnext));
+    float ve = fabsf(vprev);
+    float yb = fmaxf(fminf(__fmul_rn(a.max_steer, ve), __fdiv_rn(a.max_yawvel, fmaxf(ve, 0.1f))), 0.1f);
+    float w = clip2(w_raw, -yb, yb);
+    psi = __fadd_rn(psi, __fmul_rn(w, a.dt));
+    int m = ((a_raw >= a.acce_lo && a_raw <= a.acce_hi) ? 1 : 0) | ((w_raw >= -yb && w_raw <= yb) ? 2 : 0);
+    msk[k] = __int_as_float(m);
+    sk[k + 1] = s; psik[k + 1] = psi;
+    vprev = vnext;
+  }
+  float Gx = 0.f, Gy = 0.f, Spsi = 0.f, Ss = 0.f, dvbar_next = 0.f, direct_next = 0.f;
+  for (int m = T - 1; m >= 0; --m) {
+    const float gx = dtr[m * 4 + 0], gy = dtr[m * 4 + 1], gv = dtr[m * 4 + 2], gpsi = dtr[m * 4 + 3];
+    Gx += a.dt * gx; Gy += a.dt * gy;
+    float c = cosf(psik[m]), sn = sinf(psik[m]);
+    float dvbar = Gx * c + Gy * sn;
+    float direct = vbar[m] * (-Gx * sn + Gy * c);
+    Spsi += ((m + 1 <= T - 1) ? direct_next : 0.f) + gpsi;
+    float dvhat = 0.5f * (((m + 1 <= T - 1) ? dvbar_next : 0.f) + dvbar) + gv;
+    float s1 = sk[m + 1];
+    if (s1 >= a.v_lo && s1 <= a.v_hi) Ss += dvhat;
+    int mk = __float_as_int(msk[m]);
+    float du0 = (mk & 1) ? a.dt * Ss : 0.f;
+    float du1 = (mk & 2) ? a.dt * Spsi : 0.f;
+    dact[m * 2 + 0] = a.a_std * du0;
+    dact[m * 2 + 1] = a.w_std * du1;
+    dvbar_next = dvbar; direct_next = direct;
+  }
+}
+
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd2Args a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rg = warp >> 1, u = (warp & 1) * 32 + lane;
+  const int row0 = blockIdx.x * LS_RB, rl0 = rg * 8;
+  const int T = a.T, R = a.R;
+  float* dg = sm + LB_DG;
+  float* dact = sm + LB_DACT;      // pass 1: d(scaled action) [32][T][2]
+  float* dzs = sm + LB_DACT;       // pass 2: dz [32][T][4] (same storage)
+  const size_t srs = (size_t)5 * LS_H;
+
+  // ---- unicycle backward per row -> dact (scratch aliases the weight tile); then layer-1 weights -> smem
+  {
+    if (tid < 2 * LS_H) sm[LB_HW + tid] = a.h2a_w[tid];
+    if (tid < LS_RB) {
+      float* da = dact + tid * T * 2;
+      if (row0 + tid < R) {
+        const size_t row = (size_t)row0 + tid;
+        unicycle_row_backward2(a.act + row * T * 2, a.curr + row * 4, a.dtraj + row * T * 4, T, a.dyn, sm + LB_W + tid * 4 * (T + 1), da);
+      } else {
+        for (int i = 0; i < 2 * T; ++i) da[i] = 0.f;
+      }
+    }
+    __syncthreads();
+    const float4* s1 = reinterpret_cast<const float4*>(a.w1t);
+    float4* d1 = reinterpret_cast<float4*>(sm + LB_W);
+    for (int i = tid; i < 128 * 128 * 2 / 4; i += LS_THREADS) d1[i] = s1[i];
+  }
+  __syncthreads();
+  const float hw0 = sm[LB_HW + u], hw1 = sm[LB_HW + LS_H + u];
+  const bool rv[8] = {row0 + rl0 + 0 < R, row0 + rl0 + 1 < R, row0 + rl0 + 2 < R, row0 + rl0 + 3 < R,
+                      row0 + rl0 + 4 < R, row0 + rl0 + 5 < R, row0 + rl0 + 6 < R, row0 + rl0 + 7 < R};
+
+  // =========================== pass 1: layer 1 ===========================
+  {
+    const float* st1 = a.stash + ((size_t)T * R + row0 + rl0) * srs + u;      // + t * R * srs + r * srs + v * 64
+    float gi[8], gf[8], gg[8], go[8], cc[8], cp[8];                              // gates of step t, c(t), c(t-1)
+    float dhrec[8], dcrec[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      dhrec[r] = 0.f; dcrec[r] = 0.f;
+      const float* p = st1 + ((size_t)(T - 1) * R + r) * srs;
+      gi[r] = rv[r] ? p[0] : 0.f; gf[r] = rv[r] ? p[LS_H] : 0.f; gg[r] = rv[r] ? p[2 * LS_H] : 0.f;
+      go[r] = rv[r] ? p[3 * LS_H] : 0.f; cc[r] = rv[r] ? p[4 * LS_H] : 0.f;
+      cp[r] = (rv[r] && T >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+    }
+    for (int t = T - 1; t >= 0; --t) {
+      // prefetch: gates of t-1, cell of t-2
+      float ni[8], nf[8], ng[8], no[8], np[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float* p = st1 + ((size_t)(t - 1) * R + r) * srs;
+        const bool ok = rv[r] && t >= 1;
+        ni[r] = ok ? p[0] : 0.f; nf[r] = ok ? p[LS_H] : 0.f; ng[r] = ok ? p[2 * LS_H] : 0.f; no[r] = ok ? p[3 * LS_H] : 0.f;
+        np[r] = (rv[r] && t >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+      }
+      // gate gradients of step t
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float2 da = *reinterpret_cast<const float2*>(dact + ((rl0 + r) * T + t) * 2);
+        const float dh = fmaf(hw0, da.x, fmaf(hw1, da.y, dhrec[r]));
+        const float tc = tanh_acc(cc[r]);
+        const float dc = dcrec[r] + dh * go[r] * (1.f - tc * tc);
+        float* d = dg + (size_t)(rl0 + r) * 2 + (u & 1) + (size_t)(u >> 1) * (LS_RP * 2);
+        d[0 * 32 * (LS_RP * 2)] = dc * gg[r] * gi[r] * (1.f - gi[r]);
+        d[1 * 32 * (LS_RP * 2)] = dc * cp[r] * gf[r] * (1.f - gf[r]);
+        d[2 * 32 * (LS_RP * 2)] = dc * gi[r] * (1.f - gg[r] * gg[r]);
+        d[3 * 32 * (LS_RP * 2)] = dh * tc * go[r] * (1.f - go[r]);
+        dcrec[r] = dc * gf[r];
+      }
+      __syncthreads();
+      // [32 x 256] x [256 x 128]: this thread: 8 rows x columns (u: W_hh1^T -> dh1 recurrent, 64+u: W_ih1^T -> dh0)
+      uint64_t acc[8][2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
+      {
+        const float* wp = sm + LB_W + u * 2;
+        const float* gp = dg + rl0 * 2;
+#pragma unroll 4
+        for (int jp = 0; jp < 128; ++jp) {
+          const uint64_t w_a = *reinterpret_cast<const uint64_t*>(wp + jp * 256);
+          const uint64_t w_b = *reinterpret_cast<const uint64_t*>(wp + jp * 256 + 128);
+          const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(gp + (size_t)jp * (LS_RP * 2));
+#pragma unroll
+          for (int r2 = 0; r2 < 4; ++r2) {
+            const ulonglong2 hv = hp[r2];
+            acc[2 * r2][0] = fma2(hv.x, w_a, acc[2 * r2][0]); acc[2 * r2][1] = fma2(hv.x, w_b, acc[2 * r2][1]);
+            acc[2 * r2 + 1][0] = fma2(hv.y, w_a, acc[2 * r2 + 1][0]); acc[2 * r2 + 1][1] = fma2(hv.y, w_b, acc[2 * r2 + 1][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float x0, x1;
+        upk2(acc[r][0], x0, x1); dhrec[r] = x0 + x1;
+        upk2(acc[r][1], x0, x1);
+        if (rv[r]) a.dh0f[((size_t)t * R + row0 + rl0 + r) * LS_H + u] = x0 + x1;
+        gi[r] = ni[r]; gf[r] = nf[r]; gg[r] = ng[r]; go[r] = no[r]; cc[r] = cp[r]; cp[r] = np[r];
+      }
+      __syncthreads();
+    }
+  }
+  // =========================== pass 2: layer 0 ===========================
+  {
+    const float4* s0 = reinterpret_cast<const float4*>(a.w0t);
+    float4* d0 = reinterpret_cast<float4*>(sm + LB_W);
+    for (int i = tid; i < 128 * 68 * 2 / 4; i += LS_THREADS) d0[i] = s0[i];
+    __threadfence_block();
+    __syncthreads();
+    const float* st0 = a.stash + ((size_t)row0 + rl0) * srs + u;
+    float gi[8], gf[8], gg[8], go[8], cc[8], cp[8], dhf[8];
+    float dhrec[8], dcrec[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      dhrec[r] = 0.f; dcrec[r] = 0.f;
+      const float* p = st0 + ((size_t)(T - 1) * R + r) * srs;
+      gi[r] = rv[r] ? p[0] : 0.f; gf[r] = rv[r] ? p[LS_H] : 0.f; gg[r] = rv[r] ? p[2 * LS_H] : 0.f;
+      go[r] = rv[r] ? p[3 * LS_H] : 0.f; cc[r] = rv[r] ? p[4 * LS_H] : 0.f;
+      cp[r] = (rv[r] && T >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+      dhf[r] = rv[r] ? a.dh0f[((size_t)(T - 1) * R + row0 + rl0 + r) * LS_H + u] : 0.f;
+    }
+    for (int t = T - 1; t >= 0; --t) {
+      float ni[8], nf[8], ng[8], no[8], np[8], nh[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float* p = st0 + ((size_t)(t - 1) * R + r) * srs;
+        const bool ok = rv[r] && t >= 1;
+        ni[r] = ok ? p[0] : 0.f; nf[r] = ok ? p[LS_H] : 0.f; ng[r] = ok ? p[2 * LS_H] : 0.f; no[r] = ok ? p[3 * LS_H] : 0.f;
+        np[r] = (rv[r] && t >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+        nh[r] = ok ? a.dh0f[((size_t)(t - 1) * R + row0 + rl0 + r) * LS_H + u] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float dh = dhf[r] + dhrec[r];
+        const float tc = tanh_acc(cc[r]);
+        const float dc = dcrec[r] + dh * go[r] * (1.f - tc * tc);
+        float* d = dg + (size_t)(rl0 + r) * 2 + (u & 1) + (size_t)(u >> 1) * (LS_RP * 2);
+        d[0 * 32 * (LS_RP * 2)] = dc * gg[r] * gi[r] * (1.f - gi[r]);
+        d[1 * 32 * (LS_RP * 2)] = dc * cp[r] * gf[r] * (1.f - gf[r]);
+        d[2 * 32 * (LS_RP * 2)] = dc * gi[r] * (1.f - gg[r] * gg[r]);
+        d[3 * 32 * (LS_RP * 2)] = dh * tc * go[r] * (1.f - go[r]);
+        dcrec[r] = dc * gf[r];
+      }
+      __syncthreads();
+      // [32 x 256] x [256 x 68]: column u (W_hh0^T -> dh0 recurrent); threads with u < 4 also column 64+u (W_ih0^T -> dz)
+      uint64_t acc[8], accz[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { acc[r] = 0ull; accz[r] = 0ull; }
+      {
+        const float* wp = sm + LB_W + u * 2;
+        const float* gp = dg + rl0 * 2;
+        const bool zc = u < 4;                              // warp-uniform only for the second warp of a row group (never)
+#pragma unroll 4
+        for (int jp = 0; jp < 128; ++jp) {
+          const uint64_t w_a = *reinterpret_cast<const uint64_t*>(wp + jp * 136);
+          uint64_t w_z = 0ull;
+          if (zc) w_z = *reinterpret_cast<const uint64_t*>(wp + jp * 136 + 128);
+          const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(gp + (size_t)jp * (LS_RP * 2));
+#pragma unroll
+          for (int r2 = 0; r2 < 4; ++r2) {
+            const ulonglong2 hv = hp[r2];
+            acc[2 * r2] = fma2(hv.x, w_a, acc[2 * r2]); acc[2 * r2 + 1] = fma2(hv.y, w_a, acc[2 * r2 + 1]);
+            if (zc) { accz[2 * r2] = fma2(hv.x, w_z, accz[2 * r2]); accz[2 * r2 + 1] = fma2(hv.y, w_z, accz[2 * r2 + 1]); }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float x0, x1;
+        upk2(acc[r], x0, x1); dhrec[r] = x0 + x1;
+        if (u < 4) {
+          upk2(accz[r], x0, x1);
+          dzs[((rl0 + r) * T + t) * 4 + u] = x0 + x1;       // staged; the optimizer step runs after the loop
+        }
+        gi[r] = ni[r]; gf[r] = nf[r]; gg[r] = ng[r]; go[r] = no[r]; cc[r] = cp[r]; cp[r] = np[r]; dhf[r] = nh[r];
+      }
+      __syncthreads();
+    }
+    // ---- optimizer step (guidance_loss.py:2250-2278), coalesced over the CTA's [32][T][4] block
+    for (int i = tid; i < LS_RB * T * 4; i += LS_THREADS) {
+      const int rl = i / (T * 4);
+      if (row0 + rl >= R) continue;
+      const size_t gi_ = (size_t)row0 * T * 4 + i;
+      const float g = dzs[i], z = a.z_mean[gi_];
+      float zn;
+      if (a.optimizer == CLD_OPT_ADAM) {
+        // first torch.optim.Adam step: m = 0.1 g, v = 0.001 g^2, bias corrections 0.1 / 0.001, eps 1e-8
+        const float m = 0.1f * g;
+        const float v = (0.001f * g) * g;
+        const float denom = sqrtf(v) / 0.03162277660168379f + 1e-8f;
+        const float step = a.lr / 0.1f;
+        zn = z - step * (m / denom);
+      } else {
+        zn = z - a.lr * g;
+      }
+      a.z_out[gi_] = zn;
+      if (a.grad_out) a.grad_out[gi_] = g;
+    }
+  }
+}
+
 // prepares the packed weights on first use
 static int lstm2_prepare(CldHandle* h, cudaStream_t s) {
   DecoderW& w = h->dec;
@@ -276,7 +554,17 @@ static int lstm2_prepare(CldHandle* h, cudaStream_t s) {
   CLD_LAUNCH_OK(h, "lstm_pack_kernel");
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
-  w.w0p = w0p; w.w1p = w1p;
+  float *w1t = nullptr, *w0t = nullptr;
+  CLD_CUDA_OK(h, cudaMalloc((void**)&w1t, (size_t)128 * 128 * 2 * sizeof(float)));
+  h->allocs.push_back(w1t);
+  CLD_CUDA_OK(h, cudaMalloc((void**)&w0t, (size_t)128 * 68 * 2 * sizeof(float)));
+  h->allocs.push_back(w0t);
+  lstm_pack_t_kernel<<<(128 * 128 * 2 + 255) / 256, 256, 0, s>>>(w.whh1_raw, w.wih1_raw, 64, w1t);
+  lstm_pack_t_kernel<<<(128 * 68 * 2 + 255) / 256, 256, 0, s>>>(w.whh0_raw, w.wih0_raw, 4, w0t);
+  CLD_LAUNCH_OK(h, "lstm_pack_t_kernel");
+  if (lb_smem(h->cfg.horizon) > 232448) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the LSTM backward kernel");
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem(h->cfg.horizon)));
+  w.w0p = w0p; w.w1p = w1p; w.w1t = w1t; w.w0t = w0t;
   return 0;
 }
 
@@ -308,6 +596,27 @@ int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float
   if (save) lstm_decode2_kernel<true><<<grid, LS_THREADS, LS_SMEM, s>>>(a);
   else lstm_decode2_kernel<false><<<grid, LS_THREADS, LS_SMEM, s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_decode2_kernel");
+  return 0;
+}
+
+
+int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
+                            const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+  DecoderW& w = h->dec;
+  int rc;
+  if ((rc = lstm2_prepare(h, s))) return rc;
+  const CldConfig& c = h->cfg;
+  if (c.horizon > CLD_MAX_T) return fail(h, CLD_ERR_UNSUPPORTED, "horizon exceeds CLD_MAX_T");
+  Bwd2Args a;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash;
+  a.w1t = w.w1t; a.w0t = w.w0t; a.h2a_w = w.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.dh0f = h->ws_dh0;
+  a.R = R; a.T = c.horizon;
+  a.dyn.dt = c.dt; a.dyn.acce_lo = c.acce_lo; a.dyn.acce_hi = c.acce_hi; a.dyn.v_lo = c.v_lo; a.dyn.v_hi = c.v_hi;
+  a.dyn.max_steer = c.max_steer; a.dyn.max_yawvel = c.max_yawvel;
+  a.dyn.a_mean = c.norm_mean[4]; a.dyn.a_std = c.norm_std[4]; a.dyn.w_mean = c.norm_mean[5]; a.dyn.w_std = c.norm_std[5];
+  a.optimizer = g->optimizer; a.lr = g->lr;
+  lstm_backward2_kernel<<<(R + LS_RB - 1) / LS_RB, LS_THREADS, lb_smem(a.T), s>>>(a);
+  CLD_LAUNCH_OK(h, "lstm_backward2_kernel");
   return 0;
 }
 
