@@ -145,7 +145,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->tcm, MR * (cfg->base_dim + cfg->cond_dim));
   if (!rc) rc = dev_alloc(h, &h->tbias, MR * tb_total);
   if (!rc) rc = dev_alloc(h, &h->tvec, tb_total);
-  if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * MR * 5 * cfg->hidden);
+  if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * ((MR + 63) / 64 * 64) * 5 * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_act, MR * T * 2);
   if (!rc) rc = dev_alloc(h, &h->ws_h0, MR * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_dh0, (size_t)T * MR * cfg->hidden);

@@ -88,7 +88,7 @@ struct CldHandle {
   float* tbias = nullptr;          // [max_rows, tb_total]
   float* tvec = nullptr;           // [tb_total] per-step time part of the bias (sampler: uniform t)
   // guidance / decode workspace
-  float* stash = nullptr;          // LSTM forward stash [2][T][max_rows][5*H]
+  float* stash = nullptr;          // LSTM forward stash, see stash_index()
   float* ws_act = nullptr;         // [max_rows, T, 2]
   float* ws_h0 = nullptr;          // [max_rows, H] cond2hidden(cond): LSTM initial state
   float* ws_dh0 = nullptr;         // [T, max_rows, H] d(loss)/d(h0_t) coming down from layer 1 (backward)
@@ -114,6 +114,15 @@ struct CldHandle {
 };
 
 namespace cld {
+// LSTM stash (gate activations i, f, g, o and the cell state c of every step, for the analytic backward):
+// [layer][t][row block of 8][value 0..4][unit 0..63][row in block].  A SIMT thread (8 rows x 1 unit) moves 32
+// contiguous bytes and a warp of consecutive units 1 KB; a tensor-core epilogue warp (lane = row) touches 4 full
+// 32-byte sectors per store.  Rows are padded to a multiple of 64.
+__host__ __device__ inline size_t stash_index(int layer, int t, int T, int R, int row, int v, int u) {
+  const size_t rblk = (size_t)((R + 63) >> 6) * 8;
+  return (((((size_t)layer * T + t) * rblk + (size_t)(row >> 3)) * 5 + v) * 64 + u) * 8 + (row & 7);
+}
+constexpr int STASH_V_STRIDE = 64 * 8;   // floats between consecutive values v for the same (row block, unit)
 int fail(CldHandle* h, int code, const char* fmt, ...);
 #define CLD_CUDA_OK(h, expr)                                                                   \
   do {                                                                                         \

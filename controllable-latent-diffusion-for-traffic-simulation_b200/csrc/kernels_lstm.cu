@@ -110,9 +110,11 @@ __device__ __forceinline__ void lstm_kloop(const float* __restrict__ wp, const f
 }
 
 // LSTM cell update of one layer for the thread's 8 rows; returns the new hidden values, optionally stashes
+// (st = &stash[stash_index(layer, t, T, R, first row, 0, u)]: value v of the 8 rows is 8 consecutive floats at v * STASH_V_STRIDE)
 template <bool SAVE>
 __device__ __forceinline__ void lstm_cell(const uint64_t (&acc)[8][4], const float (&b)[4], float (&c)[8], float (&hn)[8],
-                                          float* __restrict__ stash_row0, size_t stash_row_stride, int rows_valid) {
+                                          float* __restrict__ st) {
+  float sv[5][8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     float x0, x1;
@@ -123,9 +125,14 @@ __device__ __forceinline__ void lstm_cell(const uint64_t (&acc)[8][4], const flo
     const float cn = fmaf(fg, c[r], ig * gg);
     c[r] = cn;
     hn[r] = og * tanh_acc(cn);
-    if (SAVE && r < rows_valid) {
-      float* st = stash_row0 + (size_t)r * stash_row_stride;
-      st[0] = ig; st[LS_H] = fg; st[2 * LS_H] = gg; st[3 * LS_H] = og; st[4 * LS_H] = cn;
+    if (SAVE) { sv[0][r] = ig; sv[1][r] = fg; sv[2][r] = gg; sv[3][r] = og; sv[4][r] = cn; }
+  }
+  if (SAVE) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      float4* d = reinterpret_cast<float4*>(st + (size_t)v * STASH_V_STRIDE);
+      d[0] = make_float4(sv[v][0], sv[v][1], sv[v][2], sv[v][3]);
+      d[1] = make_float4(sv[v][4], sv[v][5], sv[v][6], sv[v][7]);
     }
   }
 }
@@ -170,8 +177,6 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_decode2_kernel(const Lstm2
   const float h2a_b_o = a.h2a_b[(tid >> 1) & 1];
   const float* wp0 = sm + LS_W0 + u * 4;
   const float* wp1 = sm + LS_W1 + u * 4;
-  const int rows_valid = R - (row0 + rl0);                // rows of this thread that exist (may be <= 0 or >= 8)
-  const size_t srs = (size_t)5 * LS_H;
   __syncthreads();
 
   for (int it = 0; it <= T; ++it) {
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_decode2_kernel(const Lstm2
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[r][g] = 0ull;
       lstm_kloop(wp0, xh0 + rl0 * 2, LS_KP0, acc);
-      lstm_cell<SAVE>(acc, bias0, c0, hn0, SAVE ? a.stash + (((size_t)0 * T + it) * R + row0 + rl0) * srs + u : nullptr, srs, rows_valid);
+      lstm_cell<SAVE>(acc, bias0, c0, hn0, SAVE ? a.stash + stash_index(0, it, T, R, row0 + rl0, 0, u) : nullptr);
     }
     if (it >= 1) {                                        // layer 1, step it - 1: [h0_{it-1} | h1_{it-2}]
       uint64_t acc[8][4];
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_decode2_kernel(const Lstm2
         for (int g = 0; g < 4; ++g) acc[r][g] = 0ull;
       lstm_kloop(wp1, xh0 + (size_t)2 * (LS_RP * 2) + rl0 * 2, 32, acc);
       lstm_kloop(wp1 + 32 * (LS_H * 8), h1s + rl0 * 2, 32, acc);
-      lstm_cell<SAVE>(acc, bias1, c1, hn1, SAVE ? a.stash + (((size_t)1 * T + (it - 1)) * R + row0 + rl0) * srs + u : nullptr, srs, rows_valid);
+      lstm_cell<SAVE>(acc, bias1, c1, hn1, SAVE ? a.stash + stash_index(1, it - 1, T, R, row0 + rl0, 0, u) : nullptr);
     }
     __syncthreads();     // every read of the state tiles of this iteration is done
     if (it < T) {
@@ -339,6 +344,13 @@ __device__ void unicycle_row_backward2(const float* act, const float* curr, cons
   }
 }
 
+// 8 consecutive rows of stash value v (i, f, g, o, c) of (layer, t, unit u): two 16-byte loads
+__device__ __forceinline__ void stash_ld8(const float* __restrict__ stash, int layer, int t, int T, int R, int row, int v, int u, float (&o)[8]) {
+  const float4* p = reinterpret_cast<const float4*>(stash + stash_index(layer, t, T, R, row, v, u));
+  const float4 a = p[0], b = p[1];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd2Args a) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,7 +360,6 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd
   float* dg = sm + LB_DG;
   float* dact = sm + LB_DACT;      // pass 1: d(scaled action) [32][T][2]
   float* dzs = sm + LB_DACT;       // pass 2: dz [32][T][4] (same storage)
-  const size_t srs = (size_t)5 * LS_H;
 
   // ---- unicycle backward per row -> dact (scratch aliases the weight tile); then layer-1 weights -> smem
   {
@@ -374,26 +385,29 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd
 
   // =========================== pass 1: layer 1 ===========================
   {
-    const float* st1 = a.stash + ((size_t)T * R + row0 + rl0) * srs + u;      // + t * R * srs + r * srs + v * 64
+    const int frow = row0 + rl0;                                                // rows beyond R read the zero-padded / stale tail: masked by rv
     float gi[8], gf[8], gg[8], go[8], cc[8], cp[8];                              // gates of step t, c(t), c(t-1)
     float dhrec[8], dcrec[8];
+    stash_ld8(a.stash, 1, T - 1, T, R, frow, 0, u, gi); stash_ld8(a.stash, 1, T - 1, T, R, frow, 1, u, gf);
+    stash_ld8(a.stash, 1, T - 1, T, R, frow, 2, u, gg); stash_ld8(a.stash, 1, T - 1, T, R, frow, 3, u, go);
+    stash_ld8(a.stash, 1, T - 1, T, R, frow, 4, u, cc);
+    if (T >= 2) stash_ld8(a.stash, 1, T - 2, T, R, frow, 4, u, cp);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       dhrec[r] = 0.f; dcrec[r] = 0.f;
-      const float* p = st1 + ((size_t)(T - 1) * R + r) * srs;
-      gi[r] = rv[r] ? p[0] : 0.f; gf[r] = rv[r] ? p[LS_H] : 0.f; gg[r] = rv[r] ? p[2 * LS_H] : 0.f;
-      go[r] = rv[r] ? p[3 * LS_H] : 0.f; cc[r] = rv[r] ? p[4 * LS_H] : 0.f;
-      cp[r] = (rv[r] && T >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+      if (T < 2) cp[r] = 0.f;
     }
     for (int t = T - 1; t >= 0; --t) {
       // prefetch: gates of t-1, cell of t-2
       float ni[8], nf[8], ng[8], no[8], np[8];
+      if (t >= 1) {
+        stash_ld8(a.stash, 1, t - 1, T, R, frow, 0, u, ni); stash_ld8(a.stash, 1, t - 1, T, R, frow, 1, u, nf);
+        stash_ld8(a.stash, 1, t - 1, T, R, frow, 2, u, ng); stash_ld8(a.stash, 1, t - 1, T, R, frow, 3, u, no);
+      }
+      if (t >= 2) stash_ld8(a.stash, 1, t - 2, T, R, frow, 4, u, np);
+      else {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float* p = st1 + ((size_t)(t - 1) * R + r) * srs;
-        const bool ok = rv[r] && t >= 1;
-        ni[r] = ok ? p[0] : 0.f; nf[r] = ok ? p[LS_H] : 0.f; ng[r] = ok ? p[2 * LS_H] : 0.f; no[r] = ok ? p[3 * LS_H] : 0.f;
-        np[r] = (rv[r] && t >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+        for (int r = 0; r < 8; ++r) np[r] = 0.f;
       }
       // gate gradients of step t
 #pragma unroll
@@ -448,28 +462,32 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd
     for (int i = tid; i < 128 * 68 * 2 / 4; i += LS_THREADS) d0[i] = s0[i];
     __threadfence_block();
     __syncthreads();
-    const float* st0 = a.stash + ((size_t)row0 + rl0) * srs + u;
+    const int frow = row0 + rl0;
     float gi[8], gf[8], gg[8], go[8], cc[8], cp[8], dhf[8];
     float dhrec[8], dcrec[8];
+    stash_ld8(a.stash, 0, T - 1, T, R, frow, 0, u, gi); stash_ld8(a.stash, 0, T - 1, T, R, frow, 1, u, gf);
+    stash_ld8(a.stash, 0, T - 1, T, R, frow, 2, u, gg); stash_ld8(a.stash, 0, T - 1, T, R, frow, 3, u, go);
+    stash_ld8(a.stash, 0, T - 1, T, R, frow, 4, u, cc);
+    if (T >= 2) stash_ld8(a.stash, 0, T - 2, T, R, frow, 4, u, cp);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       dhrec[r] = 0.f; dcrec[r] = 0.f;
-      const float* p = st0 + ((size_t)(T - 1) * R + r) * srs;
-      gi[r] = rv[r] ? p[0] : 0.f; gf[r] = rv[r] ? p[LS_H] : 0.f; gg[r] = rv[r] ? p[2 * LS_H] : 0.f;
-      go[r] = rv[r] ? p[3 * LS_H] : 0.f; cc[r] = rv[r] ? p[4 * LS_H] : 0.f;
-      cp[r] = (rv[r] && T >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
+      if (T < 2) cp[r] = 0.f;
       dhf[r] = rv[r] ? a.dh0f[((size_t)(T - 1) * R + row0 + rl0 + r) * LS_H + u] : 0.f;
     }
     for (int t = T - 1; t >= 0; --t) {
       float ni[8], nf[8], ng[8], no[8], np[8], nh[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float* p = st0 + ((size_t)(t - 1) * R + r) * srs;
-        const bool ok = rv[r] && t >= 1;
-        ni[r] = ok ? p[0] : 0.f; nf[r] = ok ? p[LS_H] : 0.f; ng[r] = ok ? p[2 * LS_H] : 0.f; no[r] = ok ? p[3 * LS_H] : 0.f;
-        np[r] = (rv[r] && t >= 2) ? *(p + 4 * LS_H - (size_t)R * srs) : 0.f;
-        nh[r] = ok ? a.dh0f[((size_t)(t - 1) * R + row0 + rl0 + r) * LS_H + u] : 0.f;
+      if (t >= 1) {
+        stash_ld8(a.stash, 0, t - 1, T, R, frow, 0, u, ni); stash_ld8(a.stash, 0, t - 1, T, R, frow, 1, u, nf);
+        stash_ld8(a.stash, 0, t - 1, T, R, frow, 2, u, ng); stash_ld8(a.stash, 0, t - 1, T, R, frow, 3, u, no);
       }
+      if (t >= 2) stash_ld8(a.stash, 0, t - 2, T, R, frow, 4, u, np);
+      else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) np[r] = 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) nh[r] = (rv[r] && t >= 1) ? a.dh0f[((size_t)(t - 1) * R + row0 + rl0 + r) * LS_H + u] : 0.f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float dh = dhf[r] + dhrec[r];
