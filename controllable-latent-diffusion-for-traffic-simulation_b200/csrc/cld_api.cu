@@ -132,6 +132,8 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   h->cfg = *cfg;
   h->device = dev;
   h->num_sms = prop.multiProcessorCount;
+  // bf16-precision mode runs the LSTM decoder (forward and BPTT) on the tensor pipe; CLD_LSTM_SIMT=1 keeps the fp32 SIMT kernels
+  h->use_lstm_tc = cfg->precision == CLD_PREC_BF16 && cfg->hidden == 64 && getenv("CLD_LSTM_SIMT") == nullptr;
   const int T = cfg->horizon;
   const size_t MR = cfg->max_rows;
   size_t ae = (size_t)T * cfg->dims[0];
@@ -168,6 +170,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
 void cld_destroy(CldHandle* h) {
   if (!h) return;
   tc_destroy(h);
+  lstm_tc_destroy(h);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;

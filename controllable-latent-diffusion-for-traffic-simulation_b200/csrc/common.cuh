@@ -111,6 +111,9 @@ struct CldHandle {
   size_t ev_used = 0;
   // bf16 tensor-core path (opaque, owned by unet_tc.cu)
   void* tc = nullptr;
+  // tensor-core LSTM decoder (opaque, owned by kernels_lstm_tc.cu); used when cfg.precision == CLD_PREC_BF16
+  void* lstm_tc = nullptr;
+  bool use_lstm_tc = false;
 };
 
 namespace cld {
@@ -165,6 +168,9 @@ int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act,
                             const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
 int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
                       bool save, int R, cudaStream_t s);
+int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
+                         bool save, int R, cudaStream_t s);
+void lstm_tc_destroy(CldHandle* h);
 int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,
                float* reward, int R, cudaStream_t s);
 // ---- kernels_guidance.cu

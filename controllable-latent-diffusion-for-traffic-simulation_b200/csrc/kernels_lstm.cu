@@ -12,6 +12,7 @@
 // so a time step costs two block barriers.  With SAVE the gate activations and cell states are stashed for the
 // analytic backward (kernels_guidance.cu).
 #include "common.cuh"
+#include "lstm_shared.cuh"
 
 namespace cld {
 
@@ -47,10 +48,6 @@ __device__ __forceinline__ float tanh_acc(float x) {
 }
 }  // namespace
 
-struct DynParams2 {
-  float dt, acce_lo, acce_hi, v_lo, v_hi, max_steer, max_yawvel;
-  float a_mean, a_std, w_mean, w_std;
-};
 
 struct Lstm2Args {
   const float *z, *h0, *curr;            // [R,T,4], [R,64] (cond2hidden output), [R,4]
@@ -88,7 +85,6 @@ __global__ void __launch_bounds__(256) lstm_h0_kernel(const float* __restrict__ 
   if (r0 + b < R) h0[(size_t)(r0 + b) * LS_H + u] = acc;
 }
 
-__device__ __forceinline__ float clip2(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // acc[r][g] += sum over `nkp` k pairs of h[row r][k] * W[k][gate g] for the thread's unit
 __device__ __forceinline__ void lstm_kloop(const float* __restrict__ wp, const float* __restrict__ hsrc, int nkp, uint64_t (&acc)[8][4]) {
@@ -301,48 +297,6 @@ __global__ void lstm_pack_t_kernel(const float* __restrict__ whh, const float* _
   out[idx] = (col < 64) ? whh[(size_t)j * 64 + col] : wih[(size_t)j * in_dim + (col - 64)];
 }
 
-// reverse of the unicycle closed form for one row; writes d(scaled action) [T][2]
-__device__ void unicycle_row_backward2(const float* act, const float* curr, const float* dtr, int T, const DynParams2& a,
-                                       float* scr /*[4][T+1]*/, float* dact) {
-  float* sk = scr; float* psik = scr + (T + 1); float* vbar = scr + 2 * (T + 1); float* msk = scr + 3 * (T + 1);
-  float s = curr[2], psi = curr[3];
-  float vprev = clip2(s, a.v_lo, a.v_hi);
-  sk[0] = s; psik[0] = psi;
-  for (int k = 0; k < T; ++k) {
-    float a_raw = __fadd_rn(__fmul_rn(act[k * 2 + 0], a.a_std), a.a_mean);
-    float w_raw = __fadd_rn(__fmul_rn(act[k * 2 + 1], a.w_std), a.w_mean);
-    float ac = clip2(a_raw, a.acce_lo, a.acce_hi);
-    s = __fadd_rn(s, __fmul_rn(ac, a.dt));
-    float vnext = clip2(s, a.v_lo, a.v_hi);
-    vbar[k] = __fmul_rn(0.5f, __fadd_rn(vprev, vnext));
-    float ve = fabsf(vprev);
-    float yb = fmaxf(fminf(__fmul_rn(a.max_steer, ve), __fdiv_rn(a.max_yawvel, fmaxf(ve, 0.1f))), 0.1f);
-    float w = clip2(w_raw, -yb, yb);
-    psi = __fadd_rn(psi, __fmul_rn(w, a.dt));
-    int m = ((a_raw >= a.acce_lo && a_raw <= a.acce_hi) ? 1 : 0) | ((w_raw >= -yb && w_raw <= yb) ? 2 : 0);
-    msk[k] = __int_as_float(m);
-    sk[k + 1] = s; psik[k + 1] = psi;
-    vprev = vnext;
-  }
-  float Gx = 0.f, Gy = 0.f, Spsi = 0.f, Ss = 0.f, dvbar_next = 0.f, direct_next = 0.f;
-  for (int m = T - 1; m >= 0; --m) {
-    const float gx = dtr[m * 4 + 0], gy = dtr[m * 4 + 1], gv = dtr[m * 4 + 2], gpsi = dtr[m * 4 + 3];
-    Gx += a.dt * gx; Gy += a.dt * gy;
-    float c = cosf(psik[m]), sn = sinf(psik[m]);
-    float dvbar = Gx * c + Gy * sn;
-    float direct = vbar[m] * (-Gx * sn + Gy * c);
-    Spsi += ((m + 1 <= T - 1) ? direct_next : 0.f) + gpsi;
-    float dvhat = 0.5f * (((m + 1 <= T - 1) ? dvbar_next : 0.f) + dvbar) + gv;
-    float s1 = sk[m + 1];
-    if (s1 >= a.v_lo && s1 <= a.v_hi) Ss += dvhat;
-    int mk = __float_as_int(msk[m]);
-    float du0 = (mk & 1) ? a.dt * Ss : 0.f;
-    float du1 = (mk & 2) ? a.dt * Spsi : 0.f;
-    dact[m * 2 + 0] = a.a_std * du0;
-    dact[m * 2 + 1] = a.w_std * du1;
-    dvbar_next = dvbar; direct_next = direct;
-  }
-}
 
 // 8 consecutive rows of stash value v (i, f, g, o, c) of (layer, t, unit u): two 16-byte loads
 __device__ __forceinline__ void stash_ld8(const float* __restrict__ stash, int layer, int t, int T, int R, int row, int v, int u, float (&o)[8]) {
@@ -599,6 +553,7 @@ int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float
                       bool save, int R, cudaStream_t s) {
   DecoderW& w = h->dec;
   if (!w.loaded) return fail(h, CLD_ERR_STATE, "decoder weights not loaded");
+  if (h->use_lstm_tc) return decode_rollout_h0_tc(h, z, h0, curr, act_out, traj_out, save, R, s);
   if (h->cfg.hidden != LS_H || h->cfg.latent_dim != 4) return fail(h, CLD_ERR_UNSUPPORTED, "decoder kernel is specialised for hidden=64, latent=4");
   int rc;
   if ((rc = lstm2_prepare(h, s))) return rc;

@@ -1,0 +1,380 @@
+// LSTM decoder on the tensor pipe (bf16-precision mode): forward + rollout, and the analytic backward (BPTT).
+//   Decoder.forward                         reference models/vae/lstm_vae.py:44-52
+//   convert_action_to_state_and_action      reference models/vae/vae_model.py:100-129,157-173
+//   unicyle_forward_dynamics('parallel')    reference src/tbsim/models/diffuser_helpers.py:573-639
+//   PerturbationGuidance.perturb (backward) reference src/tbsim/utils/guidance_loss.py:2250-2278
+//
+// One CTA owns 32 rows for the whole horizon.  Per time step and layer the gate pre-activations are
+//   gates^T [256 x 32 rows] = W [256 x K] . [x_t ; h_{t-1}]^T [K x 32]
+// i.e. the WEIGHTS are the M operand (two M = 128 tiles, resident in shared memory as fp16, 128B-swizzled) and
+// the 32 rows are the N operand, so a CTA needs only 32 rows to fill a tile and 4 096 rows spread over 128 SMs.
+// The state operand is written by the cell warps as an fp16 hi + lo pair (two accumulating MMA passes): the
+// activations carry ~22 mantissa bits, the weights are rounded to fp16 once (the backward uses the same rounded
+// weights, so it is the exact gradient of the model the forward evaluates).  Accumulators live in TMEM
+// (4 x 32 columns); a cell thread reads ITS lane = one gate row for all 32 rows.  Gate rows are permuted so that
+// lanes j and j + 16 of a warp hold (i, g) and (f, o) of the same hidden unit: the two exchange what they need with
+// warp shuffles, then each updates the cell for 16 of the 32 rows -- no shared-memory exchange, uniform code.
+// The two layers run skewed by one step on separate warp sets; everything is synchronised with mbarriers
+// (MMA completion -> cell warps -> operand ready -> MMA issue).
+//
+// Warp roles (320 threads): warps 0-3 layer-0 cells, warps 4-7 layer-1 cells, warp 8 MMA issuer (one thread),
+// warp 9: stages z_t as an MMA operand, hid2act (lane = row), unicycle rollout at the end.
+#include <cuda_fp16.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "lstm_shared.cuh"
+#include "tc_common.cuh"
+
+namespace cld {
+using namespace tc;
+
+namespace {
+constexpr int LT_RB = 32;                 // rows per CTA = MMA N
+constexpr int LT_H = 64;
+constexpr int LT_THREADS = 320;
+constexpr int LT_WBLK = 16384;            // one weight k-block: 128 gate rows x 64 k fp16
+constexpr int LT_OP = 4096;               // one state operand tile: 32 rows x 64 k fp16
+// forward kernel shared memory (bytes from the 1024-aligned base)
+constexpr int LF_W = 0;                               // [layer][tile][k-block] x 16 KB
+constexpr int LF_H0 = LF_W + 8 * LT_WBLK;             // h0 operand [parity][hi, lo]
+constexpr int LF_H1 = LF_H0 + 4 * LT_OP;              // h1 operand [hi, lo]
+constexpr int LF_Z = LF_H1 + 2 * LT_OP;               // z operand [ring of 3][hi, lo] (k 0..3 used)
+constexpr int LF_H1F = LF_Z + 6 * LT_OP;              // fp32 h1 [parity][64 units][32 rows] for hid2act
+constexpr int LF_HW = LF_H1F + 2 * LT_H * LT_RB * 4;  // hid2act weights [2][64]
+constexpr int LF_BARS = LF_HW + 2 * LT_H * 4;         // m0, m1, e0, e1, a, z[3]
+constexpr int LF_TMEM = LF_BARS + 8 * 8;
+constexpr int LF_SMEM = LF_TMEM + 16;
+static_assert(LF_SMEM + 1024 <= 232448, "forward shared memory");
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // D fp32, A/B fp16, K-major
+}
+__device__ __forceinline__ float ex2f(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// s * sigmoid(-k x / log2e) + o  with (k, s, o) = (-log2e, 1, 0): sigmoid(x) ; (-2 log2e, 2, -1): tanh(x)
+__device__ __forceinline__ float act_gen(float x, float k, float s, float o) { return fmaf(s, rcpf(1.0f + ex2f(k * x)), o); }
+__device__ __forceinline__ float sigmoidf_(float x) { return rcpf(1.0f + ex2f(-LOG2E * x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(2.0f, rcpf(1.0f + ex2f(-2.0f * LOG2E * x)), -1.0f); }
+
+// mbarrier wait with a watchdog: a protocol bug traps (launch error) instead of hanging the device
+__device__ __noinline__ void lt_wait_timeout(uint32_t bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("lstm_tc: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void lt_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (!mbar_try_wait(bar, parity)) lt_wait_timeout(bar, parity, tag);
+}
+
+// fp16 hi/lo split of v, stored at element (row, k) of the 128B-swizzled operand tiles `hi` and `hi + LT_OP`
+__device__ __forceinline__ void store_split(uint8_t* hi, int row, int k, float v) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(k >> 3)) + (uint32_t)(k & 7) * 2u;
+  *reinterpret_cast<__half*>(hi + off) = h;
+  *reinterpret_cast<__half*>(hi + LT_OP + off) = l;
+}
+
+// gate row held by lane m (0..127) of M tile `tile`: lanes j, j + 16 of quadrant q serve unit 16 q + j
+__host__ __device__ inline int gate_row_of(int tile, int m) {
+  const int q = m >> 5, l = m & 31, j = l & 15, is_b = l >> 4, u = 16 * q + j;
+  const int gate = tile == 0 ? (is_b ? 1 : 0) : (is_b ? 3 : 2);      // nn.LSTM order i, f, g, o
+  return gate * LT_H + u;
+}
+}  // namespace
+
+struct LstmTcArgs {
+  const float *z, *h0, *curr;
+  const uint8_t* wblob;                  // packed fp16 forward weights, 8 x 16 KB
+  const float *b0, *b1;                  // b_ih + b_hh per layer [256]
+  const float *h2a_w, *h2a_b;
+  float *act_out, *traj_out, *stash;
+  int R, T;
+  DynParams2 dyn;
+};
+
+// forward weight blob: [layer][tile][k-block][128 lanes][64 k] fp16, swizzled.  Layer 0: k-block 0 = W_hh0, k-block 1 =
+// W_ih0 (k < 4, rest zero).  Layer 1: k-block 0 = W_ih1 (input h0_t), k-block 1 = W_hh1.
+__global__ void lstm_tc_pack_fwd_kernel(uint8_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
+                                        const float* __restrict__ wih1, const float* __restrict__ whh1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 8 * 128 * 64) return;
+  const int k = idx & 63, m = (idx >> 6) & 127, blk = idx >> 13;
+  const int kb = blk & 1, tile = (blk >> 1) & 1, layer = blk >> 2;
+  const int row = gate_row_of(tile, m);
+  float v;
+  if (layer == 0) v = kb == 0 ? whh0[row * 64 + k] : (k < 4 ? wih0[row * 4 + k] : 0.f);
+  else v = kb == 0 ? wih1[row * 64 + k] : whh1[row * 64 + k];
+  *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const LstmTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * LT_RB, T = a.T, R = a.R;
+  const uint32_t bars = smem_u32(sm + LF_BARS);
+  const uint32_t bar_m0 = bars, bar_m1 = bars + 8, bar_e0 = bars + 16, bar_e1 = bars + 24, bar_a = bars + 32, bar_z = bars + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + LF_TMEM);
+  float* h1f = reinterpret_cast<float*>(sm + LF_H1F);
+  float* hw = reinterpret_cast<float*>(sm + LF_HW);
+
+  // ---- prologue: weights, zeroed operand tiles, initial state h_{-1} = cond2hidden(cond) for both layers
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
+    uint4* dst = reinterpret_cast<uint4*>(sm + LF_W);
+    for (int i = tid; i < 8 * LT_WBLK / 16; i += LT_THREADS) dst[i] = src[i];
+    uint4* ops = reinterpret_cast<uint4*>(sm + LF_H0);
+    for (int i = tid; i < (LF_H1F - LF_H0) / 16; i += LT_THREADS) ops[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
+    if (tid == 0) {
+      mbar_init(bar_m0, 1); mbar_init(bar_m1, 1); mbar_init(bar_e0, 4); mbar_init(bar_e1, 4); mbar_init(bar_a, 1);
+      mbar_init(bar_z, 1); mbar_init(bar_z + 8, 1); mbar_init(bar_z + 16, 1);
+      fence_barrier_init();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < LT_RB * LT_H; i += LT_THREADS) {
+    const int rl = i >> 6, k = i & 63;
+    const float v = (row0 + rl < R) ? a.h0[(size_t)(row0 + rl) * LT_H + k] : 0.f;
+    store_split(sm + LF_H0 + 2 * LT_OP, rl, k, v);          // parity 1 = step -1
+    store_split(sm + LF_H1, rl, k, v);
+  }
+  if (warp == 9) {                                           // z_0, z_1, z_2
+    for (int t = 0; t < 3 && t < T; ++t) {
+      float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + lane < R) zv = reinterpret_cast<const float4*>(a.z)[(size_t)(row0 + lane) * T + t];
+      uint8_t* zt = sm + LF_Z + t * 2 * LT_OP;
+      store_split(zt, lane, 0, zv.x); store_split(zt, lane, 1, zv.y); store_split(zt, lane, 2, zv.z); store_split(zt, lane, 3, zv.w);
+    }
+  }
+  if (warp == 8) { tmem_alloc(smem_u32(tmem_slot), 128); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== cell warps =====================
+    const int L = warp >> 2, q = warp & 3, j = lane & 15;
+    const bool is_b = lane >= 16;
+    const int u = 16 * q + j;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * 64);
+    const float* bias = L == 0 ? a.b0 : a.b1;
+    const float bias0 = bias[(is_b ? 64 : 0) + u];            // tile 0: i | f
+    const float bias1 = bias[(is_b ? 192 : 128) + u];         // tile 1: g | o
+    const float k1 = is_b ? -LOG2E : -2.0f * LOG2E, s1c = is_b ? 1.0f : 2.0f, o1c = is_b ? 0.0f : -1.0f;
+    const uint32_t bar_m = L == 0 ? bar_m0 : bar_m1, bar_e = L == 0 ? bar_e0 : bar_e1;
+    const int rbase = is_b ? 16 : 0;
+    float c[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) c[r] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      lt_wait(bar_m, (uint32_t)t & 1u, 1 + L);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
+      tmem_wait_ld();
+      float a0[32], a1[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        a0[r] = sigmoidf_(__uint_as_float(v0[r]) + bias0);
+        a1[r] = act_gen(__uint_as_float(v1[r]) + bias1, k1, s1c, o1c);
+      }
+      if (SAVE) {
+        float* s0 = a.stash + stash_index(L, t, T, R, row0, is_b ? 1 : 0, u);
+        float* s1 = a.stash + stash_index(L, t, T, R, row0, is_b ? 3 : 2, u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          float4* d0 = reinterpret_cast<float4*>(s0 + (size_t)b * (5 * 64 * 8));
+          float4* d1 = reinterpret_cast<float4*>(s1 + (size_t)b * (5 * 64 * 8));
+          d0[0] = make_float4(a0[8 * b + 0], a0[8 * b + 1], a0[8 * b + 2], a0[8 * b + 3]);
+          d0[1] = make_float4(a0[8 * b + 4], a0[8 * b + 5], a0[8 * b + 6], a0[8 * b + 7]);
+          d1[0] = make_float4(a1[8 * b + 0], a1[8 * b + 1], a1[8 * b + 2], a1[8 * b + 3]);
+          d1[1] = make_float4(a1[8 * b + 4], a1[8 * b + 5], a1[8 * b + 6], a1[8 * b + 7]);
+        }
+      }
+      float hn[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float p_lo = a0[r] * a1[r], p_hi = a0[16 + r] * a1[16 + r];
+        const float x1 = __shfl_xor_sync(0xffffffffu, is_b ? a0[r] : p_hi, 16);   // A lane <- f[r] ; B lane <- (i g)[16 + r]
+        const float x2 = __shfl_xor_sync(0xffffffffu, a1[r], 16);                 // A lane <- o[r]
+        const float fg = is_b ? a0[16 + r] : x1;
+        const float pin = is_b ? x1 : p_lo;
+        const float og = is_b ? a1[16 + r] : x2;
+        c[r] = fmaf(fg, c[r], pin);
+        hn[r] = og * tanhf_(c[r]);
+      }
+      if (SAVE) {
+        float* sc = a.stash + stash_index(L, t, T, R, row0 + rbase, 4, u);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float4* d = reinterpret_cast<float4*>(sc + (size_t)b * (5 * 64 * 8));
+          d[0] = make_float4(c[8 * b + 0], c[8 * b + 1], c[8 * b + 2], c[8 * b + 3]);
+          d[1] = make_float4(c[8 * b + 4], c[8 * b + 5], c[8 * b + 6], c[8 * b + 7]);
+        }
+      }
+      if (L == 0) {
+        uint8_t* dst = sm + LF_H0 + (t & 1) * 2 * LT_OP;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) store_split(dst, rbase + r, u, hn[r]);
+      } else {
+        if (t >= 1) lt_wait(bar_a, (uint32_t)(t - 1) & 1u, 3);      // hid2act of step t - 1 is done (implies t - 2: this h1f buffer is free)
+        uint8_t* dst = sm + LF_H1;
+        float* hf = h1f + (t & 1) * (LT_H * LT_RB) + u * LT_RB + rbase;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { store_split(dst, rbase + r, u, hn[r]); hf[r] = hn[r]; }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_e);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    // all lanes walk the loop and wait; lane 0 issues
+    constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
+    const uint32_t w_u = smem_u32(sm + LF_W);
+    const uint64_t dsc = make_desc_sw128(0, 1024);
+    auto wdesc = [&](int layer, int tile, int kb) { return dsc + ((w_u + (uint32_t)(((layer * 2 + tile) * 2 + kb) * LT_WBLK)) >> 4); };
+    auto odesc = [&](int off) { return dsc + (smem_u32(sm + off) >> 4); };
+    // nk K = 16 steps of one k-block against the hi and the lo operand tile
+    auto kblock = [&](uint32_t d, uint64_t ad, uint64_t bd_hi, int nk, bool& first) {
+      for (int part = 0; part < 2; ++part) {
+        const uint64_t bd = bd_hi + (uint64_t)(part * (LT_OP >> 4));
+        for (int k = 0; k < nk; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, IDESC, first ? 0u : 1u); first = false; }
+      }
+    };
+    for (int s = 0; s <= T; ++s) {
+      const int hp = (s + 1) & 1;                            // parity of the buffer that holds h0_{s-1}
+      if (s < T) {
+        lt_wait(bar_z + 8 * (s % 3), (uint32_t)(s / 3) & 1u, 10);
+        if (s >= 1) lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 11);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int tile = 0; tile < 2; ++tile) {
+            bool first = true;
+            const uint32_t d = tmem_base + (uint32_t)(tile * 32);
+            kblock(d, wdesc(0, tile, 0), odesc(LF_H0 + hp * 2 * LT_OP), 4, first);
+            kblock(d, wdesc(0, tile, 1), odesc(LF_Z + (s % 3) * 2 * LT_OP), 1, first);
+          }
+          umma_commit(bar_m0);
+        }
+        __syncwarp();
+      }
+      if (s >= 1) {
+        if (s == T) lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 12);
+        if (s >= 2) lt_wait(bar_e1, (uint32_t)(s - 2) & 1u, 13);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int tile = 0; tile < 2; ++tile) {
+            bool first = true;
+            const uint32_t d = tmem_base + 64u + (uint32_t)(tile * 32);
+            kblock(d, wdesc(1, tile, 0), odesc(LF_H0 + hp * 2 * LT_OP), 4, first);
+            kblock(d, wdesc(1, tile, 1), odesc(LF_H1), 4, first);
+          }
+          umma_commit(bar_m1);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== warp 9: z staging, hid2act, rollout =====================
+    const int row = row0 + lane;
+    const bool valid = row < R;
+    const float hb0 = a.h2a_b[0], hb1 = a.h2a_b[1];
+    if (lane == 0) { mbar_arrive(bar_z); mbar_arrive(bar_z + 8); mbar_arrive(bar_z + 16); }      // z_0..z_2 were staged in the prologue
+    float4 zn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && 3 < T) zn = reinterpret_cast<const float4*>(a.z)[(size_t)row * T + 3];
+    for (int s = 1; s <= T; ++s) {
+      {                                                        // hid2act for step s - 1
+        const int t = s - 1;
+        lt_wait(bar_e1, (uint32_t)t & 1u, 20);
+        const float* hf = h1f + (t & 1) * (LT_H * LT_RB) + lane;
+        float s0 = hb0, s1 = hb1;
+#pragma unroll 16
+        for (int k = 0; k < LT_H; ++k) {
+          const float hv = hf[k * LT_RB];
+          s0 = fmaf(hw[k], hv, s0); s1 = fmaf(hw[LT_H + k], hv, s1);
+        }
+        if (valid) *reinterpret_cast<float2*>(a.act_out + ((size_t)row * T + t) * 2) = make_float2(s0, s1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+      }
+      if (s + 2 < T) {
+        // stage z_{s+2} over z_{s-1}: E1(s-1) done => M1(s-1) done => M0(s) and M0(s-1) done (issue order)
+        const int slot = (s + 2) % 3;
+        uint8_t* zt = sm + LF_Z + slot * 2 * LT_OP;
+        store_split(zt, lane, 0, zn.x); store_split(zt, lane, 1, zn.y); store_split(zt, lane, 2, zn.z); store_split(zt, lane, 3, zn.w);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_z + 8 * slot);
+        zn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && s + 3 < T) zn = reinterpret_cast<const float4*>(a.z)[(size_t)row * T + s + 3];
+      }
+    }
+    if (valid && a.traj_out)
+      unicycle_row_forward2(a.act_out + (size_t)row * T * 2, a.curr + (size_t)row * 4, T, a.dyn, a.traj_out + (size_t)row * T * 6);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct LstmTcState {
+  uint8_t* wfwd = nullptr;
+  uint8_t* wbwd = nullptr;
+};
+
+static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
+  if (h->lstm_tc) return 0;
+  DecoderW& w = h->dec;
+  LstmTcState* st = new LstmTcState();
+  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wfwd, 8 * LT_WBLK));
+  h->allocs.push_back(st->wfwd);
+  lstm_tc_pack_fwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wfwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
+  CLD_LAUNCH_OK(h, "lstm_tc_pack_fwd_kernel");
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  h->lstm_tc = st;
+  return 0;
+}
+
+void lstm_tc_destroy(CldHandle* h) {
+  if (h->lstm_tc) { delete reinterpret_cast<LstmTcState*>(h->lstm_tc); h->lstm_tc = nullptr; }
+}
+
+int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
+                         bool save, int R, cudaStream_t s) {
+  DecoderW& w = h->dec;
+  if (!w.loaded) return fail(h, CLD_ERR_STATE, "decoder weights not loaded");
+  if (h->cfg.hidden != LT_H || h->cfg.latent_dim != 4) return fail(h, CLD_ERR_UNSUPPORTED, "decoder kernel is specialised for hidden=64, latent=4");
+  int rc;
+  if ((rc = lstm_tc_prepare(h, s))) return rc;
+  const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
+  LstmTcArgs a;
+  a.z = z; a.h0 = h0; a.curr = curr; a.wblob = st->wfwd; a.b0 = w.b0; a.b1 = w.b1;
+  a.h2a_w = w.h2a_w; a.h2a_b = w.h2a_b; a.act_out = act_out; a.traj_out = traj_out; a.stash = save ? h->stash : nullptr;
+  a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
+  const int grid = (R + LT_RB - 1) / LT_RB;
+  if (save) lstm_decode_tc_kernel<true><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  else lstm_decode_tc_kernel<false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  CLD_LAUNCH_OK(h, "lstm_decode_tc_kernel");
+  return 0;
+}
+
+}  // namespace cld

@@ -2,6 +2,7 @@
 //   umma_bench : for N in {16,32,64,128,256} and nacc in {1,2,4}: cycles per MMA over 256 MMAs that rotate over
 //   `nacc` independent TMEM accumulators (nacc = 1: every MMA depends on the previous one's accumulator).
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../controllable-latent-diffusion-for-traffic-simulation_b200/csrc/tc_common.cuh"
@@ -37,14 +38,15 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int sa
     long long t1 = clock64();
     mbar_wait(smem_u32(&bar), 0);
     long long t2 = clock64();
-    if (tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (tid == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int grid = argc > 1 ? atoi(argv[1]) : 1;
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
   const int cnt = 256;
@@ -53,7 +55,7 @@ int main() {
       if (nacc * N > 512) continue;
       long long h[2];
       for (int rep = 0; rep < 2; ++rep) {
-        bench<<<1, 128, 65536>>>(N, nacc, cnt, 0, d);
+        bench<<<grid, 128, 65536>>>(N, nacc, cnt, 0, d);
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       }
       cudaError_t e = cudaGetLastError();
