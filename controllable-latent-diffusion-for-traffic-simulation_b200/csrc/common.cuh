@@ -170,6 +170,8 @@ int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float
                       bool save, int R, cudaStream_t s);
 int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
                          bool save, int R, cudaStream_t s);
+int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
+                              const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
 void lstm_tc_destroy(CldHandle* h);
 int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,
                float* reward, int R, cudaStream_t s);

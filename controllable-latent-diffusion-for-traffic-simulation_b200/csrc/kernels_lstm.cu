@@ -11,6 +11,8 @@
 // run skewed by one step (iteration i: layer 0 computes step i, layer 1 computes step i - 1; both read h0_{i-1}),
 // so a time step costs two block barriers.  With SAVE the gate activations and cell states are stashed for the
 // analytic backward (kernels_guidance.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lstm_shared.cuh"
 
@@ -577,6 +579,7 @@ int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act,
                             const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   DecoderW& w = h->dec;
   int rc;
+  if (h->use_lstm_tc && !getenv("CLD_LSTM_BWD_SIMT")) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, g, z_out, grad_out, R, s);
   if ((rc = lstm2_prepare(h, s))) return rc;
   const CldConfig& c = h->cfg;
   if (c.horizon > CLD_MAX_T) return fail(h, CLD_ERR_UNSUPPORTED, "horizon exceeds CLD_MAX_T");

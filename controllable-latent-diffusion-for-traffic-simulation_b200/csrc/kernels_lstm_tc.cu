@@ -62,11 +62,15 @@ __device__ __forceinline__ float tanhf_(float x) { return fmaf(2.0f, rcpf(1.0f +
 // mbarrier wait with a watchdog: a protocol bug traps (launch error) instead of hanging the device
 __device__ __noinline__ void lt_wait_timeout(uint32_t bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
+  bool said = false;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("lstm_tc: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
+    const long long dt = clock64() - t0;
+    if (dt > 2000000000ll && !said) {
+      said = true;
+      if ((threadIdx.x & 31) == 0)
+        printf("lstm_tc: mbarrier wait timed out (tag %d, block %d, warp %d, parity %u)\n", tag, (int)blockIdx.x, (int)(threadIdx.x >> 5), parity);
     }
+    if (dt > 4000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void lt_wait(uint32_t bar, uint32_t parity, int tag) {
@@ -333,6 +337,289 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward (BPTT) on the tensor pipe.  Per step and layer:
+//   [dh_rec (64) ; dx (64)]^T [128 x 32 rows] = [W_hh ; W_ih]^T [128 x 256] . dgates^T [256 x 32]
+// The M tile's lanes j / j + 16 of a quadrant are (dh_rec[u], dx[u]) of unit u = 16 q + j (layer 1: dx = gradient
+// into h0_t; layer 0: dx = dz_t for u < 4).  The gate gradients are the N operand, written by the cell warps as an
+// fp16 hi + lo pair after an exact per-row power-of-two scaling (the backward is linear in d(traj) per row), so the
+// fp16 range is never the limit and the operand carries ~22 bits relative to the row's largest gradient.
+// A cell thread owns one unit and one 8-row stash block: (unit, rows) -> i, f, g, o, c are two 16-byte loads each.
+// Layer 0 runs one step behind layer 1 (it needs layer 1's dx of the same time step); layer 1's accumulator is
+// double-buffered in TMEM so that layer 0 may still be reading dx while layer 1's next product is written.
+// Warp roles (576 threads): warps 0-7 layer-1 cells, 8-15 layer-0 cells (warp & 3 = TMEM lane quadrant,
+// (warp >> 2) & 1 = row half), warp 16 MMA issuer, warp 17 idle after the prologue.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int LB_THREADS = 576;
+constexpr int LBK_W = 0;                                // [layer][gate k-block] x 16 KB
+constexpr int LBK_DG = LBK_W + 8 * LT_WBLK;             // [layer][hi, lo][gate] x 4 KB
+constexpr int LBK_DACT = LBK_DG + 16 * LT_OP;           // fp32 [32 rows][T][2], scaled
+__host__ __device__ constexpr int lbk_scale(int T) { return LBK_DACT + LT_RB * T * 2 * 4; }      // float [32] 1 / scale
+__host__ __device__ constexpr int lbk_hw(int T) { return lbk_scale(T) + LT_RB * 4; }             // hid2act weights [2][64]
+__host__ __device__ constexpr int lbk_bars(int T) { return lbk_hw(T) + 2 * LT_H * 4; }           // m1[2], m0, e1, e0
+__host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 6 * 8 + 16; }
+// prologue scratch aliases the weight tiles: act [32][T][2], dtraj [32][T][4], scan scratch [32][4][T+1]
+}  // namespace
+
+struct BwdTcArgs {
+  const float *z_mean, *act, *curr, *dtraj, *stash;
+  const uint8_t* wblob;                 // packed fp16 backward weights, 8 x 16 KB
+  const float* h2a_w;
+  float *z_out, *grad_out;
+  int R, T;
+  DynParams2 dyn;
+  int optimizer; float lr;
+};
+
+// backward weight blob: [layer][gate g][128 lanes][64 k] fp16, swizzled; k-block g covers gate rows g*64 .. g*64+63
+__global__ void lstm_tc_pack_bwd_kernel(uint8_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
+                                        const float* __restrict__ wih1, const float* __restrict__ whh1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 8 * 128 * 64) return;
+  const int k = idx & 63, m = (idx >> 6) & 127, blk = idx >> 13;
+  const int g = blk & 3, layer = blk >> 2;
+  const int q = m >> 5, l = m & 31, j = l & 15, is_b = l >> 4, u = 16 * q + j;
+  const int grow = g * LT_H + k;
+  float v;
+  if (!is_b) v = (layer == 0 ? whh0 : whh1)[grow * 64 + u];
+  else v = layer == 0 ? (u < 4 ? wih0[grow * 4 + u] : 0.f) : wih1[grow * 64 + u];
+  *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
+}
+
+__device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+__global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const BwdTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * LT_RB, T = a.T, R = a.R;
+  const uint32_t bars = smem_u32(sm + lbk_bars(T));
+  // bar_m1 alternates between two barriers by step parity: layer 0 (one step behind) waits for MMA_L1(i) while
+  // MMA_L1(i + 1) may already complete; a barrier's next completion (step i + 2) needs layer 0's arrival for step i
+  const uint32_t bar_m1 = bars, bar_m0 = bars + 16, bar_e1 = bars + 24, bar_e0 = bars + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + lbk_bars(T) + 48);
+  float* dact = reinterpret_cast<float*>(sm + LBK_DACT);
+  float* inv_scale = reinterpret_cast<float*>(sm + lbk_scale(T));
+  float* hw = reinterpret_cast<float*>(sm + lbk_hw(T));
+
+  // ---- prologue: d(traj) -> d(scaled action) per row (reverse unicycle scans), per-row scale, weights
+  {
+    float* act_s = reinterpret_cast<float*>(sm + LBK_W);             // [32][T][2] (scratch aliases the weight tiles)
+    float* dtr_s = act_s + LT_RB * T * 2;                            // [32][T][4]
+    float* scr_s = dtr_s + LT_RB * T * 4;                            // [32][4][T+1]
+    const int nrow = min(LT_RB, R - row0);
+    for (int i = tid; i < nrow * T * 2 / 4; i += LB_THREADS)
+      reinterpret_cast<float4*>(act_s)[i] = reinterpret_cast<const float4*>(a.act + (size_t)row0 * T * 2)[i];
+    for (int i = tid; i < nrow * T; i += LB_THREADS)
+      reinterpret_cast<float4*>(dtr_s)[i] = reinterpret_cast<const float4*>(a.dtraj + (size_t)row0 * T * 4)[i];
+    uint4* dg = reinterpret_cast<uint4*>(sm + LBK_DG);
+    for (int i = tid; i < 16 * LT_OP / 16; i += LB_THREADS) dg[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
+    if (tid == 0) {
+      mbar_init(bar_m1, 1); mbar_init(bar_m1 + 8, 1); mbar_init(bar_m0, 1); mbar_init(bar_e1, 8); mbar_init(bar_e0, 8);
+      fence_barrier_init();
+    }
+    if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 128); tmem_relinquish(); }
+    __syncthreads();
+    if (tid < LT_RB) {
+      float* da = dact + tid * T * 2;
+      float sc = 1.f;
+      if (row0 + tid < R) {
+        unicycle_row_backward2(act_s + tid * T * 2, a.curr + (size_t)(row0 + tid) * 4, dtr_s + tid * T * 4, T, a.dyn,
+                               scr_s + tid * 4 * (T + 1), da);
+        float m = 0.f;
+        for (int i = 0; i < 2 * T; ++i) m = fmaxf(m, fabsf(da[i]));
+        if (m > 0.f && m < 3.0e38f) {
+          int e;
+          frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+          e = max(-100, min(100, e));
+          sc = ldexpf(1.f, -e);                // scaled maximum in [0.5, 1)
+        }
+        for (int i = 0; i < 2 * T; ++i) da[i] *= sc;
+      } else {
+        for (int i = 0; i < 2 * T; ++i) da[i] = 0.f;
+      }
+      inv_scale[tid] = 1.f / sc;
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
+    uint4* dst = reinterpret_cast<uint4*>(sm + LBK_W);
+    for (int i = tid; i < 8 * LT_WBLK / 16; i += LB_THREADS) dst[i] = src[i];
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: layer-1 accumulator [parity][32], layer-0 accumulator at 64
+
+  if (warp < 16) {
+    // ===================== cell-gradient warps =====================
+    const int L = warp < 8 ? 1 : 0;
+    const int q = warp & 3, rh = (warp >> 2) & 1, j = lane & 15;
+    const bool is_b = lane >= 16;
+    const int u = 16 * q + j;
+    const int rb = rh * 2 + (is_b ? 1 : 0);                 // this thread's 8-row block inside the CTA's 32 rows
+    const int rloc = rb * 8;
+    const uint32_t lane_t = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float hw0 = hw[u], hw1 = hw[LT_H + u];
+    const uint32_t bar_e = L ? bar_e1 : bar_e0;
+    uint8_t* dgt = sm + LBK_DG + (L ? 0 : 8 * LT_OP);       // [hi, lo][gate] tiles of this layer
+    float dcrec[8], cprev[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dcrec[r] = 0.f;
+    const bool dz_lane = (L == 0) && q == 0 && is_b && j < 4;
+    for (int i = 0; i <= T; ++i) {
+      const int t = T - 1 - i;                                // time step of this iteration (i < T)
+      float gi[8], gf[8], gg[8], go[8], cc[8];
+      if (i < T) {
+        // stash loads first: they do not depend on the MMA and complete while the thread waits below
+        ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 0, u), gi);
+        ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 1, u), gf);
+        ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 2, u), gg);
+        ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 3, u), go);
+        ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 4, u), cc);
+        if (t >= 1) ld8(a.stash + stash_index(L, t - 1, T, R, row0 + rloc, 4, u), cprev);
+        else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) cprev[r] = 0.f;
+        }
+      }
+      float dh[8];
+      uint32_t v0[16];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) dh[r] = 0.f;
+      if (L == 1) {
+        if (i >= T) break;
+        if (i >= 1) {
+          lt_wait(bar_m1 + 8 * ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u, 31000 + i);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16(lane_t + (uint32_t)(((i - 1) & 1) * 32 + rh * 16), v);      // A lanes: dh_rec[u] for this row half
+          tmem_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float x = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[8 + r]), 16);    // B lane <- A lane's rows 8..15
+            dh[r] = is_b ? x : __uint_as_float(v[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float2 da = *reinterpret_cast<const float2*>(dact + ((rloc + r) * T + t) * 2);
+          dh[r] = fmaf(hw0, da.x, fmaf(hw1, da.y, dh[r]));
+        }
+      } else {
+        if (i < T) lt_wait(bar_m1 + 8 * (i & 1), (uint32_t)(i >> 1) & 1u, 33000 + i);        // checked first: must be observed before MMA_L1(i + 1) completes
+        if (i >= 1) {
+          lt_wait(bar_m0, (uint32_t)(i - 1) & 1u, 32000 + i);
+          tc_fence_after();
+          tmem_ld16(lane_t + (uint32_t)(64 + rh * 16), v0);                     // A: dh_rec0[u] ; B (u < 4): dz of step i - 1
+          tmem_wait_ld();
+        }
+        if (i < T) {
+          tc_fence_after();
+          uint32_t v1[16];
+          tmem_ld16(lane_t + (uint32_t)((i & 1) * 32 + rh * 16), v1);           // B lanes: dx1[u] = d(loss)/d(h0_t)
+          tmem_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float rec_lo = i >= 1 ? __uint_as_float(v0[r]) : 0.f, rec_hi = i >= 1 ? __uint_as_float(v0[8 + r]) : 0.f;
+            const float send = is_b ? __uint_as_float(v1[r]) : rec_hi;           // B sends dx rows 0..7 ; A sends dh_rec rows 8..15
+            const float x = __shfl_xor_sync(0xffffffffu, send, 16);
+            dh[r] = is_b ? (__uint_as_float(v1[8 + r]) + x) : (rec_lo + x);
+          }
+        }
+      }
+      if (i < T) {
+      // ---- gate gradients of this thread's (unit, 8 rows)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float tc = tanhf_(cc[r]);
+        const float dc = fmaf(dh[r] * go[r], 1.f - tc * tc, dcrec[r]);
+        const float d_i = dc * gg[r] * gi[r] * (1.f - gi[r]);
+        const float d_f = dc * cprev[r] * gf[r] * (1.f - gf[r]);
+        const float d_g = dc * gi[r] * (1.f - gg[r] * gg[r]);
+        const float d_o = dh[r] * tc * go[r] * (1.f - go[r]);
+        dcrec[r] = dc * gf[r];
+        const int row = rloc + r;
+        const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(u >> 3)) + (uint32_t)(u & 7) * 2u;
+        const float dv[4] = {d_i, d_f, d_g, d_o};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const __half h = __float2half_rn(dv[g]);
+          const __half l = __float2half_rn(dv[g] - __half2float(h));
+          *reinterpret_cast<__half*>(dgt + g * LT_OP + off) = h;
+          *reinterpret_cast<__half*>(dgt + (4 + g) * LT_OP + off) = l;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_e);
+      }
+      if (dz_lane && i >= 1) {
+        // first optimizer step on z (guidance_loss.py:2250-2278) for step index i - 1 = time t + 1, latent channel j;
+        // off the critical path: the gate gradients of this step are already published
+        const int tz = t + 1;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int rl = rh * 16 + r;
+          if (row0 + rl < R) {
+            const size_t gi_ = ((size_t)(row0 + rl) * T + tz) * 4 + j;
+            const float g = __uint_as_float(v0[r]) * inv_scale[rl], z = a.z_mean[gi_];
+            float zn;
+            if (a.optimizer == CLD_OPT_ADAM) {
+              const float m = 0.1f * g;
+              const float vv = (0.001f * g) * g;
+              const float denom = sqrtf(vv) / 0.03162277660168379f + 1e-8f;
+              zn = z - (a.lr / 0.1f) * (m / denom);
+            } else {
+              zn = z - a.lr * g;
+            }
+            a.z_out[gi_] = zn;
+            if (a.grad_out) a.grad_out[gi_] = g;
+          }
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
+    const uint32_t w_u = smem_u32(sm + LBK_W), dg_u = smem_u32(sm + LBK_DG);
+    const uint64_t dsc = make_desc_sw128(0, 1024);
+    auto product = [&](int layer, uint32_t d) {
+      bool first = true;
+      for (int part = 0; part < 2; ++part)
+        for (int g = 0; g < 4; ++g) {
+          const uint64_t ad = dsc + ((w_u + (uint32_t)((layer * 4 + g) * LT_WBLK)) >> 4);
+          const uint64_t bd = dsc + ((dg_u + (uint32_t)(((layer ? 0 : 8) + part * 4 + g) * LT_OP)) >> 4);
+          for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, IDESC, first ? 0u : 1u); first = false; }
+        }
+    };
+    for (int s = 0; s <= T; ++s) {
+      if (s < T) {
+        lt_wait(bar_e1, (uint32_t)s & 1u, 40000 + s);
+        tc_fence_after();
+        if (lane == 0) { product(1, tmem_base + (uint32_t)((s & 1) * 32)); umma_commit(bar_m1 + 8 * (s & 1)); }
+        __syncwarp();
+      }
+      if (s >= 1) {
+        lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 41000 + s);
+        tc_fence_after();
+        if (lane == 0) { product(0, tmem_base + 64u); umma_commit(bar_m0); }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct LstmTcState {
@@ -350,6 +637,14 @@ static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
   CLD_LAUNCH_OK(h, "lstm_tc_pack_fwd_kernel");
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wbwd, 8 * LT_WBLK));
+  h->allocs.push_back(st->wbwd);
+  lstm_tc_pack_bwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wbwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
+  CLD_LAUNCH_OK(h, "lstm_tc_pack_bwd_kernel");
+  if (lbk_smem(h->cfg.horizon) + 1024 > 232448) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the tensor-core LSTM backward");
+  if (LT_RB * (h->cfg.horizon * 6 + 4 * (h->cfg.horizon + 1)) * 4 > 8 * LT_WBLK)
+    return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the LSTM backward prologue scratch");
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
   h->lstm_tc = st;
   return 0;
 }
@@ -374,6 +669,21 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
   if (save) lstm_decode_tc_kernel<true><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
   else lstm_decode_tc_kernel<false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_decode_tc_kernel");
+  return 0;
+}
+
+
+int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
+                              const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+  int rc;
+  if ((rc = lstm_tc_prepare(h, s))) return rc;
+  const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
+  BwdTcArgs a;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash; a.wblob = st->wbwd;
+  a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
+  a.optimizer = g->optimizer; a.lr = g->lr;
+  lstm_backward_tc_kernel<<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
+  CLD_LAUNCH_OK(h, "lstm_backward_tc_kernel");
   return 0;
 }
 
