@@ -366,6 +366,7 @@ struct BwdTcArgs {
   const uint8_t* wblob;                 // packed fp16 backward weights, 8 x 16 KB
   const float* h2a_w;
   float *z_out, *grad_out;
+  float* dzbuf;                         // [R][T][4] scratch for the scaled dz (the d(traj) workspace: its rows are consumed in the prologue)
   int R, T;
   DynParams2 dyn;
   int optimizer; float lr;
@@ -561,27 +562,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       if (lane == 0) mbar_arrive(bar_e);
       }
       if (dz_lane && i >= 1) {
-        // first optimizer step on z (guidance_loss.py:2250-2278) for step index i - 1 = time t + 1, latent channel j;
-        // off the critical path: the gate gradients of this step are already published
+        // dz (still scaled) of step index i - 1 = time t + 1, latent channel j: parked in dzbuf, fire-and-forget stores;
+        // the optimizer step runs over the CTA's block after the loop
         const int tz = t + 1;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const int rl = rh * 16 + r;
-          if (row0 + rl < R) {
-            const size_t gi_ = ((size_t)(row0 + rl) * T + tz) * 4 + j;
-            const float g = __uint_as_float(v0[r]) * inv_scale[rl], z = a.z_mean[gi_];
-            float zn;
-            if (a.optimizer == CLD_OPT_ADAM) {
-              const float m = 0.1f * g;
-              const float vv = (0.001f * g) * g;
-              const float denom = sqrtf(vv) / 0.03162277660168379f + 1e-8f;
-              zn = z - (a.lr / 0.1f) * (m / denom);
-            } else {
-              zn = z - a.lr * g;
-            }
-            a.z_out[gi_] = zn;
-            if (a.grad_out) a.grad_out[gi_] = g;
-          }
+          if (row0 + rl < R) a.dzbuf[((size_t)(row0 + rl) * T + tz) * 4 + j] = __uint_as_float(v0[r]);
         }
       }
     }
@@ -617,6 +604,34 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   tc_fence_before();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem_base, 128);
+  // ---- first optimizer step (guidance_loss.py:2250-2278), coalesced over the CTA's [rows][T][4] block
+  {
+    const int nrow = min(LT_RB, R - row0);
+    float4* zo = reinterpret_cast<float4*>(a.z_out + (size_t)row0 * T * 4);
+    const float4* zm = reinterpret_cast<const float4*>(a.z_mean + (size_t)row0 * T * 4);
+    const float4* dzb = reinterpret_cast<const float4*>(a.dzbuf + (size_t)row0 * T * 4);
+    float4* go = a.grad_out ? reinterpret_cast<float4*>(a.grad_out + (size_t)row0 * T * 4) : nullptr;
+    const float lr = a.lr;
+    const bool adam = a.optimizer == CLD_OPT_ADAM;
+    auto upd = [&](float z, float g) {
+      if (adam) {
+        // first torch.optim.Adam step: m = 0.1 g, v = 0.001 g^2, bias corrections 0.1 / 0.001, eps 1e-8
+        const float m = 0.1f * g;
+        const float vv = (0.001f * g) * g;
+        const float denom = sqrtf(vv) / 0.03162277660168379f + 1e-8f;
+        return z - (lr / 0.1f) * (m / denom);
+      }
+      return z - lr * g;
+    };
+    for (int i = tid; i < nrow * T; i += LB_THREADS) {
+      const float is = inv_scale[i / T];
+      float4 g = dzb[i];
+      const float4 z = zm[i];
+      g.x *= is; g.y *= is; g.z *= is; g.w *= is;
+      zo[i] = make_float4(upd(z.x, g.x), upd(z.y, g.y), upd(z.z, g.z), upd(z.w, g.w));
+      if (go) go[i] = g;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -680,6 +695,7 @@ int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* ac
   const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
   BwdTcArgs a;
   a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash; a.wblob = st->wbwd;
+  a.dzbuf = const_cast<float*>(dtraj);
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
   lstm_backward_tc_kernel<<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
