@@ -21,6 +21,7 @@
 // warp 9: stages z_t as an MMA operand, hid2act (lane = row), unicycle rollout at the end.
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "lstm_shared.cuh"
@@ -356,8 +357,9 @@ constexpr int LBK_DG = LBK_W + 8 * LT_WBLK;             // [layer][hi, lo][gate]
 constexpr int LBK_DACT = LBK_DG + 16 * LT_OP;           // fp32 [32 rows][T][2], scaled
 __host__ __device__ constexpr int lbk_scale(int T) { return LBK_DACT + LT_RB * T * 2 * 4; }      // float [32] 1 / scale
 __host__ __device__ constexpr int lbk_hw(int T) { return lbk_scale(T) + LT_RB * 4; }             // hid2act weights [2][64]
-__host__ __device__ constexpr int lbk_bars(int T) { return lbk_hw(T) + 2 * LT_H * 4; }           // m1[2], m0, e1, e0
-__host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 6 * 8 + 16; }
+__host__ __device__ constexpr int lbk_dzs(int T) { return lbk_hw(T) + 2 * LT_H * 4; }            // float [32 rows][4]: dz of one step
+__host__ __device__ constexpr int lbk_bars(int T) { return lbk_dzs(T) + LT_RB * 4 * 4; }          // m1[2], m0, e1, e0, dz, dzfree
+__host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 8 * 8 + 16; }
 // prologue scratch aliases the weight tiles: act [32][T][2], dtraj [32][T][4], scan scratch [32][4][T+1]
 }  // namespace
 
@@ -366,10 +368,10 @@ struct BwdTcArgs {
   const uint8_t* wblob;                 // packed fp16 backward weights, 8 x 16 KB
   const float* h2a_w;
   float *z_out, *grad_out;
-  float* dzbuf;                         // [R][T][4] scratch for the scaled dz (the d(traj) workspace: its rows are consumed in the prologue)
   int R, T;
   DynParams2 dyn;
   int optimizer; float lr;
+  int pf;                               // L2 prefetch distance in steps (0: off)
 };
 
 // backward weight blob: [layer][gate g][128 lanes][64 k] fp16, swizzled; k-block g covers gate rows g*64 .. g*64+63
@@ -387,12 +389,28 @@ __global__ void lstm_tc_pack_bwd_kernel(uint8_t* __restrict__ out, const float* 
   *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
 }
 
+// 16 columns of the hi accumulator at `taddr` combined with the lo accumulator 32 columns further
+__device__ __forceinline__ void tmem_ld16_hilo(uint32_t taddr, float (&o)[16]) {
+  uint32_t vh[16], vl[16];
+  tmem_ld16(taddr, vh);
+  tmem_ld16(taddr + 32, vl);
+  tmem_wait_ld();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) o[r] = fmaf(__uint_as_float(vl[r]), 1.0f / 2048.0f, __uint_as_float(vh[r]));
+}
+
 __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const BwdTcArgs a) {
+  constexpr int P0 = 20, PN = 4;        // CLD_LSTM_PROF=1: timeline of steps P0 .. P0+PN-1 of CTA 0 (clock64), printed at the end
+  long long tl[PN][4];
+  const bool rec = PROF && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+  const long long tbase = PROF ? clock64() : 0;
+  (void)tl; (void)rec; (void)tbase;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -400,8 +418,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   const uint32_t bars = smem_u32(sm + lbk_bars(T));
   // bar_m1 alternates between two barriers by step parity: layer 0 (one step behind) waits for MMA_L1(i) while
   // MMA_L1(i + 1) may already complete; a barrier's next completion (step i + 2) needs layer 0's arrival for step i
-  const uint32_t bar_m1 = bars, bar_m0 = bars + 16, bar_e1 = bars + 24, bar_e0 = bars + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + lbk_bars(T) + 48);
+  const uint32_t bar_m1 = bars, bar_m0 = bars + 16, bar_e1 = bars + 24, bar_e0 = bars + 32, bar_dz = bars + 40, bar_dzfree = bars + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + lbk_bars(T) + 64);
+  float* dzs = reinterpret_cast<float*>(sm + lbk_dzs(T));
   float* dact = reinterpret_cast<float*>(sm + LBK_DACT);
   float* inv_scale = reinterpret_cast<float*>(sm + lbk_scale(T));
   float* hw = reinterpret_cast<float*>(sm + lbk_hw(T));
@@ -421,9 +440,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
     if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
     if (tid == 0) {
       mbar_init(bar_m1, 1); mbar_init(bar_m1 + 8, 1); mbar_init(bar_m0, 1); mbar_init(bar_e1, 8); mbar_init(bar_e0, 8);
+      mbar_init(bar_dz, 2); mbar_init(bar_dzfree, 1);
       fence_barrier_init();
     }
-    if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 128); tmem_relinquish(); }
+    if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
     __syncthreads();
     if (tid < LT_RB) {
       float* da = dact + tid * T * 2;
@@ -455,7 +475,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: layer-1 accumulator [parity][32], layer-0 accumulator at 64
+  // TMEM columns: layer-1 accumulators [parity][hi 32 | lo 32] at 0..127, layer-0 accumulators [hi | lo] at 128..191.
+  // The lo pass multiplies the residual scaled by 2^11 (so that it is not lost in the fp16 subnormals) into its own
+  // accumulator; the cell warps combine  hi + 2^-11 lo.
 
   if (warp < 16) {
     // ===================== cell-gradient warps =====================
@@ -472,10 +494,15 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
     float dcrec[8], cprev[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) dcrec[r] = 0.f;
-    const bool dz_lane = (L == 0) && q == 0 && is_b && j < 4;
     for (int i = 0; i <= T; ++i) {
       const int t = T - 1 - i;                                // time step of this iteration (i < T)
       float gi[8], gf[8], gg[8], go[8], cc[8];
+      if (a.pf > 0 && (j & 3) == 0 && t - a.pf >= 0) {
+        // pull the stash lines of three steps ahead from HBM into L2 (one lane per 128-byte line): the loads below then hit L2
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.stash + stash_index(L, t - a.pf, T, R, row0 + rloc, v, u)));
+      }
       if (i < T) {
         // stash loads first: they do not depend on the MMA and complete while the thread waits below
         ld8(a.stash + stash_index(L, t, T, R, row0 + rloc, 0, u), gi);
@@ -489,8 +516,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
           for (int r = 0; r < 8; ++r) cprev[r] = 0.f;
         }
       }
+      if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][0] = clock64();
       float dh[8];
-      uint32_t v0[16];
+      float v0[16];
 #pragma unroll
       for (int r = 0; r < 8; ++r) dh[r] = 0.f;
       if (L == 1) {
@@ -498,13 +526,12 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
         if (i >= 1) {
           lt_wait(bar_m1 + 8 * ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u, 31000 + i);
           tc_fence_after();
-          uint32_t v[16];
-          tmem_ld16(lane_t + (uint32_t)(((i - 1) & 1) * 32 + rh * 16), v);      // A lanes: dh_rec[u] for this row half
-          tmem_wait_ld();
+          float v[16];
+          tmem_ld16_hilo(lane_t + (uint32_t)(((i - 1) & 1) * 64 + rh * 16), v);  // A lanes: dh_rec[u] for this row half
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const float x = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[8 + r]), 16);    // B lane <- A lane's rows 8..15
-            dh[r] = is_b ? x : __uint_as_float(v[r]);
+            const float x = __shfl_xor_sync(0xffffffffu, v[8 + r], 16);          // B lane <- A lane's rows 8..15
+            dh[r] = is_b ? x : v[r];
           }
         }
 #pragma unroll
@@ -517,23 +544,22 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
         if (i >= 1) {
           lt_wait(bar_m0, (uint32_t)(i - 1) & 1u, 32000 + i);
           tc_fence_after();
-          tmem_ld16(lane_t + (uint32_t)(64 + rh * 16), v0);                     // A: dh_rec0[u] ; B (u < 4): dz of step i - 1
-          tmem_wait_ld();
+          tmem_ld16_hilo(lane_t + (uint32_t)(128 + rh * 16), v0);               // A: dh_rec0[u] ; B (u < 4): dz of step i - 1
         }
         if (i < T) {
           tc_fence_after();
-          uint32_t v1[16];
-          tmem_ld16(lane_t + (uint32_t)((i & 1) * 32 + rh * 16), v1);           // B lanes: dx1[u] = d(loss)/d(h0_t)
-          tmem_wait_ld();
+          float v1[16];
+          tmem_ld16_hilo(lane_t + (uint32_t)((i & 1) * 64 + rh * 16), v1);      // B lanes: dx1[u] = d(loss)/d(h0_t)
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const float rec_lo = i >= 1 ? __uint_as_float(v0[r]) : 0.f, rec_hi = i >= 1 ? __uint_as_float(v0[8 + r]) : 0.f;
-            const float send = is_b ? __uint_as_float(v1[r]) : rec_hi;           // B sends dx rows 0..7 ; A sends dh_rec rows 8..15
+            const float rec_lo = i >= 1 ? v0[r] : 0.f, rec_hi = i >= 1 ? v0[8 + r] : 0.f;
+            const float send = is_b ? v1[r] : rec_hi;                            // B sends dx rows 0..7 ; A sends dh_rec rows 8..15
             const float x = __shfl_xor_sync(0xffffffffu, send, 16);
-            dh[r] = is_b ? (__uint_as_float(v1[8 + r]) + x) : (rec_lo + x);
+            dh[r] = is_b ? (v1[8 + r] + x) : (rec_lo + x);
           }
         }
       }
+      if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][1] = clock64();
       if (i < T) {
       // ---- gate gradients of this thread's (unit, 8 rows)
 #pragma unroll
@@ -551,67 +577,95 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const __half h = __float2half_rn(dv[g]);
-          const __half l = __float2half_rn(dv[g] - __half2float(h));
+          const __half l = __float2half_rn((dv[g] - __half2float(h)) * 2048.0f);
           *reinterpret_cast<__half*>(dgt + g * LT_OP + off) = h;
           *reinterpret_cast<__half*>(dgt + (4 + g) * LT_OP + off) = l;
         }
       }
+      if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][2] = clock64();
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_e);
+      if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][3] = clock64();
       }
-      if (dz_lane && i >= 1) {
-        // dz (still scaled) of step index i - 1 = time t + 1, latent channel j: parked in dzbuf, fire-and-forget stores;
-        // the optimizer step runs over the CTA's block after the loop
-        const int tz = t + 1;
+      if (L == 0 && q == 0 && i >= 1) {
+        // dz (still scaled) of step index i - 1: staged in shared memory for warp 17, off the critical path (the gate
+        // gradients of this step are already published).  One step in flight: wait until warp 17 took the previous one.
+        if (i >= 2) lt_wait(bar_dzfree, (uint32_t)(i - 2) & 1u, 34000 + i);
+        if (is_b && j < 4) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int rl = rh * 16 + r;
-          if (row0 + rl < R) a.dzbuf[((size_t)(row0 + rl) * T + tz) * 4 + j] = __uint_as_float(v0[r]);
+          for (int r = 0; r < 16; ++r) dzs[(rh * 16 + r) * 4 + j] = v0[r];
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dz);
       }
     }
+    if (PROF && rec && (warp == 0 || warp == 8 || warp == 9 || warp == 13))
+      for (int k = 0; k < PN; ++k)
+        printf("[bwd prof] warp %2d L%d step %d: top %7lld | waits done %7lld | grads done %7lld | arrived %7lld\n", warp, L, P0 + k,
+               tl[k][0] - tbase, tl[k][1] - tbase, tl[k][2] - tbase, tl[k][3] - tbase);
   } else if (warp == 16) {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
     const uint32_t w_u = smem_u32(sm + LBK_W), dg_u = smem_u32(sm + LBK_DG);
     const uint64_t dsc = make_desc_sw128(0, 1024);
-    auto product = [&](int layer, uint32_t d) {
-      bool first = true;
-      for (int part = 0; part < 2; ++part)
+    // one product = 2 passes (hi | lo gate gradients, each into its own accumulator) x 4 gate k-blocks x 4 K=16 steps;
+    // fully unrolled so that every descriptor is base + immediate
+    auto product = [&](const uint64_t a0, const uint64_t b0, const uint32_t d0) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+#pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint64_t ad = dsc + ((w_u + (uint32_t)((layer * 4 + g) * LT_WBLK)) >> 4);
-          const uint64_t bd = dsc + ((dg_u + (uint32_t)(((layer ? 0 : 8) + part * 4 + g) * LT_OP)) >> 4);
-          for (int k = 0; k < 4; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, IDESC, first ? 0u : 1u); first = false; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d0 + (uint32_t)(part * 32), a0 + (uint64_t)(g * (LT_WBLK >> 4) + 2 * k),
+                      b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + 2 * k), IDESC, (g | k) ? 1u : 0u);
         }
-    };
-    for (int s = 0; s <= T; ++s) {
-      if (s < T) {
-        lt_wait(bar_e1, (uint32_t)s & 1u, 40000 + s);
-        tc_fence_after();
-        if (lane == 0) { product(1, tmem_base + (uint32_t)((s & 1) * 32)); umma_commit(bar_m1 + 8 * (s & 1)); }
-        __syncwarp();
       }
-      if (s >= 1) {
-        lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 41000 + s);
+    };
+    const uint64_t a_l1 = dsc + ((w_u + 4u * LT_WBLK) >> 4), a_l0 = dsc + (w_u >> 4);
+    const uint64_t b_l1 = dsc + (dg_u >> 4), b_l0 = dsc + ((dg_u + 8u * LT_OP) >> 4);
+    // event loop: issue whichever layer's product has its operand ready, so that neither recurrence chain waits
+    // behind the other's barrier.  n1 / n0 = products issued so far.  M1(n1) overwrites accumulator n1 & 1, which
+    // layer 0 reads in step n1 - 2: that step is complete once M0(n1 - 2) has been issued (n0 >= n1 - 1).
+    int n1 = 0, n0 = 0;
+    const long long t_loop = clock64();
+    while (n0 < T) {
+      bool progressed = false;
+      if (n1 < T && (n1 < 2 || n0 >= n1 - 1) && mbar_test_wait(bar_e1, (uint32_t)n1 & 1u)) {
+        if (PROF && rec && n1 >= P0 && n1 < P0 + PN) tl[n1 - P0][0] = clock64();
         tc_fence_after();
-        if (lane == 0) { product(0, tmem_base + 64u); umma_commit(bar_m0); }
+        if (lane == 0) { product(a_l1, b_l1, tmem_base + (uint32_t)((n1 & 1) * 64)); umma_commit(bar_m1 + 8 * (n1 & 1)); }
         __syncwarp();
+        if (PROF && rec && n1 >= P0 && n1 < P0 + PN) tl[n1 - P0][1] = clock64();
+        ++n1;
+        progressed = true;
+      }
+      if (n0 < n1 && mbar_test_wait(bar_e0, (uint32_t)n0 & 1u)) {
+        if (PROF && rec && n0 + 1 >= P0 && n0 + 1 < P0 + PN) tl[n0 + 1 - P0][2] = clock64();
+        tc_fence_after();
+        if (lane == 0) { product(a_l0, b_l0, tmem_base + 128u); umma_commit(bar_m0); }
+        __syncwarp();
+        if (PROF && rec && n0 + 1 >= P0 && n0 + 1 < P0 + PN) tl[n0 + 1 - P0][3] = clock64();
+        ++n0;
+        progressed = true;
+      }
+      if (!progressed && clock64() - t_loop > 8000000000ll) {
+        if (lane == 0) printf("lstm_tc backward: MMA issuer stuck (block %d, n1 %d, n0 %d)\n", (int)blockIdx.x, n1, n0);
+        __trap();
       }
     }
+    if (PROF && rec)
+      for (int k = 0; k < PN; ++k)
+        printf("[bwd prof] mma s %d: e1 ok %7lld | L1 issued %7lld | e0 ok %7lld | L0 issued %7lld\n", P0 + k, tl[k][0] - tbase,
+               tl[k][1] - tbase, tl[k][2] - tbase, tl[k][3] - tbase);
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem_base, 128);
-  // ---- first optimizer step (guidance_loss.py:2250-2278), coalesced over the CTA's [rows][T][4] block
-  {
-    const int nrow = min(LT_RB, R - row0);
-    float4* zo = reinterpret_cast<float4*>(a.z_out + (size_t)row0 * T * 4);
-    const float4* zm = reinterpret_cast<const float4*>(a.z_mean + (size_t)row0 * T * 4);
-    const float4* dzb = reinterpret_cast<const float4*>(a.dzbuf + (size_t)row0 * T * 4);
-    float4* go = a.grad_out ? reinterpret_cast<float4*>(a.grad_out + (size_t)row0 * T * 4) : nullptr;
-    const float lr = a.lr;
+  else {
+    // ===================== warp 17: dz -> first optimizer step on z (guidance_loss.py:2250-2278), lane = row =====================
+    const int row = row0 + lane;
+    const bool valid = row < R;
+    const float is = inv_scale[lane], lr = a.lr;
     const bool adam = a.optimizer == CLD_OPT_ADAM;
     auto upd = [&](float z, float g) {
       if (adam) {
@@ -623,15 +677,26 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       }
       return z - lr * g;
     };
-    for (int i = tid; i < nrow * T; i += LB_THREADS) {
-      const float is = inv_scale[i / T];
-      float4 g = dzb[i];
-      const float4 z = zm[i];
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) z = reinterpret_cast<const float4*>(a.z_mean)[(size_t)row * T + (T - 1)];
+    for (int i = 1; i <= T; ++i) {
+      const int tz = T - i;
+      lt_wait(bar_dz, (uint32_t)(i - 1) & 1u, 50000 + i);
+      float4 g = reinterpret_cast<const float4*>(dzs)[lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dzfree);
       g.x *= is; g.y *= is; g.z *= is; g.w *= is;
-      zo[i] = make_float4(upd(z.x, g.x), upd(z.y, g.y), upd(z.z, g.z), upd(z.w, g.w));
-      if (go) go[i] = g;
+      const float4 zc = z;
+      if (valid && tz >= 1) z = reinterpret_cast<const float4*>(a.z_mean)[(size_t)row * T + tz - 1];   // next step's z, in flight during this step
+      if (valid) {
+        reinterpret_cast<float4*>(a.z_out)[(size_t)row * T + tz] = make_float4(upd(zc.x, g.x), upd(zc.y, g.y), upd(zc.z, g.z), upd(zc.w, g.w));
+        if (a.grad_out) reinterpret_cast<float4*>(a.grad_out)[(size_t)row * T + tz] = g;
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -659,7 +724,8 @@ static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
   if (lbk_smem(h->cfg.horizon) + 1024 > 232448) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the tensor-core LSTM backward");
   if (LT_RB * (h->cfg.horizon * 6 + 4 * (h->cfg.horizon + 1)) * 4 > 8 * LT_WBLK)
     return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the LSTM backward prologue scratch");
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
   h->lstm_tc = st;
   return 0;
 }
@@ -695,10 +761,11 @@ int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* ac
   const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
   BwdTcArgs a;
   a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash; a.wblob = st->wbwd;
-  a.dzbuf = const_cast<float*>(dtraj);
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
-  lstm_backward_tc_kernel<<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
+  { const char* e = getenv("CLD_LSTM_PF"); a.pf = e ? atoi(e) : 3; }
+  if (getenv("CLD_LSTM_PROF")) lstm_backward_tc_kernel<true><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
+  else lstm_backward_tc_kernel<false><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_backward_tc_kernel");
   return 0;
 }

@@ -103,3 +103,79 @@ def test_strided_sampler_bf16_vs_reference_golden(bf16_models, gold):
     r = rel(out["pred_traj"], g["pred_traj"])
     print("bf16 50-step strided DDPM: rel(pred_traj)=%.3e" % r)
     assert r < BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16-precision mode also runs the LSTM decoder (forward + BPTT) on the tensor pipe (kernels_lstm_tc.cu): fp16-rounded
+# weights, hi/lo split state operand.  Tolerances: decoder outputs 1e-3 (north_star allows 1e-2 under bf16).
+# ---------------------------------------------------------------------------------------------------
+def dec_sd_of(vae):
+    return {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+
+
+def test_decode_rollout_tensor_core_vs_oracle_ragged_rows(bf16_models):
+    dm, vae, _ = bf16_models(10)
+    torch.manual_seed(11)
+    for R in (37, 64, 1):                     # ragged last CTA, exact multiple, single row
+        z, cond = torch.randn(R, 52, 4), torch.randn(R, 256)
+        curr = torch.cat([torch.zeros(R, 2), torch.rand(R, 1) * 15, torch.zeros(R, 1)], dim=1)
+        act, traj = dm.engine(64).decode_rollout(z.cuda(), cond.cuda(), curr.cuda())
+        wtraj, wact = O.decode_rollout(dec_sd_of(vae), z, cond, curr)
+        ra, rt = rel(act, wact), rel(traj, wtraj)
+        print("tensor-core decode R=%d: rel(act)=%.3e rel(traj)=%.3e" % (R, ra, rt))
+        assert torch.isfinite(traj).all()
+        assert ra < 1e-3 and rt < 1e-3
+
+
+def test_guidance_step_tensor_core_vs_reference_golden(bf16_models, gold):
+    """Same golden as the fp32 test (the reference's own perturb() output); the tensor-core BPTT is held to a
+    looser gradient tolerance: 5e-3 relative, >= 99.5 % sign agreement on the non-zero entries."""
+    g = gold("guidance")
+    dm, vae, _ = bf16_models(10)
+    S, A, N = int(g["S"]), int(g["A"]), int(g["N"])
+    aux, batch = make_scenes(S, A, seed=int(g["seed"]), dense=True)
+    from cld_b200.engine import default_guidance
+    eng = dm.engine(S * A * N)
+    scene = eng.make_scene(batch, S, A, N)
+    z = torch.tensor(g["z"]).cuda()
+    cond = aux["cond_feat"].repeat_interleave(N, 0).cuda()
+    curr = aux["curr_states"].repeat_interleave(N, 0).cuda()
+    z_out, grad, loss = eng.guidance_step(z, cond, curr, scene, default_guidance())
+    assert rel(loss[0], g["loss_ac"].reshape(-1)) < 1e-3
+    assert rel(loss[1], g["loss_mc"].reshape(-1)) < 1e-3
+    g_or, _ = O.guidance_grad(dec_sd_of(vae), torch.tensor(g["z"]), aux["cond_feat"], aux["curr_states"], batch, A, N)
+    nz = g_or != 0
+    sign_agree = (torch.sign(grad.cpu())[nz] == torch.sign(g_or)[nz]).float().mean().item()
+    zero_rows = (g_or.flatten(1) == 0).all(dim=1)
+    print("tensor-core guidance: rel(grad)=%.3e sign agreement %.6f" % (rel(grad, g_or), sign_agree))
+    assert rel(grad, g_or) < 5e-3
+    assert sign_agree > 0.995
+    assert (grad.cpu()[zero_rows] == 0).all()              # rows without any active loss get an exactly zero gradient
+    frac_bad = ((z_out.cpu() - torch.tensor(g["z_out"])).abs() > 1e-3).float().mean().item()
+    print("tensor-core guidance: fraction of z_out entries off by > 1e-3: %.5f" % frac_bad)
+    assert frac_bad < 5e-3
+
+
+def test_guided_sampler_bf16_finite_and_indicators_consistent(bf16_models):
+    """cfg1-shaped guided run in bf16 mode: finite, deterministic, indicators bit-exact on the produced trajectories."""
+    dm, vae, algo = bf16_models(100)
+    S, A = 4, 16
+    aux, batch = make_scenes(S, A, seed=77, dense=True)
+    from cld_b200.engine import default_guidance
+    torch.manual_seed(78)
+    R = S * A
+    x_init, noises = torch.randn(R, 52, 4), torch.randn(50, R, 52, 4)
+    dm.stride = 2
+    try:
+        outs = [dm({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}, {k: v.cuda() for k, v in aux.items()},
+                   algo, noise=noises.cuda(), x_init=x_init.cuda(), guidance=default_guidance(), want_indicators=True)
+                for _ in range(2)]
+    finally:
+        dm.stride = 1
+    a, b = outs
+    assert torch.isfinite(a["pred_traj"]).all() and torch.isfinite(a["traj"]).all()
+    assert torch.equal(a["pred_traj"], b["pred_traj"]) and torch.equal(a["traj"], b["traj"])
+    woff, wcoll = O.indicators(a["traj"].cpu()[..., :2], batch)
+    assert torch.equal(a["offroad"].cpu(), woff) and torch.equal(a["coll"].cpu(), wcoll)
+    wtraj, _ = O.decode_rollout(dec_sd_of(vae), a["pred_traj"].cpu(), aux["cond_feat"], aux["curr_states"])
+    assert rel(a["traj"], wtraj) < 1e-3
