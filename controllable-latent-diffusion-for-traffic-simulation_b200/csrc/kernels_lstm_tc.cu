@@ -17,8 +17,9 @@
 // The two layers run skewed by one step on separate warp sets; everything is synchronised with mbarriers
 // (MMA completion -> cell warps -> operand ready -> MMA issue).
 //
-// Warp roles (320 threads): warps 0-3 layer-0 cells, warps 4-7 layer-1 cells, warp 8 MMA issuer (one thread),
-// warp 9: stages z_t as an MMA operand, hid2act (lane = row), unicycle rollout at the end.
+// Warp roles (576 threads): warps 0-7 layer-0 cells, warps 8-15 layer-1 cells (warp & 3 = TMEM lane quadrant,
+// (warp >> 2) & 1 = row half), warp 16 MMA issuer (event loop, one issuing thread), warp 17: stages z_t as an MMA
+// operand, hid2act and the unicycle rollout step by step (lane = row).
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,7 +34,7 @@ using namespace tc;
 namespace {
 constexpr int LT_RB = 32;                 // rows per CTA = MMA N
 constexpr int LT_H = 64;
-constexpr int LT_THREADS = 320;
+constexpr int LT_THREADS = 576;
 constexpr int LT_WBLK = 16384;            // one weight k-block: 128 gate rows x 64 k fp16
 constexpr int LT_OP = 4096;               // one state operand tile: 32 rows x 64 k fp16
 // forward kernel shared memory (bytes from the 1024-aligned base)
@@ -120,8 +121,13 @@ __global__ void lstm_tc_pack_fwd_kernel(uint8_t* __restrict__ out, const float* 
   *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
 }
 
-template <bool SAVE>
+template <bool SAVE, bool PROF>
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const LstmTcArgs a) {
+  constexpr int P0 = 20, PN = 4;        // CLD_LSTM_PROF=1: timeline of steps P0 .. P0+PN-1 of CTA 0 (clock64), printed at the end
+  long long tl[PN][6];
+  const bool rec = PROF && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+  const long long tbase = PROF ? clock64() : 0;
+  (void)tl; (void)rec; (void)tbase;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     for (int i = tid; i < (LF_H1F - LF_H0) / 16; i += LT_THREADS) ops[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
     if (tid == 0) {
-      mbar_init(bar_m0, 1); mbar_init(bar_m1, 1); mbar_init(bar_e0, 4); mbar_init(bar_e1, 4); mbar_init(bar_a, 1);
+      mbar_init(bar_m0, 1); mbar_init(bar_m1, 1); mbar_init(bar_e0, 8); mbar_init(bar_e1, 8); mbar_init(bar_a, 1);
       mbar_init(bar_z, 1); mbar_init(bar_z + 8, 1); mbar_init(bar_z + 16, 1);
       fence_barrier_init();
     }
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     store_split(sm + LF_H0 + 2 * LT_OP, rl, k, v);          // parity 1 = step -1
     store_split(sm + LF_H1, rl, k, v);
   }
-  if (warp == 9) {                                           // z_0, z_1, z_2
+  if (warp == 17) {                                          // z_0, z_1, z_2
     for (int t = 0; t < 3 && t < T; ++t) {
       float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row0 + lane < R) zv = reinterpret_cast<const float4*>(a.z)[(size_t)(row0 + lane) * T + t];
@@ -161,46 +167,51 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       store_split(zt, lane, 0, zv.x); store_split(zt, lane, 1, zv.y); store_split(zt, lane, 2, zv.z); store_split(zt, lane, 3, zv.w);
     }
   }
-  if (warp == 8) { tmem_alloc(smem_u32(tmem_slot), 128); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: layer 0 [tile 0 | tile 1] at 0..63 ; layer 1 [step parity][tile 0 | tile 1] at 64..191
 
-  if (warp < 8) {
-    // ===================== cell warps =====================
-    const int L = warp >> 2, q = warp & 3, j = lane & 15;
+  if (warp < 16) {
+    // ===================== cell warps: (layer, lane quadrant, row half) =====================
+    const int L = warp >> 3, q = warp & 3, rh = (warp >> 2) & 1, j = lane & 15;
     const bool is_b = lane >= 16;
     const int u = 16 * q + j;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * 64);
+    const uint32_t lane_t = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* bias = L == 0 ? a.b0 : a.b1;
     const float bias0 = bias[(is_b ? 64 : 0) + u];            // tile 0: i | f
     const float bias1 = bias[(is_b ? 192 : 128) + u];         // tile 1: g | o
     const float k1 = is_b ? -LOG2E : -2.0f * LOG2E, s1c = is_b ? 1.0f : 2.0f, o1c = is_b ? 0.0f : -1.0f;
     const uint32_t bar_m = L == 0 ? bar_m0 : bar_m1, bar_e = L == 0 ? bar_e0 : bar_e1;
-    const int rbase = is_b ? 16 : 0;
-    float c[16];
+    const int r16 = rh * 16;                                  // first of the 16 rows whose gates this thread activates
+    const int r8 = r16 + (is_b ? 8 : 0);                      // first of the 8 rows whose cell this thread updates
+    float c[8];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) c[r] = 0.f;
+    for (int r = 0; r < 8; ++r) c[r] = 0.f;
     for (int t = 0; t < T; ++t) {
-      lt_wait(bar_m, (uint32_t)t & 1u, 1 + L);
+      if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][0] = clock64();
+      lt_wait(bar_m, (uint32_t)t & 1u, 1000 * (1 + L) + t);
+      if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][1] = clock64();
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
+      const uint32_t col = L == 0 ? 0u : 64u + (uint32_t)((t & 1) * 64);
+      uint32_t v0[16], v1[16];
+      tmem_ld16(lane_t + col + (uint32_t)r16, v0);
+      tmem_ld16(lane_t + col + 32u + (uint32_t)r16, v1);
       tmem_wait_ld();
-      float a0[32], a1[32];
+      float a0[16], a1[16];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
+      for (int r = 0; r < 16; ++r) {
         a0[r] = sigmoidf_(__uint_as_float(v0[r]) + bias0);
         a1[r] = act_gen(__uint_as_float(v1[r]) + bias1, k1, s1c, o1c);
       }
       if (SAVE) {
-        float* s0 = a.stash + stash_index(L, t, T, R, row0, is_b ? 1 : 0, u);
-        float* s1 = a.stash + stash_index(L, t, T, R, row0, is_b ? 3 : 2, u);
+        float* s0 = a.stash + stash_index(L, t, T, R, row0 + r16, is_b ? 1 : 0, u);
+        float* s1 = a.stash + stash_index(L, t, T, R, row0 + r16, is_b ? 3 : 2, u);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 2; ++b) {
           float4* d0 = reinterpret_cast<float4*>(s0 + (size_t)b * (5 * 64 * 8));
           float4* d1 = reinterpret_cast<float4*>(s1 + (size_t)b * (5 * 64 * 8));
           d0[0] = make_float4(a0[8 * b + 0], a0[8 * b + 1], a0[8 * b + 2], a0[8 * b + 3]);
@@ -209,116 +220,143 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
           d1[1] = make_float4(a1[8 * b + 4], a1[8 * b + 5], a1[8 * b + 6], a1[8 * b + 7]);
         }
       }
-      float hn[16];
+      if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][2] = clock64();
+      float hn[8];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float p_lo = a0[r] * a1[r], p_hi = a0[16 + r] * a1[16 + r];
-        const float x1 = __shfl_xor_sync(0xffffffffu, is_b ? a0[r] : p_hi, 16);   // A lane <- f[r] ; B lane <- (i g)[16 + r]
+      for (int r = 0; r < 8; ++r) {
+        const float p_lo = a0[r] * a1[r], p_hi = a0[8 + r] * a1[8 + r];
+        const float x1 = __shfl_xor_sync(0xffffffffu, is_b ? a0[r] : p_hi, 16);   // A lane <- f[r] ; B lane <- (i g)[8 + r]
         const float x2 = __shfl_xor_sync(0xffffffffu, a1[r], 16);                 // A lane <- o[r]
-        const float fg = is_b ? a0[16 + r] : x1;
+        const float fg = is_b ? a0[8 + r] : x1;
         const float pin = is_b ? x1 : p_lo;
-        const float og = is_b ? a1[16 + r] : x2;
+        const float og = is_b ? a1[8 + r] : x2;
         c[r] = fmaf(fg, c[r], pin);
         hn[r] = og * tanhf_(c[r]);
       }
       if (SAVE) {
-        float* sc = a.stash + stash_index(L, t, T, R, row0 + rbase, 4, u);
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          float4* d = reinterpret_cast<float4*>(sc + (size_t)b * (5 * 64 * 8));
-          d[0] = make_float4(c[8 * b + 0], c[8 * b + 1], c[8 * b + 2], c[8 * b + 3]);
-          d[1] = make_float4(c[8 * b + 4], c[8 * b + 5], c[8 * b + 6], c[8 * b + 7]);
-        }
+        float4* d = reinterpret_cast<float4*>(a.stash + stash_index(L, t, T, R, row0 + r8, 4, u));
+        d[0] = make_float4(c[0], c[1], c[2], c[3]);
+        d[1] = make_float4(c[4], c[5], c[6], c[7]);
       }
       if (L == 0) {
         uint8_t* dst = sm + LF_H0 + (t & 1) * 2 * LT_OP;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) store_split(dst, rbase + r, u, hn[r]);
+        for (int r = 0; r < 8; ++r) store_split(dst, r8 + r, u, hn[r]);
       } else {
-        if (t >= 1) lt_wait(bar_a, (uint32_t)(t - 1) & 1u, 3);      // hid2act of step t - 1 is done (implies t - 2: this h1f buffer is free)
+        if (t >= 1) lt_wait(bar_a, (uint32_t)(t - 1) & 1u, 3000 + t);    // hid2act of step t - 1 is done (implies t - 2: this h1f buffer is free)
         uint8_t* dst = sm + LF_H1;
-        float* hf = h1f + (t & 1) * (LT_H * LT_RB) + u * LT_RB + rbase;
+        float* hf = h1f + (t & 1) * (LT_H * LT_RB) + u * LT_RB + r8;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { store_split(dst, rbase + r, u, hn[r]); hf[r] = hn[r]; }
+        for (int r = 0; r < 8; ++r) { store_split(dst, r8 + r, u, hn[r]); hf[r] = hn[r]; }
       }
+      if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][3] = clock64();
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_e);
+      if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][4] = clock64();
     }
-  } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    // all lanes walk the loop and wait; lane 0 issues
+    if (PROF && rec && (warp == 0 || warp == 8))
+      for (int k = 0; k < PN; ++k)
+        printf("[fwd prof] warp %2d L%d step %d: top %7lld | mma seen %7lld | acts done %7lld | cell+store done %7lld | arrived %7lld\n", warp, L,
+               P0 + k, tl[k][0] - tbase, tl[k][1] - tbase, tl[k][2] - tbase, tl[k][3] - tbase, tl[k][4] - tbase);
+  } else if (warp == 16) {
+    // ===================== MMA issuer: event loop over the three products of a step =====================
+    //   M0(s)  = W0 . [h0_{s-1} ; z_s]        needs E0(s-1), z_s ; and M1a(s-2) issued (it reads the h0 buffer E0(s) rewrites)
+    //   M1a(s) = W_ih1 . h0_s  (accumulate 0)  needs E0(s) ; and M1b(s-1) issued => E1(s-2) has read accumulator s & 1
+    //   M1b(s) = W_hh1 . h1_{s-1}              needs E1(s-1), after M1a(s)
+    // The completed phases of every barrier are counted here (each phase is observed before the next can complete).
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
-    const uint32_t w_u = smem_u32(sm + LF_W);
     const uint64_t dsc = make_desc_sw128(0, 1024);
-    auto wdesc = [&](int layer, int tile, int kb) { return dsc + ((w_u + (uint32_t)(((layer * 2 + tile) * 2 + kb) * LT_WBLK)) >> 4); };
-    auto odesc = [&](int off) { return dsc + (smem_u32(sm + off) >> 4); };
-    // nk K = 16 steps of one k-block against the hi and the lo operand tile
-    auto kblock = [&](uint32_t d, uint64_t ad, uint64_t bd_hi, int nk, bool& first) {
-      for (int part = 0; part < 2; ++part) {
-        const uint64_t bd = bd_hi + (uint64_t)(part * (LT_OP >> 4));
-        for (int k = 0; k < nk; ++k) { umma_bf16(d, ad + 2 * k, bd + 2 * k, IDESC, first ? 0u : 1u); first = false; }
-      }
+    const uint64_t w0 = dsc + (smem_u32(sm + LF_W) >> 4);
+    const uint64_t bh0 = dsc + (smem_u32(sm + LF_H0) >> 4), bh1 = dsc + (smem_u32(sm + LF_H1) >> 4), bz = dsc + (smem_u32(sm + LF_Z) >> 4);
+    // one weight k-block (two tiles 2 * LT_WBLK apart: [layer][tile][k-block]) against the hi and lo operand tile, nk K = 16 steps
+    auto kblock = [&](uint32_t d, uint64_t ad, uint64_t bd, int nk, bool fresh) {
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < nk)
+              umma_bf16(d + (uint32_t)(tile * 32), ad + (uint64_t)(tile * 2 * (LT_WBLK >> 4) + 2 * k), bd + (uint64_t)(part * (LT_OP >> 4) + 2 * k),
+                        IDESC, (fresh && part == 0 && k == 0) ? 0u : 1u);
     };
-    for (int s = 0; s <= T; ++s) {
-      const int hp = (s + 1) & 1;                            // parity of the buffer that holds h0_{s-1}
-      if (s < T) {
-        lt_wait(bar_z + 8 * (s % 3), (uint32_t)(s / 3) & 1u, 10);
-        if (s >= 1) lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 11);
+    int n0 = 0, n1a = 0, n1b = 0, e0_done = 0, e1_done = 0, z_done = 0;
+    const long long t_loop = clock64();
+    while (n1b < T) {
+      if (e0_done < T && mbar_test_wait(bar_e0, (uint32_t)e0_done & 1u)) ++e0_done;
+      if (e1_done < T && mbar_test_wait(bar_e1, (uint32_t)e1_done & 1u)) ++e1_done;
+      if (z_done < T && mbar_test_wait(bar_z + 8 * (z_done % 3), (uint32_t)(z_done / 3) & 1u)) ++z_done;
+      bool progressed = false;
+      if (n1b < n1a && e1_done >= n1b) {
+        if (PROF && rec && n1b >= P0 && n1b < P0 + PN) tl[n1b - P0][4] = clock64();
         tc_fence_after();
         if (lane == 0) {
-          for (int tile = 0; tile < 2; ++tile) {
-            bool first = true;
-            const uint32_t d = tmem_base + (uint32_t)(tile * 32);
-            kblock(d, wdesc(0, tile, 0), odesc(LF_H0 + hp * 2 * LT_OP), 4, first);
-            kblock(d, wdesc(0, tile, 1), odesc(LF_Z + (s % 3) * 2 * LT_OP), 1, first);
-          }
-          umma_commit(bar_m0);
-        }
-        __syncwarp();
-      }
-      if (s >= 1) {
-        if (s == T) lt_wait(bar_e0, (uint32_t)(s - 1) & 1u, 12);
-        if (s >= 2) lt_wait(bar_e1, (uint32_t)(s - 2) & 1u, 13);
-        tc_fence_after();
-        if (lane == 0) {
-          for (int tile = 0; tile < 2; ++tile) {
-            bool first = true;
-            const uint32_t d = tmem_base + 64u + (uint32_t)(tile * 32);
-            kblock(d, wdesc(1, tile, 0), odesc(LF_H0 + hp * 2 * LT_OP), 4, first);
-            kblock(d, wdesc(1, tile, 1), odesc(LF_H1), 4, first);
-          }
+          kblock(tmem_base + 64u + (uint32_t)((n1b & 1) * 64), w0 + (uint64_t)(5 * (LT_WBLK >> 4)), bh1, 4, false);
           umma_commit(bar_m1);
         }
         __syncwarp();
+        if (PROF && rec && n1b >= P0 && n1b < P0 + PN) tl[n1b - P0][5] = clock64();
+        ++n1b; progressed = true;
+      }
+      if (n0 < T && z_done > n0 && e0_done >= n0 && n1a >= n0 - 1) {
+        if (PROF && rec && n0 >= P0 && n0 < P0 + PN) tl[n0 - P0][0] = clock64();
+        tc_fence_after();
+        if (lane == 0) {
+          kblock(tmem_base, w0, bh0 + (uint64_t)(((n0 + 1) & 1) * 2 * (LT_OP >> 4)), 4, true);
+          kblock(tmem_base, w0 + (uint64_t)(LT_WBLK >> 4), bz + (uint64_t)((n0 % 3) * 2 * (LT_OP >> 4)), 1, false);
+          umma_commit(bar_m0);
+        }
+        __syncwarp();
+        if (PROF && rec && n0 >= P0 && n0 < P0 + PN) tl[n0 - P0][1] = clock64();
+        ++n0; progressed = true;
+      }
+      if (n1a < T && e0_done > n1a && n1b >= n1a) {
+        if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][2] = clock64();
+        tc_fence_after();
+        if (lane == 0)
+          kblock(tmem_base + 64u + (uint32_t)((n1a & 1) * 64), w0 + (uint64_t)(4 * (LT_WBLK >> 4)), bh0 + (uint64_t)((n1a & 1) * 2 * (LT_OP >> 4)), 4, true);
+        __syncwarp();
+        if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][3] = clock64();
+        ++n1a; progressed = true;
+      }
+      if (!progressed && clock64() - t_loop > 8000000000ll) {
+        if (lane == 0) printf("lstm_tc forward: MMA issuer stuck (block %d, n0 %d n1a %d n1b %d e0 %d e1 %d z %d)\n", (int)blockIdx.x, n0, n1a, n1b, e0_done, e1_done, z_done);
+        __trap();
       }
     }
+    if (PROF && rec)
+      for (int k = 0; k < PN; ++k)
+        printf("[fwd prof] mma step %d: M0 %7lld - %7lld | M1a %7lld - %7lld | M1b %7lld - %7lld\n", P0 + k, tl[k][0] - tbase, tl[k][1] - tbase,
+               tl[k][2] - tbase, tl[k][3] - tbase, tl[k][4] - tbase, tl[k][5] - tbase);
   } else {
-    // ===================== warp 9: z staging, hid2act, rollout =====================
+    // ===================== warp 17: z staging, hid2act, unicycle rollout (lane = row) =====================
     const int row = row0 + lane;
     const bool valid = row < R;
     const float hb0 = a.h2a_b[0], hb1 = a.h2a_b[1];
     if (lane == 0) { mbar_arrive(bar_z); mbar_arrive(bar_z + 8); mbar_arrive(bar_z + 16); }      // z_0..z_2 were staged in the prologue
     float4 zn = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid && 3 < T) zn = reinterpret_cast<const float4*>(a.z)[(size_t)row * T + 3];
+    // rollout state (diffuser_helpers.py:573-639), advanced as each action arrives
+    const DynParams2& d = a.dyn;
+    float px = 0.f, py = 0.f, sp = 0.f, psi = 0.f;
+    if (valid) { px = a.curr[(size_t)row * 4 + 0]; py = a.curr[(size_t)row * 4 + 1]; sp = a.curr[(size_t)row * 4 + 2]; psi = a.curr[(size_t)row * 4 + 3]; }
+    float vprev = clip2(sp, d.v_lo, d.v_hi);
     for (int s = 1; s <= T; ++s) {
-      {                                                        // hid2act for step s - 1
-        const int t = s - 1;
-        lt_wait(bar_e1, (uint32_t)t & 1u, 20);
-        const float* hf = h1f + (t & 1) * (LT_H * LT_RB) + lane;
-        float s0 = hb0, s1 = hb1;
+      const int t = s - 1;
+      lt_wait(bar_e1, (uint32_t)t & 1u, 20000 + t);
+      const float* hf = h1f + (t & 1) * (LT_H * LT_RB) + lane;
+      float s0 = hb0, s1 = hb1;
 #pragma unroll 16
-        for (int k = 0; k < LT_H; ++k) {
-          const float hv = hf[k * LT_RB];
-          s0 = fmaf(hw[k], hv, s0); s1 = fmaf(hw[LT_H + k], hv, s1);
-        }
-        if (valid) *reinterpret_cast<float2*>(a.act_out + ((size_t)row * T + t) * 2) = make_float2(s0, s1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a);
+      for (int k = 0; k < LT_H; ++k) {
+        const float hv = hf[k * LT_RB];
+        s0 = fmaf(hw[k], hv, s0); s1 = fmaf(hw[LT_H + k], hv, s1);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
       if (s + 2 < T) {
-        // stage z_{s+2} over z_{s-1}: E1(s-1) done => M1(s-1) done => M0(s) and M0(s-1) done (issue order)
+        // stage z_{s+2} over z_{s-1}: E1(s-1) done => M1b(s-1) done => M0(s-1) done (issued earlier, in-order pipe)
         const int slot = (s + 2) % 3;
         uint8_t* zt = sm + LF_Z + slot * 2 * LT_OP;
         store_split(zt, lane, 0, zn.x); store_split(zt, lane, 1, zn.y); store_split(zt, lane, 2, zn.z); store_split(zt, lane, 3, zn.w);
@@ -328,13 +366,33 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         zn = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && s + 3 < T) zn = reinterpret_cast<const float4*>(a.z)[(size_t)row * T + s + 3];
       }
+      if (valid) {
+        *reinterpret_cast<float2*>(a.act_out + ((size_t)row * T + t) * 2) = make_float2(s0, s1);
+        if (a.traj_out) {
+          const float a_raw = __fadd_rn(__fmul_rn(s0, d.a_std), d.a_mean);
+          const float w_raw = __fadd_rn(__fmul_rn(s1, d.w_std), d.w_mean);
+          const float ac = clip2(a_raw, d.acce_lo, d.acce_hi);
+          sp = __fadd_rn(sp, __fmul_rn(ac, d.dt));
+          const float vnext = clip2(sp, d.v_lo, d.v_hi);
+          const float vbar = __fmul_rn(0.5f, __fadd_rn(vprev, vnext));
+          const float ve = fabsf(vprev);
+          const float yb = fmaxf(fminf(__fmul_rn(d.max_steer, ve), __fdiv_rn(d.max_yawvel, fmaxf(ve, 0.1f))), 0.1f);
+          const float w = clip2(w_raw, -yb, yb);
+          px = __fadd_rn(px, __fmul_rn(__fmul_rn(vbar, cosf(psi)), d.dt));
+          py = __fadd_rn(py, __fmul_rn(__fmul_rn(vbar, sinf(psi)), d.dt));
+          psi = __fadd_rn(psi, __fmul_rn(w, d.dt));
+          float* o = a.traj_out + ((size_t)row * T + t) * 6;
+          *reinterpret_cast<float2*>(o) = make_float2(px, py);
+          *reinterpret_cast<float2*>(o + 2) = make_float2(vnext, psi);
+          *reinterpret_cast<float2*>(o + 4) = make_float2(a_raw, w_raw);
+          vprev = vnext;
+        }
+      }
     }
-    if (valid && a.traj_out)
-      unicycle_row_forward2(a.act_out + (size_t)row * T * 2, a.curr + (size_t)row * 4, T, a.dyn, a.traj_out + (size_t)row * T * 6);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 128);
+  if (warp == 16) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,8 +773,9 @@ static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
   h->allocs.push_back(st->wfwd);
   lstm_tc_pack_fwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wfwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
   CLD_LAUNCH_OK(h, "lstm_tc_pack_fwd_kernel");
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
   CLD_CUDA_OK(h, cudaMalloc((void**)&st->wbwd, 8 * LT_WBLK));
   h->allocs.push_back(st->wbwd);
   lstm_tc_pack_bwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wbwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
@@ -747,8 +806,9 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
   a.h2a_w = w.h2a_w; a.h2a_b = w.h2a_b; a.act_out = act_out; a.traj_out = traj_out; a.stash = save ? h->stash : nullptr;
   a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   const int grid = (R + LT_RB - 1) / LT_RB;
-  if (save) lstm_decode_tc_kernel<true><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
-  else lstm_decode_tc_kernel<false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  if (save) lstm_decode_tc_kernel<true, false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  else if (getenv("CLD_LSTM_PROF")) lstm_decode_tc_kernel<false, true><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  else lstm_decode_tc_kernel<false, false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_decode_tc_kernel");
   return 0;
 }
