@@ -233,15 +233,24 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
     int p = lane + 32 * q;
     if (p >= P || !((offm[q] >> lane) & 1u)) continue;
     const float pxw = qxs[warp][p], pyw = qys[warp][p];
-    float best = 3.4e38f, bx = 0.f, by = 0.f;
+    // nearest on-road point: compare squared distances (one square root per off-road point instead of one per pair)
+    float best2 = 3.4e38f, bx = 0.f, by = 0.f;
     int cnt = 0;
-    for (int k = 0; k < P; ++k) {
-      if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
-      float dx = qxs[warp][k] - pxw, dy = qys[warp][k] - pyw;
-      float dist = sqrtf(dx * dx + dy * dy);
-      if (dist < best) { best = dist; bx = qxs[warp][k]; by = qys[warp][k]; cnt = 1; }
-      else if (dist == best) ++cnt;
+#pragma unroll 1
+    for (int w = 0; w < 4; ++w) {
+      uint32_t on = ~offm[w];
+      if (w * 32 + 32 > P) on &= (P - w * 32 >= 32) ? 0xffffffffu : ((P - w * 32 > 0) ? ((1u << (P - w * 32)) - 1u) : 0u);
+      while (on) {
+        const int k = w * 32 + __ffs(on) - 1;
+        on &= on - 1;
+        const float qx = qxs[warp][k], qy = qys[warp][k];
+        const float dx = qx - pxw, dy = qy - pyw;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 < best2) { best2 = d2; bx = qx; by = qy; cnt = 1; }
+        else if (d2 == best2) ++cnt;
+      }
     }
+    const float best = sqrtf(best2);
     lsum += 1.0f - best / diag;
     if (best > 0.f) {
       if (cnt == 1) {
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
         for (int k = 0; k < P; ++k) {
           if ((offm[k >> 5] >> (k & 31)) & 1u) continue;
           float dx = qxs[warp][k] - pxw, dy = qys[warp][k] - pyw;
-          if (sqrtf(dx * dx + dy * dy) == best) {
+          if (dx * dx + dy * dy == best2) {
             float ggx = dx * f, ggy = dy * f;
             gx += ggx; gy += ggy;
             gpsi += ggx * (-(qys[warp][k] - py)) + ggy * (qxs[warp][k] - px);
