@@ -38,8 +38,7 @@ constexpr int LT_THREADS = 576;
 constexpr int LT_WBLK = 16384;            // one weight k-block: 128 gate rows x 64 k fp16
 constexpr int LT_OP = 4096;               // one state operand tile: 32 rows x 64 k fp16
 // forward kernel shared memory (bytes from the 1024-aligned base)
-constexpr int LF_W = 0;                               // [layer][tile][k-block] x 16 KB
-constexpr int LF_H0 = LF_W + 8 * LT_WBLK;             // h0 operand [parity][hi, lo]
+constexpr int LF_H0 = 0;                              // h0 operand [parity][hi, lo]
 constexpr int LF_H1 = LF_H0 + 4 * LT_OP;              // h1 operand [hi, lo]
 constexpr int LF_Z = LF_H1 + 2 * LT_OP;               // z operand [ring of 3][hi, lo] (k 0..3 used)
 constexpr int LF_H1F = LF_Z + 6 * LT_OP;              // fp32 h1 [parity][64 units][32 rows] for hid2act
@@ -48,6 +47,11 @@ constexpr int LF_BARS = LF_HW + 2 * LT_H * 4;         // m0, m1, e0, e1, a, z[3]
 constexpr int LF_TMEM = LF_BARS + 8 * 8;
 constexpr int LF_SMEM = LF_TMEM + 16;
 static_assert(LF_SMEM + 1024 <= 232448, "forward shared memory");
+
+constexpr int LF_WCOL0 = 192, LF_WCOLS = 208;        // forward weights in TMEM: columns [192, 400)
+constexpr int LB_WCOL0 = 192, LB_WCOLS = 256;        // backward weights in TMEM: columns [192, 448)
+
+constexpr int LT_MIN_SMEM = 120 * 1024;              // requested at least: one CTA per SM (each CTA allocates all 512 TMEM columns)
 
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -60,6 +64,33 @@ __device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f3
 __device__ __forceinline__ float act_gen(float x, float k, float s, float o) { return fmaf(s, rcpf(1.0f + ex2f(k * x)), o); }
 __device__ __forceinline__ float sigmoidf_(float x) { return rcpf(1.0f + ex2f(-LOG2E * x)); }
 __device__ __forceinline__ float tanhf_(float x) { return fmaf(2.0f, rcpf(1.0f + ex2f(-2.0f * LOG2E * x)), -1.0f); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (here: the LSTM weights, resident for the whole kernel) is read
+// from tensor memory -- lane = M row, one 32-bit column = two consecutive K elements (fp16x2, low half = even k).
+// With N = 32 an SS-mode MMA is bound by the 4 KB A fetch from shared memory (62 cycles measured); the TS form takes
+// 17 cycles (tools/umma_ts_bench.cu).
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// weights -> TMEM: `blob` is [ncols][128 lanes] uint32 (fp16x2); the 4 warps of each lane quadrant take the 8-column chunks round robin
+__device__ __forceinline__ void load_weights_tmem(const uint32_t* __restrict__ blob, int ncols, uint32_t tmem_col0, int q, int rq, int lane) {
+  for (int chunk = rq; chunk * 8 < ncols; chunk += 4) {
+    uint32_t r[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r[c] = blob[(size_t)(chunk * 8 + c) * 128 + q * 32 + lane];
+    tmem_st8(tmem_col0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 8), r);
+  }
+  tmem_wait_st();
+}
 
 // mbarrier wait with a watchdog: a protocol bug traps (launch error) instead of hanging the device
 __device__ __noinline__ void lt_wait_timeout(uint32_t bar, uint32_t parity, int tag) {
@@ -98,7 +129,7 @@ __host__ __device__ inline int gate_row_of(int tile, int m) {
 
 struct LstmTcArgs {
   const float *z, *h0, *curr;
-  const uint8_t* wblob;                  // packed fp16 forward weights, 8 x 16 KB
+  const uint8_t* wblob;                  // packed fp16x2 forward weights for TMEM, [208][128]
   const float *b0, *b1;                  // b_ih + b_hh per layer [256]
   const float *h2a_w, *h2a_b;
   float *act_out, *traj_out, *stash;
@@ -106,19 +137,26 @@ struct LstmTcArgs {
   DynParams2 dyn;
 };
 
-// forward weight blob: [layer][tile][k-block][128 lanes][64 k] fp16, swizzled.  Layer 0: k-block 0 = W_hh0, k-block 1 =
-// W_ih0 (k < 4, rest zero).  Layer 1: k-block 0 = W_ih1 (input h0_t), k-block 1 = W_hh1.
-__global__ void lstm_tc_pack_fwd_kernel(uint8_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
+// forward weight blob for TMEM: [208 columns][128 lanes] fp16x2 (two consecutive k per column).  Columns: layer 0 tile t at 40 t
+// (W_hh0: 32 columns, then W_ih0: k < 4 of a K = 16 step, rest zero); layer 1 tile t at 80 + 64 t (W_ih1: 32 columns, W_hh1: 32).
+__global__ void lstm_tc_pack_fwd_kernel(uint32_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
                                         const float* __restrict__ wih1, const float* __restrict__ whh1) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 8 * 128 * 64) return;
-  const int k = idx & 63, m = (idx >> 6) & 127, blk = idx >> 13;
-  const int kb = blk & 1, tile = (blk >> 1) & 1, layer = blk >> 2;
-  const int row = gate_row_of(tile, m);
-  float v;
-  if (layer == 0) v = kb == 0 ? whh0[row * 64 + k] : (k < 4 ? wih0[row * 4 + k] : 0.f);
-  else v = kb == 0 ? wih1[row * 64 + k] : whh1[row * 64 + k];
-  *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
+  if (idx >= LF_WCOLS * 128) return;
+  const int m = idx & 127, c = idx >> 7;
+  float v0, v1;
+  if (c < 80) {
+    const int tile = c / 40, cc = c % 40, row = gate_row_of(tile, m);
+    if (cc < 32) { v0 = whh0[row * 64 + 2 * cc]; v1 = whh0[row * 64 + 2 * cc + 1]; }
+    else { const int k = 2 * (cc - 32); v0 = k < 4 ? wih0[row * 4 + k] : 0.f; v1 = k + 1 < 4 ? wih0[row * 4 + k + 1] : 0.f; }
+  } else {
+    const int tile = (c - 80) / 64, cc = (c - 80) % 64, row = gate_row_of(tile, m);
+    const float* w = cc < 32 ? wih1 : whh1;
+    const int k = 2 * (cc & 31);
+    v0 = w[row * 64 + k]; v1 = w[row * 64 + k + 1];
+  }
+  const __half2 h = __floats2half2_rn(v0, v1);
+  out[idx] = *reinterpret_cast<const uint32_t*>(&h);
 }
 
 template <bool SAVE, bool PROF>
@@ -140,9 +178,6 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 
   // ---- prologue: weights, zeroed operand tiles, initial state h_{-1} = cond2hidden(cond) for both layers
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
-    uint4* dst = reinterpret_cast<uint4*>(sm + LF_W);
-    for (int i = tid; i < 8 * LT_WBLK / 16; i += LT_THREADS) dst[i] = src[i];
     uint4* ops = reinterpret_cast<uint4*>(sm + LF_H0);
     for (int i = tid; i < (LF_H1F - LF_H0) / 16; i += LT_THREADS) ops[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
@@ -167,13 +202,18 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       store_split(zt, lane, 0, zv.x); store_split(zt, lane, 1, zv.y); store_split(zt, lane, 2, zv.z); store_split(zt, lane, 3, zv.w);
     }
   }
-  if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: layer 0 [tile 0 | tile 1] at 0..63 ; layer 1 [step parity][tile 0 | tile 1] at 64..191
+  if (warp < 16) load_weights_tmem(reinterpret_cast<const uint32_t*>(a.wblob), LF_WCOLS, tmem_base + LF_WCOL0, warp & 3, warp >> 2, lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // TMEM columns: layer 0 [tile 0 | tile 1] at 0..63 ; layer 1 [step parity][tile 0 | tile 1] at 64..191 ;
+  // weights (A operand) at 192..399: layer 0 [tile][W_hh0 32 | W_ih0 8], then layer 1 [tile][W_ih1 32 | W_hh1 32]
 
   if (warp < 16) {
     // ===================== cell warps: (layer, lane quadrant, row half) =====================
@@ -268,10 +308,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     // The completed phases of every barrier are counted here (each phase is observed before the next can complete).
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
     const uint64_t dsc = make_desc_sw128(0, 1024);
-    const uint64_t w0 = dsc + (smem_u32(sm + LF_W) >> 4);
     const uint64_t bh0 = dsc + (smem_u32(sm + LF_H0) >> 4), bh1 = dsc + (smem_u32(sm + LF_H1) >> 4), bz = dsc + (smem_u32(sm + LF_Z) >> 4);
-    // one weight k-block (two tiles 2 * LT_WBLK apart: [layer][tile][k-block]) against the hi and lo operand tile, nk K = 16 steps
-    auto kblock = [&](uint32_t d, uint64_t ad, uint64_t bd, int nk, bool fresh) {
+    const uint32_t wc = tmem_base + LF_WCOL0;
+    // one weight block (TMEM columns `acol` of tile 0, `tstride` columns further for tile 1) against the hi and lo operand tile, nk K = 16 steps
+    auto kblock = [&](uint32_t d, uint32_t acol, uint32_t tstride, uint64_t bd, int nk, bool fresh) {
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
@@ -279,8 +319,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (k < nk)
-              umma_bf16(d + (uint32_t)(tile * 32), ad + (uint64_t)(tile * 2 * (LT_WBLK >> 4) + 2 * k), bd + (uint64_t)(part * (LT_OP >> 4) + 2 * k),
-                        IDESC, (fresh && part == 0 && k == 0) ? 0u : 1u);
+              umma_ts_f16(d + (uint32_t)(tile * 32), acol + (uint32_t)tile * tstride + (uint32_t)(8 * k), bd + (uint64_t)(part * (LT_OP >> 4) + 2 * k),
+                          IDESC, (fresh && part == 0 && k == 0) ? 0u : 1u);
     };
     int n0 = 0, n1a = 0, n1b = 0, e0_done = 0, e1_done = 0, z_done = 0;
     const long long t_loop = clock64();
@@ -293,7 +333,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         if (PROF && rec && n1b >= P0 && n1b < P0 + PN) tl[n1b - P0][4] = clock64();
         tc_fence_after();
         if (lane == 0) {
-          kblock(tmem_base + 64u + (uint32_t)((n1b & 1) * 64), w0 + (uint64_t)(5 * (LT_WBLK >> 4)), bh1, 4, false);
+          kblock(tmem_base + 64u + (uint32_t)((n1b & 1) * 64), wc + 80u + 32u, 64u, bh1, 4, false);
           umma_commit(bar_m1);
         }
         __syncwarp();
@@ -304,8 +344,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         if (PROF && rec && n0 >= P0 && n0 < P0 + PN) tl[n0 - P0][0] = clock64();
         tc_fence_after();
         if (lane == 0) {
-          kblock(tmem_base, w0, bh0 + (uint64_t)(((n0 + 1) & 1) * 2 * (LT_OP >> 4)), 4, true);
-          kblock(tmem_base, w0 + (uint64_t)(LT_WBLK >> 4), bz + (uint64_t)((n0 % 3) * 2 * (LT_OP >> 4)), 1, false);
+          kblock(tmem_base, wc, 40u, bh0 + (uint64_t)(((n0 + 1) & 1) * 2 * (LT_OP >> 4)), 4, true);
+          kblock(tmem_base, wc + 32u, 40u, bz + (uint64_t)((n0 % 3) * 2 * (LT_OP >> 4)), 1, false);
           umma_commit(bar_m0);
         }
         __syncwarp();
@@ -316,7 +356,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][2] = clock64();
         tc_fence_after();
         if (lane == 0)
-          kblock(tmem_base + 64u + (uint32_t)((n1a & 1) * 64), w0 + (uint64_t)(4 * (LT_WBLK >> 4)), bh0 + (uint64_t)((n1a & 1) * 2 * (LT_OP >> 4)), 4, true);
+          kblock(tmem_base + 64u + (uint32_t)((n1a & 1) * 64), wc + 80u, 64u, bh0 + (uint64_t)((n1a & 1) * 2 * (LT_OP >> 4)), 4, true);
         __syncwarp();
         if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][3] = clock64();
         ++n1a; progressed = true;
@@ -392,7 +432,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem_base, 256);
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -410,20 +450,20 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr int LB_THREADS = 576;
-constexpr int LBK_W = 0;                                // [layer][gate k-block] x 16 KB
-constexpr int LBK_DG = LBK_W + 8 * LT_WBLK;             // [layer][hi, lo][gate] x 4 KB
-constexpr int LBK_DACT = LBK_DG + 16 * LT_OP;           // fp32 [32 rows][T][2], scaled
+constexpr int LBK_DG = 0;                               // [layer][hi, lo][gate] x 4 KB (+ 4 KB: the prologue scratch aliases this region)
+constexpr int LBK_SCR_BYTES = 17 * LT_OP;
+constexpr int LBK_DACT = LBK_DG + LBK_SCR_BYTES;        // fp32 [32 rows][T][2], scaled
 __host__ __device__ constexpr int lbk_scale(int T) { return LBK_DACT + LT_RB * T * 2 * 4; }      // float [32] 1 / scale
 __host__ __device__ constexpr int lbk_hw(int T) { return lbk_scale(T) + LT_RB * 4; }             // hid2act weights [2][64]
 __host__ __device__ constexpr int lbk_dzs(int T) { return lbk_hw(T) + 2 * LT_H * 4; }            // float [32 rows][4]: dz of one step
 __host__ __device__ constexpr int lbk_bars(int T) { return lbk_dzs(T) + LT_RB * 4 * 4; }          // m1[2], m0, e1, e0, dz, dzfree
 __host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 8 * 8 + 16; }
-// prologue scratch aliases the weight tiles: act [32][T][2], dtraj [32][T][4], scan scratch [32][4][T+1]
+// prologue scratch (aliases the gate-gradient tiles): act [32][T][2], dtraj [32][T][4], scan scratch [32][4][T+1]
 }  // namespace
 
 struct BwdTcArgs {
   const float *z_mean, *act, *curr, *dtraj, *stash;
-  const uint8_t* wblob;                 // packed fp16 backward weights, 8 x 16 KB
+  const uint8_t* wblob;                 // packed fp16x2 backward weights for TMEM, [256][128]
   const float* h2a_w;
   float *z_out, *grad_out;
   int R, T;
@@ -432,19 +472,24 @@ struct BwdTcArgs {
   int pf;                               // L2 prefetch distance in steps (0: off)
 };
 
-// backward weight blob: [layer][gate g][128 lanes][64 k] fp16, swizzled; k-block g covers gate rows g*64 .. g*64+63
-__global__ void lstm_tc_pack_bwd_kernel(uint8_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
+// backward weight blob for TMEM: [256 columns][128 lanes] fp16x2; columns 0..127 layer 1, 128..255 layer 0; column 32 g + c of a
+// layer holds gate rows g * 64 + 2 c, + 1 of [W_hh | W_ih]^T for the lane's output (see the kernel comment)
+__global__ void lstm_tc_pack_bwd_kernel(uint32_t* __restrict__ out, const float* __restrict__ wih0, const float* __restrict__ whh0,
                                         const float* __restrict__ wih1, const float* __restrict__ whh1) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 8 * 128 * 64) return;
-  const int k = idx & 63, m = (idx >> 6) & 127, blk = idx >> 13;
-  const int g = blk & 3, layer = blk >> 2;
+  if (idx >= LB_WCOLS * 128) return;
+  const int m = idx & 127, c = idx >> 7;
+  const int layer = c < 128 ? 1 : 0, cc = c & 127;
+  const int grow = (cc >> 5) * LT_H + 2 * (cc & 31);
   const int q = m >> 5, l = m & 31, j = l & 15, is_b = l >> 4, u = 16 * q + j;
-  const int grow = g * LT_H + k;
-  float v;
-  if (!is_b) v = (layer == 0 ? whh0 : whh1)[grow * 64 + u];
-  else v = layer == 0 ? (u < 4 ? wih0[grow * 4 + u] : 0.f) : wih1[grow * 64 + u];
-  *reinterpret_cast<__half*>(out + (size_t)blk * LT_WBLK + sw128_off(m, k >> 3) + (k & 7) * 2) = __float2half_rn(v);
+  float v[2];
+  for (int e = 0; e < 2; ++e) {
+    const int gr = grow + e;
+    if (!is_b) v[e] = (layer == 0 ? whh0 : whh1)[gr * 64 + u];
+    else v[e] = layer == 0 ? (u < 4 ? wih0[gr * 4 + u] : 0.f) : wih1[gr * 64 + u];
+  }
+  const __half2 h = __floats2half2_rn(v[0], v[1]);
+  out[idx] = *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // 16 columns of the hi accumulator at `taddr` combined with the lo accumulator 32 columns further
@@ -485,7 +530,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
 
   // ---- prologue: d(traj) -> d(scaled action) per row (reverse unicycle scans), per-row scale, weights
   {
-    float* act_s = reinterpret_cast<float*>(sm + LBK_W);             // [32][T][2] (scratch aliases the weight tiles)
+    float* act_s = reinterpret_cast<float*>(sm + LBK_DG);            // [32][T][2] (scratch aliases the gate-gradient tiles)
     float* dtr_s = act_s + LT_RB * T * 2;                            // [32][T][4]
     float* scr_s = dtr_s + LT_RB * T * 4;                            // [32][4][T+1]
     const int nrow = min(LT_RB, R - row0);
@@ -493,16 +538,17 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       reinterpret_cast<float4*>(act_s)[i] = reinterpret_cast<const float4*>(a.act + (size_t)row0 * T * 2)[i];
     for (int i = tid; i < nrow * T; i += LB_THREADS)
       reinterpret_cast<float4*>(dtr_s)[i] = reinterpret_cast<const float4*>(a.dtraj + (size_t)row0 * T * 4)[i];
-    uint4* dg = reinterpret_cast<uint4*>(sm + LBK_DG);
-    for (int i = tid; i < 16 * LT_OP / 16; i += LB_THREADS) dg[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
     if (tid == 0) {
       mbar_init(bar_m1, 1); mbar_init(bar_m1 + 8, 1); mbar_init(bar_m0, 1); mbar_init(bar_e1, 8); mbar_init(bar_e0, 8);
       mbar_init(bar_dz, 2); mbar_init(bar_dzfree, 1);
       fence_barrier_init();
     }
-    if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 256); tmem_relinquish(); }
+    if (warp == 16) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    if (warp < 16) load_weights_tmem(reinterpret_cast<const uint32_t*>(a.wblob), LB_WCOLS, *tmem_slot + LB_WCOL0, warp & 3, (warp >> 2) & 3, lane);
     if (tid < LT_RB) {
       float* da = dact + tid * T * 2;
       float sc = 1.f;
@@ -524,16 +570,16 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       inv_scale[tid] = 1.f / sc;
     }
     __syncthreads();
-    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
-    uint4* dst = reinterpret_cast<uint4*>(sm + LBK_W);
-    for (int i = tid; i < 8 * LT_WBLK / 16; i += LB_THREADS) dst[i] = src[i];
+    uint4* dg = reinterpret_cast<uint4*>(sm + LBK_DG);
+    for (int i = tid; i < 16 * LT_OP / 16; i += LB_THREADS) dg[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: layer-1 accumulators [parity][hi 32 | lo 32] at 0..127, layer-0 accumulators [hi | lo] at 128..191.
+  // TMEM columns: layer-1 accumulators [parity][hi 32 | lo 32] at 0..127, layer-0 accumulators [hi | lo] at 128..191,
+  // weights (A operand) at 192..447: layer 1 [gate k-block 32 columns] x 4, then layer 0.
   // The lo pass multiplies the residual scaled by 2^11 (so that it is not lost in the fp16 subnormals) into its own
   // accumulator; the cell warps combine  hi + 2^-11 lo.
 
@@ -666,23 +712,23 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   } else if (warp == 16) {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
-    const uint32_t w_u = smem_u32(sm + LBK_W), dg_u = smem_u32(sm + LBK_DG);
+    const uint32_t dg_u = smem_u32(sm + LBK_DG);
     const uint64_t dsc = make_desc_sw128(0, 1024);
     // one product = 2 passes (hi | lo gate gradients, each into its own accumulator) x 4 gate k-blocks x 4 K=16 steps;
-    // fully unrolled so that every descriptor is base + immediate
-    auto product = [&](const uint64_t a0, const uint64_t b0, const uint32_t d0) {
+    // fully unrolled so that every address is base + immediate
+    auto product = [&](const uint32_t a0, const uint64_t b0, const uint32_t d0) {
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d0 + (uint32_t)(part * 32), a0 + (uint64_t)(g * (LT_WBLK >> 4) + 2 * k),
-                      b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + 2 * k), IDESC, (g | k) ? 1u : 0u);
+            umma_ts_f16(d0 + (uint32_t)(part * 32), a0 + (uint32_t)(g * 32 + 8 * k), b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + 2 * k), IDESC,
+                        (g | k) ? 1u : 0u);
         }
       }
     };
-    const uint64_t a_l1 = dsc + ((w_u + 4u * LT_WBLK) >> 4), a_l0 = dsc + (w_u >> 4);
+    const uint32_t a_l1 = tmem_base + LB_WCOL0, a_l0 = tmem_base + LB_WCOL0 + 128u;
     const uint64_t b_l1 = dsc + (dg_u >> 4), b_l0 = dsc + ((dg_u + 8u * LT_OP) >> 4);
     // event loop: issue whichever layer's product has its operand ready, so that neither recurrence chain waits
     // behind the other's barrier.  n1 / n0 = products issued so far.  M1(n1) overwrites accumulator n1 & 1, which
@@ -754,12 +800,15 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem_base, 256);
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int lf_smem_req() { return LF_SMEM + 1024 > LT_MIN_SMEM ? LF_SMEM + 1024 : LT_MIN_SMEM; }
+static int lb_smem_req(int T) { return lbk_smem(T) + 1024 > LT_MIN_SMEM ? lbk_smem(T) + 1024 : LT_MIN_SMEM; }
+
 struct LstmTcState {
   uint8_t* wfwd = nullptr;
   uint8_t* wbwd = nullptr;
@@ -769,22 +818,22 @@ static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
   if (h->lstm_tc) return 0;
   DecoderW& w = h->dec;
   LstmTcState* st = new LstmTcState();
-  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wfwd, 8 * LT_WBLK));
+  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wfwd, (size_t)LF_WCOLS * 128 * 4));
   h->allocs.push_back(st->wfwd);
-  lstm_tc_pack_fwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wfwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
+  lstm_tc_pack_fwd_kernel<<<(LF_WCOLS * 128 + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(st->wfwd), w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
   CLD_LAUNCH_OK(h, "lstm_tc_pack_fwd_kernel");
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM + 1024));
-  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wbwd, 8 * LT_WBLK));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_req()));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_req()));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_decode_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_req()));
+  CLD_CUDA_OK(h, cudaMalloc((void**)&st->wbwd, (size_t)LB_WCOLS * 128 * 4));
   h->allocs.push_back(st->wbwd);
-  lstm_tc_pack_bwd_kernel<<<(8 * 128 * 64 + 255) / 256, 256, 0, s>>>(st->wbwd, w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
+  lstm_tc_pack_bwd_kernel<<<(LB_WCOLS * 128 + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(st->wbwd), w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
   CLD_LAUNCH_OK(h, "lstm_tc_pack_bwd_kernel");
   if (lbk_smem(h->cfg.horizon) + 1024 > 232448) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the tensor-core LSTM backward");
-  if (LT_RB * (h->cfg.horizon * 6 + 4 * (h->cfg.horizon + 1)) * 4 > 8 * LT_WBLK)
+  if (LT_RB * (h->cfg.horizon * 6 + 4 * (h->cfg.horizon + 1)) * 4 > LBK_SCR_BYTES)
     return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the LSTM backward prologue scratch");
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbk_smem(h->cfg.horizon) + 1024));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lb_smem_req(h->cfg.horizon)));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lb_smem_req(h->cfg.horizon)));
   h->lstm_tc = st;
   return 0;
 }
@@ -806,9 +855,9 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
   a.h2a_w = w.h2a_w; a.h2a_b = w.h2a_b; a.act_out = act_out; a.traj_out = traj_out; a.stash = save ? h->stash : nullptr;
   a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   const int grid = (R + LT_RB - 1) / LT_RB;
-  if (save) lstm_decode_tc_kernel<true, false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
-  else if (getenv("CLD_LSTM_PROF")) lstm_decode_tc_kernel<false, true><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
-  else lstm_decode_tc_kernel<false, false><<<grid, LT_THREADS, LF_SMEM + 1024, s>>>(a);
+  if (save) lstm_decode_tc_kernel<true, false><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
+  else if (getenv("CLD_LSTM_PROF")) lstm_decode_tc_kernel<false, true><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
+  else lstm_decode_tc_kernel<false, false><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_decode_tc_kernel");
   return 0;
 }
@@ -824,8 +873,8 @@ int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* ac
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
   { const char* e = getenv("CLD_LSTM_PF"); a.pf = e ? atoi(e) : 3; }
-  if (getenv("CLD_LSTM_PROF")) lstm_backward_tc_kernel<true><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
-  else lstm_backward_tc_kernel<false><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lbk_smem(a.T) + 1024, s>>>(a);
+  if (getenv("CLD_LSTM_PROF")) lstm_backward_tc_kernel<true><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lb_smem_req(a.T), s>>>(a);
+  else lstm_backward_tc_kernel<false><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lb_smem_req(a.T), s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_backward_tc_kernel");
   return 0;
 }
