@@ -41,8 +41,9 @@ constexpr int LT_OP = 4096;               // one state operand tile: 32 rows x 6
 constexpr int LF_H0 = 0;                              // h0 operand [parity][hi, lo]
 constexpr int LF_H1 = LF_H0 + 4 * LT_OP;              // h1 operand [hi, lo]
 constexpr int LF_Z = LF_H1 + 2 * LT_OP;               // z operand [ring of 3][hi, lo] (k 0..3 used)
-constexpr int LF_H1F = LF_Z + 6 * LT_OP;              // fp32 h1 [parity][64 units][32 rows] for hid2act
-constexpr int LF_HW = LF_H1F + 2 * LT_H * LT_RB * 4;  // hid2act weights [2][64]
+constexpr int LF_H1F = LF_Z + 6 * LT_OP;              // fp32 h1 [parity][32 rows][65] for hid2act (row pitch 65: conflict-free both ways)
+constexpr int LF_H1P = LT_H + 1;
+constexpr int LF_HW = LF_H1F + 2 * LT_RB * LF_H1P * 4;  // hid2act weights [2][64]
 constexpr int LF_BARS = LF_HW + 2 * LT_H * 4;         // m0, m1, e0, e1, a, z[3]
 constexpr int LF_TMEM = LF_BARS + 8 * 8;
 constexpr int LF_SMEM = LF_TMEM + 16;
@@ -285,9 +286,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       } else {
         if (t >= 1) lt_wait(bar_a, (uint32_t)(t - 1) & 1u, 3000 + t);    // hid2act of step t - 1 is done (implies t - 2: this h1f buffer is free)
         uint8_t* dst = sm + LF_H1;
-        float* hf = h1f + (t & 1) * (LT_H * LT_RB) + u * LT_RB + r8;
+        float* hf = h1f + (t & 1) * (LT_RB * LF_H1P) + r8 * LF_H1P + u;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { store_split(dst, r8 + r, u, hn[r]); hf[r] = hn[r]; }
+        for (int r = 0; r < 8; ++r) { store_split(dst, r8 + r, u, hn[r]); hf[r * LF_H1P] = hn[r]; }
       }
       if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][3] = clock64();
       tc_fence_before();
@@ -312,12 +313,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     const uint32_t wc = tmem_base + LF_WCOL0;
     // one weight block (TMEM columns `acol` of tile 0, `tstride` columns further for tile 1) against the hi and lo operand tile, nk K = 16 steps
     auto kblock = [&](uint32_t d, uint32_t acol, uint32_t tstride, uint64_t bd, int nk, bool fresh) {
+      // consecutive MMAs alternate between the two tiles' accumulators (two independent accumulation chains)
 #pragma unroll
-      for (int tile = 0; tile < 2; ++tile)
+      for (int part = 0; part < 2; ++part)
 #pragma unroll
-        for (int part = 0; part < 2; ++part)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int tile = 0; tile < 2; ++tile)
             if (k < nk)
               umma_ts_f16(d + (uint32_t)(tile * 32), acol + (uint32_t)tile * tstride + (uint32_t)(8 * k), bd + (uint64_t)(part * (LT_OP >> 4) + 2 * k),
                           IDESC, (fresh && part == 0 && k == 0) ? 0u : 1u);
@@ -332,8 +334,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       if (n1b < n1a && e1_done >= n1b) {
         if (PROF && rec && n1b >= P0 && n1b < P0 + PN) tl[n1b - P0][4] = clock64();
         tc_fence_after();
-        if (lane == 0) {
-          kblock(tmem_base + 64u + (uint32_t)((n1b & 1) * 64), wc + 80u + 32u, 64u, bh1, 4, false);
+        const uint32_t d1b = tmem_base + 64u + (uint32_t)((n1b & 1) * 64);
+        if (elect_one()) {
+          kblock(d1b, wc + 80u + 32u, 64u, bh1, 4, false);
           umma_commit(bar_m1);
         }
         __syncwarp();
@@ -343,9 +346,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       if (n0 < T && z_done > n0 && e0_done >= n0 && n1a >= n0 - 1) {
         if (PROF && rec && n0 >= P0 && n0 < P0 + PN) tl[n0 - P0][0] = clock64();
         tc_fence_after();
-        if (lane == 0) {
-          kblock(tmem_base, wc, 40u, bh0 + (uint64_t)(((n0 + 1) & 1) * 2 * (LT_OP >> 4)), 4, true);
-          kblock(tmem_base, wc + 32u, 40u, bz + (uint64_t)((n0 % 3) * 2 * (LT_OP >> 4)), 1, false);
+        const uint64_t b_h = bh0 + (uint64_t)(((n0 + 1) & 1) * 2 * (LT_OP >> 4)), b_z = bz + (uint64_t)((n0 % 3) * 2 * (LT_OP >> 4));
+        if (elect_one()) {
+          kblock(tmem_base, wc, 40u, b_h, 4, true);
+          kblock(tmem_base, wc + 32u, 40u, b_z, 1, false);
           umma_commit(bar_m0);
         }
         __syncwarp();
@@ -355,8 +359,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       if (n1a < T && e0_done > n1a && n1b >= n1a) {
         if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][2] = clock64();
         tc_fence_after();
-        if (lane == 0)
-          kblock(tmem_base + 64u + (uint32_t)((n1a & 1) * 64), wc + 80u, 64u, bh0 + (uint64_t)((n1a & 1) * 2 * (LT_OP >> 4)), 4, true);
+        const uint32_t d1a = tmem_base + 64u + (uint32_t)((n1a & 1) * 64);
+        const uint64_t b_1a = bh0 + (uint64_t)((n1a & 1) * 2 * (LT_OP >> 4));
+        if (elect_one()) kblock(d1a, wc + 80u, 64u, b_1a, 4, true);
         __syncwarp();
         if (PROF && rec && n1a >= P0 && n1a < P0 + PN) tl[n1a - P0][3] = clock64();
         ++n1a; progressed = true;
@@ -386,11 +391,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     for (int s = 1; s <= T; ++s) {
       const int t = s - 1;
       lt_wait(bar_e1, (uint32_t)t & 1u, 20000 + t);
-      const float* hf = h1f + (t & 1) * (LT_H * LT_RB) + lane;
+      const float* hf = h1f + (t & 1) * (LT_RB * LF_H1P) + lane * LF_H1P;
       float s0 = hb0, s1 = hb1;
 #pragma unroll 16
       for (int k = 0; k < LT_H; ++k) {
-        const float hv = hf[k * LT_RB];
+        const float hv = hf[k];
         s0 = fmaf(hw[k], hv, s0); s1 = fmaf(hw[LT_H + k], hv, s1);
       }
       __syncwarp();
@@ -717,12 +722,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
     // one product = 2 passes (hi | lo gate gradients, each into its own accumulator) x 4 gate k-blocks x 4 K=16 steps;
     // fully unrolled so that every address is base + immediate
     auto product = [&](const uint32_t a0, const uint64_t b0, const uint32_t d0) {
+      // consecutive MMAs alternate between the hi and the lo accumulator (two independent accumulation chains)
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
+      for (int g = 0; g < 4; ++g) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int k = 0; k < 4; ++k) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int part = 0; part < 2; ++part)
             umma_ts_f16(d0 + (uint32_t)(part * 32), a0 + (uint32_t)(g * 32 + 8 * k), b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + 2 * k), IDESC,
                         (g | k) ? 1u : 0u);
         }
@@ -740,7 +746,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       if (n1 < T && (n1 < 2 || n0 >= n1 - 1) && mbar_test_wait(bar_e1, (uint32_t)n1 & 1u)) {
         if (PROF && rec && n1 >= P0 && n1 < P0 + PN) tl[n1 - P0][0] = clock64();
         tc_fence_after();
-        if (lane == 0) { product(a_l1, b_l1, tmem_base + (uint32_t)((n1 & 1) * 64)); umma_commit(bar_m1 + 8 * (n1 & 1)); }
+        const uint32_t d1 = tmem_base + (uint32_t)((n1 & 1) * 64), bm = bar_m1 + 8 * (n1 & 1);
+        if (elect_one()) { product(a_l1, b_l1, d1); umma_commit(bm); }
         __syncwarp();
         if (PROF && rec && n1 >= P0 && n1 < P0 + PN) tl[n1 - P0][1] = clock64();
         ++n1;
@@ -749,7 +756,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       if (n0 < n1 && mbar_test_wait(bar_e0, (uint32_t)n0 & 1u)) {
         if (PROF && rec && n0 + 1 >= P0 && n0 + 1 < P0 + PN) tl[n0 + 1 - P0][2] = clock64();
         tc_fence_after();
-        if (lane == 0) { product(a_l0, b_l0, tmem_base + 128u); umma_commit(bar_m0); }
+        if (elect_one()) { product(a_l0, b_l0, tmem_base + 128u); umma_commit(bar_m0); }
         __syncwarp();
         if (PROF && rec && n0 + 1 >= P0 && n0 + 1 < P0 + PN) tl[n0 + 1 - P0][3] = clock64();
         ++n0;
