@@ -57,7 +57,7 @@ constexpr int LT_MIN_SMEM = 120 * 1024;              // requested at least: one 
 constexpr float LOG2E = 1.4426950408889634f;
 
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // D fp32, A/B fp16, K-major
+  return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);      // D fp32, A/B fp16, A K-major (TMEM), B N-major
 }
 __device__ __forceinline__ float ex2f(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -111,13 +111,39 @@ __device__ __forceinline__ void lt_wait(uint32_t bar, uint32_t parity, int tag) 
   if (!mbar_try_wait(bar, parity)) lt_wait_timeout(bar, parity, tag);
 }
 
-// fp16 hi/lo split of v, stored at element (row, k) of the 128B-swizzled operand tiles `hi` and `hi + LT_OP`
-__device__ __forceinline__ void store_split(uint8_t* hi, int row, int k, float v) {
+// State operand tiles (MMA N operand: 32 rows x 64 k, fp16) are N-MAJOR: 64-byte lines of the 32 rows for one k, 64-byte
+// swizzle (16-byte chunk index ^= (k >> 1) & 3), 8 k per 512-byte atom.  A cell thread owns one k (its hidden unit) and 8
+// consecutive rows, i.e. exactly one 16-byte chunk: one STS.128 per tile instead of eight 2-byte stores.  Descriptor: SBO = 512,
+// layout SWIZZLE_64B, one K = 16 step = 1024 bytes; instruction descriptor bit 16 (B is MN-major).  (Probed on hardware:
+// tools/umma_ts_bench.cu.)
+__host__ __device__ constexpr uint32_t nmaj_off(uint32_t n, uint32_t k) { return k * 64u + ((((n >> 3) ^ (k >> 1)) & 3u) << 4) + (n & 7u) * 2u; }
+__device__ __forceinline__ uint64_t make_desc_nmaj(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+constexpr int NMAJ_KSTEP = 1024 >> 4;      // descriptor units (16 bytes) per K = 16 step
+
+// fp16 hi/lo split of v (lo = (v - hi) * lo_scale), stored at element (row n, k) of the operand tiles `hi` and `hi + LT_OP`
+__device__ __forceinline__ void store_split(uint8_t* hi, int row, int k, float v, float lo_scale = 1.0f) {
   const __half h = __float2half_rn(v);
-  const __half l = __float2half_rn(v - __half2float(h));
-  const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(k >> 3)) + (uint32_t)(k & 7) * 2u;
+  const __half l = __float2half_rn((v - __half2float(h)) * lo_scale);
+  const uint32_t off = nmaj_off((uint32_t)row, (uint32_t)k);
   *reinterpret_cast<__half*>(hi + off) = h;
   *reinterpret_cast<__half*>(hi + LT_OP + off) = l;
+}
+// the same for 8 consecutive rows (row block rb) of one k: two 16-byte stores
+__device__ __forceinline__ void store_split8(uint8_t* hi, int rb, int k, const float (&v)[8], float lo_scale = 1.0f, int lo_off = LT_OP) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((v[2 * i] - hf.x) * lo_scale, (v[2 * i + 1] - hf.y) * lo_scale);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  const uint32_t off = (uint32_t)k * 64u + ((((uint32_t)rb ^ ((uint32_t)k >> 1)) & 3u) << 4);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(hi + lo_off + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
 // gate row held by lane m (0..127) of M tile `tile`: lanes j, j + 16 of quadrant q serve unit 16 q + j
@@ -281,14 +307,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
       }
       if (L == 0) {
         uint8_t* dst = sm + LF_H0 + (t & 1) * 2 * LT_OP;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) store_split(dst, r8 + r, u, hn[r]);
+        store_split8(dst, r8 >> 3, u, hn);
       } else {
         if (t >= 1) lt_wait(bar_a, (uint32_t)(t - 1) & 1u, 3000 + t);    // hid2act of step t - 1 is done (implies t - 2: this h1f buffer is free)
         uint8_t* dst = sm + LF_H1;
         float* hf = h1f + (t & 1) * (LT_RB * LF_H1P) + r8 * LF_H1P + u;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { store_split(dst, r8 + r, u, hn[r]); hf[r * LF_H1P] = hn[r]; }
+        for (int r = 0; r < 8; ++r) hf[r * LF_H1P] = hn[r];
+        store_split8(dst, r8 >> 3, u, hn);
       }
       if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][3] = clock64();
       tc_fence_before();
@@ -308,8 +334,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
     //   M1b(s) = W_hh1 . h1_{s-1}              needs E1(s-1), after M1a(s)
     // The completed phases of every barrier are counted here (each phase is observed before the next can complete).
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
-    const uint64_t dsc = make_desc_sw128(0, 1024);
-    const uint64_t bh0 = dsc + (smem_u32(sm + LF_H0) >> 4), bh1 = dsc + (smem_u32(sm + LF_H1) >> 4), bz = dsc + (smem_u32(sm + LF_Z) >> 4);
+    const uint64_t bh0 = make_desc_nmaj(smem_u32(sm + LF_H0)), bh1 = make_desc_nmaj(smem_u32(sm + LF_H1)), bz = make_desc_nmaj(smem_u32(sm + LF_Z));
     const uint32_t wc = tmem_base + LF_WCOL0;
     // one weight block (TMEM columns `acol` of tile 0, `tstride` columns further for tile 1) against the hi and lo operand tile, nk K = 16 steps
     auto kblock = [&](uint32_t d, uint32_t acol, uint32_t tstride, uint64_t bd, int nk, bool fresh) {
@@ -321,7 +346,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 #pragma unroll
           for (int tile = 0; tile < 2; ++tile)
             if (k < nk)
-              umma_ts_f16(d + (uint32_t)(tile * 32), acol + (uint32_t)tile * tstride + (uint32_t)(8 * k), bd + (uint64_t)(part * (LT_OP >> 4) + 2 * k),
+              umma_ts_f16(d + (uint32_t)(tile * 32), acol + (uint32_t)tile * tstride + (uint32_t)(8 * k), bd + (uint64_t)(part * (LT_OP >> 4) + NMAJ_KSTEP * k),
                           IDESC, (fresh && part == 0 && k == 0) ? 0u : 1u);
     };
     int n0 = 0, n1a = 0, n1b = 0, e0_done = 0, e1_done = 0, z_done = 0;
@@ -671,6 +696,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][1] = clock64();
       if (i < T) {
       // ---- gate gradients of this thread's (unit, 8 rows)
+      float dgi[8], dgf[8], dgg[8], dgo[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float tc = tanhf_(cc[r]);
@@ -680,17 +706,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
         const float d_g = dc * gi[r] * (1.f - gg[r] * gg[r]);
         const float d_o = dh[r] * tc * go[r] * (1.f - go[r]);
         dcrec[r] = dc * gf[r];
-        const int row = rloc + r;
-        const uint32_t off = sw128_off((uint32_t)row, (uint32_t)(u >> 3)) + (uint32_t)(u & 7) * 2u;
-        const float dv[4] = {d_i, d_f, d_g, d_o};
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const __half h = __float2half_rn(dv[g]);
-          const __half l = __float2half_rn((dv[g] - __half2float(h)) * 2048.0f);
-          *reinterpret_cast<__half*>(dgt + g * LT_OP + off) = h;
-          *reinterpret_cast<__half*>(dgt + (4 + g) * LT_OP + off) = l;
-        }
+        dgi[r] = d_i; dgf[r] = d_f; dgg[r] = d_g; dgo[r] = d_o;
       }
+      // residual scaled by 2^11 so that it is not lost in the fp16 subnormals; one 16-byte store per tile
+      store_split8(dgt + 0 * LT_OP, rb, u, dgi, 2048.0f, 4 * LT_OP);
+      store_split8(dgt + 1 * LT_OP, rb, u, dgf, 2048.0f, 4 * LT_OP);
+      store_split8(dgt + 2 * LT_OP, rb, u, dgg, 2048.0f, 4 * LT_OP);
+      store_split8(dgt + 3 * LT_OP, rb, u, dgo, 2048.0f, 4 * LT_OP);
       if (PROF && rec && i >= P0 && i < P0 + PN) tl[i - P0][2] = clock64();
       tc_fence_before();
       fence_proxy_async();
@@ -718,7 +740,6 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_f16(128, LT_RB);
     const uint32_t dg_u = smem_u32(sm + LBK_DG);
-    const uint64_t dsc = make_desc_sw128(0, 1024);
     // one product = 2 passes (hi | lo gate gradients, each into its own accumulator) x 4 gate k-blocks x 4 K=16 steps;
     // fully unrolled so that every address is base + immediate
     auto product = [&](const uint32_t a0, const uint64_t b0, const uint32_t d0) {
@@ -729,13 +750,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
           for (int part = 0; part < 2; ++part)
-            umma_ts_f16(d0 + (uint32_t)(part * 32), a0 + (uint32_t)(g * 32 + 8 * k), b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + 2 * k), IDESC,
+            umma_ts_f16(d0 + (uint32_t)(part * 32), a0 + (uint32_t)(g * 32 + 8 * k), b0 + (uint64_t)((part * 4 + g) * (LT_OP >> 4) + NMAJ_KSTEP * k), IDESC,
                         (g | k) ? 1u : 0u);
         }
       }
     };
     const uint32_t a_l1 = tmem_base + LB_WCOL0, a_l0 = tmem_base + LB_WCOL0 + 128u;
-    const uint64_t b_l1 = dsc + (dg_u >> 4), b_l0 = dsc + ((dg_u + 8u * LT_OP) >> 4);
+    const uint64_t b_l1 = make_desc_nmaj(dg_u), b_l0 = make_desc_nmaj(dg_u + 8u * LT_OP);
     // event loop: issue whichever layer's product has its operand ready, so that neither recurrence chain waits
     // behind the other's barrier.  n1 / n0 = products issued so far.  M1(n1) overwrites accumulator n1 & 1, which
     // layer 0 reads in step n1 - 2: that step is complete once M0(n1 - 2) has been issued (n0 >= n1 - 1).

@@ -26,14 +26,20 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __host__ __device__ inline float a_val(int m, int k) { return (float)((m * 7 + k * 3) % 17 - 8) / 8.f; }
 __host__ __device__ inline float b_val(int n, int k) { return (float)((n * 5 + k) % 13 - 6) / 4.f; }
 
-__global__ void __launch_bounds__(128, 1) bench(int N, int cnt, float* d_out, long long* t_out) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int cnt, float* d_out, long long* t_out, int mn_major, int sbo_bytes, int kstep_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 64 * 64; i += 128) {                 // B tile: up to 64 rows x 64 k
     const int n = i >> 6, k = i & 63;
-    *reinterpret_cast<__half*>(smem + sw128_off(n, k >> 3) + (k & 7) * 2) = __float2half_rn(n < N ? b_val(n, k) : 0.f);
+    const __half hv = __float2half_rn(n < N ? b_val(n, k) : 0.f);
+    if (!mn_major) *reinterpret_cast<__half*>(smem + sw128_off(n, k >> 3) + (k & 7) * 2) = hv;
+    else if (n < 32) {
+      // N-major, 64-byte rows (32 n per k), SWIZZLE_64B: 16-byte chunk index ^= (k >> 1) & 3 ; 8 k per 512-byte atom
+      const int chunk = (n >> 3) ^ ((k >> 1) & 3);
+      *reinterpret_cast<__half*>(smem + k * 64 + chunk * 16 + (n & 7) * 2) = hv;
+    }
   }
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_s), 256); tmem_relinquish(); }
@@ -55,12 +61,17 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int cnt, float* d_out, lo
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint64_t bd0 = make_desc_sw128(smem_u32(smem), 1024);
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) | (mn_major ? (1u << 16) : 0u);
+  uint64_t bd0 = make_desc_sw128(smem_u32(smem), 1024);
+  int kstep = 2;
+  if (mn_major) {
+    bd0 = (uint64_t)((smem_u32(smem) & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+    kstep = kstep_bytes >> 4;
+  }
   if (warp == 0) {
     // correctness: 4 K = 16 steps
     if (elect_one()) {
-      for (int k = 0; k < 4; ++k) umma_ts_f16(tmem_base, tmem_base + 128 + 8 * k, bd0 + 2 * k, idesc, k ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_ts_f16(tmem_base, tmem_base + 128 + 8 * k, bd0 + kstep * k, idesc, k ? 1u : 0u);
       umma_commit(smem_u32(&bar));
     }
     __syncwarp();
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int cnt, float* d_out, lo
   if (warp == 0) {
     long long t0 = clock64();
     if (elect_one()) {
-      for (int i = 0; i < cnt; ++i) umma_ts_f16(tmem_base + 32 * (i & 1), tmem_base + 128 + 8 * (i & 3), bd0 + 2 * (i & 3), idesc, i >= 2 ? 1u : 0u);
+      for (int i = 0; i < cnt; ++i) umma_ts_f16(tmem_base + 32 * (i & 1), tmem_base + 128 + 8 * (i & 3), bd0 + kstep * (i & 3), idesc, i >= 2 ? 1u : 0u);
       umma_commit(smem_u32(&bar));
     }
     __syncwarp();
@@ -97,9 +108,12 @@ int main() {
   float* d; long long* t;
   cudaMalloc(&d, 128 * 64 * sizeof(float)); cudaMalloc(&t, 16);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  for (int N : {16, 32, 64}) {
+  struct Cfg { int N, mn, sbo, kstep; };
+  const Cfg cfgs[] = {{16, 0, 0, 0}, {32, 0, 0, 0}, {64, 0, 0, 0}, {32, 1, 512, 1024}, {32, 1, 1024, 1024}, {32, 1, 512, 512}, {32, 1, 64, 1024}};
+  for (const Cfg& cf : cfgs) {
+    const int N = cf.N;
     const int cnt = 256;
-    bench<<<1, 128, 65536>>>(N, cnt, d, t);
+    bench<<<1, 128, 65536>>>(N, cnt, d, t, cf.mn, cf.sbo, cf.kstep);
     cudaError_t e = cudaDeviceSynchronize();
     float h[128 * 64]; long long ht[2];
     cudaMemcpy(h, d, 128 * N * sizeof(float), cudaMemcpyDeviceToHost);
@@ -113,7 +127,7 @@ int main() {
         if (err > maxerr) maxerr = err;
         if (fabs(ref) > maxref) maxref = fabs(ref);
       }
-    printf("TS-mode N=%2d: max |D - ref| = %.3e (max |ref| %.1f) | issue %.1f cyc/MMA, complete %.1f cyc/MMA  %s\n", N, maxerr, maxref,
+    printf("TS-mode N=%2d mn_major=%d sbo=%d kstep=%d: max |D - ref| = %.3e (max |ref| %.1f) | issue %.1f cyc/MMA, complete %.1f cyc/MMA  %s\n", N, cf.mn, cf.sbo, cf.kstep, maxerr, maxref,
            (double)ht[0] / cnt, (double)ht[1] / cnt, e == cudaSuccess ? "" : cudaGetErrorString(e));
   }
   return 0;
