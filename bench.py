@@ -30,6 +30,11 @@ FLOP_PER_ROW_STEP = {52: 119.23e6, 104: 237.42e6}     # SURVEY.md App. B (hook-c
 WORKLOAD = dict(scenes=256, agents=16, samples=1, horizon=52, n_timesteps=100, stride=2)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE denoiser launch from the committed `ncu --set full` capture
+# (profiles/r01_unet_tc_ncu_full_4096rows.csv: 274.22 MB + 36.65 MB); only known for the captured shape
+NCU_DRAM_BYTES_PER_LAUNCH = {("bf16", 4096): 274220800 + 36645120}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,7 +278,9 @@ def main():
         flop = FLOP_PER_ROW_STEP[T] * R
         achieved = flop / (per_launch_ms * 1e-3) / 1e12 if den_n else 0.0
         roof = {"bound": "tensor", "kernel": "denoiser forward (%s)" % ("unet_tc megakernel" if a.precision == "bf16" else "fp32 SIMT layer kernels"),
-                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((a.precision, R)), "traffic_unit": "bytes (dram read + write per launch)",
+                "traffic_source": "profiles/r01_unet_tc_ncu_full_4096rows.csv (ncu --set full, one launch)",
                 "peak_source": peak_src + " bf16_tflops_sustained", "per_launch_ms": per_launch_ms, "launches_timed": den_n,
                 "algorithmic_flop_per_launch": flop,
                 "share_of_step": {k: v[0] / a.steps / ms for k, v in prof.items()}}
