@@ -192,20 +192,29 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
 // accumulates into dtraj.
 __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
   __shared__ float qxs[8][128], qys[8][128];
+  __shared__ float2 unit_pt[128];                        // (lwise, wwise) of sample point p: no per-point integer division
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * 8 + warp;
   const int T = a.T, N = a.N;
-  if (item >= (long long)a.R * T) return;
-  const int row = (int)(item / T), t = (int)(item - (long long)row * T);
+  const int P = a.nl * a.nw;
+  if (threadIdx.x < 128) {
+    const int p = threadIdx.x;
+    unit_pt[p] = p < P ? make_float2(a.lwise[p / a.nw], a.wwise[p % a.nw]) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  // grid: x = row, y = group of 8 time steps
+  const int row = blockIdx.x, t = blockIdx.y * 8 + warp;
+  if (t >= T) return;
   const int g = row / N;
   if (!(fabsf(a.speed[g]) > a.speed_th)) return;       // loss and gradient are zero for non-moving agents
-  const int P = a.nl * a.nw;
   const float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
   const float* M = a.rfa + (size_t)g * 9;
+  const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
   const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
   const float* tr = a.traj + ((size_t)row * T + t) * 6;
   const float px = tr[0], py = tr[1], psi = tr[3];
-  const float c = cosf(psi), sn = sinf(psi);
+  float sn, c;
+  sincosf(psi, &sn, &c);
+  const float wmax = (float)a.W, hmax = (float)a.H;
   uint32_t offm[4];
   int n_off = 0;
 #pragma unroll
@@ -213,11 +222,13 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
     int p = lane + 32 * q;
     bool off = false;
     if (p < P) {
-      float lx = a.lwise[p / a.nw] * L, ly = a.wwise[p % a.nw] * Wd;
+      const float2 up = unit_pt[p];
+      float lx = up.x * L, ly = up.y * Wd;
       float qx = lx * c - ly * sn + px, qy = lx * sn + ly * c + py;
       qxs[warp][p] = qx; qys[warp][p] = qy;
-      float rx = M[0] * qx + M[1] * qy + M[2], ry = M[3] * qx + M[4] * qy + M[5];
-      long long cx = (long long)rx, cy = (long long)ry;      // .long(): truncation (guidance_loss.py:796)
+      float rx = m0 * qx + m1 * qy + m2, ry = m3 * qx + m4 * qy + m5;
+      // .long() truncates (guidance_loss.py:796), then clamp to the raster; done in fp32 -> int32 (identical on [-1, W])
+      int cx = (int)fminf(fmaxf(rx, -1.f), wmax), cy = (int)fminf(fmaxf(ry, -1.f), hmax);
       cx = cx < 0 ? 0 : (cx > a.W - 1 ? a.W - 1 : cx);
       cy = cy < 0 ? 0 : (cy > a.H - 1 ? a.H - 1 : cy);
       off = dm[cy * a.W + cx] == 0;
@@ -332,8 +343,7 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   guidance_loss_grad_kernel<<<S * N, 256, smem, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
   if (a.w_mc != 0.f) {
-    long long items = (long long)R * T;
-    guidance_map_grad_kernel<<<(unsigned)((items + 7) / 8), 256, 0, s>>>(a);
+    guidance_map_grad_kernel<<<dim3((unsigned)R, (unsigned)((T + 7) / 8)), 256, 0, s>>>(a);
     CLD_LAUNCH_OK(h, "guidance_map_grad_kernel");
   }
   return 0;
