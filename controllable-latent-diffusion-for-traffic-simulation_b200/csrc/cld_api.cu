@@ -158,6 +158,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->ws_dh0, (size_t)T * MR * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_traj, MR * T * 6);
   if (!rc) rc = dev_alloc(h, &h->ws_dtraj, MR * T * 4);
+  if (!rc && h->use_lstm_tc) rc = dev_alloc(h, &h->ws_dtraj2, MR * T * 4);
   if (!rc) rc = dev_alloc(h, &h->ws_loss, 3 * MR);
   if (!rc) rc = dev_alloc(h, &h->ws_eps, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_mean, MR * T * cfg->latent_dim);
@@ -176,6 +177,9 @@ void cld_destroy(CldHandle* h) {
   if (!h) return;
   tc_destroy(h);
   lstm_tc_destroy(h);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
@@ -426,8 +430,11 @@ static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* co
     h0 = h->ws_h0;
   }
   if ((rc = decode_rollout_h0(h, z_mean, h0, curr, h->ws_act, h->ws_traj, true, R, s))) return rc;
-  if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, loss_out, R, s))) return rc;
-  return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, g, z_out, grad_out, R, s);
+  // bf16 mode without per-row loss output (the sampler): the two loss kernels run concurrently, each into its own buffer
+  float* dmap = (h->use_lstm_tc && !loss_out && g->w_map_collision != 0.f && !getenv("CLD_LSTM_BWD_SIMT") &&
+                 !getenv("CLD_GUIDANCE_NOFORK")) ? h->ws_dtraj2 : nullptr;
+  if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, dmap, loss_out, R, s))) return rc;
+  return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, dmap, g, z_out, grad_out, R, s);
 }
 
 int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr, const CldScene* scene,

@@ -307,7 +307,7 @@ static float host_linspace(float lo, float hi, int n, int i) {
 }
 
 int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g, float* dtraj,
-                       float* loss, int R, cudaStream_t s) {
+                       float* dtraj_map, float* loss, int R, cudaStream_t s) {
   if (!sc || !g) return fail(h, CLD_ERR_ARG, "scene / guidance config missing");
   const int S = sc->num_scenes, A = sc->agents_per_scene, N = sc->num_samp, T = h->cfg.horizon;
   if (R != S * A * N) return fail(h, CLD_ERR_ARG, "R=%d does not match S*A*N=%d*%d*%d", R, S, A, N);
@@ -340,9 +340,29 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   }
   size_t smem = ((size_t)A * T * 4 + (size_t)A * 8 + T) * sizeof(float);
   CLD_CUDA_OK(h, cudaFuncSetAttribute(guidance_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool fork = dtraj_map != nullptr && loss == nullptr && a.w_mc != 0.f;
+  if (fork) {
+    // the two loss kernels are independent given the trajectories: the map-collision kernel runs on the auxiliary stream into
+    // its own (zeroed) gradient buffer while the agent-collision kernel runs here
+    if (!h->aux_stream) {
+      CLD_CUDA_OK(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      CLD_CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CLD_CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    CLD_CUDA_OK(h, cudaEventRecord(h->ev_fork, s));
+    CLD_CUDA_OK(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    CLD_CUDA_OK(h, cudaMemsetAsync(dtraj_map, 0, (size_t)R * T * 4 * sizeof(float), h->aux_stream));
+    LossArgs am = a;
+    am.dtraj = dtraj_map;
+    guidance_map_grad_kernel<<<dim3((unsigned)R, (unsigned)((T + 7) / 8)), 256, 0, h->aux_stream>>>(am);
+    CLD_LAUNCH_OK(h, "guidance_map_grad_kernel");
+    CLD_CUDA_OK(h, cudaEventRecord(h->ev_join, h->aux_stream));
+  }
   guidance_loss_grad_kernel<<<S * N, 256, smem, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
-  if (a.w_mc != 0.f) {
+  if (fork) {
+    CLD_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+  } else if (a.w_mc != 0.f) {
     guidance_map_grad_kernel<<<dim3((unsigned)R, (unsigned)((T + 7) / 8)), 256, 0, s>>>(a);
     CLD_LAUNCH_OK(h, "guidance_map_grad_kernel");
   }

@@ -576,10 +576,11 @@ int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float
 
 
 int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                            const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+                            const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   DecoderW& w = h->dec;
   int rc;
-  if (h->use_lstm_tc && !getenv("CLD_LSTM_BWD_SIMT")) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, g, z_out, grad_out, R, s);
+  if (h->use_lstm_tc && !getenv("CLD_LSTM_BWD_SIMT")) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, dtraj2, g, z_out, grad_out, R, s);
+  if (dtraj2) return fail(h, CLD_ERR_STATE, "internal: split d(traj) buffers are only handled by the tensor-core backward");
   if ((rc = lstm2_prepare(h, s))) return rc;
   const CldConfig& c = h->cfg;
   if (c.horizon > CLD_MAX_T) return fail(h, CLD_ERR_UNSUPPORTED, "horizon exceeds CLD_MAX_T");

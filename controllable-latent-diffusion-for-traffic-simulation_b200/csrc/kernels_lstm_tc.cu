@@ -493,6 +493,7 @@ __host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 8 * 8 +
 
 struct BwdTcArgs {
   const float *z_mean, *act, *curr, *dtraj, *stash;
+  const float* dtraj2;                  // optional second d(traj) part (map-collision kernel on the auxiliary stream), added in the prologue
   const uint8_t* wblob;                 // packed fp16x2 backward weights for TMEM, [256][128]
   const float* h2a_w;
   float *z_out, *grad_out;
@@ -566,8 +567,14 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
     const int nrow = min(LT_RB, R - row0);
     for (int i = tid; i < nrow * T * 2 / 4; i += LB_THREADS)
       reinterpret_cast<float4*>(act_s)[i] = reinterpret_cast<const float4*>(a.act + (size_t)row0 * T * 2)[i];
-    for (int i = tid; i < nrow * T; i += LB_THREADS)
-      reinterpret_cast<float4*>(dtr_s)[i] = reinterpret_cast<const float4*>(a.dtraj + (size_t)row0 * T * 4)[i];
+    for (int i = tid; i < nrow * T; i += LB_THREADS) {
+      float4 v = reinterpret_cast<const float4*>(a.dtraj + (size_t)row0 * T * 4)[i];
+      if (a.dtraj2) {
+        const float4 w = reinterpret_cast<const float4*>(a.dtraj2 + (size_t)row0 * T * 4)[i];
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      reinterpret_cast<float4*>(dtr_s)[i] = v;
+    }
     if (tid < 2 * LT_H) hw[tid] = a.h2a_w[tid];
     if (tid == 0) {
       mbar_init(bar_m1, 1); mbar_init(bar_m1 + 8, 1); mbar_init(bar_m0, 1); mbar_init(bar_e1, 8); mbar_init(bar_e0, 8);
@@ -892,12 +899,12 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
 
 
 int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                              const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+                              const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   int rc;
   if ((rc = lstm_tc_prepare(h, s))) return rc;
   const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
   BwdTcArgs a;
-  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash; a.wblob = st->wbwd;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.dtraj2 = dtraj2; a.stash = h->stash; a.wblob = st->wbwd;
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
   { const char* e = getenv("CLD_LSTM_PF"); a.pf = e ? atoi(e) : 3; }
