@@ -297,3 +297,23 @@ def test_error_paths(gpu_models):
     e2 = Engine(n_timesteps=10, max_rows=4)
     with pytest.raises(RuntimeError):
         e2.unet_forward(torch.zeros(2, 52, 4).cuda(), torch.zeros(2, 256).cuda(), torch.zeros(2).long().cuda())  # no weights
+
+
+def test_guidance_step_64_agents_vs_oracle(gpu_models):
+    """cfg3-shaped scene (64 agents in one scene): agent-collision pairs across the whole scene, fp32 kernels vs oracle autograd."""
+    dm, vae, _ = gpu_models(10)
+    S, A, N = 1, 64, 1
+    aux, batch = make_scenes(S, A, seed=61, dense=True)
+    from cld_b200.engine import default_guidance
+    eng = dm.engine(S * A * N)
+    scene = eng.make_scene(batch, S, A, N)
+    torch.manual_seed(62)
+    z = torch.randn(S * A * N, 52, 4)
+    z_out, grad, loss = eng.guidance_step(z.cuda(), aux["cond_feat"].cuda(), aux["curr_states"].cuda(), scene, default_guidance())
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    g_or, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], batch, A, N)
+    assert rel(loss[0], torch.cat([p["agent_collision"] for p in per]).reshape(-1)) < 1e-4
+    assert rel(loss[1], torch.cat([p["map_collision"] for p in per]).reshape(-1)) < 1e-4
+    assert rel(grad, g_or) < 1e-3
+    nz = g_or != 0
+    assert (torch.sign(grad.cpu())[nz] == torch.sign(g_or)[nz]).float().mean().item() > 0.999
