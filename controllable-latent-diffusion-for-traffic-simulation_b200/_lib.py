@@ -18,6 +18,8 @@ EXPORTS = [
     "cld_set_schedule", "cld_unet_forward", "cld_unet_debug_stage", "cld_posterior_step", "cld_add_noise",
     "cld_decode_rollout", "cld_unicycle", "cld_indicators", "cld_guidance_step", "cld_sample",
     "cld_launch_count", "cld_profile_begin", "cld_profile_end", "cld_tc_selftest",
+    "cld_context_create", "cld_context_destroy", "cld_context_last_error", "cld_context_load", "cld_context_forward",
+    "cld_context_launch_count", "cld_context_conv_flops",
 ]
 
 
@@ -81,11 +83,24 @@ def _load():
     lib.cld_launch_count.argtypes = [vp]
     lib.cld_profile_begin.argtypes = [vp]
     lib.cld_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int), i32]
+    lib.cld_context_create.argtypes = [i32, C.POINTER(vp)]
+    lib.cld_context_destroy.argtypes = [vp]
+    lib.cld_context_last_error.argtypes = [vp]
+    lib.cld_context_load.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), i32, vp]
+    lib.cld_context_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp]
+    lib.cld_context_launch_count.argtypes = [vp]
+    lib.cld_context_conv_flops.argtypes = [vp]
+    special = ("cld_destroy", "cld_last_error", "cld_launch_count", "cld_context_destroy", "cld_context_last_error",
+               "cld_context_launch_count", "cld_context_conv_flops")
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cld_destroy", "cld_last_error", "cld_launch_count"):
+        if name not in special:
             fn.restype = C.c_int
     lib.cld_launch_count.restype = C.c_ulonglong
+    lib.cld_context_destroy.restype = None
+    lib.cld_context_last_error.restype = C.c_char_p
+    lib.cld_context_launch_count.restype = C.c_ulonglong
+    lib.cld_context_conv_flops.restype = C.c_double
     return lib
 
 

@@ -1,0 +1,753 @@
+// Context encoder of the sampling path: ContextEncoder.forward (reference models/context_utils.py:40-61) on sm_100a.
+//   map_encoder      : torchvision ResNet-18 with a 34-channel 7x7 stem, eval-mode BatchNorm, fc 512 -> 256
+//                      (src/tbsim/models/base_models.py:573-607, diffuser_helpers.py:297-348)
+//   agent_state_enc. : MLP 4 -> 64 -> 64 -> 64 with LayerNorm + ReLU (base_models.py:58-66)
+//   process_cond_mlp : MLP 320 -> 320 -> 320 -> 256 -> 256 -> 256 with LayerNorm + ReLU
+//
+// Every convolution is ONE kernel, `conv_tc_kernel`: an implicit GEMM on the tcgen05 tensor pipe.
+//   GEMM row m   = output pixel (b, oh, ow), 128 rows per tile; activations are NHWC bf16 so the 64 input channels of
+//                  one filter tap are 128 contiguous bytes = one row of a 128B-swizzled K-major operand tile
+//   k-block      = (filter tap, 64-channel panel); 4 producer warps gather it with 16-byte cp.async (zero-fill outside
+//                  the image), one thread per GEMM row, straight into the swizzled layout (no im2col buffer in HBM)
+//   weights      = pre-packed per (N tile, k-block) as swizzled [N][64] bf16 images, fetched by one bulk copy (UBLKCP)
+//   accumulators = TMEM, two buffers of up to 256 columns: the epilogue of tile i (BatchNorm scale/shift, residual add,
+//                  ReLU, bf16 NHWC store) overlaps the MMAs of tile i+1; persistent CTAs, one per SM
+// The 7x7 stem (34 input channels) uses the same kernel in STEM mode: the raster is converted once to NHWC bf16 with a
+// 40-channel pitch, so for one filter row the 7 taps x 40 channels of an output pixel are 560 CONTIGUOUS bytes; its
+// k-blocks are 5 x 64 consecutive elements of that run per filter row (K = 7 x 320 instead of 49 x 64).
+// Max-pool, the raster conversion and the MLP head are HBM-bound SIMT kernels.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cld_b200.h"
+#include "tc_common.cuh"
+
+using namespace cld::tc;
+
+namespace {
+
+constexpr int CT_THREADS = 320;        // warps 0-3 epilogue, 4-7 gather producers, 8 MMA issuer, 9 weight loader
+constexpr int CT_A_BYTES = 16384;      // 128 rows x 128 B
+constexpr int CT_MAX_STAGES = 6;
+constexpr int CT_TAIL = 4096 + 256;    // scale/bias [2][512] fp32 + barriers + TMEM slot
+constexpr int IMG_C = 34, IMG_CP = 40, IMG_HW = 224;
+
+struct ConvP {
+  const __nv_bfloat16* in; __nv_bfloat16* out; const __nv_bfloat16* res;
+  const uint8_t* wblob; const float* scale; const float* bias;
+  int H, W, Cin;            // input geometry; Cin = channel pitch in elements
+  int OH, OW, Cout;
+  int KW, stride, pad, panels;
+  int n_kb, NT, n_nt, n_mt, M, relu, stages, lag;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_lag(int lag) {
+  if (lag == 1) cp_async_wait_group<1>(); else if (lag == 2) cp_async_wait_group<2>(); else cp_async_wait_group<3>();
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution + BatchNorm (+ residual) (+ ReLU)
+// ------------------------------------------------------------------------------------------------
+template <int STEM>
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvP P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int S = P.stages, NT = P.NT;
+  const uint32_t b_bytes = (uint32_t)NT * 128u, stage_bytes = CT_A_BYTES + b_bytes;
+  uint8_t* tail = smem + (size_t)S * stage_bytes;
+  float* sc_s = reinterpret_cast<float*>(tail);
+  float* bi_s = sc_s + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 4096 + 8 * (2 * CT_MAX_STAGES + 4));
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * CT_MAX_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * CT_MAX_STAGES, bar_acce = bar_accf + 16;
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < P.Cout; i += CT_THREADS) { sc_s[i] = P.scale[i]; bi_s[i] = P.bias[i]; }
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 129); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
+    mbar_init(bar_acce, 4); mbar_init(bar_acce + 8, 4);
+    fence_barrier_init();
+  }
+  if (warp == 8) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = P.n_mt * P.n_nt, n_kb = P.n_kb;
+
+  if (warp >= 4 && warp < 8) {
+    // ===================== gather producers: thread = GEMM row =====================
+    const int r = tid - 128;
+    const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const int lag = P.lag;
+    int s = 0, sl = 0;              // stage being filled / stage being published (lag k-blocks behind)
+    uint32_t ph = 0;
+    long long it = 0;
+    const int ohw = P.OH * P.OW;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / P.n_nt;
+      const int m = mt * 128 + r;
+      const bool mv = m < P.M;
+      const int b = m / ohw, rem = m - b * ohw, oh = rem / P.OW, ow = rem - oh * P.OW;
+      const int ih0 = oh * P.stride - P.pad, iw0 = ow * P.stride - P.pad;
+      const __nv_bfloat16* base = P.in + (size_t)b * P.H * P.W * P.Cin;
+      int dy = 0, dx = 0, panel = 0;          // STEM: dy = filter row, panel = 64-element block of the 320-wide run
+      for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const uint32_t dst = smem_base + (uint32_t)s * stage_bytes + row_off;
+        const int ih = ih0 + dy;
+        const bool rv = mv && ih >= 0 && ih < P.H;
+        if (STEM) {
+          const __nv_bfloat16* rowp = base + ((long long)ih * P.W + iw0) * IMG_CP;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int j = panel * 8 + c, iw = iw0 + j / 5;
+            const bool v = rv && j < 35 && iw >= 0 && iw < P.W;
+            cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), v ? (const void*)(rowp + j * 8) : (const void*)P.in, v ? 16u : 0u);
+          }
+          if (++panel == 5) { panel = 0; ++dy; }
+        } else {
+          const int iw = iw0 + dx;
+          const bool v = rv && iw >= 0 && iw < P.W;
+          const __nv_bfloat16* src = v ? base + ((size_t)ih * P.W + iw) * P.Cin + panel * 64 : P.in;
+          const uint32_t nb = v ? 16u : 0u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), src + c * 8, nb);
+          if (++panel == P.panels) { panel = 0; if (++dx == P.KW) { dx = 0; ++dy; } }
+        }
+        cp_async_commit();
+        if (it >= lag) {
+          cp_async_wait_lag(lag);
+          fence_proxy_async();
+          mbar_arrive(bar_full + 8 * sl);
+          if (++sl == S) sl = 0;
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+    cp_async_wait_group<0>();
+    fence_proxy_async();
+    const long long pend = it < lag ? it : lag;
+    for (long long j = 0; j < pend; ++j) { mbar_arrive(bar_full + 8 * sl); if (++sl == S) sl = 0; }
+  } else if (warp == 9) {
+    // ===================== weight loader =====================
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int nt = tile % P.n_nt;
+      const uint8_t* src = P.wblob + (size_t)nt * n_kb * b_bytes;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+          bulk_g2s(smem_base + (uint32_t)s * stage_bytes + CT_A_BYTES, src + (size_t)kb * b_bytes, b_bytes, bar_full + 8 * s);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    int s = 0; uint32_t ph = 0, ti = 0;
+    const uint32_t idesc = make_idesc_bf16(128, NT);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(bar_acce + 8 * buf, aph ^ 1u);          // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + buf * 256u;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t ad = make_desc_sw128(a_addr, 1024), bd = make_desc_sw128(a_addr + CT_A_BYTES, 1024);
+        if (elect_one()) {
+          umma_bf16(d_addr, ad, bd, idesc, kb != 0 ? 1u : 0u);
+          umma_bf16(d_addr, ad + 2, bd + 2, idesc, 1u);
+          umma_bf16(d_addr, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d_addr, ad + 6, bd + 6, idesc, 1u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(bar_accf + 8 * buf);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warp q owns TMEM lanes 32q .. 32q+31 =====================
+    const int q = warp;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
+      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(bar_accf + 8 * buf, aph);
+      tc_fence_after();
+      const int m = mt * 128 + q * 32 + lane;
+      const bool mv = m < P.M;
+      const size_t orow = (size_t)m * P.Cout + (size_t)nt * NT;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_wait_ld();
+        if (mv) {
+          const float* sc = sc_s + nt * NT + c0;
+          const float* bi = bi_s + nt * NT + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[g * 8 + j], bi[g * 8 + j]);
+            if (P.res != nullptr) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(P.res + orow + c0 + g * 8);
+              y[0] += bf_lo(rr.x); y[1] += bf_hi(rr.x); y[2] += bf_lo(rr.y); y[3] += bf_hi(rr.y);
+              y[4] += bf_lo(rr.z); y[5] += bf_hi(rr.z); y[6] += bf_lo(rr.w); y[7] += bf_hi(rr.w);
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
+                make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight / parameter packing
+// ------------------------------------------------------------------------------------------------
+// w [Cout][Cin][KH][KW] fp32 -> per (N tile, k-block) swizzled [NT][64] bf16 images
+__global__ void ctx_pack_conv_kernel(uint8_t* __restrict__ dst, const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
+                                     int NT, int n_kb, int panels, int stem, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx & 63);
+  long long t = idx >> 6;
+  const int nr = (int)(t % NT); t /= NT;
+  const int kb = (int)(t % n_kb);
+  const int nt = (int)(t / n_kb);
+  const int n = nt * NT + nr;
+  float v = 0.f;
+  if (stem) {
+    const int dy = kb / 5, kk = (kb % 5) * 64 + k, dxp = kk / IMG_CP, ch = kk % IMG_CP;
+    if (dxp < KW && ch < Cin) v = w[(((size_t)n * Cin + ch) * KH + dy) * KW + dxp];
+  } else {
+    const int tap = kb / panels, ci = (kb % panels) * 64 + k, dy = tap / KW, dx = tap % KW;
+    if (ci < Cin) v = w[(((size_t)n * Cin + ci) * KH + dy) * KW + dx];
+  }
+  *reinterpret_cast<__nv_bfloat16*>(dst + ((size_t)nt * n_kb + kb) * NT * 128 + sw128_off(nr, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(v);
+}
+
+// eval-mode BatchNorm as y = x * scale + shift
+__global__ void ctx_fold_bn_kernel(float* scale, float* shift, const float* g, const float* b, const float* rm, const float* rv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = g[i] / sqrtf(rv[i] + 1e-5f);
+  scale[i] = s;
+  shift[i] = b[i] - rm[i] * s;
+}
+
+__global__ void ctx_transpose_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx - r * cols;
+  dst[(size_t)c * rows + r] = src[idx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// HBM-bound helpers
+// ------------------------------------------------------------------------------------------------
+// image [B,34,224,224] fp32 (NCHW) -> [B,224,224,40] bf16 (NHWC, channels 34..39 zero); one block per image row
+__global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 tile[IMG_HW * IMG_CP];
+  const int b = blockIdx.x / IMG_HW, h = blockIdx.x % IMG_HW;
+  const float* src = img + ((size_t)b * IMG_C * IMG_HW + h) * IMG_HW;
+  for (int i = threadIdx.x; i < IMG_C * IMG_HW; i += 256) {
+    const int c = i / IMG_HW, w = i - c * IMG_HW;
+    tile[w * IMG_CP + c] = __float2bfloat16_rn(src[(size_t)c * IMG_HW * IMG_HW + w]);
+  }
+  for (int i = threadIdx.x; i < (IMG_CP - IMG_C) * IMG_HW; i += 256) {
+    const int c = IMG_C + i / IMG_HW, w = i % IMG_HW;
+    tile[w * IMG_CP + c] = __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * IMG_HW * IMG_CP);
+  const uint4* ts = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < IMG_HW * IMG_CP / 8; i += 256) dst[i] = ts[i];
+}
+
+__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// MaxPool2d(3, stride 2, padding 1) on NHWC bf16, 8 channels per thread
+__global__ void ctx_maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
+                                   int OH, int OW) {
+  const long long total = (long long)B * OH * OW * (C >> 3);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cc = (int)(idx % (C >> 3));
+  long long t = idx / (C >> 3);
+  const int ow = (int)(t % OW); t /= OW;
+  const int oh = (int)(t % OH);
+  const int b = (int)(t / OH);
+  uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf pairs
+  for (int dy = 0; dy < 3; ++dy) {
+    const int ih = oh * 2 - 1 + dy;
+    if (ih < 0 || ih >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int iw = ow * 2 - 1 + dx;
+      if (iw < 0 || iw >= W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)b * H + ih) * W + iw) * C + cc * 8);
+      m.x = bmax2(m.x, v.x); m.y = bmax2(m.y, v.y); m.z = bmax2(m.z, v.z); m.w = bmax2(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)b * OH + oh) * OW + ow) * C + cc * 8) = m;
+}
+
+// debug / verification tap: NHWC bf16 -> NCHW fp32
+__global__ void ctx_tap_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  long long t = idx / C;
+  const int w = (int)(t % W); t /= W;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  out[(((size_t)b * C + c) * H + h) * W + w] = __bfloat162float(in[idx]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: avg-pool + fc + agent-state MLP + process_cond MLP, 8 agents per CTA, fp32
+// ------------------------------------------------------------------------------------------------
+constexpr int HD_AG = 8, HD_THREADS = 320, HD_LD = 512;
+struct HeadP {
+  const __nv_bfloat16* feat;      // [B,7,7,512] layer4 output
+  const float* curr;              // [B,4]
+  float* cond;                    // [B,256]
+  float* map_feat;                // optional [B,256]
+  int B, npix;
+  // transposed weights [K][N], biases, LayerNorm scale / shift
+  const float *s0w, *s0b, *s0g, *s0e, *s1w, *s1b, *s1g, *s1e, *s2w, *s2b;
+  const float *fcw, *fcb;
+  const float *p0w, *p0b, *p0g, *p0e, *p1w, *p1b, *p1g, *p1e, *p2w, *p2b, *p2g, *p2e, *p3w, *p3b, *p3g, *p3e, *p4w, *p4b;
+};
+
+// out[a][n] = sum_k in[a][k] * Wt[k][n] + b[n]   (thread = n, 8 agents share every weight read)
+__device__ __forceinline__ void hd_linear(const float* in, int ldi, const float* __restrict__ Wt, const float* __restrict__ b, float* out,
+                                          int ldo, int K, int N) {
+  const int n = threadIdx.x;
+  if (n < N) {
+    float acc[HD_AG];
+#pragma unroll
+    for (int a = 0; a < HD_AG; ++a) acc[a] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float w = Wt[(size_t)k * N + n];
+#pragma unroll
+      for (int a = 0; a < HD_AG; ++a) acc[a] = fmaf(in[a * ldi + k], w, acc[a]);
+    }
+    const float bb = b[n];
+#pragma unroll
+    for (int a = 0; a < HD_AG; ++a) out[a * ldo + n] = acc[a] + bb;
+  }
+  __syncthreads();
+}
+// LayerNorm (eps 1e-5, biased variance) + ReLU in place; warp a handles agent a
+__device__ __forceinline__ void hd_ln_relu(float* x, int ld, const float* __restrict__ g, const float* __restrict__ e, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < HD_AG) {
+    float* row = x + warp * ld;
+    float s = 0.f;
+    for (int i = lane; i < N; i += 32) s += row[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / N;
+    float v = 0.f;
+    for (int i = lane; i < N; i += 32) { const float d = row[i] - mean; v = fmaf(d, d, v); }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / N + 1e-5f);
+    for (int i = lane; i < N; i += 32) row[i] = fmaxf((row[i] - mean) * rstd * g[i] + e[i], 0.f);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
+  __shared__ float bufA[HD_AG * HD_LD], bufB[HD_AG * HD_LD];
+  const int a0 = blockIdx.x * HD_AG, tid = threadIdx.x;
+  // average pool: bufA[a][c], c < 512
+  for (int i = tid; i < HD_AG * 64; i += HD_THREADS) {
+    const int a = i >> 6, cc = i & 63, ag = min(a0 + a, P.B - 1);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < P.npix; ++p) {
+      const uint4 v = *reinterpret_cast<const uint4*>(P.feat + ((size_t)ag * P.npix + p) * 512 + cc * 8);
+      acc[0] += bf_lo(v.x); acc[1] += bf_hi(v.x); acc[2] += bf_lo(v.y); acc[3] += bf_hi(v.y);
+      acc[4] += bf_lo(v.z); acc[5] += bf_hi(v.z); acc[6] += bf_lo(v.w); acc[7] += bf_hi(v.w);
+    }
+    const float inv = 1.f / P.npix;
+    for (int j = 0; j < 8; ++j) bufA[a * HD_LD + cc * 8 + j] = acc[j] * inv;
+  }
+  __syncthreads();
+  // fc 512 -> 256 into bufB[a][64 + n]  (the concat layout: [state 0..63 | map 64..319])
+  hd_linear(bufA, HD_LD, P.fcw, P.fcb, bufB + 64, HD_LD, 512, 256);
+  if (P.map_feat != nullptr) {
+    for (int i = tid; i < HD_AG * 256; i += HD_THREADS) {
+      const int a = i >> 8, n = i & 255;
+      if (a0 + a < P.B) P.map_feat[(size_t)(a0 + a) * 256 + n] = bufB[a * HD_LD + 64 + n];
+    }
+  }
+  // agent-state MLP: curr -> bufA
+  if (tid < HD_AG * 4) { const int a = tid >> 2, ag = min(a0 + a, P.B - 1); bufA[a * HD_LD + (tid & 3)] = P.curr[(size_t)ag * 4 + (tid & 3)]; }
+  __syncthreads();
+  float* t1 = bufA + 64;          // scratch columns inside bufA (row stride HD_LD)
+  hd_linear(bufA, HD_LD, P.s0w, P.s0b, t1, HD_LD, 4, 64);
+  hd_ln_relu(t1, HD_LD, P.s0g, P.s0e, 64);
+  float* t2 = bufA + 128;
+  hd_linear(t1, HD_LD, P.s1w, P.s1b, t2, HD_LD, 64, 64);
+  hd_ln_relu(t2, HD_LD, P.s1g, P.s1e, 64);
+  hd_linear(t2, HD_LD, P.s2w, P.s2b, bufB, HD_LD, 64, 64);            // state feature -> bufB[a][0..63]
+  // process_cond_mlp on bufB[a][0..319]
+  hd_linear(bufB, HD_LD, P.p0w, P.p0b, bufA, HD_LD, 320, 320);
+  hd_ln_relu(bufA, HD_LD, P.p0g, P.p0e, 320);
+  hd_linear(bufA, HD_LD, P.p1w, P.p1b, bufB, HD_LD, 320, 320);
+  hd_ln_relu(bufB, HD_LD, P.p1g, P.p1e, 320);
+  hd_linear(bufB, HD_LD, P.p2w, P.p2b, bufA, HD_LD, 320, 256);
+  hd_ln_relu(bufA, HD_LD, P.p2g, P.p2e, 256);
+  hd_linear(bufA, HD_LD, P.p3w, P.p3b, bufB, HD_LD, 256, 256);
+  hd_ln_relu(bufB, HD_LD, P.p3g, P.p3e, 256);
+  hd_linear(bufB, HD_LD, P.p4w, P.p4b, bufA, HD_LD, 256, 256);
+  for (int i = tid; i < HD_AG * 256; i += HD_THREADS) {
+    const int a = i >> 8, n = i & 255;
+    if (a0 + a < P.B) P.cond[(size_t)(a0 + a) * 256 + n] = bufA[a * HD_LD + n];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct ConvLayer {
+  int Cin_real, Cin, Cout, KH, KW, stride, pad, stem, panels, n_kb, NT, n_nt, stages, lag;
+  uint8_t* wblob = nullptr; float* scale = nullptr; float* shift = nullptr;
+};
+
+std::string g_ctx_create_err;
+
+}  // namespace
+
+struct CldContext {
+  int device = 0, num_sms = 0, max_agents = 0, chunk = 0;
+  std::string err;
+  std::vector<void*> allocs;
+  ConvLayer conv[20];           // 0 stem; then per block conv1, conv2[, downsample] in execution order
+  float* head_w[30] = {nullptr};
+  __nv_bfloat16 *img16 = nullptr, *stem_out = nullptr, *bufX = nullptr, *bufY = nullptr, *bufZ = nullptr, *bufD = nullptr;
+  bool loaded = false;
+  unsigned long long launches = 0;
+  double conv_flops_per_agent = 0.0;     // 2*MAC of the 20 convolutions as executed (padded K included)
+};
+
+namespace {
+
+int cfail(CldContext* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_ctx_create_err = buf;
+  return code;
+}
+#define CTX_CUDA_OK(c, expr)                                                                                     \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if (_e != cudaSuccess) return cfail(c, CLD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CTX_LAUNCH_OK(c, name)                                                                                   \
+  do {                                                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                                         \
+    if (_e != cudaSuccess) return cfail(c, CLD_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    ++(c)->launches;                                                                                             \
+  } while (0)
+
+template <typename T>
+int calloc_dev(CldContext* c, T** p, size_t n) {
+  void* q = nullptr;
+  CTX_CUDA_OK(c, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+  c->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+void plan_conv(ConvLayer& L, int cin_real, int cout, int k, int stride, int pad, int stem) {
+  L.Cin_real = cin_real; L.Cout = cout; L.KH = k; L.KW = k; L.stride = stride; L.pad = pad; L.stem = stem;
+  L.Cin = stem ? IMG_CP : cin_real;
+  L.panels = stem ? 5 : cin_real / 64;
+  L.n_kb = stem ? k * 5 : k * k * L.panels;
+  const int nt_max = env_int("CLD_CTX_NT", 128);
+  L.NT = cout < nt_max ? cout : nt_max;
+  L.n_nt = cout / L.NT;
+  const int stage_bytes = CT_A_BYTES + L.NT * 128;
+  int st = (200 * 1024) / stage_bytes;
+  L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
+  L.lag = L.stages / 2 > 3 ? 3 : L.stages / 2;
+}
+
+int launch_conv(CldContext* c, const ConvLayer& L, const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* res, int B,
+                int H, int W, int relu, cudaStream_t s) {
+  ConvP P;
+  P.in = in; P.out = out; P.res = res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
+  P.H = H; P.W = W; P.Cin = L.Cin;
+  P.OH = (H + 2 * L.pad - L.KH) / L.stride + 1; P.OW = (W + 2 * L.pad - L.KW) / L.stride + 1; P.Cout = L.Cout;
+  P.KW = L.KW; P.stride = L.stride; P.pad = L.pad; P.panels = L.panels;
+  P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.M = B * P.OH * P.OW; P.n_mt = (P.M + 127) / 128; P.relu = relu;
+  P.stages = L.stages; P.lag = L.lag;
+  const int tiles = P.n_mt * P.n_nt;
+  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  const size_t smem = (size_t)L.stages * (CT_A_BYTES + L.NT * 128) + CT_TAIL;
+  if (L.stem) conv_tc_kernel<1><<<grid, CT_THREADS, smem, s>>>(P);
+  else conv_tc_kernel<0><<<grid, CT_THREADS, smem, s>>>(P);
+  CTX_LAUNCH_OK(c, "conv_tc_kernel");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cld_context_create(int max_agents, CldContext** out) {
+  if (!out || max_agents <= 0) return cfail(nullptr, CLD_ERR_ARG, "cld_context_create: bad arguments");
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: no CUDA device");
+  if (prop.major != 10) return cfail(nullptr, CLD_ERR_ARCH, "cld_context_create: device is sm_%d%d, this library is sm_100a only (no fallback)", prop.major, prop.minor);
+  CldContext* c = new CldContext();
+  c->device = dev; c->num_sms = prop.multiProcessorCount; c->max_agents = max_agents;
+  const int chunk_max = env_int("CLD_CTX_CHUNK", 2048);
+  c->chunk = max_agents < chunk_max ? max_agents : chunk_max;
+  // plan: stem, then (conv1, conv2[, downsample]) per BasicBlock
+  int li = 0;
+  plan_conv(c->conv[li++], IMG_C, 64, 7, 2, 3, 1);
+  int cin = 64;
+  for (int l = 0; l < 4; ++l) {
+    const int cout = 64 << l;
+    for (int b = 0; b < 2; ++b) {
+      const int stride = (l > 0 && b == 0) ? 2 : 1;
+      plan_conv(c->conv[li++], cin, cout, 3, stride, 1, 0);
+      plan_conv(c->conv[li++], cout, cout, 3, 1, 1, 0);
+      if (stride == 2) plan_conv(c->conv[li++], cin, cout, 1, 2, 0, 0);
+      cin = cout;
+    }
+  }
+  const size_t n = (size_t)c->chunk;
+  int rc = 0;
+  // workspace: raster (NHWC bf16), stem output, one standing block buffer; the other three alias the raster region, which
+  // is dead once the stem has run
+  if ((rc = calloc_dev(c, &c->img16, n * IMG_HW * IMG_HW * IMG_CP)) || (rc = calloc_dev(c, &c->stem_out, n * 112 * 112 * 64)) ||
+      (rc = calloc_dev(c, &c->bufX, n * 56 * 56 * 64))) {
+    g_ctx_create_err = c->err;
+    for (void* q : c->allocs) cudaFree(q);
+    delete c;
+    *out = nullptr;
+    return rc;
+  }
+  c->bufY = c->img16;
+  c->bufZ = c->img16 + n * 56 * 56 * 64;
+  c->bufD = c->img16 + 2 * n * 56 * 56 * 64;
+  cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  *out = c;
+  return 0;
+}
+
+void cld_context_destroy(CldContext* c) {
+  if (!c) return;
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+}
+
+const char* cld_context_last_error(const CldContext* c) { return c ? c->err.c_str() : g_ctx_create_err.c_str(); }
+
+unsigned long long cld_context_launch_count(const CldContext* c) { return c ? c->launches : 0ull; }
+
+double cld_context_conv_flops(const CldContext* c) { return c ? c->conv_flops_per_agent : 0.0; }
+
+/* 130 fp32 device tensors: ContextEncoder.state_dict() order without the `num_batches_tracked` entries. */
+int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels, int n, void* stream) {
+  if (!c || !p) return CLD_ERR_ARG;
+  if (n != 130) return cfail(c, CLD_ERR_ARG, "cld_context_load: expected 130 tensors, got %d", n);
+  cudaStream_t s = (cudaStream_t)stream;
+  int idx = 10, rc = 0;
+  auto want = [&](int i, long long ne) -> int {
+    if (numels && numels[i] != ne) return cfail(c, CLD_ERR_ARG, "cld_context_load: tensor %d has %lld elements, expected %lld", i, (long long)numels[i], ne);
+    return 0;
+  };
+  double flops = 0.0;
+  for (int li = 0; li < 20; ++li) {
+    ConvLayer& L = c->conv[li];
+    // state-dict order inside a BasicBlock is conv1, bn1, conv2, bn2, downsample; execution order is the same
+    const float* w = p[idx];
+    if ((rc = want(idx, (long long)L.Cout * L.Cin_real * L.KH * L.KW))) return rc;
+    const float *g = p[idx + 1], *b = p[idx + 2], *rm = p[idx + 3], *rv = p[idx + 4];
+    for (int j = 1; j <= 4; ++j) if ((rc = want(idx + j, L.Cout))) return rc;
+    idx += 5;
+    const size_t bytes = (size_t)L.n_nt * L.n_kb * L.NT * 128;
+    if (!L.wblob) {
+      if ((rc = calloc_dev(c, &L.wblob, bytes))) return rc;
+      if ((rc = calloc_dev(c, &L.scale, L.Cout))) return rc;
+      if ((rc = calloc_dev(c, &L.shift, L.Cout))) return rc;
+    }
+    const long long total = (long long)L.n_nt * L.n_kb * L.NT * 64;
+    ctx_pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L.wblob, w, L.Cout, L.Cin_real, L.KH, L.KW, L.NT, L.n_kb, L.panels,
+                                                                        L.stem, total);
+    CTX_LAUNCH_OK(c, "ctx_pack_conv_kernel");
+    ctx_fold_bn_kernel<<<(L.Cout + 127) / 128, 128, 0, s>>>(L.scale, L.shift, g, b, rm, rv, L.Cout);
+    CTX_LAUNCH_OK(c, "ctx_fold_bn_kernel");
+  }
+  // conv FLOPs per agent as executed (2 * M * N * K with the padded K)
+  {
+    int h = IMG_HW;
+    int li = 0;
+    auto add = [&](const ConvLayer& L, int hin) { const int oh = (hin + 2 * L.pad - L.KH) / L.stride + 1; flops += 2.0 * oh * oh * L.Cout * (double)L.n_kb * 64; return oh; };
+    h = add(c->conv[li++], h);      // stem -> 112
+    h = 56;                         // max-pool
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 2; ++b) {
+        const bool ds = l > 0 && b == 0;
+        const int ho = add(c->conv[li++], h);
+        add(c->conv[li++], ho);
+        if (ds) add(c->conv[li++], h);
+        h = ho;
+      }
+    c->conv_flops_per_agent = flops;
+  }
+  // head weights: transposed copies [K][N] of the Linear layers, vectors as they are
+  // tensor indices: agent_state_encoder 0..9, fc idx..idx+1, process_cond_mlp after
+  const int fc = idx, pm = idx + 2;
+  if (pm + 18 != 130) return cfail(c, CLD_ERR_STATE, "cld_context_load: internal index mismatch (%d)", pm);
+  // (source index, out features, in features) for matrices; vectors copied verbatim
+  const int mats[][3] = {{0, 64, 4}, {4, 64, 64}, {8, 64, 64}, {fc, 256, 512}, {pm + 0, 320, 320}, {pm + 4, 320, 320}, {pm + 8, 256, 320},
+                         {pm + 12, 256, 256}, {pm + 16, 256, 256}};
+  const int mat_slot[] = {0, 4, 8, 10, 12, 16, 20, 24, 28};
+  for (int i = 0; i < 9; ++i) {
+    const int src = mats[i][0], rows = mats[i][1], cols = mats[i][2];
+    if ((rc = want(src, (long long)rows * cols))) return rc;
+    float*& d = c->head_w[mat_slot[i]];
+    if (!d && (rc = calloc_dev(c, &d, (size_t)rows * cols))) return rc;
+    ctx_transpose_kernel<<<(rows * cols + 255) / 256, 256, 0, s>>>(d, p[src], rows, cols);
+    CTX_LAUNCH_OK(c, "ctx_transpose_kernel");
+  }
+  // vectors: slot <- source
+  const int vecs[][3] = {{1, 1, 64}, {2, 2, 64}, {3, 3, 64}, {5, 5, 64}, {6, 6, 64}, {7, 7, 64}, {9, 9, 64}, {11, fc + 1, 256},
+                         {13, pm + 1, 320}, {14, pm + 2, 320}, {15, pm + 3, 320}, {17, pm + 5, 320}, {18, pm + 6, 320}, {19, pm + 7, 320},
+                         {21, pm + 9, 256}, {22, pm + 10, 256}, {23, pm + 11, 256}, {25, pm + 13, 256}, {26, pm + 14, 256}, {27, pm + 15, 256},
+                         {29, pm + 17, 256}};
+  for (auto& v : vecs) {
+    if ((rc = want(v[1], v[2]))) return rc;
+    float*& d = c->head_w[v[0]];
+    if (!d && (rc = calloc_dev(c, &d, (size_t)v[2]))) return rc;
+    CTX_CUDA_OK(c, cudaMemcpyAsync(d, p[v[1]], sizeof(float) * v[2], cudaMemcpyDeviceToDevice, s));
+  }
+  c->loaded = true;
+  return 0;
+}
+
+/* cond_feat = ContextEncoder.forward(data_batch)['cond_feat']  (models/context_utils.py:40-61).
+ * image [B,34,224,224] fp32, curr_states [B,4] fp32 (x, y, vel, yaw: batch_utils.get_current_states) -> cond_feat [B,256].
+ * map_feat_out (optional) [B,256] = the ResNet's fc output.  tap_stage >= 0 (debug, B <= chunk): copies the activation after
+ * stage 0 (stem + max-pool), 1..4 (layer1..layer4) to tap_out as fp32 NCHW. */
+int cld_context_forward(CldContext* c, const float* image, const float* curr_states, int B, float* cond_feat, float* map_feat_out,
+                        int tap_stage, float* tap_out, void* stream) {
+  if (!c || !image || !curr_states || !cond_feat || B <= 0) return c ? cfail(c, CLD_ERR_ARG, "cld_context_forward: bad arguments") : CLD_ERR_ARG;
+  if (!c->loaded) return cfail(c, CLD_ERR_STATE, "cld_context_forward: weights not loaded");
+  if (tap_stage >= 0 && B > c->chunk) return cfail(c, CLD_ERR_ARG, "cld_context_forward: taps need B <= %d", c->chunk);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = 0;
+  for (int b0 = 0; b0 < B; b0 += c->chunk) {
+    const int nb = (B - b0) < c->chunk ? (B - b0) : c->chunk;
+    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16);
+    CTX_LAUNCH_OK(c, "ctx_image_to_nhwc_kernel");
+    if ((rc = launch_conv(c, c->conv[0], c->img16, c->stem_out, nullptr, nb, IMG_HW, IMG_HW, 1, s))) return rc;
+    {
+      const long long total = (long long)nb * 56 * 56 * 8;
+      ctx_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->stem_out, c->bufX, nb, 112, 112, 64, 56, 56);
+      CTX_LAUNCH_OK(c, "ctx_maxpool_kernel");
+    }
+    auto tap = [&](int stage, const __nv_bfloat16* buf, int h, int ch) -> int {
+      if (tap_stage != stage || !tap_out) return 0;
+      const long long total = (long long)nb * h * h * ch;
+      ctx_tap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(buf, tap_out, nb, h, h, ch);
+      CTX_LAUNCH_OK(c, "ctx_tap_kernel");
+      return 0;
+    };
+    if ((rc = tap(0, c->bufX, 56, 64))) return rc;
+    __nv_bfloat16 *X = c->bufX, *Y = c->bufY, *Z = c->bufZ, *D = c->bufD;
+    int li = 1, h = 56;
+    for (int l = 0; l < 4; ++l) {
+      for (int b = 0; b < 2; ++b) {
+        const bool ds = l > 0 && b == 0;
+        const int ho = ds ? h / 2 : h;
+        if ((rc = launch_conv(c, c->conv[li], X, Y, nullptr, nb, h, h, 1, s))) return rc;
+        const __nv_bfloat16* res = X;
+        if (ds) {
+          if ((rc = launch_conv(c, c->conv[li + 2], X, D, nullptr, nb, h, h, 0, s))) return rc;
+          res = D;
+        }
+        if ((rc = launch_conv(c, c->conv[li + 1], Y, Z, res, nb, ho, ho, 1, s))) return rc;
+        li += ds ? 3 : 2;
+        __nv_bfloat16* t = X; X = Z; Z = t;
+        h = ho;
+      }
+      if ((rc = tap(l + 1, X, h, 64 << l))) return rc;
+    }
+    HeadP hp;
+    hp.feat = X; hp.curr = curr_states + (size_t)b0 * 4; hp.cond = cond_feat + (size_t)b0 * 256;
+    hp.map_feat = map_feat_out ? map_feat_out + (size_t)b0 * 256 : nullptr;
+    hp.B = nb; hp.npix = 49;
+    float** w = c->head_w;
+    hp.s0w = w[0]; hp.s0b = w[1]; hp.s0g = w[2]; hp.s0e = w[3]; hp.s1w = w[4]; hp.s1b = w[5]; hp.s1g = w[6]; hp.s1e = w[7]; hp.s2w = w[8]; hp.s2b = w[9];
+    hp.fcw = w[10]; hp.fcb = w[11];
+    hp.p0w = w[12]; hp.p0b = w[13]; hp.p0g = w[14]; hp.p0e = w[15]; hp.p1w = w[16]; hp.p1b = w[17]; hp.p1g = w[18]; hp.p1e = w[19];
+    hp.p2w = w[20]; hp.p2b = w[21]; hp.p2g = w[22]; hp.p2e = w[23]; hp.p3w = w[24]; hp.p3b = w[25]; hp.p3g = w[26]; hp.p3e = w[27];
+    hp.p4w = w[28]; hp.p4b = w[29];
+    ctx_head_kernel<<<(nb + HD_AG - 1) / HD_AG, HD_THREADS, 0, s>>>(hp);
+    CTX_LAUNCH_OK(c, "ctx_head_kernel");
+  }
+  return 0;
+}
+
+}  // extern "C"

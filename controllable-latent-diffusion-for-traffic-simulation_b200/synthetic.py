@@ -87,3 +87,40 @@ def make_scenes(num_scenes, agents_per_scene, horizon=52, seed=123, cond_dim=256
         'target_pos': target,
     }
     return aux, batch
+
+
+def make_context_batch(num_agents, seed=321, hist=31, size=224):
+    """Synthetic inputs of the context encoder (models/context_utils.py:40-61), shaped like trajdata's agent-centric
+    raster (src/tbsim/utils/trajdata_utils.py:123-156): channels 0..30 are the history frames (ego pixel +1, other agents
+    -1, everything else 0), channels 31..33 the map layers in [0,1].  Every image value is a multiple of 0.5, so a
+    golden file can keep the raster as int8.  Returns the `data_batch` entries ContextEncoder.forward reads."""
+    g = torch.Generator().manual_seed(seed)
+    B = num_agents
+    img = torch.zeros(B, hist + 3, size, size)
+    v = torch.rand(B, generator=g) * 15.0
+    t_back = torch.arange(hist - 1, -1, -1).float() * 0.1                    # seconds before now, oldest first
+    hist_pos = torch.stack([-v[:, None] * t_back[None, :], 0.2 * torch.randn(B, hist, generator=g)], dim=-1)
+    hist_pos[:, -1] = 0.0
+    hist_yaw = 0.05 * torch.randn(B, hist, 1, generator=g)
+    bi = torch.arange(B)
+    for t in range(hist):
+        px = (hist_pos[:, t, 0] * 2 + 56).round().long().clamp(0, size - 1)
+        py = (hist_pos[:, t, 1] * 2 + 112).round().long().clamp(0, size - 1)
+        n_other = 6
+        ox = torch.randint(0, size, (B, n_other), generator=g)
+        oy = torch.randint(0, size, (B, n_other), generator=g)
+        for k in range(n_other):
+            img[bi, t, oy[:, k], ox[:, k]] = -1.0
+        img[bi, t, py, px] = 1.0
+    rows = torch.arange(size)[None, :, None]
+    cols = torch.arange(size)[None, None, :]
+    for c in range(3):
+        half = torch.randint(6, 40, (B,), generator=g)[:, None, None]
+        off = torch.randint(-20, 21, (B,), generator=g)[:, None, None]
+        band = ((rows >= 112 + off - half) & (rows <= 112 + off + half)).expand(B, size, size)
+        r0 = torch.randint(0, 180, (B,), generator=g)[:, None, None]
+        c0 = torch.randint(0, 180, (B,), generator=g)[:, None, None]
+        rect = (rows >= r0) & (rows < r0 + 44) & (cols >= c0) & (cols < c0 + 44)
+        img[:, hist + c] = band.float() * (1.0 if c != 1 else 0.5) + rect.float() * 0.5
+    img[:, hist:].clamp_(0.0, 1.0)
+    return {'image': img, 'history_positions': hist_pos, 'history_yaws': hist_yaw, 'curr_speed': v}

@@ -200,6 +200,37 @@ unsigned long long cld_launch_count(const CldHandle* h);
 int cld_profile_begin(CldHandle* h);
 int cld_profile_end(CldHandle* h, double* ms_by_kind, int* count_by_kind, int nkinds);
 
+/* ---------------------------------------------------------------------------------------------
+ * Context encoder: ContextEncoder.forward (models/context_utils.py:40-61), the provider
+ * of cond_feat for the sampler.  Own handle type (its workspace is sized per agent, not per row).
+ *   map_encoder  = torchvision ResNet-18, 34-channel 7x7 stem, eval-mode BatchNorm, fc 512 -> 256
+ *                  (src/tbsim/models/base_models.py:573-607, src/tbsim/models/diffuser_helpers.py:297-348)
+ *   agent_state_encoder / process_cond_mlp = base_models.MLP with LayerNorm (base_models.py:58-66)
+ * Arithmetic: bf16 tcgen05 implicit-GEMM convolutions with fp32 accumulation, fp32 BatchNorm / residual / head. */
+typedef struct CldContext CldContext;
+
+/* Workspace for up to max_agents agents per forward call (processed in chunks of <= 2048 agents, 6 MB each) on the
+ * CURRENT device; fails with CLD_ERR_ARCH on a device that is not compute capability 10.x. */
+int cld_context_create(int max_agents, CldContext** out);
+void cld_context_destroy(CldContext* c);
+const char* cld_context_last_error(const CldContext* c);   /* c may be NULL: last create() error */
+
+/* The 130 fp32 tensors of ContextEncoder.state_dict() in state-dict order WITHOUT the 20 `num_batches_tracked`
+ * entries (device pointers; numels optional).  Packs the convolution weights into MMA-ready bf16 tiles and folds the
+ * BatchNorm running statistics into a per-channel scale / shift.  Replaces ContextEncoder.__init__/load_state_dict. */
+int cld_context_load(CldContext* c, const float* const* dev_ptrs, const int64_t* numels, int n, void* stream);
+
+/* cond_feat [B,256] = ContextEncoder.forward(data_batch)['cond_feat'] for image [B,34,224,224] (NCHW fp32) and
+ * curr_states [B,4] = (x, y, vel, yaw) of batch_utils.get_current_states (src/tbsim/utils/batch_utils.py:61-65).
+ * map_feat_out (optional) [B,256] receives the ResNet's fc output.  Verification tap: tap_stage 0 (stem + max-pool),
+ * 1..4 (layer1..layer4) copies that activation to tap_out as fp32 NCHW (B <= chunk); pass -1 / NULL otherwise. */
+int cld_context_forward(CldContext* c, const float* image, const float* curr_states, int B, float* cond_feat,
+                        float* map_feat_out, int tap_stage, float* tap_out, void* stream);
+
+unsigned long long cld_context_launch_count(const CldContext* c);
+/* 2*MAC per agent of the 20 convolutions as executed (includes the zero-padded K of the stem). */
+double cld_context_conv_flops(const CldContext* c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,3 +480,99 @@ def sample(unet_sd, sched, cond_rows, x_init, noises, n_timesteps, stride=1, sam
             if sampler == 'ddpm':
                 logp = torch.distributions.Normal(mean, sigma).log_prob(x).mean(dim=(1, 2))
     return {'pred_traj': x0, 'x1': x1, 'log_prob_final': logp}
+
+
+# --------------------------------------------------------------------------------------------------
+# a14. context encoder  (models/context_utils.py:8-61)  -- input provider of the sampler
+#   curr_states      : batch_utils.get_current_states            src/tbsim/utils/batch_utils.py:61-65
+#   agent_state_enc. : base_models.MLP(4 -> 64, (64,64), LayerNorm) src/tbsim/models/base_models.py:58-66
+#   map_encoder      : torchvision resnet18 with a 34-channel 7x7 stem and fc 512 -> 256
+#                      (base_models.py:573-607, diffuser_helpers.py:297-348; the 'map_model.fc' node is taken,
+#                      i.e. WITHOUT RasterizedMapEncoder's trailing ReLU)
+#   process_cond_mlp : MLP(320 -> 256, (320,320,256,256), LayerNorm)
+# State-dict keys are the reference's `vae.context_encoder.*` names (prefix stripped).  eval mode: BatchNorm
+# uses its running statistics.
+# --------------------------------------------------------------------------------------------------
+_RESNET = 'map_encoder.encoder_heads.map_model.'
+
+
+def current_states(batch):
+    """[x, y, vel, yaw] of the current step (batch_utils.py:61-65, unicycle branch)."""
+    return torch.cat([batch['history_positions'][..., -1, :], batch['curr_speed'][..., None],
+                      batch['history_yaws'][..., -1, :1]], dim=-1)
+
+
+def _mlp_ln(sd, p, x, n_hidden):
+    """base_models.MLP with normalization=True: (Linear, LayerNorm, ReLU) x n_hidden, then Linear."""
+    for i in range(n_hidden):
+        x = F.linear(x, sd[p + '%d.weight' % (3 * i)], sd[p + '%d.bias' % (3 * i)])
+        w = sd[p + '%d.weight' % (3 * i + 1)]
+        x = F.relu(F.layer_norm(x, w.shape, w, sd[p + '%d.bias' % (3 * i + 1)], 1e-5))
+    return F.linear(x, sd[p + '%d.weight' % (3 * n_hidden)], sd[p + '%d.bias' % (3 * n_hidden)])
+
+
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'], sd[p + 'bias'], False, 0.0, 1e-5)
+
+
+def _basic_block(sd, p, x, stride):
+    """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)."""
+    out = F.relu(_bn(sd, p + 'bn1.', F.conv2d(x, sd[p + 'conv1.weight'], None, stride, 1)))
+    out = _bn(sd, p + 'bn2.', F.conv2d(out, sd[p + 'conv2.weight'], None, 1, 1))
+    if (p + 'downsample.0.weight') in sd:
+        x = _bn(sd, p + 'downsample.1.', F.conv2d(x, sd[p + 'downsample.0.weight'], None, stride, 0))
+    return F.relu(out + x)
+
+
+def resnet18_global_feature(sd, image, taps=None):
+    """image [B,34,224,224] -> fc output [B,256].  taps (optional dict) receives 'stem' (after maxpool) and
+    'layer1'..'layer4' activations [B,C,H,W]."""
+    p = _RESNET
+    x = F.relu(_bn(sd, p + 'bn1.', F.conv2d(image, sd[p + 'conv1.weight'], None, 2, 3)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    if taps is not None:
+        taps['stem'] = x
+    for li in range(1, 5):
+        for bi in range(2):
+            x = _basic_block(sd, p + 'layer%d.%d.' % (li, bi), x, 2 if (li > 1 and bi == 0) else 1)
+        if taps is not None:
+            taps['layer%d' % li] = x
+    x = x.mean(dim=(2, 3))
+    return F.linear(x, sd[p + 'fc.weight'], sd[p + 'fc.bias'])
+
+
+def context_encode(sd, batch, taps=None):
+    """ContextEncoder.forward (models/context_utils.py:40-61) -> dict(cond_feat [B,256], curr_states [B,4])."""
+    curr = current_states(batch)
+    state_feat = _mlp_ln(sd, 'agent_state_encoder._model.', curr, 2)
+    map_feat = resnet18_global_feature(sd, batch['image'], taps)
+    if taps is not None:
+        taps['state_feat'], taps['map_feat'] = state_feat, map_feat
+    cond = _mlp_ln(sd, 'process_cond_mlp._model.', torch.cat([state_feat, map_feat], dim=-1), 4)
+    return {'cond_feat': cond, 'curr_states': curr}
+
+
+def synth_context_state(shapes, seed=2024):
+    """Deterministic non-trivial parameters for a context encoder (the 47 MB set is not stored in the goldens):
+    `shapes` = ordered {state-dict key: shape}; every tensor comes from its own seeded CPU generator, so the real
+    reference module (oracle/make_golden.py) and cld_b200's mirror get bit-identical values.  BatchNorm running
+    statistics and affine parameters are randomised so that the folding is exercised."""
+    sd = {}
+    for i, (k, shp) in enumerate(shapes.items()):
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        shp = tuple(shp)
+        if k.endswith('num_batches_tracked'):
+            v = torch.tensor(1, dtype=torch.long)
+        elif k.endswith('running_var'):
+            v = 0.5 + torch.rand(shp, generator=g)
+        elif k.endswith('running_mean'):
+            v = 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith('.bias'):
+            v = 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:                      # BatchNorm / LayerNorm scale
+            v = 0.5 + torch.rand(shp, generator=g)
+        else:                                    # conv / linear: He-style fan-in scaling
+            fan_in = int(np.prod(shp[1:]))
+            v = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)
+        sd[k] = v
+    return sd

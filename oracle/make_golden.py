@@ -235,8 +235,41 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "guidance.npz"), S=S, A=A, N=N, seed=41, z=zg.numpy(), z_out=z_ref.numpy(),
                         grad_sgd=grads_ref.numpy(), loss_ac=loss_ref['agent_collision'].numpy(),
                         loss_mc=loss_ref['map_collision'].numpy(), **wsum)
+    context_golden()
     print("golden files written to", GOLD)
 
 
+def context_golden():
+    """a14: the REAL ContextEncoder (models/context_utils.py:8-61) on 3 synthetic agents with the deterministic
+    parameter set of O.synth_context_state -> tests/golden/context.npz (raster as int8 = 2 x value, reference outputs)."""
+    RH.install()
+    from cld_b200.synthetic import make_context_batch
+    _, vae, _ = RH.build_models(n_timesteps=10)
+    ce = vae.context_encoder.eval()
+    shapes = {k: tuple(v.shape) for k, v in ce.state_dict().items()}
+    sd = O.synth_context_state(shapes)
+    ce.load_state_dict(sd)
+    batch = make_context_batch(3, seed=321)
+    with torch.no_grad():
+        ref = ce(batch)
+        taps = {}
+        mine = O.context_encode(sd, batch, taps)
+    check("context cond_feat (oracle vs reference)", mine['cond_feat'], ref['cond_feat'], 1e-6)
+    check("context curr_states", mine['curr_states'], ref['curr_states'], 0.0)
+    img2 = (batch['image'] * 2).round()
+    assert torch.equal(img2 / 2, batch['image'])
+    np.savez_compressed(os.path.join(GOLD, "context.npz"), seed=321, image_x2=img2.to(torch.int8).numpy(),
+                        history_positions=batch['history_positions'].numpy(), history_yaws=batch['history_yaws'].numpy(),
+                        curr_speed=batch['curr_speed'].numpy(), cond_feat=ref['cond_feat'].numpy(),
+                        curr_states=ref['curr_states'].numpy(), map_feat=taps['map_feat'].numpy(),
+                        layer_absmean=np.array([taps[k].abs().mean().item() for k in ('stem', 'layer1', 'layer2', 'layer3', 'layer4')]),
+                        w_sum=float(sum(v.double().sum() for v in sd.values())),
+                        keys=np.array(list(shapes.keys())), shapes=np.array([str(v) for v in shapes.values()]))
+    print("context golden written")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-context" in sys.argv:
+        context_golden()
+    else:
+        main()

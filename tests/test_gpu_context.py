@@ -1,0 +1,99 @@
+"""GPU (-m gpu): the context encoder through the C ABI against the oracle and the golden
+produced by the REAL reference (tests/golden/context.npz).
+
+Tolerances: the convolutions run in bf16 with fp32 accumulation (17 layers deep), BatchNorm / residual / head in fp32:
+ResNet stages <= 2e-2 relative L2, cond_feat <= 2e-2 relative L2 (measured values are printed)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _build(gold, max_agents=64):
+    import cld_oracle as O
+    from cld_b200 import default_algo_config
+    from cld_b200.context import ContextEncoder
+    g = gold("context")
+    shapes = {str(k): eval(str(s)) for k, s in zip(g["keys"], g["shapes"])}
+    sd = O.synth_context_state(shapes)
+    ce = ContextEncoder(4, default_algo_config(), {"image": (34, 224, 224)}, max_agents=max_agents)
+    ce.load_state_dict(sd)
+    return g, sd, ce.cuda()
+
+
+def _golden_batch(g):
+    return {"image": torch.from_numpy(g["image_x2"]).float() / 2, "history_positions": torch.from_numpy(g["history_positions"]),
+            "history_yaws": torch.from_numpy(g["history_yaws"]), "curr_speed": torch.from_numpy(g["curr_speed"])}
+
+
+def test_context_stages_vs_oracle(gold):
+    import cld_oracle as O
+    g, sd, ce = _build(gold)
+    batch = _golden_batch(g)
+    with torch.no_grad():
+        taps = {}
+        O.context_encode(sd, batch, taps)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    for stage, name in enumerate(("stem", "layer1", "layer2", "layer3", "layer4")):
+        out = ce(cb, tap_stage=stage)
+        torch.cuda.synchronize()
+        r = rel(out["tap"], taps[name])
+        print("context stage %s: rel %.3e" % (name, r))
+        assert r < 2e-2, (name, r)
+
+
+def test_context_vs_reference_golden(gold):
+    g, sd, ce = _build(gold)
+    cb = {k: v.cuda() for k, v in _golden_batch(g).items()}
+    out = ce(cb, want_map_feat=True)
+    torch.cuda.synchronize()
+    r_map = rel(out["map_feat"], torch.from_numpy(g["map_feat"]))
+    r = rel(out["cond_feat"], torch.from_numpy(g["cond_feat"]))
+    print("context: rel(map_feat) %.3e rel(cond_feat) %.3e" % (r_map, r))
+    assert torch.equal(out["curr_states"].cpu(), torch.from_numpy(g["curr_states"]))
+    assert r_map < 2e-2 and r < 2e-2, (r_map, r)
+    assert ce.launch_count() > 0
+
+
+def test_context_batch_invariance_and_chunking(gold):
+    """An agent's feature does not depend on what else is in the batch, on the tile it lands in, or on the workspace
+    chunking (B = 21 agents: ragged last GEMM tile in every layer; chunk of 8 agents -> three passes)."""
+    import cld_oracle as O
+    from cld_b200.synthetic import make_context_batch
+    g, sd, ce = _build(gold)
+    batch = make_context_batch(21, seed=5)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    full = ce(cb)["cond_feat"].clone()
+    sub = {k: v[7:12].contiguous() for k, v in cb.items()}
+    part = ce(sub)["cond_feat"]
+    torch.cuda.synchronize()
+    assert torch.equal(full[7:12], part)
+    with torch.no_grad():
+        want = O.context_encode(sd, batch)["cond_feat"]
+    r = rel(full, want)
+    print("context B=21: rel(cond_feat) %.3e" % r)
+    assert r < 2e-2
+    os.environ["CLD_CTX_CHUNK"] = "8"
+    try:
+        g2, sd2, ce2 = _build(gold)
+        chunked = ce2(cb)["cond_feat"]
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["CLD_CTX_CHUNK"]
+    assert torch.equal(chunked, full)
+
+
+def test_context_requires_cuda_module(gold):
+    from cld_b200 import default_algo_config
+    from cld_b200.context import ContextEncoder
+    ce = ContextEncoder(4, default_algo_config(), {"image": (34, 224, 224)})
+    with pytest.raises(RuntimeError):
+        ce({"image": torch.zeros(1, 34, 224, 224), "history_positions": torch.zeros(1, 31, 2),
+            "history_yaws": torch.zeros(1, 31, 1), "curr_speed": torch.zeros(1)})

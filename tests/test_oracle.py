@@ -129,3 +129,46 @@ def test_ddim_final_step_is_x0_prediction():
     x, eps = torch.randn(2, 52, 4), torch.randn(2, 52, 4)
     x0 = O.ddim_next(s, x, eps, 0, -1)
     assert torch.allclose(x0, s["sqrt_recip_alphas_cumprod"][0] * x - s["sqrt_recipm1_alphas_cumprod"][0] * eps)
+
+
+# ----------------------------------------------------------------------------------------------------
+# a14 context encoder
+# ----------------------------------------------------------------------------------------------------
+def _context_case(gold):
+    import torch
+    import cld_oracle as O
+    g = gold("context")
+    shapes = {str(k): eval(str(s)) for k, s in zip(g["keys"], g["shapes"])}
+    sd = O.synth_context_state(shapes)
+    batch = {"image": torch.from_numpy(g["image_x2"]).float() / 2, "history_positions": torch.from_numpy(g["history_positions"]),
+             "history_yaws": torch.from_numpy(g["history_yaws"]), "curr_speed": torch.from_numpy(g["curr_speed"])}
+    return g, sd, batch
+
+
+def test_context_oracle_vs_reference_golden(gold):
+    """oracle.context_encode == the REAL ContextEncoder (models/context_utils.py:40-61) on the golden inputs."""
+    import torch
+    import cld_oracle as O
+    g, sd, batch = _context_case(gold)
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["w_sum"])) < 1e-6 * abs(float(g["w_sum"])) + 1e-6
+    with torch.no_grad():
+        taps = {}
+        out = O.context_encode(sd, batch, taps)
+    assert rel(out["cond_feat"], torch.from_numpy(g["cond_feat"])) < 1e-5
+    assert torch.equal(out["curr_states"], torch.from_numpy(g["curr_states"]))
+    assert rel(taps["map_feat"], torch.from_numpy(g["map_feat"])) < 1e-5
+    am = [taps[k].abs().mean().item() for k in ("stem", "layer1", "layer2", "layer3", "layer4")]
+    assert max(abs(a - b) / b for a, b in zip(am, g["layer_absmean"])) < 1e-4
+
+
+def test_context_mirror_state_dict_matches_reference(gold):
+    """cld_b200.ContextEncoder exposes the reference's 150 state-dict keys with the reference's shapes, and the C ABI
+    gets the 130 floating-point ones."""
+    from cld_b200 import default_algo_config
+    from cld_b200.context import ContextEncoder
+    g = gold("context")
+    ce = ContextEncoder(4, default_algo_config(), {"image": (34, 224, 224)})
+    sd = ce.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in g["shapes"]]
+    assert len(ce.weight_list()) == 130
