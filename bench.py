@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--scenes", type=int, default=WORKLOAD["scenes"])
     ap.add_argument("--cpu-scenes", type=int, default=1, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-context", action="store_true", help="do not time the context encoder (row a14) after the headline")
     return ap.parse_args()
 
 
@@ -153,6 +154,40 @@ def run_reference(a):
         "cpu_baseline": {"value": rate, "unit": "scenarios/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "scenarios/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def context_encoder_rate(dev, agents=1024, iters=5, warmup=3):
+    """SURVEY.md sec. 8 row a14, measured beside the headline (NOT inside its timed region): ContextEncoder.forward
+    (34 x 224 x 224 raster -> cond_feat) for `agents` agents through cld_b200.ContextEncoder / cld_context_forward, inputs resident
+    in HBM, CUDA events.  Algorithmic FLOPs: 6.07 GFLOP per agent (hook-counted on the reference)."""
+    import torch
+    from cld_b200 import default_algo_config
+    from cld_b200.context import ContextEncoder
+    torch.manual_seed(0)
+    ce = ContextEncoder(4, default_algo_config(), {"image": (34, 224, 224)}, max_agents=agents).to(dev)
+    g = torch.Generator(device=dev).manual_seed(11)
+    batch = {"image": (torch.rand(agents, 34, 224, 224, device=dev, generator=g) < 0.05).float(),
+             "history_positions": torch.zeros(agents, 31, 2, device=dev), "history_yaws": torch.zeros(agents, 31, 1, device=dev),
+             "curr_speed": torch.rand(agents, device=dev, generator=g) * 10}
+    for _ in range(warmup):
+        ce(batch)
+    torch.cuda.synchronize()
+    l0 = ce.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ce(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf_peak, _, peak_src = measured_peaks()
+    tflops = 6.07e9 * agents / (ms * 1e-3) / 1e12
+    out = {"value": agents / ms * 1e3, "unit": "agents/s", "agents": agents, "ms": ms, "iters": iters, "dtype": "bf16 (fp32 accumulate)",
+           "algorithmic_gflop_per_agent": 6.07, "executed_gflop_per_agent": ce.conv_flops_per_agent() / 1e9,
+           "achieved_tflops": tflops, "frac_of_bf16_peak": tflops / tf_peak, "peak_source": peak_src + " bf16_tflops_sustained",
+           "gpu_launches": ce.launch_count() - l0, "bytes_in_per_agent": 34 * 224 * 224 * 4}
+    ce.close()
+    return out
 
 
 def workload_config(a):
@@ -290,6 +325,11 @@ def main():
             cpu = {"value": rate, "unit": "scenarios/s", "cores": cores, "kind": "port",
                    "sample": "%d of %d scenes x %d agents, same 50-step %s%s sampler + decode + indicators, 1 timed pass (%.1f s)" % (
                        a.cpu_scenes, S, A, a.sampler, "" if a.no_guidance else " guided", dt)}
+        ctx = None
+        if world == 1 and not a.skip_context:
+            del out, x_init, noise
+            torch.cuda.empty_cache()
+            ctx = context_encoder_rate(dev)
         print(json.dumps({
             "metric": "guided scenarios/sec (50-step DDIM)", "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -297,7 +337,7 @@ def main():
             "row_steps_per_s": value * A * N * K_d, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scenarios/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te.item()},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/cld_b200.h"
@@ -34,7 +35,7 @@ namespace {
 
 constexpr int CT_THREADS = 320;        // warps 0-3 epilogue, 4-7 gather producers, 8 MMA issuer, 9 weight loader
 constexpr int CT_A_BYTES = 16384;      // 128 rows x 128 B
-constexpr int CT_MAX_STAGES = 6;
+constexpr int CT_MAX_STAGES = 8;
 constexpr int CT_TAIL = 4096 + 256;    // scale/bias [2][512] fp32 + barriers + TMEM slot
 constexpr int IMG_C = 34, IMG_CP = 40, IMG_HW = 224;
 
@@ -244,6 +245,164 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvP P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same convolution with the A operand moved by the TMA unit (cp.async.bulk.tensor, SASS UTMALDG).
+// A GEMM tile is a BOX of output pixels (bw x bh pixels of bn images, bw*bh*bn = 128), so the A k-block of filter tap
+// (dy, dx) and channel panel p is ONE 4-D tensor-map box of the NHWC input: {64 channels from p*64, bw pixels from
+// ow0*s + dx - pad (traversal stride s), bh rows from oh0*s + dy - pad, bn images}; out-of-image elements are zero-filled by
+// the TMA unit (= the convolution's padding) and the box lands in the 128B-swizzled K-major layout the MMA reads.
+// Stem: the raster is stored [B,224,232,40] (3 zero pixels left, 5 right) and described to the TMA unit as an OVERLAPPING
+// view {320 elements, 112 output columns at a 160-byte stride, 224 rows, B}: row (ow) of the view is the 7-tap x 40-channel
+// run of output column ow, and its five 64-element boxes per filter row are the k-blocks.
+// One elected thread issues both copies of a stage (A box + weight image) on one mbarrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int CT2_THREADS = 192;       // warps 0-3 epilogue, 4 MMA issuer, 5 TMA producer
+struct ConvT {
+  __nv_bfloat16* out; const __nv_bfloat16* res;
+  const uint8_t* wblob; const float* scale; const float* bias;
+  int OH, OW, Cout, n_kb, NT, n_nt, n_mt, nb, relu, stages;
+  int sx, sy, lbw, lbh, TX, TY;
+  uint16_t kbt[80];         // per k-block: [0,4) channel box index | [4,8) dx - pad + 8 | [8,12) dy - pad + 8
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvT P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int S = P.stages, NT = P.NT;
+  const uint32_t b_bytes = (uint32_t)NT * 128u, stage_bytes = CT_A_BYTES + b_bytes;
+  uint8_t* tail = smem + (size_t)S * stage_bytes;
+  float* sc_s = reinterpret_cast<float*>(tail);
+  float* bi_s = sc_s + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 4096 + 8 * (2 * CT_MAX_STAGES + 4));
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * CT_MAX_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * CT_MAX_STAGES, bar_acce = bar_accf + 16;
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < P.Cout; i += CT2_THREADS) { sc_s[i] = P.scale[i]; bi_s[i] = P.bias[i]; }
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
+    mbar_init(bar_acce, 4); mbar_init(bar_acce + 8, 4);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = P.n_mt * P.n_nt, n_kb = P.n_kb;
+  const int bw = 1 << P.lbw, bh = 1 << P.lbh, bn = 128 >> (P.lbw + P.lbh);
+
+  if (warp == 5) {
+    // ===================== TMA producer: activations box + weight image per stage =====================
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
+      const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
+      const int cx0 = tx * bw * P.sx, cy0 = ty * bh * P.sy, cb0 = tb * bn;
+      const uint8_t* wsrc = P.wblob + (size_t)nt * n_kb * b_bytes;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t e = P.kbt[kb];
+          const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+          mbar_arrive_expect_tx(bar_full + 8 * s, CT_A_BYTES + b_bytes);
+          tma_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx0 + (int)((e >> 4) & 15u) - 8, cy0 + (int)((e >> 8) & 15u) - 8, cb0, bar_full + 8 * s);
+          bulk_g2s(dst + CT_A_BYTES, wsrc + (size_t)kb * b_bytes, b_bytes, bar_full + 8 * s);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    int s = 0; uint32_t ph = 0, ti = 0;
+    const uint32_t idesc = make_idesc_bf16(128, NT);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(bar_acce + 8 * buf, aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + buf * 256u;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t ad = make_desc_sw128(a_addr, 1024), bd = make_desc_sw128(a_addr + CT_A_BYTES, 1024);
+        if (elect_one()) {
+          umma_bf16(d_addr, ad, bd, idesc, kb != 0 ? 1u : 0u);
+          umma_bf16(d_addr, ad + 2, bd + 2, idesc, 1u);
+          umma_bf16(d_addr, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d_addr, ad + 6, bd + 6, idesc, 1u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(bar_accf + 8 * buf);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warp q owns TMEM lanes 32q .. 32q+31 =====================
+    const int q = warp;
+    uint32_t ti = 0;
+    const int r = q * 32 + lane;
+    const int wi = r & (bw - 1), hi = (r >> P.lbw) & (bh - 1), bi = r >> (P.lbw + P.lbh);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
+      const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
+      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+      const int b = tb * bn + bi, oh = ty * bh + hi, ow = tx * bw + wi;
+      const bool mv = b < P.nb;
+      const size_t orow = (((size_t)b * P.OH + oh) * P.OW + ow) * P.Cout + (size_t)nt * NT;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
+      mbar_wait(bar_accf + 8 * buf, aph);
+      tc_fence_after();
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_wait_ld();
+        if (mv) {
+          const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
+          const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
+            float y[8];
+            y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
+            y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
+            y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
+            y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
+            if (P.res != nullptr) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(P.res + orow + c0 + g * 8);
+              y[0] += bf_lo(rr.x); y[1] += bf_hi(rr.x); y[2] += bf_lo(rr.y); y[3] += bf_hi(rr.y);
+              y[4] += bf_lo(rr.z); y[5] += bf_hi(rr.z); y[6] += bf_lo(rr.w); y[7] += bf_hi(rr.w);
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
+                make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight / parameter packing
 // ------------------------------------------------------------------------------------------------
 // w [Cout][Cin][KH][KW] fp32 -> per (N tile, k-block) swizzled [NT][64] bf16 images
@@ -287,23 +446,23 @@ __global__ void ctx_transpose_kernel(float* __restrict__ dst, const float* __res
 // ------------------------------------------------------------------------------------------------
 // HBM-bound helpers
 // ------------------------------------------------------------------------------------------------
-// image [B,34,224,224] fp32 (NCHW) -> [B,224,224,40] bf16 (NHWC, channels 34..39 zero); one block per image row
-__global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) __nv_bfloat16 tile[IMG_HW * IMG_CP];
+// image [B,34,224,224] fp32 (NCHW) -> [B,224,wp,40] bf16 (NHWC, channels 34..39 zero, pixel w stored at column w + woff,
+// the other columns zero); one block per image row
+constexpr int IMG_WP_MAX = 232;
+__global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int wp, int woff) {
+  __shared__ __align__(16) __nv_bfloat16 tile[IMG_WP_MAX * IMG_CP];
   const int b = blockIdx.x / IMG_HW, h = blockIdx.x % IMG_HW;
   const float* src = img + ((size_t)b * IMG_C * IMG_HW + h) * IMG_HW;
+  for (int i = threadIdx.x; i < wp * IMG_CP / 8; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
   for (int i = threadIdx.x; i < IMG_C * IMG_HW; i += 256) {
     const int c = i / IMG_HW, w = i - c * IMG_HW;
-    tile[w * IMG_CP + c] = __float2bfloat16_rn(src[(size_t)c * IMG_HW * IMG_HW + w]);
-  }
-  for (int i = threadIdx.x; i < (IMG_CP - IMG_C) * IMG_HW; i += 256) {
-    const int c = IMG_C + i / IMG_HW, w = i % IMG_HW;
-    tile[w * IMG_CP + c] = __float2bfloat16_rn(0.f);
+    tile[(w + woff) * IMG_CP + c] = __float2bfloat16_rn(src[(size_t)c * IMG_HW * IMG_HW + w]);
   }
   __syncthreads();
-  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * IMG_HW * IMG_CP);
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * wp * IMG_CP);
   const uint4* ts = reinterpret_cast<const uint4*>(tile);
-  for (int i = threadIdx.x; i < IMG_HW * IMG_CP / 8; i += 256) dst[i] = ts[i];
+  for (int i = threadIdx.x; i < wp * IMG_CP / 8; i += 256) dst[i] = ts[i];
 }
 
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
@@ -457,9 +616,16 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
 struct ConvLayer {
   int Cin_real, Cin, Cout, KH, KW, stride, pad, stem, panels, n_kb, NT, n_nt, stages, lag;
   uint8_t* wblob = nullptr; float* scale = nullptr; float* shift = nullptr;
+  // execution plan (fixed buffers): input / output / residual, input size, ReLU, TMA description of the input
+  const __nv_bfloat16* in = nullptr; __nv_bfloat16* out = nullptr; const __nv_bfloat16* res = nullptr;
+  int H = 0, relu = 0, use_tma = 0, lbw = 0, lbh = 0;
+  CUtensorMap tmap;
 };
 
 std::string g_ctx_create_err;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
 
@@ -467,9 +633,12 @@ struct CldContext {
   int device = 0, num_sms = 0, max_agents = 0, chunk = 0;
   std::string err;
   std::vector<void*> allocs;
-  ConvLayer conv[20];           // 0 stem; then per block conv1, conv2[, downsample] in execution order
+  ConvLayer conv[20];           // 0 stem; then per block conv1, conv2[, downsample] (state-dict order)
+  int order[20];                // execution order: conv1, downsample, conv2
+  const __nv_bfloat16* tap_buf[5] = {nullptr};
   float* head_w[30] = {nullptr};
   __nv_bfloat16 *img16 = nullptr, *stem_out = nullptr, *bufX = nullptr, *bufY = nullptr, *bufZ = nullptr, *bufD = nullptr;
+  int img_wp = IMG_HW, img_woff = 0;     // raster layout: row pitch in pixels, left padding
   bool loaded = false;
   unsigned long long launches = 0;
   double conv_flops_per_agent = 0.0;     // 2*MAC of the 20 convolutions as executed (padded K included)
@@ -526,18 +695,69 @@ void plan_conv(ConvLayer& L, int cin_real, int cout, int k, int stride, int pad,
   L.lag = L.stages / 2 > 3 ? 3 : L.stages / 2;
 }
 
-int launch_conv(CldContext* c, const ConvLayer& L, const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* res, int B,
-                int H, int W, int relu, cudaStream_t s) {
+// tensor map of a layer's input for conv_tma_kernel; returns false when the driver refuses it
+bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk, int img_wp) {
+  const int OH = (L.H + 2 * L.pad - L.KH) / L.stride + 1;
+  switch (OH) {
+    case 112: L.lbw = 4; L.lbh = 3; break;
+    case 56: L.lbw = 3; L.lbh = 3; break;
+    case 28: L.lbw = 2; L.lbh = 2; break;
+    case 14: L.lbw = 1; L.lbh = 1; break;
+    case 7: L.lbw = 0; L.lbh = 0; break;
+    default: return false;
+  }
+  const cuuint32_t bw = 1u << L.lbw, bh = 1u << L.lbh, bn = 128u >> (L.lbw + L.lbh);
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4];
+  if (L.stem) {
+    dims[0] = 320; dims[1] = 112; dims[2] = IMG_HW; dims[3] = (cuuint64_t)chunk;
+    strides[0] = 2 * IMG_CP * 2; strides[1] = (cuuint64_t)img_wp * IMG_CP * 2; strides[2] = strides[1] * IMG_HW;
+    box[0] = 64; box[1] = bw; box[2] = bh * 2; box[3] = bn;
+    es[0] = 1; es[1] = 1; es[2] = 2; es[3] = 1;
+  } else {
+    dims[0] = (cuuint64_t)L.Cin; dims[1] = (cuuint64_t)L.H; dims[2] = (cuuint64_t)L.H; dims[3] = (cuuint64_t)chunk;
+    strides[0] = (cuuint64_t)L.Cin * 2; strides[1] = strides[0] * L.H; strides[2] = strides[1] * L.H;
+    box[0] = 64; box[1] = bw * L.stride; box[2] = bh * L.stride; box[3] = bn;
+    es[0] = 1; es[1] = (cuuint32_t)L.stride; es[2] = (cuuint32_t)L.stride; es[3] = 1;
+  }
+  const CUresult r = enc(&L.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)L.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int launch_conv(CldContext* c, const ConvLayer& L, int B, cudaStream_t s) {
+  const int H = L.H, W = L.H;
+  const int OH = (H + 2 * L.pad - L.KH) / L.stride + 1, OW = OH;
+  const size_t smem = (size_t)L.stages * (CT_A_BYTES + L.NT * 128) + CT_TAIL;
+  if (L.use_tma) {
+    ConvT P;
+    P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
+    P.OH = OH; P.OW = OW; P.Cout = L.Cout; P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.nb = B; P.relu = L.relu; P.stages = L.stages;
+    P.lbw = L.lbw; P.lbh = L.lbh; P.TX = OW >> L.lbw; P.TY = OH >> L.lbh;
+    const int bn = 128 >> (L.lbw + L.lbh);
+    P.n_mt = P.TX * P.TY * ((B + bn - 1) / bn);
+    P.sx = L.stem ? 1 : L.stride; P.sy = L.stride;
+    for (int kb = 0; kb < L.n_kb; ++kb) {
+      int cbox, dxo, dyo;
+      if (L.stem) { cbox = kb % 5; dxo = 0; dyo = kb / 5 - L.pad; }
+      else { const int tap = kb / L.panels; cbox = kb % L.panels; dxo = tap % L.KW - L.pad; dyo = tap / L.KW - L.pad; }
+      P.kbt[kb] = (uint16_t)(cbox | ((dxo + 8) << 4) | ((dyo + 8) << 8));
+    }
+    const int tiles = P.n_mt * P.n_nt;
+    const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+    conv_tma_kernel<<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+    CTX_LAUNCH_OK(c, "conv_tma_kernel");
+    return 0;
+  }
   ConvP P;
-  P.in = in; P.out = out; P.res = res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
+  P.in = L.in; P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
   P.H = H; P.W = W; P.Cin = L.Cin;
-  P.OH = (H + 2 * L.pad - L.KH) / L.stride + 1; P.OW = (W + 2 * L.pad - L.KW) / L.stride + 1; P.Cout = L.Cout;
+  P.OH = OH; P.OW = OW; P.Cout = L.Cout;
   P.KW = L.KW; P.stride = L.stride; P.pad = L.pad; P.panels = L.panels;
-  P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.M = B * P.OH * P.OW; P.n_mt = (P.M + 127) / 128; P.relu = relu;
+  P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.M = B * P.OH * P.OW; P.n_mt = (P.M + 127) / 128; P.relu = L.relu;
   P.stages = L.stages; P.lag = L.lag;
   const int tiles = P.n_mt * P.n_nt;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  const size_t smem = (size_t)L.stages * (CT_A_BYTES + L.NT * 128) + CT_TAIL;
   if (L.stem) conv_tc_kernel<1><<<grid, CT_THREADS, smem, s>>>(P);
   else conv_tc_kernel<0><<<grid, CT_THREADS, smem, s>>>(P);
   CTX_LAUNCH_OK(c, "conv_tc_kernel");
@@ -550,6 +770,7 @@ extern "C" {
 
 int cld_context_create(int max_agents, CldContext** out) {
   if (!out || max_agents <= 0) return cfail(nullptr, CLD_ERR_ARG, "cld_context_create: bad arguments");
+  *out = nullptr;
   int dev = 0;
   cudaDeviceProp prop;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
@@ -559,6 +780,16 @@ int cld_context_create(int max_agents, CldContext** out) {
   c->device = dev; c->num_sms = prop.multiProcessorCount; c->max_agents = max_agents;
   const int chunk_max = env_int("CLD_CTX_CHUNK", 2048);
   c->chunk = max_agents < chunk_max ? max_agents : chunk_max;
+  const bool want_tma = env_int("CLD_CTX_GATHER", 0) == 0;
+  EncodeTiledFn enc = nullptr;
+  if (want_tma) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      enc = (EncodeTiledFn)fn;
+    if (!enc) { delete c; return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled is not available from the driver"); }
+    c->img_wp = 232; c->img_woff = 3;
+  }
   // plan: stem, then (conv1, conv2[, downsample]) per BasicBlock
   int li = 0;
   plan_conv(c->conv[li++], IMG_C, 64, 7, 2, 3, 1);
@@ -577,19 +808,65 @@ int cld_context_create(int max_agents, CldContext** out) {
   int rc = 0;
   // workspace: raster (NHWC bf16), stem output, one standing block buffer; the other three alias the raster region, which
   // is dead once the stem has run
-  if ((rc = calloc_dev(c, &c->img16, n * IMG_HW * IMG_HW * IMG_CP)) || (rc = calloc_dev(c, &c->stem_out, n * 112 * 112 * 64)) ||
+  if ((rc = calloc_dev(c, &c->img16, n * IMG_HW * IMG_WP_MAX * IMG_CP)) || (rc = calloc_dev(c, &c->stem_out, n * 112 * 112 * 64)) ||
       (rc = calloc_dev(c, &c->bufX, n * 56 * 56 * 64))) {
     g_ctx_create_err = c->err;
     for (void* q : c->allocs) cudaFree(q);
     delete c;
-    *out = nullptr;
     return rc;
   }
   c->bufY = c->img16;
   c->bufZ = c->img16 + n * 56 * 56 * 64;
   c->bufD = c->img16 + 2 * n * 56 * 56 * 64;
+  // execution plan
+  {
+    int k = 0;
+    ConvLayer& st = c->conv[0];
+    st.in = c->img16; st.out = c->stem_out; st.res = nullptr; st.H = IMG_HW; st.relu = 1;
+    c->order[k++] = 0;
+    c->tap_buf[0] = c->bufX;
+    __nv_bfloat16 *X = c->bufX, *Y = c->bufY, *Z = c->bufZ, *D = c->bufD;
+    int l1 = 1, h = 56;
+    for (int l = 0; l < 4; ++l) {
+      for (int b = 0; b < 2; ++b) {
+        const bool ds = l > 0 && b == 0;
+        const int ho = ds ? h / 2 : h;
+        ConvLayer &c1 = c->conv[l1], &c2 = c->conv[l1 + 1];
+        c1.in = X; c1.out = Y; c1.res = nullptr; c1.H = h; c1.relu = 1;
+        c->order[k++] = l1;
+        c2.res = X;
+        if (ds) {
+          ConvLayer& cd = c->conv[l1 + 2];
+          cd.in = X; cd.out = D; cd.res = nullptr; cd.H = h; cd.relu = 0;
+          c->order[k++] = l1 + 2;
+          c2.res = D;
+        }
+        c2.in = Y; c2.out = Z; c2.H = ho; c2.relu = 1;
+        c->order[k++] = l1 + 1;
+        l1 += ds ? 3 : 2;
+        __nv_bfloat16* t = X; X = Z; Z = t;
+        h = ho;
+      }
+      c->tap_buf[l + 1] = X;
+    }
+  }
+  if (want_tma) {
+    for (int i = 0; i < 20; ++i) {
+      ConvLayer& L = c->conv[i];
+      if (L.stem && env_int("CLD_CTX_STEM_GATHER", 0)) { L.use_tma = 0; continue; }
+      L.use_tma = make_tmap(enc, L, c->chunk, c->img_wp) ? 1 : 0;
+      if (!L.use_tma && !L.stem) {
+        for (void* q : c->allocs) cudaFree(q);
+        delete c;
+        return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled rejected the activation tensor of convolution %d", i);
+      }
+      if (L.use_tma) { const int sb = CT_A_BYTES + L.NT * 128; int st = (200 * 1024) / sb; L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st; }
+    }
+    if (!c->conv[0].use_tma) { c->img_wp = IMG_HW; c->img_woff = 0; }    // the gather stem reads the unpadded raster
+  }
   cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   *out = c;
   return 0;
 }
@@ -605,6 +882,13 @@ const char* cld_context_last_error(const CldContext* c) { return c ? c->err.c_st
 unsigned long long cld_context_launch_count(const CldContext* c) { return c ? c->launches : 0ull; }
 
 double cld_context_conv_flops(const CldContext* c) { return c ? c->conv_flops_per_agent : 0.0; }
+
+/* bit i set: convolution i (state-dict order, 0 = stem) gets its activations through the TMA unit */
+unsigned int cld_context_tma_mask(const CldContext* c) {
+  unsigned int m = 0;
+  if (c) for (int i = 0; i < 20; ++i) if (c->conv[i].use_tma) m |= 1u << i;
+  return m;
+}
 
 /* 130 fp32 device tensors: ContextEncoder.state_dict() order without the `num_batches_tracked` entries. */
 int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels, int n, void* stream) {
@@ -699,41 +983,31 @@ int cld_context_forward(CldContext* c, const float* image, const float* curr_sta
   int rc = 0;
   for (int b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = (B - b0) < c->chunk ? (B - b0) : c->chunk;
-    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16);
+    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16, c->img_wp, c->img_woff);
     CTX_LAUNCH_OK(c, "ctx_image_to_nhwc_kernel");
-    if ((rc = launch_conv(c, c->conv[0], c->img16, c->stem_out, nullptr, nb, IMG_HW, IMG_HW, 1, s))) return rc;
-    {
-      const long long total = (long long)nb * 56 * 56 * 8;
-      ctx_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->stem_out, c->bufX, nb, 112, 112, 64, 56, 56);
-      CTX_LAUNCH_OK(c, "ctx_maxpool_kernel");
-    }
-    auto tap = [&](int stage, const __nv_bfloat16* buf, int h, int ch) -> int {
+    auto tap = [&](int stage, int h, int ch) -> int {
       if (tap_stage != stage || !tap_out) return 0;
       const long long total = (long long)nb * h * h * ch;
-      ctx_tap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(buf, tap_out, nb, h, h, ch);
+      ctx_tap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->tap_buf[stage], tap_out, nb, h, h, ch);
       CTX_LAUNCH_OK(c, "ctx_tap_kernel");
       return 0;
     };
-    if ((rc = tap(0, c->bufX, 56, 64))) return rc;
-    __nv_bfloat16 *X = c->bufX, *Y = c->bufY, *Z = c->bufZ, *D = c->bufD;
-    int li = 1, h = 56;
-    for (int l = 0; l < 4; ++l) {
-      for (int b = 0; b < 2; ++b) {
-        const bool ds = l > 0 && b == 0;
-        const int ho = ds ? h / 2 : h;
-        if ((rc = launch_conv(c, c->conv[li], X, Y, nullptr, nb, h, h, 1, s))) return rc;
-        const __nv_bfloat16* res = X;
-        if (ds) {
-          if ((rc = launch_conv(c, c->conv[li + 2], X, D, nullptr, nb, h, h, 0, s))) return rc;
-          res = D;
-        }
-        if ((rc = launch_conv(c, c->conv[li + 1], Y, Z, res, nb, ho, ho, 1, s))) return rc;
-        li += ds ? 3 : 2;
-        __nv_bfloat16* t = X; X = Z; Z = t;
-        h = ho;
+    for (int k = 0; k < 20; ++k) {
+      const ConvLayer& L = c->conv[c->order[k]];
+      if ((rc = launch_conv(c, L, nb, s))) return rc;
+      if (k == 0) {
+        const long long total = (long long)nb * 56 * 56 * 8;
+        ctx_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->stem_out, c->bufX, nb, 112, 112, 64, 56, 56);
+        CTX_LAUNCH_OK(c, "ctx_maxpool_kernel");
+        if ((rc = tap(0, 56, 64))) return rc;
       }
-      if ((rc = tap(l + 1, X, h, 64 << l))) return rc;
+      // a layer ends after its 4th (layer1) / 5th (layer2..4) convolution
+      if (k == 4 && (rc = tap(1, 56, 64))) return rc;
+      if (k == 9 && (rc = tap(2, 28, 128))) return rc;
+      if (k == 14 && (rc = tap(3, 14, 256))) return rc;
+      if (k == 19 && (rc = tap(4, 7, 512))) return rc;
     }
+    const __nv_bfloat16* X = c->tap_buf[4];
     HeadP hp;
     hp.feat = X; hp.curr = curr_states + (size_t)b0 * 4; hp.cond = cond_feat + (size_t)b0 * 256;
     hp.map_feat = map_feat_out ? map_feat_out + (size_t)b0 * 256 : nullptr;
