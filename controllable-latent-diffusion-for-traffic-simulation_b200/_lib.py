@@ -19,7 +19,7 @@ EXPORTS = [
     "cld_decode_rollout", "cld_unicycle", "cld_indicators", "cld_guidance_step", "cld_sample",
     "cld_launch_count", "cld_profile_begin", "cld_profile_end", "cld_tc_selftest",
     "cld_context_create", "cld_context_destroy", "cld_context_last_error", "cld_context_load", "cld_context_forward",
-    "cld_context_launch_count", "cld_context_conv_flops", "cld_context_tma_mask",
+    "cld_context_launch_count", "cld_context_conv_flops",
 ]
 
 
@@ -90,9 +90,8 @@ def _load():
     lib.cld_context_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp]
     lib.cld_context_launch_count.argtypes = [vp]
     lib.cld_context_conv_flops.argtypes = [vp]
-    lib.cld_context_tma_mask.argtypes = [vp]
     special = ("cld_destroy", "cld_last_error", "cld_launch_count", "cld_context_destroy", "cld_context_last_error",
-               "cld_context_launch_count", "cld_context_conv_flops", "cld_context_tma_mask")
+               "cld_context_launch_count", "cld_context_conv_flops")
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in special:
@@ -102,7 +101,6 @@ def _load():
     lib.cld_context_last_error.restype = C.c_char_p
     lib.cld_context_launch_count.restype = C.c_ulonglong
     lib.cld_context_conv_flops.restype = C.c_double
-    lib.cld_context_tma_mask.restype = C.c_uint
     return lib
 
 

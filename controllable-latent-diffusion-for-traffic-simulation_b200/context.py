@@ -182,7 +182,3 @@ class ContextEncoder(nn.Module):
 
     def conv_flops_per_agent(self):
         return float(lib.cld_context_conv_flops(self._handle)) if self._handle is not None else 0.0
-
-    def tma_mask(self):
-        """Bit i: convolution i (0 = stem) is fed by the TMA unit (see cld_context_tma_mask)."""
-        return int(lib.cld_context_tma_mask(self._handle)) if self._handle is not None else 0

@@ -4,17 +4,18 @@
 //   agent_state_enc. : MLP 4 -> 64 -> 64 -> 64 with LayerNorm + ReLU (base_models.py:58-66)
 //   process_cond_mlp : MLP 320 -> 320 -> 320 -> 256 -> 256 -> 256 with LayerNorm + ReLU
 //
-// Every convolution is ONE kernel, `conv_tc_kernel`: an implicit GEMM on the tcgen05 tensor pipe.
-//   GEMM row m   = output pixel (b, oh, ow), 128 rows per tile; activations are NHWC bf16 so the 64 input channels of
-//                  one filter tap are 128 contiguous bytes = one row of a 128B-swizzled K-major operand tile
-//   k-block      = (filter tap, 64-channel panel); 4 producer warps gather it with 16-byte cp.async (zero-fill outside
-//                  the image), one thread per GEMM row, straight into the swizzled layout (no im2col buffer in HBM)
+// Every convolution is ONE kernel, `conv_tma_kernel`: an implicit GEMM on the tcgen05 tensor pipe, fed by the TMA unit.
+//   GEMM tile    = a BOX of 128 output pixels (bw x bh pixels of bn images); activations are NHWC bf16, so the 64 input
+//                  channels of one filter tap are 128 contiguous bytes = one row of a 128B-swizzled K-major operand tile
+//   k-block      = (filter tap, 64-channel panel) = ONE 4-D tensor-map box of the input, shifted by the tap; elements
+//                  outside the image are zero-filled by the TMA unit (= the convolution's padding); no im2col buffer
 //   weights      = pre-packed per (N tile, k-block) as swizzled [N][64] bf16 images, fetched by one bulk copy (UBLKCP)
 //   accumulators = TMEM, two buffers of up to 256 columns: the epilogue of tile i (BatchNorm scale/shift, residual add,
 //                  ReLU, bf16 NHWC store) overlaps the MMAs of tile i+1; persistent CTAs, one per SM
-// The 7x7 stem (34 input channels) uses the same kernel in STEM mode: the raster is converted once to NHWC bf16 with a
-// 40-channel pitch, so for one filter row the 7 taps x 40 channels of an output pixel are 560 CONTIGUOUS bytes; its
-// k-blocks are 5 x 64 consecutive elements of that run per filter row (K = 7 x 320 instead of 49 x 64).
+// The 7x7 stem (34 input channels) uses the same kernel: the raster is converted once to NHWC bf16 with a 36-channel
+// pitch and 3 zero pixels left of every row, so for one filter row the 7 taps x 36 channels of an output pixel are 504
+// CONTIGUOUS bytes; the TMA unit sees an OVERLAPPING view {256 elements, 112 output columns at a 144-byte stride, 224
+// rows, B} and the four 64-element boxes of a view row are the k-blocks of that filter row (K = 7 x 256, not 49 x 64).
 // Max-pool, the raster conversion and the MLP head are HBM-bound SIMT kernels.
 #include <stdarg.h>
 #include <stdlib.h>
@@ -33,29 +34,10 @@ using namespace cld::tc;
 
 namespace {
 
-constexpr int CT_THREADS = 320;        // warps 0-3 epilogue, 4-7 gather producers, 8 MMA issuer, 9 weight loader
 constexpr int CT_A_BYTES = 16384;      // 128 rows x 128 B
 constexpr int CT_MAX_STAGES = 8;
 constexpr int CT_TAIL = 4096 + 256;    // scale/bias [2][512] fp32 + barriers + TMEM slot
-constexpr int IMG_C = 34, IMG_CP = 40, IMG_HW = 224;
-
-struct ConvP {
-  const __nv_bfloat16* in; __nv_bfloat16* out; const __nv_bfloat16* res;
-  const uint8_t* wblob; const float* scale; const float* bias;
-  int H, W, Cin;            // input geometry; Cin = channel pitch in elements
-  int OH, OW, Cout;
-  int KW, stride, pad, panels;
-  int n_kb, NT, n_nt, n_mt, M, relu, stages, lag;
-};
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_lag(int lag) {
-  if (lag == 1) cp_async_wait_group<1>(); else if (lag == 2) cp_async_wait_group<2>(); else cp_async_wait_group<3>();
-}
+constexpr int IMG_C = 34, IMG_CP = 36, IMG_HW = 224, IMG_WP = 232, IMG_WOFF = 3, IMG_RUN = 256;
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -65,194 +47,14 @@ __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u <<
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // ------------------------------------------------------------------------------------------------
-// implicit-GEMM convolution + BatchNorm (+ residual) (+ ReLU)
-// ------------------------------------------------------------------------------------------------
-template <int STEM>
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvP P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int S = P.stages, NT = P.NT;
-  const uint32_t b_bytes = (uint32_t)NT * 128u, stage_bytes = CT_A_BYTES + b_bytes;
-  uint8_t* tail = smem + (size_t)S * stage_bytes;
-  float* sc_s = reinterpret_cast<float*>(tail);
-  float* bi_s = sc_s + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 4096 + 8 * (2 * CT_MAX_STAGES + 4));
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * CT_MAX_STAGES;
-  const uint32_t bar_accf = bar_empty + 8 * CT_MAX_STAGES, bar_acce = bar_accf + 16;
-  const uint32_t smem_base = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  for (int i = tid; i < P.Cout; i += CT_THREADS) { sc_s[i] = P.scale[i]; bi_s[i] = P.bias[i]; }
-  if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 129); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
-    mbar_init(bar_acce, 4); mbar_init(bar_acce + 8, 4);
-    fence_barrier_init();
-  }
-  if (warp == 8) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = P.n_mt * P.n_nt, n_kb = P.n_kb;
-
-  if (warp >= 4 && warp < 8) {
-    // ===================== gather producers: thread = GEMM row =====================
-    const int r = tid - 128;
-    const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    const int lag = P.lag;
-    int s = 0, sl = 0;              // stage being filled / stage being published (lag k-blocks behind)
-    uint32_t ph = 0;
-    long long it = 0;
-    const int ohw = P.OH * P.OW;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int mt = tile / P.n_nt;
-      const int m = mt * 128 + r;
-      const bool mv = m < P.M;
-      const int b = m / ohw, rem = m - b * ohw, oh = rem / P.OW, ow = rem - oh * P.OW;
-      const int ih0 = oh * P.stride - P.pad, iw0 = ow * P.stride - P.pad;
-      const __nv_bfloat16* base = P.in + (size_t)b * P.H * P.W * P.Cin;
-      int dy = 0, dx = 0, panel = 0;          // STEM: dy = filter row, panel = 64-element block of the 320-wide run
-      for (int kb = 0; kb < n_kb; ++kb, ++it) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        const uint32_t dst = smem_base + (uint32_t)s * stage_bytes + row_off;
-        const int ih = ih0 + dy;
-        const bool rv = mv && ih >= 0 && ih < P.H;
-        if (STEM) {
-          const __nv_bfloat16* rowp = base + ((long long)ih * P.W + iw0) * IMG_CP;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int j = panel * 8 + c, iw = iw0 + j / 5;
-            const bool v = rv && j < 35 && iw >= 0 && iw < P.W;
-            cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), v ? (const void*)(rowp + j * 8) : (const void*)P.in, v ? 16u : 0u);
-          }
-          if (++panel == 5) { panel = 0; ++dy; }
-        } else {
-          const int iw = iw0 + dx;
-          const bool v = rv && iw >= 0 && iw < P.W;
-          const __nv_bfloat16* src = v ? base + ((size_t)ih * P.W + iw) * P.Cin + panel * 64 : P.in;
-          const uint32_t nb = v ? 16u : 0u;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), src + c * 8, nb);
-          if (++panel == P.panels) { panel = 0; if (++dx == P.KW) { dx = 0; ++dy; } }
-        }
-        cp_async_commit();
-        if (it >= lag) {
-          cp_async_wait_lag(lag);
-          fence_proxy_async();
-          mbar_arrive(bar_full + 8 * sl);
-          if (++sl == S) sl = 0;
-        }
-        if (++s == S) { s = 0; ph ^= 1u; }
-      }
-    }
-    cp_async_wait_group<0>();
-    fence_proxy_async();
-    const long long pend = it < lag ? it : lag;
-    for (long long j = 0; j < pend; ++j) { mbar_arrive(bar_full + 8 * sl); if (++sl == S) sl = 0; }
-  } else if (warp == 9) {
-    // ===================== weight loader =====================
-    int s = 0; uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int nt = tile % P.n_nt;
-      const uint8_t* src = P.wblob + (size_t)nt * n_kb * b_bytes;
-      for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-          bulk_g2s(smem_base + (uint32_t)s * stage_bytes + CT_A_BYTES, src + (size_t)kb * b_bytes, b_bytes, bar_full + 8 * s);
-        }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    int s = 0; uint32_t ph = 0, ti = 0;
-    const uint32_t idesc = make_idesc_bf16(128, NT);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
-      mbar_wait(bar_acce + 8 * buf, aph ^ 1u);          // the epilogue has drained this accumulator buffer
-      tc_fence_after();
-      const uint32_t d_addr = tmem_base + buf * 256u;
-      for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint64_t ad = make_desc_sw128(a_addr, 1024), bd = make_desc_sw128(a_addr + CT_A_BYTES, 1024);
-        if (elect_one()) {
-          umma_bf16(d_addr, ad, bd, idesc, kb != 0 ? 1u : 0u);
-          umma_bf16(d_addr, ad + 2, bd + 2, idesc, 1u);
-          umma_bf16(d_addr, ad + 4, bd + 4, idesc, 1u);
-          umma_bf16(d_addr, ad + 6, bd + 6, idesc, 1u);
-          umma_commit(bar_empty + 8 * s);
-        }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
-      }
-      if (elect_one()) umma_commit(bar_accf + 8 * buf);
-      __syncwarp();
-    }
-  } else {
-    // ===================== epilogue: warp q owns TMEM lanes 32q .. 32q+31 =====================
-    const int q = warp;
-    uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
-      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
-      mbar_wait(bar_accf + 8 * buf, aph);
-      tc_fence_after();
-      const int m = mt * 128 + q * 32 + lane;
-      const bool mv = m < P.M;
-      const size_t orow = (size_t)m * P.Cout + (size_t)nt * NT;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_wait_ld();
-        if (mv) {
-          const float* sc = sc_s + nt * NT + c0;
-          const float* bi = bi_s + nt * NT + c0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[g * 8 + j]), sc[g * 8 + j], bi[g * 8 + j]);
-            if (P.res != nullptr) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(P.res + orow + c0 + g * 8);
-              y[0] += bf_lo(rr.x); y[1] += bf_hi(rr.x); y[2] += bf_lo(rr.y); y[3] += bf_hi(rr.y);
-              y[4] += bf_lo(rr.z); y[5] += bf_hi(rr.z); y[6] += bf_lo(rr.w); y[7] += bf_hi(rr.w);
-            }
-            if (P.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
-            }
-            *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
-                make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same convolution with the A operand moved by the TMA unit (cp.async.bulk.tensor, SASS UTMALDG).
+// implicit-GEMM convolution + BatchNorm (+ residual) (+ ReLU); A operand moved by the TMA unit (cp.async.bulk.tensor, SASS UTMALDG).
 // A GEMM tile is a BOX of output pixels (bw x bh pixels of bn images, bw*bh*bn = 128), so the A k-block of filter tap
 // (dy, dx) and channel panel p is ONE 4-D tensor-map box of the NHWC input: {64 channels from p*64, bw pixels from
 // ow0*s + dx - pad (traversal stride s), bh rows from oh0*s + dy - pad, bn images}; out-of-image elements are zero-filled by
 // the TMA unit (= the convolution's padding) and the box lands in the 128B-swizzled K-major layout the MMA reads.
-// Stem: the raster is stored [B,224,232,40] (3 zero pixels left, 5 right) and described to the TMA unit as an OVERLAPPING
-// view {320 elements, 112 output columns at a 160-byte stride, 224 rows, B}: row (ow) of the view is the 7-tap x 40-channel
-// run of output column ow, and its five 64-element boxes per filter row are the k-blocks.
+// Stem: the raster is stored [B,224,232,36] (3 zero pixels left, 5 right) and described to the TMA unit as an OVERLAPPING
+// view {256 elements, 112 output columns at a 144-byte stride, 224 rows, B}: row (ow) of the view is the 7-tap x 36-channel
+// run of output column ow, and its four 64-element boxes per filter row are the k-blocks.
 // One elected thread issues both copies of a stage (A box + weight image) on one mbarrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int CT2_THREADS = 192;       // warps 0-3 epilogue, 4 MMA issuer, 5 TMA producer
@@ -361,34 +163,47 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
       const bool mv = b < P.nb;
       const size_t orow = (((size_t)b * P.OH + oh) * P.OW + ow) * P.Cout + (size_t)nt * NT;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
-      mbar_wait(bar_accf + 8 * buf, aph);
-      tc_fence_after();
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_wait_ld();
-        if (mv) {
-          const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
-          const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+      const bool has_res = P.res != nullptr;
+      for (int h0 = 0; h0 < NT; h0 += 128) {
+        // the residual does not depend on the MMAs: fetch it (up to 128 channels of this row) before waiting for the accumulator
+        uint4 rr[16];
+        if (has_res && mv) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
-            float y[8];
-            y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
-            y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
-            y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
-            y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
-            if (P.res != nullptr) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(P.res + orow + c0 + g * 8);
-              y[0] += bf_lo(rr.x); y[1] += bf_hi(rr.x); y[2] += bf_lo(rr.y); y[3] += bf_hi(rr.y);
-              y[4] += bf_lo(rr.z); y[5] += bf_hi(rr.z); y[6] += bf_lo(rr.w); y[7] += bf_hi(rr.w);
-            }
-            if (P.relu) {
+          for (int j = 0; j < 16; ++j)
+            if (h0 + j * 8 < NT) rr[j] = __ldg(reinterpret_cast<const uint4*>(P.res + orow + h0 + j * 8));
+        }
+        if (h0 == 0) { mbar_wait(bar_accf + 8 * buf, aph); tc_fence_after(); }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = h0 + cc * 32;
+          if (c0 < NT) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_wait_ld();
+            if (mv) {
+              const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
+              const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
+                float y[8];
+                y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
+                y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
+                y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
+                y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
+                if (has_res) {
+                  const uint4 r4 = rr[cc * 4 + g];
+                  y[0] += bf_lo(r4.x); y[1] += bf_hi(r4.x); y[2] += bf_lo(r4.y); y[3] += bf_hi(r4.y);
+                  y[4] += bf_lo(r4.z); y[5] += bf_hi(r4.z); y[6] += bf_lo(r4.w); y[7] += bf_hi(r4.w);
+                }
+                if (P.relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
+                    make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+              }
             }
-            *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
-                make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
           }
         }
       }
@@ -418,7 +233,7 @@ __global__ void ctx_pack_conv_kernel(uint8_t* __restrict__ dst, const float* __r
   const int n = nt * NT + nr;
   float v = 0.f;
   if (stem) {
-    const int dy = kb / 5, kk = (kb % 5) * 64 + k, dxp = kk / IMG_CP, ch = kk % IMG_CP;
+    const int dy = kb / 4, kk = (kb % 4) * 64 + k, dxp = kk / IMG_CP, ch = kk % IMG_CP;
     if (dxp < KW && ch < Cin) v = w[(((size_t)n * Cin + ch) * KH + dy) * KW + dxp];
   } else {
     const int tap = kb / panels, ci = (kb % panels) * 64 + k, dy = tap / KW, dx = tap % KW;
@@ -446,23 +261,30 @@ __global__ void ctx_transpose_kernel(float* __restrict__ dst, const float* __res
 // ------------------------------------------------------------------------------------------------
 // HBM-bound helpers
 // ------------------------------------------------------------------------------------------------
-// image [B,34,224,224] fp32 (NCHW) -> [B,224,wp,40] bf16 (NHWC, channels 34..39 zero, pixel w stored at column w + woff,
-// the other columns zero); one block per image row
-constexpr int IMG_WP_MAX = 232;
-__global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int wp, int woff) {
-  __shared__ __align__(16) __nv_bfloat16 tile[IMG_WP_MAX * IMG_CP];
-  const int b = blockIdx.x / IMG_HW, h = blockIdx.x % IMG_HW;
-  const float* src = img + ((size_t)b * IMG_C * IMG_HW + h) * IMG_HW;
-  for (int i = threadIdx.x; i < wp * IMG_CP / 8; i += 256) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  for (int i = threadIdx.x; i < IMG_C * IMG_HW; i += 256) {
-    const int c = i / IMG_HW, w = i - c * IMG_HW;
-    tile[(w + woff) * IMG_CP + c] = __float2bfloat16_rn(src[(size_t)c * IMG_HW * IMG_HW + w]);
+// image [B,34,224,224] fp32 (NCHW) -> [B,224,232,36] bf16 (NHWC; channels 34,35 zero; pixel w stored at column w + 3, the other
+// columns zero); one block per image row, thread = pixel (17 independent coalesced loads of channel pairs in flight)
+__global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) uint32_t tile[IMG_WP * IMG_CP / 2];
+  const int b = blockIdx.x / IMG_HW, h = blockIdx.x % IMG_HW, w = threadIdx.x;
+  const float* src = img + ((size_t)b * IMG_C * IMG_HW + h) * IMG_HW + w;
+  constexpr size_t CS = (size_t)IMG_HW * IMG_HW;
+  for (int i = threadIdx.x; i < (IMG_WP - IMG_HW) * IMG_CP / 2; i += 256) {       // left / right padding columns
+    const int col = i / (IMG_CP / 2), k = i % (IMG_CP / 2);
+    tile[(col < IMG_WOFF ? col : col + IMG_HW) * (IMG_CP / 2) + k] = 0u;
+  }
+  if (w < IMG_HW) {
+    float v[IMG_C];
+#pragma unroll
+    for (int c = 0; c < IMG_C; ++c) v[c] = __ldg(src + c * CS);
+    uint32_t* dst = tile + (w + IMG_WOFF) * (IMG_CP / 2);
+#pragma unroll
+    for (int c = 0; c < IMG_C / 2; ++c) dst[c] = pack2(v[2 * c], v[2 * c + 1]);
+    dst[IMG_C / 2] = 0u;
   }
   __syncthreads();
-  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * wp * IMG_CP);
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * IMG_WP * IMG_CP);
   const uint4* ts = reinterpret_cast<const uint4*>(tile);
-  for (int i = threadIdx.x; i < wp * IMG_CP / 8; i += 256) dst[i] = ts[i];
+  for (int i = threadIdx.x; i < IMG_WP * IMG_CP / 8; i += 256) dst[i] = ts[i];
 }
 
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
@@ -614,11 +436,11 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
 // host side
 // ------------------------------------------------------------------------------------------------
 struct ConvLayer {
-  int Cin_real, Cin, Cout, KH, KW, stride, pad, stem, panels, n_kb, NT, n_nt, stages, lag;
+  int Cin_real, Cin, Cout, KH, KW, stride, pad, stem, panels, n_kb, NT, n_nt, stages;
   uint8_t* wblob = nullptr; float* scale = nullptr; float* shift = nullptr;
   // execution plan (fixed buffers): input / output / residual, input size, ReLU, TMA description of the input
   const __nv_bfloat16* in = nullptr; __nv_bfloat16* out = nullptr; const __nv_bfloat16* res = nullptr;
-  int H = 0, relu = 0, use_tma = 0, lbw = 0, lbh = 0;
+  int H = 0, relu = 0, lbw = 0, lbh = 0;
   CUtensorMap tmap;
 };
 
@@ -638,7 +460,6 @@ struct CldContext {
   const __nv_bfloat16* tap_buf[5] = {nullptr};
   float* head_w[30] = {nullptr};
   __nv_bfloat16 *img16 = nullptr, *stem_out = nullptr, *bufX = nullptr, *bufY = nullptr, *bufZ = nullptr, *bufD = nullptr;
-  int img_wp = IMG_HW, img_woff = 0;     // raster layout: row pitch in pixels, left padding
   bool loaded = false;
   unsigned long long launches = 0;
   double conv_flops_per_agent = 0.0;     // 2*MAC of the 20 convolutions as executed (padded K included)
@@ -684,19 +505,18 @@ int env_int(const char* name, int dflt) {
 void plan_conv(ConvLayer& L, int cin_real, int cout, int k, int stride, int pad, int stem) {
   L.Cin_real = cin_real; L.Cout = cout; L.KH = k; L.KW = k; L.stride = stride; L.pad = pad; L.stem = stem;
   L.Cin = stem ? IMG_CP : cin_real;
-  L.panels = stem ? 5 : cin_real / 64;
-  L.n_kb = stem ? k * 5 : k * k * L.panels;
+  L.panels = stem ? IMG_RUN / 64 : cin_real / 64;
+  L.n_kb = stem ? k * L.panels : k * k * L.panels;
   const int nt_max = env_int("CLD_CTX_NT", 128);
   L.NT = cout < nt_max ? cout : nt_max;
   L.n_nt = cout / L.NT;
   const int stage_bytes = CT_A_BYTES + L.NT * 128;
   int st = (200 * 1024) / stage_bytes;
   L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
-  L.lag = L.stages / 2 > 3 ? 3 : L.stages / 2;
 }
 
 // tensor map of a layer's input for conv_tma_kernel; returns false when the driver refuses it
-bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk, int img_wp) {
+bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk) {
   const int OH = (L.H + 2 * L.pad - L.KH) / L.stride + 1;
   switch (OH) {
     case 112: L.lbw = 4; L.lbh = 3; break;
@@ -710,8 +530,8 @@ bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk, int img_wp) {
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], es[4];
   if (L.stem) {
-    dims[0] = 320; dims[1] = 112; dims[2] = IMG_HW; dims[3] = (cuuint64_t)chunk;
-    strides[0] = 2 * IMG_CP * 2; strides[1] = (cuuint64_t)img_wp * IMG_CP * 2; strides[2] = strides[1] * IMG_HW;
+    dims[0] = IMG_RUN; dims[1] = 112; dims[2] = IMG_HW; dims[3] = (cuuint64_t)chunk;
+    strides[0] = 2 * IMG_CP * 2; strides[1] = (cuuint64_t)IMG_WP * IMG_CP * 2; strides[2] = strides[1] * IMG_HW;
     box[0] = 64; box[1] = bw; box[2] = bh * 2; box[3] = bn;
     es[0] = 1; es[1] = 1; es[2] = 2; es[3] = 1;
   } else {
@@ -729,38 +549,23 @@ int launch_conv(CldContext* c, const ConvLayer& L, int B, cudaStream_t s) {
   const int H = L.H, W = L.H;
   const int OH = (H + 2 * L.pad - L.KH) / L.stride + 1, OW = OH;
   const size_t smem = (size_t)L.stages * (CT_A_BYTES + L.NT * 128) + CT_TAIL;
-  if (L.use_tma) {
-    ConvT P;
-    P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
-    P.OH = OH; P.OW = OW; P.Cout = L.Cout; P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.nb = B; P.relu = L.relu; P.stages = L.stages;
-    P.lbw = L.lbw; P.lbh = L.lbh; P.TX = OW >> L.lbw; P.TY = OH >> L.lbh;
-    const int bn = 128 >> (L.lbw + L.lbh);
-    P.n_mt = P.TX * P.TY * ((B + bn - 1) / bn);
-    P.sx = L.stem ? 1 : L.stride; P.sy = L.stride;
-    for (int kb = 0; kb < L.n_kb; ++kb) {
-      int cbox, dxo, dyo;
-      if (L.stem) { cbox = kb % 5; dxo = 0; dyo = kb / 5 - L.pad; }
-      else { const int tap = kb / L.panels; cbox = kb % L.panels; dxo = tap % L.KW - L.pad; dyo = tap / L.KW - L.pad; }
-      P.kbt[kb] = (uint16_t)(cbox | ((dxo + 8) << 4) | ((dyo + 8) << 8));
-    }
-    const int tiles = P.n_mt * P.n_nt;
-    const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-    conv_tma_kernel<<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
-    CTX_LAUNCH_OK(c, "conv_tma_kernel");
-    return 0;
+  ConvT P;
+  P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
+  P.OH = OH; P.OW = OW; P.Cout = L.Cout; P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.nb = B; P.relu = L.relu; P.stages = L.stages;
+  P.lbw = L.lbw; P.lbh = L.lbh; P.TX = OW >> L.lbw; P.TY = OH >> L.lbh;
+  const int bn = 128 >> (L.lbw + L.lbh);
+  P.n_mt = P.TX * P.TY * ((B + bn - 1) / bn);
+  P.sx = L.stem ? 1 : L.stride; P.sy = L.stride;
+  for (int kb = 0; kb < L.n_kb; ++kb) {
+    int cbox, dxo, dyo;
+    if (L.stem) { cbox = kb % L.panels; dxo = 0; dyo = kb / L.panels - L.pad; }
+    else { const int tap = kb / L.panels; cbox = kb % L.panels; dxo = tap % L.KW - L.pad; dyo = tap / L.KW - L.pad; }
+    P.kbt[kb] = (uint16_t)(cbox | ((dxo + 8) << 4) | ((dyo + 8) << 8));
   }
-  ConvP P;
-  P.in = L.in; P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
-  P.H = H; P.W = W; P.Cin = L.Cin;
-  P.OH = OH; P.OW = OW; P.Cout = L.Cout;
-  P.KW = L.KW; P.stride = L.stride; P.pad = L.pad; P.panels = L.panels;
-  P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.M = B * P.OH * P.OW; P.n_mt = (P.M + 127) / 128; P.relu = L.relu;
-  P.stages = L.stages; P.lag = L.lag;
   const int tiles = P.n_mt * P.n_nt;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  if (L.stem) conv_tc_kernel<1><<<grid, CT_THREADS, smem, s>>>(P);
-  else conv_tc_kernel<0><<<grid, CT_THREADS, smem, s>>>(P);
-  CTX_LAUNCH_OK(c, "conv_tc_kernel");
+  conv_tma_kernel<<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+  CTX_LAUNCH_OK(c, "conv_tma_kernel");
   return 0;
 }
 
@@ -780,15 +585,13 @@ int cld_context_create(int max_agents, CldContext** out) {
   c->device = dev; c->num_sms = prop.multiProcessorCount; c->max_agents = max_agents;
   const int chunk_max = env_int("CLD_CTX_CHUNK", 2048);
   c->chunk = max_agents < chunk_max ? max_agents : chunk_max;
-  const bool want_tma = env_int("CLD_CTX_GATHER", 0) == 0;
   EncodeTiledFn enc = nullptr;
-  if (want_tma) {
+  {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
       enc = (EncodeTiledFn)fn;
     if (!enc) { delete c; return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled is not available from the driver"); }
-    c->img_wp = 232; c->img_woff = 3;
   }
   // plan: stem, then (conv1, conv2[, downsample]) per BasicBlock
   int li = 0;
@@ -808,7 +611,7 @@ int cld_context_create(int max_agents, CldContext** out) {
   int rc = 0;
   // workspace: raster (NHWC bf16), stem output, one standing block buffer; the other three alias the raster region, which
   // is dead once the stem has run
-  if ((rc = calloc_dev(c, &c->img16, n * IMG_HW * IMG_WP_MAX * IMG_CP)) || (rc = calloc_dev(c, &c->stem_out, n * 112 * 112 * 64)) ||
+  if ((rc = calloc_dev(c, &c->img16, n * IMG_HW * IMG_WP * IMG_CP)) || (rc = calloc_dev(c, &c->stem_out, n * 112 * 112 * 64)) ||
       (rc = calloc_dev(c, &c->bufX, n * 56 * 56 * 64))) {
     g_ctx_create_err = c->err;
     for (void* q : c->allocs) cudaFree(q);
@@ -850,22 +653,13 @@ int cld_context_create(int max_agents, CldContext** out) {
       c->tap_buf[l + 1] = X;
     }
   }
-  if (want_tma) {
-    for (int i = 0; i < 20; ++i) {
-      ConvLayer& L = c->conv[i];
-      if (L.stem && env_int("CLD_CTX_STEM_GATHER", 0)) { L.use_tma = 0; continue; }
-      L.use_tma = make_tmap(enc, L, c->chunk, c->img_wp) ? 1 : 0;
-      if (!L.use_tma && !L.stem) {
-        for (void* q : c->allocs) cudaFree(q);
-        delete c;
-        return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled rejected the activation tensor of convolution %d", i);
-      }
-      if (L.use_tma) { const int sb = CT_A_BYTES + L.NT * 128; int st = (200 * 1024) / sb; L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st; }
+  for (int i = 0; i < 20; ++i) {
+    if (!make_tmap(enc, c->conv[i], c->chunk)) {
+      for (void* q : c->allocs) cudaFree(q);
+      delete c;
+      return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled rejected the activation tensor of convolution %d", i);
     }
-    if (!c->conv[0].use_tma) { c->img_wp = IMG_HW; c->img_woff = 0; }    // the gather stem reads the unpadded raster
   }
-  cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-  cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   *out = c;
   return 0;
@@ -882,13 +676,6 @@ const char* cld_context_last_error(const CldContext* c) { return c ? c->err.c_st
 unsigned long long cld_context_launch_count(const CldContext* c) { return c ? c->launches : 0ull; }
 
 double cld_context_conv_flops(const CldContext* c) { return c ? c->conv_flops_per_agent : 0.0; }
-
-/* bit i set: convolution i (state-dict order, 0 = stem) gets its activations through the TMA unit */
-unsigned int cld_context_tma_mask(const CldContext* c) {
-  unsigned int m = 0;
-  if (c) for (int i = 0; i < 20; ++i) if (c->conv[i].use_tma) m |= 1u << i;
-  return m;
-}
 
 /* 130 fp32 device tensors: ContextEncoder.state_dict() order without the `num_batches_tracked` entries. */
 int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels, int n, void* stream) {
@@ -983,7 +770,7 @@ int cld_context_forward(CldContext* c, const float* image, const float* curr_sta
   int rc = 0;
   for (int b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = (B - b0) < c->chunk ? (B - b0) : c->chunk;
-    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16, c->img_wp, c->img_woff);
+    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16);
     CTX_LAUNCH_OK(c, "ctx_image_to_nhwc_kernel");
     auto tap = [&](int stage, int h, int ch) -> int {
       if (tap_stage != stage || !tap_out) return 0;

@@ -230,10 +230,6 @@ int cld_context_forward(CldContext* c, const float* image, const float* curr_sta
 unsigned long long cld_context_launch_count(const CldContext* c);
 /* 2*MAC per agent of the 20 convolutions as executed (includes the zero-padded K of the stem). */
 double cld_context_conv_flops(const CldContext* c);
-/* Bit i set: convolution i (state-dict order, 0 = the 7x7 stem) receives its activations through the TMA unit
- * (cp.async.bulk.tensor boxes); clear: through the cp.async gather kernel (debug switches CLD_CTX_GATHER / CLD_CTX_STEM_GATHER,
- * or a driver that rejects the stem's overlapping tensor view). */
-unsigned int cld_context_tma_mask(const CldContext* c);
 
 #ifdef __cplusplus
 }

@@ -60,9 +60,6 @@ def test_context_vs_reference_golden(gold):
     assert torch.equal(out["curr_states"].cpu(), torch.from_numpy(g["curr_states"]))
     assert r_map < 2e-2 and r < 2e-2, (r_map, r)
     assert ce.launch_count() > 0
-    print("context: TMA-fed convolutions mask 0x%05x" % ce.tma_mask())
-    if not os.environ.get("CLD_CTX_GATHER"):
-        assert ce.tma_mask() & 0xFFFFE == 0xFFFFE          # the 19 ResNet-block convolutions
 
 
 def test_context_batch_invariance_and_chunking(gold):
