@@ -4,7 +4,7 @@ Importing the configuration / synthetic-data helpers needs no GPU; anything that
 libcld_b200.so and fails loudly when it is missing or the device is not sm_100.
 """
 from .config import ConfigBase, default_algo_config, dict_to_config  # noqa: F401
-from .synthetic import make_scenes  # noqa: F401
+from .synthetic import make_context_batch, make_scenes  # noqa: F401
 
 
 def __getattr__(name):
@@ -18,6 +18,9 @@ def __getattr__(name):
     if name in ("Engine", "default_guidance", "DECODER_KEYS"):
         from . import engine
         return getattr(engine, name)
+    if name == "ContextEncoder":
+        from . import context
+        return context.ContextEncoder
     if name in ("failure_rate_compute", "compute_reward", "indicators"):
         from . import critic
         return getattr(critic, name)

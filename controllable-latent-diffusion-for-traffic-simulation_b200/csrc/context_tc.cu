@@ -18,6 +18,7 @@
 // rows, B} and the four 64-element boxes of a view row are the k-blocks of that filter row (K = 7 x 256, not 49 x 64).
 // Max-pool, the raster conversion and the MLP head are HBM-bound SIMT kernels.
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -58,14 +59,23 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // One elected thread issues both copies of a stage (A box + weight image) on one mbarrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int CT2_THREADS = 192;       // warps 0-3 epilogue, 4 MMA issuer, 5 TMA producer
+// A pipeline STAGE holds one activation box and the weight images of up to 4 filter taps that read it:
+//   * plain stage (E = 1): the box is the 128-pixel tile shifted by one tap;
+//   * grouped stage (3x3 stride-1 convolutions with tall tiles, and the stem): the box carries E-1 extra pixel rows
+//     ("slices": bw pixels x bn images = slice_bytes), and filter row e of the group reads the SAME shared-memory box
+//     through a descriptor that starts e slices further down -- the tensor map orders the box {channels, x, image, y} so
+//     that a y step is one slice for every image of the tile.  L2 -> SM traffic per tile drops by E*bh/(bh+E-1).
+//   * MT > 1 (stem): the CTA tile is MT m-tiles stacked in y (box rows MT*bh + E-1), every weight image feeds MT MMAs.
 struct ConvT {
   __nv_bfloat16* out; const __nv_bfloat16* res;
   const uint8_t* wblob; const float* scale; const float* bias;
   int OH, OW, Cout, n_kb, NT, n_nt, n_mt, nb, relu, stages;
   int sx, sy, lbw, lbh, TX, TY;
-  uint16_t kbt[80];         // per k-block: [0,4) channel box index | [4,8) dx - pad + 8 | [8,12) dy - pad + 8
+  int n_st, MT, a_bytes, slice_bytes, w_slots;     // stages per tile, m-tiles per CTA tile, A box bytes, weight images reserved per stage
+  uint16_t stt[80];         // per stage: [0,4) channel box | [4,8) dx + 8 | [8,12) dy of sub-block 0 + 8 | [12,15) sub-blocks E
 };
 
+// operand order of the tensor maps: {channel run, x, image, y}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
@@ -74,8 +84,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
 __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvT P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int S = P.stages, NT = P.NT;
-  const uint32_t b_bytes = (uint32_t)NT * 128u, stage_bytes = CT_A_BYTES + b_bytes;
+  const int S = P.stages, NT = P.NT, MT = P.MT;
+  const uint32_t b_bytes = (uint32_t)NT * 128u, a_bytes = (uint32_t)P.a_bytes, stage_bytes = a_bytes + (uint32_t)P.w_slots * b_bytes;
   uint8_t* tail = smem + (size_t)S * stage_bytes;
   float* sc_s = reinterpret_cast<float*>(tail);
   float* bi_s = sc_s + 512;
@@ -98,27 +108,29 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = P.n_mt * P.n_nt, n_kb = P.n_kb;
+  const int n_tiles = P.n_mt * P.n_nt, n_st = P.n_st;
   const int bw = 1 << P.lbw, bh = 1 << P.lbh, bn = 128 >> (P.lbw + P.lbh);
 
   if (warp == 5) {
-    // ===================== TMA producer: activations box + weight image per stage =====================
+    // ===================== TMA producer: activation box + weight images per stage =====================
     int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
       const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
-      const int cx0 = tx * bw * P.sx, cy0 = ty * bh * P.sy, cb0 = tb * bn;
-      const uint8_t* wsrc = P.wblob + (size_t)nt * n_kb * b_bytes;
-      for (int kb = 0; kb < n_kb; ++kb) {
+      const int cx0 = tx * bw * P.sx, cy0 = ty * bh * MT * P.sy, cb0 = tb * bn;
+      const uint8_t* wsrc = P.wblob + (size_t)nt * P.n_kb * b_bytes;
+      for (int st = 0; st < n_st; ++st) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const uint32_t e = P.stt[st];
+        const uint32_t w_bytes = ((e >> 12) & 7u) * b_bytes;
         if (elect_one()) {
-          const uint32_t e = P.kbt[kb];
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-          mbar_arrive_expect_tx(bar_full + 8 * s, CT_A_BYTES + b_bytes);
-          tma_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx0 + (int)((e >> 4) & 15u) - 8, cy0 + (int)((e >> 8) & 15u) - 8, cb0, bar_full + 8 * s);
-          bulk_g2s(dst + CT_A_BYTES, wsrc + (size_t)kb * b_bytes, b_bytes, bar_full + 8 * s);
+          mbar_arrive_expect_tx(bar_full + 8 * s, a_bytes + w_bytes);
+          tma_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx0 + (int)((e >> 4) & 15u) - 8, cb0, cy0 + (int)((e >> 8) & 15u) - 8, bar_full + 8 * s);
+          bulk_g2s(dst + a_bytes, wsrc, w_bytes, bar_full + 8 * s);
         }
         __syncwarp();
+        wsrc += w_bytes;
         if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
@@ -126,21 +138,30 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
     // ===================== MMA issuer =====================
     int s = 0; uint32_t ph = 0, ti = 0;
     const uint32_t idesc = make_idesc_bf16(128, NT);
+    const uint32_t slice16 = (uint32_t)P.slice_bytes >> 4, mt16 = slice16 * (uint32_t)bh;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(bar_acce + 8 * buf, aph ^ 1u);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + buf * 256u;
-      for (int kb = 0; kb < n_kb; ++kb) {
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t E = (P.stt[st] >> 12) & 7u;
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint64_t ad = make_desc_sw128(a_addr, 1024), bd = make_desc_sw128(a_addr + CT_A_BYTES, 1024);
+        const uint64_t ad0 = make_desc_sw128(a_addr, 1024), bd0 = make_desc_sw128(a_addr + a_bytes, 1024);
         if (elect_one()) {
-          umma_bf16(d_addr, ad, bd, idesc, kb != 0 ? 1u : 0u);
-          umma_bf16(d_addr, ad + 2, bd + 2, idesc, 1u);
-          umma_bf16(d_addr, ad + 4, bd + 4, idesc, 1u);
-          umma_bf16(d_addr, ad + 6, bd + 6, idesc, 1u);
+          for (uint32_t e = 0; e < E; ++e) {
+            const uint64_t bd = bd0 + (uint64_t)(e * (b_bytes >> 4));
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t ad = ad0 + (uint64_t)(e * slice16 + (uint32_t)m * mt16);
+              const uint32_t d = d_addr + (uint32_t)(m * NT);
+              umma_bf16(d, ad, bd, idesc, (st | (int)e) != 0 ? 1u : 0u);
+              umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+              umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+              umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+            }
+          }
           umma_commit(bar_empty + 8 * s);
         }
         __syncwarp();
@@ -154,54 +175,58 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
     const int q = warp;
     uint32_t ti = 0;
     const int r = q * 32 + lane;
-    const int wi = r & (bw - 1), hi = (r >> P.lbw) & (bh - 1), bi = r >> (P.lbw + P.lbh);
+    // box order {x, image, y}: row r = (hi * bn + bi) * bw + wi
+    const int wi = r & (bw - 1), bi = (r >> P.lbw) & (bn - 1), hi = r >> (7 - P.lbh);
+    const bool has_res = P.res != nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
       const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
       const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
-      const int b = tb * bn + bi, oh = ty * bh + hi, ow = tx * bw + wi;
+      const int b = tb * bn + bi, ow = tx * bw + wi;
       const bool mv = b < P.nb;
-      const size_t orow = (((size_t)b * P.OH + oh) * P.OW + ow) * P.Cout + (size_t)nt * NT;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
-      const bool has_res = P.res != nullptr;
-      for (int h0 = 0; h0 < NT; h0 += 128) {
-        // the residual does not depend on the MMAs: fetch it (up to 128 channels of this row) before waiting for the accumulator
-        uint4 rr[16];
-        if (has_res && mv) {
+      for (int m = 0; m < MT; ++m) {
+        const int oh = (ty * MT + m) * bh + hi;
+        const size_t orow = (((size_t)b * P.OH + oh) * P.OW + ow) * P.Cout + (size_t)nt * NT;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)(m * NT);
+        for (int h0 = 0; h0 < NT; h0 += 128) {
+          // the residual does not depend on the MMAs: fetch it (up to 128 channels of this row) before waiting for the accumulator
+          uint4 rr[16];
+          if (has_res && mv) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (h0 + j * 8 < NT) rr[j] = __ldg(reinterpret_cast<const uint4*>(P.res + orow + h0 + j * 8));
-        }
-        if (h0 == 0) { mbar_wait(bar_accf + 8 * buf, aph); tc_fence_after(); }
+            for (int j = 0; j < 16; ++j)
+              if (h0 + j * 8 < NT) rr[j] = __ldg(reinterpret_cast<const uint4*>(P.res + orow + h0 + j * 8));
+          }
+          if (h0 == 0 && m == 0) { mbar_wait(bar_accf + 8 * buf, aph); tc_fence_after(); }
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c0 = h0 + cc * 32;
-          if (c0 < NT) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            tmem_wait_ld();
-            if (mv) {
-              const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
-              const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = h0 + cc * 32;
+            if (c0 < NT) {
+              uint32_t v[32];
+              tmem_ld32(taddr + c0, v);
+              tmem_wait_ld();
+              if (mv) {
+                const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
+                const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
-                float y[8];
-                y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
-                y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
-                y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
-                y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
-                if (has_res) {
-                  const uint4 r4 = rr[cc * 4 + g];
-                  y[0] += bf_lo(r4.x); y[1] += bf_hi(r4.x); y[2] += bf_lo(r4.y); y[3] += bf_hi(r4.y);
-                  y[4] += bf_lo(r4.z); y[5] += bf_hi(r4.z); y[6] += bf_lo(r4.w); y[7] += bf_hi(r4.w);
+                for (int g = 0; g < 4; ++g) {
+                  const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
+                  float y[8];
+                  y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
+                  y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
+                  y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
+                  y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
+                  if (has_res) {
+                    const uint4 r4 = rr[cc * 4 + g];
+                    y[0] += bf_lo(r4.x); y[1] += bf_hi(r4.x); y[2] += bf_lo(r4.y); y[3] += bf_hi(r4.y);
+                    y[4] += bf_lo(r4.z); y[5] += bf_hi(r4.z); y[6] += bf_lo(r4.w); y[7] += bf_hi(r4.w);
+                  }
+                  if (P.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+                  }
+                  *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
+                      make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
                 }
-                if (P.relu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
-                    make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
               }
             }
           }
@@ -220,9 +245,11 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // weight / parameter packing
 // ------------------------------------------------------------------------------------------------
-// w [Cout][Cin][KH][KW] fp32 -> per (N tile, k-block) swizzled [NT][64] bf16 images
+// w [Cout][Cin][KH][KW] fp32 -> per (N tile, k-block) swizzled [NT][64] bf16 images; k-block kb covers filter row
+// tap.t[kb] & 15, filter column (>> 4) & 15 and channel box >> 8 (stem: the box is 64 elements of the 7-tap x 36-channel run)
+struct KbTaps { uint16_t t[80]; };
 __global__ void ctx_pack_conv_kernel(uint8_t* __restrict__ dst, const float* __restrict__ w, int Cout, int Cin, int KH, int KW,
-                                     int NT, int n_kb, int panels, int stem, long long total) {
+                                     int NT, int n_kb, int stem, long long total, const KbTaps tap) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int k = (int)(idx & 63);
@@ -231,12 +258,13 @@ __global__ void ctx_pack_conv_kernel(uint8_t* __restrict__ dst, const float* __r
   const int kb = (int)(t % n_kb);
   const int nt = (int)(t / n_kb);
   const int n = nt * NT + nr;
+  const int dy = tap.t[kb] & 15, dx = (tap.t[kb] >> 4) & 15, box = tap.t[kb] >> 8;
   float v = 0.f;
   if (stem) {
-    const int dy = kb / 4, kk = (kb % 4) * 64 + k, dxp = kk / IMG_CP, ch = kk % IMG_CP;
+    const int kk = box * 64 + k, dxp = kk / IMG_CP, ch = kk % IMG_CP;
     if (dxp < KW && ch < Cin) v = w[(((size_t)n * Cin + ch) * KH + dy) * KW + dxp];
   } else {
-    const int tap = kb / panels, ci = (kb % panels) * 64 + k, dy = tap / KW, dx = tap % KW;
+    const int ci = box * 64 + k;
     if (ci < Cin) v = w[(((size_t)n * Cin + ci) * KH + dy) * KW + dx];
   }
   *reinterpret_cast<__nv_bfloat16*>(dst + ((size_t)nt * n_kb + kb) * NT * 128 + sw128_off(nr, k >> 3) + (k & 7) * 2) = __float2bfloat16_rn(v);
@@ -441,6 +469,9 @@ struct ConvLayer {
   // execution plan (fixed buffers): input / output / residual, input size, ReLU, TMA description of the input
   const __nv_bfloat16* in = nullptr; __nv_bfloat16* out = nullptr; const __nv_bfloat16* res = nullptr;
   int H = 0, relu = 0, lbw = 0, lbh = 0;
+  int group = 0, MT = 1, n_st = 0, a_bytes = CT_A_BYTES, slice_bytes = 0, w_slots = 1;   // stage grouping (see ConvT)
+  uint16_t stt[80];
+  KbTaps taps;
   CUtensorMap tmap;
 };
 
@@ -510,13 +541,11 @@ void plan_conv(ConvLayer& L, int cin_real, int cout, int k, int stride, int pad,
   const int nt_max = env_int("CLD_CTX_NT", 128);
   L.NT = cout < nt_max ? cout : nt_max;
   L.n_nt = cout / L.NT;
-  const int stage_bytes = CT_A_BYTES + L.NT * 128;
-  int st = (200 * 1024) / stage_bytes;
-  L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
+  L.stages = 0;
 }
 
-// tensor map of a layer's input for conv_tma_kernel; returns false when the driver refuses it
-bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk) {
+// stage plan + tensor map of a layer's input for conv_tma_kernel; returns false when the driver refuses the tensor map
+bool plan_stages(EncodeTiledFn enc, ConvLayer& L, int chunk, bool group) {
   const int OH = (L.H + 2 * L.pad - L.KH) / L.stride + 1;
   switch (OH) {
     case 112: L.lbw = 4; L.lbh = 3; break;
@@ -527,18 +556,59 @@ bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk) {
     default: return false;
   }
   const cuuint32_t bw = 1u << L.lbw, bh = 1u << L.lbh, bn = 128u >> (L.lbw + L.lbh);
+  L.slice_bytes = (int)(bw * bn * 128u);
+  // ---- stages and the weight-image order that goes with them
+  int emax = 1;
+  L.group = 0; L.MT = 1; L.n_st = 0;
+  int kb = 0;
+  auto stage = [&](int cbox, int dxo, int dy0, int E) { L.stt[L.n_st++] = (uint16_t)(cbox | ((dxo + 8) << 4) | ((dy0 + 8) << 8) | (E << 12)); };
+  if (L.stem && group) {
+    // filter rows of equal parity read the same box: (even rows 0,2,4,6 | odd rows 1,3,5) x 4 channel-run boxes
+    L.group = 1; L.MT = 2; emax = 4;
+    for (int par = 0; par < 2; ++par)
+      for (int kp = 0; kp < L.panels; ++kp) {
+        const int E = par == 0 ? 4 : 3;
+        stage(kp, 0, par - L.pad, E);
+        for (int e = 0; e < E; ++e) L.taps.t[kb++] = (uint16_t)((2 * e + par) | (kp << 8));
+      }
+  } else if (!L.stem && group && L.KH == 3 && L.stride == 1 && bh >= 4 && (bh >= 8 || env_int("CLD_CTX_GROUP", 3) & 4)) {
+    L.group = 1; emax = 3;
+    for (int dx = 0; dx < 3; ++dx)
+      for (int pn = 0; pn < L.panels; ++pn) {
+        stage(pn, dx - L.pad, -L.pad, 3);
+        for (int e = 0; e < 3; ++e) L.taps.t[kb++] = (uint16_t)(e | (dx << 4) | (pn << 8));
+      }
+  } else if (L.stem) {
+    for (int dy = 0; dy < L.KH; ++dy)
+      for (int kp = 0; kp < L.panels; ++kp) { stage(kp, 0, dy - L.pad, 1); L.taps.t[kb++] = (uint16_t)(dy | (kp << 8)); }
+  } else {
+    for (int dy = 0; dy < L.KH; ++dy)
+      for (int dx = 0; dx < L.KW; ++dx)
+        for (int pn = 0; pn < L.panels; ++pn) { stage(pn, dx - L.pad, dy - L.pad, 1); L.taps.t[kb++] = (uint16_t)(dy | (dx << 4) | (pn << 8)); }
+  }
+  if (kb != L.n_kb || L.n_st > 80) return false;
+  const int rows_y = L.MT * (int)bh + emax - 1;            // box extent in y, in output rows
+  L.a_bytes = rows_y * L.slice_bytes;
+  L.w_slots = emax;
+  const int stage_bytes = L.a_bytes + L.w_slots * L.NT * 128;
+  int st = (216 * 1024) / stage_bytes;
+  L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
+  if (L.stages < 2) return false;
+  // ---- tensor map, operand order {channel run, x, image, y}
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], es[4];
   if (L.stem) {
-    dims[0] = IMG_RUN; dims[1] = 112; dims[2] = IMG_HW; dims[3] = (cuuint64_t)chunk;
-    strides[0] = 2 * IMG_CP * 2; strides[1] = (cuuint64_t)IMG_WP * IMG_CP * 2; strides[2] = strides[1] * IMG_HW;
-    box[0] = 64; box[1] = bw; box[2] = bh * 2; box[3] = bn;
-    es[0] = 1; es[1] = 1; es[2] = 2; es[3] = 1;
+    const cuuint64_t row = (cuuint64_t)IMG_WP * IMG_CP * 2;
+    dims[0] = IMG_RUN; dims[1] = 112; dims[2] = (cuuint64_t)chunk; dims[3] = IMG_HW;
+    strides[0] = 2 * IMG_CP * 2; strides[1] = row * IMG_HW; strides[2] = row;
+    box[0] = 64; box[1] = bw; box[2] = bn; box[3] = (cuuint32_t)rows_y * 2;
+    es[0] = 1; es[1] = 1; es[2] = 1; es[3] = 2;
   } else {
-    dims[0] = (cuuint64_t)L.Cin; dims[1] = (cuuint64_t)L.H; dims[2] = (cuuint64_t)L.H; dims[3] = (cuuint64_t)chunk;
-    strides[0] = (cuuint64_t)L.Cin * 2; strides[1] = strides[0] * L.H; strides[2] = strides[1] * L.H;
-    box[0] = 64; box[1] = bw * L.stride; box[2] = bh * L.stride; box[3] = bn;
-    es[0] = 1; es[1] = (cuuint32_t)L.stride; es[2] = (cuuint32_t)L.stride; es[3] = 1;
+    const cuuint64_t px = (cuuint64_t)L.Cin * 2;
+    dims[0] = (cuuint64_t)L.Cin; dims[1] = (cuuint64_t)L.H; dims[2] = (cuuint64_t)chunk; dims[3] = (cuuint64_t)L.H;
+    strides[0] = px; strides[1] = px * L.H * L.H; strides[2] = px * L.H;
+    box[0] = 64; box[1] = bw * L.stride; box[2] = bn; box[3] = (cuuint32_t)rows_y * L.stride;
+    es[0] = 1; es[1] = (cuuint32_t)L.stride; es[2] = 1; es[3] = (cuuint32_t)L.stride;
   }
   const CUresult r = enc(&L.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)L.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -546,22 +616,17 @@ bool make_tmap(EncodeTiledFn enc, ConvLayer& L, int chunk) {
 }
 
 int launch_conv(CldContext* c, const ConvLayer& L, int B, cudaStream_t s) {
-  const int H = L.H, W = L.H;
-  const int OH = (H + 2 * L.pad - L.KH) / L.stride + 1, OW = OH;
-  const size_t smem = (size_t)L.stages * (CT_A_BYTES + L.NT * 128) + CT_TAIL;
+  const int OH = (L.H + 2 * L.pad - L.KH) / L.stride + 1, OW = OH;
+  const size_t smem = (size_t)L.stages * (L.a_bytes + L.w_slots * L.NT * 128) + CT_TAIL;
   ConvT P;
   P.out = L.out; P.res = L.res; P.wblob = L.wblob; P.scale = L.scale; P.bias = L.shift;
   P.OH = OH; P.OW = OW; P.Cout = L.Cout; P.n_kb = L.n_kb; P.NT = L.NT; P.n_nt = L.n_nt; P.nb = B; P.relu = L.relu; P.stages = L.stages;
-  P.lbw = L.lbw; P.lbh = L.lbh; P.TX = OW >> L.lbw; P.TY = OH >> L.lbh;
+  P.lbw = L.lbw; P.lbh = L.lbh; P.TX = OW >> L.lbw; P.TY = (OH >> L.lbh) / L.MT;
   const int bn = 128 >> (L.lbw + L.lbh);
   P.n_mt = P.TX * P.TY * ((B + bn - 1) / bn);
   P.sx = L.stem ? 1 : L.stride; P.sy = L.stride;
-  for (int kb = 0; kb < L.n_kb; ++kb) {
-    int cbox, dxo, dyo;
-    if (L.stem) { cbox = kb % L.panels; dxo = 0; dyo = kb / L.panels - L.pad; }
-    else { const int tap = kb / L.panels; cbox = kb % L.panels; dxo = tap % L.KW - L.pad; dyo = tap / L.KW - L.pad; }
-    P.kbt[kb] = (uint16_t)(cbox | ((dxo + 8) << 4) | ((dyo + 8) << 8));
-  }
+  P.n_st = L.n_st; P.MT = L.MT; P.a_bytes = L.a_bytes; P.slice_bytes = L.slice_bytes; P.w_slots = L.w_slots;
+  memcpy(P.stt, L.stt, sizeof(P.stt));
   const int tiles = P.n_mt * P.n_nt;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
   conv_tma_kernel<<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
@@ -653,12 +718,20 @@ int cld_context_create(int max_agents, CldContext** out) {
       c->tap_buf[l + 1] = X;
     }
   }
+  // CLD_CTX_GROUP (debug): bit 0 groups the stem's filter rows, bit 1 those of the stride-1 3x3 convolutions with 8-row tiles
+  // (layer1), bit 2 also those with 4-row tiles (layer2)
+  const int group_mask = env_int("CLD_CTX_GROUP", 3);
   for (int i = 0; i < 20; ++i) {
-    if (!make_tmap(enc, c->conv[i], c->chunk)) {
+    ConvLayer& L = c->conv[i];
+    const bool want = L.stem ? (group_mask & 1) : (group_mask & 2);
+    if (!plan_stages(enc, L, c->chunk, want) && !(want && plan_stages(enc, L, c->chunk, false))) {
       for (void* q : c->allocs) cudaFree(q);
       delete c;
       return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled rejected the activation tensor of convolution %d", i);
     }
+    if (env_int("CLD_CTX_VERBOSE", 0))
+      fprintf(stderr, "[cld_context] conv %2d: Cin %3d Cout %3d k%d s%d in %3d | NT %3d stages %d x %5.1f KB, %2d stages/tile, grouped %d, MT %d\n", i,
+              L.Cin_real, L.Cout, L.KH, L.stride, L.H, L.NT, L.stages, (L.a_bytes + L.w_slots * L.NT * 128) / 1024.0, L.n_st, L.group, L.MT);
   }
   cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   *out = c;
@@ -703,8 +776,8 @@ int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels
       if ((rc = calloc_dev(c, &L.shift, L.Cout))) return rc;
     }
     const long long total = (long long)L.n_nt * L.n_kb * L.NT * 64;
-    ctx_pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L.wblob, w, L.Cout, L.Cin_real, L.KH, L.KW, L.NT, L.n_kb, L.panels,
-                                                                        L.stem, total);
+    ctx_pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L.wblob, w, L.Cout, L.Cin_real, L.KH, L.KW, L.NT, L.n_kb, L.stem, total,
+                                                                        L.taps);
     CTX_LAUNCH_OK(c, "ctx_pack_conv_kernel");
     ctx_fold_bn_kernel<<<(L.Cout + 127) / 128, 128, 0, s>>>(L.scale, L.shift, g, b, rm, rv, L.Cout);
     CTX_LAUNCH_OK(c, "ctx_fold_bn_kernel");

@@ -1,7 +1,8 @@
 """Drop-in for the parts of the reference's VaeModel that sit on the sampling path
 (models/vae/vae_model.py, models/vae/lstm_vae.py): the LSTM decoder, the action -> state rollout and
 the (de)scaling helpers.  `lstmvae.*` parameter names match the reference so `vae.lstmvae.*`
-checkpoint keys load unchanged; the context encoder is not part of this path.
+checkpoint keys load unchanged.  `context_encoder` (models/vae/vae_model.py:48) is created when
+`modality_shapes` is given, as in the reference; `pre_vae`'s context part is `self.context_encoder(batch)`.
 """
 import numpy as np
 import torch
@@ -64,6 +65,10 @@ class VaeModel(nn.Module):
         self._dm = None
         if dm is not None:
             self.bind(dm)
+        if modality_shapes is not None:
+            # reference order (vae_model.py:28-52): lstmvae first, the context encoder last
+            from .context import ContextEncoder
+            self.context_encoder = ContextEncoder(4, algo_config, modality_shapes, None)
 
     def bind(self, dm):
         """Share the DmModel's engine (one handle per device) and hand it the decoder weights."""

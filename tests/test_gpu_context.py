@@ -97,3 +97,28 @@ def test_context_requires_cuda_module(gold):
     with pytest.raises(RuntimeError):
         ce({"image": torch.zeros(1, 34, 224, 224), "history_positions": torch.zeros(1, 31, 2),
             "history_yaws": torch.zeros(1, 31, 1), "curr_speed": torch.zeros(1)})
+
+
+def test_raster_to_trajectories_chain(gold):
+    """The reference's inference chain end to end on the device: VaeModel.context_encoder(batch) -> DmModel(batch, aux_info)
+    (guide_dm_trainer.py:85-90 with vae_model.py:84): cond_feat / curr_states produced by the context kernels feed the
+    sampler unchanged."""
+    from cld_b200 import default_algo_config, make_scenes
+    from cld_b200.dm_model import DmModel
+    from cld_b200.synthetic import make_context_batch
+    from cld_b200.vae import VaeModel
+    algo = default_algo_config()
+    torch.manual_seed(0)
+    dm = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=10, precision="bf16").cuda()
+    vae = VaeModel(algo, None, {"image": (34, 224, 224)}).cuda().bind(dm)
+    assert any(k.startswith("context_encoder.map_encoder.encoder_heads.map_model.layer4.1.bn2") for k in vae.state_dict())
+    S, A = 2, 4
+    _, batch = make_scenes(S, A, seed=9, dense=True)
+    batch.update(make_context_batch(S * A, seed=4))
+    batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    aux = vae.context_encoder(batch)
+    assert aux["cond_feat"].shape == (S * A, 256) and aux["curr_states"].shape == (S * A, 4)
+    out = dm(batch, {"cond_feat": aux["cond_feat"], "curr_states": aux["curr_states"]}, algo, want_indicators=True,
+             agents_per_scene=A, seed=5)
+    torch.cuda.synchronize()
+    assert out["traj"].shape == (S * A, 52, 6) and torch.isfinite(out["traj"]).all()
