@@ -37,7 +37,7 @@ namespace {
 
 constexpr int CT_A_BYTES = 16384;      // 128 rows x 128 B
 constexpr int CT_MAX_STAGES = 8;
-constexpr int CT_TAIL = 4096 + 256;    // scale/bias [2][512] fp32 + barriers + TMEM slot
+constexpr int CT_TAIL = 4096 + 256 + 256;    // scale/bias [2][512] fp32 + barriers + TMEM slot + stage table
 constexpr int IMG_C = 34, IMG_CP = 36, IMG_HW = 224, IMG_WP = 232, IMG_WOFF = 3, IMG_RUN = 256;
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -71,20 +71,26 @@ struct ConvT {
   const uint8_t* wblob; const float* scale; const float* bias;
   int OH, OW, Cout, n_kb, NT, n_nt, n_mt, nb, relu, stages;
   int sx, sy, lbw, lbh, TX, TY;
+  int e0, e1, e_split;                             // sub-blocks per stage: e0 for stages < e_split, e1 after (MMA issuer: no table read)
+  int yb;                                          // box operand order: 1 = {run, x, image, y} (grouped stages), 0 = {run, x, y, image}
   int n_st, MT, a_bytes, slice_bytes, w_slots;     // stages per tile, m-tiles per CTA tile, A box bytes, weight images reserved per stage
   uint16_t stt[80];         // per stage: [0,4) channel box | [4,8) dx + 8 | [8,12) dy of sub-block 0 + 8 | [12,15) sub-blocks E
 };
 
-// operand order of the tensor maps: {channel run, x, image, y}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
+// keep a loop-invariant value in a register (the kernel parameters live in the constant bank and would otherwise be re-read
+// inside the issue loop, behind the barrier wait)
+__device__ __forceinline__ uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+
+template <int EMAX, int MT>
 __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const ConvT P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int S = P.stages, NT = P.NT, MT = P.MT;
+  const int S = P.stages, NT = P.NT;
   const uint32_t b_bytes = (uint32_t)NT * 128u, a_bytes = (uint32_t)P.a_bytes, stage_bytes = a_bytes + (uint32_t)P.w_slots * b_bytes;
   uint8_t* tail = smem + (size_t)S * stage_bytes;
   float* sc_s = reinterpret_cast<float*>(tail);
@@ -96,7 +102,9 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
   const uint32_t smem_base = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  uint32_t* stt_s = reinterpret_cast<uint32_t*>(tail + 4096 + 256);      // stage table, two entries per word
   for (int i = tid; i < P.Cout; i += CT2_THREADS) { sc_s[i] = P.scale[i]; bi_s[i] = P.bias[i]; }
+  if (tid < 40) stt_s[tid] = (uint32_t)P.stt[2 * tid] | ((uint32_t)P.stt[2 * tid + 1] << 16);
   if (tid == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
@@ -120,13 +128,14 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
       const int cx0 = tx * bw * P.sx, cy0 = ty * bh * MT * P.sy, cb0 = tb * bn;
       const uint8_t* wsrc = P.wblob + (size_t)nt * P.n_kb * b_bytes;
       for (int st = 0; st < n_st; ++st) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        const uint32_t e = P.stt[st];
+        const uint32_t e = (stt_s[st >> 1] >> ((st & 1) * 16)) & 0xffffu;
         const uint32_t w_bytes = ((e >> 12) & 7u) * b_bytes;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         if (elect_one()) {
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(bar_full + 8 * s, a_bytes + w_bytes);
-          tma_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx0 + (int)((e >> 4) & 15u) - 8, cb0, cy0 + (int)((e >> 8) & 15u) - 8, bar_full + 8 * s);
+          const int cx = cx0 + (int)((e >> 4) & 15u) - 8, cy = cy0 + (int)((e >> 8) & 15u) - 8;
+          tma_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx, P.yb ? cb0 : cy, P.yb ? cy : cb0, bar_full + 8 * s);
           bulk_g2s(dst + a_bytes, wsrc, w_bytes, bar_full + 8 * s);
         }
         __syncwarp();
@@ -137,35 +146,42 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     int s = 0; uint32_t ph = 0, ti = 0;
-    const uint32_t idesc = make_idesc_bf16(128, NT);
-    const uint32_t slice16 = (uint32_t)P.slice_bytes >> 4, mt16 = slice16 * (uint32_t)bh;
+    const uint32_t idesc = pin(make_idesc_bf16(128, NT));
+    const uint32_t slice16 = pin((uint32_t)P.slice_bytes >> 4), mt16 = pin(slice16 * (uint32_t)bh);
+    const uint32_t stage16 = pin(stage_bytes >> 4), a16 = pin(a_bytes >> 4), b16 = pin(b_bytes >> 4), nt_cols = pin((uint32_t)NT);
+    const int e0 = (int)pin((uint32_t)P.e0), e1 = (int)pin((uint32_t)P.e1);
+    const int e_split = (int)pin((uint32_t)P.e_split), n_st_r = (int)pin((uint32_t)n_st), S_r = (int)pin((uint32_t)S);
+    const uint64_t desc0 = make_desc_sw128(smem_base, 1024);       // + (byte offset >> 4) selects a tile inside the CTA's shared memory
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(bar_acce + 8 * buf, aph ^ 1u);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + buf * 256u;
-      for (int st = 0; st < n_st; ++st) {
-        const uint32_t E = (P.stt[st] >> 12) & 7u;
+      for (int st = 0; st < n_st_r; ++st) {
+        const uint64_t ad0 = desc0 + (uint64_t)((uint32_t)s * stage16), bd0 = ad0 + a16;
+        const int E = EMAX == 1 ? 1 : (st < e_split ? e0 : e1);      // stem: 4 filter rows in the even group, 3 in the odd one
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-        const uint64_t ad0 = make_desc_sw128(a_addr, 1024), bd0 = make_desc_sw128(a_addr + a_bytes, 1024);
         if (elect_one()) {
-          for (uint32_t e = 0; e < E; ++e) {
-            const uint64_t bd = bd0 + (uint64_t)(e * (b_bytes >> 4));
-            for (int m = 0; m < MT; ++m) {
-              const uint64_t ad = ad0 + (uint64_t)(e * slice16 + (uint32_t)m * mt16);
-              const uint32_t d = d_addr + (uint32_t)(m * NT);
-              umma_bf16(d, ad, bd, idesc, (st | (int)e) != 0 ? 1u : 0u);
-              umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-              umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-              umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+#pragma unroll
+          for (int e = 0; e < EMAX; ++e) {
+            if (e < E) {
+              const uint64_t bd = bd0 + (uint64_t)((uint32_t)e * b16);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint64_t ad = ad0 + (uint64_t)((uint32_t)e * slice16 + (uint32_t)m * mt16);
+                const uint32_t d = d_addr + (uint32_t)m * nt_cols;
+                umma_bf16(d, ad, bd, idesc, (st | e) != 0 ? 1u : 0u);
+                umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+              }
             }
           }
           umma_commit(bar_empty + 8 * s);
         }
         __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
+        if (++s == S_r) { s = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(bar_accf + 8 * buf);
       __syncwarp();
@@ -175,8 +191,10 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
     const int q = warp;
     uint32_t ti = 0;
     const int r = q * 32 + lane;
-    // box order {x, image, y}: row r = (hi * bn + bi) * bw + wi
-    const int wi = r & (bw - 1), bi = (r >> P.lbw) & (bn - 1), hi = r >> (7 - P.lbh);
+    // box order {x, image, y}: row r = (hi * bn + bi) * bw + wi;  {x, y, image}: r = (bi * bh + hi) * bw + wi
+    const int wi = r & (bw - 1);
+    const int bi = P.yb ? (r >> P.lbw) & (bn - 1) : r >> (P.lbw + P.lbh);
+    const int hi = P.yb ? r >> (7 - P.lbh) : (r >> P.lbw) & (bh - 1);
     const bool has_res = P.res != nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int mt = tile / P.n_nt, nt = tile - mt * P.n_nt;
@@ -469,7 +487,7 @@ struct ConvLayer {
   // execution plan (fixed buffers): input / output / residual, input size, ReLU, TMA description of the input
   const __nv_bfloat16* in = nullptr; __nv_bfloat16* out = nullptr; const __nv_bfloat16* res = nullptr;
   int H = 0, relu = 0, lbw = 0, lbh = 0;
-  int group = 0, MT = 1, n_st = 0, a_bytes = CT_A_BYTES, slice_bytes = 0, w_slots = 1;   // stage grouping (see ConvT)
+  int yb = 0, group = 0, MT = 1, n_st = 0, a_bytes = CT_A_BYTES, slice_bytes = 0, w_slots = 1;   // stage grouping (see ConvT)
   uint16_t stt[80];
   KbTaps taps;
   CUtensorMap tmap;
@@ -594,21 +612,24 @@ bool plan_stages(EncodeTiledFn enc, ConvLayer& L, int chunk, bool group) {
   int st = (216 * 1024) / stage_bytes;
   L.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
   if (L.stages < 2) return false;
-  // ---- tensor map, operand order {channel run, x, image, y}
+  // ---- tensor map; grouped stages need the y extent of the box outermost ({channel run, x, image, y}), plain stages use the
+  // natural order {channel run, x, y, image}
+  L.yb = (L.group && bn > 1) || env_int("CLD_CTX_YB", 0);
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], es[4];
+  const int iy = L.yb ? 3 : 2, ib = L.yb ? 2 : 3;
   if (L.stem) {
     const cuuint64_t row = (cuuint64_t)IMG_WP * IMG_CP * 2;
-    dims[0] = IMG_RUN; dims[1] = 112; dims[2] = (cuuint64_t)chunk; dims[3] = IMG_HW;
-    strides[0] = 2 * IMG_CP * 2; strides[1] = row * IMG_HW; strides[2] = row;
-    box[0] = 64; box[1] = bw; box[2] = bn; box[3] = (cuuint32_t)rows_y * 2;
-    es[0] = 1; es[1] = 1; es[2] = 1; es[3] = 2;
+    dims[0] = IMG_RUN; dims[1] = 112; dims[ib] = (cuuint64_t)chunk; dims[iy] = IMG_HW;
+    strides[0] = 2 * IMG_CP * 2; strides[ib - 1] = row * IMG_HW; strides[iy - 1] = row;
+    box[0] = 64; box[1] = bw; box[ib] = bn; box[iy] = (cuuint32_t)rows_y * 2;
+    es[0] = 1; es[1] = 1; es[ib] = 1; es[iy] = 2;
   } else {
     const cuuint64_t px = (cuuint64_t)L.Cin * 2;
-    dims[0] = (cuuint64_t)L.Cin; dims[1] = (cuuint64_t)L.H; dims[2] = (cuuint64_t)chunk; dims[3] = (cuuint64_t)L.H;
-    strides[0] = px; strides[1] = px * L.H * L.H; strides[2] = px * L.H;
-    box[0] = 64; box[1] = bw * L.stride; box[2] = bn; box[3] = (cuuint32_t)rows_y * L.stride;
-    es[0] = 1; es[1] = (cuuint32_t)L.stride; es[2] = 1; es[3] = (cuuint32_t)L.stride;
+    dims[0] = (cuuint64_t)L.Cin; dims[1] = (cuuint64_t)L.H; dims[ib] = (cuuint64_t)chunk; dims[iy] = (cuuint64_t)L.H;
+    strides[0] = px; strides[ib - 1] = px * L.H * L.H; strides[iy - 1] = px * L.H;
+    box[0] = 64; box[1] = bw * L.stride; box[ib] = bn; box[iy] = (cuuint32_t)rows_y * L.stride;
+    es[0] = 1; es[1] = (cuuint32_t)L.stride; es[ib] = 1; es[iy] = (cuuint32_t)L.stride;
   }
   const CUresult r = enc(&L.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)L.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -625,11 +646,15 @@ int launch_conv(CldContext* c, const ConvLayer& L, int B, cudaStream_t s) {
   const int bn = 128 >> (L.lbw + L.lbh);
   P.n_mt = P.TX * P.TY * ((B + bn - 1) / bn);
   P.sx = L.stem ? 1 : L.stride; P.sy = L.stride;
-  P.n_st = L.n_st; P.MT = L.MT; P.a_bytes = L.a_bytes; P.slice_bytes = L.slice_bytes; P.w_slots = L.w_slots;
+  P.e0 = (L.stt[0] >> 12) & 7; P.e1 = (L.stt[L.n_st - 1] >> 12) & 7; P.e_split = L.n_st / 2;
+  P.yb = L.yb; P.n_st = L.n_st; P.MT = L.MT; P.a_bytes = L.a_bytes; P.slice_bytes = L.slice_bytes; P.w_slots = L.w_slots;
   memcpy(P.stt, L.stt, sizeof(P.stt));
   const int tiles = P.n_mt * P.n_nt;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  conv_tma_kernel<<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+  if (L.w_slots == 1 && L.MT == 1) conv_tma_kernel<1, 1><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+  else if (L.w_slots == 3 && L.MT == 1) conv_tma_kernel<3, 1><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+  else if (L.w_slots == 4 && L.MT == 2) conv_tma_kernel<4, 2><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
+  else return cfail(c, CLD_ERR_STATE, "launch_conv: no kernel variant for %d weight slots x %d m-tiles", L.w_slots, L.MT);
   CTX_LAUNCH_OK(c, "conv_tma_kernel");
   return 0;
 }
@@ -733,7 +758,9 @@ int cld_context_create(int max_agents, CldContext** out) {
       fprintf(stderr, "[cld_context] conv %2d: Cin %3d Cout %3d k%d s%d in %3d | NT %3d stages %d x %5.1f KB, %2d stages/tile, grouped %d, MT %d\n", i,
               L.Cin_real, L.Cout, L.KH, L.stride, L.H, L.NT, L.stages, (L.a_bytes + L.w_slots * L.NT * 128) / 1024.0, L.n_st, L.group, L.MT);
   }
-  cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(conv_tma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(conv_tma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(conv_tma_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   *out = c;
   return 0;
 }
