@@ -399,8 +399,9 @@ __device__ __forceinline__ void hd_linear(const float* in, int ldi, const float*
     float acc[HD_AG];
 #pragma unroll
     for (int a = 0; a < HD_AG; ++a) acc[a] = 0.f;
+#pragma unroll 8
     for (int k = 0; k < K; ++k) {
-      const float w = Wt[(size_t)k * N + n];
+      const float w = __ldg(Wt + (size_t)k * N + n);
 #pragma unroll
       for (int a = 0; a < HD_AG; ++a) acc[a] = fmaf(in[a * ldi + k], w, acc[a]);
     }
@@ -556,7 +557,7 @@ void plan_conv(ConvLayer& L, int cin_real, int cout, int k, int stride, int pad,
   L.Cin = stem ? IMG_CP : cin_real;
   L.panels = stem ? IMG_RUN / 64 : cin_real / 64;
   L.n_kb = stem ? k * L.panels : k * k * L.panels;
-  const int nt_max = env_int("CLD_CTX_NT", 128);
+  const int nt_max = env_int("CLD_CTX_NT", 256);
   L.NT = cout < nt_max ? cout : nt_max;
   L.n_nt = cout / L.NT;
   L.stages = 0;
@@ -589,7 +590,7 @@ bool plan_stages(EncodeTiledFn enc, ConvLayer& L, int chunk, bool group) {
         stage(kp, 0, par - L.pad, E);
         for (int e = 0; e < E; ++e) L.taps.t[kb++] = (uint16_t)((2 * e + par) | (kp << 8));
       }
-  } else if (!L.stem && group && L.KH == 3 && L.stride == 1 && bh >= 4 && (bh >= 8 || env_int("CLD_CTX_GROUP", 3) & 4)) {
+  } else if (!L.stem && group && L.KH == 3 && L.stride == 1 && bh >= 4 && (bh >= 8 || env_int("CLD_CTX_GROUP", 7) & 4)) {
     L.group = 1; emax = 3;
     for (int dx = 0; dx < 3; ++dx)
       for (int pn = 0; pn < L.panels; ++pn) {
@@ -745,7 +746,7 @@ int cld_context_create(int max_agents, CldContext** out) {
   }
   // CLD_CTX_GROUP (debug): bit 0 groups the stem's filter rows, bit 1 those of the stride-1 3x3 convolutions with 8-row tiles
   // (layer1), bit 2 also those with 4-row tiles (layer2)
-  const int group_mask = env_int("CLD_CTX_GROUP", 3);
+  const int group_mask = env_int("CLD_CTX_GROUP", 7);
   for (int i = 0; i < 20; ++i) {
     ConvLayer& L = c->conv[i];
     const bool want = L.stem ? (group_mask & 1) : (group_mask & 2);
