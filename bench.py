@@ -156,7 +156,7 @@ def run_reference(a):
     }))
 
 
-def context_encoder_rate(dev, agents=1024, iters=5, warmup=3):
+def context_encoder_rate(dev, agents=1024, iters=5, warmup=3, cpu_agents=256):
     """SURVEY.md sec. 8 row a14, measured beside the headline (NOT inside its timed region): ContextEncoder.forward
     (34 x 224 x 224 raster -> cond_feat) for `agents` agents through cld_b200.ContextEncoder / cld_context_forward, inputs resident
     in HBM, CUDA events.  Algorithmic FLOPs: 6.07 GFLOP per agent (hook-counted on the reference)."""
@@ -187,6 +187,20 @@ def context_encoder_rate(dev, agents=1024, iters=5, warmup=3):
            "achieved_tflops": tflops, "frac_of_bf16_peak": tflops / tf_peak, "peak_source": peak_src + " bf16_tflops_sustained",
            "gpu_launches": ce.launch_count() - l0, "bytes_in_per_agent": 34 * 224 * 224 * 4}
     ce.close()
+    # the reference's CPU path for the same row, timed beside it: the oracle restatement of ContextEncoder.forward (bit-equal to the
+    # real reference, oracle/make_golden.py) on a bounded sample with all host threads
+    if cpu_agents:
+        import cld_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = {k: v.detach().cpu() for k, v in ce.state_dict().items()}
+        sub = {k: v[:cpu_agents].cpu() for k, v in batch.items()}
+        with torch.no_grad():
+            O.context_encode(sd, {k: v[:2] for k, v in sub.items()})
+            t0 = time.perf_counter()
+            O.context_encode(sd, sub)
+            dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": cpu_agents / dt, "unit": "agents/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d of %d agents, 1 timed pass (%.1f s)" % (cpu_agents, agents, dt)}
     return out
 
 
@@ -329,7 +343,7 @@ def main():
         if world == 1 and not a.skip_context:
             del out, x_init, noise
             torch.cuda.empty_cache()
-            ctx = context_encoder_rate(dev)
+            ctx = context_encoder_rate(dev, cpu_agents=0 if a.skip_cpu else 256)
         print(json.dumps({
             "metric": "guided scenarios/sec (50-step DDIM)", "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

@@ -155,6 +155,10 @@ class ContextEncoder(nn.Module):
         dev = image.device
         B = image.shape[0]
         h = self._engine(B)
+        if dev != self._handle_dev:
+            raise RuntimeError("ContextEncoder: data_batch['image'] is on %s but the module is on %s" % (dev, self._handle_dev))
+        if tuple(image.shape[1:]) != (34, 224, 224):
+            raise RuntimeError("ContextEncoder: expected a [B,34,224,224] raster, got %s" % (tuple(image.shape),))
         image = image.to(torch.float32).contiguous()
         curr = self.current_states(data_batch).to(device=dev, dtype=torch.float32).contiguous()
         cond = torch.empty(B, 256, device=dev, dtype=torch.float32)

@@ -400,7 +400,7 @@ __device__ __forceinline__ void hd_linear(const float* in, int ldi, const float*
     float acc[HD_AG];
 #pragma unroll
     for (int a = 0; a < HD_AG; ++a) acc[a] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < K; k += 4) {
       const float w0 = __ldg(Wt + (size_t)k * N + n), w1 = __ldg(Wt + (size_t)(k + 1) * N + n);
       const float w2 = __ldg(Wt + (size_t)(k + 2) * N + n), w3 = __ldg(Wt + (size_t)(k + 3) * N + n);

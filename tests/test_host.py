@@ -98,3 +98,17 @@ def test_synthetic_scene_shapes():
     assert b["all_other_agents_future_positions"].shape == (15, 4, 52, 2)
     assert b["scene_index"].tolist() == [0] * 5 + [1] * 5 + [2] * 5
     assert torch.equal(b["raster_from_agent"][0], torch.tensor([[2., 0., 56.], [0., 2., 112.], [0., 0., 1.]]))
+
+
+def test_context_encoder_has_no_cpu_path():
+    """cld_b200.ContextEncoder is a parameter container + C-ABI call: on a CPU module it must raise, not fall back."""
+    import pytest
+    import torch
+    from cld_b200 import default_algo_config
+    from cld_b200.context import ContextEncoder
+    ce = ContextEncoder(4, default_algo_config(), {"image": (34, 224, 224)})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ce({"image": torch.zeros(1, 34, 224, 224), "history_positions": torch.zeros(1, 31, 2),
+            "history_yaws": torch.zeros(1, 31, 1), "curr_speed": torch.zeros(1)})
+    with pytest.raises(RuntimeError):
+        ContextEncoder(4, default_algo_config(), {"image": (3, 224, 224)})
