@@ -90,6 +90,25 @@ def test_context_batch_invariance_and_chunking(gold):
     assert torch.equal(chunked, full)
 
 
+def test_context_crosses_image_box_boundaries(gold):
+    """B = 133 agents: more than one 128-image box in layer4 (1x1x128 tiles), ragged boxes of 2 / 8 / 32 images in layers 1-3;
+    every agent still matches the oracle and its own single-agent result."""
+    import cld_oracle as O
+    from cld_b200.synthetic import make_context_batch
+    g, sd, ce = _build(gold, max_agents=133)
+    batch = make_context_batch(133, seed=17)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    full = ce(cb)["cond_feat"]
+    one = ce({k: v[130:131].contiguous() for k, v in cb.items()})["cond_feat"]
+    torch.cuda.synchronize()
+    assert torch.equal(full[130:131], one)
+    with torch.no_grad():
+        want = O.context_encode(sd, batch)["cond_feat"]
+    per_agent = ((full.cpu().double() - want.double()).norm(dim=1) / want.double().norm(dim=1)).max().item()
+    print("context B=133: worst per-agent rel(cond_feat) %.3e" % per_agent)
+    assert per_agent < 2e-2
+
+
 def test_context_requires_cuda_module(gold):
     from cld_b200 import default_algo_config
     from cld_b200.context import ContextEncoder
