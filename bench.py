@@ -204,6 +204,36 @@ def context_encoder_rate(dev, agents=1024, iters=5, warmup=3, cpu_agents=256):
     return out
 
 
+def raster_chain_rate(dev, S, A, batch_d, hot_path, algo, iters=2):
+    """The reference's inference chain in one timed region (rows a14 + a1..a13): rasters resident in HBM ->
+    ContextEncoder.forward -> DmModel.forward (guided sampler + decode + rollout + indicators), same workload as the headline."""
+    import torch
+    from cld_b200.context import ContextEncoder
+    B = S * A
+    torch.manual_seed(0)
+    ce = ContextEncoder(4, algo, {"image": (34, 224, 224)}, max_agents=B).to(dev)
+    g = torch.Generator(device=dev).manual_seed(13)
+    b2 = dict(batch_d)
+    b2["image"] = (torch.rand(B, 34, 224, 224, device=dev, generator=g) < 0.05).float()
+    b2["history_yaws"] = torch.zeros(B, 31, 1, device=dev)
+
+    def step():
+        aux2 = ce(b2)
+        return hot_path(b2, {"cond_feat": aux2["cond_feat"], "curr_states": aux2["curr_states"]})
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    ce.close()
+    del b2
+    return {"value": S / ms * 1e3, "unit": "scenarios/s", "ms_per_step": ms, "iters": iters, "raster_bytes_per_scene": A * 34 * 224 * 224 * 4}
+
+
 def workload_config(a):
     return {"workload": "cfg1: %d scenes x %d agents x %d sample, T=%d, n_timesteps=%d stride %d (50 denoising steps, %s)%s, "
                         "decode+rollout+indicators; random-init weights" % (
@@ -341,9 +371,11 @@ def main():
                        a.cpu_scenes, S, A, a.sampler, "" if a.no_guidance else " guided", dt)}
         ctx = None
         if world == 1 and not a.skip_context:
+            chain = raster_chain_rate(dev, S, A, batch_d, hot_path, algo)
             del out, x_init, noise
             torch.cuda.empty_cache()
             ctx = context_encoder_rate(dev, cpu_agents=0 if a.skip_cpu else 256)
+            ctx["raster_to_trajectories"] = chain
         print(json.dumps({
             "metric": "guided scenarios/sec (50-step DDIM)", "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
