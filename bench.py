@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--scenes", type=int, default=WORKLOAD["scenes"])
     ap.add_argument("--cpu-scenes", type=int, default=1, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-lanes", action="store_true", help="do not time the 2-lane variant after the headline")
     ap.add_argument("--skip-context", action="store_true", help="do not time the context encoder (row a14) after the headline")
     return ap.parse_args()
 
@@ -369,6 +370,32 @@ def main():
             cpu = {"value": rate, "unit": "scenarios/s", "cores": cores, "kind": "port",
                    "sample": "%d of %d scenes x %d agents, same 50-step %s%s sampler + decode + indicators, 1 timed pass (%.1f s)" % (
                        a.cpu_scenes, S, A, a.sampler, "" if a.no_guidance else " guided", dt)}
+        lanes = None
+        if world == 1 and not a.skip_lanes:
+            # informational: the same workload with DmModel(lanes=2) -- whole-scene half batches on two engines / CUDA streams fill the
+            # SMs that the denoiser's last wave and the 128-CTA decoder kernels leave idle.  Not the headline: concurrent lanes blur the
+            # per-launch timing the roofline is quoted on.
+            torch.manual_seed(0)
+            dm2 = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=WORKLOAD["n_timesteps"], precision=a.precision, max_rows=R,
+                          lanes=2).to(dev)
+            dm2.stride = WORKLOAD["stride"]
+            VaeModel(algo).bind(dm2)
+
+            def lane_step():
+                return dm2(batch_d, aux_d, algo, x_init=x_init, noise=noise, sampler=a.sampler, guidance=guidance, want_indicators=True,
+                           agents_per_scene=A)
+            for _ in range(2):
+                lane_step()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(a.steps):
+                lane_step()
+            f1.record()
+            torch.cuda.synchronize()
+            lms = f0.elapsed_time(f1) / a.steps
+            lanes = {"lanes": 2, "value": S / lms * 1e3, "unit": "scenarios/s", "ms_per_step": lms}
+            del dm2
         ctx = None
         if world == 1 and not a.skip_context:
             chain = raster_chain_rate(dev, S, A, batch_d, hot_path, algo)
@@ -383,7 +410,7 @@ def main():
             "row_steps_per_s": value * A * N * K_d, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scenarios/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te.item()},
-            "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx,
+            "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx, "lanes": lanes,
         }))
     if world > 1:
         dist.destroy_process_group()
