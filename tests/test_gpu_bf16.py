@@ -266,3 +266,26 @@ def test_bf16_mode_rejects_unsupported_horizon():
     from cld_b200.engine import Engine
     with pytest.raises(RuntimeError, match="bf16 tensor-core path"):
         Engine(horizon=104, precision="bf16", max_rows=8)
+
+
+def test_lanes_give_the_single_engine_result(models_cpu):
+    """DmModel(lanes=2): whole-scene half batches on two engines / CUDA streams.  Scenes never interact and every kernel is
+    row-wise deterministic, so the result must equal the single-engine one bit for bit (supplied noise, guided DDPM)."""
+    from cld_b200.engine import default_guidance
+    S, A = 6, 8
+    aux, batch = make_scenes(S, A, seed=31, dense=True)
+    torch.manual_seed(32)
+    R = S * A
+    x_init, noises = torch.randn(R, 52, 4).cuda(), torch.randn(10, R, 52, 4).cuda()
+    bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    ad = {k: v.cuda() for k, v in aux.items()}
+    outs = []
+    for lanes in (1, 2, 3):
+        dm, vae, algo = models_cpu(10, precision="bf16", lanes=lanes)
+        dm = dm.cuda()
+        vae.bind(dm)
+        outs.append(dm(bd, ad, algo, noise=noises, x_init=x_init, guidance=default_guidance(), want_indicators=True, agents_per_scene=A))
+        torch.cuda.synchronize()
+    for o in outs[1:]:
+        for k in ("pred_traj", "traj", "offroad", "coll"):
+            assert torch.equal(outs[0][k], o[k]), k
