@@ -18,7 +18,7 @@ EXPORTS = [
     "cld_set_schedule", "cld_unet_forward", "cld_unet_debug_stage", "cld_posterior_step", "cld_add_noise",
     "cld_decode_rollout", "cld_unicycle", "cld_indicators", "cld_guidance_step", "cld_sample",
     "cld_launch_count", "cld_profile_begin", "cld_profile_end", "cld_tc_selftest",
-    "cld_context_create", "cld_context_destroy", "cld_context_last_error", "cld_context_load", "cld_context_forward",
+    "cld_context_create", "cld_context_destroy", "cld_context_last_error", "cld_context_load", "cld_context_forward", "cld_context_forward_history",
     "cld_context_launch_count", "cld_context_conv_flops",
 ]
 
@@ -88,6 +88,7 @@ def _load():
     lib.cld_context_last_error.argtypes = [vp]
     lib.cld_context_load.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), i32, vp]
     lib.cld_context_forward.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp]
+    lib.cld_context_forward_history.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.cld_context_launch_count.argtypes = [vp]
     lib.cld_context_conv_flops.argtypes = [vp]
     special = ("cld_destroy", "cld_last_error", "cld_launch_count", "cld_context_destroy", "cld_context_last_error",

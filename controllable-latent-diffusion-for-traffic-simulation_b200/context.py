@@ -181,6 +181,52 @@ class ContextEncoder(nn.Module):
             out["tap"] = tap
         return out
 
+    def _history_args(self, maps, agent_hist_pos, agent_hist_mask, raster_from_agent):
+        dev = maps.device
+        B, A, T = agent_hist_pos.shape[:3]
+        if tuple(maps.shape) != (B, 3, 224, 224) or T != 31 or tuple(agent_hist_mask.shape) != (B, A, T):
+            raise RuntimeError("history rasteriser: expected maps [B,3,224,224], positions [B,A,31,2], mask [B,A,31]; got %s %s %s"
+                               % (tuple(maps.shape), tuple(agent_hist_pos.shape), tuple(agent_hist_mask.shape)))
+        return (maps.to(torch.float32).contiguous(), agent_hist_pos.to(device=dev, dtype=torch.float32).contiguous(),
+                agent_hist_mask.to(device=dev).to(torch.uint8).contiguous(),
+                raster_from_agent.to(device=dev, dtype=torch.float32).contiguous(), B, A)
+
+    @torch.no_grad()
+    def rasterize_agents(self, maps, agent_hist_pos, agent_hist_yaw, agent_mask, raster_from_agent, map_res=None):
+        """Drop-in for tbsim.utils.trajdata_utils.rasterize_agents (src/tbsim/utils/trajdata_utils.py:123-156): returns the
+        [B,34,224,224] fp32 image (`agent_hist_yaw` / `map_res` are unused there as well)."""
+        self._engine(maps.shape[0])
+        m, p, k, r, B, A = self._history_args(maps, agent_hist_pos, agent_mask, raster_from_agent)
+        img = torch.empty(B, 34, 224, 224, device=m.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(m.device).cuda_stream
+        rc = lib.cld_context_forward_history(self._handle, C.c_void_p(m.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(k.data_ptr()),
+                                             C.c_void_p(r.data_ptr()), A, None, B, None, None, C.c_void_p(img.data_ptr()), C.c_void_p(stream))
+        if rc != 0:
+            self._err("cld_context_forward_history")
+        return img
+
+    @torch.no_grad()
+    def forward_history(self, data_batch, maps, agent_hist_pos, agent_hist_mask, *, want_image=False):
+        """ContextEncoder.forward with the rasterisation fused in: `maps` [B,3,224,224] map layers, `agent_hist_pos` [B,A,31,2]
+        (ego first) and `agent_hist_mask` [B,A,31] are what parse_node_centric hands to rasterize_agents
+        (trajdata_utils.py:395-420); `data_batch` supplies raster_from_agent, history_positions / history_yaws / curr_speed."""
+        self._engine(maps.shape[0])
+        m, p, k, r, B, A = self._history_args(maps, agent_hist_pos, agent_hist_mask, data_batch["raster_from_agent"])
+        dev = m.device
+        curr = self.current_states(data_batch).to(device=dev, dtype=torch.float32).contiguous()
+        cond = torch.empty(B, 256, device=dev, dtype=torch.float32)
+        img = torch.empty(B, 34, 224, 224, device=dev, dtype=torch.float32) if want_image else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.cld_context_forward_history(self._handle, C.c_void_p(m.data_ptr()), C.c_void_p(p.data_ptr()), C.c_void_p(k.data_ptr()),
+                                             C.c_void_p(r.data_ptr()), A, C.c_void_p(curr.data_ptr()), B, C.c_void_p(cond.data_ptr()), None,
+                                             C.c_void_p(img.data_ptr()) if img is not None else None, C.c_void_p(stream))
+        if rc != 0:
+            self._err("cld_context_forward_history")
+        out = {"cond_feat": cond, "curr_states": curr}
+        if img is not None:
+            out["image"] = img
+        return out
+
     def launch_count(self):
         return int(lib.cld_context_launch_count(self._handle)) if self._handle is not None else 0
 

@@ -333,6 +333,61 @@ __global__ void __launch_bounds__(256) ctx_image_to_nhwc_kernel(const float* __r
   for (int i = threadIdx.x; i < IMG_WP * IMG_CP / 8; i += 256) dst[i] = ts[i];
 }
 
+// History rasterisation fused with the raster layout (rasterize_agents, reference src/tbsim/utils/trajdata_utils.py:123-156):
+// pass 1 writes the map layers into channels 31..33 and zeros everywhere else, one block per image row
+__global__ void __launch_bounds__(256) ctx_raster_base_kernel(const float* __restrict__ maps, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) uint32_t tile[IMG_WP * IMG_CP / 2];
+  const int b = blockIdx.x / IMG_HW, h = blockIdx.x % IMG_HW, w = threadIdx.x;
+  for (int i = threadIdx.x; i < IMG_WP * IMG_CP / 2; i += 256) tile[i] = 0u;
+  __syncthreads();
+  if (w < IMG_HW) {
+    constexpr size_t CS = (size_t)IMG_HW * IMG_HW;
+    const float* src = maps + ((size_t)b * 3 * IMG_HW + h) * IMG_HW + w;
+    const float m0 = __ldg(src), m1 = __ldg(src + CS), m2 = __ldg(src + 2 * CS);
+    uint32_t* dst = tile + (w + IMG_WOFF) * (IMG_CP / 2);
+    dst[15] = pack2(0.f, m0);            // channels 30 (last history frame, scattered later), 31
+    dst[16] = pack2(m1, m2);             // channels 32, 33
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * IMG_HW + h) * IMG_WP * IMG_CP);
+  const uint4* ts = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < IMG_WP * IMG_CP / 8; i += 256) dst[i] = ts[i];
+}
+// pass 2 (others, value -1) and pass 3 (ego = agent 0, value +1, launched after so that it wins): one thread per
+// (image, agent, history frame); pixel = round(clip(raster_from_agent * p)); the first and the last pixel of the raster are
+// never written (trajdata_utils.py:148-149: they collect the unavailable / out-of-range positions)
+__global__ void ctx_raster_scatter_kernel(const float* __restrict__ pos, const uint8_t* __restrict__ mask, const float* __restrict__ rfa,
+                                          __nv_bfloat16* __restrict__ out, int nb, int A, int T, int ego) {
+  const int na = ego ? 1 : A - 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * na * T) return;
+  const int t = idx % T, a = (idx / T) % na + (ego ? 0 : 1), b = idx / (T * na);
+  const size_t pi = ((size_t)b * A + a) * T + t;
+  float x = 0.f, y = 0.f;
+  if (mask[pi]) {
+    const float px = pos[pi * 2], py = pos[pi * 2 + 1];
+    const float* M = rfa + (size_t)b * 9;
+    x = __fadd_rn(__fadd_rn(__fmul_rn(px, M[0]), __fmul_rn(py, M[1])), M[2]);
+    y = __fadd_rn(__fadd_rn(__fmul_rn(px, M[3]), __fmul_rn(py, M[4])), M[5]);
+  }
+  const int ix = (int)rintf(fminf(fmaxf(x, 0.f), (float)(IMG_HW - 1))), iy = (int)rintf(fminf(fmaxf(y, 0.f), (float)(IMG_HW - 1)));
+  const int flat = iy * IMG_HW + ix;
+  if (flat == 0 || flat == IMG_HW * IMG_HW - 1) return;
+  out[(((size_t)b * IMG_HW + iy) * IMG_WP + ix + IMG_WOFF) * IMG_CP + t] = __float2bfloat16_rn(ego ? 1.f : -1.f);
+}
+// the workspace raster back as the reference's image [B,34,224,224] fp32
+__global__ void ctx_raster_export_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int nb) {
+  const long long total = (long long)nb * IMG_C * IMG_HW * IMG_HW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = (int)(idx % IMG_HW);
+  long long t = idx / IMG_HW;
+  const int h = (int)(t % IMG_HW); t /= IMG_HW;
+  const int c = (int)(t % IMG_C);
+  const int b = (int)(t / IMG_C);
+  out[idx] = __bfloat162float(in[(((size_t)b * IMG_HW + h) * IMG_WP + w + IMG_WOFF) * IMG_CP + c]);
+}
+
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
@@ -863,21 +918,45 @@ int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels
   return 0;
 }
 
-/* cond_feat = ContextEncoder.forward(data_batch)['cond_feat']  (models/context_utils.py:40-61).
- * image [B,34,224,224] fp32, curr_states [B,4] fp32 (x, y, vel, yaw: batch_utils.get_current_states) -> cond_feat [B,256].
- * map_feat_out (optional) [B,256] = the ResNet's fc output.  tap_stage >= 0 (debug, B <= chunk): copies the activation after
- * stage 0 (stem + max-pool), 1..4 (layer1..layer4) to tap_out as fp32 NCHW. */
-int cld_context_forward(CldContext* c, const float* image, const float* curr_states, int B, float* cond_feat, float* map_feat_out,
-                        int tap_stage, float* tap_out, void* stream) {
-  if (!c || !image || !curr_states || !cond_feat || B <= 0) return c ? cfail(c, CLD_ERR_ARG, "cld_context_forward: bad arguments") : CLD_ERR_ARG;
-  if (!c->loaded) return cfail(c, CLD_ERR_STATE, "cld_context_forward: weights not loaded");
-  if (tap_stage >= 0 && B > c->chunk) return cfail(c, CLD_ERR_ARG, "cld_context_forward: taps need B <= %d", c->chunk);
-  cudaStream_t s = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace {
+struct RasterSrc {           // exactly one of the two sources is set
+  const float* image = nullptr;                                      // [B,34,224,224] fp32
+  const float* maps = nullptr; const float* hist_pos = nullptr; const uint8_t* hist_mask = nullptr; const float* rfa = nullptr;
+  int A = 0;                                                          // agents per history (ego first)
+  float* image_out = nullptr;                                         // optional export of the rasterised image
+};
+
+int forward_impl(CldContext* c, const RasterSrc& src, const float* curr_states, int B, float* cond_feat, float* map_feat_out, int tap_stage,
+                 float* tap_out, cudaStream_t s) {
   int rc = 0;
+  constexpr int T = IMG_C - 3;
   for (int b0 = 0; b0 < B; b0 += c->chunk) {
     const int nb = (B - b0) < c->chunk ? (B - b0) : c->chunk;
-    ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16);
-    CTX_LAUNCH_OK(c, "ctx_image_to_nhwc_kernel");
+    if (src.image) {
+      ctx_image_to_nhwc_kernel<<<nb * IMG_HW, 256, 0, s>>>(src.image + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, c->img16);
+      CTX_LAUNCH_OK(c, "ctx_image_to_nhwc_kernel");
+    } else {
+      ctx_raster_base_kernel<<<nb * IMG_HW, 256, 0, s>>>(src.maps + (size_t)b0 * 3 * IMG_HW * IMG_HW, c->img16);
+      CTX_LAUNCH_OK(c, "ctx_raster_base_kernel");
+      const float* pos = src.hist_pos + (size_t)b0 * src.A * T * 2;
+      const uint8_t* msk = src.hist_mask + (size_t)b0 * src.A * T;
+      const float* rfa = src.rfa + (size_t)b0 * 9;
+      if (src.A > 1) {
+        const int n = nb * (src.A - 1) * T;
+        ctx_raster_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pos, msk, rfa, c->img16, nb, src.A, T, 0);
+        CTX_LAUNCH_OK(c, "ctx_raster_scatter_kernel");
+      }
+      ctx_raster_scatter_kernel<<<(nb * T + 255) / 256, 256, 0, s>>>(pos, msk, rfa, c->img16, nb, src.A, T, 1);
+      CTX_LAUNCH_OK(c, "ctx_raster_scatter_kernel");
+      if (src.image_out) {
+        const long long total = (long long)nb * IMG_C * IMG_HW * IMG_HW;
+        ctx_raster_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->img16, src.image_out + (size_t)b0 * IMG_C * IMG_HW * IMG_HW, nb);
+        CTX_LAUNCH_OK(c, "ctx_raster_export_kernel");
+      }
+      if (!cond_feat) continue;            // rasterisation only
+    }
     auto tap = [&](int stage, int h, int ch) -> int {
       if (tap_stage != stage || !tap_out) return 0;
       const long long total = (long long)nb * h * h * ch;
@@ -915,6 +994,40 @@ int cld_context_forward(CldContext* c, const float* image, const float* curr_sta
     CTX_LAUNCH_OK(c, "ctx_head_kernel");
   }
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+/* cond_feat = ContextEncoder.forward(data_batch)['cond_feat']  (models/context_utils.py:40-61).
+ * image [B,34,224,224] fp32, curr_states [B,4] fp32 (x, y, vel, yaw: batch_utils.get_current_states) -> cond_feat [B,256].
+ * map_feat_out (optional) [B,256] = the ResNet's fc output.  tap_stage >= 0 (debug, B <= chunk): copies the activation after
+ * stage 0 (stem + max-pool), 1..4 (layer1..layer4) to tap_out as fp32 NCHW. */
+int cld_context_forward(CldContext* c, const float* image, const float* curr_states, int B, float* cond_feat, float* map_feat_out,
+                        int tap_stage, float* tap_out, void* stream) {
+  if (!c || !image || !curr_states || !cond_feat || B <= 0) return c ? cfail(c, CLD_ERR_ARG, "cld_context_forward: bad arguments") : CLD_ERR_ARG;
+  if (!c->loaded) return cfail(c, CLD_ERR_STATE, "cld_context_forward: weights not loaded");
+  if (tap_stage >= 0 && B > c->chunk) return cfail(c, CLD_ERR_ARG, "cld_context_forward: taps need B <= %d", c->chunk);
+  RasterSrc src;
+  src.image = image;
+  return forward_impl(c, src, curr_states, B, cond_feat, map_feat_out, tap_stage, tap_out, (cudaStream_t)stream);
+}
+
+/* The same from the un-rasterised inputs: rasterize_agents (src/tbsim/utils/trajdata_utils.py:123-156, called by
+ * parse_node_centric :395-420) is fused with the raster layout, so the 6.8 MB/agent fp32 image never exists.
+ *   maps [B,3,224,224] fp32 map layers; hist_pos [B,A,31,2] fp32 history positions in the ego frame, agent 0 = ego;
+ *   hist_mask [B,A,31] bytes (availability); raster_from_agent [B,3,3] fp32.
+ * cond_feat == NULL: rasterise only.  image_out (optional) [B,34,224,224] fp32 receives the image rasterize_agents returns. */
+int cld_context_forward_history(CldContext* c, const float* maps, const float* hist_pos, const uint8_t* hist_mask, const float* raster_from_agent,
+                                int num_hist_agents, const float* curr_states, int B, float* cond_feat, float* map_feat_out, float* image_out,
+                                void* stream) {
+  if (!c || !maps || !hist_pos || !hist_mask || !raster_from_agent || B <= 0 || num_hist_agents < 1)
+    return c ? cfail(c, CLD_ERR_ARG, "cld_context_forward_history: bad arguments") : CLD_ERR_ARG;
+  if (cond_feat && !curr_states) return cfail(c, CLD_ERR_ARG, "cld_context_forward_history: curr_states missing");
+  if (cond_feat && !c->loaded) return cfail(c, CLD_ERR_STATE, "cld_context_forward_history: weights not loaded");
+  RasterSrc src;
+  src.maps = maps; src.hist_pos = hist_pos; src.hist_mask = hist_mask; src.rfa = raster_from_agent; src.A = num_hist_agents; src.image_out = image_out;
+  return forward_impl(c, src, curr_states, B, cond_feat, map_feat_out, -1, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

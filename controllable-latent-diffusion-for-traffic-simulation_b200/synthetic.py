@@ -124,3 +124,32 @@ def make_context_batch(num_agents, seed=321, hist=31, size=224):
         img[:, hist + c] = band.float() * (1.0 if c != 1 else 0.5) + rect.float() * 0.5
     img[:, hist:].clamp_(0.0, 1.0)
     return {'image': img, 'history_positions': hist_pos, 'history_yaws': hist_yaw, 'curr_speed': v}
+
+
+def make_history_batch(num_agents, num_neighbors=5, seed=77, hist=31, size=224):
+    """Inputs of the history rasteriser (src/tbsim/utils/trajdata_utils.py:123-156) as `parse_node_centric` assembles them
+    (:395-420): map layers [B,3,H,W] with values in {0, 0.5, 1}, history positions of the ego (index 0) and its neighbours
+    in the ego frame [B,1+Nn,T,2], their availability mask and `raster_from_agent`.  Some positions fall outside the raster,
+    some are unavailable, several agents share a pixel."""
+    g = torch.Generator().manual_seed(seed)
+    B, A = num_agents, 1 + num_neighbors
+    rows = torch.arange(size)[None, :, None]
+    cols = torch.arange(size)[None, None, :]
+    maps = torch.zeros(B, 3, size, size)
+    for c in range(3):
+        half = torch.randint(6, 40, (B,), generator=g)[:, None, None]
+        off = torch.randint(-20, 21, (B,), generator=g)[:, None, None]
+        band = ((rows >= 112 + off - half) & (rows <= 112 + off + half)).expand(B, size, size)
+        c0 = torch.randint(0, 180, (B,), generator=g)[:, None, None]
+        rect = (cols >= c0) & (cols < c0 + 44)
+        maps[:, c] = (band.float() * (1.0 if c != 1 else 0.5) + (band & rect).float() * 0.5).clamp(0, 1)
+    v = torch.rand(B, A, generator=g) * 12.0
+    t_back = torch.arange(hist - 1, -1, -1).float() * 0.1
+    start = (torch.rand(B, A, 2, generator=g) * 2 - 1) * torch.tensor([70.0, 60.0])       # some start outside the 112 m raster
+    start[:, 0] = 0.0
+    pos = start[:, :, None, :] + torch.stack([-v[:, :, None] * t_back[None, None, :], torch.zeros(B, A, hist)], dim=-1)
+    pos[:, 1] = pos[:, 2]                                                               # two neighbours on the same pixels
+    mask = torch.rand(B, A, hist, generator=g) < 0.8
+    mask[:, 0] = True
+    rfa = torch.tensor([[2., 0., 56.], [0., 2., 112.], [0., 0., 1.]]).repeat(B, 1, 1)
+    return {'maps': maps, 'agent_hist_pos': pos, 'agent_hist_mask': mask, 'raster_from_agent': rfa}

@@ -227,6 +227,16 @@ int cld_context_load(CldContext* c, const float* const* dev_ptrs, const int64_t*
 int cld_context_forward(CldContext* c, const float* image, const float* curr_states, int B, float* cond_feat,
                         float* map_feat_out, int tap_stage, float* tap_out, void* stream);
 
+/* The same from the UN-RASTERISED inputs of the data layer: rasterize_agents (src/tbsim/utils/trajdata_utils.py:123-156, called
+ * by parse_node_centric :395-420) fused with the encoder's raster layout, so the 6.8 MB/agent fp32 image never exists.
+ *   maps [B,3,224,224] fp32 map layers; hist_pos [B,A,31,2] fp32 history positions in the ego frame, agent 0 = the ego;
+ *   hist_mask [B,A,31] bytes (availability); raster_from_agent [B,3,3] fp32.
+ * cond_feat == NULL rasterises only; image_out (optional) [B,34,224,224] fp32 receives the image rasterize_agents returns
+ * (history channel t: +1 at the ego's pixel, -1 at the other agents'; then the map layers). */
+int cld_context_forward_history(CldContext* c, const float* maps, const float* hist_pos, const uint8_t* hist_mask,
+                                const float* raster_from_agent, int num_hist_agents, const float* curr_states, int B,
+                                float* cond_feat, float* map_feat_out, float* image_out, void* stream);
+
 unsigned long long cld_context_launch_count(const CldContext* c);
 /* 2*MAC per agent of the 20 convolutions as executed (includes the zero-padded K of the stem). */
 double cld_context_conv_flops(const CldContext* c);

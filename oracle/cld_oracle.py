@@ -576,3 +576,29 @@ def synth_context_state(shapes, seed=2024):
             v = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)
         sd[k] = v
     return sd
+
+
+# --------------------------------------------------------------------------------------------------
+# a14 input: history rasterisation  (src/tbsim/utils/trajdata_utils.py:123-156, rasterize_agents)
+#   maps [B,C,H,W], agent_hist_pos [B,A,T,2] (agent 0 = ego), agent_mask [B,A,T] bool, raster_from_agent [B,3,3]
+#   -> [B,T+C,H,W]: channel t has +1 at the ego's pixel of history frame t and -1 at the other agents' pixels
+# --------------------------------------------------------------------------------------------------
+def rasterize_agents(maps, agent_hist_pos, agent_mask, raster_from_agent):
+    b, a, t, _ = agent_hist_pos.shape
+    _, _, h, w = maps.shape
+    pts = agent_hist_pos.reshape(b, a * t, 2)
+    # transform_points_tensor (geometry_utils.py:98-140), batched 2-D case: p @ R^T + t
+    rot = raster_from_agent[:, :2, :2].transpose(1, 2)
+    pos = pts @ rot + raster_from_agent[:, None, :2, 2]
+    pos[~agent_mask.reshape(b, a * t)] = 0.0
+    pos = pos.reshape(b, a, t, 2).permute(0, 2, 1, 3).clone()
+    pos[..., 0].clip_(0, w - 1)
+    pos[..., 1].clip_(0, h - 1)
+    pos = torch.round(pos).long()
+    flat = pos[..., 1] * w + pos[..., 0]                                   # [B,T,A]
+    img = torch.zeros(b, t, h * w, dtype=maps.dtype)
+    img.scatter_(2, flat[:, :, 1:], torch.ones_like(img) * -1)             # others
+    img.scatter_(2, flat[:, :, [0]], torch.ones_like(img))                 # ego (wins)
+    img[:, :, 0] = 0
+    img[:, :, -1] = 0
+    return torch.cat((img.reshape(b, t, h, w), maps), dim=1)

@@ -236,6 +236,7 @@ def main():
                         grad_sgd=grads_ref.numpy(), loss_ac=loss_ref['agent_collision'].numpy(),
                         loss_mc=loss_ref['map_collision'].numpy(), **wsum)
     context_golden()
+    raster_golden()
     print("golden files written to", GOLD)
 
 
@@ -268,8 +269,31 @@ def context_golden():
     print("context golden written")
 
 
+def raster_golden():
+    """History rasterisation: the REAL rasterize_agents (src/tbsim/utils/trajdata_utils.py:123-156) on synthetic histories ->
+    tests/golden/raster.npz (image as int8 = 2 x value)."""
+    RH.install()
+    from tbsim.utils.trajdata_utils import rasterize_agents
+    from cld_b200.synthetic import make_history_batch
+    hb = make_history_batch(4, num_neighbors=5, seed=77)
+    yaw = torch.zeros(*hb['agent_hist_pos'].shape[:3], 1)
+    ref = rasterize_agents(hb['maps'], hb['agent_hist_pos'], yaw, hb['agent_hist_mask'], hb['raster_from_agent'], None)
+    mine = O.rasterize_agents(hb['maps'], hb['agent_hist_pos'], hb['agent_hist_mask'], hb['raster_from_agent'])
+    assert torch.equal(ref, mine), "oracle rasterize_agents differs from the reference"
+    n_ego, n_oth = int((ref[:, :31] == 1).sum()), int((ref[:, :31] == -1).sum())
+    print("rasterize_agents: oracle == reference (bit-equal); ego pixels %d, other-agent pixels %d" % (n_ego, n_oth))
+    assert torch.equal((ref * 2).round() / 2, ref)
+    np.savez_compressed(os.path.join(GOLD, "raster.npz"), seed=77, image_x2=(ref * 2).round().to(torch.int8).numpy(),
+                        maps_x2=(hb['maps'] * 2).round().to(torch.int8).numpy(), agent_hist_pos=hb['agent_hist_pos'].numpy(),
+                        agent_hist_mask=hb['agent_hist_mask'].numpy(), raster_from_agent=hb['raster_from_agent'].numpy(),
+                        n_ego=n_ego, n_oth=n_oth)
+    print("raster golden written")
+
+
 if __name__ == "__main__":
-    if "--only-context" in sys.argv:
+    if "--only-raster" in sys.argv:
+        raster_golden()
+    elif "--only-context" in sys.argv:
         context_golden()
     else:
         main()

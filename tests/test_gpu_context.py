@@ -141,3 +141,37 @@ def test_raster_to_trajectories_chain(gold):
              agents_per_scene=A, seed=5)
     torch.cuda.synchronize()
     assert out["traj"].shape == (S * A, 52, 6) and torch.isfinite(out["traj"]).all()
+
+
+def test_rasterize_agents_vs_reference_golden(gold):
+    """The fused history rasteriser against the REAL rasterize_agents (tests/golden/raster.npz): bit-exact image."""
+    g, sd, ce = _build(gold)
+    r = gold("raster")
+    img = ce.rasterize_agents(torch.from_numpy(r["maps_x2"]).float().cuda() / 2, torch.from_numpy(r["agent_hist_pos"]).cuda(), None,
+                              torch.from_numpy(r["agent_hist_mask"]).cuda(), torch.from_numpy(r["raster_from_agent"]).cuda())
+    torch.cuda.synchronize()
+    want = torch.from_numpy(r["image_x2"]).float() / 2
+    assert torch.equal(img.cpu(), want)
+
+
+def test_forward_history_equals_forward_on_the_rasterised_image(gold):
+    """Rasterising inside the encoder gives the same cond_feat as encoding the image rasterize_agents returns (bit for bit: the
+    bf16 raster is identical), for a ragged batch and against the oracle chain."""
+    import cld_oracle as O
+    from cld_b200.synthetic import make_history_batch
+    g, sd, ce = _build(gold)
+    hb = make_history_batch(11, num_neighbors=7, seed=5)
+    B = 11
+    batch = {"raster_from_agent": hb["raster_from_agent"], "history_positions": hb["agent_hist_pos"][:, 0],
+             "history_yaws": torch.zeros(B, 31, 1), "curr_speed": torch.rand(B) * 9}
+    cb = {k: v.cuda() for k, v in batch.items()}
+    fused = ce.forward_history(cb, hb["maps"].cuda(), hb["agent_hist_pos"].cuda(), hb["agent_hist_mask"].cuda(), want_image=True)
+    cb["image"] = fused["image"]
+    plain = ce(cb)
+    torch.cuda.synchronize()
+    assert torch.equal(fused["cond_feat"], plain["cond_feat"])
+    img = O.rasterize_agents(hb["maps"], hb["agent_hist_pos"], hb["agent_hist_mask"], hb["raster_from_agent"])
+    assert torch.equal(fused["image"].cpu(), img)
+    with torch.no_grad():
+        want = O.context_encode(sd, dict(batch, image=img))["cond_feat"]
+    assert rel(fused["cond_feat"], want) < 2e-2

@@ -172,3 +172,14 @@ def test_context_mirror_state_dict_matches_reference(gold):
     assert list(sd.keys()) == [str(k) for k in g["keys"]]
     assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in g["shapes"]]
     assert len(ce.weight_list()) == 130
+
+
+def test_rasterize_agents_oracle_vs_reference_golden(gold):
+    """oracle.rasterize_agents == the REAL rasterize_agents (src/tbsim/utils/trajdata_utils.py:123-156), bit for bit."""
+    import torch
+    import cld_oracle as O
+    g = gold("raster")
+    img = O.rasterize_agents(torch.from_numpy(g["maps_x2"]).float() / 2, torch.from_numpy(g["agent_hist_pos"]),
+                             torch.from_numpy(g["agent_hist_mask"]), torch.from_numpy(g["raster_from_agent"]))
+    assert torch.equal(img, torch.from_numpy(g["image_x2"]).float() / 2)
+    assert int((img[:, :31] == 1).sum()) == int(g["n_ego"]) and int((img[:, :31] == -1).sum()) == int(g["n_oth"])

@@ -39,6 +39,17 @@ ms = timeit(lambda: ce(batch), iters)
 fl = ce.conv_flops_per_agent()
 print("cld_context_forward: B=%d  %.2f ms  %.0f agents/s  executed conv %.2f GFLOP/agent -> %.1f TFLOP/s (algorithmic 6.07 GFLOP/agent -> %.1f TFLOP/s)"
       % (B, ms, B / ms * 1e3, fl / 1e9, fl * B / ms / 1e9, 6.07e9 * B / ms / 1e9))
+# fused history rasteriser: map layers + history points instead of the fp32 image
+from cld_b200.synthetic import make_history_batch
+hb = make_history_batch(64, num_neighbors=15, seed=3)
+rep = (B + 63) // 64
+maps = hb["maps"].cuda().repeat(rep, 1, 1, 1)[:B].contiguous()
+hpos = hb["agent_hist_pos"].cuda().repeat(rep, 1, 1, 1)[:B].contiguous()
+hmask = hb["agent_hist_mask"].cuda().repeat(rep, 1, 1)[:B].contiguous()
+b2 = dict(batch)
+b2["raster_from_agent"] = hb["raster_from_agent"].cuda().repeat(rep, 1, 1)[:B].contiguous()
+ms2 = timeit(lambda: ce.forward_history(b2, maps, hpos, hmask), iters)
+print("cld_context_forward_history (16 agents per raster): B=%d  %.2f ms  %.0f agents/s" % (B, ms2, B / ms2 * 1e3))
 if eager:
     sdc = {k: v.cuda() for k, v in sd.items()}
     Bs = min(B, 512)
