@@ -187,6 +187,26 @@ def context_encoder_rate(dev, agents=1024, iters=5, warmup=3, cpu_agents=256):
            "algorithmic_gflop_per_agent": 6.07, "executed_gflop_per_agent": ce.conv_flops_per_agent() / 1e9,
            "achieved_tflops": tflops, "frac_of_bf16_peak": tflops / tf_peak, "peak_source": peak_src + " bf16_tflops_sustained",
            "gpu_launches": ce.launch_count() - l0, "bytes_in_per_agent": 34 * 224 * 224 * 4}
+    # the same with the rasterisation fused in (cld_context_forward_history): map layers + history points of 16 agents per raster
+    from cld_b200.synthetic import make_history_batch
+    hb = make_history_batch(64, num_neighbors=15, seed=3)
+    rep = (agents + 63) // 64
+    maps = hb["maps"].to(dev).repeat(rep, 1, 1, 1)[:agents].contiguous()
+    hpos = hb["agent_hist_pos"].to(dev).repeat(rep, 1, 1, 1)[:agents].contiguous()
+    hmask = hb["agent_hist_mask"].to(dev).repeat(rep, 1, 1)[:agents].contiguous()
+    b2 = dict(batch)
+    b2["raster_from_agent"] = hb["raster_from_agent"].to(dev).repeat(rep, 1, 1)[:agents].contiguous()
+    for _ in range(2):
+        ce.forward_history(b2, maps, hpos, hmask)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ce.forward_history(b2, maps, hpos, hmask)
+    e1.record()
+    torch.cuda.synchronize()
+    hms = e0.elapsed_time(e1) / iters
+    out["from_history"] = {"value": agents / hms * 1e3, "unit": "agents/s", "ms": hms, "agents_per_raster": 16,
+                           "bytes_in_per_agent": 3 * 224 * 224 * 4 + 16 * 31 * 9 + 36}
     ce.close()
     # the reference's CPU path for the same row, timed beside it: the oracle restatement of ContextEncoder.forward (bit-equal to the
     # real reference, oracle/make_golden.py) on a bounded sample with all host threads
