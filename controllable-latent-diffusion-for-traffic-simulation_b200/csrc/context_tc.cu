@@ -44,6 +44,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 32-byte global accesses (LDG/STG.256): a full sector per thread instead of two half-sector transactions
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
@@ -211,8 +220,8 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
           uint4 rr[16];
           if (has_res && mv) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (h0 + j * 8 < NT) rr[j] = __ldg(reinterpret_cast<const uint4*>(P.res + orow + h0 + j * 8));
+            for (int j = 0; j < 16; j += 2)
+              if (h0 + j * 8 < NT) ldg256(P.res + orow + h0 + j * 8, rr[j], rr[j + 1]);
           }
           if (h0 == 0 && m == 0) { mbar_wait(bar_accf + 8 * buf, aph); tc_fence_after(); }
 #pragma unroll
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
               if (mv) {
                 const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
                 const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+                uint4 pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
@@ -242,9 +252,10 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
                   }
-                  *reinterpret_cast<uint4*>(P.out + orow + c0 + g * 8) =
-                      make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+                  pk[g] = make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
                 }
+                stg256(P.out + orow + c0, pk[0], pk[1]);
+                stg256(P.out + orow + c0 + 16, pk[2], pk[3]);
               }
             }
           }
