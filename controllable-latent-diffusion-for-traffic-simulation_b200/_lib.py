@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcld_b200.so")
+LIB_PATH = os.environ.get("CLD_B200_LIB") or os.path.join(_HERE, "libcld_b200.so")   # override: A/B of two builds
 
 CLD_PREC_FP32, CLD_PREC_BF16 = 0, 1
 CLD_SAMPLER_DDPM, CLD_SAMPLER_DDIM = 0, 1

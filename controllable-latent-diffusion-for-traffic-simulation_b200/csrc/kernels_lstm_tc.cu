@@ -154,6 +154,11 @@ __host__ __device__ inline int gate_row_of(int tile, int m) {
 }
 }  // namespace
 
+// 32-byte stash accesses (LDG/STG.256): one full sector per instruction
+__device__ __forceinline__ void st8(float* p, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7) : "memory");
+}
 struct LstmTcArgs {
   const float *z, *h0, *curr;
   const uint8_t* wblob;                  // packed fp16x2 forward weights for TMEM, [208][128]
@@ -279,12 +284,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         float* s1 = a.stash + stash_index(L, t, T, R, row0 + r16, is_b ? 3 : 2, u);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          float4* d0 = reinterpret_cast<float4*>(s0 + (size_t)b * (5 * 64 * 8));
-          float4* d1 = reinterpret_cast<float4*>(s1 + (size_t)b * (5 * 64 * 8));
-          d0[0] = make_float4(a0[8 * b + 0], a0[8 * b + 1], a0[8 * b + 2], a0[8 * b + 3]);
-          d0[1] = make_float4(a0[8 * b + 4], a0[8 * b + 5], a0[8 * b + 6], a0[8 * b + 7]);
-          d1[0] = make_float4(a1[8 * b + 0], a1[8 * b + 1], a1[8 * b + 2], a1[8 * b + 3]);
-          d1[1] = make_float4(a1[8 * b + 4], a1[8 * b + 5], a1[8 * b + 6], a1[8 * b + 7]);
+          st8(s0 + (size_t)b * (5 * 64 * 8), a0[8 * b + 0], a0[8 * b + 1], a0[8 * b + 2], a0[8 * b + 3], a0[8 * b + 4], a0[8 * b + 5],
+              a0[8 * b + 6], a0[8 * b + 7]);
+          st8(s1 + (size_t)b * (5 * 64 * 8), a1[8 * b + 0], a1[8 * b + 1], a1[8 * b + 2], a1[8 * b + 3], a1[8 * b + 4], a1[8 * b + 5],
+              a1[8 * b + 6], a1[8 * b + 7]);
         }
       }
       if (PROF && rec && t >= P0 && t < P0 + PN) tl[t - P0][2] = clock64();
@@ -301,9 +304,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
         hn[r] = og * tanhf_(c[r]);
       }
       if (SAVE) {
-        float4* d = reinterpret_cast<float4*>(a.stash + stash_index(L, t, T, R, row0 + r8, 4, u));
-        d[0] = make_float4(c[0], c[1], c[2], c[3]);
-        d[1] = make_float4(c[4], c[5], c[6], c[7]);
+        st8(a.stash + stash_index(L, t, T, R, row0 + r8, 4, u), c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
       }
       if (L == 0) {
         uint8_t* dst = sm + LF_H0 + (t & 1) * 2 * LT_OP;
@@ -534,8 +535,8 @@ __device__ __forceinline__ void tmem_ld16_hilo(uint32_t taddr, float (&o)[16]) {
 }
 
 __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "l"(p) : "memory");
 }
 
 template <bool PROF>
