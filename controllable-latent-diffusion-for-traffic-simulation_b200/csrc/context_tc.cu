@@ -403,29 +403,31 @@ __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
-// MaxPool2d(3, stride 2, padding 1) on NHWC bf16, 8 channels per thread
+// MaxPool2d(3, stride 2, padding 1) on NHWC bf16, 16 channels (one 32-byte sector) per thread
 __global__ void ctx_maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                                    int OH, int OW) {
-  const long long total = (long long)B * OH * OW * (C >> 3);
+  const long long total = (long long)B * OH * OW * (C >> 4);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cc = (int)(idx % (C >> 3));
-  long long t = idx / (C >> 3);
+  const int cc = (int)(idx % (C >> 4));
+  long long t = idx / (C >> 4);
   const int ow = (int)(t % OW); t /= OW;
   const int oh = (int)(t % OH);
   const int b = (int)(t / OH);
-  uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf pairs
+  uint4 m0 = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u), m1 = m0;   // -inf pairs
   for (int dy = 0; dy < 3; ++dy) {
     const int ih = oh * 2 - 1 + dy;
     if (ih < 0 || ih >= H) continue;
     for (int dx = 0; dx < 3; ++dx) {
       const int iw = ow * 2 - 1 + dx;
       if (iw < 0 || iw >= W) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)b * H + ih) * W + iw) * C + cc * 8);
-      m.x = bmax2(m.x, v.x); m.y = bmax2(m.y, v.y); m.z = bmax2(m.z, v.z); m.w = bmax2(m.w, v.w);
+      uint4 v0, v1;
+      ldg256(in + (((size_t)b * H + ih) * W + iw) * C + cc * 16, v0, v1);
+      m0.x = bmax2(m0.x, v0.x); m0.y = bmax2(m0.y, v0.y); m0.z = bmax2(m0.z, v0.z); m0.w = bmax2(m0.w, v0.w);
+      m1.x = bmax2(m1.x, v1.x); m1.y = bmax2(m1.y, v1.y); m1.z = bmax2(m1.z, v1.z); m1.w = bmax2(m1.w, v1.w);
     }
   }
-  *reinterpret_cast<uint4*>(out + (((size_t)b * OH + oh) * OW + ow) * C + cc * 8) = m;
+  stg256(out + (((size_t)b * OH + oh) * OW + ow) * C + cc * 16, m0, m1);
 }
 
 // debug / verification tap: NHWC bf16 -> NCHW fp32
@@ -979,7 +981,7 @@ int forward_impl(CldContext* c, const RasterSrc& src, const float* curr_states, 
       const ConvLayer& L = c->conv[c->order[k]];
       if ((rc = launch_conv(c, L, nb, s))) return rc;
       if (k == 0) {
-        const long long total = (long long)nb * 56 * 56 * 8;
+        const long long total = (long long)nb * 56 * 56 * 4;
         ctx_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->stem_out, c->bufX, nb, 112, 112, 64, 56, 56);
         CTX_LAUNCH_OK(c, "ctx_maxpool_kernel");
         if ((rc = tap(0, 56, 64))) return rc;
