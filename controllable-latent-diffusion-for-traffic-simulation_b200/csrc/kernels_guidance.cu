@@ -205,13 +205,16 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
   const int row = blockIdx.x, t = blockIdx.y * 8 + warp;
   if (t >= T) return;
   const int g = row / N;
-  if (!(fabsf(a.speed[g]) > a.speed_th)) return;       // loss and gradient are zero for non-moving agents
-  const float L = a.extent[g * 3 + 0], Wd = a.extent[g * 3 + 1];
+  // every input of this (row, step) is fetched before the first use: one memory round trip instead of a chain of three
   const float* M = a.rfa + (size_t)g * 9;
-  const float m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
-  const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
   const float* tr = a.traj + ((size_t)row * T + t) * 6;
-  const float px = tr[0], py = tr[1], psi = tr[3];
+  const float spd = __ldg(a.speed + g);
+  const float L = __ldg(a.extent + g * 3 + 0), Wd = __ldg(a.extent + g * 3 + 1);
+  const float m0 = __ldg(M + 0), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3), m4 = __ldg(M + 4), m5 = __ldg(M + 5);
+  const float2 pxy = *reinterpret_cast<const float2*>(tr);
+  const float px = pxy.x, py = pxy.y, psi = tr[3];
+  if (!(fabsf(spd) > a.speed_th)) return;       // loss and gradient are zero for non-moving agents
+  const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
   float sn, c;
   sincosf(psi, &sn, &c);
   const float wmax = (float)a.W, hmax = (float)a.H;
