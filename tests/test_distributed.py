@@ -79,3 +79,21 @@ def test_gather_world2_gloo_equal_shards():
 
 def test_gather_world2_gloo_ragged_shards():
     _run(5, 2)
+
+
+def test_shard_batch_carries_the_context_encoder_inputs():
+    """The raster and the history tensors of the context encoder (row a14) shard by scene like every other per-agent entry."""
+    S, A = 5, 3
+    B = S * A
+    full = {"image": torch.arange(B).float().view(B, 1, 1, 1).expand(B, 2, 4, 4).contiguous(),
+            "history_positions": torch.arange(B).float().view(B, 1, 1).expand(B, 31, 2).contiguous(),
+            "history_yaws": torch.zeros(B, 31, 1), "curr_speed": torch.arange(B).float(), "scene_index": torch.arange(S).repeat_interleave(A),
+            "map_names": ["m"] * B}
+    seen = []
+    for rank in range(2):
+        mine = shard_batch(full, A, 2, rank)
+        s0, s1 = shard_scenes(S, 2, rank)
+        assert mine["image"].shape[0] == (s1 - s0) * A and mine["map_names"] == full["map_names"]
+        assert torch.equal(mine["image"][:, 0, 0, 0], mine["curr_speed"]) and torch.equal(mine["history_positions"][:, 0, 0], mine["curr_speed"])
+        seen.append(mine["curr_speed"])
+    assert torch.equal(torch.cat(seen), full["curr_speed"])
