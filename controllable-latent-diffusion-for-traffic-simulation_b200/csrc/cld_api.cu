@@ -152,6 +152,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->tcm, MR * (cfg->base_dim + cfg->cond_dim));
   if (!rc) rc = dev_alloc(h, &h->tbias, MR * tb_total);
   if (!rc) rc = dev_alloc(h, &h->tvec, tb_total);
+  if (!rc) rc = dev_alloc(h, &h->tvec_all, (size_t)cfg->n_timesteps * tb_total);
   if (!rc) rc = dev_alloc(h, &h->stash, (size_t)2 * T * ((MR + 63) / 64 * 64) * 5 * cfg->hidden);
   if (!rc) rc = dev_alloc(h, &h->ws_act, MR * T * 2);
   if (!rc) rc = dev_alloc(h, &h->ws_h0, MR * cfg->hidden);
@@ -179,6 +180,7 @@ void cld_destroy(CldHandle* h) {
   lstm_tc_destroy(h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_tvec) cudaEventDestroy(h->ev_tvec);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
@@ -301,6 +303,7 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
   if (tc_enabled(h) && (rc = tc_finalize(h, s))) return rc;
   CLD_CUDA_OK(h, cudaStreamSynchronize(s));
   u.loaded = true;
+  h->tvec_all_valid = false;
   return CLD_OK;
 }
 
@@ -497,6 +500,17 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     // bf16 path: the cond half of every block's time/cond projection is step-invariant -> once per chunk
     const bool split_bias = (c.precision == CLD_PREC_BF16);
     if (split_bias && (rc = unet_cond_bias(h, condc, Rc, s))) return rc;
+    if (split_bias && !h->tvec_all_valid) {
+      // the time part of every block's bias depends on the timestep only: one table per weight load instead of a kernel per step
+      for (int t = 0; t < n_t; ++t)
+        if ((rc = unet_time_vec_to(h, t, h->tvec_all + (size_t)t * h->unet.tb_total, s))) return rc;
+      if (!h->ev_tvec) CLD_CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_tvec, cudaEventDisableTiming));
+      CLD_CUDA_OK(h, cudaEventRecord(h->ev_tvec, s));
+      h->tvec_stream = s;
+      h->tvec_all_valid = true;
+    } else if (split_bias && s != h->tvec_stream && h->ev_tvec) {
+      CLD_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_tvec, 0));
+    }
     // LSTM initial state (cond2hidden) is step-invariant as well
     if ((g || traj_out || offroad_out || coll_out) && (rc = decode_h0(h, condc, h->ws_h0, Rc, s))) return rc;
     for (int k = 0; k < K; ++k) {
@@ -507,8 +521,7 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
         return fail(h, CLD_ERR_ARG, "either a noise tensor or a non-zero seed is required");
       if ((rc = prof_begin(h, 0, s))) return rc;
       if (split_bias) {
-        if ((rc = unet_time_vec(h, i, s))) return rc;
-        if ((rc = tc_unet_forward_prepared(h, x, h->ws_eps, Rc, s))) return rc;
+        if ((rc = tc_unet_forward_prepared(h, x, h->ws_eps, Rc, s, h->tvec_all + (size_t)i * h->unet.tb_total))) return rc;
       } else {
         if ((rc = fill_t(h, h->ws_t, i, Rc, s))) return rc;
         if ((rc = unet_dispatch(h, x, condc, h->ws_t, h->ws_eps, Rc, s))) return rc;

@@ -87,6 +87,10 @@ struct CldHandle {
   float* tcm = nullptr;            // [max_rows, 32+cond] Mish([t_emb, cond])
   float* tbias = nullptr;          // [max_rows, tb_total]
   float* tvec = nullptr;           // [tb_total] per-step time part of the bias (sampler: uniform t)
+  float* tvec_all = nullptr;       // [n_timesteps, tb_total]: the same for every timestep, filled once after a weight load (cld_sample)
+  bool tvec_all_valid = false;
+  cudaEvent_t ev_tvec = nullptr;   // recorded after the table was filled: later calls on another stream wait for it
+  cudaStream_t tvec_stream = nullptr;
   // guidance / decode workspace
   float* stash = nullptr;          // LSTM forward stash, see stash_index()
   float* ws_act = nullptr;         // [max_rows, T, 2]
@@ -154,6 +158,7 @@ int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int
 int unet_stage_elems(const CldHandle* h, int stage);
 int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s);   // -> h->tbias (cond part + bias)
 int unet_time_vec(CldHandle* h, int t, cudaStream_t s);                        // -> h->tvec
+int unet_time_vec_to(CldHandle* h, int t, float* dst, cudaStream_t s);
 // ---- kernels_step.cu
 int posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise, uint64_t seed,
                    uint64_t seq, int t, int t_next, int sampler, float* x_out, float* mean_out, int R,

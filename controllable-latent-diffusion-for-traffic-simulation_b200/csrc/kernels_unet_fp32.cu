@@ -303,14 +303,14 @@ int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s) {
   return launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s);
 }
 
-int unet_time_vec(CldHandle* h, int t, cudaStream_t s) {
+int unet_time_vec_to(CldHandle* h, int t, float* dst, cudaStream_t s) {
   const UnetW& u = h->unet;
   const CldConfig& c = h->cfg;
-  time_vec_kernel<<<(u.tb_total + 255) / 256, 256, 0, s>>>(t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, u.tb_w, h->tvec,
-                                                            c.base_dim, u.tb_total);
+  time_vec_kernel<<<(u.tb_total + 255) / 256, 256, 0, s>>>(t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, u.tb_w, dst, c.base_dim, u.tb_total);
   CLD_LAUNCH_OK(h, "time_vec_kernel");
   return 0;
 }
+int unet_time_vec(CldHandle* h, int t, cudaStream_t s) { return unet_time_vec_to(h, t, h->tvec, s); }
 
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R,
                       cudaStream_t s) {

@@ -1028,10 +1028,10 @@ int tc_unet_forward(CldHandle* h, const float* x, const float* cond, const int64
   return tc_launch(h, x, eps, R, s->zeros, stream);
 }
 
-int tc_unet_forward_prepared(CldHandle* h, const float* x, float* eps, int R, cudaStream_t stream) {
+int tc_unet_forward_prepared(CldHandle* h, const float* x, float* eps, int R, cudaStream_t stream, const float* tvec) {
   TcState* s = st_of(h);
   if (!s || !s->ready) return fail(h, CLD_ERR_STATE, "bf16 denoiser weights not packed");
-  return tc_launch(h, x, eps, R, h->tvec, stream);
+  return tc_launch(h, x, eps, R, tvec ? tvec : h->tvec, stream);
 }
 
 static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const float* tvec, cudaStream_t stream) {

@@ -15,6 +15,7 @@ int tc_finalize(CldHandle* h, cudaStream_t s);
 int tc_unet_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R,
                     cudaStream_t s);
 // same, with h->tbias (cond part) and h->tvec (time part) already computed by unet_cond_bias / unet_time_vec
-int tc_unet_forward_prepared(CldHandle* h, const float* x, float* eps, int R, cudaStream_t s);
+// (tvec == nullptr: h->tvec; otherwise one row of h->tvec_all)
+int tc_unet_forward_prepared(CldHandle* h, const float* x, float* eps, int R, cudaStream_t s, const float* tvec = nullptr);
 void tc_destroy(CldHandle* h);
 }  // namespace cld
