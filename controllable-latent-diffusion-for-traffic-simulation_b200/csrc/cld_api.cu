@@ -538,11 +538,15 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
         if ((rc = posterior_step(h, x, h->ws_eps, nullptr, 0, 0, i, i_next, sampler, nullptr, h->ws_mean, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
         if ((rc = prof_begin(h, 2, s))) return rc;
-        if ((rc = guidance_step_impl(h, h->ws_mean, condc, h->ws_h0, currc, sc, g, h->ws_mean, nullptr, nullptr, Rc, s))) return rc;
+        // DDIM (eta = 0) injects no noise: the guidance update writes the next state directly
+        const bool noiseless = sampler != CLD_SAMPLER_DDPM;
+        if ((rc = guidance_step_impl(h, h->ws_mean, condc, h->ws_h0, currc, sc, g, noiseless ? x : h->ws_mean, nullptr, nullptr, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
-        if ((rc = prof_begin(h, 1, s))) return rc;
-        if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, sampler == CLD_SAMPLER_DDPM ? i : 0, x, Rc, s))) return rc;
-        if ((rc = prof_end(h, s))) return rc;
+        if (!noiseless) {
+          if ((rc = prof_begin(h, 1, s))) return rc;
+          if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, i, x, Rc, s))) return rc;
+          if ((rc = prof_end(h, s))) return rc;
+        }
       }
       if (i == 1 && x1_out) {
         CLD_CUDA_OK(h, cudaMemcpyAsync(x1_out + r0 * row_e, x, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
