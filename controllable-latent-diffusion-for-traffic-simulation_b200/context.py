@@ -62,7 +62,7 @@ class _Holder(nn.Module):
 
 
 class ContextEncoder(nn.Module):
-    def __init__(self, state_in_dim, algo_config, modality_shapes, dyn=None, *, max_agents=4096):
+    def __init__(self, state_in_dim, algo_config, modality_shapes, dyn=None, *, max_agents=None):
         super().__init__()
         self.dyn = dyn
         d = algo_config.curr_state_feat_dim
@@ -78,7 +78,9 @@ class ContextEncoder(nn.Module):
         cin = d + algo_config.map_feature_dim
         cout = algo_config.cond_feat_dim
         self.process_cond_mlp = _MLP(cin, cout, (cin, cin, cout, cout))
-        self._max_agents = int(max_agents)
+        # workspace capacity in agents (5.9 MB each, processed in chunks of <= 2048); None: sized by the largest batch seen
+        self._max_agents = None if max_agents is None else int(max_agents)
+        self._capacity = 0
         self._handle = None
         self._handle_dev = None
         self._dirty = True
@@ -122,15 +124,15 @@ class ContextEncoder(nn.Module):
         p = next(self.parameters())
         if p.device.type != "cuda":
             raise RuntimeError("cld_b200.ContextEncoder runs on a B200 only (module is on %s); there is no CPU fallback" % p.device)
-        need = max(self._max_agents, 1)
-        if self._handle is None or self._handle_dev != p.device:
+        need = max(self._max_agents, 1) if self._max_agents is not None else min(max(int(B), 1), 2048)
+        if self._handle is None or self._handle_dev != p.device or (self._max_agents is None and need > self._capacity):
             self.close()
             with torch.cuda.device(p.device):
                 h = C.c_void_p()
                 if lib.cld_context_create(int(need), C.byref(h)) != 0:
                     self._handle = None
                     self._err("cld_context_create")
-            self._handle, self._handle_dev, self._dirty = h, p.device, True
+            self._handle, self._handle_dev, self._dirty, self._capacity = h, p.device, True, need
         if self._dirty:
             ws = [w.detach().to(torch.float32).contiguous() for w in self.weight_list()]
             ptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
