@@ -272,6 +272,217 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) conv_tma_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (cta_group::2) for the plain-stage layers with wide N (layers 3 and 4, the stride-2 convolutions): a
+// cluster of two CTAs computes two adjacent m-tiles of the same N tile with ONE tcgen05.mma.cta_group::2 per K step (M = 256,
+// 128 rows per CTA).  Each CTA stages its own activation box and only HALF of the weight image (N/2 rows); the instruction
+// reads both halves, so the weight bytes per CTA and k-block halve (48 -> 32 KB at N = 256) -- the layers are bound by the
+// L2 -> SM ingest.  Protocol: both producers' TMA copies complete on the LEADER's (rank 0) full barrier; the leader's MMA
+// thread issues for the pair and commits with a multicast arrive onto the empty / accumulator-full barriers of both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier (remote mbarrier arrive for rank 1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_pair(uint32_t bar) {          // arrive on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __launch_bounds__(CT2_THREADS, 1) conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                                   const ConvT P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int S = P.stages, NT = P.NT;
+  const uint32_t bh_bytes = (uint32_t)NT * 64u;                       // this CTA's half of a weight image: NT/2 rows x 128 B
+  const uint32_t a_bytes = CT_A_BYTES, stage_bytes = a_bytes + bh_bytes;
+  uint8_t* tail = smem + (size_t)S * stage_bytes;
+  float* sc_s = reinterpret_cast<float*>(tail);
+  float* bi_s = sc_s + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 4096 + 8 * (2 * CT_MAX_STAGES + 4));
+  uint32_t* stt_s = reinterpret_cast<uint32_t*>(tail + 4096 + 256);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * CT_MAX_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * CT_MAX_STAGES, bar_acce = bar_accf + 16;
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  for (int i = tid; i < P.Cout; i += CT2_THREADS) { sc_s[i] = P.scale[i]; bi_s[i] = P.bias[i]; }
+  if (tid < 40) stt_s[tid] = (uint32_t)P.stt[2 * tid] | ((uint32_t)P.stt[2 * tid + 1] << 16);
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
+    mbar_init(bar_acce, 8); mbar_init(bar_acce + 8, 8);                // 4 epilogue warps of each CTA (used in the leader only)
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // both CTAs' barriers exist before any remote arrive / remote complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_pair_tiles = ((P.n_mt + 1) >> 1) * P.n_nt, n_st = P.n_st;
+  const int cid = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const int bw = 1 << P.lbw, bh = 1 << P.lbh, bn = 128 >> (P.lbw + P.lbh);
+
+  if (warp == 5) {
+    // ===================== TMA producer (both CTAs): own activation box + own half of the weight image =====================
+    int s = 0; uint32_t ph = 0;
+    const uint32_t full0 = mapa_shared(bar_full, 0);                     // the leader's full barriers
+    for (int pt = cid; pt < n_pair_tiles; pt += n_clusters) {
+      const int mp = pt / P.n_nt, nt = pt - mp * P.n_nt;
+      const int mt = 2 * mp + (int)rank;
+      const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
+      const int cx0 = tx * bw * P.sx, cy0 = ty * bh * P.sy, cb0 = tb * bn;
+      const int wrow0 = nt * n_st * NT + (int)rank * (NT >> 1);          // first weight row of this CTA's half, k-block 0
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t e = (stt_s[st >> 1] >> ((st & 1) * 16)) & 0xffffu;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+          if (leader) mbar_expect_tx_only(bar_full + 8 * s, 2u * (a_bytes + bh_bytes));
+          const int cx = cx0 + (int)((e >> 4) & 15u) - 8, cy = cy0 + (int)((e >> 8) & 15u) - 8;
+          tma2_load_4d(dst, &tmA, (int)(e & 15u) * 64, cx, P.yb ? cb0 : cy, P.yb ? cy : cb0, full0 + 8 * s);
+          tma2_load_2d(dst + a_bytes, &tmW, 0, wrow0 + st * NT, full0 + 8 * s);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer (leader only): one instruction drives both CTAs =====================
+    if (leader) {
+      int s = 0; uint32_t ph = 0, ti = 0;
+      const uint32_t idesc = pin(make_idesc_bf16(256, NT));
+      const uint32_t stage16 = pin(stage_bytes >> 4), a16 = pin(a_bytes >> 4);
+      const int n_st_r = (int)pin((uint32_t)n_st), S_r = (int)pin((uint32_t)S);
+      const uint64_t desc0 = make_desc_sw128(smem_base, 1024);
+      for (int pt = cid; pt < n_pair_tiles; pt += n_clusters, ++ti) {
+        const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+        mbar_wait(bar_acce + 8 * buf, aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + buf * 256u;
+        for (int st = 0; st < n_st_r; ++st) {
+          const uint64_t ad = desc0 + (uint64_t)((uint32_t)s * stage16), bd = ad + a16;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            umma2_bf16(d_addr, ad, bd, idesc, st != 0 ? 1u : 0u);
+            umma2_bf16(d_addr, ad + 2, bd + 2, idesc, 1u);
+            umma2_bf16(d_addr, ad + 4, bd + 4, idesc, 1u);
+            umma2_bf16(d_addr, ad + 6, bd + 6, idesc, 1u);
+            umma2_commit_pair(bar_empty + 8 * s);
+          }
+          __syncwarp();
+          if (++s == S_r) { s = 0; ph ^= 1u; }
+        }
+        if (elect_one()) umma2_commit_pair(bar_accf + 8 * buf);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own 128 rows =====================
+    const int q = warp;
+    uint32_t ti = 0;
+    const int r = q * 32 + lane;
+    const int wi = r & (bw - 1);
+    const int bi = P.yb ? (r >> P.lbw) & (bn - 1) : r >> (P.lbw + P.lbh);
+    const int hi = P.yb ? r >> (7 - P.lbh) : (r >> P.lbw) & (bh - 1);
+    const bool has_res = P.res != nullptr;
+    const uint32_t acce0 = mapa_shared(bar_acce, 0);
+    for (int pt = cid; pt < n_pair_tiles; pt += n_clusters, ++ti) {
+      const int mp = pt / P.n_nt, nt = pt - mp * P.n_nt;
+      const int mt = 2 * mp + (int)rank;
+      const int tx = mt % P.TX, t2 = mt / P.TX, ty = t2 % P.TY, tb = t2 / P.TY;
+      const uint32_t buf = ti & 1u, aph = (ti >> 1) & 1u;
+      const int b = tb * bn + bi, ow = tx * bw + wi, oh = ty * bh + hi;
+      const bool mv = b < P.nb;
+      const size_t orow = (((size_t)b * P.OH + oh) * P.OW + ow) * P.Cout + (size_t)nt * NT;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
+      for (int h0 = 0; h0 < NT; h0 += 128) {
+        uint4 rr[16];
+        if (has_res && mv) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2)
+            if (h0 + j * 8 < NT) ldg256(P.res + orow + h0 + j * 8, rr[j], rr[j + 1]);
+        }
+        if (h0 == 0) { mbar_wait(bar_accf + 8 * buf, aph); tc_fence_after(); }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = h0 + cc * 32;
+          if (c0 < NT) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_wait_ld();
+            if (mv) {
+              const float4* sc4 = reinterpret_cast<const float4*>(sc_s + nt * NT + c0);
+              const float4* bi4 = reinterpret_cast<const float4*>(bi_s + nt * NT + c0);
+              uint4 pk[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 s0 = sc4[2 * g], s1 = sc4[2 * g + 1], o0 = bi4[2 * g], o1 = bi4[2 * g + 1];
+                float y[8];
+                y[0] = fmaf(__uint_as_float(v[g * 8 + 0]), s0.x, o0.x); y[1] = fmaf(__uint_as_float(v[g * 8 + 1]), s0.y, o0.y);
+                y[2] = fmaf(__uint_as_float(v[g * 8 + 2]), s0.z, o0.z); y[3] = fmaf(__uint_as_float(v[g * 8 + 3]), s0.w, o0.w);
+                y[4] = fmaf(__uint_as_float(v[g * 8 + 4]), s1.x, o1.x); y[5] = fmaf(__uint_as_float(v[g * 8 + 5]), s1.y, o1.y);
+                y[6] = fmaf(__uint_as_float(v[g * 8 + 6]), s1.z, o1.z); y[7] = fmaf(__uint_as_float(v[g * 8 + 7]), s1.w, o1.w);
+                if (has_res) {
+                  const uint4 r4 = rr[cc * 4 + g];
+                  y[0] += bf_lo(r4.x); y[1] += bf_hi(r4.x); y[2] += bf_lo(r4.y); y[3] += bf_hi(r4.y);
+                  y[4] += bf_lo(r4.z); y[5] += bf_hi(r4.z); y[6] += bf_lo(r4.w); y[7] += bf_hi(r4.w);
+                }
+                if (P.relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                pk[g] = make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+              }
+              stg256(P.out + orow + c0, pk[0], pk[1]);
+              stg256(P.out + orow + c0 + 16, pk[2], pk[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acce0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // nobody leaves (or frees tensor memory) while the peer may still touch this CTA
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight / parameter packing
 // ------------------------------------------------------------------------------------------------
 // w [Cout][Cin][KH][KW] fp32 -> per (N tile, k-block) swizzled [NT][64] bf16 images; k-block kb covers filter row
@@ -565,6 +776,8 @@ struct ConvLayer {
   uint16_t stt[80];
   KbTaps taps;
   CUtensorMap tmap;
+  int pair = 0;             // CTA-pair kernel (cta_group::2): needs tmap_w, the weight blob as a 2-D tensor {64, rows}
+  CUtensorMap tmap_w;
 };
 
 std::string g_ctx_create_err;
@@ -585,6 +798,7 @@ struct CldContext {
   __nv_bfloat16 *img16 = nullptr, *stem_out = nullptr, *bufX = nullptr, *bufY = nullptr, *bufZ = nullptr, *bufD = nullptr;
   bool loaded = false;
   unsigned long long launches = 0;
+  void* enc = nullptr;                   // cuTensorMapEncodeTiled
   double conv_flops_per_agent = 0.0;     // 2*MAC of the 20 convolutions as executed (padded K included)
 };
 
@@ -725,6 +939,25 @@ int launch_conv(CldContext* c, const ConvLayer& L, int B, cudaStream_t s) {
   memcpy(P.stt, L.stt, sizeof(P.stt));
   const int tiles = P.n_mt * P.n_nt;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  if (L.pair) {
+    const int pair_tiles = ((P.n_mt + 1) / 2) * P.n_nt;
+    int clusters = c->num_sms / 2;
+    if (pair_tiles < clusters) clusters = pair_tiles;
+    const int stage_b = CT_A_BYTES + L.NT * 64;
+    int st = (216 * 1024) / stage_b;
+    P.stages = st > CT_MAX_STAGES ? CT_MAX_STAGES : st;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(CT2_THREADS);
+    cfg.dynamicSmemBytes = (size_t)P.stages * stage_b + CT_TAIL; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_pair_kernel, L.tmap, L.tmap_w, P);
+    if (e != cudaSuccess) return cfail(c, CLD_ERR_CUDA, "launch of conv_pair_kernel failed: %s", cudaGetErrorString(e));
+    ++c->launches;
+    return 0;
+  }
   if (L.w_slots == 1 && L.MT == 1) conv_tma_kernel<1, 1><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
   else if (L.w_slots == 3 && L.MT == 1) conv_tma_kernel<3, 1><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
   else if (L.w_slots == 4 && L.MT == 2) conv_tma_kernel<4, 2><<<grid, CT2_THREADS, smem, s>>>(L.tmap, P);
@@ -757,6 +990,7 @@ int cld_context_create(int max_agents, CldContext** out) {
       enc = (EncodeTiledFn)fn;
     if (!enc) { delete c; return cfail(nullptr, CLD_ERR_CUDA, "cld_context_create: cuTensorMapEncodeTiled is not available from the driver"); }
   }
+  c->enc = (void*)enc;
   // plan: stem, then (conv1, conv2[, downsample]) per BasicBlock
   int li = 0;
   plan_conv(c->conv[li++], IMG_C, 64, 7, 2, 3, 1);
@@ -832,6 +1066,7 @@ int cld_context_create(int max_agents, CldContext** out) {
       fprintf(stderr, "[cld_context] conv %2d: Cin %3d Cout %3d k%d s%d in %3d | NT %3d stages %d x %5.1f KB, %2d stages/tile, grouped %d, MT %d\n", i,
               L.Cin_real, L.Cout, L.KH, L.stride, L.H, L.NT, L.stages, (L.a_bytes + L.w_slots * L.NT * 128) / 1024.0, L.n_st, L.group, L.MT);
   }
+  cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   cudaFuncSetAttribute(conv_tma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   cudaFuncSetAttribute(conv_tma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   cudaFuncSetAttribute(conv_tma_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -875,6 +1110,21 @@ int cld_context_load(CldContext* c, const float* const* p, const int64_t* numels
       if ((rc = calloc_dev(c, &L.wblob, bytes))) return rc;
       if ((rc = calloc_dev(c, &L.scale, L.Cout))) return rc;
       if ((rc = calloc_dev(c, &L.shift, L.Cout))) return rc;
+    }
+    // CTA-pair kernel: the long-K plain-stage layers with N = 256 tiles (the 3x3 convolutions of layers 3 and 4; measured -4..-8 %
+    // per launch, while the short 1x1 / stride-2 launches lose to the pair protocol).  CLD_CTX_PAIR=0 disables it, =2 uses it for
+    // every plain-stage layer with N tiles >= 128.  The weight blob is described as a 2-D tensor whose boxes are the half images
+    // (NT/2 rows) each CTA of a pair stages.
+    L.pair = 0;
+    const int pair_mode = env_int("CLD_CTX_PAIR", 1);
+    if (!L.stem && !L.group && ((pair_mode == 1 && L.NT == 256 && L.n_kb >= 36) || (pair_mode >= 2 && L.NT >= 128))) {
+      cuuint64_t dims[2] = {64, (cuuint64_t)L.n_nt * L.n_kb * L.NT};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, (cuuint32_t)(L.NT / 2)}, es[2] = {1, 1};
+      const CUresult r = ((EncodeTiledFn)c->enc)(&L.tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)L.wblob, dims, strides, box, es,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      L.pair = r == CUDA_SUCCESS ? 1 : 0;
     }
     const long long total = (long long)L.n_nt * L.n_kb * L.NT * 64;
     ctx_pack_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(L.wblob, w, L.Cout, L.Cin_real, L.KH, L.KW, L.NT, L.n_kb, L.stem, total,
