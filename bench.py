@@ -207,6 +207,25 @@ def context_encoder_rate(dev, agents=1024, iters=5, warmup=3, cpu_agents=256):
     hms = e0.elapsed_time(e1) / iters
     out["from_history"] = {"value": agents / hms * 1e3, "unit": "agents/s", "ms": hms, "agents_per_raster": 16,
                            "bytes_in_per_agent": 3 * 224 * 224 * 4 + 16 * 31 * 9 + 36}
+    # end to end through the public API from pinned HOST buffers: H2D of the un-rasterised inputs + forward_history + D2H of cond_feat
+    host = {"maps": maps.cpu().pin_memory(), "hpos": hpos.cpu().pin_memory(), "hmask": hmask.cpu().pin_memory(),
+            "rfa": b2["raster_from_agent"].cpu().pin_memory(), "history_positions": batch["history_positions"].cpu().pin_memory(),
+            "history_yaws": batch["history_yaws"].cpu().pin_memory(), "curr_speed": batch["curr_speed"].cpu().pin_memory()}
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        o = ce.forward_history({"raster_from_agent": d["rfa"], "history_positions": d["history_positions"], "history_yaws": d["history_yaws"],
+                                "curr_speed": d["curr_speed"]}, d["maps"], d["hpos"], d["hmask"])
+        return o["cond_feat"].cpu()
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    ems = (time.perf_counter() - t0) / 3 * 1e3
+    out["from_history"]["e2e"] = {"value": agents / ems * 1e3, "unit": "agents/s", "ms": ems,
+                                  "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": agents * 256 * 4}
     ce.close()
     # the reference's CPU path for the same row, timed beside it: the oracle restatement of ContextEncoder.forward (bit-equal to the
     # real reference, oracle/make_golden.py) on a bounded sample with all host threads
