@@ -657,7 +657,7 @@ __global__ void ctx_tap_kernel(const __nv_bfloat16* __restrict__ in, float* __re
 // ------------------------------------------------------------------------------------------------
 // head: avg-pool + fc + agent-state MLP + process_cond MLP, 8 agents per CTA, fp32
 // ------------------------------------------------------------------------------------------------
-constexpr int HD_AG = 8, HD_THREADS = 320, HD_LD = 512;
+constexpr int HD_THREADS = 320, HD_LD = 512;       // AG agents per CTA (template): 8 amortises the weight reads of large batches, 1 fills the SMs for small ones
 struct HeadP {
   const __nv_bfloat16* feat;      // [B,7,7,512] layer4 output
   const float* curr;              // [B,4]
@@ -672,6 +672,7 @@ struct HeadP {
 
 // out[a][n] = sum_k in[a][k] * Wt[k][n] + b[n]   (thread = n, 8 agents share every weight read; K is a multiple of 4 and the
 // activations are read as broadcast float4 -- two shared-memory instructions per k instead of eight)
+template <int HD_AG>
 __device__ __forceinline__ void hd_linear(const float* in, int ldi, const float* __restrict__ Wt, const float* __restrict__ b, float* out,
                                           int ldo, int K, int N) {
   const int n = threadIdx.x;
@@ -679,7 +680,7 @@ __device__ __forceinline__ void hd_linear(const float* in, int ldi, const float*
     float acc[HD_AG];
 #pragma unroll
     for (int a = 0; a < HD_AG; ++a) acc[a] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < K; k += 4) {
       const float w0 = __ldg(Wt + (size_t)k * N + n), w1 = __ldg(Wt + (size_t)(k + 1) * N + n);
       const float w2 = __ldg(Wt + (size_t)(k + 2) * N + n), w3 = __ldg(Wt + (size_t)(k + 3) * N + n);
@@ -696,6 +697,7 @@ __device__ __forceinline__ void hd_linear(const float* in, int ldi, const float*
   __syncthreads();
 }
 // LayerNorm (eps 1e-5, biased variance) + ReLU in place; warp a handles agent a
+template <int HD_AG>
 __device__ __forceinline__ void hd_ln_relu(float* x, int ld, const float* __restrict__ g, const float* __restrict__ e, int N) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < HD_AG) {
@@ -713,6 +715,7 @@ __device__ __forceinline__ void hd_ln_relu(float* x, int ld, const float* __rest
   __syncthreads();
 }
 
+template <int HD_AG>
 __global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
   __shared__ __align__(16) float bufA[HD_AG * HD_LD], bufB[HD_AG * HD_LD];
   const int a0 = blockIdx.x * HD_AG, tid = threadIdx.x;
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
   }
   __syncthreads();
   // fc 512 -> 256 into bufB[a][64 + n]  (the concat layout: [state 0..63 | map 64..319])
-  hd_linear(bufA, HD_LD, P.fcw, P.fcb, bufB + 64, HD_LD, 512, 256);
+  hd_linear<HD_AG>(bufA, HD_LD, P.fcw, P.fcb, bufB + 64, HD_LD, 512, 256);
   if (P.map_feat != nullptr) {
     for (int i = tid; i < HD_AG * 256; i += HD_THREADS) {
       const int a = i >> 8, n = i & 255;
@@ -741,22 +744,22 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_head_kernel(const HeadP P) {
   if (tid < HD_AG * 4) { const int a = tid >> 2, ag = min(a0 + a, P.B - 1); bufA[a * HD_LD + (tid & 3)] = P.curr[(size_t)ag * 4 + (tid & 3)]; }
   __syncthreads();
   float* t1 = bufA + 64;          // scratch columns inside bufA (row stride HD_LD)
-  hd_linear(bufA, HD_LD, P.s0w, P.s0b, t1, HD_LD, 4, 64);
-  hd_ln_relu(t1, HD_LD, P.s0g, P.s0e, 64);
+  hd_linear<HD_AG>(bufA, HD_LD, P.s0w, P.s0b, t1, HD_LD, 4, 64);
+  hd_ln_relu<HD_AG>(t1, HD_LD, P.s0g, P.s0e, 64);
   float* t2 = bufA + 128;
-  hd_linear(t1, HD_LD, P.s1w, P.s1b, t2, HD_LD, 64, 64);
-  hd_ln_relu(t2, HD_LD, P.s1g, P.s1e, 64);
-  hd_linear(t2, HD_LD, P.s2w, P.s2b, bufB, HD_LD, 64, 64);            // state feature -> bufB[a][0..63]
+  hd_linear<HD_AG>(t1, HD_LD, P.s1w, P.s1b, t2, HD_LD, 64, 64);
+  hd_ln_relu<HD_AG>(t2, HD_LD, P.s1g, P.s1e, 64);
+  hd_linear<HD_AG>(t2, HD_LD, P.s2w, P.s2b, bufB, HD_LD, 64, 64);            // state feature -> bufB[a][0..63]
   // process_cond_mlp on bufB[a][0..319]
-  hd_linear(bufB, HD_LD, P.p0w, P.p0b, bufA, HD_LD, 320, 320);
-  hd_ln_relu(bufA, HD_LD, P.p0g, P.p0e, 320);
-  hd_linear(bufA, HD_LD, P.p1w, P.p1b, bufB, HD_LD, 320, 320);
-  hd_ln_relu(bufB, HD_LD, P.p1g, P.p1e, 320);
-  hd_linear(bufB, HD_LD, P.p2w, P.p2b, bufA, HD_LD, 320, 256);
-  hd_ln_relu(bufA, HD_LD, P.p2g, P.p2e, 256);
-  hd_linear(bufA, HD_LD, P.p3w, P.p3b, bufB, HD_LD, 256, 256);
-  hd_ln_relu(bufB, HD_LD, P.p3g, P.p3e, 256);
-  hd_linear(bufB, HD_LD, P.p4w, P.p4b, bufA, HD_LD, 256, 256);
+  hd_linear<HD_AG>(bufB, HD_LD, P.p0w, P.p0b, bufA, HD_LD, 320, 320);
+  hd_ln_relu<HD_AG>(bufA, HD_LD, P.p0g, P.p0e, 320);
+  hd_linear<HD_AG>(bufA, HD_LD, P.p1w, P.p1b, bufB, HD_LD, 320, 320);
+  hd_ln_relu<HD_AG>(bufB, HD_LD, P.p1g, P.p1e, 320);
+  hd_linear<HD_AG>(bufB, HD_LD, P.p2w, P.p2b, bufA, HD_LD, 320, 256);
+  hd_ln_relu<HD_AG>(bufA, HD_LD, P.p2g, P.p2e, 256);
+  hd_linear<HD_AG>(bufA, HD_LD, P.p3w, P.p3b, bufB, HD_LD, 256, 256);
+  hd_ln_relu<HD_AG>(bufB, HD_LD, P.p3g, P.p3e, 256);
+  hd_linear<HD_AG>(bufB, HD_LD, P.p4w, P.p4b, bufA, HD_LD, 256, 256);
   for (int i = tid; i < HD_AG * 256; i += HD_THREADS) {
     const int a = i >> 8, n = i & 255;
     if (a0 + a < P.B) P.cond[(size_t)(a0 + a) * 256 + n] = bufA[a * HD_LD + n];
@@ -1253,7 +1256,13 @@ int forward_impl(CldContext* c, const RasterSrc& src, const float* curr_states, 
     hp.p0w = w[12]; hp.p0b = w[13]; hp.p0g = w[14]; hp.p0e = w[15]; hp.p1w = w[16]; hp.p1b = w[17]; hp.p1g = w[18]; hp.p1e = w[19];
     hp.p2w = w[20]; hp.p2b = w[21]; hp.p2g = w[22]; hp.p2e = w[23]; hp.p3w = w[24]; hp.p3b = w[25]; hp.p3g = w[26]; hp.p3e = w[27];
     hp.p4w = w[28]; hp.p4b = w[29];
-    ctx_head_kernel<<<(nb + HD_AG - 1) / HD_AG, HD_THREADS, 0, s>>>(hp);
+    // agents per CTA: enough CTAs to fill the SMs for small batches, weight reads amortised over 8 agents for large ones
+    const int ag = nb <= c->num_sms ? 1 : (nb <= 2 * c->num_sms ? 2 : (nb <= 8 * c->num_sms ? 4 : 8));
+    const int hgrid = (nb + ag - 1) / ag;
+    if (ag == 1) ctx_head_kernel<1><<<hgrid, HD_THREADS, 0, s>>>(hp);
+    else if (ag == 2) ctx_head_kernel<2><<<hgrid, HD_THREADS, 0, s>>>(hp);
+    else if (ag == 4) ctx_head_kernel<4><<<hgrid, HD_THREADS, 0, s>>>(hp);
+    else ctx_head_kernel<8><<<hgrid, HD_THREADS, 0, s>>>(hp);
     CTX_LAUNCH_OK(c, "ctx_head_kernel");
   }
   return 0;
