@@ -175,3 +175,26 @@ def test_forward_history_equals_forward_on_the_rasterised_image(gold):
     with torch.no_grad():
         want = O.context_encode(sd, dict(batch, image=img))["cond_feat"]
     assert rel(fused["cond_feat"], want) < 2e-2
+
+
+def test_context_kernel_variants_agree(gold):
+    """The debug switches select other kernel variants for the same layers (single-CTA vs CTA-pair `cta_group::2`, plain vs
+    grouped stages, N tile 128 vs 256): every variant must reproduce the default result (same bf16 operands and fp32
+    accumulation; only the accumulation grouping differs)."""
+    from cld_b200.synthetic import make_context_batch
+    batch = {k: v.cuda() for k, v in make_context_batch(37, seed=23).items()}
+    g, sd, ce = _build(gold)
+    base = ce(batch)["cond_feat"].clone()
+    torch.cuda.synchronize()
+    for env in ({"CLD_CTX_PAIR": "0"}, {"CLD_CTX_PAIR": "2"}, {"CLD_CTX_GROUP": "0"}, {"CLD_CTX_NT": "128", "CLD_CTX_PAIR": "2"}):
+        os.environ.update(env)
+        try:
+            _, _, ce2 = _build(gold)
+            out = ce2(batch)["cond_feat"]
+            torch.cuda.synchronize()
+        finally:
+            for k in env:
+                del os.environ[k]
+        r = rel(out, base)
+        print("context variant %s: rel vs default %.3e" % (env, r))
+        assert r < 2e-3, (env, r)
