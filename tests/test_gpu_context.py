@@ -198,3 +198,23 @@ def test_context_kernel_variants_agree(gold):
         r = rel(out, base)
         print("context variant %s: rel vs default %.3e" % (env, r))
         assert r < 2e-3, (env, r)
+
+
+def test_context_permutation_equivariance_at_scale(gold):
+    """Size-independent property at a large batch (700 agents: several head variants, many GEMM tiles, ragged image boxes):
+    permuting the agents permutes the features, bit for bit, and a slice of the batch reproduces the same rows."""
+    g, sd, ce = _build(gold, max_agents=700)
+    B = 700
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    img = (torch.rand(B, 34, 224, 224, device="cuda", generator=gen) < 0.03).float()
+    batch = {"image": img, "history_positions": torch.randn(B, 31, 2, device="cuda", generator=gen),
+             "history_yaws": torch.randn(B, 31, 1, device="cuda", generator=gen) * 0.1, "curr_speed": torch.rand(B, device="cuda", generator=gen) * 10}
+    base = ce(batch)["cond_feat"].clone()
+    perm = torch.randperm(B, device="cuda", generator=gen)
+    out = ce({k: v[perm].contiguous() for k, v in batch.items()})["cond_feat"]
+    torch.cuda.synchronize()
+    assert torch.isfinite(base).all()
+    assert torch.equal(out, base[perm])
+    sub = ce({k: v[123:260].contiguous() for k, v in batch.items()})["cond_feat"]
+    torch.cuda.synchronize()
+    assert torch.equal(sub, base[123:260])
