@@ -77,7 +77,7 @@ def _load():
     lib.cld_indicators.argtypes = [vp, vp, C.POINTER(CldScene), vp, vp, vp, i32, vp]
     lib.cld_guidance_step.argtypes = [vp, vp, vp, vp, C.POINTER(CldScene), C.POINTER(CldGuidanceConfig), vp, vp, vp,
                                       i32, vp]
-    lib.cld_sample.argtypes = [vp, vp, vp, u64, vp, vp, C.POINTER(CldScene), C.POINTER(CldGuidanceConfig), i32, i32,
+    lib.cld_sample.argtypes = [vp, vp, vp, u64, C.c_int64, vp, vp, C.POINTER(CldScene), C.POINTER(CldGuidanceConfig), i32, i32,
                                vp, vp, C.POINTER(C.c_int), vp, vp, vp, i32, vp]
     lib.cld_tc_selftest.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.cld_launch_count.argtypes = [vp]

@@ -88,13 +88,13 @@ class ContextEncoder(nn.Module):
 
     # ------------------------------------------------------------------ engine plumbing
     def invalidate(self):
-        """Call after changing parameters in place (load_state_dict does it automatically)."""
+        """Force a re-pack of the parameters at the next call (normally not needed, see `_weights_signature`)."""
         self._dirty = True
 
-    def load_state_dict(self, *a, **k):
-        out = super().load_state_dict(*a, **k)
-        self._dirty = True
-        return out
+    def _weights_signature(self):
+        """(identity, in-place version) of every parameter / buffer: changes on any load_state_dict (also a parent module's,
+        which never calls this module's own load_state_dict), optimizer step or manual copy_."""
+        return hash(tuple((id(v), v._version) for v in list(self.parameters()) + list(self.buffers())))
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -133,7 +133,9 @@ class ContextEncoder(nn.Module):
                     self._handle = None
                     self._err("cld_context_create")
             self._handle, self._handle_dev, self._dirty, self._capacity = h, p.device, True, need
-        if self._dirty:
+        sig = self._weights_signature()
+        if self._dirty or sig != getattr(self, "_loaded_sig", None):
+            self._loaded_sig = sig
             ws = [w.detach().to(torch.float32).contiguous() for w in self.weight_list()]
             ptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
             numels = (C.c_int64 * len(ws))(*[w.numel() for w in ws])

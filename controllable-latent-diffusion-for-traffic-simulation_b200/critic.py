@@ -3,9 +3,9 @@ import torch
 
 
 def _scene_of(dm, batch, rows, num_samp):
+    from .keys import agents_per_scene
     B = rows // num_samp
-    sidx = batch.get('scene_index')
-    A = int((sidx == sidx[0]).sum().item()) if sidx is not None else B
+    A = agents_per_scene(batch.get('scene_index'), B)
     return dm.engine(rows).make_scene(batch, B // A, A, num_samp)
 
 

@@ -1,6 +1,7 @@
 // C ABI of libcld_b200.so (see include/cld_b200.h): handle, weight packing, dispatch, sampler loop.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -139,6 +140,10 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   // bf16-precision mode runs the LSTM decoder (forward and BPTT) on the tensor pipe; CLD_LSTM_SIMT=1 keeps the fp32 SIMT kernels
   h->use_lstm_tc = cfg->precision == CLD_PREC_BF16 && cfg->hidden == 64 && getenv("CLD_LSTM_SIMT") == nullptr;
+  h->env_lstm_bwd_simt = getenv("CLD_LSTM_BWD_SIMT") != nullptr;
+  h->env_guidance_nofork = getenv("CLD_GUIDANCE_NOFORK") != nullptr;
+  h->env_lstm_prof = getenv("CLD_LSTM_PROF") != nullptr;
+  if (const char* e = getenv("CLD_LSTM_PF")) h->env_lstm_pf = atoi(e);
   const int T = cfg->horizon;
   const size_t MR = cfg->max_rows;
   size_t ae = (size_t)T * cfg->dims[0];
@@ -394,14 +399,14 @@ int cld_posterior_step(CldHandle* h, const float* x, const float* eps, const flo
   if (!x || !eps) return fail(h, CLD_ERR_ARG, "null argument");
   if (!noise && x_out && sampler == CLD_SAMPLER_DDPM && t != 0)
     return fail(h, CLD_ERR_ARG, "noise tensor required for a DDPM step with t != 0");
-  return posterior_step(h, x, eps, noise, 0, 0, t, t_next, sampler, x_out, mean_out, R, (cudaStream_t)stream);
+  return posterior_step(h, x, eps, noise, 0, 0, 0, t, t_next, sampler, x_out, mean_out, R, (cudaStream_t)stream);
 }
 
 int cld_add_noise(CldHandle* h, const float* mean, const float* noise, int t, float* x_out, int R, void* stream) {
   int rc = check_rows(h, R);
   if (rc) return rc;
   if (!mean || !x_out || (!noise && t != 0)) return fail(h, CLD_ERR_ARG, "null argument");
-  return add_noise(h, mean, noise, 0, 0, t, x_out, R, (cudaStream_t)stream);
+  return add_noise(h, mean, noise, 0, 0, 0, t, x_out, R, (cudaStream_t)stream);
 }
 
 int cld_decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr, float* act_out,
@@ -434,8 +439,8 @@ static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* co
   }
   if ((rc = decode_rollout_h0(h, z_mean, h0, curr, h->ws_act, h->ws_traj, true, R, s))) return rc;
   // bf16 mode without per-row loss output (the sampler): the two loss kernels run concurrently, each into its own buffer
-  float* dmap = (h->use_lstm_tc && !loss_out && g->w_map_collision != 0.f && !getenv("CLD_LSTM_BWD_SIMT") &&
-                 !getenv("CLD_GUIDANCE_NOFORK")) ? h->ws_dtraj2 : nullptr;
+  float* dmap = (h->use_lstm_tc && !loss_out && g->w_map_collision != 0.f && !h->env_lstm_bwd_simt &&
+                 !h->env_guidance_nofork) ? h->ws_dtraj2 : nullptr;
   if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, dmap, loss_out, R, s))) return rc;
   return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, dmap, g, z_out, grad_out, R, s);
 }
@@ -448,11 +453,13 @@ int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, cons
   return guidance_step_impl(h, z_mean, cond, nullptr, curr, scene, g, z_out, grad_out, loss_out, R, (cudaStream_t)stream);
 }
 
-int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t seed, const float* cond,
+int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t seed, int64_t row_offset, const float* cond,
                const float* curr, const CldScene* scene, const CldGuidanceConfig* g, int stride, int sampler,
                float* x0_out, float* x1_out, int* x1_valid, float* traj_out, uint8_t* offroad_out, float* coll_out,
                int R, void* stream) {
-  if (!h || !x_init || !cond) return fail(h, CLD_ERR_ARG, "null argument");
+  if (!h || !cond) return fail(h, CLD_ERR_ARG, "null argument");
+  if (!x_init && seed == 0) return fail(h, CLD_ERR_ARG, "either x_init or a non-zero seed (in-kernel Philox initial state) is required");
+  if (row_offset < 0) return fail(h, CLD_ERR_ARG, "row_offset must be >= 0");
   if (R < 1 || stride < 1) return fail(h, CLD_ERR_ARG, "bad R / stride");
   if ((traj_out || offroad_out || coll_out || g) && !curr) return fail(h, CLD_ERR_ARG, "curr states required");
   if ((offroad_out || coll_out || g) && !scene) return fail(h, CLD_ERR_ARG, "scene tensors required");
@@ -496,7 +503,14 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     const float* condc = cond + (size_t)r0 * c.cond_dim;
     const float* currc = curr ? curr + (size_t)r0 * 4 : nullptr;
     float* x = h->ws_x;
-    CLD_CUDA_OK(h, cudaMemcpyAsync(x, x_init + r0 * row_e, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // Philox counters are indexed by the GLOBAL row id (row_offset + r0 + local row): results do not depend on how rows are
+    // sharded over ranks, chunked by max_rows or split into lanes
+    const uint64_t idx_base = ((uint64_t)row_offset + (uint64_t)r0) * (uint64_t)(row_e / 4);
+    if (x_init) {
+      CLD_CUDA_OK(h, cudaMemcpyAsync(x, x_init + r0 * row_e, Rc * row_e * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else if ((rc = philox_fill(h, seed, ~0ull, idx_base, x, Rc, s))) {
+      return rc;
+    }
     // bf16 path: the cond half of every block's time/cond projection is step-invariant -> once per chunk
     const bool split_bias = (c.precision == CLD_PREC_BF16);
     if (split_bias && (rc = unet_cond_bias(h, condc, Rc, s))) return rc;
@@ -528,14 +542,14 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
       }
       if ((rc = prof_end(h, s))) return rc;
       const bool guided = (g != nullptr) && i != 0;
-      const uint64_t seq = ((uint64_t)k << 32) ^ (uint64_t)r0;
+      const uint64_t seq = (uint64_t)k;
       if (!guided) {
         if ((rc = prof_begin(h, 1, s))) return rc;
-        if ((rc = posterior_step(h, x, h->ws_eps, nz, seed, seq, i, i_next, sampler, x, nullptr, Rc, s))) return rc;
+        if ((rc = posterior_step(h, x, h->ws_eps, nz, seed, seq, idx_base, i, i_next, sampler, x, nullptr, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
       } else {
         if ((rc = prof_begin(h, 1, s))) return rc;
-        if ((rc = posterior_step(h, x, h->ws_eps, nullptr, 0, 0, i, i_next, sampler, nullptr, h->ws_mean, Rc, s))) return rc;
+        if ((rc = posterior_step(h, x, h->ws_eps, nullptr, 0, 0, 0, i, i_next, sampler, nullptr, h->ws_mean, Rc, s))) return rc;
         if ((rc = prof_end(h, s))) return rc;
         if ((rc = prof_begin(h, 2, s))) return rc;
         // DDIM (eta = 0) injects no noise: the guidance update writes the next state directly
@@ -544,7 +558,7 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
         if ((rc = prof_end(h, s))) return rc;
         if (!noiseless) {
           if ((rc = prof_begin(h, 1, s))) return rc;
-          if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, i, x, Rc, s))) return rc;
+          if ((rc = add_noise(h, h->ws_mean, nz, seed, seq, idx_base, i, x, Rc, s))) return rc;
           if ((rc = prof_end(h, s))) return rc;
         }
       }

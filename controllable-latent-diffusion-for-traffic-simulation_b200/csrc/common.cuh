@@ -121,6 +121,9 @@ struct CldHandle {
   // tensor-core LSTM decoder (opaque, owned by kernels_lstm_tc.cu); used when cfg.precision == CLD_PREC_BF16
   void* lstm_tc = nullptr;
   bool use_lstm_tc = false;
+  // debug switches, read from the environment ONCE at cld_create (never inside the step path)
+  bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false;
+  int env_lstm_pf = 3;
 };
 
 namespace cld {
@@ -160,11 +163,14 @@ int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s);   //
 int unet_time_vec(CldHandle* h, int t, cudaStream_t s);                        // -> h->tvec
 int unet_time_vec_to(CldHandle* h, int t, float* dst, cudaStream_t s);
 // ---- kernels_step.cu
+// in-kernel noise: Philox4x32-10(key = seed, counter = (idx_base + element quad, seq)); idx_base = GLOBAL row id * T*D/4 and
+// seq = position of the step in the schedule, so the draw of a row does not depend on sharding / chunking / lanes
 int posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise, uint64_t seed,
-                   uint64_t seq, int t, int t_next, int sampler, float* x_out, float* mean_out, int R,
+                   uint64_t seq, uint64_t idx_base, int t, int t_next, int sampler, float* x_out, float* mean_out, int R,
                    cudaStream_t s);
-int add_noise(CldHandle* h, const float* mean, const float* noise, uint64_t seed, uint64_t seq, int t,
+int add_noise(CldHandle* h, const float* mean, const float* noise, uint64_t seed, uint64_t seq, uint64_t idx_base, int t,
               float* x_out, int R, cudaStream_t s);
+int philox_fill(CldHandle* h, uint64_t seed, uint64_t seq, uint64_t idx_base, float* out, int R, cudaStream_t s);
 int fill_t(CldHandle* h, int64_t* t, int value, int R, cudaStream_t s);
 // ---- kernels_decode.cu
 int decode_rollout(CldHandle* h, const float* z, const float* cond, const float* curr, float* act_out,

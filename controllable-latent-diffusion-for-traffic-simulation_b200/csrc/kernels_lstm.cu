@@ -579,7 +579,7 @@ int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act,
                             const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   DecoderW& w = h->dec;
   int rc;
-  if (h->use_lstm_tc && !getenv("CLD_LSTM_BWD_SIMT")) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, dtraj2, g, z_out, grad_out, R, s);
+  if (h->use_lstm_tc && !h->env_lstm_bwd_simt) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, dtraj2, g, z_out, grad_out, R, s);
   if (dtraj2) return fail(h, CLD_ERR_STATE, "internal: split d(traj) buffers are only handled by the tensor-core backward");
   if ((rc = lstm2_prepare(h, s))) return rc;
   const CldConfig& c = h->cfg;

@@ -892,7 +892,7 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
   a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   const int grid = (R + LT_RB - 1) / LT_RB;
   if (save) lstm_decode_tc_kernel<true, false><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
-  else if (getenv("CLD_LSTM_PROF")) lstm_decode_tc_kernel<false, true><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
+  else if (h->env_lstm_prof) lstm_decode_tc_kernel<false, true><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
   else lstm_decode_tc_kernel<false, false><<<grid, LT_THREADS, lf_smem_req(), s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_decode_tc_kernel");
   return 0;
@@ -908,8 +908,8 @@ int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* ac
   a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.dtraj2 = dtraj2; a.stash = h->stash; a.wblob = st->wbwd;
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
-  { const char* e = getenv("CLD_LSTM_PF"); a.pf = e ? atoi(e) : 3; }
-  if (getenv("CLD_LSTM_PROF")) lstm_backward_tc_kernel<true><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lb_smem_req(a.T), s>>>(a);
+  a.pf = h->env_lstm_pf;
+  if (h->env_lstm_prof) lstm_backward_tc_kernel<true><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lb_smem_req(a.T), s>>>(a);
   else lstm_backward_tc_kernel<false><<<(R + LT_RB - 1) / LT_RB, LB_THREADS, lb_smem_req(a.T), s>>>(a);
   CLD_LAUNCH_OK(h, "lstm_backward_tc_kernel");
   return 0;

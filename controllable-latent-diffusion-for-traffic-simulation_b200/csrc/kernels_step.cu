@@ -46,7 +46,7 @@ struct StepCoef {
 
 __global__ void __launch_bounds__(256) posterior_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                                                              const float4* __restrict__ noise, uint64_t seed,
-                                                             uint64_t seq, StepCoef k, float4* __restrict__ x_out,
+                                                             uint64_t seq, uint64_t idx_base, StepCoef k, float4* __restrict__ x_out,
                                                              float4* __restrict__ mean_out, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 xv = x[i], ev = eps[i], m;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const float4* __res
     if (x_out) {
       float4 o = m;
       if (k.sigma != 0.f) {
-        float4 nz = noise ? noise[i] : philox_normal4(seed, seq, i);
+        float4 nz = noise ? noise[i] : philox_normal4(seed, seq, idx_base + i);
         o.x += k.sigma * nz.x; o.y += k.sigma * nz.y; o.z += k.sigma * nz.z; o.w += k.sigma * nz.w;
       }
       x_out[i] = o;
@@ -69,16 +69,22 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(const float4* __res
 }
 
 __global__ void __launch_bounds__(256) add_noise_kernel(const float4* __restrict__ mean, const float4* __restrict__ noise,
-                                                        uint64_t seed, uint64_t seq, float sigma,
+                                                        uint64_t seed, uint64_t seq, uint64_t idx_base, float sigma,
                                                         float4* __restrict__ x_out, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 o = mean[i];
     if (sigma != 0.f) {
-      float4 nz = noise ? noise[i] : philox_normal4(seed, seq, i);
+      float4 nz = noise ? noise[i] : philox_normal4(seed, seq, idx_base + i);
       o.x += sigma * nz.x; o.y += sigma * nz.y; o.z += sigma * nz.z; o.w += sigma * nz.w;
     }
     x_out[i] = o;
   }
+}
+
+// x_init drawn in-kernel: the same Philox stream family, sequence id ~0 (never a step index)
+__global__ void __launch_bounds__(256) philox_fill_kernel(uint64_t seed, uint64_t seq, uint64_t idx_base, float4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = philox_normal4(seed, seq, idx_base + i);
 }
 
 __global__ void fill_t_kernel(int64_t* t, int64_t v, int n) {
@@ -93,7 +99,7 @@ static int grid_for(const CldHandle* h, size_t n4) {
 }
 
 int posterior_step(CldHandle* h, const float* x, const float* eps, const float* noise, uint64_t seed, uint64_t seq,
-                   int t, int t_next, int sampler, float* x_out, float* mean_out, int R, cudaStream_t s) {
+                   uint64_t idx_base, int t, int t_next, int sampler, float* x_out, float* mean_out, int R, cudaStream_t s) {
   const Schedule& sc = h->sched;
   if (!sc.loaded) return fail(h, CLD_ERR_STATE, "schedule not set");
   if (t < 0 || t >= (int)sc.x_t_cof.size() || t_next >= (int)sc.x_t_cof.size())
@@ -110,21 +116,28 @@ int posterior_step(CldHandle* h, const float* x, const float* eps, const float* 
   size_t n = (size_t)R * h->cfg.horizon * h->cfg.latent_dim;
   if (n % 4) return fail(h, CLD_ERR_ARG, "R*T*D must be a multiple of 4");
   posterior_step_kernel<<<grid_for(h, n / 4), 256, 0, s>>>((const float4*)x, (const float4*)eps, (const float4*)noise,
-                                                           seed, seq, k, (float4*)x_out, (float4*)mean_out, n / 4);
+                                                           seed, seq, idx_base, k, (float4*)x_out, (float4*)mean_out, n / 4);
   CLD_LAUNCH_OK(h, "posterior_step_kernel");
   return 0;
 }
 
-int add_noise(CldHandle* h, const float* mean, const float* noise, uint64_t seed, uint64_t seq, int t, float* x_out,
+int add_noise(CldHandle* h, const float* mean, const float* noise, uint64_t seed, uint64_t seq, uint64_t idx_base, int t, float* x_out,
               int R, cudaStream_t s) {
   const Schedule& sc = h->sched;
   if (!sc.loaded) return fail(h, CLD_ERR_STATE, "schedule not set");
   if (t < 0 || t >= (int)sc.logvar.size()) return fail(h, CLD_ERR_ARG, "step index out of range: t=%d", t);
   float sigma = (t == 0) ? 0.f : expf(0.5f * sc.logvar[t]);
   size_t n = (size_t)R * h->cfg.horizon * h->cfg.latent_dim;
-  add_noise_kernel<<<grid_for(h, n / 4), 256, 0, s>>>((const float4*)mean, (const float4*)noise, seed, seq, sigma,
+  add_noise_kernel<<<grid_for(h, n / 4), 256, 0, s>>>((const float4*)mean, (const float4*)noise, seed, seq, idx_base, sigma,
                                                       (float4*)x_out, n / 4);
   CLD_LAUNCH_OK(h, "add_noise_kernel");
+  return 0;
+}
+
+int philox_fill(CldHandle* h, uint64_t seed, uint64_t seq, uint64_t idx_base, float* out, int R, cudaStream_t s) {
+  size_t n = (size_t)R * h->cfg.horizon * h->cfg.latent_dim;
+  philox_fill_kernel<<<grid_for(h, n / 4), 256, 0, s>>>(seed, seq, idx_base, (float4*)out, n / 4);
+  CLD_LAUNCH_OK(h, "philox_fill_kernel");
   return 0;
 }
 

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .engine import Engine
+from .keys import agents_per_scene
 
 
 class _Slot(nn.Module):
@@ -160,6 +160,8 @@ class DmModel(nn.Module):
         self._engine = None
         self._engine_key = None
         self._decoder_sd = None
+        self._decoder_mod = None          # weakref to the VAE's lstm_dec container (VaeModel.bind)
+        self._loaded_sig = None
 
     def _create_dynamics(self):
         if str(self._dynamics_type) in ("Unicycle", "DynType.UNICYCLE"):
@@ -170,24 +172,34 @@ class DmModel(nn.Module):
             self.dyn = None
 
     # ------------------------------------------------------------------ engine management
-    def attach_decoder(self, lstm_dec_state_dict):
-        """Give the sampler the VAE decoder (needed for guidance and for fused decode+rollout)."""
+    def attach_decoder(self, lstm_dec_state_dict, module=None):
+        """Give the sampler the VAE decoder (needed for guidance and for fused decode+rollout).  With `module` (the
+        `lstm_dec` container, passed by VaeModel.bind) later changes of its parameters -- a parent-level
+        load_state_dict, an optimizer step -- are noticed and re-read, see `_weights_signature`."""
+        import weakref
         self._decoder_sd = {k: v.detach().clone() for k, v in lstm_dec_state_dict.items()}
-        if self._engine is not None:
-            self._engine.load_decoder(self._decoder_sd)
-        for e in self._lane_engines.values():
-            e.load_decoder(self._decoder_sd)
-
-    def invalidate(self):
-        """Call after changing parameters in place (load_state_dict does it automatically)."""
+        if module is not None:
+            self._decoder_mod = weakref.ref(module)
         self._engine_key = None
 
-    def load_state_dict(self, *a, **k):
-        out = super().load_state_dict(*a, **k)
-        self.invalidate()
-        return out
+    def invalidate(self):
+        """Force a re-read of all parameters at the next call (normally not needed: see `_weights_signature`)."""
+        self._engine_key = None
+
+    def _weights_signature(self):
+        """The engine holds a packed SNAPSHOT of the parameters.  Every in-place change of a tensor (Module.load_state_dict
+        at any level of the module tree -- Lightning's load_from_checkpoint recurses through _load_from_state_dict and never
+        calls a child's load_state_dict --, optimizer steps, manual copy_) bumps its `_version`; identity covers `.data =`
+        / re-assignment.  The engine is rebuilt whenever the signature differs from the one it was packed from."""
+        sig = [(id(p), p._version) for p in self.model.parameters()]
+        sig += [(id(b), b._version) for b in self.buffers()]
+        dec = self._decoder_mod() if self._decoder_mod is not None else None
+        if dec is not None:
+            sig += [(id(p), p._version) for p in dec.parameters()]
+        return hash(tuple(sig))
 
     def _build_engine(self, max_rows, dev):
+        from .engine import Engine          # maps libcld_b200.so; raises when it is missing (no fallback)
         if self.dyn is None:
             raise RuntimeError("only the Unicycle dynamics are implemented")
         eng = Engine(horizon=self.horizon, latent_dim=self.latent_size, cond_dim=self.cond_dim,
@@ -210,8 +222,14 @@ class DmModel(nn.Module):
         if rows > self._max_rows:
             self._max_rows = min(int(rows), 65536)      # cld_sample chunks anything larger
         need = max(self._max_rows, 1)
-        key = (str(dev), need, self._precision)
+        sig = self._weights_signature()
+        key = (str(dev), need, self._precision, sig)
         if self._engine is None or self._engine_key != key:
+            dec = self._decoder_mod() if self._decoder_mod is not None else None
+            if dec is not None:              # re-read the live decoder parameters
+                from .keys import DECODER_KEYS
+                dsd = dec.state_dict()
+                self._decoder_sd = {k: dsd[k].detach().clone() for k in DECODER_KEYS}
             if self._engine is not None:
                 self._engine.close()
             for e in self._lane_engines.values():
@@ -241,7 +259,7 @@ class DmModel(nn.Module):
 
     def sample_traj(self, data_batch, algo_config, aux_info, *, noise=None, x_init=None, sampler="ddpm",
                     guidance=None, seed=None, use_device_rng=False, want_traj=False, want_indicators=False,
-                    agents_per_scene=None):
+                    agents_per_scene=None, row_offset=0):
         B = data_batch['history_positions'].size()[0]
         N = algo_config.num_samp
         T, D = algo_config.horizon, algo_config.vae.latent_size
@@ -253,8 +271,14 @@ class DmModel(nn.Module):
         steps = [i for i in reversed(range(0, self.n_timesteps, self.stride))]
         K = len(steps)
         if noise is None and not use_device_rng and sampler == "ddpm":
-            # the reference draws randn_like at every visited step (also at t == 0)
-            noise = torch.randn((K, R, T, D), device=device)
+            # the reference draws randn_like at every visited step (also at t == 0); above 256 MB of pre-drawn noise the
+            # in-kernel Philox generator takes over (seeded from torch's generator, so torch.manual_seed still governs)
+            if K * R * T * D * 4 <= (256 << 20):
+                noise = torch.randn((K, R, T, D), device=device)
+            else:
+                use_device_rng = True
+        if use_device_rng and not seed:
+            seed = int(torch.randint(1, 2 ** 62, (1,)).item())
         cond = aux_info['cond_feat']
         rep = (lambda v: v.repeat_interleave(N, dim=0)) if N > 1 else (lambda v: v)
         cond_rows = rep(cond)
@@ -262,17 +286,18 @@ class DmModel(nn.Module):
         scene, A = None, agents_per_scene
         if guidance is not None or want_indicators:
             if A is None:
-                sidx = data_batch['scene_index']
-                A = int((sidx == sidx[0]).sum().item())
+                A = agents_per_scene(data_batch.get('scene_index'), B)
+            elif B % A:
+                raise ValueError("B=%d agents is not a multiple of agents_per_scene=%d" % (B, A))
         dev_seed = (seed or 0) if use_device_rng else 0
         n_lanes = min(self._lanes, B // A) if (A and self._lanes > 1) else 1
         if n_lanes > 1:
             out = self._sample_lanes(n_lanes, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance,
-                                     sampler, want_traj, want_indicators)
+                                     sampler, want_traj, want_indicators, row_offset)
         else:
             if guidance is not None or want_indicators:
                 scene = eng.make_scene(data_batch, B // A, A, N)
-            out = eng.sample(x_init, cond_rows, noises=noise, seed=dev_seed,
+            out = eng.sample(x_init, cond_rows, noises=noise, seed=dev_seed, row_offset=row_offset,
                              curr_rows=curr_rows, scene=scene, guidance=guidance, stride=self.stride, sampler=sampler,
                              want_traj=want_traj, want_indicators=want_indicators)
         log_prob_final = None
@@ -295,10 +320,10 @@ class DmModel(nn.Module):
         return res
 
     def _sample_lanes(self, n_lanes, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler,
-                      want_traj, want_indicators):
+                      want_traj, want_indicators, row_offset=0):
         """Scenes split into `n_lanes` contiguous whole-scene sub-batches, each sampled by its own engine on its own stream
-        (scenes never interact, so the result equals the single-lane one; with in-kernel Philox noise every lane draws
-        from its own seed)."""
+        (scenes never interact and in-kernel Philox noise is indexed by the global row id, so the result equals the
+        single-lane one bit for bit)."""
         device = self.betas.device
         S = B // A
         cur = torch.cuda.current_stream(device)
@@ -314,7 +339,7 @@ class DmModel(nn.Module):
                 sub = {k: (v[b0:b1] if (torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B) else v) for k, v in data_batch.items()}
                 scene = eng.make_scene(sub, s1 - s0, A, N) if (guidance is not None or want_indicators) else None
                 o = eng.sample(x_init[r0:r1], cond_rows[r0:r1], noises=None if noise is None else noise[:, r0:r1],
-                               seed=(dev_seed + li) if dev_seed else 0, curr_rows=None if curr_rows is None else curr_rows[r0:r1],
+                               seed=dev_seed, row_offset=row_offset + r0, curr_rows=None if curr_rows is None else curr_rows[r0:r1],
                                scene=scene, guidance=guidance, stride=self.stride, sampler=sampler, want_traj=want_traj,
                                want_indicators=want_indicators)
             parts.append(o)

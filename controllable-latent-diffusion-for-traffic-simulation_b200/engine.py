@@ -8,22 +8,7 @@ import torch
 from . import _lib
 from ._lib import CldConfig, CldGuidanceConfig, CldScene, lib
 
-NORM_MEAN = (13.162, -0.13891, 5.0223, -0.0046415, -0.0080072, -0.0013546)
-NORM_STD = (13.0717, 2.2462, 3.6187, 0.2210, 2.5770, 0.0840)
-
-DECODER_KEYS = [
-    "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
-    "lstm.weight_ih_l1", "lstm.weight_hh_l1", "lstm.bias_ih_l1", "lstm.bias_hh_l1",
-    "cond2hidden.weight", "cond2hidden.bias", "hid2act.weight", "hid2act.bias",
-]
-
-
-def default_guidance(**over):
-    """Defaults of the reference's SceneEditingConfig (src/tbsim/configs/scene_edit_config.py:73-92,302-325)."""
-    g = dict(agent_collision=50.0, map_collision=1.0, target_pos=0.0, num_disks=2, buffer_dist=0.2, decay=0.9,
-             num_points=(10, 10), speed_th=0.5, min_target_time=0.0, optimizer="adam", lr=0.3)
-    g.update(over)
-    return g
+from .keys import DECODER_KEYS, NORM_MEAN, NORM_STD, default_guidance  # noqa: F401  (re-exported)
 
 
 def _ptr(t):
@@ -43,6 +28,20 @@ def _u8(t, dev):
     if t.dtype == torch.bool:
         t = t.to(torch.uint8)
     return t.to(torch.uint8).contiguous()
+
+
+def _on_device(fn):
+    """Run a method with the engine's device current: the handle's buffers, the kernels and the caller's stream all
+    belong to `self.device`, whatever device the calling thread had selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 class Engine:
@@ -98,9 +97,11 @@ class Engine:
     def launch_count(self):
         return int(lib.cld_launch_count(self._h))
 
+    @_on_device
     def profile_begin(self):
         self._check(lib.cld_profile_begin(self._h), "cld_profile_begin")
 
+    @_on_device
     def profile_end(self):
         """-> {kind: (total_ms, brackets)} for kinds denoiser / step / guidance / decode."""
         ms, cnt = (C.c_double * 4)(), (C.c_int * 4)()
@@ -109,6 +110,7 @@ class Engine:
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
     # ------------------------------------------------------------------ weights / schedule
+    @_on_device
     def load_unet(self, state_dict):
         """state_dict: DmModel.model.state_dict() (reference key order)."""
         ts = [_f32(v.detach(), self.device) for v in state_dict.values()]
@@ -118,6 +120,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(lib.cld_load_unet(self._h, ptrs, numels, n, self._stream()), "cld_load_unet")
 
+    @_on_device
     def load_decoder(self, state_dict):
         """state_dict: VaeModel.lstmvae.lstm_dec.state_dict() (keys DECODER_KEYS)."""
         ts = [_f32(state_dict[k].detach(), self.device) for k in DECODER_KEYS]
@@ -125,6 +128,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(lib.cld_load_decoder(self._h, ptrs, 12, self._stream()), "cld_load_decoder")
 
+    @_on_device
     def set_schedule(self, bufs):
         names = ["x_t_cof", "noise_cof", "posterior_log_variance_clipped", "sqrt_recip_alphas_cumprod",
                  "sqrt_recipm1_alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"]
@@ -136,6 +140,7 @@ class Engine:
         self._check(lib.cld_set_schedule(self._h, *arrs, n), "cld_set_schedule")
 
     # ------------------------------------------------------------------ scene / guidance structs
+    @_on_device
     def make_scene(self, batch, num_scenes, agents_per_scene, num_samp):
         """batch: the reference's data_batch dict (extent, world_from_agent, raster_from_agent, curr_speed,
         drivable_map, [target_pos], [all_other_agents_future_positions/_availability])."""
@@ -178,6 +183,7 @@ class Engine:
         return gc
 
     # ------------------------------------------------------------------ kernels
+    @_on_device
     def unet_forward(self, x, cond, t, debug_stage=None):
         x, cond = _f32(x, self.device), _f32(cond, self.device)
         t = t.to(self.device, torch.int64).contiguous()
@@ -198,6 +204,7 @@ class Engine:
                 lib.cld_unet_debug_stage(self._h, -1, C.c_void_p(0), R, self._stream())
         return (eps, dbg) if debug_stage is not None else eps
 
+    @_on_device
     def posterior_step(self, x, eps, noise, t, t_next=-1, sampler="ddpm", want_mean=False):
         x, eps, noise = _f32(x, self.device), _f32(eps, self.device), _f32(noise, self.device)
         out = torch.empty_like(x)
@@ -207,6 +214,7 @@ class Engine:
                                            _ptr(out), _ptr(mean), x.shape[0], self._stream()), "cld_posterior_step")
         return (out, mean) if want_mean else out
 
+    @_on_device
     def decode_rollout(self, z, cond, curr):
         z, cond, curr = _f32(z, self.device), _f32(cond, self.device), _f32(curr, self.device)
         R = z.shape[0]
@@ -216,6 +224,7 @@ class Engine:
                                            self._stream()), "cld_decode_rollout")
         return act, traj
 
+    @_on_device
     def unicycle(self, curr, u):
         curr, u = _f32(curr, self.device), _f32(u, self.device)
         R = u.shape[0]
@@ -223,6 +232,7 @@ class Engine:
         self._check(lib.cld_unicycle(self._h, _ptr(curr), _ptr(u), _ptr(st), R, self._stream()), "cld_unicycle")
         return st
 
+    @_on_device
     def indicators(self, traj, scene):
         traj = _f32(traj, self.device)
         R = traj.shape[0]
@@ -233,6 +243,7 @@ class Engine:
                                        self._stream()), "cld_indicators")
         return off.bool(), coll, rew
 
+    @_on_device
     def guidance_step(self, z_mean, cond_rows, curr_rows, scene, guidance):
         z, cond, curr = _f32(z_mean, self.device), _f32(cond_rows, self.device), _f32(curr_rows, self.device)
         R = z.shape[0]
@@ -243,19 +254,23 @@ class Engine:
                                           _ptr(z_out), _ptr(grad), _ptr(loss), R, self._stream()), "cld_guidance_step")
         return z_out, grad, loss
 
-    def sample(self, x_init, cond_rows, *, noises=None, seed=0, curr_rows=None, scene=None, guidance=None, stride=1,
-               sampler="ddpm", want_traj=False, want_indicators=False):
+    @_on_device
+    def sample(self, x_init, cond_rows, *, noises=None, seed=0, row_offset=0, curr_rows=None, scene=None, guidance=None,
+               stride=1, sampler="ddpm", want_traj=False, want_indicators=False):
+        """x_init None (with seed != 0): the initial state is drawn in-kernel; row_offset: global id of row 0 (sharded calls)."""
         x_init, cond = _f32(x_init, self.device), _f32(cond_rows, self.device)
         noises, curr = _f32(noises, self.device), _f32(curr_rows, self.device)
-        R = x_init.shape[0]
-        x0, x1 = torch.empty_like(x_init), torch.empty_like(x_init)
+        R = cond.shape[0]
+        x0 = torch.empty(R, self.T, self.D, device=self.device)
+        x1 = torch.empty_like(x0)
         x1_valid = C.c_int(0)
         traj = torch.empty(R, self.T, 6, device=self.device) if (want_traj or want_indicators) else None
         off = torch.empty(R, self.T, device=self.device, dtype=torch.uint8) if want_indicators else None
         coll = torch.empty(R, device=self.device) if want_indicators else None
         gc = self.make_guidance(guidance) if guidance is not None else None
         smp = _lib.CLD_SAMPLER_DDPM if sampler == "ddpm" else _lib.CLD_SAMPLER_DDIM
-        self._check(lib.cld_sample(self._h, _ptr(x_init), _ptr(noises), C.c_uint64(int(seed)), _ptr(cond), _ptr(curr),
+        self._check(lib.cld_sample(self._h, _ptr(x_init), _ptr(noises), C.c_uint64(int(seed)), C.c_int64(int(row_offset)), _ptr(cond),
+                                   _ptr(curr),
                                    C.byref(scene) if scene is not None else None,
                                    C.byref(gc) if gc is not None else None, int(stride), smp, _ptr(x0), _ptr(x1),
                                    C.byref(x1_valid), _ptr(traj), _ptr(off), _ptr(coll), R, self._stream()),

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .engine import DECODER_KEYS
+from .keys import DECODER_KEYS
 
 
 class _LstmBlock(nn.Module):
@@ -73,18 +73,12 @@ class VaeModel(nn.Module):
     def bind(self, dm):
         """Share the DmModel's engine (one handle per device) and hand it the decoder weights."""
         object.__setattr__(self, "_dm", dm)
-        dm.attach_decoder(self.decoder_state_dict())
+        dm.attach_decoder(self.decoder_state_dict(), module=self.lstmvae.lstm_dec)
         return self
 
     def decoder_state_dict(self):
         sd = self.lstmvae.lstm_dec.state_dict()
         return {k: sd[k] for k in DECODER_KEYS}
-
-    def load_state_dict(self, *a, **k):
-        out = super().load_state_dict(*a, **k)
-        if self._dm is not None:
-            self._dm.attach_decoder(self.decoder_state_dict())
-        return out
 
     def _engine(self, rows):
         if self._dm is None:

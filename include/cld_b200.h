@@ -176,12 +176,15 @@ int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, cons
 
 /* Whole sampler: DmModel.sample_traj (models/dm/dm_model.py:103-142) + optional guidance
  * (template src/tbsim/models/diffuser.py:843-929) + decode/rollout + indicators.
- *   x_init [R,T,D]; noises [K,R,T,D] or NULL with seed!=0 for in-kernel Philox noise;
+ *   x_init [R,T,D] (NULL with seed!=0: drawn in-kernel); noises [K,R,T,D] or NULL with seed!=0 for in-kernel
+ *   Philox4x32-10 noise.  row_offset = GLOBAL id of row 0 of this call (0 for an unsharded call): the Philox
+ *   counter of an element is (global row, element, step), so a shard / chunk / lane of a batch draws exactly
+ *   what the unsharded batch would.
  *   cond [R,C], curr [R,4] per row; scene/g may be NULL (unguided, no indicators).
  * Outputs (any may be NULL): x0 [R,T,D], x1 [R,T,D] (written only if step index 1 is visited;
  * *x1_valid says so), traj [R,T,6], offroad [R,T], coll [R]. */
 int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t seed,
-               const float* cond, const float* curr, const CldScene* scene,
+               int64_t row_offset, const float* cond, const float* curr, const CldScene* scene,
                const CldGuidanceConfig* g, int stride, int sampler, float* x0_out, float* x1_out,
                int* x1_valid, float* traj_out, uint8_t* offroad_out, float* coll_out, int R,
                void* stream);

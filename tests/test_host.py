@@ -112,3 +112,58 @@ def test_context_encoder_has_no_cpu_path():
             "history_yaws": torch.zeros(1, 31, 1), "curr_speed": torch.zeros(1)})
     with pytest.raises(RuntimeError):
         ContextEncoder(4, default_algo_config(), {"image": (3, 224, 224)})
+
+
+def test_ragged_or_interleaved_scenes_are_rejected():
+    """every scene of a call must hold the same number of contiguous agents; anything else raises a clear error
+    instead of silently mis-partitioning rows (the reference builds a block-diagonal mask, guidance_loss.py:493-503)."""
+    from cld_b200.keys import agents_per_scene
+    assert agents_per_scene(torch.tensor([0, 0, 0, 1, 1, 1]), 6) == 3
+    assert agents_per_scene(torch.tensor([7, 7, 3, 3]), 4) == 2
+    assert agents_per_scene(None, 5) == 5
+    with pytest.raises(ValueError, match="same number of agents"):
+        agents_per_scene(torch.tensor([0] * 4 + [1] * 2 + [2] * 6), 12)       # B % A == 0 but ragged
+    with pytest.raises(ValueError, match="not contiguous"):
+        agents_per_scene(torch.tensor([0, 1, 0, 1]), 4)
+    with pytest.raises(ValueError):
+        agents_per_scene(torch.tensor([0, 0, 1]), 4)
+
+
+def test_weight_signature_sees_parent_level_loads_and_in_place_updates(models_cpu):
+    """the engine's packed weights are a snapshot; the signature it is keyed on must change on a load through a
+    PARENT module (Lightning's load_from_checkpoint never calls the child's load_state_dict), on optimizer steps and on
+    decoder changes after VaeModel.bind."""
+    dm, vae, _ = models_cpu(10)
+    vae.bind(dm)
+
+    class Parent(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dm, self.vae = dm, vae
+    parent = Parent()
+    s0 = dm._weights_signature()
+    assert dm._weights_signature() == s0
+    sd = {k: v.clone() for k, v in parent.state_dict().items()}
+    parent.load_state_dict(sd)                                    # parent-level load: values equal, versions bumped
+    s1 = dm._weights_signature()
+    assert s1 != s0
+    with torch.no_grad():
+        dm.model.final_conv[1].bias.add_(1.0)                     # what an optimizer step does
+    s2 = dm._weights_signature()
+    assert s2 != s1
+    with torch.no_grad():
+        vae.lstmvae.lstm_dec.hid2act.bias.mul_(2.0)               # decoder changed after bind
+    assert dm._weights_signature() != s2
+
+
+def test_containers_construct_without_the_shared_library():
+    """The parameter containers must not map libcld_b200.so (the bench's reference arm draws its weights from them);
+    the library is loaded by engine.Engine only."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from cld_b200 import default_algo_config; "
+            "from cld_b200.dm_model import DmModel; from cld_b200.vae import VaeModel; a = default_algo_config(); "
+            "DmModel(a, {'image': (34, 224, 224)}, n_timesteps=10); VaeModel(a); "
+            "assert not any(m.endswith('._lib') for m in sys.modules), [m for m in sys.modules if 'cld' in m]; "
+            "assert 'libcld_b200' not in open('/proc/self/maps').read()") % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
