@@ -366,6 +366,22 @@ def target_pos_loss(x, target_pos, min_target_time=0.0):
     return (wgt * (diff ** 2).sum(-1)).mean(-1)
 
 
+def target_speed_loss(x, target_speed):
+    """TargetSpeedLoss.forward (guidance_loss.py:219-254) at global_t = 0 with a target for every step of the horizon
+    (no NaN targets: a NaN target makes the reference's own gradient NaN): mean_t |v_t - v*_t|.  target_speed [A,T]."""
+    return (x[..., 2] - target_speed[:, None, :]).abs().mean(-1)
+
+
+def acc_limit_loss(x, acc_limit):
+    """AccLimitLoss.forward (guidance_loss.py:1444-1468): mean_t max(|acc_t| - limit, 0)."""
+    return (x[..., 4].abs() - acc_limit).clamp(min=0).mean(-1)
+
+
+def speed_limit_loss(x, speed_limit):
+    """SpeedLimitLoss.forward (guidance_loss.py:1509-1538): mean_t max(|v_t| - limit, 0)."""
+    return (x[..., 2].abs() - speed_limit).clamp(min=0).mean(-1)
+
+
 DEFAULT_GUIDANCE = dict(agent_collision=50.0, map_collision=1.0, target_pos=0.0,
                         num_disks=2, buffer_dist=0.2, decay=0.9, num_points=(10, 10),
                         optimizer='adam', lr=0.3)
@@ -391,9 +407,21 @@ def guidance_loss_scene(x6, scene, g):
         per['map_collision'] = l.detach()
         tot = tot + l.mean() * g['map_collision']
     if g.get('target_pos', 0.0) != 0.0:
-        l = target_pos_loss(x6, scene['target_pos'])
+        l = target_pos_loss(x6, scene['target_pos'], g.get('min_target_time', 0.0))
         per['target_pos'] = l.detach()
         tot = tot + l.mean() * g['target_pos']
+    if g.get('target_speed', 0.0) != 0.0:
+        l = target_speed_loss(x6, scene['target_speed'])
+        per['target_speed'] = l.detach()
+        tot = tot + l.mean() * g['target_speed']
+    if g.get('acc_limit', 0.0) != 0.0:
+        l = acc_limit_loss(x6, g['acc_limit_value'])
+        per['acc_limit'] = l.detach()
+        tot = tot + l.mean() * g['acc_limit']
+    if g.get('speed_limit', 0.0) != 0.0:
+        l = speed_limit_loss(x6, g['speed_limit_value'])
+        per['speed_limit'] = l.detach()
+        tot = tot + l.mean() * g['speed_limit']
     return tot, per
 
 
@@ -411,16 +439,19 @@ def guidance_grad(dec_sd, z, cond, curr, batch, agents_per_scene, num_samp, g=DE
     grads, losses = [], []
     for s in range(S):
         r0, r1 = s * A * N, (s + 1) * A * N
-        zs = z[r0:r1].detach().clone().requires_grad_()
         scene = slice_scene(batch, s * A, (s + 1) * A)
         rep = lambda v: v.repeat_interleave(N, dim=0)                         # noqa: E731
-        x6, _ = decode_rollout(dec_sd, zs, rep(cond[s * A:(s + 1) * A]), rep(curr[s * A:(s + 1) * A]))
-        tot, per = guidance_loss_scene(x6.reshape(A, N, x6.shape[1], 6), scene, g)
-        if tot.requires_grad:
-            tot.backward()
-            grads.append(zs.grad if zs.grad is not None else torch.zeros_like(zs))
-        else:
-            grads.append(torch.zeros_like(zs))
+        # the reference's perturb runs under torch.enable_grad() (guidance_loss.py:2244): a caller's no_grad must not
+        # silently turn the guidance off
+        with torch.enable_grad():
+            zs = z[r0:r1].detach().clone().requires_grad_()
+            x6, _ = decode_rollout(dec_sd, zs, rep(cond[s * A:(s + 1) * A]), rep(curr[s * A:(s + 1) * A]))
+            tot, per = guidance_loss_scene(x6.reshape(A, N, x6.shape[1], 6), scene, g)
+            if tot.requires_grad:
+                tot.backward()
+                grads.append(zs.grad if zs.grad is not None else torch.zeros_like(zs))
+            else:
+                grads.append(torch.zeros_like(zs))
         losses.append(per)
     return torch.cat(grads, 0), losses
 
@@ -446,10 +477,12 @@ def step_indices(n_timesteps, stride):
 
 
 def sample(unet_sd, sched, cond_rows, x_init, noises, n_timesteps, stride=1, sampler='ddpm',
-           guidance=None, unet_fn=None):
+           guidance=None, unet_fn=None, trace=None):
     """cond_rows [R,C] (aux_info already repeated xN), x_init [R,T,D], noises [K,R,T,D] (noises[k]
     used at the k-th visited step; ignored where the reference multiplies by 0).
-    guidance: None or dict(dec_sd, cond, curr, batch, A, N, cfg).  Returns dict like DmModel.forward."""
+    guidance: None or dict(dec_sd, cond, curr, batch, A, N, cfg).  Returns dict like DmModel.forward.
+    trace: optional list; one dict per visited step is appended (i, i_next, x_t, eps, mean, grad, x_next) so that a
+    test can feed the oracle's own x_t into ONE step of another implementation (teacher forcing)."""
     steps = step_indices(n_timesteps, stride)
     x = x_init.clone()
     R = x.shape[0]
@@ -458,21 +491,29 @@ def sample(unet_sd, sched, cond_rows, x_init, noises, n_timesteps, stride=1, sam
     for k, i in enumerate(steps):
         t = torch.full((R,), i, dtype=torch.long)
         eps = fn(x, t)
+        i_next = steps[k + 1] if k + 1 < len(steps) else -1
         if sampler == 'ddpm':
             mean, sigma = ddpm_mean_sigma(sched, x, eps, i)
         else:
-            i_next = steps[k + 1] if k + 1 < len(steps) else -1
             mean = ddim_next(sched, x, eps, i, i_next)
             sigma = torch.zeros(())
+        rec = None
+        if trace is not None:
+            rec = {'i': i, 'i_next': i_next, 'x_t': x.clone(), 'eps': eps.clone(), 'mean': mean.clone(), 'grad': None}
+            trace.append(rec)
         if guidance is not None and i != 0:
             gd = guidance
             grad, _ = guidance_grad(gd['dec_sd'], mean, gd['cond'], gd['curr'], gd['batch'], gd['A'], gd['N'],
                                     gd['cfg'])
             mean = apply_guidance_update(mean, grad, gd['cfg'])
+            if rec is not None:
+                rec['grad'] = grad.clone()
         if sampler == 'ddpm' and i != 0:
             x = mean + sigma * noises[k]
         else:
             x = mean
+        if rec is not None:
+            rec['x_next'] = x.clone()
         if i == 1:
             x1 = x.clone()
         if i == 0:

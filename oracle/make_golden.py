@@ -235,9 +235,122 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "guidance.npz"), S=S, A=A, N=N, seed=41, z=zg.numpy(), z_out=z_ref.numpy(),
                         grad_sgd=grads_ref.numpy(), loss_ac=loss_ref['agent_collision'].numpy(),
                         loss_mc=loss_ref['map_collision'].numpy(), **wsum)
+    guidance_ext_golden()
     context_golden()
     raster_golden()
     print("golden files written to", GOLD)
+
+
+def guidance_ext_golden():
+    """Row a13 (TargetPosLoss), the f-4 analytic terms (TargetSpeedLoss, AccLimitLoss, SpeedLimitLoss) and the big shape
+    (T = 104, 64 agents, 8 samples) against the REAL PerturbationGuidance.perturb -> tests/golden/guidance_ext.npz,
+    guidance_t104.npz.  Every term is pinned alone (loss + SGD-extracted gradient) and all together (Adam update)."""
+    RH.install()
+    from tbsim.utils.guidance_loss import PerturbationGuidance
+    dm, vae, algo = RH.build_models(n_timesteps=10)
+    dec_sd = {k: v.detach() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+
+    def ref_perturb(z_mean, aux_s, batch_s, N, cfg_list, opt):
+        def transform(x_dec, data_batch, params, bsize=None, num_samp=1):
+            cs = aux_s['curr_states'].unsqueeze(1).expand(bsize, num_samp, 4).reshape(bsize * num_samp, 4)
+            return vae.convert_action_to_state_and_action(x_dec, cs, scaled_input=True, descaled_output=True)
+        pg = PerturbationGuidance(transform, {})
+        pg.set_guidance([cfg_list])
+        condN = aux_s['cond_feat'].repeat_interleave(N, 0)
+        xg = z_mean.clone().detach().requires_grad_()
+        x_out, per = pg.perturb(xg, batch_s, opt, num_samp=N, decoder=lambda zz: vae.lstmvae.lstm_dec(zz, condN))
+        return x_out.detach(), per
+
+    SGD = {'optimizer': 'sgd', 'lr': 1.0, 'grad_steps': 1, 'perturb_th': None}
+    ADAM = {'optimizer': 'adam', 'lr': 0.3, 'grad_steps': 1, 'perturb_th': None}
+
+    def run_ref(S, A, N, T, aux, batch, zg, terms, sgd_lr):
+        """terms: list of (oracle key, reference cfg dict builder(scene slice) )"""
+        z_out, grads, losses = [], [], {}
+        for s in range(S):
+            aux_s = {k: v[s * A:(s + 1) * A] for k, v in aux.items()}
+            batch_s = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in O.slice_scene(batch, s * A, (s + 1) * A).items()}
+            cfg_list = [mk(batch_s) for _, mk in terms]
+            zs = zg[s * A * N:(s + 1) * A * N]
+            # z' = z - lr * g: a large lr lifts the gradient above the fp32 rounding of the subtraction
+            zo_sgd, _ = ref_perturb(zs, aux_s, batch_s, N, cfg_list, dict(SGD, lr=sgd_lr))
+            grads.append((zs - zo_sgd) / sgd_lr)
+            zo, per = ref_perturb(zs, aux_s, batch_s, N, cfg_list, ADAM)
+            z_out.append(zo)
+            for i, (key, _) in enumerate(terms):
+                name = cfg_list[i]['name']
+                losses.setdefault(key, []).append(per['%s_scene_000_%02d' % (name, i)])
+        return torch.cat(z_out), torch.cat(grads), {k: torch.cat(v) for k, v in losses.items()}
+
+    def compare(tag, S, A, N, aux, batch, zg, terms, g_cfg, out, grad_tol=1e-3, sgd_lr=100.0):
+        z_ref, g_ref, l_ref = run_ref(S, A, N, zg.shape[1], aux, batch, zg, terms, sgd_lr)
+        g_or, per_or = O.guidance_grad(dec_sd, zg, aux['cond_feat'], aux['curr_states'], batch, A, N, g_cfg)
+        z_or = O.apply_guidance_update(zg, g_or, g_cfg)
+        for key, _ in terms:
+            lo = torch.cat([p[key] for p in per_or])
+            check("%s loss %s" % (tag, key), lo, l_ref[key], 2e-5)
+            out["%s_loss_%s" % (tag, key)] = l_ref[key].numpy()
+        big = g_ref.abs() > 1e-4 * g_ref.abs().max()
+        print("%s: |g|max %.3e nonzero frac %.3f" % (tag, g_ref.abs().max(), (g_ref != 0).float().mean()))
+        check("%s grad (sgd-extracted)" % tag, g_or[big], g_ref[big], grad_tol)
+        agree = (torch.sign(g_or) == torch.sign(zg - z_ref)).float().mean().item()
+        print("%s: sign agreement oracle grad vs reference adam step %.6f" % (tag, agree))
+        check("%s adam update z'" % tag, z_or, z_ref, 3e-3)
+        out["%s_grad_sgd" % tag] = g_ref.numpy()
+        out["%s_z_out" % tag] = z_ref.numpy()
+
+    # ---- T = 52: every term alone, then all together
+    S, A, N, T = 2, 5, 2, 52
+    aux, batch = make_scenes(S, A, horizon=T, seed=51, dense=True)
+    g = torch.Generator().manual_seed(52)
+    batch['target_pos'] = torch.stack([aux['curr_states'][:, 2] * 3.0 + 2.0, torch.rand(S * A, generator=g) * 6 - 3], 1)
+    batch['target_speed'] = (aux['curr_states'][:, 2:3] + torch.linspace(0, 3, T)[None] * (torch.rand(S * A, 1, generator=g) - 0.3)).contiguous()
+    torch.manual_seed(53)
+    zg = torch.randn(S * A * N, T, 4)
+    ACC_LIM, SPD_LIM, MIN_TT = 0.05, 5.0, 0.3
+    mk = {
+        'agent_collision': lambda b: {'name': 'agent_collision', 'weight': 50.0, 'agents': None,
+                                      'params': {'num_disks': 2, 'buffer_dist': 0.2, 'decay_rate': 0.9, 'excluded_agents': None}},
+        'map_collision': lambda b: {'name': 'map_collision', 'weight': 1.0, 'agents': None,
+                                    'params': {'num_points_lw': (10, 10), 'decay_rate': 0.9}},
+        'target_pos': lambda b: {'name': 'target_pos', 'weight': 2.0, 'agents': None,
+                                 'params': {'target_pos': b['target_pos'].clone(), 'min_target_time': MIN_TT}},
+        'target_speed': lambda b: {'name': 'target_speed', 'weight': 3.0, 'agents': None,
+                                   'params': {'dt': 0.1, 'target_speed': b['target_speed'].numpy().copy(),
+                                              'fut_valid': np.ones(tuple(b['target_speed'].shape), dtype=bool)}},
+        'acc_limit': lambda b: {'name': 'acc_limit', 'weight': 1.5, 'agents': None, 'params': {'acc_limit': ACC_LIM}},
+        'speed_limit': lambda b: {'name': 'speed_limit', 'weight': 4.0, 'agents': None, 'params': {'speed_limit': SPD_LIM}},
+    }
+    wts = {'target_pos': 2.0, 'target_speed': 3.0, 'acc_limit': 1.5, 'speed_limit': 4.0, 'agent_collision': 50.0, 'map_collision': 1.0}
+    base = dict(O.DEFAULT_GUIDANCE, agent_collision=0.0, map_collision=0.0, min_target_time=MIN_TT, acc_limit_value=ACC_LIM,
+                speed_limit_value=SPD_LIM)
+    out = {'S': S, 'A': A, 'N': N, 'seed': 51, 'z': zg.numpy(), 'target_pos': batch['target_pos'].numpy(),
+           'target_speed': batch['target_speed'].numpy(), 'acc_limit_value': ACC_LIM, 'speed_limit_value': SPD_LIM,
+           'min_target_time': MIN_TT, 'weights': np.array([wts[k] for k in ('target_pos', 'target_speed', 'acc_limit', 'speed_limit')])}
+    for key in ('target_pos', 'target_speed', 'acc_limit', 'speed_limit'):
+        compare(key, S, A, N, aux, batch, zg, [(key, mk[key])], dict(base, **{key: wts[key]}), out)
+    order = ['agent_collision', 'map_collision', 'target_pos', 'target_speed', 'acc_limit', 'speed_limit']
+    compare('all', S, A, N, aux, batch, zg, [(k, mk[k]) for k in order], dict(base, **wts), out)
+    np.savez_compressed(os.path.join(GOLD, "guidance_ext.npz"), **out)
+
+    # ---- T = 104, one scene of 64 agents, 8 samples (cfg3 / cfg2 shapes): agent + map collision
+    S, A, N, T = 1, 64, 8, 104
+    aux, batch = make_scenes(S, A, horizon=T, seed=61, dense=True)
+    torch.manual_seed(62)
+    zg = torch.randn(S * A * N, T, 4)
+    out = {'S': S, 'A': A, 'N': N, 'T': T, 'seed': 61, 'z_seed': 62, 'z_sum': float(zg.double().sum())}
+    compare('big', S, A, N, aux, batch, zg, [(k, mk[k]) for k in ('agent_collision', 'map_collision')], dict(O.DEFAULT_GUIDANCE), out, sgd_lr=1e4)
+    # store compactly: gradient as fp32 of the non-zero ROWS only; z' is reproducible from z and the gradient up to the Adam eps,
+    # so only its first 64 rows are kept as a spot check
+    gfull = out.pop('big_grad_sgd'); zfull = out.pop('big_z_out')
+    rows = np.nonzero(np.abs(gfull).reshape(gfull.shape[0], -1).sum(1) > 0)[0]
+    out['big_rows'] = rows.astype(np.int32)
+    out['big_grad_rows'] = gfull[rows[:96]]
+    out['big_grad_rowsum'] = gfull.reshape(gfull.shape[0], -1).astype(np.float64).sum(1)
+    out['big_grad_rowabs'] = np.abs(gfull).reshape(gfull.shape[0], -1).astype(np.float64).sum(1)
+    out['big_z_out_head'] = zfull[:64]
+    np.savez_compressed(os.path.join(GOLD, "guidance_t104.npz"), **out)
+    print("guidance ext goldens written")
 
 
 def context_golden():
@@ -291,7 +404,9 @@ def raster_golden():
 
 
 if __name__ == "__main__":
-    if "--only-raster" in sys.argv:
+    if "--only-guidance-ext" in sys.argv:
+        guidance_ext_golden()
+    elif "--only-raster" in sys.argv:
         raster_golden()
     elif "--only-context" in sys.argv:
         context_golden()

@@ -124,6 +124,44 @@ def test_guidance_oracle_vs_reference_golden(models_cpu, gold):
     assert float(lo_ac.sum()) > 0 and float(lo_mc.sum()) > 0
 
 
+def test_guidance_terms_oracle_vs_reference_golden(models_cpu, gold):
+    """Rows a13 / f-4: TargetPosLoss, TargetSpeedLoss, AccLimitLoss, SpeedLimitLoss alone and all six terms together against
+    the outputs of the REAL PerturbationGuidance.perturb (golden written by oracle/make_golden.py --only-guidance-ext)."""
+    from conftest import guidance_ext_case
+    g = gold("guidance_ext")
+    _, _, dec_sd = _sds(models_cpu, 10)
+    S, A, N, aux, batch, z, cfgs = guidance_ext_case(g)
+    for tag, cfg in cfgs.items():
+        grad, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], batch, A, N, cfg)
+        for key in ("target_pos", "target_speed", "acc_limit", "speed_limit"):
+            if cfg.get(key, 0.0) != 0.0:
+                lo = torch.cat([p[key] for p in per]).reshape(-1)
+                assert rel(lo, g["%s_loss_%s" % (tag, key)].reshape(-1)) < 2e-5, (tag, key)
+        gref = torch.tensor(g[tag + "_grad_sgd"])
+        big = gref.abs() > 1e-4 * gref.abs().max()
+        assert rel(grad[big], gref[big]) < 1e-3, tag
+        assert rel(O.apply_guidance_update(z, grad, cfg), g[tag + "_z_out"]) < 3e-3, tag
+        assert float(gref.abs().max()) > 0
+
+
+def test_guidance_big_shape_oracle_vs_reference_golden(models_cpu, gold):
+    """T = 104, 64 agents, 8 samples (cfg2 / cfg3 shapes) against the real reference: per-row gradient sums for all 512 rows,
+    full gradients of 96 rows, z' of 64 rows."""
+    from conftest import guidance_big_case
+    g = gold("guidance_t104")
+    _, _, dec_sd = _sds(models_cpu, 10)
+    S, A, N, T, aux, batch, z = guidance_big_case(g)
+    grad, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], batch, A, N)
+    rows = torch.tensor(g["big_rows"]).long()
+    assert rel(grad[rows[:96]], g["big_grad_rows"]) < 1e-3
+    assert rel(grad.flatten(1).double().abs().sum(1), g["big_grad_rowabs"]) < 1e-3
+    nz = (grad.flatten(1).abs().sum(1) > 0).nonzero().flatten()
+    assert torch.equal(nz, rows)
+    assert rel(O.apply_guidance_update(z, grad)[:64], g["big_z_out_head"]) < 3e-3
+    assert rel(torch.cat([p["agent_collision"] for p in per]).reshape(-1), g["big_loss_agent_collision"].reshape(-1)) < 2e-5
+    assert rel(torch.cat([p["map_collision"] for p in per]).reshape(-1), g["big_loss_map_collision"].reshape(-1)) < 2e-5
+
+
 def test_ddim_final_step_is_x0_prediction():
     s = O.make_schedule(100)
     x, eps = torch.randn(2, 52, 4), torch.randn(2, 52, 4)
