@@ -20,6 +20,8 @@
 
 #include <vector>
 
+#include <cuda.h>
+
 #include "tc_common.cuh"
 #include "unet_tc.cuh"
 
@@ -29,9 +31,11 @@ using namespace tc;
 constexpr int TC_G = 8;
 constexpr int TC_UNIT = 4096;
 constexpr int TC_UNITS = 16;
-constexpr int TC_SLOT = 16384;          // ring slot: every k-block (<= 128 rows x 128 B) takes one
-constexpr int TC_SLOTS = 4;
-static_assert(TC_SLOT * TC_SLOTS == TC_UNIT * TC_UNITS, "ring size");
+// weight ring (64 KB): every k-block takes one slot.  Single-CTA kernel: 4 slots of 16 KB (<= 128 weight rows x 128 B);
+// CTA-pair kernel: each CTA stages HALF of the rows of a k-block, 8 slots of 8 KB -> twice as many k-blocks in flight for the
+// same L2 -> SM bytes (the level-2 layers are bound by the latency of this stream, tools/umma_bench.cu)
+template <bool PAIR> struct Ring { static constexpr int SLOT = PAIR ? 8192 : 16384, SLOTS = PAIR ? 8 : 4; };
+static_assert(Ring<false>::SLOT * Ring<false>::SLOTS == TC_UNIT * TC_UNITS && Ring<true>::SLOT * Ring<true>::SLOTS == TC_UNIT * TC_UNITS, "ring size");
 constexpr int TC_EW = 16;                       // epilogue warps
 constexpr int TC_ETHREADS = TC_EW * 32;
 constexpr int TC_THREADS = 64 + TC_ETHREADS;
@@ -83,7 +87,7 @@ static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 struct TcParams {
   const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
-  const uint8_t* wblob; size_t wcopy_stride; int wcopies; const float* par; const float* tbias; const float* tvec; int tb_stride;
+  const uint8_t* wblob; size_t wcopy_stride; int wcopies; int w_rows_per_copy; const float* par; const float* tbias; const float* tvec; int tb_stride;
   const float* x; float* eps; int R, T, n_groups;
   uint8_t* skipbuf; int skip_stride;
   int zero0_pitch, zero0_npanels, zero0_offB;
@@ -96,6 +100,8 @@ struct TcState {
   std::vector<TcKb> kbs;
   TcOp* d_ops = nullptr; uint32_t* d_kbs = nullptr;
   uint8_t* wblob = nullptr; size_t wblob_bytes = 0; int wcopies = 1;
+  bool pair = false;                    // CTA-pair kernel (cluster of 2, tcgen05 cta_group::2); CLD_TC_PAIR=0 selects the single-CTA kernel
+  CUtensorMap tm8, tm32, tm64;          // the weight blob as a 2-D tensor {64 bf16, rows}; boxes of 8 / 32 / 64 rows = half a k-block
   float* par = nullptr; size_t par_floats = 0;
   float* zeros = nullptr;
   long long* prof = nullptr;
@@ -405,8 +411,21 @@ __device__ __forceinline__ void prefetch_params(const TcOp* o, const TcParams& P
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool PROF>
-__global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P) {
+// PAIR: a cluster of two CTAs carries two row groups (8 rows each, one per CTA: activations, GroupNorm statistics, epilogue and skip
+// buffers stay CTA-local) through the network in lock step.  Every MMA is ONE tcgen05.mma.cta_group::2 (M = 256: 128 GEMM rows per
+// CTA) issued by the leader (rank 0); each CTA stages only HALF of the weight rows of a k-block (2-D TMA boxes of the weight blob,
+// both CTAs' copies complete on the leader's full barrier), the instruction reads both halves.  The leader commits with a
+// multicast arrive onto the ring-empty / accumulator-full barriers of both CTAs; the epilogue warps of both CTAs arrive on the
+// leader's activation-ready barriers (remote mbarrier arrive for rank 1).
+template <bool PROF, bool PAIR>
+__global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm32,
+                                                                const __grid_constant__ CUtensorMap tm64, const TcParams P) {
+  constexpr int TC_SLOT = Ring<PAIR>::SLOT, TC_SLOTS = Ring<PAIR>::SLOTS;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // row groups: a single CTA walks g = blockIdx.x, += gridDim.x; a pair walks pair-groups and CTA `rank` takes group 2 * pg + rank
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = PAIR ? (P.n_groups + 1) >> 1 : P.n_groups;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* arena = smem_raw;   // kept as a __shared__-space pointer so that ptxas emits LDS/STS, not generic LD/ST
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();   // the swizzle atoms need 1024-byte alignment
@@ -428,14 +447,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
   for (int i = tid; i < P.n_kbs; i += TC_THREADS) kbs_s[i] = P.kbs[i];
   if (tid == 0) {
     for (int i = 0; i < TC_UNITS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_act, TC_EW); mbar_init(bar_act + 8, TC_EW);
+    mbar_init(bar_act, PAIR ? 2 * TC_EW : TC_EW); mbar_init(bar_act + 8, PAIR ? 2 * TC_EW : TC_EW);
     mbar_init(bar_acc, 1); mbar_init(bar_acc + 8, 1);
     fence_barrier_init();
     gsh->skip_cta = P.skipbuf + (size_t)blockIdx.x * P.skip_stride;
   }
-  if (warp == TC_EW + 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  if (warp == TC_EW + 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish();
+    }
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();            // both CTAs' barriers exist before any remote arrive / remote complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -445,27 +472,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
     uint32_t par_empty = 0;
     int pos = 0;
     long long t_empty = 0;
-    for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
-      const uint8_t* src = P.wblob + (size_t)(blockIdx.x % P.wcopies) * P.wcopy_stride;
+    const uint32_t full0 = PAIR ? mapa_shared(bar_full, 0) : bar_full;       // pair: the leader's full barriers
+    for (int g = unit0; g < n_units; g += unit_step) {
+      const uint8_t* src = P.wblob + (size_t)(unit0 % P.wcopies) * P.wcopy_stride;
+      int row = (unit0 % P.wcopies) * P.w_rows_per_copy;                     // pair: first blob row (128 B) of the k-block
       for (int k = 0; k < P.n_kbs; ++k) {
         const uint32_t kb = kbs_s[k];
-        const uint32_t bytes = ((kb >> 14) & 0x3Fu) * (8u * 128u);
+        const uint32_t n8 = (kb >> 14) & 0x3Fu;
+        const uint32_t bytes = n8 * (8u * 128u);
         const long long tw0 = PROF ? clock64() : 0;
         mbar_wait(bar_empty + 8 * pos, ((par_empty >> pos) & 1u) ^ 1u);
         par_empty ^= 1u << pos;
         if (PROF) t_empty += clock64() - tw0;
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_full + 8 * pos, bytes);
-          bulk_g2s(smem_u32(ring + pos * TC_SLOT), src, bytes, bar_full + 8 * pos);
+          if (PAIR) {
+            // this CTA's half of the weight rows: a box of N/2 rows starting at row + rank * N/2; completion on the leader's barrier
+            if (leader) mbar_expect_tx_only(bar_full + 8 * pos, bytes);
+            const void* tm = n8 == 16u ? (const void*)&tm64 : (n8 == 8u ? (const void*)&tm32 : (const void*)&tm8);
+            tma2_load_2d(smem_u32(ring + pos * TC_SLOT), tm, 0, row + (int)(rank * n8 * 4u), full0 + 8 * pos);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8 * pos, bytes);
+            bulk_g2s(smem_u32(ring + pos * TC_SLOT), src, bytes, bar_full + 8 * pos);
+          }
         }
         __syncwarp();
         src += (size_t)(1u << ((kb >> 24) & 3)) * TC_UNIT;
+        row += (int)(1u << ((kb >> 24) & 3)) * (TC_UNIT / 128);
         pos = (pos + 1) & (TC_SLOTS - 1);
       }
     }
     if (PROF && lane == 0) { P.prof[blockIdx.x * 8 + 0] = t_empty; }
-  } else if (warp == TC_EW + 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == TC_EW + 1 && leader) {
+    // ===================== MMA issuer (pair: the leader issues for both CTAs) =====================
     // all lanes walk the (warp-uniform) loop so that descriptors are computed on the uniform datapath; one elected
     // lane issues the tcgen05 instructions
     uint32_t par_full = 0, opn = 0;
@@ -476,8 +514,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
     const long long t_start = PROF ? clock64() : 0;
     const uint32_t arena_u = smem_u32(arena), ring_u = smem_u32(ring);
     const uint64_t b_const = make_desc_sw128(0, 1024);
-    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
-    for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    for (int g = unit0; g < n_units; g += unit_step) {
       kb_next = kbs_s[0];
       for (int oi = 0; oi < P.n_ops; ++oi, ++opn) {
         const TcOp* o = ops_s + oi;
@@ -503,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
             tc_fence_after();
             // probe the next slot now; the answer is consumed after this k-block's MMAs have been issued
             const int pos_n = (pos + 1) & (TC_SLOTS - 1);
-            const bool ready_n = mbar_try_wait(bar_full + 8 * pos_n, (par_full >> pos_n) & 1u);
+            const bool ready_n = mbar_test_wait(bar_full + 8 * pos_n, (par_full >> pos_n) & 1u);   // non-blocking
             const uint64_t bd0 = b_const + ((ring_u + pos * TC_SLOT) >> 4);
             const uint64_t a_kb = a_const + a_slots * 64u;
             const long long ti0 = PROF ? clock64() : 0;
@@ -513,15 +551,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
                 if (mt < nt) {
                   const uint64_t ad0 = a_kb + (mt == 0 ? ts0 : mt == 1 ? ts1 : mt == 2 ? ts2 : ts3);
                   const uint32_t d_addr = tmem_base + acc_col + mt * N;
-                  umma_bf16(d_addr, ad0, bd0, idesc, accum);
-                  if (nk16 > 1) {
-                    umma_bf16(d_addr, ad0 + 2, bd0 + 2, idesc, 1u);
-                    umma_bf16(d_addr, ad0 + 4, bd0 + 4, idesc, 1u);
-                    umma_bf16(d_addr, ad0 + 6, bd0 + 6, idesc, 1u);
+                  if (PAIR) {
+                    umma2_bf16(d_addr, ad0, bd0, idesc, accum);
+                    if (nk16 > 1) {
+                      umma2_bf16(d_addr, ad0 + 2, bd0 + 2, idesc, 1u);
+                      umma2_bf16(d_addr, ad0 + 4, bd0 + 4, idesc, 1u);
+                      umma2_bf16(d_addr, ad0 + 6, bd0 + 6, idesc, 1u);
+                    }
+                  } else {
+                    umma_bf16(d_addr, ad0, bd0, idesc, accum);
+                    if (nk16 > 1) {
+                      umma_bf16(d_addr, ad0 + 2, bd0 + 2, idesc, 1u);
+                      umma_bf16(d_addr, ad0 + 4, bd0 + 4, idesc, 1u);
+                      umma_bf16(d_addr, ad0 + 6, bd0 + 6, idesc, 1u);
+                    }
                   }
                 }
               }
-              umma_commit(bar_empty + 8 * pos);
+              if (PAIR) umma2_commit_pair(bar_empty + 8 * pos); else umma_commit(bar_empty + 8 * pos);
             }
             __syncwarp();
             if (PROF) t_issue += clock64() - ti0;
@@ -530,11 +577,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           }
         };
         auto commit = [&](uint32_t bar) {
-          if (elect_one()) umma_commit(bar);
+          if (elect_one()) { if (PAIR) umma2_commit_pair(bar); else umma_commit(bar); }
           __syncwarp();
         };
         const uint32_t ph = opn & 1u;
-        long long* tl = (PROF && blockIdx.x == 0 && g == blockIdx.x && lane == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
+        long long* tl = (PROF && blockIdx.x == 0 && g == unit0 && lane == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
         if (tl) tl[0] = clock64();
         long long tw1 = PROF ? clock64() : 0;
         mbar_wait(bar_act, ph);                                  // inputs written by half 0 of the previous epilogue
@@ -558,7 +605,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       }
     }
     if (PROF && lane == 0) { P.prof[blockIdx.x * 8 + 2] = t_full; P.prof[blockIdx.x * 8 + 3] = t_act; P.prof[blockIdx.x * 8 + 4] = clock64() - t_start; P.prof[blockIdx.x * 8 + 7] = t_issue; P.prof[blockIdx.x * 8 + 1] = t_commit; }
-  } else {
+  } else if (warp < TC_EW) {
     // ===================== epilogue warps =====================
     EpiCtx cx;
     cx.etid = tid; cx.q = warp & 3; cx.cq = warp >> 2; cx.lane = lane;
@@ -570,7 +617,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
     uint32_t opn = 0;
     long long t_acc = 0;
     const long long t_start = PROF ? clock64() : 0;
-    for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
+    const uint32_t act0 = PAIR ? mapa_shared(bar_act, 0) : bar_act;          // pair: the leader's activation-ready barriers
+    for (int u = unit0; u < n_units; u += unit_step) {
+      const int g = PAIR ? 2 * u + (int)rank : u;
       cx.g = g;
       // ---- stage the latent x [8,T,4] fp32 as bf16 hi/lo channels 0..7 of panel 0 (region A, level 0)
       prefetch_params(ops_s, P, par_s, tb_s, g, etid);
@@ -588,7 +637,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar_act); mbar_arrive(bar_act + 8); }
+      if (lane == 0) {
+        if (PAIR) { mbar_arrive_cluster(act0); mbar_arrive_cluster(act0 + 8); }
+        else { mbar_arrive(bar_act); mbar_arrive(bar_act + 8); }
+      }
 
       for (int oi = 0; oi < P.n_ops; ++oi, ++opn) {
         const TcOp* o = ops_s + oi;
@@ -612,7 +664,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           const long long tw0 = PROF ? clock64() : 0;
           mbar_wait(bar_acc + 8 * h, opn & 1u);
           if (PROF) t_acc += clock64() - tw0;
-          long long* tl = (PROF && blockIdx.x == 0 && g == blockIdx.x && etid == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
+          long long* tl = (PROF && blockIdx.x == 0 && u == unit0 && etid == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
           if (tl) tl[3 + 2 * h] = clock64();
           cx.tl = (tl && h == 0) ? P.prof + (gridDim.x + TC_MAX_OPS) * 8 + oi * 4 : nullptr;
           tc_fence_after();
@@ -642,7 +694,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && oi + 1 < P.n_ops) mbar_arrive(bar_act + 8 * h);
+          if (lane == 0 && oi + 1 < P.n_ops) {
+            if (PAIR) mbar_arrive_cluster(act0 + 8 * h); else mbar_arrive(bar_act + 8 * h);
+          }
           if (tl) tl[4 + 2 * h] = clock64();
         }
       }
@@ -651,7 +705,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const TcParams P
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_EW + 1) tmem_dealloc(tmem_base, 512);
+  if (PAIR) cluster_sync_all();            // nobody leaves (or frees tensor memory) while the peer may still touch this CTA
+  if (warp == TC_EW + 1) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -986,7 +1044,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     expect_off += (size_t)kb.units * TC_UNIT;
     uint32_t a_slots = (uint32_t)(kb.a_base / 1024 + kb.shift);
     int ul = kb.units == 1 ? 0 : kb.units == 2 ? 1 : kb.units == 4 ? 2 : kb.units == 8 ? 3 : -1;
-    if (a_slots > 255u || kb.acc_col > 504 || kb.nk16 > 4 || kb.n > 256 || ul < 0 || kb.units * TC_UNIT > TC_SLOT)
+    if (a_slots > 255u || kb.acc_col > 504 || kb.nk16 > 4 || kb.n > 256 || ul < 0 || kb.units * TC_UNIT > Ring<false>::SLOT)
       return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block field overflow");
     packed[k] = a_slots | ((uint32_t)(kb.acc_col / 8) << 8) | ((uint32_t)(kb.n / 8) << 14) | ((uint32_t)kb.nk16 << 20) |
                 ((uint32_t)kb.first << 23) | ((uint32_t)ul << 24);
@@ -1007,8 +1065,36 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     if ((rc = alloc((void**)&s->prof, (size_t)(s->grid + 2 * TC_MAX_OPS) * 8 * sizeof(long long)))) return rc;
     CLD_CUDA_OK(h, cudaMemsetAsync(s->prof, 0, (size_t)(s->grid + 2 * TC_MAX_OPS) * 8 * sizeof(long long), stream));
   }
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  // CTA-pair kernel (default): the weight blob (all replicas) as a 2-D tensor of 128-byte rows; a box = the half of a k-block
+  // one CTA stages (N/2 = 8, 32 or 64 rows).  The blob is already swizzled, so the copies are flat (SWIZZLE_NONE).
+  s->pair = true;
+  if (const char* e = getenv("CLD_TC_PAIR")) s->pair = atoi(e) != 0;
+  memset(&s->tm8, 0, sizeof(CUtensorMap)); memset(&s->tm32, 0, sizeof(CUtensorMap)); memset(&s->tm64, 0, sizeof(CUtensorMap));
+  if (s->pair) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(h, CLD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if (B.w_bytes % 128) return fail(h, CLD_ERR_UNSUPPORTED, "internal: weight blob is not a whole number of 128-byte rows");
+    CUtensorMap* maps[3] = {&s->tm8, &s->tm32, &s->tm64};
+    const cuuint32_t rows[3] = {8, 32, 64};
+    for (int i = 0; i < 3; ++i) {
+      cuuint64_t dims[2] = {64, (cuuint64_t)(B.w_bytes / 128) * (cuuint64_t)s->wcopies};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, rows[i]}, es[2] = {1, 1};
+      const CUresult r = ((EncodeTiledFn)fn)(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)s->wblob, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(h, CLD_ERR_CUDA, "cuTensorMapEncodeTiled rejected the weight tensor (box of %u rows): %d", rows[i], (int)r);
+    }
+    for (const TcKb& kb : s->kbs)
+      if (kb.n != 16 && kb.n != 64 && kb.n != 128) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block of %d weight rows has no pair box", kb.n);
+  }
   CLD_CUDA_OK(h, cudaStreamSynchronize(stream));
   s->ready = true;
   (void)skip2_off;
@@ -1039,6 +1125,7 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
   TcParams P;
   P.tvec = tvec;
   P.ops = s->d_ops; P.n_ops = (int)s->ops.size(); P.kbs = s->d_kbs; P.n_kbs = (int)s->kbs.size(); P.wblob = s->wblob; P.wcopy_stride = s->wblob_bytes; P.wcopies = s->wcopies; P.par = s->par;
+  P.w_rows_per_copy = (int)(s->wblob_bytes / 128);
   P.tbias = h->tbias; P.tb_stride = h->unet.tb_total; P.x = x; P.eps = eps; P.R = R; P.T = h->cfg.horizon;
   P.n_groups = (R + TC_G - 1) / TC_G; P.skipbuf = s->skipbuf; P.skip_stride = s->skip_stride;
   const int T = h->cfg.horizon;
@@ -1046,8 +1133,23 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
   P.dbg_stage = h->dbg_out ? h->dbg_stage : -1; P.dbg_out = h->dbg_out;
   P.prof = s->prof;
   int grid = P.n_groups < s->grid ? P.n_groups : s->grid;
-  if (s->prof) unet_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, stream>>>(P);
-  else unet_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, stream>>>(P);
+  if (s->pair) {
+    const int n_pairs = (P.n_groups + 1) / 2, clusters = n_pairs < s->grid / 2 ? n_pairs : s->grid / 2;
+    grid = 2 * clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = s->prof ? cudaLaunchKernelEx(&cfg, unet_tc_kernel<true, true>, s->tm8, s->tm32, s->tm64, P)
+                            : cudaLaunchKernelEx(&cfg, unet_tc_kernel<false, true>, s->tm8, s->tm32, s->tm64, P);
+    if (e != cudaSuccess) return fail(h, CLD_ERR_CUDA, "launch of unet_tc_kernel (pair) failed: %s", cudaGetErrorString(e));
+  } else if (s->prof) {
+    unet_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, P);
+  } else {
+    unet_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, P);
+  }
   CLD_LAUNCH_OK(h, "unet_tc_kernel");
   if (s->prof) {
     // debug only (CLD_TC_PROF=1): per-CTA cycle counters of the three roles, printed for CTA 0 and averaged

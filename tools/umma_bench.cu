@@ -1,6 +1,8 @@
-// Microbenchmark (not part of the product): issue rate / latency of tcgen05.mma (M=128, K=16) chains.
-//   umma_bench : for N in {16,32,64,128,256} and nacc in {1,2,4}: cycles per MMA over 256 MMAs that rotate over
-//   `nacc` independent TMEM accumulators (nacc = 1: every MMA depends on the previous one's accumulator).
+// Microbenchmark (not part of the product): execution rate of tcgen05.mma (M=128, K=16, bf16, SS mode: both operands in
+// shared memory) as a function of N, with and without a concurrent stream of bulk copies (UBLKCP, global -> shared) into a
+// 4 x 16 KB ring, which is what the denoiser's weight producer does.  Answers: is an SS-mode MMA bound by its operand
+// fetch from shared memory, and how much of that bandwidth do the weight copies take?
+//   umma_bench [grid]
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -8,13 +10,19 @@
 #include "../controllable-latent-diffusion-for-traffic-simulation_b200/csrc/tc_common.cuh"
 using namespace cld::tc;
 
-__global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int same_ab, long long* out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+__global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int copy_bytes, const uint8_t* gsrc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];     // [0,64K) operands, [64K,128K) copy ring
+  __shared__ __align__(8) uint64_t bar, cbar[4];
   __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (64 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&cbar[i]), 1);
+    fence_barrier_init();
+    done = 0;
+  }
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_base_s), 512); tmem_relinquish(); }
   fence_proxy_async();
   tc_fence_before();
@@ -29,7 +37,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int sa
     if (elect_one()) {
       for (int i = 0; i < cnt; ++i) {
         const int a = i % nacc;
-        const int kk = same_ab ? 0 : (i & 3);
+        const int kk = i & 3;
         umma_bf16(tmem_base + a * N, ad0 + 2 * kk, bd0 + 2 * kk, idesc, i >= nacc ? 1u : 0u);
       }
       umma_commit(smem_u32(&bar));
@@ -38,7 +46,31 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int sa
     long long t1 = clock64();
     mbar_wait(smem_u32(&bar), 0);
     long long t2 = clock64();
+    done = 1;
     if (tid == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (warp == 1 && copy_bytes > 0) {
+    // copy stream: keep 4 bulk copies of copy_bytes in flight until the MMAs are done
+    long long copied = 0;
+    uint32_t par = 0;
+    const uint8_t* src = gsrc + (size_t)blockIdx.x * 65536;
+    if (elect_one()) {
+      for (int s = 0; s < 4; ++s) {
+        mbar_arrive_expect_tx(smem_u32(&cbar[s]), copy_bytes);
+        bulk_g2s(smem_u32(smem) + 65536 + s * 16384, src + s * 16384, copy_bytes, smem_u32(&cbar[s]));
+      }
+      int s = 0;
+      while (!done) {
+        mbar_wait(smem_u32(&cbar[s]), (par >> s) & 1u);
+        par ^= 1u << s;
+        copied += copy_bytes;
+        mbar_arrive_expect_tx(smem_u32(&cbar[s]), copy_bytes);
+        bulk_g2s(smem_u32(smem) + 65536 + s * 16384, src + s * 16384, copy_bytes, smem_u32(&cbar[s]));
+        s = (s + 1) & 3;
+      }
+      for (int k = 0; k < 4; ++k) { mbar_wait(smem_u32(&cbar[s]), (par >> s) & 1u); par ^= 1u << s; s = (s + 1) & 3; }
+      if (blockIdx.x == 0) out[2] = copied;
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -47,20 +79,23 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int sa
 
 int main(int argc, char** argv) {
   const int grid = argc > 1 ? atoi(argv[1]) : 1;
-  long long* d; cudaMalloc(&d, 16);
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  const int cnt = 256;
-  for (int N : {16, 32, 64, 128, 256})
-    for (int nacc : {1, 2, 4}) {
-      if (nacc * N > 512) continue;
-      long long h[2];
+  long long* d; cudaMalloc(&d, 32);
+  uint8_t* src; cudaMalloc(&src, (size_t)grid * 65536); cudaMemset(src, 0, (size_t)grid * 65536);
+  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+  const int cnt = 1024;
+  for (int copy_bytes : {0, 16384})
+    for (int N : {32, 64, 128, 256}) {
+      const int nacc = 512 / N > 4 ? 4 : (512 / N);
+      long long h[4] = {0, 0, 0, 0};
       for (int rep = 0; rep < 2; ++rep) {
-        bench<<<grid, 128, 65536>>>(N, nacc, cnt, 0, d);
-        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        cudaMemset(d, 0, 32);
+        bench<<<grid, 128, 131072>>>(N, nacc, cnt, copy_bytes, src, d);
+        cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
       }
       cudaError_t e = cudaGetLastError();
-      printf("N=%3d nacc=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %.1f) %s\n", N, nacc, (double)h[0] / cnt,
-             (double)h[1] / cnt, N * 0.5, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      const double cyc = (double)h[1] / cnt;
+      printf("grid %3d N=%3d nacc=%d copies %5d B: %.1f cyc/MMA (math floor %.1f), operand bytes/cyc %.1f, copy bytes/cyc %.1f %s\n", grid, N, nacc,
+             copy_bytes, cyc, N * 0.5, (4096.0 + N * 32.0) / cyc, (double)h[2] / (double)h[1], e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
   return 0;
 }
