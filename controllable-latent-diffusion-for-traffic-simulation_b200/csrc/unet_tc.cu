@@ -34,7 +34,10 @@ constexpr int TC_UNITS = 16;
 // weight ring (64 KB): every k-block takes one slot.  Single-CTA kernel: 4 slots of 16 KB (<= 128 weight rows x 128 B);
 // CTA-pair kernel: each CTA stages HALF of the rows of a k-block, 8 slots of 8 KB -> twice as many k-blocks in flight for the
 // same L2 -> SM bytes (the level-2 layers are bound by the latency of this stream, tools/umma_bench.cu)
-template <bool PAIR> struct Ring { static constexpr int SLOT = PAIR ? 8192 : 16384, SLOTS = PAIR ? 8 : 4; };
+// A slot carries a GROUP of consecutive k-blocks of one op (as many as fit): the issuer pays one full-barrier wait and one
+// ring-release commit per group, not per k-block -- with 4 MMAs per barrier round trip the single issuing thread, not the
+// tensor pipe, set the pace of the N = 256 layers (measured ~550 cycles per k-block for 256 cycles of math).
+template <bool PAIR> struct Ring { static constexpr int SLOT = 16384, SLOTS = 4; };
 static_assert(Ring<false>::SLOT * Ring<false>::SLOTS == TC_UNIT * TC_UNITS && Ring<true>::SLOT * Ring<true>::SLOTS == TC_UNIT * TC_UNITS, "ring size");
 constexpr int TC_EW = 16;                       // epilogue warps
 constexpr int TC_ETHREADS = TC_EW * 32;
@@ -69,8 +72,9 @@ static_assert(sizeof(TcOp) % 16 == 0, "TcOp is copied as uint4");
 
 // host-side k-block record; the device gets it packed in 32 bits:
 //   [0,8) A start in 1 KB slots (panel base + tap shift) | [8,14) TMEM column / 8 | [14,20) MMA N / 8 |
-//   [20,23) number of K=16 steps | [23] first (overwrite accumulator) | [24,26) log2(ring units)
-struct TcKb { int a_base, shift, w_off, acc_col, n, nk16, first, units; };
+//   [20,23) number of K=16 steps | [23] first (overwrite accumulator) | [24,26) log2(ring units) |
+//   [26] first k-block of its ring slot (wait for the slot) | [27] last k-block of its ring slot (release the slot)
+struct TcKb { int a_base, shift, w_off, acc_col, n, nk16, first, units, slot_first, slot_last; };
 
 // shared-memory layout (byte offsets from the 1024-aligned base)
 constexpr int SM_RING = TC_ARENA;
@@ -84,6 +88,14 @@ constexpr int SM_GLOB = SM_BARS + 40 * 8;                     // TcShared
 constexpr int TC_SMEM = SM_GLOB + 32;
 struct TcShared { uint32_t tmem_base, pad; uint8_t* skip_cta; };
 static_assert(TC_SMEM <= 232448, "shared memory budget");
+
+// What the MMA issuer reads, passed BY VALUE as a kernel parameter: it lives in the constant bank, so the (warp-uniform) loop
+// counters index it with uniform loads and the whole descriptor arithmetic stays on the uniform datapath.  Read from shared
+// memory the same values arrive in per-lane registers and every operand of every tcgen05.mma costs an R2UR: ~90 instructions per
+// k-block, ~450 cycles of a single warp's dependent issue for 256 cycles of math in the N = 256 layers.
+struct TcIssueOp { int n_g0, n_g1, n_g2, flags, n, nt, sbo, ts[4]; };     // ts: A start of m-tile i in 16-byte units (tile_slot0 * slot_stride * 64)
+struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint32_t kb[TC_MAX_KBS + 4]; };
+static_assert(sizeof(TcIssueTab) + 3 * 128 + 256 < 32000, "kernel parameters");
 
 struct TcParams {
   const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
@@ -100,6 +112,7 @@ struct TcState {
   std::vector<TcKb> kbs;
   TcOp* d_ops = nullptr; uint32_t* d_kbs = nullptr;
   uint8_t* wblob = nullptr; size_t wblob_bytes = 0; int wcopies = 1;
+  TcIssueTab* itab = nullptr;          // host copy of the issuer's table
   bool pair = false;                    // CTA-pair kernel (cluster of 2, tcgen05 cta_group::2); CLD_TC_PAIR=0 selects the single-CTA kernel
   CUtensorMap tm8, tm32, tm64;          // the weight blob as a 2-D tensor {64 bf16, rows}; boxes of 8 / 32 / 64 rows = half a k-block
   float* par = nullptr; size_t par_floats = 0;
@@ -133,6 +146,7 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ void epi_bar() { named_bar(1, TC_ETHREADS); }
+
 
 __device__ __forceinline__ void zero_halos(uint8_t* arena, int offB, int pitch, int npanels, int etid) {
   // per region: leading 2 slots of every panel + 2 tail slots after the last panel = (npanels+1) blocks of 2 KB
@@ -419,7 +433,8 @@ __device__ __forceinline__ void prefetch_params(const TcOp* o, const TcParams& P
 // leader's activation-ready barriers (remote mbarrier arrive for rank 1).
 template <bool PROF, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm32,
-                                                                const __grid_constant__ CUtensorMap tm64, const TcParams P) {
+                                                                const __grid_constant__ CUtensorMap tm64, const __grid_constant__ TcIssueTab IT,
+                                                                const TcParams P) {
   constexpr int TC_SLOT = Ring<PAIR>::SLOT, TC_SLOTS = Ring<PAIR>::SLOTS;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
@@ -438,7 +453,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(arena + SM_BARS);
   TcShared* gsh = reinterpret_cast<TcShared*>(arena + SM_GLOB);
   uint32_t* tmem_slot = &gsh->tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index goes through a full-mask shuffle: the compiler then knows that the role branches below are warp-uniform and
+  // keeps the issuer's / producer's loop state and descriptor arithmetic on the uniform datapath (the CUTLASS idiom)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_UNITS);
   const uint32_t bar_act = smem_u32(bars + 2 * TC_UNITS), bar_acc = smem_u32(bars + 2 * TC_UNITS + 2);
 
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
   if (warp == TC_EW) {
     // ===================== weight producer =====================
     // every k-block takes one 16 KB ring slot; all lanes walk the loop, one elected lane issues the copy
-    uint32_t par_empty = 0;
+    uint32_t par_empty = 0, slot_off = 0;
     int pos = 0;
     long long t_empty = 0;
     const uint32_t full0 = PAIR ? mapa_shared(bar_full, 0) : bar_full;       // pair: the leader's full barriers
@@ -479,26 +496,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
       for (int k = 0; k < P.n_kbs; ++k) {
         const uint32_t kb = kbs_s[k];
         const uint32_t n8 = (kb >> 14) & 0x3Fu;
-        const uint32_t bytes = n8 * (8u * 128u);
-        const long long tw0 = PROF ? clock64() : 0;
-        mbar_wait(bar_empty + 8 * pos, ((par_empty >> pos) & 1u) ^ 1u);
-        par_empty ^= 1u << pos;
-        if (PROF) t_empty += clock64() - tw0;
+        const uint32_t bytes = n8 * (8u * 128u);                 // whole k-block (both halves in pair mode)
+        if ((kb >> 26) & 1u) {
+          // first k-block of a slot: wait for the slot, announce the bytes of the whole group
+          uint32_t total = 0;
+          for (int j = k; ; ++j) { const uint32_t kj = kbs_s[j]; total += ((kj >> 14) & 0x3Fu) * (8u * 128u); if ((kj >> 27) & 1u) break; }
+          const long long tw0 = PROF ? clock64() : 0;
+          mbar_wait(bar_empty + 8 * pos, ((par_empty >> pos) & 1u) ^ 1u);
+          par_empty ^= 1u << pos;
+          if (PROF) t_empty += clock64() - tw0;
+          slot_off = 0;
+          if (elect_one()) {
+            if (PAIR) { if (leader) mbar_expect_tx_only(bar_full + 8 * pos, total); }
+            else mbar_arrive_expect_tx(bar_full + 8 * pos, total);
+          }
+          __syncwarp();
+        }
         if (elect_one()) {
           if (PAIR) {
             // this CTA's half of the weight rows: a box of N/2 rows starting at row + rank * N/2; completion on the leader's barrier
-            if (leader) mbar_expect_tx_only(bar_full + 8 * pos, bytes);
             const void* tm = n8 == 16u ? (const void*)&tm64 : (n8 == 8u ? (const void*)&tm32 : (const void*)&tm8);
-            tma2_load_2d(smem_u32(ring + pos * TC_SLOT), tm, 0, row + (int)(rank * n8 * 4u), full0 + 8 * pos);
+            tma2_load_2d(smem_u32(ring + pos * TC_SLOT) + slot_off, tm, 0, row + (int)(rank * n8 * 4u), full0 + 8 * pos);
           } else {
-            mbar_arrive_expect_tx(bar_full + 8 * pos, bytes);
-            bulk_g2s(smem_u32(ring + pos * TC_SLOT), src, bytes, bar_full + 8 * pos);
+            bulk_g2s(smem_u32(ring + pos * TC_SLOT) + slot_off, src, bytes, bar_full + 8 * pos);
           }
         }
         __syncwarp();
+        slot_off += PAIR ? bytes >> 1 : bytes;
         src += (size_t)(1u << ((kb >> 24) & 3)) * TC_UNIT;
         row += (int)(1u << ((kb >> 24) & 3)) * (TC_UNIT / 128);
-        pos = (pos + 1) & (TC_SLOTS - 1);
+        if ((kb >> 27) & 1u) pos = (pos + 1) & (TC_SLOTS - 1);
       }
     }
     if (PROF && lane == 0) { P.prof[blockIdx.x * 8 + 0] = t_empty; }
@@ -506,44 +533,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
     // ===================== MMA issuer (pair: the leader issues for both CTAs) =====================
     // all lanes walk the (warp-uniform) loop so that descriptors are computed on the uniform datapath; one elected
     // lane issues the tcgen05 instructions
-    uint32_t par_full = 0, opn = 0;
+    uint32_t par_full = 0, opn = 0, b_off = 0;
     int pos = 0;
-    bool ready = false;
-    uint32_t kb_next = kbs_s[0];
     long long t_full = 0, t_act = 0, t_issue = 0, t_commit = 0;
     const long long t_start = PROF ? clock64() : 0;
     const uint32_t arena_u = smem_u32(arena), ring_u = smem_u32(ring);
     const uint64_t b_const = make_desc_sw128(0, 1024);
     constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     for (int g = unit0; g < n_units; g += unit_step) {
-      kb_next = kbs_s[0];
-      for (int oi = 0; oi < P.n_ops; ++oi, ++opn) {
-        const TcOp* o = ops_s + oi;
-        const int N = o->n, nt = o->n_tiles, flags = o->flags;
-        const uint64_t a_const = make_desc_sw128(0, (uint32_t)o->sbo);
-        // A-descriptor start of each m-tile (kept in 4 registers: an indexed array would live in local memory)
-        const uint32_t ts0 = (arena_u >> 4) + (uint32_t)(o->tile_slot0[0] * o->slot_stride) * 64u;
-        const uint32_t ts1 = (arena_u >> 4) + (uint32_t)(o->tile_slot0[1] * o->slot_stride) * 64u;
-        const uint32_t ts2 = (arena_u >> 4) + (uint32_t)(o->tile_slot0[2] * o->slot_stride) * 64u;
-        const uint32_t ts3 = (arena_u >> 4) + (uint32_t)(o->tile_slot0[3] * o->slot_stride) * 64u;
-        int kbi = o->kb_first;
+      int kbi = 0;
+      for (int oi = 0; oi < IT.n_ops; ++oi, ++opn) {
+        const TcIssueOp& o = IT.op[oi];
+        const int N = o.n, nt = o.nt, flags = o.flags;
+        const int n_g0 = o.n_g0, n_g1 = o.n_g1, n_g2 = o.n_g2;
+        const uint64_t a_const = make_desc_sw128(0, (uint32_t)o.sbo);
+        const uint32_t ts0 = (arena_u >> 4) + (uint32_t)o.ts[0], ts1 = (arena_u >> 4) + (uint32_t)o.ts[1];
+        const uint32_t ts2 = (arena_u >> 4) + (uint32_t)o.ts[2], ts3 = (arena_u >> 4) + (uint32_t)o.ts[3];
         auto issue = [&](int count) {
           for (int k = 0; k < count; ++k, ++kbi) {
-            const uint32_t kb = kb_next;
-            kb_next = kbs_s[kbi + 1];                         // next record (the table has slack past the end)
+            const uint32_t kb = IT.kb[kbi];
             const uint32_t a_slots = kb & 0xFFu, acc_col = ((kb >> 8) & 0x3Fu) << 3, nk16 = (kb >> 20) & 7u;
             const uint32_t idesc = IDESC0 | (((kb >> 14) & 0x3Fu) << 17);
             const uint32_t accum = ((kb >> 23) & 1u) ^ 1u;
-            const long long tw0 = PROF ? clock64() : 0;
-            while (!ready) ready = mbar_try_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
-            if (PROF) t_full += clock64() - tw0;
-            par_full ^= 1u << pos;
-            tc_fence_after();
-            // probe the next slot now; the answer is consumed after this k-block's MMAs have been issued
-            const int pos_n = (pos + 1) & (TC_SLOTS - 1);
-            const bool ready_n = mbar_test_wait(bar_full + 8 * pos_n, (par_full >> pos_n) & 1u);   // non-blocking
-            const uint64_t bd0 = b_const + ((ring_u + pos * TC_SLOT) >> 4);
+            if ((kb >> 26) & 1u) {                            // first k-block of a ring slot: its weights have landed?
+              const long long tw0 = PROF ? clock64() : 0;
+              mbar_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
+              if (PROF) t_full += clock64() - tw0;
+              par_full ^= 1u << pos;
+              tc_fence_after();
+              b_off = 0;
+            }
+            const uint64_t bd0 = b_const + ((ring_u + pos * TC_SLOT + b_off) >> 4);
             const uint64_t a_kb = a_const + a_slots * 64u;
+            b_off += ((kb >> 14) & 0x3Fu) * (PAIR ? 512u : 1024u);
+            const bool release = (kb >> 27) & 1u;
             const long long ti0 = PROF ? clock64() : 0;
             if (elect_one()) {
 #pragma unroll
@@ -568,12 +591,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
                   }
                 }
               }
-              if (PAIR) umma2_commit_pair(bar_empty + 8 * pos); else umma_commit(bar_empty + 8 * pos);
+              if (release) { if (PAIR) umma2_commit_pair(bar_empty + 8 * pos); else umma_commit(bar_empty + 8 * pos); }
             }
             __syncwarp();
             if (PROF) t_issue += clock64() - ti0;
-            pos = pos_n;
-            ready = ready_n;
+            if (release) pos = (pos + 1) & (TC_SLOTS - 1);
           }
         };
         auto commit = [&](uint32_t bar) {
@@ -589,16 +611,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
         if (PROF) t_act += clock64() - tw1;
         if (tl) tl[1] = clock64();
         tc_fence_after();
-        issue(o->n_g0);
+        issue(n_g0);
         if (flags & F_SPLIT_K) {
           tw1 = PROF ? clock64() : 0;
           mbar_wait(bar_act + 8, ph);
           if (PROF) t_act += clock64() - tw1;
           tc_fence_after();
         }
-        issue(o->n_g1);
+        issue(n_g1);
         if (flags & F_COMMIT_SPLIT) commit(bar_acc);
-        issue(o->n_g2);
+        issue(n_g2);
         if (!(flags & F_COMMIT_SPLIT)) commit(bar_acc);
         commit(bar_acc + 8);
         if (tl) tl[2] = clock64();
@@ -806,7 +828,7 @@ struct Builder {
         kb.acc_col = acc_col; kb.n = rows;
         kb.nk16 = cv.dup4 ? 1 : ((cv.cin - p * 64 >= 64) ? 4 : (cv.cin - p * 64 + 15) / 16);
         kb.first = first ? 1 : 0;
-        kb.units = units;
+        kb.units = units; kb.slot_first = 1; kb.slot_last = 1;
         first = false;
         s->kbs.push_back(kb);
         ++count;
@@ -1035,6 +1057,29 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     CLD_CUDA_OK(h, cudaMemcpyAsync(s->wblob + (size_t)cpy * B.w_bytes, s->wblob, B.w_bytes, cudaMemcpyDeviceToDevice, stream));
   for (const auto& j : B.pars) tc_copy_scale_kernel<<<(j.n + 255) / 256, 256, 0, stream>>>(s->par + j.off, j.src, j.n, j.scale);
   CLD_LAUNCH_OK(h, "tc_copy_scale_kernel");
+  // ring-slot groups: consecutive k-blocks of one issue group (G0 | G1 | G2 of an op) with the same N share a slot while their
+  // bytes (per CTA: half the rows in pair mode) fit; a k-block smaller than a 4 KB unit is not contiguous with its successor
+  s->pair = true;
+  if (const char* e = getenv("CLD_TC_PAIR")) s->pair = atoi(e) != 0;
+  {
+    int max_group = 8;
+    if (const char* e = getenv("CLD_TC_KBGROUP")) { int v = atoi(e); if (v >= 1 && v <= 8) max_group = v; }
+    for (const TcOp& o : s->ops) {
+      const int lens[3] = {o.n_g0, o.n_g1, o.n_g2};
+      int k = o.kb_first;
+      for (int gi = 0; gi < 3; ++gi) {
+        const int end = k + lens[gi];
+        while (k < end) {
+          const int n = s->kbs[k].n;
+          const int per_cta = s->pair ? n * 64 : n * 128;
+          int cnt = 1;
+          while (k + cnt < end && cnt < max_group && s->kbs[k + cnt].n == n && n * 128 >= TC_UNIT && (cnt + 1) * per_cta <= Ring<true>::SLOT) ++cnt;
+          for (int j = 0; j < cnt; ++j) { s->kbs[k + j].slot_first = j == 0; s->kbs[k + j].slot_last = j == cnt - 1; }
+          k += cnt;
+        }
+      }
+    }
+  }
   std::vector<uint32_t> packed(s->kbs.size());
   size_t expect_off = 0;
   for (size_t k = 0; k < s->kbs.size(); ++k) {
@@ -1047,12 +1092,26 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     if (a_slots > 255u || kb.acc_col > 504 || kb.nk16 > 4 || kb.n > 256 || ul < 0 || kb.units * TC_UNIT > Ring<false>::SLOT)
       return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block field overflow");
     packed[k] = a_slots | ((uint32_t)(kb.acc_col / 8) << 8) | ((uint32_t)(kb.n / 8) << 14) | ((uint32_t)kb.nk16 << 20) |
-                ((uint32_t)kb.first << 23) | ((uint32_t)ul << 24);
+                ((uint32_t)kb.first << 23) | ((uint32_t)ul << 24) | ((uint32_t)kb.slot_first << 26) | ((uint32_t)kb.slot_last << 27);
   }
-  for (const TcOp& o : s->ops) {
-    size_t end = (size_t)o.kb_first + o.n_g0 + o.n_g1 + o.n_g2;
-    if (end > s->kbs.size()) return fail(h, CLD_ERR_UNSUPPORTED, "internal: op k-block range");
+  {
+    size_t next = 0;
+    for (const TcOp& o : s->ops) {
+      if ((size_t)o.kb_first != next) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-blocks of the ops are not consecutive");
+      next += (size_t)(o.n_g0 + o.n_g1 + o.n_g2);
+    }
+    if (next != s->kbs.size()) return fail(h, CLD_ERR_UNSUPPORTED, "internal: op k-block range");
   }
+  if (!s->itab) s->itab = new TcIssueTab();
+  memset(s->itab, 0, sizeof(TcIssueTab));
+  s->itab->n_ops = (int)s->ops.size(); s->itab->n_kbs = (int)s->kbs.size();
+  for (size_t i = 0; i < s->ops.size(); ++i) {
+    const TcOp& o = s->ops[i];
+    TcIssueOp& d = s->itab->op[i];
+    d.n_g0 = o.n_g0; d.n_g1 = o.n_g1; d.n_g2 = o.n_g2; d.flags = o.flags; d.n = o.n; d.nt = o.n_tiles; d.sbo = o.sbo;
+    for (int t = 0; t < 4; ++t) d.ts[t] = o.tile_slot0[t] * o.slot_stride * 64;
+  }
+  for (size_t k = 0; k < packed.size(); ++k) s->itab->kb[k] = packed[k];
   if ((rc = alloc((void**)&s->d_ops, s->ops.size() * sizeof(TcOp)))) return rc;
   if ((rc = alloc((void**)&s->d_kbs, packed.size() * sizeof(uint32_t)))) return rc;
   CLD_CUDA_OK(h, cudaMemcpyAsync(s->d_ops, s->ops.data(), s->ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice, stream));
@@ -1071,8 +1130,6 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   // CTA-pair kernel (default): the weight blob (all replicas) as a 2-D tensor of 128-byte rows; a box = the half of a k-block
   // one CTA stages (N/2 = 8, 32 or 64 rows).  The blob is already swizzled, so the copies are flat (SWIZZLE_NONE).
-  s->pair = true;
-  if (const char* e = getenv("CLD_TC_PAIR")) s->pair = atoi(e) != 0;
   memset(&s->tm8, 0, sizeof(CUtensorMap)); memset(&s->tm32, 0, sizeof(CUtensorMap)); memset(&s->tm64, 0, sizeof(CUtensorMap));
   if (s->pair) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1142,13 +1199,13 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = s->prof ? cudaLaunchKernelEx(&cfg, unet_tc_kernel<true, true>, s->tm8, s->tm32, s->tm64, P)
-                            : cudaLaunchKernelEx(&cfg, unet_tc_kernel<false, true>, s->tm8, s->tm32, s->tm64, P);
+    cudaError_t e = s->prof ? cudaLaunchKernelEx(&cfg, unet_tc_kernel<true, true>, s->tm8, s->tm32, s->tm64, *s->itab, P)
+                            : cudaLaunchKernelEx(&cfg, unet_tc_kernel<false, true>, s->tm8, s->tm32, s->tm64, *s->itab, P);
     if (e != cudaSuccess) return fail(h, CLD_ERR_CUDA, "launch of unet_tc_kernel (pair) failed: %s", cudaGetErrorString(e));
   } else if (s->prof) {
-    unet_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, P);
+    unet_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, *s->itab, P);
   } else {
-    unet_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, P);
+    unet_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, *s->itab, P);
   }
   CLD_LAUNCH_OK(h, "unet_tc_kernel");
   if (s->prof) {
@@ -1178,7 +1235,7 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
 }
 
 void tc_destroy(CldHandle* h) {
-  if (h->tc) { delete st_of(h); h->tc = nullptr; }
+  if (h->tc) { delete st_of(h)->itab; delete st_of(h); h->tc = nullptr; }
 }
 
 }  // namespace cld

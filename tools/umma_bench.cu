@@ -84,8 +84,9 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
   const int cnt = 1024;
   for (int copy_bytes : {0, 16384})
-    for (int N : {32, 64, 128, 256}) {
-      const int nacc = 512 / N > 4 ? 4 : (512 / N);
+    for (int N : {32, 64, 128, 256})
+    for (int nacc : {1, 2, 4}) {
+      if (nacc * N > 512) continue;
       long long h[4] = {0, 0, 0, 0};
       for (int rep = 0; rep < 2; ++rep) {
         cudaMemset(d, 0, 32);
