@@ -18,6 +18,7 @@
 // in registers between the statistics pass and the normalise pass).
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include <cuda.h>
@@ -46,7 +47,7 @@ constexpr int TC_ARENA = 128 * 1024;
 constexpr int TB_LD = 260;            // padded row stride of the time-bias tile (bank-conflict free float4 reads)
 constexpr int PAR_ROWS = 5;           // conv bias, GN gamma, GN beta, residual-conv bias, time vector
 constexpr int TC_MAX_OPS = 32;
-constexpr int TC_MAX_KBS = 1280;
+constexpr int TC_MAX_KBS = 768;
 constexpr int TC_RES_COL = 256;       // TMEM: accumulators in columns [0,256), residual 1x1 conv in [256,512)
 
 enum { EPI_GN_TB = 0, EPI_GN_RES_ACC = 1, EPI_GN_RES_ID = 2, EPI_BIAS = 3, EPI_UP = 4, EPI_GN = 5, EPI_OUT = 6 };
@@ -94,7 +95,13 @@ static_assert(TC_SMEM <= 232448, "shared memory budget");
 // memory the same values arrive in per-lane registers and every operand of every tcgen05.mma costs an R2UR: ~90 instructions per
 // k-block, ~450 cycles of a single warp's dependent issue for 256 cycles of math in the N = 256 layers.
 struct TcIssueOp { int n_g0, n_g1, n_g2, flags, n, nt, sbo, ts[4]; };     // ts: A start of m-tile i in 16-byte units (tile_slot0 * slot_stride * 64)
-struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint32_t kb[TC_MAX_KBS + 4]; };
+// one record per k-block -- or per PAIR of consecutive k-blocks of a single-m-tile op (KB_DUAL: the issuer's loop overhead per
+// iteration, ~300 cycles of barrier / constant-load / elect latency, is then paid once per 8 MMAs instead of once per 4):
+// x = A start (16-byte units from the arena base), y = A start of the second k-block, z = instruction descriptor,
+// w = [0] four K=16 steps (else one) | [1] accumulate | [2] first record of its ring slot | [3] last one | [4] dual |
+//     [5,14) TMEM column of the accumulator | [16,32) bytes / 16 this CTA stages per k-block
+enum { KB_K4 = 1, KB_ACC = 2, KB_SLOT_FIRST = 4, KB_SLOT_LAST = 8, KB_DUAL = 16 };
+struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint4 kb[TC_MAX_KBS]; };
 static_assert(sizeof(TcIssueTab) + 3 * 128 + 256 < 32000, "kernel parameters");
 
 struct TcParams {
@@ -162,6 +169,20 @@ __device__ __forceinline__ void zero_halos(uint8_t* arena, int offB, int pitch, 
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+
+// tcgen05.mma with the 64-bit descriptors given as (low, high) words: the start-address field lives in the low word and never
+// carries, so a tap / K-step / tile offset is ONE 32-bit add instead of an add-with-carry pair
+template <bool PAIR>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 struct EpiCtx {
   uint8_t* arena; const float* par; const float* tb_s; float2* st; uint32_t lane_addr;
@@ -257,21 +278,26 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
     if (k < nch) {
       const int vt = (cpt == 1) ? k : ((cpt == 2) ? (k >> 1) : 0);
       const int lo = o->tile_lo[vt], hi = o->tile_hi[vt];
-      if (!(q * 4 + 4 <= lo || q * 4 >= hi)) {           // warp-uniform: some row of this warp is valid
-        actm |= 1u << k;
-        uint32_t r[8];
-        tmem_ld8(cx.lane_addr + vt * N + c0 + (k & (cpt - 1)) * 8, r);
-        v[k][0] = pk2u(r[0], r[1]); v[k][1] = pk2u(r[2], r[3]); v[k][2] = pk2u(r[4], r[5]); v[k][3] = pk2u(r[6], r[7]);
-      }
+      if (!(q * 4 + 4 <= lo || q * 4 >= hi)) actm |= 1u << k;           // warp-uniform: some row of this warp is valid
       if (sl >= lo && sl < hi) validm |= 1u << k;
     }
   }
-  tmem_wait_ld();
-  if (cx.tl) cx.tl[0] = clock64();
-  // ---- pass 1: conv bias, statistics over (time, channels of the group) per batch row
+  // ---- pass 1: conv bias, statistics over (time, channels of the group) per batch row.  Software pipeline over the chunks: the
+  // tensor-memory read of chunk k + 1 (64 B / cycle for the whole SM, ~250 cycles per chunk with 16 warps reading) is in flight
+  // while chunk k is summed (tcgen05.wait::ld waits for ALL outstanding loads, so the next one is issued right after the wait)
+  auto load_chunk = [&](int k) {
+    const int vt = (cpt == 1) ? k : ((cpt == 2) ? (k >> 1) : 0);
+    uint32_t r[8];
+    tmem_ld8(cx.lane_addr + vt * N + c0 + (k & (cpt - 1)) * 8, r);
+    v[k][0] = pk2u(r[0], r[1]); v[k][1] = pk2u(r[2], r[3]); v[k][2] = pk2u(r[4], r[5]); v[k][3] = pk2u(r[6], r[7]);
+  };
+  if (actm & 1u) load_chunk(0);
   uint64_t s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    tmem_wait_ld();
+    if (k == 0 && cx.tl) cx.tl[0] = clock64();
+    if (k + 1 < 4 && ((actm >> (k + 1)) & 1u)) load_chunk(k + 1);
     if (!((actm >> k) & 1u)) continue;
     const int c = c0 + (k & (cpt - 1)) * 8;
     const float4 b0 = *reinterpret_cast<const float4*>(cx.par + c), b1 = *reinterpret_cast<const float4*>(cx.par + c + 4);
@@ -538,24 +564,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
     long long t_full = 0, t_act = 0, t_issue = 0, t_commit = 0;
     const long long t_start = PROF ? clock64() : 0;
     const uint32_t arena_u = smem_u32(arena), ring_u = smem_u32(ring);
-    const uint64_t b_const = make_desc_sw128(0, 1024);
-    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    const uint32_t arena16 = arena_u >> 4, ring16 = ring_u >> 4;
+    const uint32_t b_hi = (uint32_t)(make_desc_sw128(0, 1024) >> 32);
     for (int g = unit0; g < n_units; g += unit_step) {
       int kbi = 0;
       for (int oi = 0; oi < IT.n_ops; ++oi, ++opn) {
         const TcIssueOp& o = IT.op[oi];
         const int N = o.n, nt = o.nt, flags = o.flags;
         const int n_g0 = o.n_g0, n_g1 = o.n_g1, n_g2 = o.n_g2;
-        const uint64_t a_const = make_desc_sw128(0, (uint32_t)o.sbo);
-        const uint32_t ts0 = (arena_u >> 4) + (uint32_t)o.ts[0], ts1 = (arena_u >> 4) + (uint32_t)o.ts[1];
-        const uint32_t ts2 = (arena_u >> 4) + (uint32_t)o.ts[2], ts3 = (arena_u >> 4) + (uint32_t)o.ts[3];
-        auto issue = [&](int count) {
+        const uint32_t a_hi = (uint32_t)(make_desc_sw128(0, (uint32_t)o.sbo) >> 32);
+        const uint32_t ts0 = arena16 + (uint32_t)o.ts[0], ts1 = arena16 + (uint32_t)o.ts[1];
+        const uint32_t ts2 = arena16 + (uint32_t)o.ts[2], ts3 = arena16 + (uint32_t)o.ts[3];
+        // `count` k-blocks of an op with NT m-tiles (compile-time: no per-tile branches in the loop)
+        auto issue_nt = [&](int count, auto nt_c) {
+          constexpr int NT = decltype(nt_c)::value;
           for (int k = 0; k < count; ++k, ++kbi) {
-            const uint32_t kb = IT.kb[kbi];
-            const uint32_t a_slots = kb & 0xFFu, acc_col = ((kb >> 8) & 0x3Fu) << 3, nk16 = (kb >> 20) & 7u;
-            const uint32_t idesc = IDESC0 | (((kb >> 14) & 0x3Fu) << 17);
-            const uint32_t accum = ((kb >> 23) & 1u) ^ 1u;
-            if ((kb >> 26) & 1u) {                            // first k-block of a ring slot: its weights have landed?
+            const uint4 rec = IT.kb[kbi];
+            if (rec.w & KB_SLOT_FIRST) {                      // first k-block of a ring slot: its weights have landed?
               const long long tw0 = PROF ? clock64() : 0;
               mbar_wait(bar_full + 8 * pos, (par_full >> pos) & 1u);
               if (PROF) t_full += clock64() - tw0;
@@ -563,40 +588,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
               tc_fence_after();
               b_off = 0;
             }
-            const uint64_t bd0 = b_const + ((ring_u + pos * TC_SLOT + b_off) >> 4);
-            const uint64_t a_kb = a_const + a_slots * 64u;
-            b_off += ((kb >> 14) & 0x3Fu) * (PAIR ? 512u : 1024u);
-            const bool release = (kb >> 27) & 1u;
+            const uint32_t b_lo = ring16 + (uint32_t)pos * (TC_SLOT / 16) + b_off;
+            const uint32_t b16 = rec.w >> 16, d_col = (rec.w >> 5) & 0x1FFu;
+            b_off += (NT == 1 && (rec.w & KB_DUAL)) ? 2u * b16 : b16;
+            const uint32_t acc = (rec.w >> 1) & 1u;
             const long long ti0 = PROF ? clock64() : 0;
             if (elect_one()) {
 #pragma unroll
-              for (int mt = 0; mt < 4; ++mt) {
-                if (mt < nt) {
-                  const uint64_t ad0 = a_kb + (mt == 0 ? ts0 : mt == 1 ? ts1 : mt == 2 ? ts2 : ts3);
-                  const uint32_t d_addr = tmem_base + acc_col + mt * N;
-                  if (PAIR) {
-                    umma2_bf16(d_addr, ad0, bd0, idesc, accum);
-                    if (nk16 > 1) {
-                      umma2_bf16(d_addr, ad0 + 2, bd0 + 2, idesc, 1u);
-                      umma2_bf16(d_addr, ad0 + 4, bd0 + 4, idesc, 1u);
-                      umma2_bf16(d_addr, ad0 + 6, bd0 + 6, idesc, 1u);
-                    }
-                  } else {
-                    umma_bf16(d_addr, ad0, bd0, idesc, accum);
-                    if (nk16 > 1) {
-                      umma_bf16(d_addr, ad0 + 2, bd0 + 2, idesc, 1u);
-                      umma_bf16(d_addr, ad0 + 4, bd0 + 4, idesc, 1u);
-                      umma_bf16(d_addr, ad0 + 6, bd0 + 6, idesc, 1u);
-                    }
-                  }
+              for (int mt = 0; mt < NT; ++mt) {
+                const uint32_t a_lo = rec.x + (mt == 0 ? ts0 : mt == 1 ? ts1 : mt == 2 ? ts2 : ts3);
+                const uint32_t d_addr = tmem_base + d_col + mt * N;
+                umma_lohi<PAIR>(d_addr, a_lo, a_hi, b_lo, b_hi, rec.z, acc);
+                if (rec.w & KB_K4) {
+                  umma_lohi<PAIR>(d_addr, a_lo + 2, a_hi, b_lo + 2, b_hi, rec.z, 1u);
+                  umma_lohi<PAIR>(d_addr, a_lo + 4, a_hi, b_lo + 4, b_hi, rec.z, 1u);
+                  umma_lohi<PAIR>(d_addr, a_lo + 6, a_hi, b_lo + 6, b_hi, rec.z, 1u);
+                }
+                if (NT == 1 && (rec.w & KB_DUAL)) {            // second k-block of the record (always 4 K steps, accumulating)
+                  const uint32_t a1 = rec.y + ts0, b1 = b_lo + b16;
+                  umma_lohi<PAIR>(d_addr, a1, a_hi, b1, b_hi, rec.z, 1u);
+                  umma_lohi<PAIR>(d_addr, a1 + 2, a_hi, b1 + 2, b_hi, rec.z, 1u);
+                  umma_lohi<PAIR>(d_addr, a1 + 4, a_hi, b1 + 4, b_hi, rec.z, 1u);
+                  umma_lohi<PAIR>(d_addr, a1 + 6, a_hi, b1 + 6, b_hi, rec.z, 1u);
                 }
               }
-              if (release) { if (PAIR) umma2_commit_pair(bar_empty + 8 * pos); else umma_commit(bar_empty + 8 * pos); }
+              if (rec.w & KB_SLOT_LAST) { if (PAIR) umma2_commit_pair(bar_empty + 8 * pos); else umma_commit(bar_empty + 8 * pos); }
             }
             __syncwarp();
             if (PROF) t_issue += clock64() - ti0;
-            if (release) pos = (pos + 1) & (TC_SLOTS - 1);
+            if (rec.w & KB_SLOT_LAST) pos = (pos + 1) & (TC_SLOTS - 1);
           }
+        };
+        auto issue = [&](int count) {
+          if (nt == 1) issue_nt(count, std::integral_constant<int, 1>());
+          else if (nt == 2) issue_nt(count, std::integral_constant<int, 2>());
+          else if (nt == 3) issue_nt(count, std::integral_constant<int, 3>());
+          else issue_nt(count, std::integral_constant<int, 4>());
         };
         auto commit = [&](uint32_t bar) {
           if (elect_one()) { if (PAIR) umma2_commit_pair(bar); else umma_commit(bar); }
@@ -1111,7 +1138,49 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     d.n_g0 = o.n_g0; d.n_g1 = o.n_g1; d.n_g2 = o.n_g2; d.flags = o.flags; d.n = o.n; d.nt = o.n_tiles; d.sbo = o.sbo;
     for (int t = 0; t < 4; ++t) d.ts[t] = o.tile_slot0[t] * o.slot_stride * 64;
   }
-  for (size_t k = 0; k < packed.size(); ++k) s->itab->kb[k] = packed[k];
+  {
+    int dual = 1;
+    if (const char* e = getenv("CLD_TC_DUAL")) dual = atoi(e) != 0;
+    int nrec = 0;
+    for (size_t i = 0; i < s->ops.size(); ++i) {
+      const TcOp& o = s->ops[i];
+      TcIssueOp& d = s->itab->op[i];
+      const int lens[3] = {o.n_g0, o.n_g1, o.n_g2};
+      int* out_len[3] = {&d.n_g0, &d.n_g1, &d.n_g2};
+      int k = o.kb_first;
+      for (int gi = 0; gi < 3; ++gi) {
+        const int end = k + lens[gi];
+        int cnt = 0;
+        while (k < end) {
+          const TcKb& kb = s->kbs[k];
+          if (kb.nk16 != 1 && kb.nk16 != 4) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block with %d K=16 steps", kb.nk16);
+          const uint32_t per_cta16 = (uint32_t)(s->pair ? kb.n * 64 : kb.n * 128) / 16u;
+          uint4 r;
+          r.x = (uint32_t)(kb.a_base / 1024 + kb.shift) * 64u;
+          r.y = 0;
+          r.z = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kb.n >> 3) << 17) | ((uint32_t)((s->pair ? 256 : 128) >> 4) << 24);
+          r.w = (kb.nk16 == 4 ? KB_K4 : 0u) | (kb.first ? 0u : KB_ACC) | (kb.slot_first ? KB_SLOT_FIRST : 0u) | ((uint32_t)kb.acc_col << 5) | (per_cta16 << 16);
+          bool last = kb.slot_last;
+          int used = 1;
+          if (dual && o.n_tiles == 1 && !kb.slot_last && k + 1 < end) {
+            const TcKb& k2 = s->kbs[k + 1];
+            if (kb.nk16 == 4 && k2.nk16 == 4 && !k2.first && k2.acc_col == kb.acc_col && k2.n == kb.n && !k2.slot_first) {
+              r.y = (uint32_t)(k2.a_base / 1024 + k2.shift) * 64u;
+              r.w |= KB_DUAL;
+              last = k2.slot_last;
+              used = 2;
+            }
+          }
+          if (last) r.w |= KB_SLOT_LAST;
+          if (nrec >= TC_MAX_KBS) return fail(h, CLD_ERR_UNSUPPORTED, "internal: issuer table overflow");
+          s->itab->kb[nrec++] = r;
+          k += used; ++cnt;
+        }
+        *out_len[gi] = cnt;
+      }
+    }
+    s->itab->n_kbs = nrec;
+  }
   if ((rc = alloc((void**)&s->d_ops, s->ops.size() * sizeof(TcOp)))) return rc;
   if ((rc = alloc((void**)&s->d_kbs, packed.size() * sizeof(uint32_t)))) return rc;
   CLD_CUDA_OK(h, cudaMemcpyAsync(s->d_ops, s->ops.data(), s->ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice, stream));

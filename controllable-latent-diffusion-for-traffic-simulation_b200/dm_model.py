@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .keys import agents_per_scene
+from .keys import agents_per_scene as _agents_per_scene
 
 
 class _Slot(nn.Module):
@@ -286,7 +286,7 @@ class DmModel(nn.Module):
         scene, A = None, agents_per_scene
         if guidance is not None or want_indicators:
             if A is None:
-                A = agents_per_scene(data_batch.get('scene_index'), B)
+                A = _agents_per_scene(data_batch.get('scene_index'), B)
             elif B % A:
                 raise ValueError("B=%d agents is not a multiple of agents_per_scene=%d" % (B, A))
         dev_seed = (seed or 0) if use_device_rng else 0

@@ -93,8 +93,11 @@ def _gpu_model(models_cpu, precision, sched):
     return dm, vae, algo
 
 
-# per-step bounds: (rel(x_next) outside flipped signs, sign agreement, zero-set agreement)
-BOUNDS = {"bf16": (1e-2, 0.995, 0.999), "fp32": (1e-4, 0.999, 0.9999)}
+# per-step bounds: (rel(x_next) outside flipped signs, sign agreement, zero-set agreement) and the bound on the sign agreement
+# averaged over the 49 guided steps.  bf16: the denoiser output differs from the oracle's by ~8.5e-3 relative, so the guidance
+# gradient is evaluated at a slightly different mean and elements whose gradient is ~0 relative to the row maximum may change
+# sign (measured: 0 .. 0.15 % of the elements per step, worst single step 0.5 %); fp32: no flips observed.
+BOUNDS = {"bf16": (1e-2, 0.99, 0.999, 0.995), "fp32": (1e-4, 0.999, 0.9999, 0.9995)}
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
@@ -105,8 +108,9 @@ def test_teacher_forced_guided_ddim_every_step(models_cpu, case, precision):
     eng = dm.engine(R)
     scene = eng.make_scene(case["batch"], S, A, N)
     cond, curr = case["aux"]["cond_feat"].cuda(), case["aux"]["curr_states"].cuda()
-    tol, sign_min, zero_min = BOUNDS[precision]
+    tol, sign_min, zero_min, sign_mean_min = BOUNDS[precision]
     worst = dict(rel=0.0, sign=1.0, zero=1.0, flip=0.0, eps=0.0)
+    signs = []
     for rec in case["trace"]:
         i, i_next = rec["i"], rec["i_next"]
         x_t = rec["x_t"].cuda()
@@ -130,14 +134,17 @@ def test_teacher_forced_guided_ddim_every_step(models_cpu, case, precision):
         r = rel(x_next.cpu()[same], rec["x_next"][same])
         print("step t=%2d  rel(eps) %.2e  rel(x_next | same sign) %.2e  sign agreement %.5f  zero-set agreement %.5f  "
               "flipped %.5f  grad non-zero %.3f" % (i, r_eps, r, sign_agree, zero_agree, flip, nz.float().mean().item()))
+        signs.append(sign_agree)
         worst["rel"], worst["eps"] = max(worst["rel"], r), max(worst["eps"], r_eps)
         worst["sign"], worst["zero"], worst["flip"] = min(worst["sign"], sign_agree), min(worst["zero"], zero_agree), max(worst["flip"], flip)
         assert r_eps <= tol, (i, r_eps)
         assert r <= tol, (i, r)
         assert sign_agree >= sign_min, (i, sign_agree)
         assert zero_agree >= zero_min, (i, zero_agree)
-    print("teacher-forced %s: worst rel(eps) %.2e, worst rel(x_next) %.2e, min sign agreement %.5f, min zero-set agreement %.5f, "
-          "max flipped fraction %.5f" % (precision, worst["eps"], worst["rel"], worst["sign"], worst["zero"], worst["flip"]))
+    mean_sign = sum(signs) / len(signs)
+    print("teacher-forced %s: worst rel(eps) %.2e, worst rel(x_next) %.2e, sign agreement mean %.5f min %.5f, min zero-set agreement %.5f, "
+          "max flipped fraction %.5f" % (precision, worst["eps"], worst["rel"], mean_sign, worst["sign"], worst["zero"], worst["flip"]))
+    assert mean_sign >= sign_mean_min, mean_sign
 
 
 # free-running bounds, from the measured values (printed): fraction of latents that end on the other side of a sign flip
