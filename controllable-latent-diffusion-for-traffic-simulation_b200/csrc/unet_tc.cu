@@ -101,7 +101,8 @@ struct TcIssueOp { int n_g0, n_g1, n_g2, flags, n, nt, sbo, ts[4]; };     // ts:
 // w = [0] four K=16 steps (else one) | [1] accumulate | [2] first record of its ring slot | [3] last one | [4] dual |
 //     [5,14) TMEM column of the accumulator | [16,32) bytes / 16 this CTA stages per k-block
 enum { KB_K4 = 1, KB_ACC = 2, KB_SLOT_FIRST = 4, KB_SLOT_LAST = 8, KB_DUAL = 16 };
-struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint4 kb[TC_MAX_KBS]; };
+// `ops`: the full op records for the epilogue warps (uniform loads instead of a chain of shared-memory loads per op and half)
+struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint4 kb[TC_MAX_KBS]; TcOp ops[TC_MAX_OPS]; };
 static_assert(sizeof(TcIssueTab) + 3 * 128 + 256 < 32000, "kernel parameters");
 
 struct TcParams {
@@ -219,7 +220,11 @@ __device__ __forceinline__ void dump_stage(const TcOp* o, const EpiCtx& cx) {
 // GroupNorm + Mish (+ time bias | + residual) for ONE GroupNorm group (CPG channels) of one half of the op,
 // over the warp's 32 GEMM rows x NVT m-tiles.  NVT * CPG values per thread stay in registers between the passes;
 // both passes walk them in 8-channel chunks with compiler barriers in between to keep the live set small.
+#ifdef TC_NO_FENCE
+#define TC_SCHED_FENCE()
+#else
 #define TC_SCHED_FENCE() asm volatile("" ::: "memory")
+#endif
 __device__ __forceinline__ EpiCtx make_epi_ctx(uint8_t* smem, const float* par) {
   EpiCtx cx;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -263,7 +268,13 @@ __device__ __forceinline__ uint64_t mish2_log2(uint64_t t) {
 // warp's 32 GEMM rows.  The thread's values are `nch` chunks of 8 channels held in registers between the statistics
 // pass and the normalise pass; chunk k belongs to m-tile k / cpt and covers channels c0 + (k % cpt) * 8.
 // (n_vt, cpg) = (4,8) (2,16) (1,32): 4 chunks; (2,8) (1,16): 2.  gamma / beta arrive pre-scaled by log2(e).
+#ifdef TC_NO_FENCE
+#define TC_SCHED_FENCE()
+#else
 #define TC_SCHED_FENCE() asm volatile("" ::: "memory")
+#endif
+// (Tried and dropped, twice: refilling the registers of every finished chunk with the same chunk of the NEXT half during the
+// normalise pass, to hide its ~1 100 cycles of tensor-memory reads.  The reads slow the pass down by as much as they save.)
 __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
   const int EPI = o->epi;
   const int q = cx.q, lane = cx.lane, b = lane & 7, sl = q * 4 + (lane >> 3);
@@ -671,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
       const int g = PAIR ? 2 * u + (int)rank : u;
       cx.g = g;
       // ---- stage the latent x [8,T,4] fp32 as bf16 hi/lo channels 0..7 of panel 0 (region A, level 0)
-      prefetch_params(ops_s, P, par_s, tb_s, g, etid);
+      prefetch_params(IT.ops, P, par_s, tb_s, g, etid);
       zero_halos(arena, P.zero0_offB, P.zero0_pitch, P.zero0_npanels, etid);
       for (int i = etid; i < P.T * TC_G; i += TC_ETHREADS) {
         int t = i >> 3, bb = i & 7, r = g * TC_G + bb;
@@ -687,12 +698,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) { mbar_arrive_cluster(act0); mbar_arrive_cluster(act0 + 8); }
+        if (PAIR) { mbar_arrive_remote(act0); mbar_arrive_remote(act0 + 8); }
         else { mbar_arrive(bar_act); mbar_arrive(bar_act + 8); }
       }
 
       for (int oi = 0; oi < P.n_ops; ++oi, ++opn) {
-        const TcOp* o = ops_s + oi;
+        const TcOp* o = IT.ops + oi;
         cp_async_wait_all();
         epi_bar();                                   // parameters of this op are visible to every epilogue thread
         if (o->epi == EPI_GN_TB) {
@@ -744,7 +755,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && oi + 1 < P.n_ops) {
-            if (PAIR) mbar_arrive_cluster(act0 + 8 * h); else mbar_arrive(bar_act + 8 * h);
+            if (PAIR) mbar_arrive_remote(act0 + 8 * h); else mbar_arrive(bar_act + 8 * h);
           }
           if (tl) tl[4 + 2 * h] = clock64();
         }
@@ -1135,6 +1146,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   for (size_t i = 0; i < s->ops.size(); ++i) {
     const TcOp& o = s->ops[i];
     TcIssueOp& d = s->itab->op[i];
+    s->itab->ops[i] = o;
     d.n_g0 = o.n_g0; d.n_g1 = o.n_g1; d.n_g2 = o.n_g2; d.flags = o.flags; d.n = o.n; d.nt = o.n_tiles; d.sbo = o.sbo;
     for (int t = 0; t < 4; ++t) d.ts[t] = o.tile_slot0[t] * o.slot_stride * 64;
   }
