@@ -482,9 +482,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_decode_tc_kernel(const Lst
 namespace {
 constexpr int LB_THREADS = 576;
 constexpr int LBK_DG = 0;                               // [layer][hi, lo][gate] x 4 KB (+ 4 KB: the prologue scratch aliases this region)
-constexpr int LBK_SCR_BYTES = 17 * LT_OP;
-constexpr int LBK_DACT = LBK_DG + LBK_SCR_BYTES;        // fp32 [32 rows][T][2], scaled
-__host__ __device__ constexpr int lbk_scale(int T) { return LBK_DACT + LT_RB * T * 2 * 4; }      // float [32] 1 / scale
+// 17 operand tiles, or the prologue scratch when that is larger (horizon > 52: 134 KB at T = 104), rounded to 1 KB
+__host__ __device__ constexpr int lbk_scr(int T) {
+  return (LT_RB * (T * 6 + 4 * (T + 1)) * 4 > 17 * LT_OP) ? ((LT_RB * (T * 6 + 4 * (T + 1)) * 4 + 1023) / 1024) * 1024 : 17 * LT_OP;
+}
+__host__ __device__ constexpr int lbk_dact(int T) { return LBK_DG + lbk_scr(T); }                 // fp32 [32 rows][T][2], scaled
+__host__ __device__ constexpr int lbk_scale(int T) { return lbk_dact(T) + LT_RB * T * 2 * 4; }    // float [32] 1 / scale
 __host__ __device__ constexpr int lbk_hw(int T) { return lbk_scale(T) + LT_RB * 4; }             // hid2act weights [2][64]
 __host__ __device__ constexpr int lbk_dzs(int T) { return lbk_hw(T) + 2 * LT_H * 4; }            // float [32 rows][4]: dz of one step
 __host__ __device__ constexpr int lbk_bars(int T) { return lbk_dzs(T) + LT_RB * 4 * 4; }          // m1[2], m0, e1, e0, dz, dzfree
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
   const uint32_t bar_m1 = bars, bar_m0 = bars + 16, bar_e1 = bars + 24, bar_e0 = bars + 32, bar_dz = bars + 40, bar_dzfree = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + lbk_bars(T) + 64);
   float* dzs = reinterpret_cast<float*>(sm + lbk_dzs(T));
-  float* dact = reinterpret_cast<float*>(sm + LBK_DACT);
+  float* dact = reinterpret_cast<float*>(sm + lbk_dact(T));
   float* inv_scale = reinterpret_cast<float*>(sm + lbk_scale(T));
   float* hw = reinterpret_cast<float*>(sm + lbk_hw(T));
 
@@ -866,8 +869,6 @@ static int lstm_tc_prepare(CldHandle* h, cudaStream_t s) {
   lstm_tc_pack_bwd_kernel<<<(LB_WCOLS * 128 + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(st->wbwd), w.wih0_raw, w.whh0_raw, w.wih1_raw, w.whh1_raw);
   CLD_LAUNCH_OK(h, "lstm_tc_pack_bwd_kernel");
   if (lbk_smem(h->cfg.horizon) + 1024 > 232448) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the tensor-core LSTM backward");
-  if (LT_RB * (h->cfg.horizon * 6 + 4 * (h->cfg.horizon + 1)) * 4 > LBK_SCR_BYTES)
-    return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the LSTM backward prologue scratch");
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lb_smem_req(h->cfg.horizon)));
   CLD_CUDA_OK(h, cudaFuncSetAttribute(lstm_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lb_smem_req(h->cfg.horizon)));
   h->lstm_tc = st;

@@ -43,7 +43,7 @@ static_assert(Ring<false>::SLOT * Ring<false>::SLOTS == TC_UNIT * TC_UNITS && Ri
 constexpr int TC_EW = 16;                       // epilogue warps
 constexpr int TC_ETHREADS = TC_EW * 32;
 constexpr int TC_THREADS = 64 + TC_ETHREADS;
-constexpr int TC_ARENA = 128 * 1024;
+constexpr int TC_ARENA = 136 * 1024;   // split-time mode at level 2: 2 regions x 4 panels x (13 + 4) slots
 constexpr int TB_LD = 260;            // padded row stride of the time-bias tile (bank-conflict free float4 reads)
 constexpr int PAR_ROWS = 5;           // conv bias, GN gamma, GN beta, residual-conv bias, time vector
 constexpr int TC_MAX_OPS = 32;
@@ -82,8 +82,7 @@ constexpr int SM_RING = TC_ARENA;
 constexpr int SM_PAR = SM_RING + TC_UNITS * TC_UNIT;          // float [2][PAR_ROWS][256]
 constexpr int SM_TB = SM_PAR + 2 * PAR_ROWS * 256 * 4;        // float [8][TB_LD]
 constexpr int SM_ST = SM_TB + TC_G * TB_LD * 4;               // float2 [2][4 cq][4 quadrants][8 rows]
-constexpr int SM_OPS = SM_ST + 2 * 4 * 4 * 8 * 8;             // TcOp [TC_MAX_OPS]
-constexpr int SM_KBS = SM_OPS + TC_MAX_OPS * (int)sizeof(TcOp);   // uint32 [TC_MAX_KBS]
+constexpr int SM_KBS = SM_ST + 2 * 4 * 4 * 8 * 8;             // uint32 [TC_MAX_KBS] (the producer's k-block records)
 constexpr int SM_BARS = SM_KBS + TC_MAX_KBS * 4;              // full[16], empty[16], act[2], acc[2]
 constexpr int SM_GLOB = SM_BARS + 40 * 8;                     // TcShared
 constexpr int TC_SMEM = SM_GLOB + 32;
@@ -109,6 +108,11 @@ struct TcParams {
   const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
   const uint8_t* wblob; size_t wcopy_stride; int wcopies; int w_rows_per_copy; const float* par; const float* tbias; const float* tvec; int tb_stride;
   const float* x; float* eps; int R, T, n_groups;
+  // split-time mode (horizon 2 * T, e.g. 104): a CTA carries 4 rows; GEMM lane b = half * 4 + row holds time [half * T, (half + 1) * T)
+  // of row b & 3, so the arena / tensor-memory budget is the one of T.  The two halves of a row meet at the inner edges: every
+  // panel has its own leading and trailing halo (pitch T' + 4 slots), the inner ones carry copies of the partner lane's edge slots
+  // (written by whoever writes the data), the outer ones are zero; GroupNorm statistics are summed over both lanes of a row.
+  int tsplit;
   uint8_t* skipbuf; int skip_stride;
   int zero0_pitch, zero0_npanels, zero0_offB;
   int dbg_stage; float* dbg_out;
@@ -121,6 +125,8 @@ struct TcState {
   TcOp* d_ops = nullptr; uint32_t* d_kbs = nullptr;
   uint8_t* wblob = nullptr; size_t wblob_bytes = 0; int wcopies = 1;
   TcIssueTab* itab = nullptr;          // host copy of the issuer's table
+  bool tsplit = false; int t_eff = 0;   // split-time mode (horizon > 56): lanes of t_eff = horizon / 2 steps
+  int zero0_pitch = 0, zero0_offB = 0;
   bool pair = false;                    // CTA-pair kernel (cluster of 2, tcgen05 cta_group::2); CLD_TC_PAIR=0 selects the single-CTA kernel
   CUtensorMap tm8, tm32, tm64;          // the weight blob as a 2-D tensor {64 bf16, rows}; boxes of 8 / 32 / 64 rows = half a k-block
   float* par = nullptr; size_t par_floats = 0;
@@ -156,6 +162,22 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 __device__ __forceinline__ void epi_bar() { named_bar(1, TC_ETHREADS); }
 
 
+// batch row of GEMM lane b of group g; split-time mode: 4 rows per group, lane b = half * 4 + row
+__device__ __forceinline__ int row_of(int g, int b, int tsplit) { return tsplit ? g * 4 + (b & 3) : g * TC_G + b; }
+
+// split-time mode: outer halos = leading halo (slots 0, 1 of the panel) of the half-0 lanes (rows 0..3 of the slot) and trailing halo
+// (slots T' + 2, T' + 3) of the half-1 lanes (rows 4..7); 512 bytes each, both regions, every panel
+__device__ __forceinline__ void zero_halos_split(uint8_t* arena, int offB, int pitch, int npanels, int etid) {
+  const int per_panel = 2 * 2 * 32;                 // {leading, trailing} x 2 slots x 32 uint4 (4 rows x 128 B)
+  for (int i = etid; i < 2 * npanels * per_panel; i += TC_ETHREADS) {
+    const int w = i & 31, sl = (i >> 5) & 1, tr = (i >> 6) & 1, pp = i >> 7;
+    const int reg = pp / npanels, p = pp - reg * npanels;
+    uint8_t* base = arena + (reg ? offB : 0) + p * pitch;
+    uint4* dst = reinterpret_cast<uint4*>(base + (tr ? (pitch - 2048 + sl * 1024 + 512) : sl * 1024)) + w;
+    *dst = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 __device__ __forceinline__ void zero_halos(uint8_t* arena, int offB, int pitch, int npanels, int etid) {
   // per region: leading 2 slots of every panel + 2 tail slots after the last panel = (npanels+1) blocks of 2 KB
   const int blocks = 2 * (npanels + 1);
@@ -187,10 +209,21 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
 
 struct EpiCtx {
   uint8_t* arena; const float* par; const float* tb_s; float2* st; uint32_t lane_addr;
-  int q, cq, lane, etid, g;
+  int q, cq, lane, etid, g, tsplit;
   uint8_t* skip_cta; float* dbg_out; int dbg_stage; int R;
   long long* tl;   // profiling build only: per-item phase timestamps
 };
+
+// split-time mode: an edge slot of lane b is also the inner halo of its partner lane (the other half of the same row): the first two
+// slots of a half-1 lane are the trailing halo (slots T', T' + 1) of lane b - 4, the last two of a half-0 lane the leading halo
+// (slots -2, -1) of lane b + 4.  `panel` = start of the panel (its slot -2).
+__device__ __forceinline__ void store_inner_halo(uint8_t* panel, int t_out, int slot, int b, int c, const uint4& pk) {
+  int bp, hs;
+  if (b >= 4 && slot < 2) { bp = b - 4; hs = t_out + 2 + slot; }
+  else if (b < 4 && slot >= t_out - 2) { bp = b + 4; hs = slot - (t_out - 2); }
+  else return;
+  *reinterpret_cast<uint4*>(panel + hs * 1024 + bp * 128 + ((((c >> 3) & 7) ^ bp) << 4)) = pk;
+}
 
 // store 8 consecutive channels of one (slot, batch row) as bf16: next layer's A operand (+ skip buffer, + debug tap)
 __device__ __forceinline__ void store_chunk(const TcOp* o, const EpiCtx& cx, const float (&y)[8], int c, int slot, int b, bool valid) {
@@ -198,6 +231,7 @@ __device__ __forceinline__ void store_chunk(const TcOp* o, const EpiCtx& cx, con
   uint4 pk = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
   const int sw = ((((c >> 3) & 7) ^ b) << 4);
   *reinterpret_cast<uint4*>(cx.arena + o->dst_off + (slot + 2) * 1024 + b * 128 + (c >> 6) * o->dst_pitch + sw) = pk;
+  if (cx.tsplit) store_inner_halo(cx.arena + o->dst_off + (c >> 6) * o->dst_pitch, o->t_out, slot, b, c, pk);
   if (o->save_skip >= 0)
     *reinterpret_cast<uint4*>(cx.skip_cta + o->save_skip + ((size_t)(c >> 6) * o->t_out + slot) * 1024 + b * 128 + sw) = pk;
 }
@@ -207,11 +241,12 @@ __device__ __forceinline__ void dump_stage(const TcOp* o, const EpiCtx& cx) {
   const int chunks = o->cout >> 3, total = o->t_out * TC_G * chunks;
   for (int i = cx.etid; i < total; i += TC_ETHREADS) {
     const int ch = i % chunks, b = (i / chunks) & 7, slot = i / (chunks * 8), c = ch * 8;
-    const int row = cx.g * TC_G + b;
+    const int row = row_of(cx.g, b, cx.tsplit);
     if (row >= cx.R) continue;
     const uint4 pk = *reinterpret_cast<const uint4*>(cx.arena + o->dst_off + (slot + 2) * 1024 + b * 128 + (c >> 6) * o->dst_pitch +
                                                      ((((c >> 3) & 7) ^ b) << 4));
-    float* dp = cx.dbg_out + ((size_t)row * o->t_out + slot) * o->cout + c;
+    float* dp = cx.tsplit ? cx.dbg_out + ((size_t)row * 2 * o->t_out + (b >> 2) * o->t_out + slot) * o->cout + c
+                          : cx.dbg_out + ((size_t)row * o->t_out + slot) * o->cout + c;
     float2 f0 = unpack_bf16(pk.x), f1 = unpack_bf16(pk.y), f2 = unpack_bf16(pk.z), f3 = unpack_bf16(pk.w);
     dp[0] = f0.x; dp[1] = f0.y; dp[2] = f1.x; dp[3] = f1.y; dp[4] = f2.x; dp[5] = f2.y; dp[6] = f3.x; dp[7] = f3.y;
   }
@@ -234,7 +269,7 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(uint8_t* smem, const float* par) 
   const TcShared* gs = reinterpret_cast<const TcShared*>(smem + SM_GLOB);
   cx.lane_addr = gs->tmem_base + ((uint32_t)(cx.q * 32) << 16);
   cx.skip_cta = gs->skip_cta;
-  cx.g = 0; cx.dbg_out = nullptr; cx.dbg_stage = -1; cx.R = 0; cx.tl = nullptr;
+  cx.g = 0; cx.dbg_out = nullptr; cx.dbg_stage = -1; cx.R = 0; cx.tl = nullptr; cx.tsplit = 0;
   return cx;
 }
 
@@ -337,8 +372,13 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
   uint64_t rstd2, nmean2;
   {
     const float2 p0 = st[b], p1 = st[8 + b], p2 = st[16 + b], p3 = st[24 + b];   // fixed order: deterministic
-    const float S = ((p0.x + p1.x) + p2.x) + p3.x, SS = ((p0.y + p1.y) + p2.y) + p3.y;
-    const float inv_n = __frcp_rn((float)(t_out * cpg));
+    float S = ((p0.x + p1.x) + p2.x) + p3.x, SS = ((p0.y + p1.y) + p2.y) + p3.y;
+    if (cx.tsplit) {                                          // the other half of the row (a + b is symmetric: both lanes get the same bits)
+      const int bp = b ^ 4;
+      const float2 r0 = st[bp], r1 = st[8 + bp], r2 = st[16 + bp], r3 = st[24 + bp];
+      S += ((r0.x + r1.x) + r2.x) + r3.x; SS += ((r0.y + r1.y) + r2.y) + r3.y;
+    }
+    const float inv_n = __frcp_rn((float)((cx.tsplit ? 2 : 1) * t_out * cpg));
     const float mean = S * inv_n;
     const float var = fmaxf(SS * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
@@ -387,6 +427,7 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
       }
       const uint4 pk = make_uint4(pack_bf16_2(y[0]), pack_bf16_2(y[1]), pack_bf16_2(y[2]), pack_bf16_2(y[3]));
       *reinterpret_cast<uint4*>(dp) = pk;
+      if (cx.tsplit) store_inner_halo(cx.arena + o->dst_off + (c >> 6) * dst_pitch, t_out, slot, b, c, pk);
       if (save_skip >= 0)
         *reinterpret_cast<uint4*>(cx.skip_cta + save_skip + ((size_t)(c >> 6) * t_out + slot) * 1024 + b * 128 + sw) = pk;
     }
@@ -400,7 +441,7 @@ __device__ __forceinline__ void epi_plain(const TcOp* o, const EpiCtx& cx, int h
   const int N = o->n, nt = o->n_tiles, epi = o->epi;
   if (epi == EPI_OUT) {
     if (h != 0 || cx.cq != 0) return;
-    const int row = cx.g * TC_G + b;
+    const int row = row_of(cx.g, b, cx.tsplit);
     for (int vt = 0; vt < o->n_vt; ++vt) {
       const int lo = o->tile_lo[vt], hi = o->tile_hi[vt];
       if (q * 4 + 4 <= lo || q * 4 >= hi) continue;
@@ -411,7 +452,8 @@ __device__ __forceinline__ void epi_plain(const TcOp* o, const EpiCtx& cx, int h
       if (sl >= lo && sl < hi && row < cx.R) {
         float4 ov = make_float4(__uint_as_float(r[0]) + cx.par[0], __uint_as_float(r[1]) + cx.par[1],
                                 __uint_as_float(r[2]) + cx.par[2], __uint_as_float(r[3]) + cx.par[3]);
-        reinterpret_cast<float4*>(P.eps)[(size_t)row * P.T + slot] = ov;
+        const size_t ti = cx.tsplit ? (size_t)row * 2 * P.T + (b >> 2) * P.T + slot : (size_t)row * P.T + slot;
+        reinterpret_cast<float4*>(P.eps)[ti] = ov;
       }
     }
     return;
@@ -448,7 +490,7 @@ __device__ __forceinline__ void prefetch_params(const TcOp* o, const TcParams& P
       for (int i = etid; i < q4; i += TC_ETHREADS) cp_async16(smem_u32(par_buf + 1024 + i * 4), P.tvec + o->tb_off + i * 4);
       for (int i = etid; i < TC_G * q4; i += TC_ETHREADS) {
         const int bb = i / q4, c4 = i - bb * q4;
-        int r = g * TC_G + bb;
+        int r = row_of(g, bb, P.tsplit);
         r = r < P.R ? r : P.R - 1;
         cp_async16(smem_u32(tb_s + bb * TB_LD + c4 * 4), P.tbias + (size_t)r * P.tb_stride + o->tb_off + c4 * 4);
       }
@@ -485,7 +527,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
   float* par_s = reinterpret_cast<float*>(arena + SM_PAR);
   float* tb_s = reinterpret_cast<float*>(arena + SM_TB);
   float2* st_s = reinterpret_cast<float2*>(arena + SM_ST);
-  TcOp* ops_s = reinterpret_cast<TcOp*>(arena + SM_OPS);
   uint32_t* kbs_s = reinterpret_cast<uint32_t*>(arena + SM_KBS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(arena + SM_BARS);
   TcShared* gsh = reinterpret_cast<TcShared*>(arena + SM_GLOB);
@@ -496,8 +537,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_UNITS);
   const uint32_t bar_act = smem_u32(bars + 2 * TC_UNITS), bar_acc = smem_u32(bars + 2 * TC_UNITS + 2);
 
-  for (int i = tid; i < P.n_ops * (int)(sizeof(TcOp) / 16); i += TC_THREADS)
-    reinterpret_cast<uint4*>(ops_s)[i] = reinterpret_cast<const uint4*>(P.ops)[i];
   for (int i = tid; i < P.n_kbs; i += TC_THREADS) kbs_s[i] = P.kbs[i];
   if (tid == 0) {
     for (int i = 0; i < TC_UNITS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -672,7 +711,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
     cx.arena = arena; cx.tb_s = tb_s; cx.st = st_s;
     cx.lane_addr = tmem_base + ((uint32_t)(cx.q * 32) << 16);
     cx.skip_cta = P.skipbuf + (size_t)blockIdx.x * P.skip_stride;
-    cx.dbg_out = P.dbg_out; cx.dbg_stage = P.dbg_stage; cx.R = P.R; cx.tl = nullptr;
+    cx.dbg_out = P.dbg_out; cx.dbg_stage = P.dbg_stage; cx.R = P.R; cx.tl = nullptr; cx.tsplit = P.tsplit;
     const int etid = cx.etid;
     uint32_t opn = 0;
     long long t_acc = 0;
@@ -683,11 +722,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
       cx.g = g;
       // ---- stage the latent x [8,T,4] fp32 as bf16 hi/lo channels 0..7 of panel 0 (region A, level 0)
       prefetch_params(IT.ops, P, par_s, tb_s, g, etid);
-      zero_halos(arena, P.zero0_offB, P.zero0_pitch, P.zero0_npanels, etid);
-      for (int i = etid; i < P.T * TC_G; i += TC_ETHREADS) {
-        int t = i >> 3, bb = i & 7, r = g * TC_G + bb;
+      if (P.tsplit) zero_halos_split(arena, P.zero0_offB, P.zero0_pitch, P.zero0_npanels, etid);
+      else zero_halos(arena, P.zero0_offB, P.zero0_pitch, P.zero0_npanels, etid);
+      // split-time mode: lane bb = half * 4 + row covers times [half * T, half * T + T); the slots -2, -1 / T, T + 1 of a lane are its
+      // inner halo where the other half of the row continues (zero outside [0, 2T): those lines are the outer halo, zeroed above)
+      const int t_lo = P.tsplit ? -2 : 0, t_n = P.tsplit ? P.T + 4 : P.T;
+      for (int i = etid; i < t_n * TC_G; i += TC_ETHREADS) {
+        const int t = (i >> 3) + t_lo, bb = i & 7, r = row_of(g, bb, P.tsplit);
+        const int tg = P.tsplit ? (bb >> 2) * P.T + t : t, t_full = P.tsplit ? 2 * P.T : P.T;
+        if (tg < 0 || tg >= t_full) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < P.R) v = reinterpret_cast<const float4*>(P.x)[(size_t)r * P.T + t];
+        if (r < P.R) v = reinterpret_cast<const float4*>(P.x)[(size_t)r * t_full + tg];
         float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
         float hz = __bfloat162float(__float2bfloat16_rn(v.z)), hw = __bfloat162float(__float2bfloat16_rn(v.w));
         uint4 c0 = make_uint4(pack_bf16(hx, hy), pack_bf16(hz, hw), pack_bf16(v.x - hx, v.y - hy), pack_bf16(v.z - hz, v.w - hw));
@@ -739,7 +784,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
           }
           if (h == 1) {
             // ---- level change: zero the halo slots of the new layout; reload a skip connection
-            if (o->zero_pitch) zero_halos(arena, o->zero_offB, o->zero_pitch, o->zero_npanels, etid);
+            if (o->zero_pitch) {
+              if (P.tsplit) zero_halos_split(arena, o->zero_offB, o->zero_pitch, o->zero_npanels, etid);
+              else zero_halos(arena, o->zero_offB, o->zero_pitch, o->zero_npanels, etid);
+            }
             if (o->load_skip >= 0) {
               epi_bar();     // the skip stores of this CTA (possibly by this very op) are complete and visible
               const uint8_t* gp = cx.skip_cta + o->load_skip;
@@ -748,6 +796,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
                 int p = i / per_panel, w = i - p * per_panel;
                 *reinterpret_cast<uint4*>(arena + o->load_off + p * o->load_pitch + 2048 + w * 16) =
                     *reinterpret_cast<const uint4*>(gp + (size_t)i * 16);
+              }
+              if (P.tsplit) {
+                // inner halos of the reloaded tensor, straight from the skip buffer: lane b >= 4 continues lane b - 4 (its last two
+                // slots), lane b < 4 is continued by lane b + 4 (its first two slots); 16-byte chunk i of a lane sits at (i ^ lane)
+                for (int i = etid; i < o->load_npanels * 128; i += TC_ETHREADS) {
+                  const int ch = i & 7, bb = (i >> 3) & 7, j = (i >> 6) & 1, p = i >> 7;
+                  const int bp = bb ^ 4, src_slot = bb >= 4 ? o->load_T - 2 + j : j, dst_slot = bb >= 4 ? j : o->load_T + 2 + j;
+                  *reinterpret_cast<uint4*>(arena + o->load_off + p * o->load_pitch + dst_slot * 1024 + bb * 128 + ((ch ^ bb) << 4)) =
+                      *reinterpret_cast<const uint4*>(gp + ((size_t)p * o->load_T + src_slot) * 1024 + bp * 128 + ((ch ^ bp) << 4));
+                }
               }
             }
           }
@@ -797,8 +855,9 @@ static TcState* st_of(CldHandle* h) { return reinterpret_cast<TcState*>(h->tc); 
 
 bool tc_enabled(const CldHandle* h) {
   const CldConfig& c = h->cfg;
-  return c.precision == CLD_PREC_BF16 && c.dims[0] == 64 && c.dims[1] == 128 && c.dims[2] == 256 && c.horizon <= 64 &&
-         c.horizon >= 16 && c.latent_dim == 4;
+  // horizon 16..56: 8 rows per CTA; 64..112 (multiple of 8): split-time mode, 4 rows per CTA as two half-horizon lanes each
+  const bool t_ok = (c.horizon >= 16 && c.horizon <= 56) || (c.horizon >= 64 && c.horizon <= 112 && c.horizon % 8 == 0);
+  return c.precision == CLD_PREC_BF16 && c.dims[0] == 64 && c.dims[1] == 128 && c.dims[2] == 256 && t_ok && c.latent_dim == 4;
 }
 
 int tc_pack_block(CldHandle* h, int exec_idx, int cin, int cout, const float* c0w, const float* c0b, const float* g0,
@@ -891,12 +950,18 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   TcState* s = st_of(h);
   if (!s) return fail(h, CLD_ERR_STATE, "tc_finalize without weights");
   const CldConfig& c = h->cfg;
-  const int T = c.horizon;
+  s->tsplit = c.horizon > 56;
+  const int T = s->tsplit ? c.horizon / 2 : c.horizon;
+  s->t_eff = T;
   Level L[3];
   const int np[3] = {1, 2, 4};
   for (int l = 0; l < 3; ++l) {
     Level& v = L[l];
-    v.T = T >> l; v.pitch = (v.T + 2) * 1024; v.npanels = np[l]; v.offB = np[l] * v.pitch + 2048;
+    v.T = T >> l; v.npanels = np[l];
+    // 8-row mode: the 2 halo slots between two panels are shared (both zero); split-time mode: every panel has its own leading and
+    // trailing halo, because the inner one carries the partner lane's edge slots
+    if (s->tsplit) { v.pitch = (v.T + 4) * 1024; v.offB = np[l] * v.pitch; }
+    else { v.pitch = (v.T + 2) * 1024; v.offB = np[l] * v.pitch + 2048; }
     v.n_tiles = (v.T + 15) / 16;
     for (int i = 0; i < 4; ++i) { v.slot0[i] = 0; v.lo[i] = 0; v.hi[i] = 0; }
     for (int i = 0; i < v.n_tiles; ++i) {
@@ -906,7 +971,10 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
       v.hi[i] = (v.T - v.slot0[i] < 16) ? v.T - v.slot0[i] : 16;
     }
     // every 16-slot tile read (plus taps, plus stride-2 reads from the level above) must stay inside the arena
-    if (v.offB + v.npanels * v.pitch + 5 * 1024 > TC_ARENA) return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the bf16 arena");
+    // (split-time mode: the regions fill the arena exactly; the reads of masked rows past its end land in the weight ring)
+    if (s->tsplit ? (v.offB + v.npanels * v.pitch > TC_ARENA) : (v.offB + v.npanels * v.pitch + 5 * 1024 > TC_ARENA))
+      return fail(h, CLD_ERR_UNSUPPORTED, "horizon too long for the bf16 arena");
+    if (l == 0) { s->zero0_pitch = v.pitch; s->zero0_offB = v.offB; }
   }
   Builder B{s};
   s->ops.clear(); s->kbs.clear();
@@ -1264,10 +1332,10 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
   P.tvec = tvec;
   P.ops = s->d_ops; P.n_ops = (int)s->ops.size(); P.kbs = s->d_kbs; P.n_kbs = (int)s->kbs.size(); P.wblob = s->wblob; P.wcopy_stride = s->wblob_bytes; P.wcopies = s->wcopies; P.par = s->par;
   P.w_rows_per_copy = (int)(s->wblob_bytes / 128);
-  P.tbias = h->tbias; P.tb_stride = h->unet.tb_total; P.x = x; P.eps = eps; P.R = R; P.T = h->cfg.horizon;
-  P.n_groups = (R + TC_G - 1) / TC_G; P.skipbuf = s->skipbuf; P.skip_stride = s->skip_stride;
-  const int T = h->cfg.horizon;
-  P.zero0_pitch = (T + 2) * 1024; P.zero0_npanels = 1; P.zero0_offB = (T + 2) * 1024 + 2048;
+  P.tbias = h->tbias; P.tb_stride = h->unet.tb_total; P.x = x; P.eps = eps; P.R = R; P.T = s->t_eff; P.tsplit = s->tsplit ? 1 : 0;
+  const int rows_per_group = s->tsplit ? 4 : TC_G;
+  P.n_groups = (R + rows_per_group - 1) / rows_per_group; P.skipbuf = s->skipbuf; P.skip_stride = s->skip_stride;
+  P.zero0_pitch = s->zero0_pitch; P.zero0_npanels = 1; P.zero0_offB = s->zero0_offB;
   P.dbg_stage = h->dbg_out ? h->dbg_stage : -1; P.dbg_out = h->dbg_out;
   P.prof = s->prof;
   int grid = P.n_groups < s->grid ? P.n_groups : s->grid;

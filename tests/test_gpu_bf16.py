@@ -264,8 +264,10 @@ def test_ppo_mode_sampler_bf16_outputs(bf16_models, models_cpu):
 
 def test_bf16_mode_rejects_unsupported_horizon():
     from cld_b200.engine import Engine
-    with pytest.raises(RuntimeError, match="bf16 tensor-core path"):
-        Engine(horizon=104, precision="bf16", max_rows=8)
+    for bad in (60, 100, 120):            # 16..56 and 64..112 (multiples of 8) are supported
+        with pytest.raises(RuntimeError, match="bf16 tensor-core path"):
+            Engine(horizon=bad, precision="bf16", max_rows=8)
+    Engine(horizon=104, precision="bf16", max_rows=8).close()
 
 
 def test_lanes_give_the_single_engine_result(models_cpu):
@@ -289,3 +291,96 @@ def test_lanes_give_the_single_engine_result(models_cpu):
     for o in outs[1:]:
         for k in ("pred_traj", "traj", "offroad", "coll"):
             assert torch.equal(outs[0][k], o[k]), k
+
+
+# ----------------------------------------------------------------------------------------------------
+# horizon 104 (cfg3): split-time mode of the tensor-core denoiser (4 rows per CTA as two 52-step lanes with halo exchange)
+# ----------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bf16_t104():
+    from cld_b200 import default_algo_config
+    from cld_b200.dm_model import DmModel
+    from cld_b200.vae import VaeModel
+    algo = default_algo_config()
+    algo.horizon = 104
+    torch.manual_seed(0)
+    dm = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=10, precision="bf16", max_rows=1024).cuda()
+    vae = VaeModel(algo).bind(dm)
+    torch.manual_seed(0)
+    dm32 = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=10, max_rows=1024).cuda()
+    VaeModel(algo).bind(dm32)
+    return dm, vae, dm32, algo
+
+
+def test_unet_bf16_t104_every_stage_vs_oracle_and_reference_golden(bf16_t104, gold):
+    g = gold("unet")
+    dm, _, _, _ = bf16_t104
+    x, cond, t = torch.tensor(g["x104"]), torch.tensor(g["cond"][:3]), torch.tensor(g["t"][:3])
+    taps = {}
+    with torch.no_grad():
+        O.unet_forward(cpu_sd(dm.model), x, cond, t, taps=taps)
+    eng = dm.engine(x.shape[0])
+    for i, nm in enumerate(STAGES):
+        _, dbg = eng.unet_forward(x.cuda(), cond.cuda(), t.cuda(), debug_stage=i)
+        want = taps[nm].reshape(x.shape[0], -1)
+        r = rel(dbg, want)
+        print("T=104 stage %2d %-14s rel=%.3e" % (i, nm, r))
+        assert dbg.shape == want.shape, nm
+        assert r < 2e-2, (nm, r)
+    eps = eng.unet_forward(x.cuda(), cond.cuda(), t.cuda())
+    r = rel(eps, g["eps104"])                                  # the REAL reference's output (oracle/make_golden.py)
+    print("T=104 eps rel=%.3e vs the reference golden" % r)
+    assert r < BF16_TOL
+
+
+def test_unet_bf16_t104_many_rows_vs_fp32_path(bf16_t104):
+    """R = 611 rows: 153 groups of 4 rows (ragged last group, > 74 CTA pairs -> every pair loops, odd number of groups) vs the fp32 path."""
+    dm, _, dm32, _ = bf16_t104
+    torch.manual_seed(3)
+    R = 611
+    x, cond = torch.randn(R, 104, 4).cuda(), torch.randn(R, 256).cuda()
+    t = torch.randint(0, 10, (R,)).cuda()
+    a = dm.engine(R).unet_forward(x, cond, t)
+    b = dm32.engine(R).unet_forward(x, cond, t)
+    assert torch.isfinite(a).all()
+    per_row = ((a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1)).max().item()
+    print("T=104 bf16 vs fp32 path: rel %.3e, worst row %.3e" % (rel(a, b), per_row))
+    assert rel(a, b) < BF16_TOL and per_row < 3e-2
+    assert torch.equal(a, dm.engine(R).unet_forward(x, cond, t))      # deterministic
+    # a row does not depend on its lane / group / CTA of the pair
+    a2 = dm.engine(R).unet_forward(x[5:90].contiguous(), cond[5:90].contiguous(), t[5:90].contiguous())
+    assert torch.equal(a[5:90], a2)
+
+
+def test_sampler_bf16_t104_guided_vs_fp32_path(bf16_t104):
+    """cfg3-shaped: horizon 104, one scene of 64 agents, 10 DDPM steps with guidance: the bf16 product path (split-time denoiser +
+    tensor-core LSTM decoder / BPTT at T = 104) against the fp32 kernels on the same noise; decode + indicators self-consistent."""
+    from cld_b200.engine import default_guidance
+    dm, vae, dm32, algo = bf16_t104
+    S, A = 1, 64
+    aux, batch = make_scenes(S, A, horizon=104, seed=61, dense=True)
+    torch.manual_seed(8)
+    x_init, noises = torch.randn(S * A, 104, 4).cuda(), torch.randn(10, S * A, 104, 4).cuda()
+    cu = lambda d: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items()}       # noqa: E731
+    kw = dict(x_init=x_init, noise=noises, want_indicators=True, agents_per_scene=A)
+    a = dm(cu(batch), cu(aux), algo, **kw)
+    b = dm32(cu(batch), cu(aux), algo, **kw)
+    r = rel(a["pred_traj"], b["pred_traj"])
+    print("T=104 unguided bf16 vs fp32: rel(pred_traj) %.3e rel(traj) %.3e" % (r, rel(a["traj"], b["traj"])))
+    assert r < BF16_TOL
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    wtraj, _ = O.decode_rollout(dec_sd, a["pred_traj"].cpu(), aux["cond_feat"], aux["curr_states"])
+    assert rel(a["traj"], wtraj) < 1e-3
+    woff, wcoll = O.indicators(a["traj"].cpu()[..., :2], batch)
+    assert torch.equal(a["offroad"].cpu(), woff) and torch.equal(a["coll"].cpu(), wcoll)
+    # one guided step: gradient of the bf16-mode kernels vs the fp32 kernels
+    z = torch.randn(S * A, 104, 4).cuda()
+    e16, e32 = dm.engine(S * A), dm32.engine(S * A)
+    _, g16, _ = e16.guidance_step(z, aux["cond_feat"].cuda(), aux["curr_states"].cuda(), e16.make_scene(batch, S, A, 1), default_guidance())
+    _, g32, _ = e32.guidance_step(z, aux["cond_feat"].cuda(), aux["curr_states"].cuda(), e32.make_scene(batch, S, A, 1), default_guidance())
+    nz = g32 != 0
+    agree = (torch.sign(g16)[nz] == torch.sign(g32)[nz]).float().mean().item()
+    print("T=104 guidance: rel(grad) %.3e sign agreement %.6f" % (rel(g16, g32), agree))
+    assert rel(g16, g32) < 1e-2 and agree > 0.995
+    g = dm(cu(batch), cu(aux), algo, guidance=default_guidance(), **kw)
+    assert torch.isfinite(g["pred_traj"]).all()
