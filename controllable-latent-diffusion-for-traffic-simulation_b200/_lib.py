@@ -48,7 +48,7 @@ class CldScene(C.Structure):
         ("extent", C.c_void_p), ("world_from_agent", C.c_void_p), ("raster_from_agent", C.c_void_p),
         ("curr_speed", C.c_void_p), ("drivable_map", C.c_void_p), ("map_h", C.c_int32), ("map_w", C.c_int32),
         ("target_pos", C.c_void_p), ("others_pos", C.c_void_p), ("others_avail", C.c_void_p),
-        ("num_others", C.c_int32),
+        ("num_others", C.c_int32), ("map_packed", C.c_int32),
     ]
 
 

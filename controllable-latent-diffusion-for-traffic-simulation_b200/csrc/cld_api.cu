@@ -496,7 +496,7 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
       if (sub.world_from_agent) sub.world_from_agent += a0 * 9;
       if (sub.raster_from_agent) sub.raster_from_agent += a0 * 9;
       if (sub.curr_speed) sub.curr_speed += a0;
-      if (sub.drivable_map) sub.drivable_map += a0 * scene->map_h * scene->map_w;
+      if (sub.drivable_map) sub.drivable_map += a0 * scene->map_h * (scene->map_packed ? (scene->map_w + 7) / 8 : scene->map_w);
       if (sub.target_pos) sub.target_pos += a0 * 2;
       if (sub.others_pos) sub.others_pos += a0 * scene->num_others * T * 2;
       if (sub.others_avail) sub.others_avail += a0 * scene->num_others * T;

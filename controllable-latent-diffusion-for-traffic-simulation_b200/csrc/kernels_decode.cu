@@ -257,7 +257,7 @@ int unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, 
 struct IndArgs {
   const float* traj;            // [R,T,6]
   const float* rfa;             // [B,3,3]
-  const uint8_t* dmap; int H, W;
+  const uint8_t* dmap; int H, W, packed;
   const float* others; const uint8_t* avail; int So;
   uint8_t* offroad; float* coll; float* reward;
   int R, T, N;
@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(256) indicators_kernel(IndArgs a) {
     if (!(yr == yr)) ri = 0;
     ci = ci < 0 ? 0 : (ci > a.W - 1 ? a.W - 1 : ci);
     ri = ri < 0 ? 0 : (ri > a.H - 1 ? a.H - 1 : ri);
-    uint8_t dv = a.dmap[((size_t)ag * a.H + ri) * a.W + ci];
+    const int wb = a.packed ? (a.W + 7) >> 3 : a.W;
+    uint8_t dv = a.packed ? (a.dmap[((size_t)ag * a.H + ri) * wb + (ci >> 3)] >> (ci & 7)) & 1 : a.dmap[((size_t)ag * a.H + ri) * wb + ci];
     uint8_t off = dv ? 0 : 1;
     if (a.offroad) a.offroad[(size_t)row * a.T + t] = off;
     n_off += off;
@@ -321,7 +322,7 @@ int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* off
     return fail(h, CLD_ERR_ARG, "R=%d does not match S*A*N=%d*%d*%d", R, sc->num_scenes, sc->agents_per_scene,
                 sc->num_samp);
   IndArgs a;
-  a.traj = traj; a.rfa = sc->raster_from_agent; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w;
+  a.traj = traj; a.rfa = sc->raster_from_agent; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w; a.packed = sc->map_packed;
   a.others = sc->others_pos; a.avail = sc->others_avail; a.So = sc->num_others;
   if (!a.avail) a.others = nullptr;
   a.offroad = offroad; a.coll = coll; a.reward = reward; a.R = R; a.T = h->cfg.horizon; a.N = sc->num_samp;

@@ -21,7 +21,7 @@ struct LossArgs {
   float* dtraj;          // [R,T,4]  d/d(x, y, v, yaw)
   float* loss;           // [3,R] or nullptr
   const float *extent, *wfa, *rfa, *speed, *target;
-  const uint8_t* dmap; int H, W;
+  const uint8_t* dmap; int H, W, packed;   // packed: rows of (W + 7) / 8 bytes, pixel x = bit (x & 7) of byte x >> 3
   int S, A, N, T, R;
   float w_ac, w_mc, w_tp;
   int D; float buffer, decay, speed_th, min_target_time;
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
   const float2 pxy = *reinterpret_cast<const float2*>(tr);
   const float px = pxy.x, py = pxy.y, psi = tr[3];
   if (!(fabsf(spd) > a.speed_th)) return;       // loss and gradient are zero for non-moving agents
-  const uint8_t* dm = a.dmap + (size_t)g * a.H * a.W;
+  const int wb = a.packed ? (a.W + 7) >> 3 : a.W;
+  const uint8_t* dm = a.dmap + (size_t)g * a.H * wb;
   float sn, c;
   sincosf(psi, &sn, &c);
   const float wmax = (float)a.W, hmax = (float)a.H;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) guidance_map_grad_kernel(LossArgs a) {
       int cx = (int)fminf(fmaxf(rx, -1.f), wmax), cy = (int)fminf(fmaxf(ry, -1.f), hmax);
       cx = cx < 0 ? 0 : (cx > a.W - 1 ? a.W - 1 : cx);
       cy = cy < 0 ? 0 : (cy > a.H - 1 ? a.H - 1 : cy);
-      off = dm[cy * a.W + cx] == 0;
+      off = a.packed ? ((dm[cy * wb + (cx >> 3)] >> (cx & 7)) & 1) == 0 : dm[cy * wb + cx] == 0;
     }
     offm[q] = __ballot_sync(0xffffffffu, off);
     n_off += __popc(offm[q]);
@@ -325,7 +326,7 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   LossArgs a;
   a.traj = traj; a.dtraj = dtraj; a.loss = loss;
   a.extent = sc->extent; a.wfa = sc->world_from_agent; a.rfa = sc->raster_from_agent; a.speed = sc->curr_speed;
-  a.target = sc->target_pos; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w;
+  a.target = sc->target_pos; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w; a.packed = sc->map_packed;
   a.S = S; a.A = A; a.N = N; a.T = T; a.R = R;
   a.w_ac = g->w_agent_collision; a.w_mc = g->w_map_collision; a.w_tp = g->w_target_pos;
   a.D = g->num_disks; a.buffer = g->buffer_dist; a.decay = g->decay_rate; a.speed_th = g->speed_th;

@@ -266,8 +266,9 @@ class DmModel(nn.Module):
         device = self.betas.device
         R = B * N
         eng = self.engine(R)
-        if x_init is None:
+        if x_init is None and not use_device_rng:
             x_init = torch.randn((B, N, T, D), device=device).reshape(R, T, D)   # dm_model.py:109-110
+        # (use_device_rng with x_init None: the initial state is drawn in-kernel as well, Philox keyed by the global row id)
         steps = [i for i in reversed(range(0, self.n_timesteps, self.stride))]
         K = len(steps)
         if noise is None and not use_device_rng and sampler == "ddpm":
@@ -338,7 +339,7 @@ class DmModel(nn.Module):
             with torch.cuda.stream(st):
                 sub = {k: (v[b0:b1] if (torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B) else v) for k, v in data_batch.items()}
                 scene = eng.make_scene(sub, s1 - s0, A, N) if (guidance is not None or want_indicators) else None
-                o = eng.sample(x_init[r0:r1], cond_rows[r0:r1], noises=None if noise is None else noise[:, r0:r1],
+                o = eng.sample(None if x_init is None else x_init[r0:r1], cond_rows[r0:r1], noises=None if noise is None else noise[:, r0:r1],
                                seed=dev_seed, row_offset=row_offset + r0, curr_rows=None if curr_rows is None else curr_rows[r0:r1],
                                scene=scene, guidance=guidance, stride=self.stride, sampler=sampler, want_traj=want_traj,
                                want_indicators=want_indicators)

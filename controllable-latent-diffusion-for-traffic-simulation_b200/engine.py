@@ -145,10 +145,12 @@ class Engine:
         """batch: the reference's data_batch dict (extent, world_from_agent, raster_from_agent, curr_speed,
         drivable_map, [target_pos], [all_other_agents_future_positions/_availability])."""
         d = self.device
+        # the drivable map may arrive bit-packed ("drivable_map_bits" [B,H,W/8] uint8, synthetic.pack_drivable_map): 1/8 of the bytes
+        bits = batch.get("drivable_map_bits")
         keep = {
             "extent": _f32(batch.get("extent"), d), "wfa": _f32(batch.get("world_from_agent"), d),
             "rfa": _f32(batch.get("raster_from_agent"), d), "speed": _f32(batch.get("curr_speed"), d),
-            "dmap": _u8(batch.get("drivable_map"), d), "target": _f32(batch.get("target_pos"), d),
+            "dmap": _u8(bits if bits is not None else batch.get("drivable_map"), d), "target": _f32(batch.get("target_pos"), d),
             "others": _f32(batch.get("all_other_agents_future_positions"), d),
             "avail": _u8(batch.get("all_other_agents_future_availability"), d),
         }
@@ -156,8 +158,10 @@ class Engine:
         sc.num_scenes, sc.agents_per_scene, sc.num_samp = int(num_scenes), int(agents_per_scene), int(num_samp)
         sc.extent, sc.world_from_agent, sc.raster_from_agent = _ptr(keep["extent"]), _ptr(keep["wfa"]), _ptr(keep["rfa"])
         sc.curr_speed, sc.drivable_map = _ptr(keep["speed"]), _ptr(keep["dmap"])
+        sc.map_packed = 1 if bits is not None else 0
         if keep["dmap"] is not None:
-            sc.map_h, sc.map_w = int(keep["dmap"].shape[-2]), int(keep["dmap"].shape[-1])
+            sc.map_h = int(keep["dmap"].shape[-2])
+            sc.map_w = int(batch.get("drivable_map_width", keep["dmap"].shape[-1] * 8)) if bits is not None else int(keep["dmap"].shape[-1])
         sc.target_pos, sc.others_pos, sc.others_avail = _ptr(keep["target"]), _ptr(keep["others"]), _ptr(keep["avail"])
         sc.num_others = int(keep["others"].shape[1]) if keep["others"] is not None else 0
         if keep["others"] is not None and keep["others"].shape[2] != self.T:

@@ -10,6 +10,17 @@ import math
 import torch
 
 
+def pack_drivable_map(dmap):
+    """[B,H,W] bool / uint8 -> [B,H,(W+7)//8] uint8, pixel x = bit (x & 7) of byte x >> 3 (numpy.packbits bitorder="little"): the
+    format `Engine.make_scene` accepts as data_batch["drivable_map_bits"] -- 1/8 of the bytes to ship per agent."""
+    d = dmap.to(torch.uint8)
+    B, H, W = d.shape
+    if W % 8:
+        d = torch.nn.functional.pad(d, (0, 8 - W % 8))
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=d.device)
+    return (d.reshape(B, H, -1, 8) * w).sum(-1).to(torch.uint8).contiguous()
+
+
 def make_scenes(num_scenes, agents_per_scene, horizon=52, seed=123, cond_dim=256, dense=False):
     """Returns (aux_info, batch).  B = num_scenes * agents_per_scene agent rows, scene-major.
 

@@ -94,6 +94,8 @@ typedef struct {
   const float* others_pos;          /* [B,So,T,2] all_other_agents_future_positions or NULL      */
   const uint8_t* others_avail;      /* [B,So,T]   all_other_agents_future_availability or NULL   */
   int32_t num_others;               /* So */
+  int32_t map_packed;               /* 0: drivable_map is [B,H,W] bytes; 1: bit-packed [B,H,(W+7)/8] bytes, pixel x = bit (x & 7) of
+                                       byte x >> 3 (numpy.packbits(..., bitorder="little")): 8x fewer bytes to ship per scene      */
 } CldScene;
 
 int cld_version(void);
