@@ -167,7 +167,8 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->ws_traj, MR * T * 6);
   if (!rc) rc = dev_alloc(h, &h->ws_dtraj, MR * T * 4);
   if (!rc && h->use_lstm_tc) rc = dev_alloc(h, &h->ws_dtraj2, MR * T * 4);
-  if (!rc) rc = dev_alloc(h, &h->ws_loss, 3 * MR);
+  if (!rc) rc = dev_alloc(h, &h->ws_dacc, MR * T);
+  if (!rc) rc = dev_alloc(h, &h->ws_loss, 6 * MR);
   if (!rc) rc = dev_alloc(h, &h->ws_eps, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_mean, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_x, MR * T * cfg->latent_dim);
@@ -443,8 +444,9 @@ static int guidance_step_impl(CldHandle* h, const float* z_mean, const float* co
   // bf16 mode without per-row loss output (the sampler): the two loss kernels run concurrently, each into its own buffer
   float* dmap = (h->use_lstm_tc && !loss_out && g->w_map_collision != 0.f && !h->env_lstm_bwd_simt &&
                  !h->env_guidance_nofork) ? h->ws_dtraj2 : nullptr;
-  if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, dmap, loss_out, R, s))) return rc;
-  return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, dmap, g, z_out, grad_out, R, s);
+  float* dacc = g->w_acc_limit != 0.f ? h->ws_dacc : nullptr;
+  if ((rc = guidance_loss_grad(h, h->ws_traj, scene, g, h->ws_dtraj, dmap, dacc, loss_out, R, s))) return rc;
+  return decode_backward_update2(h, z_mean, h->ws_act, curr, h->ws_dtraj, dmap, dacc, g, z_out, grad_out, R, s);
 }
 
 int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr, const CldScene* scene,

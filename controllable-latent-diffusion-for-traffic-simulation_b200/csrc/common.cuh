@@ -99,6 +99,7 @@ struct CldHandle {
   float* ws_traj = nullptr;        // [max_rows, T, 6]
   float* ws_dtraj = nullptr;       // [max_rows, T, 4]
   float* ws_dtraj2 = nullptr;      // [max_rows, T, 4] map-collision part when it runs concurrently (bf16 mode sampler)
+  float* ws_dacc = nullptr;        // [max_rows, T] d/d(acc) of the acc-limit guidance term
   cudaStream_t aux_stream = nullptr;   // forked from / joined to the caller's stream with the two events below
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* ws_loss = nullptr;        // [3, max_rows]
@@ -179,21 +180,22 @@ int unicycle(CldHandle* h, const float* curr, const float* u, float* state_out, 
 // ---- kernels_lstm.cu
 int decode_h0(CldHandle* h, const float* cond, float* h0, int R, cudaStream_t s);
 int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                            const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
+                            const float* dtraj2, const float* dacc, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
 int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
                       bool save, int R, cudaStream_t s);
 int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const float* curr, float* act_out, float* traj_out,
                          bool save, int R, cudaStream_t s);
 int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                              const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
+                              const float* dtraj2, const float* dacc, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s);
 void lstm_tc_destroy(CldHandle* h);
 int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* offroad, float* coll,
                float* reward, int R, cudaStream_t s);
 // ---- kernels_guidance.cu
 // dtraj_map != nullptr (and loss == nullptr): the map-collision part runs concurrently on the handle's auxiliary stream and
 // writes its own buffer; the caller adds the two
+// dacc [R,T]: d/d(acc) of the acc-limit term (written when g->w_acc_limit != 0; consumed by the unicycle backward)
 int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g,
-                       float* dtraj, float* dtraj_map, float* loss, int R, cudaStream_t s);
+                       float* dtraj, float* dtraj_map, float* dacc, float* loss, int R, cudaStream_t s);
 int decode_backward_update(CldHandle* h, const float* z_mean, const float* act, const float* curr,
                            const float* dtraj, const CldGuidanceConfig* g, float* z_out, float* grad_out,
                            int R, cudaStream_t s);

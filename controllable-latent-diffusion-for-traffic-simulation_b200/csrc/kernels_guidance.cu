@@ -19,8 +19,10 @@ __device__ __forceinline__ float clipg(float x, float lo, float hi) { return fmi
 struct LossArgs {
   const float* traj;     // [R,T,6]
   float* dtraj;          // [R,T,4]  d/d(x, y, v, yaw)
-  float* loss;           // [3,R] or nullptr
-  const float *extent, *wfa, *rfa, *speed, *target;
+  float* loss;           // [6,R] or nullptr: agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit
+  float* dacc;           // [R,T] d/d(acc) of the acc-limit term (acc = de-scaled action, not a function of the rollout) or nullptr
+  const float *extent, *wfa, *rfa, *speed, *target, *tspeed;
+  float w_ts, w_al, acc_limit, w_sl, speed_limit;
   const uint8_t* dmap; int H, W, packed;   // packed: rows of (W + 7) / 8 bytes, pixel x = bit (x & 7) of byte x >> 3
   int S, A, N, T, R;
   float w_ac, w_mc, w_tp;
@@ -184,6 +186,54 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   } else if (a.loss) {
     for (int i = tid; i < A; i += 256) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
   }
+  __syncthreads();       // the terms below add to dtraj[..][2] of the same rows (different lanes <-> steps than above)
+
+  // ---------------- speed / acceleration terms: warp per agent, lanes over time -------------------
+  //   TargetSpeedLoss (guidance_loss.py:219-254)   mean_t |v_t - v*_t|
+  //   AccLimitLoss    (guidance_loss.py:1444-1468)  mean_t max(|acc_t| - limit, 0)   (acc = de-scaled action: gradient goes to dacc)
+  //   SpeedLimitLoss  (guidance_loss.py:1509-1538)  mean_t max(|v_t| - limit, 0)
+  const bool any_sp = (a.w_ts != 0.f && a.tspeed) || a.w_al != 0.f || a.w_sl != 0.f;
+  if (any_sp || a.loss) {
+    const float invT = 1.0f / (float)T;
+    for (int i = warp; i < A; i += 8) {
+      const int g = ag0 + i;
+      const size_t row = (size_t)g * N + n;
+      const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);     // in-place detach of stationary agents, as above
+      const float* tr = a.traj + (size_t)row * T * 6;
+      float l_ts = 0.f, l_al = 0.f, l_sl = 0.f;
+      for (int t = lane; t < T; t += 32) {
+        const float v = tr[t * 6 + 2], acc = tr[t * 6 + 4];
+        float gv = 0.f, ga = 0.f;
+        if (a.w_ts != 0.f && a.tspeed) {
+          const float d = v - a.tspeed[(size_t)g * T + t];
+          l_ts += fabsf(d);
+          gv += a.w_ts * (float)((d > 0.f) - (d < 0.f));
+        }
+        if (a.w_sl != 0.f) {
+          const float e = fabsf(v) - a.speed_limit;
+          if (e >= 0.f) { l_sl += e; gv += a.w_sl * (float)((v > 0.f) - (v < 0.f)); }
+        }
+        if (a.w_al != 0.f) {
+          const float e = fabsf(acc) - a.acc_limit;
+          if (e >= 0.f) { l_al += e; ga = a.w_al * (float)((acc > 0.f) - (acc < 0.f)); }
+        }
+        if (any_sp) {
+          const float kk = has_grad ? inv_AN * invT : 0.f;
+          a.dtraj[((size_t)row * T + t) * 4 + 2] += kk * gv;
+          if (a.dacc) a.dacc[(size_t)row * T + t] = kk * ga;
+        }
+      }
+      if (a.loss) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          l_ts += __shfl_xor_sync(0xffffffffu, l_ts, o); l_al += __shfl_xor_sync(0xffffffffu, l_al, o); l_sl += __shfl_xor_sync(0xffffffffu, l_sl, o);
+        }
+        if (lane == 0) {
+          a.loss[3 * (size_t)a.R + row] = l_ts * invT; a.loss[4 * (size_t)a.R + row] = l_al * invT; a.loss[5 * (size_t)a.R + row] = l_sl * invT;
+        }
+      }
+    }
+  }
 }
 
 
@@ -311,7 +361,7 @@ static float host_linspace(float lo, float hi, int n, int i) {
 }
 
 int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g, float* dtraj,
-                       float* dtraj_map, float* loss, int R, cudaStream_t s) {
+                       float* dtraj_map, float* dacc, float* loss, int R, cudaStream_t s) {
   if (!sc || !g) return fail(h, CLD_ERR_ARG, "scene / guidance config missing");
   const int S = sc->num_scenes, A = sc->agents_per_scene, N = sc->num_samp, T = h->cfg.horizon;
   if (R != S * A * N) return fail(h, CLD_ERR_ARG, "R=%d does not match S*A*N=%d*%d*%d", R, S, A, N);
@@ -329,6 +379,10 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   a.target = sc->target_pos; a.dmap = sc->drivable_map; a.H = sc->map_h; a.W = sc->map_w; a.packed = sc->map_packed;
   a.S = S; a.A = A; a.N = N; a.T = T; a.R = R;
   a.w_ac = g->w_agent_collision; a.w_mc = g->w_map_collision; a.w_tp = g->w_target_pos;
+  a.tspeed = sc->target_speed; a.w_ts = g->w_target_speed; a.w_al = g->w_acc_limit; a.acc_limit = g->acc_limit;
+  a.w_sl = g->w_speed_limit; a.speed_limit = g->speed_limit; a.dacc = a.w_al != 0.f ? dacc : nullptr;
+  if (a.w_ts != 0.f && !sc->target_speed) return fail(h, CLD_ERR_ARG, "target_speed guidance needs CldScene.target_speed");
+  if (a.w_al != 0.f && !dacc) return fail(h, CLD_ERR_STATE, "internal: acc-limit guidance without a d(acc) buffer");
   a.D = g->num_disks; a.buffer = g->buffer_dist; a.decay = g->decay_rate; a.speed_th = g->speed_th;
   a.min_target_time = g->min_target_time; a.nl = g->num_points_l; a.nw = g->num_points_w;
   for (int i = 0; i < 16; ++i) {

@@ -281,7 +281,7 @@ static_assert(128 * 128 * 2 >= LS_RB * 4 * (CLD_MAX_T + 1), "unicycle scratch al
 }  // namespace
 
 struct Bwd2Args {
-  const float *z_mean, *act, *curr, *dtraj, *stash;
+  const float *z_mean, *act, *curr, *dtraj, *stash, *dacc;
   const float *w1t, *w0t, *h2a_w;
   float *z_out, *grad_out, *dh0f;
   int R, T;
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_backward2_kernel(const Bwd
       float* da = dact + tid * T * 2;
       if (row0 + tid < R) {
         const size_t row = (size_t)row0 + tid;
-        unicycle_row_backward2(a.act + row * T * 2, a.curr + row * 4, a.dtraj + row * T * 4, T, a.dyn, sm + LB_W + tid * 4 * (T + 1), da);
+        unicycle_row_backward2(a.act + row * T * 2, a.curr + row * 4, a.dtraj + row * T * 4, T, a.dyn, sm + LB_W + tid * 4 * (T + 1), da,
+                               a.dacc ? a.dacc + row * T : nullptr);
       } else {
         for (int i = 0; i < 2 * T; ++i) da[i] = 0.f;
       }
@@ -576,16 +577,16 @@ int decode_rollout_h0(CldHandle* h, const float* z, const float* h0, const float
 
 
 int decode_backward_update2(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                            const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+                            const float* dtraj2, const float* dacc, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   DecoderW& w = h->dec;
   int rc;
-  if (h->use_lstm_tc && !h->env_lstm_bwd_simt) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, dtraj2, g, z_out, grad_out, R, s);
+  if (h->use_lstm_tc && !h->env_lstm_bwd_simt) return decode_backward_update_tc(h, z_mean, act, curr, dtraj, dtraj2, dacc, g, z_out, grad_out, R, s);
   if (dtraj2) return fail(h, CLD_ERR_STATE, "internal: split d(traj) buffers are only handled by the tensor-core backward");
   if ((rc = lstm2_prepare(h, s))) return rc;
   const CldConfig& c = h->cfg;
   if (c.horizon > CLD_MAX_T) return fail(h, CLD_ERR_UNSUPPORTED, "horizon exceeds CLD_MAX_T");
   Bwd2Args a;
-  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.stash = h->stash; a.dacc = dacc;
   a.w1t = w.w1t; a.w0t = w.w0t; a.h2a_w = w.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.dh0f = h->ws_dh0;
   a.R = R; a.T = c.horizon;
   a.dyn.dt = c.dt; a.dyn.acce_lo = c.acce_lo; a.dyn.acce_hi = c.acce_hi; a.dyn.v_lo = c.v_lo; a.dyn.v_hi = c.v_hi;

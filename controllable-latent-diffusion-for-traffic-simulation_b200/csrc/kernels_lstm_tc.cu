@@ -497,6 +497,7 @@ __host__ __device__ constexpr int lbk_smem(int T) { return lbk_bars(T) + 8 * 8 +
 
 struct BwdTcArgs {
   const float *z_mean, *act, *curr, *dtraj, *stash;
+  const float* dacc;                    // optional [R,T] direct gradient w.r.t. the acceleration command (acc-limit guidance)
   const float* dtraj2;                  // optional second d(traj) part (map-collision kernel on the auxiliary stream), added in the prologue
   const uint8_t* wblob;                 // packed fp16x2 backward weights for TMEM, [256][128]
   const float* h2a_w;
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lstm_backward_tc_kernel(const B
       float sc = 1.f;
       if (row0 + tid < R) {
         unicycle_row_backward2(act_s + tid * T * 2, a.curr + (size_t)(row0 + tid) * 4, dtr_s + tid * T * 4, T, a.dyn,
-                               scr_s + tid * 4 * (T + 1), da);
+                               scr_s + tid * 4 * (T + 1), da, a.dacc ? a.dacc + (size_t)(row0 + tid) * T : nullptr);
         float m = 0.f;
         for (int i = 0; i < 2 * T; ++i) m = fmaxf(m, fabsf(da[i]));
         if (m > 0.f && m < 3.0e38f) {
@@ -901,12 +902,12 @@ int decode_rollout_h0_tc(CldHandle* h, const float* z, const float* h0, const fl
 
 
 int decode_backward_update_tc(CldHandle* h, const float* z_mean, const float* act, const float* curr, const float* dtraj,
-                              const float* dtraj2, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
+                              const float* dtraj2, const float* dacc, const CldGuidanceConfig* g, float* z_out, float* grad_out, int R, cudaStream_t s) {
   int rc;
   if ((rc = lstm_tc_prepare(h, s))) return rc;
   const LstmTcState* st = reinterpret_cast<const LstmTcState*>(h->lstm_tc);
   BwdTcArgs a;
-  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.dtraj2 = dtraj2; a.stash = h->stash; a.wblob = st->wbwd;
+  a.z_mean = z_mean; a.act = act; a.curr = curr; a.dtraj = dtraj; a.dtraj2 = dtraj2; a.dacc = dacc; a.stash = h->stash; a.wblob = st->wbwd;
   a.h2a_w = h->dec.h2a_w; a.z_out = z_out; a.grad_out = grad_out; a.R = R; a.T = h->cfg.horizon; a.dyn = make_dyn2(h->cfg);
   a.optimizer = g->optimizer; a.lr = g->lr;
   a.pf = h->env_lstm_pf;

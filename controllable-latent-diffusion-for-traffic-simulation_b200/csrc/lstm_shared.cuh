@@ -44,8 +44,9 @@ __device__ __forceinline__ void unicycle_row_forward2(const float* act, const fl
 }
 
 // reverse of the unicycle closed form for one row; writes d(scaled action) [T][2]
+// dacc: optional [T] direct gradient w.r.t. the de-scaled acceleration command (acc-limit guidance: x6[..., 4] is the command itself)
 __device__ inline void unicycle_row_backward2(const float* act, const float* curr, const float* dtr, int T, const DynParams2& a,
-                                       float* scr /*[4][T+1]*/, float* dact) {
+                                       float* scr /*[4][T+1]*/, float* dact, const float* dacc = nullptr) {
   float* sk = scr; float* psik = scr + (T + 1); float* vbar = scr + 2 * (T + 1); float* msk = scr + 3 * (T + 1);
   float s = curr[2], psi = curr[3];
   float vprev = clip2(s, a.v_lo, a.v_hi);
@@ -80,6 +81,7 @@ __device__ inline void unicycle_row_backward2(const float* act, const float* cur
     int mk = __float_as_int(msk[m]);
     float du0 = (mk & 1) ? a.dt * Ss : 0.f;
     float du1 = (mk & 2) ? a.dt * Spsi : 0.f;
+    if (dacc) du0 += dacc[m];
     dact[m * 2 + 0] = a.a_std * du0;
     dact[m * 2 + 1] = a.w_std * du1;
     dvbar_next = dvbar; direct_next = direct;

@@ -153,6 +153,7 @@ class Engine:
             "dmap": _u8(bits if bits is not None else batch.get("drivable_map"), d), "target": _f32(batch.get("target_pos"), d),
             "others": _f32(batch.get("all_other_agents_future_positions"), d),
             "avail": _u8(batch.get("all_other_agents_future_availability"), d),
+            "tspeed": _f32(batch.get("target_speed"), d),
         }
         sc = CldScene()
         sc.num_scenes, sc.agents_per_scene, sc.num_samp = int(num_scenes), int(agents_per_scene), int(num_samp)
@@ -164,6 +165,9 @@ class Engine:
             sc.map_w = int(batch.get("drivable_map_width", keep["dmap"].shape[-1] * 8)) if bits is not None else int(keep["dmap"].shape[-1])
         sc.target_pos, sc.others_pos, sc.others_avail = _ptr(keep["target"]), _ptr(keep["others"]), _ptr(keep["avail"])
         sc.num_others = int(keep["others"].shape[1]) if keep["others"] is not None else 0
+        sc.target_speed = _ptr(keep["tspeed"])
+        if keep["tspeed"] is not None and tuple(keep["tspeed"].shape[-1:]) != (self.T,):
+            raise ValueError("target_speed must be [B, T=%d]" % self.T)
         if keep["others"] is not None and keep["others"].shape[2] != self.T:
             raise ValueError("all_other_agents_future_positions must cover the horizon T=%d" % self.T)
         sc._keep = keep
@@ -184,6 +188,9 @@ class Engine:
         gc.min_target_time = float(g.get("min_target_time", 0.0))
         gc.optimizer = {"adam": _lib.CLD_OPT_ADAM, "sgd": _lib.CLD_OPT_SGD}[g.get("optimizer", "adam")]
         gc.lr = float(g.get("lr", 0.3))
+        gc.w_target_speed = float(g.get("target_speed", 0.0))
+        gc.w_acc_limit, gc.acc_limit = float(g.get("acc_limit", 0.0)), float(g.get("acc_limit_value", 0.0))
+        gc.w_speed_limit, gc.speed_limit = float(g.get("speed_limit", 0.0)), float(g.get("speed_limit_value", 0.0))
         return gc
 
     # ------------------------------------------------------------------ kernels
@@ -253,7 +260,7 @@ class Engine:
         R = z.shape[0]
         gc = self.make_guidance(guidance)
         z_out, grad = torch.empty_like(z), torch.empty_like(z)
-        loss = torch.empty(3, R, device=self.device)
+        loss = torch.empty(6, R, device=self.device)      # agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit
         self._check(lib.cld_guidance_step(self._h, _ptr(z), _ptr(cond), _ptr(curr), C.byref(scene), C.byref(gc),
                                           _ptr(z_out), _ptr(grad), _ptr(loss), R, self._stream()), "cld_guidance_step")
         return z_out, grad, loss

@@ -77,6 +77,12 @@ typedef struct {
   float min_target_time;    /* 0.0                                                               */
   int32_t optimizer;        /* CLD_OPT_ADAM                                                      */
   float lr;                 /* 0.3                                                               */
+  /* further analytic terms; weight 0 disables a term */
+  float w_target_speed;     /* TargetSpeedLoss  guidance_loss.py:219-254: mean_t |v_t - v*_t|, v* = CldScene.target_speed */
+  float w_acc_limit;        /* AccLimitLoss     guidance_loss.py:1444-1468: mean_t max(|acc_t| - acc_limit, 0)            */
+  float acc_limit;
+  float w_speed_limit;      /* SpeedLimitLoss   guidance_loss.py:1509-1538: mean_t max(|v_t| - speed_limit, 0)            */
+  float speed_limit;
 } CldGuidanceConfig;
 
 /* Per-agent scene tensors (the reference's data_batch entries), B = S*A agent rows, scene-major. */
@@ -96,6 +102,7 @@ typedef struct {
   int32_t num_others;               /* So */
   int32_t map_packed;               /* 0: drivable_map is [B,H,W] bytes; 1: bit-packed [B,H,(W+7)/8] bytes, pixel x = bit (x & 7) of
                                        byte x >> 3 (numpy.packbits(..., bitorder="little")): 8x fewer bytes to ship per scene      */
+  const float* target_speed;        /* [B,T] target speed of every step (TargetSpeedLoss) or NULL */
 } CldScene;
 
 int cld_version(void);
@@ -171,7 +178,7 @@ int cld_indicators(CldHandle* h, const float* traj, const CldScene* scene, uint8
  * decoder = lstm_dec and transform = convert_action_to_state_and_action, one scene per reference
  * call: z_out = z_mean - lr*g/(|g|+1e-8) (Adam step 1) or z_mean - lr*g (SGD), g = dL/dz by an
  * analytic backward.  cond/curr are per ROW ([R,C], [R,4]).  grad_out [R,T,4] and
- * loss_out [3,R] (agent_collision, map_collision, target_pos per row) may be NULL. */
+ * loss_out [6,R] (agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit per row) may be NULL. */
 int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr,
                       const CldScene* scene, const CldGuidanceConfig* g, float* z_out,
                       float* grad_out, float* loss_out, int R, void* stream);

@@ -397,24 +397,39 @@ def test_two_rank_nccl_job_equals_one_rank(tmp_path):
 # ----------------------------------------------------------------------------------------------------
 # guidance terms pinned to the REAL reference (tests/golden/guidance_ext.npz, guidance_t104.npz)
 # ----------------------------------------------------------------------------------------------------
-def test_target_pos_vs_reference_golden(gpu_models, gold):
-    """Row a13: TargetPosLoss (guidance_loss.py:672-712, min_target_time 0.3) alone: per-row loss, SGD-extracted gradient and
-    the Adam update of the real PerturbationGuidance.perturb."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_guidance_terms_vs_reference_golden(models_cpu, gold, precision):
+    """Rows a13 / f-4: TargetPosLoss (guidance_loss.py:672-712, min_target_time 0.3), TargetSpeedLoss (:219-254), AccLimitLoss (:1444-1468),
+    SpeedLimitLoss (:1509-1538), each alone and all six terms together: per-row losses, the SGD-extracted gradient and the Adam update
+    of the REAL PerturbationGuidance.perturb (tests/golden/guidance_ext.npz)."""
     from conftest import guidance_ext_case
     from cld_b200.engine import default_guidance
     g = gold("guidance_ext")
-    dm, vae, _ = gpu_models(10)
+    dm, vae, _ = models_cpu(10, precision=precision)
+    dm = dm.cuda()
+    vae.bind(dm)
     S, A, N, aux, batch, z, cfgs = guidance_ext_case(g)
     eng = dm.engine(S * A * N)
     scene = eng.make_scene(batch, S, A, N)
     cond, curr = aux["cond_feat"].repeat_interleave(N, 0).cuda(), aux["curr_states"].repeat_interleave(N, 0).cuda()
-    cfg = default_guidance(agent_collision=0.0, map_collision=0.0, target_pos=float(g["weights"][0]), min_target_time=float(g["min_target_time"]))
-    z_out, grad, loss = eng.guidance_step(z.cuda(), cond, curr, scene, cfg)
-    assert rel(loss[2], g["target_pos_loss_target_pos"].reshape(-1)) < 1e-4
-    gref = torch.tensor(g["target_pos_grad_sgd"])
-    big = gref.abs() > 1e-4 * gref.abs().max()
-    assert rel(grad.cpu()[big], gref[big]) < 1e-3
-    assert rel(z_out, g["target_pos_z_out"]) < 3e-3
+    rows = {"agent_collision": 0, "map_collision": 1, "target_pos": 2, "target_speed": 3, "acc_limit": 4, "speed_limit": 5}
+    # bf16 mode: the tensor-core LSTM decoder's actions differ by ~1e-4 relative, which thresholded terms (limits) amplify
+    gtol, ztol, ltol = (1e-3, 3e-3, 1e-4) if precision == "fp32" else (5e-3, 1e-2, 1e-3)
+    for tag, ocfg in cfgs.items():
+        cfg = default_guidance(**{k: ocfg[k] for k in ("agent_collision", "map_collision", "target_pos", "target_speed", "acc_limit",
+                                                       "acc_limit_value", "speed_limit", "speed_limit_value", "min_target_time") if k in ocfg})
+        z_out, grad, loss = eng.guidance_step(z.cuda(), cond, curr, scene, cfg)
+        for key, r in rows.items():
+            name = "%s_loss_%s" % (tag, key)
+            if name in g:
+                assert rel(loss[r], g[name].reshape(-1)) < ltol, (tag, key)
+        gref = torch.tensor(g[tag + "_grad_sgd"])
+        big = gref.abs() > 1e-4 * gref.abs().max()
+        rg = rel(grad.cpu()[big], gref[big])
+        agree = (torch.sign(grad.cpu())[big] == torch.sign(gref)[big]).float().mean().item()
+        rz = rel(z_out, g[tag + "_z_out"])
+        print("%s %-12s rel(grad) %.2e sign agreement %.5f rel(z') %.2e" % (precision, tag, rg, agree, rz))
+        assert rg < gtol and agree > 0.999 and rz < ztol, (tag, rg, agree, rz)
 
 
 def test_guidance_t104_64_agents_8_samples_vs_reference_golden(models_cpu, gold):
