@@ -21,6 +21,15 @@ def __getattr__(name):
     if name == "ContextEncoder":
         from . import context
         return context.ContextEncoder
+    if name in ("ReplayBuffer", "ppo_surrogate"):
+        from . import replay
+        return getattr(replay, name)
+    if name in ("GuidedDiffusionPolicy", "choose_action_from_guidance"):
+        from . import policy
+        return getattr(policy, name)
+    if name == "HostStager":
+        from . import staging
+        return staging.HostStager
     if name in ("failure_rate_compute", "compute_reward", "indicators"):
         from . import critic
         return getattr(critic, name)

@@ -469,6 +469,18 @@ def apply_guidance_update(z, grad, g=DEFAULT_GUIDANCE):
     return p.detach()
 
 
+def choose_action_from_guidance(guide_losses, agents_per_scene, scene_level):
+    """choose_action_from_guidance (src/tbsim/utils/guidance_loss.py:22-65) for one guidance set: guide_losses [B,N,G] (NaN = not
+    applicable) -> index of the chosen sample per agent; scene-level terms pick one sample for the whole scene."""
+    B, N, _ = guide_losses.shape
+    tot = torch.nansum(guide_losses, dim=-1)
+    if scene_level:
+        S = B // agents_per_scene
+        idx = torch.argmin(tot.reshape(S, agents_per_scene, N).sum(dim=1), dim=1)
+        return idx.unsqueeze(-1).expand(S, agents_per_scene).reshape(B)
+    return torch.argmin(tot, dim=-1)
+
+
 # --------------------------------------------------------------------------------------------------
 # a2. sampler loops  (models/dm/dm_model.py:103-142)  + guided composition (diffuser.py:843-929)
 # --------------------------------------------------------------------------------------------------

@@ -236,6 +236,7 @@ def main():
                         grad_sgd=grads_ref.numpy(), loss_ac=loss_ref['agent_collision'].numpy(),
                         loss_mc=loss_ref['map_collision'].numpy(), **wsum)
     guidance_ext_golden()
+    choose_golden()
     context_golden()
     raster_golden()
     print("golden files written to", GOLD)
@@ -353,6 +354,29 @@ def guidance_ext_golden():
     print("guidance ext goldens written")
 
 
+def choose_golden():
+    """f-3: the REAL choose_action_from_guidance (src/tbsim/utils/guidance_loss.py:22-65) on random per-sample guidance losses of one
+    scene (the reference's agent-centric batch: B = 1, M agents) -> tests/golden/choose.npz."""
+    RH.install()
+    from tbsim.utils.guidance_loss import choose_action_from_guidance
+    import types
+    g = torch.Generator().manual_seed(5)
+    M, N, T = 7, 6, 52
+    preds = {"positions": torch.zeros(M, N, T, 2)}
+    out = {}
+    for tag, names in (("scene", ["agent_collision", "map_collision"]), ("agent", ["map_collision", "target_pos"])):
+        losses = {("%s_scene_000_%02d" % (n, i)): torch.rand(M, N, generator=g) for i, n in enumerate(names)}
+        losses[list(losses)[1]][2, 3] = float("nan")                      # nansum path
+        cfgs = [[types.SimpleNamespace(name=n) for n in names]]
+        idx = choose_action_from_guidance(preds, {}, cfgs, losses)
+        mine = O.choose_action_from_guidance(torch.stack(list(losses.values()), dim=2), M, tag == "scene")
+        assert torch.equal(idx, mine), tag
+        out[tag + "_losses"] = torch.stack(list(losses.values()), dim=2).numpy()
+        out[tag + "_idx"] = idx.numpy()
+    np.savez_compressed(os.path.join(GOLD, "choose.npz"), **out)
+    print("choose_action_from_guidance: oracle == reference; golden written")
+
+
 def context_golden():
     """a14: the REAL ContextEncoder (models/context_utils.py:8-61) on 3 synthetic agents with the deterministic
     parameter set of O.synth_context_state -> tests/golden/context.npz (raster as int8 = 2 x value, reference outputs)."""
@@ -404,7 +428,9 @@ def raster_golden():
 
 
 if __name__ == "__main__":
-    if "--only-guidance-ext" in sys.argv:
+    if "--only-choose" in sys.argv:
+        choose_golden()
+    elif "--only-guidance-ext" in sys.argv:
         guidance_ext_golden()
     elif "--only-raster" in sys.argv:
         raster_golden()
