@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(256) indicators_kernel(IndArgs a) {
   int n_off = 0, n_col = 0;
   float jerk = 0.f;
   for (int t = lane; t < a.T; t += 32) {
-    float px = tr[t * 6 + 0], py = tr[t * 6 + 1];
+    const float2 pxy = *reinterpret_cast<const float2*>(tr + t * 6);
+    const float px = pxy.x, py = pxy.y;
     // criticmodel.py:101-112: bmm(points, M^T[:2,:2]) + M^T[-1,:2]; then round().long(), clamp
     float xr = __fadd_rn(__fadd_rn(__fmul_rn(px, m00), __fmul_rn(py, m01)), m02);
     float yr = __fadd_rn(__fadd_rn(__fmul_rn(px, m10), __fmul_rn(py, m11)), m12);
@@ -289,12 +290,24 @@ __global__ void __launch_bounds__(256) indicators_kernel(IndArgs a) {
     if (a.offroad) a.offroad[(size_t)row * a.T + t] = off;
     n_off += off;
     if (a.others) {
-      for (int s = 0; s < a.So; ++s) {
-        size_t o = ((size_t)ag * a.So + s) * a.T + t;
-        if (a.avail[o]) {
-          float dx = px - a.others[o * 2 + 0], dy = py - a.others[o * 2 + 1];
-          float d = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-          n_col += (d < 0.8f) ? 1 : 0;
+      // four neighbours per iteration, positions fetched whether available or not: eight independent loads in flight per lane
+      // instead of a dependent (flag -> position) chain per neighbour
+      const float2* oth2 = reinterpret_cast<const float2*>(a.others);
+      for (int s = 0; s < a.So; s += 4) {
+        uint8_t av[4];
+        float2 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sj = s + j < a.So ? s + j : a.So - 1;
+          const size_t o = ((size_t)ag * a.So + sj) * a.T + t;
+          av[j] = s + j < a.So ? a.avail[o] : (uint8_t)0;
+          q[j] = oth2[o];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dx = px - q[j].x, dy = py - q[j].y;
+          const float d = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+          n_col += (av[j] && d < 0.8f) ? 1 : 0;
         }
       }
     }

@@ -102,7 +102,7 @@ struct TcIssueOp { int n_g0, n_g1, n_g2, flags, n, nt, sbo, ts[4]; };     // ts:
 enum { KB_K4 = 1, KB_ACC = 2, KB_SLOT_FIRST = 4, KB_SLOT_LAST = 8, KB_DUAL = 16 };
 // `ops`: the full op records for the epilogue warps (uniform loads instead of a chain of shared-memory loads per op and half)
 struct TcIssueTab { int n_ops, n_kbs; TcIssueOp op[TC_MAX_OPS]; uint4 kb[TC_MAX_KBS]; TcOp ops[TC_MAX_OPS]; };
-static_assert(sizeof(TcIssueTab) + 3 * 128 + 256 < 32000, "kernel parameters");
+static_assert(sizeof(TcIssueTab) + 4 * 128 + 256 < 32000, "kernel parameters");
 
 struct TcParams {
   const TcOp* ops; int n_ops; const uint32_t* kbs; int n_kbs;
@@ -128,7 +128,7 @@ struct TcState {
   bool tsplit = false; int t_eff = 0;   // split-time mode (horizon > 56): lanes of t_eff = horizon / 2 steps
   int zero0_pitch = 0, zero0_offB = 0;
   bool pair = false;                    // CTA-pair kernel (cluster of 2, tcgen05 cta_group::2); CLD_TC_PAIR=0 selects the single-CTA kernel
-  CUtensorMap tm8, tm32, tm64;          // the weight blob as a 2-D tensor {64 bf16, rows}; boxes of 8 / 32 / 64 rows = half a k-block
+  CUtensorMap tm8, tm16, tm32, tm64;    // the weight blob as a 2-D tensor {64 bf16, rows}; boxes of 8 / 16 / 32 / 64 rows = half a k-block
   float* par = nullptr; size_t par_floats = 0;
   float* zeros = nullptr;
   long long* prof = nullptr;
@@ -511,8 +511,9 @@ __device__ __forceinline__ void prefetch_params(const TcOp* o, const TcParams& P
 // multicast arrive onto the ring-empty / accumulator-full barriers of both CTAs; the epilogue warps of both CTAs arrive on the
 // leader's activation-ready barriers (remote mbarrier arrive for rank 1).
 template <bool PROF, bool PAIR>
-__global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm32,
-                                                                const __grid_constant__ CUtensorMap tm64, const __grid_constant__ TcIssueTab IT,
+__global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm16,
+                                                                const __grid_constant__ CUtensorMap tm32, const __grid_constant__ CUtensorMap tm64,
+                                                                const __grid_constant__ TcIssueTab IT,
                                                                 const TcParams P) {
   constexpr int TC_SLOT = Ring<PAIR>::SLOT, TC_SLOTS = Ring<PAIR>::SLOTS;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
         if (elect_one()) {
           if (PAIR) {
             // this CTA's half of the weight rows: a box of N/2 rows starting at row + rank * N/2; completion on the leader's barrier
-            const void* tm = n8 == 16u ? (const void*)&tm64 : (n8 == 8u ? (const void*)&tm32 : (const void*)&tm8);
+            const void* tm = n8 == 16u ? (const void*)&tm64 : (n8 == 8u ? (const void*)&tm32 : (n8 == 4u ? (const void*)&tm16 : (const void*)&tm8));
             tma2_load_2d(smem_u32(ring + pos * TC_SLOT) + slot_off, tm, 0, row + (int)(rank * n8 * 4u), full0 + 8 * pos);
           } else {
             bulk_g2s(smem_u32(ring + pos * TC_SLOT) + slot_off, src, bytes, bar_full + 8 * pos);
@@ -983,6 +984,9 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   const int k3[3] = {0, 1, 2}, o3[3] = {-1, 0, 1};
   const int kue[2] = {1, 3}, oue[2] = {0, -1}, kuo[2] = {0, 2}, ouo[2] = {1, 0};
   bool prev_commit_split = false;     // the previous op published its two output halves separately
+  // ops with N >= split_min compute their output channels as two halves (epilogue of half 0 under the MMAs of half 1)
+  int split_min = 128;      // measured: 256 -> 128 is -2 % on the launch (level 1), 64 gains nothing more (N = 32 MMAs cost what N = 64 ones do)
+  if (const char* e = getenv("CLD_TC_SPLIT_MIN")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) split_min = v; }
 
   auto res_block = [&](int e, int lvl, const int* in_panels, int n_in, bool concat, int stage) {
     const TcState::Blk& bk = s->blk[e];
@@ -994,7 +998,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     const ConvSpec conv1{bk.c1w, N, N, 5, 0, k5, o5, 5, false};
     // ---- op A: conv0 (+ residual 1x1 conv into the second accumulator set), GroupNorm + Mish + time bias
     // an M=128 MMA costs >= 64 cycles whatever its N (A-operand fetch), so only N = 256 layers are split into halves
-    const bool csA = (N >= 256) && !concat;          // concat blocks write h over x: the epilogue must wait for all MMAs
+    const bool csA = (N >= split_min) && !concat;    // concat blocks write h over x: the epilogue must wait for all MMAs
     const bool skA = csA && prev_commit_split && (n_in % 2 == 0);
     TcOp a = blank_op();
     a.n = N; set_tiles(a, lv); a.kb_first = (int)s->kbs.size();
@@ -1022,7 +1026,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     }
     s->ops.push_back(a);
     // ---- op B: conv1, GroupNorm + Mish + residual
-    const bool csB = (N >= 256) && !concat;           // concat blocks run conv1 in place (h and the output share region A)
+    const bool csB = (N >= split_min) && !concat;     // concat blocks run conv1 in place (h and the output share region A)
     const bool skB = csB && csA;                      // h has N/64 >= 2 panels
     TcOp b = blank_op();
     b.n = N; set_tiles(b, lv); b.kb_first = (int)s->kbs.size();
@@ -1279,7 +1283,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
   CLD_CUDA_OK(h, cudaFuncSetAttribute(unet_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   // CTA-pair kernel (default): the weight blob (all replicas) as a 2-D tensor of 128-byte rows; a box = the half of a k-block
   // one CTA stages (N/2 = 8, 32 or 64 rows).  The blob is already swizzled, so the copies are flat (SWIZZLE_NONE).
-  memset(&s->tm8, 0, sizeof(CUtensorMap)); memset(&s->tm32, 0, sizeof(CUtensorMap)); memset(&s->tm64, 0, sizeof(CUtensorMap));
+  memset(&s->tm8, 0, sizeof(CUtensorMap)); memset(&s->tm16, 0, sizeof(CUtensorMap)); memset(&s->tm32, 0, sizeof(CUtensorMap)); memset(&s->tm64, 0, sizeof(CUtensorMap));
   if (s->pair) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1288,9 +1292,9 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
       return fail(h, CLD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if (B.w_bytes % 128) return fail(h, CLD_ERR_UNSUPPORTED, "internal: weight blob is not a whole number of 128-byte rows");
-    CUtensorMap* maps[3] = {&s->tm8, &s->tm32, &s->tm64};
-    const cuuint32_t rows[3] = {8, 32, 64};
-    for (int i = 0; i < 3; ++i) {
+    CUtensorMap* maps[4] = {&s->tm8, &s->tm16, &s->tm32, &s->tm64};
+    const cuuint32_t rows[4] = {8, 16, 32, 64};
+    for (int i = 0; i < 4; ++i) {
       cuuint64_t dims[2] = {64, (cuuint64_t)(B.w_bytes / 128) * (cuuint64_t)s->wcopies};
       cuuint64_t strides[1] = {128};
       cuuint32_t box[2] = {64, rows[i]}, es[2] = {1, 1};
@@ -1299,7 +1303,7 @@ int tc_finalize(CldHandle* h, cudaStream_t stream) {
       if (r != CUDA_SUCCESS) return fail(h, CLD_ERR_CUDA, "cuTensorMapEncodeTiled rejected the weight tensor (box of %u rows): %d", rows[i], (int)r);
     }
     for (const TcKb& kb : s->kbs)
-      if (kb.n != 16 && kb.n != 64 && kb.n != 128) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block of %d weight rows has no pair box", kb.n);
+      if (kb.n != 16 && kb.n != 32 && kb.n != 64 && kb.n != 128) return fail(h, CLD_ERR_UNSUPPORTED, "internal: k-block of %d weight rows has no pair box", kb.n);
   }
   CLD_CUDA_OK(h, cudaStreamSynchronize(stream));
   s->ready = true;
@@ -1348,13 +1352,13 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = s->prof ? cudaLaunchKernelEx(&cfg, unet_tc_kernel<true, true>, s->tm8, s->tm32, s->tm64, *s->itab, P)
-                            : cudaLaunchKernelEx(&cfg, unet_tc_kernel<false, true>, s->tm8, s->tm32, s->tm64, *s->itab, P);
+    cudaError_t e = s->prof ? cudaLaunchKernelEx(&cfg, unet_tc_kernel<true, true>, s->tm8, s->tm16, s->tm32, s->tm64, *s->itab, P)
+                            : cudaLaunchKernelEx(&cfg, unet_tc_kernel<false, true>, s->tm8, s->tm16, s->tm32, s->tm64, *s->itab, P);
     if (e != cudaSuccess) return fail(h, CLD_ERR_CUDA, "launch of unet_tc_kernel (pair) failed: %s", cudaGetErrorString(e));
   } else if (s->prof) {
-    unet_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, *s->itab, P);
+    unet_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm16, s->tm32, s->tm64, *s->itab, P);
   } else {
-    unet_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm32, s->tm64, *s->itab, P);
+    unet_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(s->tm8, s->tm16, s->tm32, s->tm64, *s->itab, P);
   }
   CLD_LAUNCH_OK(h, "unet_tc_kernel");
   if (s->prof) {
