@@ -310,7 +310,10 @@ __device__ __forceinline__ uint64_t mish2_log2(uint64_t t) {
 #endif
 // (Tried and dropped, twice: refilling the registers of every finished chunk with the same chunk of the NEXT half during the
 // normalise pass, to hide its ~1 100 cycles of tensor-memory reads.  The reads slow the pass down by as much as they save.)
-__device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
+// `acc_bar` / `acc_parity`: the accumulator-full barrier of this half is waited for HERE, after the per-op set-up (masks, pointers:
+// ~100 dependent instructions, ~700 cycles of a warp that shares its scheduler with three others) instead of before it, so the
+// set-up runs under the MMAs.  `t_acc` (profiling build): clock after the wait.
+__device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h, uint32_t acc_bar, uint32_t acc_parity, long long* t_acc) {
   const int EPI = o->epi;
   const int q = cx.q, lane = cx.lane, b = lane & 7, sl = q * 4 + (lane >> 3);
   const int N = o->n, cpg = o->cpg, cpt = cpg >> 3, nch = o->n_vt * cpt;
@@ -337,6 +340,10 @@ __device__ __forceinline__ void epi_gn(const TcOp* o, const EpiCtx& cx, int h) {
     tmem_ld8(cx.lane_addr + vt * N + c0 + (k & (cpt - 1)) * 8, r);
     v[k][0] = pk2u(r[0], r[1]); v[k][1] = pk2u(r[2], r[3]); v[k][2] = pk2u(r[4], r[5]); v[k][3] = pk2u(r[6], r[7]);
   };
+  mbar_wait(acc_bar, acc_parity);
+  if (t_acc) *t_acc = clock64();
+  tc_fence_after();
+  if (cx.tl) cx.tl[3] = clock64();
   if (actm & 1u) load_chunk(0);
   uint64_t s2 = pk2(0.f, 0.f), ss2 = pk2(0.f, 0.f);
 #pragma unroll
@@ -768,15 +775,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unet_tc_kernel(const __grid_con
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const long long tw0 = PROF ? clock64() : 0;
-          mbar_wait(bar_acc + 8 * h, opn & 1u);
-          if (PROF) t_acc += clock64() - tw0;
           long long* tl = (PROF && blockIdx.x == 0 && u == unit0 && etid == 0) ? P.prof + gridDim.x * 8 + oi * 8 : nullptr;
-          if (tl) tl[3 + 2 * h] = clock64();
           cx.tl = (tl && h == 0) ? P.prof + (gridDim.x + TC_MAX_OPS) * 8 + oi * 4 : nullptr;
-          tc_fence_after();
           if (is_gn) {
-            epi_gn(o, cx, h);
+            epi_gn(o, cx, h, bar_acc + 8 * h, opn & 1u, tl ? tl + 3 + 2 * h : nullptr);
+            if (PROF) t_acc += clock64() - tw0;
           } else {
+            mbar_wait(bar_acc + 8 * h, opn & 1u);
+            if (PROF) t_acc += clock64() - tw0;
+            if (tl) tl[3 + 2 * h] = clock64();
+            tc_fence_after();
             epi_plain(o, cx, h, P);
           }
           if (h == 1 && o->dbg_stage >= 0 && o->dbg_stage == P.dbg_stage && P.dbg_out != nullptr) {
@@ -1380,7 +1388,7 @@ static int tc_launch(CldHandle* h, const float* x, float* eps, int R, const floa
                 oi, o.epi, o.n, o.n_vt, o.n_g0 + o.n_g1 + o.n_g2, o.flags, r[0] - t0, r[1] - t0, r[2] - t0, r[2] - r[1], r[3] - t0, r[4] - t0, r[4] - r[3],
                 r[5] - t0, r[6] - t0, r[6] - r[5]);
         const long long* e = hp.data() + (size_t)(grid + TC_MAX_OPS) * 8 + oi * 4;
-        if (e[0]) fprintf(stderr, "      item h0 warp0: acc->loaded %lld | pass1 %lld | bar %lld | pass2+store %lld\n", e[0] - r[3], e[1] - e[0], e[2] - e[1], r[4] - e[2]);
+        if (e[0]) fprintf(stderr, "      item h0 warp0: acc->first load issued %lld | -> loaded %lld | pass1 %lld | bar %lld | pass2+store %lld\n", e[3] - r[3], e[0] - e[3], e[1] - e[0], e[2] - e[1], r[4] - e[2]);
       }
     }
   }
