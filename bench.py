@@ -489,10 +489,10 @@ def main():
                       "teacher_forced": "tests/test_gpu_headline.py (16 scenes x 16 agents, every one of the 50 steps)"}
         lanes = None
         if world == 1 and not a.skip_lanes and R <= MAX_CHUNK_ROWS and ce is None:
-            # informational: the same workload with DmModel(lanes=2) -- whole-scene half batches on two engines / CUDA streams fill the
+            # informational: the same workload with DmModel(lanes=4) -- whole-scene quarter batches on four engines / CUDA streams fill the
             # SMs that the denoiser's last wave and the 128-CTA decoder kernels leave idle
             torch.manual_seed(0)
-            dm2 = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=w["n_timesteps"], precision=a.precision, max_rows=R, lanes=2).to(dev)
+            dm2 = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=w["n_timesteps"], precision=a.precision, max_rows=R, lanes=4).to(dev)
             dm2.stride = w["stride"]
             VaeModel(algo).bind(dm2)
 
@@ -509,7 +509,7 @@ def main():
             f1.record()
             torch.cuda.synchronize()
             lms = f0.elapsed_time(f1) / a.steps
-            lanes = {"lanes": 2, "value": S / lms * 1e3, "unit": "scenarios/s", "ms_per_step": lms,
+            lanes = {"lanes": 4, "value": S / lms * 1e3, "unit": "scenarios/s", "ms_per_step": lms,
                      "equals_single_lane": bool(torch.equal(lo["traj"], out["traj"]))}
             del dm2
         ctx = None
