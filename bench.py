@@ -58,13 +58,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="DmModel(lanes=L): whole-scene sub-batches on L engines / CUDA streams (0 = 4 where the workload allows it, else 1)")
     ap.add_argument("--precision", default=os.environ.get("CLD_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--sampler", default=None, choices=["ddim", "ddpm"])
     ap.add_argument("--no-guidance", action="store_true")
     ap.add_argument("--scenes", type=int, default=None, help="override the number of scenes (total for cfg2, per rank otherwise)")
     ap.add_argument("--cpu-scenes", type=int, default=1, help="scenes in the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--skip-lanes", action="store_true", help="do not time the 2-lane variant after the headline")
+    ap.add_argument("--skip-lanes", action="store_true", help="same as --lanes 1 (one engine / stream; the kernel brackets then come from the timed region)")
     ap.add_argument("--skip-context", action="store_true", help="do not time the context encoder (row a14) after the headline")
     ap.add_argument("--skip-hbm", action="store_true", help="do not time the HBM-bound kernels (K3, K6) alone")
     a = ap.parse_args()
@@ -339,6 +341,18 @@ def main():
         batch["scene_index"] = torch.arange(S).repeat_interleave(A)
     guidance = default_guidance() if w["guided"] else None
     eng = dm.engine(rows_per_launch)
+    # The measured configuration of the product: DmModel(lanes=L) splits the scenes of a call into L whole-scene sub-batches that run
+    # concurrently on their own engines / CUDA streams (bit-identical results: scenes never interact, Philox noise is keyed by the
+    # global row id).  The sub-batches fill the SMs that the denoiser's last wave (4 096 rows = 3.46 waves of 148 CTAs) and the
+    # 128-CTA LSTM kernels leave idle.  The kernel brackets of `roofline` come from a single-lane pass (kernels timed alone).
+    n_lanes = 1 if a.skip_lanes else a.lanes if a.lanes > 0 else (4 if (not w["context"] and S >= 8 and 2048 <= R <= MAX_CHUNK_ROWS) else 1)
+    dm_run = dm
+    if n_lanes > 1:
+        torch.manual_seed(0)
+        dm_run = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=w["n_timesteps"], precision=a.precision, max_rows=rows_per_launch,
+                         lanes=n_lanes).to(dev)
+        dm_run.stride = w["stride"]
+        VaeModel(algo).bind(dm_run)
     K_d = k_steps(w)
     host_keys = ["extent", "world_from_agent", "raster_from_agent", "curr_speed", "drivable_map_bits", "scene_index",
                  "all_other_agents_future_positions", "all_other_agents_future_availability", "history_positions"]
@@ -363,14 +377,15 @@ def main():
     gathered = torch.empty(world * R, T * 6 + T + 1, device=dev) if world > 1 else None
     SEED = 20240707
 
-    def hot_path(b, ax, hd=None):
+    def hot_path(b, ax, hd=None, model=None):
+        model = model if model is not None else dm_run
         if ce is not None:
             cb = {"raster_from_agent": b["raster_from_agent"], "history_positions": b["history_positions"], "history_yaws": hd["history_yaws"],
                   "curr_speed": b["curr_speed"]}
             cx = ce.forward_history(cb, hd["maps"], hd["hpos"], hd["hmask"])
             ax = {"cond_feat": cx["cond_feat"], "curr_states": cx["curr_states"]}
-        out = dm(b, ax, algo, sampler=w["sampler"], guidance=guidance, want_indicators=True, agents_per_scene=A,
-                 use_device_rng=True, seed=SEED, row_offset=row_offset)
+        out = model(b, ax, algo, sampler=w["sampler"], guidance=guidance, want_indicators=True, agents_per_scene=A,
+                    use_device_rng=True, seed=SEED, row_offset=row_offset)
         if world > 1:
             # the path's one exchange: trajectories + indicator flags + collision counts of every rank
             out["all_traj"], out["all_offroad"], out["all_coll"] = gather_results(out["traj"], out["offroad"], out["coll"], out=gathered)
@@ -387,18 +402,41 @@ def main():
     sampler_thread = ClockSampler(local) if rank == 0 else None
     if sampler_thread:
         sampler_thread.start()
-    l0 = eng.launch_count() + (ce.launch_count() if ce is not None else 0)
-    eng.profile_begin()
+    def count_launches():
+        n = dm_run.launch_count() + (ce.launch_count() if ce is not None else 0)
+        return n + (dm.launch_count() if dm_run is not dm else 0)
+    l0 = count_launches()
+    if n_lanes == 1:
+        eng.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         out = hot_path(batch_d, aux_d, hist_d)
     e1.record()
     barrier()
-    prof = eng.profile_end()
-    launches = eng.launch_count() + (ce.launch_count() if ce is not None else 0) - l0
+    if n_lanes == 1:
+        prof = eng.profile_end()
+    launches = count_launches() - l0
     clocks = sampler_thread.stop() if sampler_thread else None
     ms = e0.elapsed_time(e1) / a.steps
+    single = None
+    if n_lanes > 1:
+        # the same workload on ONE engine / stream, per-kind CUDA-event brackets around every kernel group: each kernel is timed alone
+        hot_path(batch_d, aux_d, hist_d, model=dm)
+        barrier()
+        eng.profile_begin()
+        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0e.record()
+        for _ in range(a.steps):
+            out1 = hot_path(batch_d, aux_d, hist_d, model=dm)
+        s1e.record()
+        barrier()
+        prof = eng.profile_end()
+        ms1 = s0e.elapsed_time(s1e) / a.steps
+        single = {"lanes": 1, "value": (job_scenes / world) / (ms1 / 1e3) * world, "unit": "scenarios/s", "ms_per_step": ms1,
+                  "equals_lanes_result": bool(torch.equal(out1["traj"], out["traj"]))}
+        del out1
+    ms_brackets = ms if single is None else single["ms_per_step"]
     tms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -458,7 +496,9 @@ def main():
                 "traffic_source": "profiles/r02_unet_tc_ncu_full_4096rows.csv (ncu --set full, one launch)" if key in NCU_DRAM_BYTES_PER_LAUNCH else None,
                 "peak_source": peak_src + " bf16_tflops_sustained", "per_launch_ms": per_launch_ms, "launches_timed": den_n,
                 "rows_per_launch": rows_per_launch, "algorithmic_flop_per_launch": flop,
-                "share_of_step": {k: v[0] / a.steps / ms for k, v in prof.items()}}
+                "measured_in": "the timed region" if single is None else "single-lane pass of the same workload and step count (kernels timed alone; "
+                               "in the %d-lane timed region kernels of different lanes overlap)" % n_lanes,
+                "share_of_step": {k: v[0] / a.steps / ms_brackets for k, v in prof.items()}}
         hbm = None
         if not a.skip_hbm:
             scene = eng.make_scene({k: (v[:rows_per_launch // N] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == S * A else v)
@@ -487,31 +527,6 @@ def main():
                       "offroad_flag_mismatch": (og["offroad"].cpu() != o_off).float().mean().item(),
                       "collision_count_mismatch": (og["coll"].cpu() != o_coll).float().mean().item(),
                       "teacher_forced": "tests/test_gpu_headline.py (16 scenes x 16 agents, every one of the 50 steps)"}
-        lanes = None
-        if world == 1 and not a.skip_lanes and R <= MAX_CHUNK_ROWS and ce is None:
-            # informational: the same workload with DmModel(lanes=4) -- whole-scene quarter batches on four engines / CUDA streams fill the
-            # SMs that the denoiser's last wave and the 128-CTA decoder kernels leave idle
-            torch.manual_seed(0)
-            dm2 = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=w["n_timesteps"], precision=a.precision, max_rows=R, lanes=4).to(dev)
-            dm2.stride = w["stride"]
-            VaeModel(algo).bind(dm2)
-
-            def lane_step():
-                return dm2(batch_d, aux_d, algo, sampler=w["sampler"], guidance=guidance, want_indicators=True, agents_per_scene=A,
-                           use_device_rng=True, seed=SEED, row_offset=row_offset)
-            for _ in range(2):
-                lane_step()
-            torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(a.steps):
-                lo = lane_step()
-            f1.record()
-            torch.cuda.synchronize()
-            lms = f0.elapsed_time(f1) / a.steps
-            lanes = {"lanes": 4, "value": S / lms * 1e3, "unit": "scenarios/s", "ms_per_step": lms,
-                     "equals_single_lane": bool(torch.equal(lo["traj"], out["traj"]))}
-            del dm2
         ctx = None
         if world == 1 and not a.skip_context and a.config == "cfg1":
             del out
@@ -521,12 +536,12 @@ def main():
             "metric": "guided scenarios/sec (50-step DDIM)" if a.config in ("cfg1", "cfg2") else "guided scenarios/sec (%s)" % a.config,
             "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": w["scaling"],
-            "vs_baseline": None, "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world, R),
+            "vs_baseline": None, "dtype": a.precision, "data": "synthetic", "config": dict(workload_config(a, world, R), lanes=n_lanes),
             "row_steps_per_s": value * A * N * K_d, "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": "scenarios/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te.item(), "staging": "drivable map shipped bit-packed (1 bit per pixel); H2D of call i+1 overlaps call i "
                                                          "(cld_b200.staging.HostStager); results read back to pinned host memory every call"},
-            "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx, "lanes": lanes,
+            "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx, "lanes": n_lanes, "single_lane": single,
         }
         if world > 1:
             line["all_gather"] = {"ms": gather_ms, "bytes_per_rank": R * (T * 7 + 1) * 4, "share_of_step": gather_ms / ms}

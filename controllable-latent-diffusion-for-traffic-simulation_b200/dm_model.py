@@ -252,6 +252,11 @@ class DmModel(nn.Module):
             self._lane_streams.append(torch.cuda.Stream(device=dev))
         return eng, self._lane_streams[lane]
 
+    def launch_count(self):
+        """Kernels launched so far by the engines of this model (the main one and the lanes)."""
+        engs = ([self._engine] if self._engine is not None else []) + list(self._lane_engines.values())
+        return sum(e.launch_count() for e in engs)
+
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def forward(self, data_batch, aux_info, algo_config, **kw):

@@ -2,7 +2,7 @@
 // shared memory) as a function of N, with and without a concurrent stream of bulk copies (UBLKCP, global -> shared) into a
 // 4 x 16 KB ring, which is what the denoiser's weight producer does.  Answers: is an SS-mode MMA bound by its operand
 // fetch from shared memory, and how much of that bandwidth do the weight copies take?
-//   umma_bench [grid]
+//   umma_bench [grid] [a_off bytes: 0 | 128 .. 896]
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -12,7 +12,7 @@ using namespace cld::tc;
 
 // fresh != 0: every MMA reads a different A tile (16 x 4 KB) and a different B tile (rotating over 64 KB), as in the denoiser where
 // no operand is re-read by the next instruction; fresh == 0: the same four K slices over and over
-__global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int copy_bytes, int fresh, const uint8_t* gsrc, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int copy_bytes, int fresh, const uint8_t* gsrc, long long* out, int a_off) {
   extern __shared__ __align__(1024) uint8_t smem[];     // [0,64K) A, [64K,128K) B, [128K,192K) copy ring
   __shared__ __align__(8) uint64_t bar, cbar[4];
   __shared__ uint32_t tmem_base_s;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int co
   const uint32_t tmem_base = tmem_base_s;
   if (warp == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N);
-    const uint64_t ad0 = make_desc_sw128(smem_u32(smem), 1024);
+    const uint64_t ad0 = make_desc_sw128(smem_u32(smem) + a_off, 1024);     // a_off: A start inside the 1024-byte swizzle atom (row-shifted tile)
     const uint64_t bd0 = make_desc_sw128(smem_u32(smem) + 65536, 1024);
     long long t0 = clock64();
     if (elect_one()) {
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nacc, int cnt, int co
 
 int main(int argc, char** argv) {
   const int grid = argc > 1 ? atoi(argv[1]) : 1;
+  const int a_off = argc > 2 ? atoi(argv[2]) : 0;
   long long* d; cudaMalloc(&d, 32);
   uint8_t* src; cudaMalloc(&src, (size_t)grid * 65536); cudaMemset(src, 0, (size_t)grid * 65536);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
@@ -100,12 +101,12 @@ int main(int argc, char** argv) {
       long long h[4] = {0, 0, 0, 0};
       for (int rep = 0; rep < 2; ++rep) {
         cudaMemset(d, 0, 32);
-        bench<<<grid, 128, 196608>>>(N, nacc, cnt, copy_bytes, fresh, src, d);
+        bench<<<grid, 128, 196608>>>(N, nacc, cnt, copy_bytes, fresh, src, d, a_off);
         cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
       }
       cudaError_t e = cudaGetLastError();
       const double cyc = (double)h[1] / cnt;
-      printf("grid %3d fresh %d N=%3d nacc=%d copies %5d B: %.1f cyc/MMA (math floor %.1f), operand bytes/cyc %.1f, copy bytes/cyc %.1f %s\n", grid, fresh, N, nacc,
+      printf("a_off %3d grid %3d fresh %d N=%3d nacc=%d copies %5d B: %.1f cyc/MMA (math floor %.1f), operand bytes/cyc %.1f, copy bytes/cyc %.1f %s\n", a_off, grid, fresh, N, nacc,
              copy_bytes, cyc, N * 0.5, (4096.0 + N * 32.0) / cyc, (double)h[2] / (double)h[1], e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
   return 0;
