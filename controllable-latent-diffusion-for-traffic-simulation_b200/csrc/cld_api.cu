@@ -168,6 +168,8 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->ws_dtraj, MR * T * 4);
   if (!rc && h->use_lstm_tc) rc = dev_alloc(h, &h->ws_dtraj2, MR * T * 4);
   if (!rc) rc = dev_alloc(h, &h->ws_dacc, MR * T);
+  if (!rc) rc = dev_alloc(h, &h->map_work, MR * T + 8);
+  if (!rc && cudaMemset(h->map_work, 0, 8 * sizeof(int)) != cudaSuccess) rc = fail(h, CLD_ERR_CUDA, "cudaMemset of the map work list failed");
   if (!rc) rc = dev_alloc(h, &h->ws_loss, 6 * MR);
   if (!rc) rc = dev_alloc(h, &h->ws_eps, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_mean, MR * T * cfg->latent_dim);
@@ -454,6 +456,7 @@ int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, cons
   int rc = check_rows(h, R);
   if (rc) return rc;
   if (!z_mean || !cond || !curr || !scene || !g || !z_out) return fail(h, CLD_ERR_ARG, "null argument");
+  if (g->w_map_collision != 0.f && (rc = guidance_prepare_maps(h, scene, (cudaStream_t)stream))) return rc;
   return guidance_step_impl(h, z_mean, cond, nullptr, curr, scene, g, z_out, grad_out, loss_out, R, (cudaStream_t)stream);
 }
 
@@ -529,6 +532,8 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
     } else if (split_bias && s != h->tvec_stream && h->ev_tvec) {
       CLD_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_tvec, 0));
     }
+    // so is the tile table that screens the map-collision term (the maps of this chunk)
+    if (g && g->w_map_collision != 0.f && (rc = guidance_prepare_maps(h, sc, s))) return rc;
     // LSTM initial state (cond2hidden) is step-invariant as well
     if ((g || traj_out || offroad_out || coll_out) && (rc = decode_h0(h, condc, h->ws_h0, Rc, s))) return rc;
     for (int k = 0; k < K; ++k) {

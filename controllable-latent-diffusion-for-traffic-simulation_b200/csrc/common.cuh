@@ -100,6 +100,13 @@ struct CldHandle {
   float* ws_dtraj = nullptr;       // [max_rows, T, 4]
   float* ws_dtraj2 = nullptr;      // [max_rows, T, 4] map-collision part when it runs concurrently (bf16 mode sampler)
   float* ws_dacc = nullptr;        // [max_rows, T] d/d(acc) of the acc-limit guidance term
+  // map-collision guidance: work list of the (row, step) items whose footprint may leave the road (+ 2 counters), and per agent
+  // map the "all 64 pixels drivable" bits of its 8 x 8 pixel tiles (one uint32 per tile row), rebuilt by guidance_prepare_maps
+  int* map_work = nullptr;
+  uint32_t* map_coarse = nullptr;
+  size_t map_coarse_words = 0;
+  const void* coarse_src = nullptr;
+  int coarse_agents = 0, coarse_h = 0, coarse_w = 0, coarse_packed = 0;
   cudaStream_t aux_stream = nullptr;   // forked from / joined to the caller's stream with the two events below
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* ws_loss = nullptr;        // [3, max_rows]
@@ -196,6 +203,9 @@ int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* off
 // dacc [R,T]: d/d(acc) of the acc-limit term (written when g->w_acc_limit != 0; consumed by the unicycle backward)
 int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g,
                        float* dtraj, float* dtraj_map, float* dacc, float* loss, int R, cudaStream_t s);
+// per agent map: which 8 x 8 pixel tiles are drivable throughout (the screen of the map-collision term).  Valid for the scene's
+// drivable_map pointer until the next call; cld_sample calls it once per chunk, cld_guidance_step once per call.
+int guidance_prepare_maps(CldHandle* h, const CldScene* sc, cudaStream_t s);
 int decode_backward_update(CldHandle* h, const float* z_mean, const float* act, const float* curr,
                            const float* dtraj, const CldGuidanceConfig* g, float* z_out, float* grad_out,
                            int R, cudaStream_t s);
