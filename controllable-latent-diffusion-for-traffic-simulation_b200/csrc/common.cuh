@@ -100,13 +100,14 @@ struct CldHandle {
   float* ws_dtraj = nullptr;       // [max_rows, T, 4]
   float* ws_dtraj2 = nullptr;      // [max_rows, T, 4] map-collision part when it runs concurrently (bf16 mode sampler)
   float* ws_dacc = nullptr;        // [max_rows, T] d/d(acc) of the acc-limit guidance term
-  // map-collision guidance: work list of the (row, step) items whose footprint may leave the road (+ 2 counters), and per agent
-  // map the "all 64 pixels drivable" bits of its 8 x 8 pixel tiles (one uint32 per tile row), rebuilt by guidance_prepare_maps
+  // map-collision guidance: work list of the (row, step) items whose footprint may cross a road edge (+ 2 counters), and the
+  // one-bit-per-pixel copy of byte-per-pixel drivable maps that the screen reads (guidance_prepare_maps; bit-packed scenes are read in place)
   int* map_work = nullptr;
-  uint32_t* map_coarse = nullptr;
-  size_t map_coarse_words = 0;
-  const void* coarse_src = nullptr;
-  int coarse_agents = 0, coarse_h = 0, coarse_w = 0, coarse_packed = 0;
+  uint8_t* map_bits = nullptr;
+  size_t map_bits_bytes = 0;
+  const void* screen_src = nullptr;        // the drivable_map pointer the screen data belongs to (nullptr: none)
+  const uint8_t* screen_pk = nullptr;      // where the screen reads: map_bits or the scene's own packed maps
+  int screen_agents = 0, screen_h = 0, screen_w = 0, screen_packed = 0, screen_pitch = 0;
   cudaStream_t aux_stream = nullptr;   // forked from / joined to the caller's stream with the two events below
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* ws_loss = nullptr;        // [3, max_rows]
@@ -130,7 +131,7 @@ struct CldHandle {
   void* lstm_tc = nullptr;
   bool use_lstm_tc = false;
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)
-  bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false;
+  bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false;
   int env_lstm_pf = 3;
 };
 
@@ -203,8 +204,8 @@ int indicators(CldHandle* h, const float* traj, const CldScene* sc, uint8_t* off
 // dacc [R,T]: d/d(acc) of the acc-limit term (written when g->w_acc_limit != 0; consumed by the unicycle backward)
 int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, const CldGuidanceConfig* g,
                        float* dtraj, float* dtraj_map, float* dacc, float* loss, int R, cudaStream_t s);
-// per agent map: which 8 x 8 pixel tiles are drivable throughout (the screen of the map-collision term).  Valid for the scene's
-// drivable_map pointer until the next call; cld_sample calls it once per chunk, cld_guidance_step once per call.
+// the screen of the map-collision term reads the drivable maps with one bit per pixel: byte-per-pixel maps are packed here, once per
+// cld_sample chunk / cld_guidance_step call (the maps of a call do not change between denoising steps)
 int guidance_prepare_maps(CldHandle* h, const CldScene* sc, cudaStream_t s);
 int decode_backward_update(CldHandle* h, const float* z_mean, const float* act, const float* curr,
                            const float* dtraj, const CldGuidanceConfig* g, float* z_out, float* grad_out,

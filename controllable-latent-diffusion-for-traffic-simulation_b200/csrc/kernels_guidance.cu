@@ -9,6 +9,7 @@
 //                           Adam / SGD step of perturb (:2250-2278).
 // All arithmetic fp32 (the update is sign-sensitive: SURVEY.md section 7, hard part 3).
 #include <math.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -29,7 +30,7 @@ struct LossArgs {
   int D; float buffer, decay, speed_th, min_target_time;
   int nl, nw;
   // map-collision term: screen + work list (see guidance_map_screen_kernel)
-  const uint32_t* coarse; int tiles_y;      // [agent][tiles_y] all-drivable bits of the 8 x 8 pixel tiles (nullptr: no screen)
+  const uint8_t* pk; int pk_pitch;          // the drivable maps with one bit per pixel (rows of pk_pitch bytes; nullptr: no screen)
   int* work;                                // [0] items listed, [1] CTAs of the list kernel that have finished, [2...] items = row * T + t
   int assign;                               // the map term OWNS dtraj (writes every item, zeros included) instead of adding to it
   float lwise[16], wwise[16];
@@ -43,7 +44,7 @@ __device__ __forceinline__ float linspace_at(float lo, float hi, int n, int i) {
   return (i < n / 2) ? lo + step * (float)i : hi - step * (float)(n - 1 - i);
 }
 
-__global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
+__global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int A = a.A, T = a.T, N = a.N;
   float* pose = sm;                         // [A][T][4] world Px, Py, cos(Psi), sin(Psi)
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   float* wts = agt + A * 8;                 // [T] decay weights
   const int s = blockIdx.x / N, n = blockIdx.x % N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;       // 16 warps: one agent per warp at 16 agents per scene (latency-bound loops: more warps per SM)
   const int ag0 = s * A;
   const float inv_AN = 1.0f / (float)(A * N);
 
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
     q[3] = (fabsf(a.speed[g]) > a.speed_th) ? 1.f : 0.f;
     q[4] = a.wfa[g * 9 + 0]; q[5] = a.wfa[g * 9 + 1]; q[6] = a.wfa[g * 9 + 3]; q[7] = a.wfa[g * 9 + 4];
   }
-  for (int t = tid; t < T; t += 256) wts[t] = a.wts[t];
-  for (int it = tid; it < A * T; it += 256) {
+  for (int t = tid; t < T; t += nthr) wts[t] = a.wts[t];
+  for (int it = tid; it < A * T; it += nthr) {
     int i = it / T, t = it - i * T, g = ag0 + i;
     const float* tr = a.traj + (((size_t)g * N + n) * T + t) * 6;
     float px = tr[0], py = tr[1], psi = tr[3];
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   __syncthreads();
 
   // ---------------- agent-agent collision: warp per agent, lanes over time ---------------------
-  for (int i = warp; i < A; i += 8) {
+  for (int i = warp; i < A; i += nwarps) {
     const int g = ag0 + i;
     const size_t row = (size_t)g * N + n;
     const float* qi = agt + i * 8;
@@ -141,13 +143,13 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   __syncthreads();
 
   if (a.loss)
-    for (int i = tid; i < A; i += 256) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;   // map term: own kernel
+    for (int i = tid; i < A; i += nthr) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;   // map term: own kernel
 
   // ---------------- target position (softmin-weighted squared distance): warp per agent ------------
   if (a.w_tp != 0.f && a.target) {
     const int t0 = (int)(a.min_target_time * (float)T);
     const int Tn = T - t0;
-    for (int i = warp; i < A; i += 8) {
+    for (int i = warp; i < A; i += nwarps) {
       const int g = ag0 + i;
       const size_t row = (size_t)g * N + n;
       const float tx = a.target[g * 2 + 0], ty = a.target[g * 2 + 1];
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
       }
     }
   } else if (a.loss) {
-    for (int i = tid; i < A; i += 256) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
+    for (int i = tid; i < A; i += nthr) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
   }
   __syncthreads();       // the terms below add to dtraj[..][2] of the same rows (different lanes <-> steps than above)
 
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
   const bool any_sp = (a.w_ts != 0.f && a.tspeed) || a.w_al != 0.f || a.w_sl != 0.f;
   if (any_sp || a.loss) {
     const float invT = 1.0f / (float)T;
-    for (int i = warp; i < A; i += 8) {
+    for (int i = warp; i < A; i += nwarps) {
       const int g = ag0 + i;
       const size_t row = (size_t)g * N + n;
       const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);     // in-place detach of stationary agents, as above
@@ -244,41 +246,23 @@ __global__ void __launch_bounds__(256) guidance_loss_grad_kernel(LossArgs a) {
 // ---------------- map collision (MapCollisionLoss.forward, guidance_loss.py:772-870) --------------------------------
 // Two kernels.  (1) guidance_map_screen_kernel, one THREAD per (row, step): the raster-space bounding box of the footprint's four
 // corners (the sample points are a grid spanned by them, so every sample pixel lies inside it; widened by a pixel fraction against
-// rounding) is tested against the per-map table of 8 x 8 pixel tiles that are drivable throughout.  A footprint whose box is all
-// drivable has no off-road sample point, one whose box has no drivable pixel has no on-road one: either way loss and gradient are
-// zero (only partially overlapping steps contribute) and nothing else is to do -- on the benchmark scenes 97 % of the items of moving agents.  The others are appended to a work list.  (2) guidance_map_list_kernel, one WARP per listed item
-// (persistent warps striding over the list): the 10 x 10 sample points, the drivable-map look-ups and the nearest on-road point of
-// every off-road one.
-__global__ void __launch_bounds__(256) guidance_map_coarse_kernel(const uint8_t* __restrict__ dmap, int H, int W, int packed, int tiles_y,
-                                                                  int n_maps, uint32_t* __restrict__ coarse) {
-  // one warp per (map, tile row), lane = tile column (W <= 256)
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= n_maps * tiles_y) return;
-  const int g = wid / tiles_y, ty = wid - g * tiles_y;
-  const int wb = packed ? (W + 7) >> 3 : W;
-  const uint8_t* dm = dmap + (size_t)g * H * wb;
-  bool all_on = false, all_off = false;
-  if (lane * 8 < W) {
-    all_on = all_off = true;
-    for (int y = ty * 8; y < min(ty * 8 + 8, H); ++y) {
-      if (packed) {
-        // byte `lane` of the row = pixels 8 lane .. 8 lane + 7 (bit x & 7); a partial last byte only counts its existing pixels
-        const int nbits = min(8, W - lane * 8);
-        const uint32_t m = (1u << nbits) - 1u, v = dm[(size_t)y * wb + lane] & m;
-        all_on = all_on && v == m;
-        all_off = all_off && v == 0u;
-      } else {
-        for (int x = lane * 8; x < min(lane * 8 + 8, W); ++x) {
-          const bool on = dm[(size_t)y * wb + x] != 0;
-          all_on = all_on && on;
-          all_off = all_off && !on;
-        }
-      }
-    }
-  }
-  // [map][tile row][0: tiles drivable throughout | 1: tiles with no drivable pixel]
-  const uint32_t w_on = __ballot_sync(0xffffffffu, all_on), w_off = __ballot_sync(0xffffffffu, all_off);
-  if (lane == 0) { coarse[2 * wid] = w_on; coarse[2 * wid + 1] = w_off; }
+// rounding) is read from the bit-packed map, a few bytes per pixel row.  All of its pixels drivable: no sample point is off the
+// road; none drivable: none is on it; either way loss and gradient are zero (only partially overlapping steps contribute) and
+// nothing else is to do.  The other items are appended to a work list.  (2) guidance_map_list_kernel, one WARP per listed item
+// (persistent warps striding over the list): the 10 x 10 sample points, their map look-ups and the nearest on-road point of every
+// off-road one.
+// byte-per-pixel maps -> one bit per pixel (pixel x = bit x & 7 of byte x >> 3, rows of `pitch` bytes): what the screen reads
+__global__ void __launch_bounds__(256) guidance_map_pack_kernel(const uint8_t* __restrict__ dmap, int H, int W, int pitch, int n_maps,
+                                                                uint8_t* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_maps * H * pitch) return;
+  const int bx = (int)(idx % pitch);
+  const size_t rowi = idx / pitch;                        // map * H + y
+  const uint8_t* src = dmap + rowi * W + (size_t)bx * 8;
+  uint32_t v = 0;
+  for (int k = 0; k < 8; ++k)
+    if (bx * 8 + k < W && src[k] != 0) v |= 1u << k;
+  out[idx] = (uint8_t)v;
 }
 
 __global__ void __launch_bounds__(256) guidance_map_screen_kernel(LossArgs a) {
@@ -289,7 +273,7 @@ __global__ void __launch_bounds__(256) guidance_map_screen_kernel(LossArgs a) {
     const int row = item / T, g = row / N;
     if (fabsf(__ldg(a.speed + g)) > a.speed_th) {        // loss and gradient are zero for non-moving agents
       flag = true;
-      if (a.coarse) {
+      if (a.pk) {
         const float* M = a.rfa + (size_t)g * 9;
         const float* tr = a.traj + (size_t)item * 6;
         const float L = __ldg(a.extent + g * 3 + 0), Wd = __ldg(a.extent + g * 3 + 1);
@@ -310,17 +294,21 @@ __global__ void __launch_bounds__(256) guidance_map_screen_kernel(LossArgs a) {
         if (x0 == x0 && x1 == x1 && y0 == y0 && y1 == y1) {           // a NaN pose goes to the full path
           const int cx0 = (int)fminf(fmaxf(floorf(x0 - ex), 0.f), (float)(a.W - 1)), cx1 = (int)fminf(fmaxf(floorf(x1 + ex), 0.f), (float)(a.W - 1));
           const int cy0 = (int)fminf(fmaxf(floorf(y0 - ey), 0.f), (float)(a.H - 1)), cy1 = (int)fminf(fmaxf(floorf(y1 + ey), 0.f), (float)(a.H - 1));
-          const int tx0 = cx0 >> 3, tx1 = cx1 >> 3;
-          const uint32_t need = (tx1 >= 31 ? 0xffffffffu : ((2u << tx1) - 1u)) & ~((1u << tx0) - 1u);
-          // every sample point on the road, or every one off it: n_off is 0 or P and the term vanishes (guidance_loss.py:807-809)
-          const uint2* cw = reinterpret_cast<const uint2*>(a.coarse) + (size_t)g * a.tiles_y;
-          bool all_on = true, all_off = true;
-          for (int ty = cy0 >> 3; ty <= (cy1 >> 3); ++ty) {
-            const uint2 w = __ldg(cw + ty);
-            all_on = all_on && ((w.x & need) == need);
-            all_off = all_off && ((w.y & need) == need);
+          const int b0 = cx0 >> 3, nb = (cx1 >> 3) - b0 + 1, width = cx1 - cx0 + 1;
+          if (nb <= 8 && cy1 - cy0 < 64) {                             // larger boxes (a footprint of > 56 pixels) go to the full path
+            // every pixel of the box drivable, or none: n_off is 0 or P and the term vanishes (guidance_loss.py:807-809)
+            const uint64_t need = width >= 64 ? ~0ull : ((1ull << width) - 1ull);
+            const uint8_t* rowp = a.pk + ((size_t)g * a.H + cy0) * a.pk_pitch + b0;
+            bool all_on = true, all_off = true;
+            for (int y = cy0; y <= cy1; ++y, rowp += a.pk_pitch) {
+              uint64_t v = 0;
+              for (int k = 0; k < nb; ++k) v |= (uint64_t)__ldg(rowp + k) << (8 * k);
+              v = (v >> (cx0 & 7)) & need;
+              all_on = all_on && v == need;
+              all_off = all_off && v == 0ull;
+            }
+            flag = !(all_on || all_off);
           }
-          flag = !(all_on || all_off);
         }
       }
     }
@@ -519,21 +507,26 @@ static float host_linspace(float lo, float hi, int n, int i) {
 }
 
 int guidance_prepare_maps(CldHandle* h, const CldScene* sc, cudaStream_t s) {
-  h->coarse_src = nullptr;
-  if (!sc || !sc->drivable_map || sc->map_w > 256 || sc->map_w < 1 || sc->map_h < 1) return 0;     // no screen: every moving item takes the full path
-  const int n_maps = sc->num_scenes * sc->agents_per_scene, tiles_y = (sc->map_h + 7) / 8;
-  const size_t words = (size_t)n_maps * tiles_y * 2;
-  if (words > h->map_coarse_words) {
-    // grows only when a larger scene / map arrives (first guided call): not on the per-step path
-    uint32_t* p = nullptr;
-    CLD_CUDA_OK(h, cudaMalloc((void**)&p, words * sizeof(uint32_t)));
-    h->allocs.push_back(p);
-    h->map_coarse = p; h->map_coarse_words = words;
+  h->screen_src = nullptr;
+  if (!sc || !sc->drivable_map || sc->map_w < 1 || sc->map_h < 1) return 0;     // no screen: every moving item takes the full path
+  const int n_maps = sc->num_scenes * sc->agents_per_scene;
+  if (sc->map_packed) {
+    h->screen_pk = sc->drivable_map; h->screen_pitch = (sc->map_w + 7) / 8;
+  } else {
+    const int pitch = (sc->map_w + 7) / 8;
+    const size_t bytes = (size_t)n_maps * sc->map_h * pitch;
+    if (bytes > h->map_bits_bytes) {
+      // grows only when a larger scene / map arrives (first guided call): not on the per-step path
+      uint8_t* p = nullptr;
+      CLD_CUDA_OK(h, cudaMalloc((void**)&p, bytes));
+      h->allocs.push_back(p);
+      h->map_bits = p; h->map_bits_bytes = bytes;
+    }
+    guidance_map_pack_kernel<<<(unsigned)((bytes + 255) / 256), 256, 0, s>>>(sc->drivable_map, sc->map_h, sc->map_w, pitch, n_maps, h->map_bits);
+    CLD_LAUNCH_OK(h, "guidance_map_pack_kernel");
+    h->screen_pk = h->map_bits; h->screen_pitch = pitch;
   }
-  guidance_map_coarse_kernel<<<(unsigned)((words / 2 * 32 + 255) / 256), 256, 0, s>>>(sc->drivable_map, sc->map_h, sc->map_w, sc->map_packed, tiles_y, n_maps,
-                                                                                 h->map_coarse);
-  CLD_LAUNCH_OK(h, "guidance_map_coarse_kernel");
-  h->coarse_src = sc->drivable_map; h->coarse_agents = n_maps; h->coarse_h = sc->map_h; h->coarse_w = sc->map_w; h->coarse_packed = sc->map_packed;
+  h->screen_src = sc->drivable_map; h->screen_agents = n_maps; h->screen_h = sc->map_h; h->screen_w = sc->map_w; h->screen_packed = sc->map_packed;
   return 0;
 }
 
@@ -541,6 +534,12 @@ static int launch_map(CldHandle* h, const LossArgs& a, cudaStream_t s) {
   const int items = a.R * a.T;
   guidance_map_screen_kernel<<<(items + 255) / 256, 256, 0, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_map_screen_kernel");
+  if (h->env_map_stats) {                       // debug (CLD_MAP_STATS=1): how many items the screen lets through
+    int n = 0;
+    CLD_CUDA_OK(h, cudaStreamSynchronize(s));
+    CLD_CUDA_OK(h, cudaMemcpy(&n, a.work, sizeof(int), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[map screen] %d of %d (row, step) items listed\n", n, items);
+  }
   // persistent warps over the list: 8 CTAs of 8 warps per SM at most, no more warps than items could ever be listed
   int grid = h->num_sms * 8;
   if (grid * 8 > items) grid = (items + 7) / 8;
@@ -573,10 +572,11 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   a.w_sl = g->w_speed_limit; a.speed_limit = g->speed_limit; a.dacc = a.w_al != 0.f ? dacc : nullptr;
   if (a.w_ts != 0.f && !sc->target_speed) return fail(h, CLD_ERR_ARG, "target_speed guidance needs CldScene.target_speed");
   if (a.w_al != 0.f && !dacc) return fail(h, CLD_ERR_STATE, "internal: acc-limit guidance without a d(acc) buffer");
-  a.work = h->map_work; a.assign = 0; a.tiles_y = (sc->map_h + 7) / 8;
-  // the tile table belongs to the maps guidance_prepare_maps last saw
-  a.coarse = (h->coarse_src == (const void*)sc->drivable_map && h->coarse_agents >= S * A && h->coarse_h == sc->map_h && h->coarse_w == sc->map_w &&
-              h->coarse_packed == sc->map_packed) ? h->map_coarse : nullptr;
+  a.work = h->map_work; a.assign = 0;
+  // the screen data belongs to the maps guidance_prepare_maps last saw
+  const bool screen_ok = h->screen_src == (const void*)sc->drivable_map && h->screen_agents >= S * A && h->screen_h == sc->map_h &&
+                         h->screen_w == sc->map_w && h->screen_packed == sc->map_packed;
+  a.pk = screen_ok ? h->screen_pk : nullptr; a.pk_pitch = h->screen_pitch;
   a.D = g->num_disks; a.buffer = g->buffer_dist; a.decay = g->decay_rate; a.speed_th = g->speed_th;
   a.min_target_time = g->min_target_time; a.nl = g->num_points_l; a.nw = g->num_points_w;
   for (int i = 0; i < 16; ++i) {
@@ -608,7 +608,7 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
     if ((rc = launch_map(h, am, h->aux_stream))) return rc;
     CLD_CUDA_OK(h, cudaEventRecord(h->ev_join, h->aux_stream));
   }
-  guidance_loss_grad_kernel<<<S * N, 256, smem, s>>>(a);
+  guidance_loss_grad_kernel<<<S * N, 512, smem, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
   if (fork) {
     CLD_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
