@@ -146,6 +146,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   h->env_guidance_nofork = getenv("CLD_GUIDANCE_NOFORK") != nullptr;
   h->env_lstm_prof = getenv("CLD_LSTM_PROF") != nullptr;
   h->env_map_stats = getenv("CLD_MAP_STATS") != nullptr;
+  h->env_map_exhaustive = getenv("CLD_MAP_EXHAUSTIVE") != nullptr;
   if (const char* e = getenv("CLD_LSTM_PF")) h->env_lstm_pf = atoi(e);
   const int T = cfg->horizon;
   const size_t MR = cfg->max_rows;

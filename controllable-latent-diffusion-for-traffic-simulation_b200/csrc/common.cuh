@@ -131,7 +131,7 @@ struct CldHandle {
   void* lstm_tc = nullptr;
   bool use_lstm_tc = false;
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)
-  bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false;
+  bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false, env_map_exhaustive = false;
   int env_lstm_pf = 3;
 };
 

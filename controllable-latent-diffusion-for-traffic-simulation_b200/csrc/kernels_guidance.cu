@@ -32,6 +32,7 @@ struct LossArgs {
   // map-collision term: screen + work list (see guidance_map_screen_kernel)
   const uint8_t* pk; int pk_pitch;          // the drivable maps with one bit per pixel (rows of pk_pitch bytes; nullptr: no screen)
   int* work;                                // [0] items listed, [1] CTAs of the list kernel that have finished, [2...] items = row * T + t
+  int exhaustive;                           // debug (CLD_MAP_EXHAUSTIVE=1): nearest on-road point by the exhaustive search only
   int assign;                               // the map term OWNS dtraj (writes every item, zeros included) instead of adding to it
   float lwise[16], wwise[16];
   float wts[CLD_MAX_T];   // decay^t / sum_t decay^t  (guidance_loss.py:607-608)
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) guidance_map_list_kernel(LossArgs a) {
       }
       // rounding noise of the coordinates vs the grid spacing (see the comment above the kernel)
       const float sl = nl > 1 ? L / (float)(nl - 1) : 3.4e38f, sw = nw > 1 ? Wd / (float)(nw - 1) : 3.4e38f, smin = fminf(sl, sw);
-      const bool pruned = 6.f * diag * 2.5e-7f * (fabsf(px) + fabsf(py) + L + Wd) < 0.5f * smin * smin;
+      const bool pruned = !a.exhaustive && 6.f * diag * 2.5e-7f * (fabsf(px) + fabsf(py) + L + Wd) < 0.5f * smin * smin;
       const int c0 = __popc(offm[0]), c1 = c0 + __popc(offm[1]), c2 = c1 + __popc(offm[2]);
       // the off-road points are dealt to the lanes in order: pass k takes the 32 k-th .. (32 k + 31)-th of them
       for (int r0 = 0; r0 < n_off; r0 += 32) {
@@ -572,7 +573,7 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   a.w_sl = g->w_speed_limit; a.speed_limit = g->speed_limit; a.dacc = a.w_al != 0.f ? dacc : nullptr;
   if (a.w_ts != 0.f && !sc->target_speed) return fail(h, CLD_ERR_ARG, "target_speed guidance needs CldScene.target_speed");
   if (a.w_al != 0.f && !dacc) return fail(h, CLD_ERR_STATE, "internal: acc-limit guidance without a d(acc) buffer");
-  a.work = h->map_work; a.assign = 0;
+  a.work = h->map_work; a.assign = 0; a.exhaustive = h->env_map_exhaustive ? 1 : 0;
   // the screen data belongs to the maps guidance_prepare_maps last saw
   const bool screen_ok = h->screen_src == (const void*)sc->drivable_map && h->screen_agents >= S * A && h->screen_h == sc->map_h &&
                          h->screen_w == sc->map_w && h->screen_packed == sc->map_packed;
