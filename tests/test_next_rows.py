@@ -130,3 +130,104 @@ def test_get_action_picks_the_sample_the_reference_rule_picks(models_cpu, scene_
     stat = batch["curr_speed"].abs() < 0.5
     assert stat.any() and (action["positions"].cpu()[stat] == 0).all() and (info["action_samples"]["yaws"].cpu()[stat] == 0).all()
     assert algo.num_samp == 1                                    # restored
+
+
+def test_wasserstein_1d_equals_scipy():
+    """the device-resident 1-D Wasserstein distance against scipy.stats.wasserstein_distance, which the reference
+    calls on host copies (guide_dm_trainer.py:277-279): unequal sizes, ties, single elements, heavy tails."""
+    import numpy as np
+    import torch
+    from scipy.stats import wasserstein_distance
+    from cld_b200.metrics import wasserstein_1d
+    rng = np.random.default_rng(5)
+    cases = [(rng.normal(size=1000), rng.normal(0.3, 2.0, size=777)),
+             (rng.integers(0, 5, size=300).astype(np.float64), rng.integers(2, 9, size=450).astype(np.float64)),       # many ties
+             (np.array([1.5]), np.array([-2.0])),
+             (np.array([0.0, 0.0, 0.0]), np.array([0.0])),
+             (rng.standard_cauchy(size=2000).astype(np.float32), rng.standard_cauchy(size=64).astype(np.float32))]
+    for u, v in cases:
+        want = wasserstein_distance(u, v)
+        got = wasserstein_1d(torch.tensor(u), torch.tensor(v)).item()
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (got, want)
+    import pytest
+    with pytest.raises(ValueError):
+        wasserstein_1d(torch.tensor([]), torch.tensor([1.0]))
+    with pytest.raises(ValueError):
+        wasserstein_1d(torch.tensor([float("nan")]), torch.tensor([1.0]))
+
+
+def test_realism_accumulator_equals_the_reference_test_epoch_arithmetic():
+    """The statistics of test_step / on_test_epoch_end (guide_dm_trainer.py:219-296) restated with numpy + scipy exactly as the
+    reference writes them, against cld_b200.metrics on two batches; `last_batch_only` reproduces the reference's re-created lists."""
+    import numpy as np
+    import torch
+    from scipy.stats import wasserstein_distance
+    from cld_b200.metrics import RealismAccumulator
+    torch.manual_seed(11)
+    dt = 0.1
+    batches = [(torch.randn(24, 52, 6), torch.randn(24, 52, 6) * 1.3 + 0.1), (torch.randn(8, 52, 6) * 0.7, torch.randn(8, 52, 6))]
+    stats = [{"offroad_failure_rate": 0.25, "collision_failure_rate": 0.5, "overall_failure_rate": 0.375},
+             {"offroad_failure_rate": 0.75, "collision_failure_rate": 0.0, "overall_failure_rate": 0.375}]
+
+    def reference(bs):
+        outs = []
+        for pred, gt in bs:
+            long_acc_gt, long_acc_pred = gt[..., 4], pred[..., 4]
+            lat_acc_gt, lat_acc_pred = gt[..., 2] * gt[..., 5], pred[..., 2] * pred[..., 5]
+            jerk_gt = (long_acc_gt[:, 1:] - long_acc_gt[:, :-1]) / dt
+            jerk_pred = (long_acc_pred[:, 1:] - long_acc_pred[:, :-1]) / dt
+            outs.append([a.numpy().flatten() for a in (long_acc_gt, long_acc_pred, lat_acc_gt, lat_acc_pred, jerk_gt, jerk_pred)])
+        cat = [np.concatenate([o[i] for o in outs]) for i in range(6)]
+        wl, wa, wj = wasserstein_distance(cat[0], cat[1]), wasserstein_distance(cat[2], cat[3]), wasserstein_distance(cat[4], cat[5])
+        return wl, wa, wj, (wl + wa + wj) / 3.0
+
+    acc = RealismAccumulator(dt)
+    for (pred, gt), st in zip(batches, stats):
+        acc.add_batch(pred, gt, st)
+    got = acc.compute()
+    want = reference(batches)
+    for k, w in zip(("wd_long", "wd_lat", "wd_jerk", "realism_deviation"), want):
+        assert abs(got[k] - w) < 1e-9, (k, got[k], w)
+    assert abs(got["avg_offroad_failure_rate"] - 0.5) < 1e-12 and abs(got["avg_collision_failure_rate"] - 0.25) < 1e-12
+    last = RealismAccumulator(dt, last_batch_only=True)
+    for (pred, gt), st in zip(batches, stats):
+        last.add_batch(pred, gt, st)
+    got_last, want_last = last.compute(), reference(batches[-1:])
+    assert abs(got_last["realism_deviation"] - want_last[3]) < 1e-9 and got_last["avg_offroad_failure_rate"] == 0.75
+
+
+@pytest.mark.gpu
+def test_test_step_mirror_feeds_realism_statistics(models_cpu):
+    """cld_b200.metrics.test_step (guide_dm_trainer.py:205-247 on the B200 path): its statistics equal the reference's arithmetic
+    (numpy + scipy) applied to the trajectories the oracle decodes from the SAME sampled latents."""
+    from scipy.stats import wasserstein_distance
+    from cld_b200.engine import default_guidance
+    from cld_b200.metrics import RealismAccumulator, test_step
+    dm, vae, algo = models_cpu(10)
+    dm = dm.cuda()
+    vae.bind(dm)
+    S, A = 2, 4
+    aux, batch = make_scenes(S, A, seed=77, dense=True)
+    bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    ad = {k: v.cuda() for k, v in aux.items()}
+    torch.manual_seed(3)
+    gt = torch.randn(S * A, 52, 6)
+    acc = RealismAccumulator(algo.step_time)
+    torch.manual_seed(4)
+    stats = test_step(dm, vae, bd, ad, gt, algo, acc, guidance=default_guidance())
+    got = acc.compute()
+    assert set(stats) == {"offroad_failure_rate", "collision_failure_rate", "overall_failure_rate"}
+    # the same sampled latents through the oracle's decoder + rollout, then the reference's arithmetic
+    torch.manual_seed(4)
+    out = dm(bd, ad, algo, guidance=default_guidance())
+    dec_sd = {k: v.detach().cpu() for k, v in vae.lstmvae.lstm_dec.state_dict().items()}
+    traj, _ = O.decode_rollout(dec_sd, out["pred_traj"].cpu(), aux["cond_feat"], aux["curr_states"])
+    scaled = vae.scale_traj(traj)
+    la_p, la_g = scaled[..., 4], gt[..., 4]
+    lat_p, lat_g = scaled[..., 2] * scaled[..., 5], gt[..., 2] * gt[..., 5]
+    dt = algo.step_time
+    jp, jg = (la_p[:, 1:] - la_p[:, :-1]) / dt, (la_g[:, 1:] - la_g[:, :-1]) / dt
+    want = [wasserstein_distance(a.numpy().flatten(), b.numpy().flatten()) for a, b in ((la_g, la_p), (lat_g, lat_p), (jg, jp))]
+    for k, w in zip(("wd_long", "wd_lat", "wd_jerk"), want):
+        assert abs(got[k] - w) <= 1e-3 * max(1.0, abs(w)), (k, got[k], w)
+    assert abs(got["realism_deviation"] - sum(want) / 3.0) <= 1e-3 * max(1.0, sum(want) / 3.0)
