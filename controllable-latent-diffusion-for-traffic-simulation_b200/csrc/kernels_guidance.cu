@@ -54,6 +54,10 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   const int s = blockIdx.x / N, n = blockIdx.x % N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nthr = blockDim.x, nwarps = nthr >> 5;       // 16 warps: one agent per warp at 16 agents per scene (latency-bound loops: more warps per SM)
+  // the agents of a scene are dealt to gridDim.y CTAs (large scenes: 64 agents x 104 steps x 63 partners would otherwise sit on
+  // S * N CTAs); every CTA stages the poses of ALL agents (the partners) and evaluates the terms of agents [i_lo, i_hi)
+  const int per_cta = (A + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int i_lo = (int)blockIdx.y * per_cta, i_hi = min(A, i_lo + per_cta);
   const int ag0 = s * A;
   const float inv_AN = 1.0f / (float)(A * N);
 
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   __syncthreads();
 
   // ---------------- agent-agent collision: warp per agent, lanes over time ---------------------
-  for (int i = warp; i < A; i += nwarps) {
+  for (int i = i_lo + warp; i < i_hi; i += nwarps) {
     const int g = ag0 + i;
     const size_t row = (size_t)g * N + n;
     const float* qi = agt + i * 8;
@@ -98,6 +102,15 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
           if (j == i) continue;
           const float* qj = agt + j * 8;
           const float* pj = pose + ((size_t)j * T + t) * 4;
+          float pd = rad_i + qj[0] + a.buffer;
+          {
+            // the disk centres lie within reach_i / reach_j of the agents' centres: when the centres are further apart than
+            // pd + both reaches no pair of disks is within the penalty distance and the pair (i, j) contributes nothing
+            const float ddx = Pix - pj[0], ddy = Piy - pj[1];
+            const float reach = fmaxf(fabsf(qi[1]), fabsf(qi[2])) + fmaxf(fabsf(qj[1]), fabsf(qj[2]));
+            const float lim = (pd + reach) * 1.0001f + 1e-4f;
+            if (ddx * ddx + ddy * ddy > lim * lim) continue;
+          }
           float best = 3.4e38f, bdx = 0.f, bdy = 0.f, bxi = 0.f;
           for (int d = 0; d < a.D; ++d) {
             float xi = linspace_at(qi[1], qi[2], a.D, d);
@@ -109,7 +122,6 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
               if (dist < best) { best = dist; bdx = dx; bdy = dy; bxi = xi; }
             }
           }
-          float pd = rad_i + qj[0] + a.buffer;
           if (best <= pd) {
             pen_sum += 1.0f - best / pd;
             if (mov_i != 0.f && best > 0.f) {
@@ -144,13 +156,13 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   __syncthreads();
 
   if (a.loss)
-    for (int i = tid; i < A; i += nthr) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;   // map term: own kernel
+    for (int i = i_lo + tid; i < i_hi; i += nthr) a.loss[(size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;   // map term: own kernel
 
   // ---------------- target position (softmin-weighted squared distance): warp per agent ------------
   if (a.w_tp != 0.f && a.target) {
     const int t0 = (int)(a.min_target_time * (float)T);
     const int Tn = T - t0;
-    for (int i = warp; i < A; i += nwarps) {
+    for (int i = i_lo + warp; i < i_hi; i += nwarps) {
       const int g = ag0 + i;
       const size_t row = (size_t)g * N + n;
       const float tx = a.target[g * 2 + 0], ty = a.target[g * 2 + 1];
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
       }
     }
   } else if (a.loss) {
-    for (int i = tid; i < A; i += nthr) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
+    for (int i = i_lo + tid; i < i_hi; i += nthr) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
   }
   __syncthreads();       // the terms below add to dtraj[..][2] of the same rows (different lanes <-> steps than above)
 
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   const bool any_sp = (a.w_ts != 0.f && a.tspeed) || a.w_al != 0.f || a.w_sl != 0.f;
   if (any_sp || a.loss) {
     const float invT = 1.0f / (float)T;
-    for (int i = warp; i < A; i += nwarps) {
+    for (int i = i_lo + warp; i < i_hi; i += nwarps) {
       const int g = ag0 + i;
       const size_t row = (size_t)g * N + n;
       const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);     // in-place detach of stationary agents, as above
@@ -609,7 +621,12 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
     if ((rc = launch_map(h, am, h->aux_stream))) return rc;
     CLD_CUDA_OK(h, cudaEventRecord(h->ev_join, h->aux_stream));
   }
-  guidance_loss_grad_kernel<<<S * N, 512, smem, s>>>(a);
+  // enough CTAs for ~2 per SM: the agents of a scene are split over gridDim.y CTAs when there are few (scene, sample) pairs
+  int split = 1;
+  while (S * N * split < 2 * h->num_sms && split * 2 <= (A + 3) / 4) split *= 2;
+  const int per_cta = (A + split - 1) / split;
+  const int threads = 32 * (per_cta < 4 ? 4 : (per_cta > 16 ? 16 : per_cta));       // one warp per agent, 4 .. 16 warps
+  guidance_loss_grad_kernel<<<dim3((unsigned)(S * N), (unsigned)split), threads, smem, s>>>(a);
   CLD_LAUNCH_OK(h, "guidance_loss_grad_kernel");
   if (fork) {
     CLD_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
