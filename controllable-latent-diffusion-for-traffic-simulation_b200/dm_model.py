@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .keys import agents_per_scene as _agents_per_scene
+from .keys import agents_per_scene as _agents_per_scene, scene_buckets as _scene_buckets, scene_sizes as _scene_sizes
 
 
 class _Slot(nn.Module):
@@ -289,23 +289,23 @@ class DmModel(nn.Module):
         rep = (lambda v: v.repeat_interleave(N, dim=0)) if N > 1 else (lambda v: v)
         cond_rows = rep(cond)
         curr_rows = rep(aux_info['curr_states']) if 'curr_states' in aux_info else None
-        scene, A = None, agents_per_scene
+        A, buckets = agents_per_scene, None
         if guidance is not None or want_indicators:
             if A is None:
-                A = _agents_per_scene(data_batch.get('scene_index'), B)
+                sizes = _scene_sizes(data_batch.get('scene_index'), B)
+                if len(set(sizes)) > 1:
+                    buckets = _scene_buckets(sizes)
+                else:
+                    A = sizes[0]
             elif B % A:
                 raise ValueError("B=%d agents is not a multiple of agents_per_scene=%d" % (B, A))
         dev_seed = (seed or 0) if use_device_rng else 0
-        n_lanes = min(self._lanes, B // A) if (A and self._lanes > 1) else 1
-        if n_lanes > 1:
-            out = self._sample_lanes(n_lanes, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance,
-                                     sampler, want_traj, want_indicators, row_offset)
+        if buckets is not None:
+            out = self._sample_ragged(buckets, data_batch, B, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler,
+                                      want_traj, want_indicators, row_offset)
         else:
-            if guidance is not None or want_indicators:
-                scene = eng.make_scene(data_batch, B // A, A, N)
-            out = eng.sample(x_init, cond_rows, noises=noise, seed=dev_seed, row_offset=row_offset,
-                             curr_rows=curr_rows, scene=scene, guidance=guidance, stride=self.stride, sampler=sampler,
-                             want_traj=want_traj, want_indicators=want_indicators)
+            out = self._sample_uniform(eng, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler,
+                                       want_traj, want_indicators, row_offset)
         log_prob_final = None
         if 0 in steps and sampler == "ddpm":
             # x0 == mean at t == 0, so Normal(mean, sigma).log_prob(x0) is constant (dm_model.py:128-132)
@@ -324,6 +324,46 @@ class DmModel(nn.Module):
             res['offroad'] = out['offroad']
             res['coll'] = out['coll']
         return res
+
+    def _sample_uniform(self, eng, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler, want_traj,
+                        want_indicators, row_offset):
+        """One call of the sampler for a batch whose scenes all hold A agents (or whose scene structure does not matter)."""
+        n_lanes = min(self._lanes, B // A) if (A and self._lanes > 1) else 1
+        if n_lanes > 1:
+            return self._sample_lanes(n_lanes, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance,
+                                      sampler, want_traj, want_indicators, row_offset)
+        scene = eng.make_scene(data_batch, B // A, A, N) if (guidance is not None or want_indicators) else None
+        return eng.sample(x_init, cond_rows, noises=noise, seed=dev_seed, row_offset=row_offset, curr_rows=curr_rows, scene=scene,
+                          guidance=guidance, stride=self.stride, sampler=sampler, want_traj=want_traj, want_indicators=want_indicators)
+
+    def _sample_ragged(self, buckets, data_batch, B, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler, want_traj,
+                       want_indicators, row_offset):
+        """Scenes of different sizes: one uniform sub-batch per distinct scene size (`keys.scene_buckets`), results scattered back
+        into batch order.  Scenes never interact, so this equals sampling every scene on its own.  With pre-drawn `x_init` / `noise`
+        every row gets its own draw whatever the bucketing; the in-kernel Philox generator is keyed by the row's position in the
+        bucketed order (deterministic for a given batch composition, but not the id the row has in `data_batch`)."""
+        device = self.betas.device
+        out, pos = None, 0
+        for A, idx in buckets:
+            idx = idx.to(device)
+            rows = (idx[:, None] * N + torch.arange(N, device=device)[None, :]).reshape(-1)
+            nb = idx.numel()
+            sub = {k: (v.index_select(0, idx.to(v.device)) if (torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B) else v)
+                   for k, v in data_batch.items()}
+            sub['scene_index'] = torch.arange(nb // A, device=device).repeat_interleave(A)
+            sel = lambda v: None if v is None else v.index_select(0, rows.to(v.device))                  # noqa: E731
+            o = self._sample_uniform(self.engine(nb * N), sub, nb, A, N, sel(x_init), sel(cond_rows), sel(curr_rows),
+                                     None if noise is None else noise.index_select(1, rows.to(noise.device)), dev_seed, guidance,
+                                     sampler, want_traj, want_indicators, row_offset + pos)
+            pos += nb * N
+            if out is None:
+                out = {k: (None if v is None else v.new_empty((B * N,) + tuple(v.shape[1:]))) for k, v in o.items()}
+            for k, v in o.items():
+                if v is None:
+                    out[k] = None
+                elif out[k] is not None:
+                    out[k].index_copy_(0, rows.to(v.device), v)
+        return out
 
     def _sample_lanes(self, n_lanes, data_batch, B, A, N, x_init, cond_rows, curr_rows, noise, dev_seed, guidance, sampler,
                       want_traj, want_indicators, row_offset=0):

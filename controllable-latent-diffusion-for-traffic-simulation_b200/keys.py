@@ -22,11 +22,39 @@ def default_guidance(**over):
     return g
 
 
+def scene_sizes(scene_index, B):
+    """Agents per scene, in batch order, checked for contiguity (the agents of a scene must be adjacent rows)."""
+    import torch
+    if scene_index is None:
+        return [int(B)]
+    sidx = torch.as_tensor(scene_index).reshape(-1)
+    if sidx.numel() != B:
+        raise ValueError("scene_index has %d entries for %d agents" % (sidx.numel(), B))
+    _, counts = torch.unique_consecutive(sidx, return_counts=True)
+    if torch.unique(sidx).numel() != counts.numel():
+        raise ValueError("scene_index is not contiguous: the agents of a scene must be adjacent rows")
+    return [int(c) for c in counts.tolist()]
+
+
+def scene_buckets(sizes):
+    """Ragged batches (the reference builds a block-diagonal scene mask from `scene_index`, guidance_loss.py:493-503, and accepts
+    scenes of different sizes): the kernels index rows as (scene * A + agent) * N + sample with ONE A per call, so a ragged batch is
+    sampled as one uniform sub-batch per distinct scene size.  Returns [(A, agent_index LongTensor)], sizes ascending; the agent
+    indices of a bucket are scene-major in batch order."""
+    import torch
+    starts, pos = [], 0
+    for c in sizes:
+        starts.append(pos)
+        pos += c
+    out = []
+    for A in sorted(set(sizes)):
+        idx = torch.cat([torch.arange(st, st + A) for st, c in zip(starts, sizes) if c == A])
+        out.append((A, idx))
+    return out
+
+
 def agents_per_scene(scene_index, B):
-    """Number of agents A of every scene, checked: the kernels index rows as (scene * A + agent) * N + sample, so all
-    scenes of a call must hold the SAME number of CONTIGUOUS agents (the reference builds a block-diagonal mask from
-    `scene_index`, guidance_loss.py:493-503, and accepts ragged scenes; pad scenes to a common A -- extra agents with
-    curr_speed = 0 and far-away positions take no part in any term -- or call once per scene size)."""
+    """Number of agents A of every scene of a UNIFORM batch, checked (ragged batches: `scene_buckets`)."""
     import torch
     if scene_index is None:
         return int(B)

@@ -538,3 +538,36 @@ def test_map_collision_screen_edge_cases_vs_oracle(gpu_models, models_cpu, packe
     # the sampler's path runs the same kernels
     out = eng.sample(z.cuda(), cond.cuda(), noises=None, curr_rows=curr_rows.cuda(), scene=scene, guidance=cfg, sampler="ddim")
     assert torch.isfinite(out["x0"]).all()
+
+
+def test_ragged_scenes_equal_per_scene_calls(gpu_models):
+    """A batch whose scenes hold 4, 2, 6 and 4 agents (trajdata batches are ragged; the reference masks scenes block-diagonally):
+    the guided sampler + indicators on the whole batch equal the same scenes sampled one call per scene, row for row."""
+    from cld_b200.critic import failure_rate_compute, indicators
+    from cld_b200.engine import default_guidance
+    dm, vae, algo = gpu_models(10)
+    sizes = [4, 2, 6, 4]
+    B = sum(sizes)
+    aux, batch = make_scenes(1, B, seed=801, dense=True)                       # one pool of 16 agents, re-partitioned into 4 scenes
+    batch["scene_index"] = torch.cat([torch.full((c,), 10 + i) for i, c in enumerate(sizes)])
+    others = batch["all_other_agents_future_positions"]
+    torch.manual_seed(802)
+    x_init, noises = torch.randn(B, 52, 4), torch.randn(10, B, 52, 4)
+    bd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    ad = {k: v.cuda() for k, v in aux.items()}
+    out = dm(bd, ad, algo, noise=noises.cuda(), x_init=x_init.cuda(), guidance=default_guidance(), want_indicators=True)
+    pos = 0
+    for c in sizes:
+        sl = slice(pos, pos + c)
+        sb = {k: (v[sl].cuda() if (torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B) else v) for k, v in batch.items()}
+        sa = {k: v[sl].cuda() for k, v in aux.items()}
+        one = dm(sb, sa, algo, noise=noises[:, sl].cuda(), x_init=x_init[sl].cuda(), guidance=default_guidance(), want_indicators=True)
+        for k in ("pred_traj", "traj", "offroad", "coll"):
+            assert torch.equal(out[k][sl], one[k]), (k, c)
+        pos += c
+    # the critic drop-ins take the ragged batch as well
+    off, coll, _ = indicators(dm, out["traj"], bd, 1)
+    assert torch.equal(off, out["offroad"]) and torch.equal(coll, out["coll"])
+    stats = failure_rate_compute(dm, out["traj"], bd)
+    assert 0.0 <= stats["overall_failure_rate"] <= 1.0
+    assert others.shape[0] == B

@@ -129,6 +129,23 @@ def test_ragged_or_interleaved_scenes_are_rejected():
         agents_per_scene(torch.tensor([0, 0, 1]), 4)
 
 
+def test_ragged_batches_are_bucketed_by_scene_size():
+    """Scenes of different sizes (the reference accepts them through a block-diagonal mask, guidance_loss.py:493-503) are sampled as
+    one uniform sub-batch per scene size: the buckets partition the agents, keep scenes whole and scene-major."""
+    from cld_b200.keys import scene_buckets, scene_sizes
+    sidx = torch.tensor([5] * 4 + [9] * 2 + [2] * 6 + [7] * 2 + [1] * 4)
+    sizes = scene_sizes(sidx, 18)
+    assert sizes == [4, 2, 6, 2, 4]
+    buckets = scene_buckets(sizes)
+    assert [a for a, _ in buckets] == [2, 4, 6]
+    got = {a: idx.tolist() for a, idx in buckets}
+    assert got[2] == [4, 5, 12, 13] and got[4] == [0, 1, 2, 3, 14, 15, 16, 17] and got[6] == list(range(6, 12))
+    assert sorted(sum(got.values(), [])) == list(range(18))
+    assert scene_sizes(None, 7) == [7]
+    with pytest.raises(ValueError, match="not contiguous"):
+        scene_sizes(torch.tensor([0, 1, 0, 1]), 4)
+
+
 def test_weight_signature_sees_parent_level_loads_and_in_place_updates(models_cpu):
     """the engine's packed weights are a snapshot; the signature it is keyed on must change on a load through a
     PARENT module (Lightning's load_from_checkpoint never calls the child's load_state_dict), on optimizer steps and on
