@@ -536,7 +536,7 @@ def main():
             "metric": "guided scenarios/sec (50-step DDIM)" if a.config in ("cfg1", "cfg2") else "guided scenarios/sec (%s)" % a.config,
             "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": w["scaling"],
-            "vs_baseline": None, "dtype": a.precision, "data": "synthetic", "config": dict(workload_config(a, world, R), lanes=n_lanes),
+            "vs_baseline": None, "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world, R),
             "row_steps_per_s": value * A * N * K_d, "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": "scenarios/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te.item(), "staging": "drivable map shipped bit-packed (1 bit per pixel); H2D of call i+1 overlaps call i "
