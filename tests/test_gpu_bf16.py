@@ -156,7 +156,7 @@ def test_guidance_step_tensor_core_vs_reference_golden(bf16_models, gold):
     assert frac_bad < 5e-3
 
 
-def test_guided_sampler_bf16_finite_and_indicators_consistent(bf16_models):
+def test_guided_sampler_bf16_finite_and_indicators_consistent(bf16_models, models_cpu, monkeypatch):
     """cfg1-shaped guided run in bf16 mode: finite, deterministic, indicators bit-exact on the produced trajectories."""
     dm, vae, algo = bf16_models(100)
     S, A = 4, 16
@@ -177,15 +177,15 @@ def test_guided_sampler_bf16_finite_and_indicators_consistent(bf16_models):
     assert torch.equal(a["pred_traj"], b["pred_traj"]) and torch.equal(a["traj"], b["traj"])
     # the sampler runs the two loss kernels concurrently (auxiliary stream, separate gradient buffers: a + b is rounded once
     # more than the serial fused multiply-add); the serial order must give the same sample up to that rounding
-    import os
-    os.environ["CLD_GUIDANCE_NOFORK"] = "1"
-    dm.stride = 2
-    try:
-        c = dm({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}, {k: v.cuda() for k, v in aux.items()},
-               algo, noise=noises.cuda(), x_init=x_init.cuda(), guidance=default_guidance(), want_indicators=True)
-    finally:
-        dm.stride = 1
-        del os.environ["CLD_GUIDANCE_NOFORK"]
+    # (the switch is read when an engine is created: a second model with the same seed-0 weights)
+    monkeypatch.setenv("CLD_GUIDANCE_NOFORK", "1")
+    dm_s, vae_s, _ = models_cpu(100, precision="bf16")
+    dm_s = dm_s.cuda()
+    vae_s.bind(dm_s)
+    dm_s.stride = 2
+    c = dm_s({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}, {k: v.cuda() for k, v in aux.items()},
+             algo, noise=noises.cuda(), x_init=x_init.cuda(), guidance=default_guidance(), want_indicators=True)
+    monkeypatch.delenv("CLD_GUIDANCE_NOFORK")
     diff = (a["pred_traj"] - c["pred_traj"]).abs()
     frac = (diff > 1e-2 * c["pred_traj"].abs().max()).float().mean().item()
     print("concurrent vs serial loss kernels: rel %.3e, fraction off by > 1%% of max %.5f" % (rel(a["pred_traj"], c["pred_traj"]), frac))
