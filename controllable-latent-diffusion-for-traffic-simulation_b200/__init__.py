@@ -33,7 +33,7 @@ def __getattr__(name):
     if name in ("failure_rate_compute", "compute_reward", "indicators"):
         from . import critic
         return getattr(critic, name)
-    if name in ("RealismAccumulator", "wasserstein_1d", "realism_samples"):
+    if name in ("RealismAccumulator", "wasserstein_1d", "realism_samples", "validation_step"):
         from . import metrics
         return getattr(metrics, name)
     raise AttributeError(name)

@@ -100,3 +100,18 @@ def test_step(dm, vae, batch, aux_info, state_and_action, algo_config, accumulat
 
 
 test_step.__test__ = False        # not a pytest test
+
+
+@torch.no_grad()
+def validation_step(dm, vae, batch, aux_info, algo_config, **sample_kw):
+    """GuideDMLightningModule.validation_step (guide_dm_trainer.py:185-202) on the B200 path: sample, decode + roll out, mean reward
+    (`val/reward`).  Returns a 0-d tensor on the sampler's device."""
+    from .critic import compute_reward
+    out = dm(batch, aux_info, algo_config, **sample_kw)
+    x0, aux = out["pred_traj"], out["aux_info"]
+    action = vae.lstmvae.lstm_dec(x0, aux["cond_feat"])
+    recon_descaled = vae.convert_action_to_state_and_action(action, aux["curr_states"], descaled_output=True)
+    N = int(algo_config.num_samp)
+    B = recon_descaled.shape[0] // N
+    state = recon_descaled.reshape(B, N, *recon_descaled.shape[1:])
+    return compute_reward(dm, state, batch).mean()

@@ -231,3 +231,11 @@ def test_test_step_mirror_feeds_realism_statistics(models_cpu):
     for k, w in zip(("wd_long", "wd_lat", "wd_jerk"), want):
         assert abs(got[k] - w) <= 1e-3 * max(1.0, abs(w)), (k, got[k], w)
     assert abs(got["realism_deviation"] - sum(want) / 3.0) <= 1e-3 * max(1.0, sum(want) / 3.0)
+    # validation_step mirror (guide_dm_trainer.py:185-202): mean reward of the decoded samples = the critic drop-in on the same latents
+    from cld_b200.critic import compute_reward
+    from cld_b200.metrics import validation_step
+    torch.manual_seed(4)
+    r = validation_step(dm, vae, bd, ad, algo, guidance=default_guidance())
+    traj_d = vae.convert_action_to_state_and_action(vae.lstmvae.lstm_dec(out["pred_traj"], ad["cond_feat"]), ad["curr_states"], descaled_output=True)
+    want_r = compute_reward(dm, traj_d.reshape(S * A, 1, 52, 6), bd).mean()
+    assert torch.isfinite(r) and abs(r.item() - want_r.item()) <= 1e-5 * max(1.0, abs(want_r.item()))
