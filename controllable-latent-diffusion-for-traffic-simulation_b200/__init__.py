@@ -24,6 +24,9 @@ def __getattr__(name):
     if name in ("ReplayBuffer", "ppo_surrogate"):
         from . import replay
         return getattr(replay, name)
+    if name in ("GuideDMTrainer", "FusedAdam", "warmup_cosine"):
+        from . import trainer
+        return getattr(trainer, name)
     if name in ("GuidedDiffusionPolicy", "choose_action_from_guidance"):
         from . import policy
         return getattr(policy, name)

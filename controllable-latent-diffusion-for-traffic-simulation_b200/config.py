@@ -43,6 +43,8 @@ def default_algo_config(**over):
         nusc_norm_info=dict(diffuser=[[13.162, -0.13891, 5.0223, -0.0046415, -0.0080072, -0.0013546],
                                       [13.0717, 2.2462, 3.6187, 0.2210, 2.5770, 0.0840]]),
         num_samp=1,
+        # PPO fine-tuning (config.yaml:167-172)
+        ppo_mini_batch=128, ppo_update_times=300, update_interval=10,
     )
     d.update(over)
     return ConfigBase(**d)

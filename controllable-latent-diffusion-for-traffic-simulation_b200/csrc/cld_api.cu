@@ -44,6 +44,7 @@ int prof_end(CldHandle* h, cudaStream_t s) {
 
 template <typename T>
 static int dev_alloc(CldHandle* h, T** p, size_t n) {
+  if (*p) return 0;      // re-load of the weights (every optimizer step of the PPO update): sizes are fixed by the config, reuse
   void* q = nullptr;
   CLD_CUDA_OK(h, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
   h->allocs.push_back(q);
@@ -190,6 +191,7 @@ void cld_destroy(CldHandle* h) {
   if (!h) return;
   tc_destroy(h);
   lstm_tc_destroy(h);
+  train_destroy(h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_tvec) cudaEventDestroy(h->ev_tvec);
@@ -389,6 +391,63 @@ int cld_unet_forward(CldHandle* h, const float* x, const float* cond, const int6
   if (rc) return rc;
   if (!x || !cond || !t || !eps_out) return fail(h, CLD_ERR_ARG, "null argument");
   return unet_dispatch(h, x, cond, t, eps_out, R, (cudaStream_t)stream);
+}
+
+/* ---- denoiser training step (PPO update / DM loss) ---- */
+int cld_unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps_out, int R, void* stream) {
+  int rc = check_rows(h, R);
+  if (rc) return rc;
+  if (!x || !cond || !t || !eps_out) return fail(h, CLD_ERR_ARG, "null argument");
+  if (!h->unet.loaded) return fail(h, CLD_ERR_STATE, "denoiser weights not loaded");
+  return unet_train_forward(h, x, cond, t, eps_out, R, (cudaStream_t)stream);
+}
+
+int cld_unet_backward(CldHandle* h, const float* d_eps, float* const* grads, int n, float* dx_out, int R, void* stream) {
+  int rc = check_rows(h, R);
+  if (rc) return rc;
+  if (!d_eps || !grads) return fail(h, CLD_ERR_ARG, "null argument");
+  for (int i = 0; i < n; ++i)
+    if (!grads[i]) return fail(h, CLD_ERR_ARG, "gradient pointer %d is null", i);
+  return unet_train_backward(h, d_eps, grads, n, dx_out, R, (cudaStream_t)stream);
+}
+
+int cld_ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
+                 const float* reward, float baseline, float clip_eps, float* logp_new_out, float* loss_out, float* d_eps_out, int R,
+                 void* stream) {
+  int rc = check_rows(h, R);
+  if (rc) return rc;
+  if (!eps || !x_t || !x_tm1 || !t || !logp_old || !reward) return fail(h, CLD_ERR_ARG, "null argument");
+  return ppo_head(h, eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps, logp_new_out, loss_out, d_eps_out, R, (cudaStream_t)stream);
+}
+
+int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps_out, int R, void* stream) {
+  int rc = check_rows(h, R);
+  if (rc) return rc;
+  if (!eps || !noise) return fail(h, CLD_ERR_ARG, "null argument");
+  return mse_head(h, eps, noise, loss_out, d_eps_out, R, (cudaStream_t)stream);
+}
+
+int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float* cond, const int64_t* t, const float* logp_old,
+                 const float* reward, float baseline, float clip_eps, float* const* grads, int n, float* logp_new_out, float* loss_out,
+                 int R, void* stream) {
+  int rc = check_rows(h, R);
+  if (rc) return rc;
+  if (!x_t || !x_tm1 || !cond || !t || !logp_old || !reward || !grads) return fail(h, CLD_ERR_ARG, "null argument");
+  if (!h->unet.loaded) return fail(h, CLD_ERR_STATE, "denoiser weights not loaded");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = unet_train_forward(h, x_t, cond, t, h->ws_eps, R, s))) return rc;
+  float* d_eps = train_deps_buffer(h);
+  if ((rc = ppo_head(h, h->ws_eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps, logp_new_out, loss_out, d_eps, R, s))) return rc;
+  for (int i = 0; i < n; ++i)
+    if (!grads[i]) return fail(h, CLD_ERR_ARG, "gradient pointer %d is null", i);
+  return unet_train_backward(h, d_eps, grads, n, nullptr, R, s);
+}
+
+int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  if (!h || !params || !grads || !exp_avg || !exp_avg_sq) return fail(h, CLD_ERR_ARG, "null argument");
+  if (numel < 1 || step < 1) return fail(h, CLD_ERR_ARG, "numel and step must be positive");
+  return adam_step(h, params, grads, exp_avg, exp_avg_sq, (size_t)numel, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
 }
 
 int cld_unet_debug_stage(CldHandle* h, int stage_index, float* out, int R, void* stream) {

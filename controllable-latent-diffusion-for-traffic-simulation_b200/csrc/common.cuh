@@ -130,6 +130,8 @@ struct CldHandle {
   // tensor-core LSTM decoder (opaque, owned by kernels_lstm_tc.cu); used when cfg.precision == CLD_PREC_BF16
   void* lstm_tc = nullptr;
   bool use_lstm_tc = false;
+  // denoiser training state (opaque, owned by kernels_unet_train.cu): activation stash + gradient scratch, allocated on first use
+  void* train = nullptr;
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)
   bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false, env_map_exhaustive = false;
   int env_lstm_pf = 3;
@@ -168,9 +170,23 @@ int prof_end(CldHandle* h, cudaStream_t s);
 int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps,
                       int R, cudaStream_t s);
 int unet_stage_elems(const CldHandle* h, int stage);
+int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s);   // per-row t -> h->tcm, h->tbias
 int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s);   // -> h->tbias (cond part + bias)
 int unet_time_vec(CldHandle* h, int t, cudaStream_t s);                        // -> h->tvec
 int unet_time_vec_to(CldHandle* h, int t, float* dst, cudaStream_t s);
+int gn_mish_launch(CldHandle* h, const float* in, const GnW& n, const float* tbias, int tb_stride, const float* res, float* out,
+                   int T, int C, int R, cudaStream_t s);
+// ---- kernels_unet_train.cu
+int unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R, cudaStream_t s);
+int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, int n, float* dx_out, int R, cudaStream_t s);
+int ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
+             const float* reward, float baseline, float clip, float* logp_new, float* loss_out, float* d_eps, int R, cudaStream_t s);
+int mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps, int R, cudaStream_t s);
+int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+              int step, cudaStream_t s);
+float* train_deps_buffer(CldHandle* h);
+void train_destroy(CldHandle* h);
+void train_invalidate(CldHandle* h);     // the time / cond bias buffers the backward reads were overwritten
 // ---- kernels_step.cu
 // in-kernel noise: Philox4x32-10(key = seed, counter = (idx_base + element quad, seq)); idx_base = GLOBAL row id * T*D/4 and
 // seq = position of the step in the schedule, so the draw of a row does not depend on sharding / chunking / lanes

@@ -174,6 +174,13 @@ __global__ void __launch_bounds__(128) time_cond_mish(const int64_t* __restrict_
   for (int c = tid; c < cond_dim; c += blockDim.x) orow[d + c] = mish_f(cond[(size_t)r * cond_dim + c]);
 }
 
+int gn_mish_launch(CldHandle* h, const float* in, const GnW& n, const float* tbias, int tb_stride, const float* res, float* out,
+                   int T, int C, int R, cudaStream_t s) {
+  gn_mish_fp32<<<R, 256, 0, s>>>(in, n.g, n.b, tbias, tb_stride, res, out, T, C);
+  CLD_LAUNCH_OK(h, "gn_mish_fp32");
+  return 0;
+}
+
 static int launch_conv(CldHandle* h, const ConvW& w, const float* in0, int c0, const float* in1, int c1,
                        int Tin, float* out, int Tout, int Tj, int istride, int ostride, int ooff,
                        const int* ioff, const float* bias, int R, cudaStream_t s) {
@@ -242,6 +249,7 @@ static int tap(CldHandle* h, int stage, const float* buf, int R, cudaStream_t s)
 int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s) {
   const UnetW& u = h->unet;
   const CldConfig& c = h->cfg;
+  train_invalidate(h);
   time_cond_mish<<<R, 128, 0, s>>>(t, cond, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, h->tcm, c.base_dim, c.cond_dim);
   CLD_LAUNCH_OK(h, "time_cond_mish");
   ConvW tb; tb.w = u.tb_w; tb.b = u.tb_b; tb.cin = c.base_dim + c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;
@@ -297,6 +305,7 @@ int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s) {
   const UnetW& u = h->unet;
   const CldConfig& c = h->cfg;
   const size_t n = (size_t)R * c.cond_dim;
+  train_invalidate(h);
   cond_mish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cond, h->tcm, n);
   CLD_LAUNCH_OK(h, "cond_mish_kernel");
   ConvW tb; tb.w = u.tb_w + (size_t)c.base_dim * u.tb_total; tb.b = u.tb_b; tb.cin = c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;

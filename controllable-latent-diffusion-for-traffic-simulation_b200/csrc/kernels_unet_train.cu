@@ -1,0 +1,932 @@
+// the PPO inner loop's denoiser update (reference src/trainers/guide_dm_trainer.py:127-183,
+// models/dm/dm_model.py:165-174) without autograd: forward of TemporalMapUnet (src/tbsim/models/temporal.py:122-180) that keeps
+// what the backward needs, the analytic backward of every layer down to the 148 parameter gradients (written in the state-dict
+// layouts the reference's optimizer sees), the PPO clipped-surrogate and MSE loss heads, and Adam (torch.optim.Adam semantics,
+// guide_dm_trainer.py:59-65).  fp32 on the CUDA cores: this is the parity-first build of the row (1e-4 against autograd of the real
+// reference module); the minibatch is 128 rows (config.yaml:168), i.e. launch- and latency-bound.
+//
+// Layout: activations channels-last [R, T', C] fp32 as in kernels_unet_fp32.cu.  Every convolution (forward), its data gradient
+// and its weight gradient is one implicit GEMM over M = R * T' rows:
+//   forward   out[r, j*os+oo, :]  = bias + sum_tap in[r, j*is+io[tap], :] @ W[tap]              (W packed [tap][cin][cout])
+//   data grad dIn[r, ti, :]      += sum_tap dOut[r, ...] @ W[tap]^T                              (same kernel, B read transposed)
+//   weight    dW[tap][ci][co]     = sum_{r,j} in[r, j*is+io[tap], ci] * dOut[r, j*os+oo, co]     (split over M, fixed-order reduce)
+// No atomics anywhere: all reductions have a fixed order, so a step is bit-reproducible.
+#include "common.cuh"
+
+namespace cld {
+
+// ------------------------------------------------------------------------------------------------
+// implicit GEMM, forward / data gradient
+// ------------------------------------------------------------------------------------------------
+struct TGemm {
+  const float* in0; int c0;     // A source [R, Tin, c0]
+  const float* in1; int c1;     // optional concatenated source [R, Tin, c1]
+  int Tin;
+  const float* w[5];            // per GEMM tap: TRANSB = 0: [K][ldw] (n contiguous);  TRANSB = 1: [N][ldw] (k contiguous)
+  int ldw;
+  const float* bias;            // [N] or nullptr
+  float* out; int Tout; int cout;
+  int ntaps; int ioff[5]; int istride, ostride, ooff;
+  int Tj; int R; int accum;
+};
+
+constexpr int GBM = 128, GBN = 64, GBK = 16;
+
+template <bool TRANSB>
+__global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
+  __shared__ float As[GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+  const int M = a.R * a.Tj;
+  const int cin = a.c0 + a.c1;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int a_row[2], a_q[2], a_r[2], a_j[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + i * 256;
+    a_row[i] = idx >> 2; a_q[i] = idx & 3;
+    const int m = m0 + a_row[i];
+    a_r[i] = (m < M) ? m / a.Tj : -1;
+    a_j[i] = (m < M) ? m % a.Tj : 0;
+  }
+  const int kchunks = (cin + GBK - 1) / GBK;
+  for (int tap = 0; tap < a.ntaps; ++tap) {
+    const float* __restrict__ wt = a.w[tap];
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const int ci0 = kc * GBK;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = ci0 + a_q[i] * 4;
+        const int ti = a_j[i] * a.istride + a.ioff[tap];
+        if (a_r[i] >= 0 && c < cin && ti >= 0 && ti < a.Tin) {
+          const float* p = (c < a.c0) ? a.in0 + ((size_t)a_r[i] * a.Tin + ti) * a.c0 + c
+                                      : a.in1 + ((size_t)a_r[i] * a.Tin + ti) * a.c1 + (c - a.c0);
+          v = *reinterpret_cast<const float4*>(p);
+        }
+        As[a_q[i] * 4 + 0][a_row[i]] = v.x; As[a_q[i] * 4 + 1][a_row[i]] = v.y;
+        As[a_q[i] * 4 + 2][a_row[i]] = v.z; As[a_q[i] * 4 + 3][a_row[i]] = v.w;
+      }
+      if (!TRANSB) {
+        const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = ci0 + b_k, n = n0 + b_n;
+        if (c < cin && n < a.cout) v = *reinterpret_cast<const float4*>(wt + (size_t)c * a.ldw + n);
+        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = v;
+      } else {
+        const int b_n = tid >> 2, b_k = (tid & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = ci0 + b_k, n = n0 + b_n;
+        if (c < cin && n < a.cout) v = *reinterpret_cast<const float4*>(wt + (size_t)n * a.ldw + c);
+        Bs[b_k + 0][b_n] = v.x; Bs[b_k + 1][b_n] = v.y; Bs[b_k + 2][b_n] = v.z; Bs[b_k + 3][b_n] = v.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < GBK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n < a.cout) {
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + ty * 8 + i;
+      if (m < M) {
+        const int r = m / a.Tj, j = m % a.Tj;
+        float4* op = reinterpret_cast<float4*>(a.out + ((size_t)r * a.Tout + j * a.ostride + a.ooff) * a.cout + n);
+        float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+        if (a.accum) { const float4 p = *op; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *op = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[tap][ci][co] = sum_m in[m @ tap][ci] * dOut[m][co], M split over grid.z, partials reduced in fixed order
+// ------------------------------------------------------------------------------------------------
+struct TWgrad {
+  const float* in0; int c0; const float* in1; int c1; int Tin;
+  const float* dout; int Tout; int cout;
+  int ntaps; int ioff[5]; int istride, ostride, ooff;
+  int Tj; int R;
+  float* part;                  // [splits][ntaps][cin][cout]
+  int splits, chunk;            // chunk = rows of M per split (multiple of 16)
+};
+
+__global__ void __launch_bounds__(256) twgrad_kernel(TWgrad a) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
+  const int tap = blockIdx.z % a.ntaps, split = blockIdx.z / a.ntaps;
+  const int cin = a.c0 + a.c1;
+  const int M = a.R * a.Tj;
+  const int m_lo = split * a.chunk, m_hi = min(M, m_lo + a.chunk);
+  const int ty = tid >> 4, tx = tid & 15;
+  const int l_row = tid >> 4, l_c = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int mb = m_lo; mb < m_hi; mb += 16) {
+    const int m = mb + l_row;
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    if (m < m_hi) {
+      const int r = m / a.Tj, j = m - r * a.Tj;
+      const int ti = j * a.istride + a.ioff[tap];
+      const int c = ci0 + l_c;
+      if (c < cin && ti >= 0 && ti < a.Tin) {
+        const float* p = (c < a.c0) ? a.in0 + ((size_t)r * a.Tin + ti) * a.c0 + c
+                                    : a.in1 + ((size_t)r * a.Tin + ti) * a.c1 + (c - a.c0);
+        va = *reinterpret_cast<const float4*>(p);
+      }
+      const int n = co0 + l_c;
+      if (n < a.cout) vb = *reinterpret_cast<const float4*>(a.dout + ((size_t)r * a.Tout + j * a.ostride + a.ooff) * a.cout + n);
+    }
+    *reinterpret_cast<float4*>(&As[l_row][l_c]) = va;
+    *reinterpret_cast<float4*>(&Bs[l_row][l_c]) = vb;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 y = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float xv[4] = {x.x, x.y, x.z, x.w}, yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int n = co0 + tx * 4;
+  if (n < a.cout) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ci = ci0 + ty * 4 + i;
+      if (ci < cin)
+        *reinterpret_cast<float4*>(a.part + (((size_t)split * a.ntaps + tap) * cin + ci) * a.cout + n) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+  }
+}
+
+// sum the split partials (fixed order) and write the gradient in the reference's parameter layout:
+//   Conv1d / Linear  [cout][cin][K]   (transposed = 0)      ConvTranspose1d  [cin][cout][K]   (transposed = 1)
+// The columns [co_off, co_off + co_n) of the packed matrix are written (a slice for the concatenated time-bias projection).
+struct TKs { int k[5]; };
+__global__ void __launch_bounds__(256) twreduce_kernel(const float* __restrict__ part, int splits, int ntaps, int cin, int cout,
+                                                       int co_off, int co_n, float* __restrict__ dst, int K, TKs ks, int transposed) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int total = ntaps * cin * co_n;
+  if (idx >= total) return;
+  const int co = idx % co_n, ci = (idx / co_n) % cin, tap = idx / (co_n * cin);
+  const size_t stride = (size_t)ntaps * cin * cout;
+  const float* p = part + ((size_t)tap * cin + ci) * cout + co_off + co;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += p[i * stride];
+  const int k = ks.k[tap];
+  if (transposed) dst[((size_t)ci * co_n + co) * K + k] = s;
+  else dst[((size_t)co * cin + ci) * K + k] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a [M, C] matrix (bias / affine / time-bias gradients): two stages, fixed order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int M, int C, float* __restrict__ partial) {
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int m = blockIdx.x;
+  const int st = gridDim.x;
+  for (; m + 3 * st < M; m += 4 * st) {
+    s0 += src[(size_t)m * C + c]; s1 += src[(size_t)(m + st) * C + c];
+    s2 += src[(size_t)(m + 2 * st) * C + c]; s3 += src[(size_t)(m + 3 * st) * C + c];
+  }
+  for (; m < M; m += st) s0 += src[(size_t)m * C + c];
+  partial[(size_t)blockIdx.x * C + c] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dst) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * C + c];
+  dst[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------------
+// dst[m, c] (+)= src[m * ld + off + c]
+__global__ void __launch_bounds__(256) slice_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n, int C, int ld,
+                                                    int off, int add) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const size_t m = i / C;
+  const int c = (int)(i - m * C);
+  const float v = src[m * ld + off + c];
+  dst[i] = add ? dst[i] + v : v;
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return (x > 20.f) ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float mish_fwd(float x) { return x * tanhf(softplus_f(x)); }
+// d/dx [x tanh(softplus(x))] = tanh(sp) + x sigmoid(x) (1 - tanh(sp)^2)   (ATen mish_backward)
+__device__ __forceinline__ float mish_grad(float x) {
+  const float tsp = tanhf(softplus_f(x));
+  const float sig = 1.f / (1.f + expf(-x));
+  return fmaf(x * sig, 1.f - tsp * tsp, tsp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of GroupNorm(8) -> Mish -> (+ time bias | + residual)        (diffuser_helpers.py:58-64, temporal.py:37-45)
+//   x = conv output [R,T,C];  xh = (x - mean) rstd;  u = xh g + b;  y = mish(u) (+ ...)
+//   dU = dY mish'(u);  dg[c] += dU xh;  db[c] += dU;  dxh = dU g;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh))
+// One CTA per row, warp = group.  cpg divides 32, so a lane always meets the same channel: per-channel sums stay in registers.
+// Per-row partials (dg, db, and sum_t dY = d(time bias)) are written; colsum reduces them over the rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, float* __restrict__ rp_g, float* __restrict__ rp_b,
+                                                          float* __restrict__ dtb, int tb_stride, int T, int C) {
+  const int r = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = C >> 3, n = T * cpg;
+  const size_t base = (size_t)r * T * C + g * cpg;
+  const float* xin = x + base;
+  const float* dyin = dy + base;
+  float* dxo = dx + base;
+  float s = 0.f;
+  for (int e = lane; e < n; e += 32) s += xin[(e / cpg) * C + (e % cpg)];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)n;
+  float v = 0.f;
+  for (int e = lane; e < n; e += 32) {
+    const float d = xin[(e / cpg) * C + (e % cpg)] - mean;
+    v = fmaf(d, d, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = 1.0f / sqrtf(v / (float)n + 1e-5f);
+  const int cl = lane % cpg, c = g * cpg + cl;        // this lane's channel (cpg | 32)
+  const float gm = gamma[c], bt = beta[c];
+  float sg = 0.f, sb = 0.f, sy = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int e = lane; e < n; e += 32) {
+    const int off = (e / cpg) * C + cl;
+    const float xh = (xin[off] - mean) * rstd;
+    const float u = fmaf(xh, gm, bt);
+    const float gy = dyin[off];
+    const float du = gy * mish_grad(u);
+    const float dxh = du * gm;
+    sg = fmaf(du, xh, sg); sb += du; sy += gy;
+    s1 += dxh; s2 = fmaf(dxh, xh, s2);
+    dxo[off] = dxh;
+  }
+  // per-channel sums: lanes with equal lane % cpg
+  for (int o = 16; o >= cpg; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if (lane < cpg) {
+    rp_g[(size_t)r * C + c] = sg; rp_b[(size_t)r * C + c] = sb;
+    if (dtb) dtb[(size_t)r * tb_stride + c] = sy;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const float m1 = s1 / (float)n, m2 = s2 / (float)n;
+  for (int e = lane; e < n; e += 32) {
+    const int off = (e / cpg) * C + cl;
+    const float xh = (xin[off] - mean) * rstd;
+    dxo[off] = rstd * (dxo[off] - m1 - xh * m2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the time MLP (temporal.py:74-79): emb -> Linear(d,4d) -> Mish -> Linear(4d,d), then the block-side Mish.
+// dtm [R, ld] holds d(loss)/d(Mish(time embedding)) in its first d columns.  Writes the operands of the two weight-gradient GEMMs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) time_mlp_bwd_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, const float* __restrict__ freqs,
+                                                           const float* __restrict__ dtm, int ld, float* __restrict__ emb_o,
+                                                           float* __restrict__ hid_o, float* __restrict__ dpre1_o,
+                                                           float* __restrict__ dpre2_o, int d) {
+  __shared__ float emb[64], pre1[256], hid[256], dp2[64];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float tv = (float)t[r];
+  const int half = d >> 1;
+  if (tid < d) {
+    const float a = tv * freqs[tid % half];
+    emb[tid] = (tid < half) ? sinf(a) : cosf(a);
+    emb_o[(size_t)r * d + tid] = emb[tid];
+  }
+  __syncthreads();
+  for (int o = tid; o < 4 * d; o += blockDim.x) {
+    float acc = b1[o];
+    for (int k = 0; k < d; ++k) acc = fmaf(w1[o * d + k], emb[k], acc);
+    pre1[o] = acc; hid[o] = mish_fwd(acc);
+    hid_o[(size_t)r * 4 * d + o] = hid[o];
+  }
+  __syncthreads();
+  if (tid < d) {
+    float acc = b2[tid];
+    for (int k = 0; k < 4 * d; ++k) acc = fmaf(w2[tid * 4 * d + k], hid[k], acc);
+    const float g = dtm[(size_t)r * ld + tid] * mish_grad(acc);
+    dp2[tid] = g;
+    dpre2_o[(size_t)r * d + tid] = g;
+  }
+  __syncthreads();
+  for (int o = tid; o < 4 * d; o += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(w2[k * 4 * d + o], dp2[k], acc);
+    dpre1_o[(size_t)r * 4 * d + o] = acc * mish_grad(pre1[o]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss heads
+// ------------------------------------------------------------------------------------------------
+// PPO clipped surrogate on log_prob (guide_dm_trainer.py:150-168 with dm_model.py:165-174), one CTA per row:
+//   mean = c1[t] x_t - c2[t] eps;  logp = mean_{T,D} Normal(mean, sigma[t]).log_prob(x_tm1);  ratio = exp(logp - logp_old)
+//   loss = -(1/R) sum_r min(ratio A, clamp(ratio, 1-e, 1+e) A),  A = reward - baseline
+// d_eps = dloss/deps (torch.min sends the gradient to the smaller argument; inside the clip range both arguments carry it).
+__global__ void __launch_bounds__(128) ppo_head_kernel(const float* __restrict__ eps, const float* __restrict__ x_t,
+                                                       const float* __restrict__ x_tm1, const int64_t* __restrict__ t,
+                                                       const float* __restrict__ sched, int n_t, const float* __restrict__ logp_old,
+                                                       const float* __restrict__ reward, float baseline, float clip,
+                                                       float* __restrict__ logp_new, float* __restrict__ loss_row,
+                                                       float* __restrict__ d_eps, int n, int R) {
+  __shared__ float red[4];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  int tt = (int)t[r];
+  tt = tt < 0 ? 0 : (tt >= n_t ? n_t - 1 : tt);
+  const float c1 = sched[tt], c2 = sched[n_t + tt], lv = sched[2 * n_t + tt];
+  const float sigma = expf(0.5f * lv), var = sigma * sigma;
+  const size_t base = (size_t)r * n;
+  float s = 0.f;
+  for (int i = tid; i < n; i += 128) {
+    const float mean = c1 * x_t[base + i] - c2 * eps[base + i];
+    const float d = x_tm1[base + i] - mean;
+    s += -(d * d) / (2.f * var) - logf(sigma) - 0.91893853320467274f;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  const float logp = ((red[0] + red[1]) + (red[2] + red[3])) / (float)n;
+  const float ratio = expf(logp - logp_old[r]);
+  const float A = reward[r] - baseline;
+  const float s1 = ratio * A, s2 = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip) * A;
+  const bool inside = ratio >= 1.f - clip && ratio <= 1.f + clip;
+  float gl = 0.f;                                   // d min(s1, s2) / d logp
+  if (inside || s1 < s2) gl = s1;
+  else if (s1 == s2) gl = 0.5f * s1;
+  if (tid == 0) {
+    if (logp_new) logp_new[r] = logp;
+    loss_row[r] = -fminf(s1, s2) / (float)R;
+  }
+  if (d_eps) {
+    const float k = (-gl / (float)R) * (-c2) / (var * (float)n);
+    for (int i = tid; i < n; i += 128) {
+      const float mean = c1 * x_t[base + i] - c2 * eps[base + i];
+      d_eps[base + i] = k * (x_tm1[base + i] - mean);
+    }
+  }
+}
+
+// F.mse_loss(noise, eps) of DmModel.compute_losses (dm_model.py:83-90): loss_row[r] = sum_i (eps - noise)^2 / (R n)
+__global__ void __launch_bounds__(128) mse_head_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
+                                                       float* __restrict__ loss_row, float* __restrict__ d_eps, int n, int R) {
+  __shared__ float red[4];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const size_t base = (size_t)r * n;
+  const float inv = 1.f / ((float)R * (float)n);
+  float s = 0.f;
+  for (int i = tid; i < n; i += 128) {
+    const float d = eps[base + i] - noise[base + i];
+    s = fmaf(d, d, s);
+    if (d_eps) d_eps[base + i] = 2.f * d * inv;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) loss_row[r] = ((red[0] + red[1]) + (red[2] + red[3])) * inv;
+}
+
+// one CTA: out[0] = sum_r v[r] (fixed order)
+__global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__ v, int R, float* __restrict__ out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < R; i += 256) s += v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// torch.optim.Adam (no amsgrad; weight_decay added to the gradient), one flat parameter vector
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                                                   float bc1, float bc2_sqrt) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float pi = p[i];
+  const float gi = fmaf(wd, pi, g[i]);
+  const float mi = m[i] + (gi - m[i]) * (1.f - b1);               // torch: exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct BlkStash { const float* in0; int c0; const float* in1; int c1; int T; float *A0, *B0, *A1, *OUT; };
+struct BlkIdx { int tw, tb, c0w, c0b, g0, b0, c1w, c1b, g1, b1, rw, rb; };
+
+struct TrainState {
+  int cap_rows = 0;
+  float* arena = nullptr;
+  BlkStash blk[12];
+  float *p0 = nullptr, *p1 = nullptr, *q0 = nullptr, *q1 = nullptr, *fA = nullptr, *fB = nullptr, *tmpR = nullptr;
+  float *gA = nullptr, *gB = nullptr, *gX = nullptr, *gY = nullptr, *gcat8 = nullptr, *gcat10 = nullptr;
+  float *dtbias = nullptr, *dtcm = nullptr, *emb = nullptr, *hid = nullptr, *dpre1 = nullptr, *dpre2 = nullptr;
+  float *rp_g = nullptr, *rp_b = nullptr, *loss_row = nullptr, *deps = nullptr;
+  float* part = nullptr;  size_t part_floats = 0;
+  float* colpart = nullptr;
+  float* tb_bgrad = nullptr;       // [tb_total] bias gradient of the concatenated time / cond projection
+  float* sched_dev = nullptr;
+  const float* x = nullptr;
+  const int64_t* t = nullptr;
+  int R = 0;
+  bool fwd_valid = false;
+};
+
+static TrainState* ts_of(CldHandle* h) { return reinterpret_cast<TrainState*>(h->train); }
+
+void train_destroy(CldHandle* h) {
+  TrainState* st = ts_of(h);
+  if (!st) return;
+  if (st->arena) cudaFree(st->arena);
+  if (st->part) cudaFree(st->part);
+  if (st->colpart) cudaFree(st->colpart);
+  if (st->sched_dev) cudaFree(st->sched_dev);
+  delete st;
+  h->train = nullptr;
+}
+
+void train_invalidate(CldHandle* h) {
+  if (TrainState* st = ts_of(h)) st->fwd_valid = false;
+}
+
+constexpr int COLSUM_BLOCKS = 128;
+constexpr size_t PART_FLOATS = (size_t)6 << 20;
+
+static int train_prepare(CldHandle* h, int R) {
+  if (!h->train) h->train = new TrainState();
+  TrainState* st = ts_of(h);
+  const CldConfig& c = h->cfg;
+  const int tb_total = h->unet.tb_total;
+  if (!st->part) {
+    CLD_CUDA_OK(h, cudaMalloc((void**)&st->part, PART_FLOATS * sizeof(float)));
+    st->part_floats = PART_FLOATS;
+    CLD_CUDA_OK(h, cudaMalloc((void**)&st->colpart, (size_t)(COLSUM_BLOCKS + 1) * CLD_TB_TOTAL_MAX * sizeof(float)));
+    st->tb_bgrad = st->colpart + (size_t)COLSUM_BLOCKS * CLD_TB_TOTAL_MAX;
+    CLD_CUDA_OK(h, cudaMalloc((void**)&st->sched_dev, (size_t)3 * c.n_timesteps * sizeof(float)));
+  }
+  if (R <= st->cap_rows) return 0;
+  if (st->arena) { cudaFree(st->arena); st->arena = nullptr; st->cap_rows = 0; }
+  const size_t E = h->act_elems;                 // per-row elements of the largest activation
+  const int td = c.base_dim;
+  for (int i = 0; i < 3; ++i) {
+    const int cpg = c.dims[i] / 8;
+    if (c.dims[i] > 256 || (cpg != 1 && cpg != 2 && cpg != 4 && cpg != 8 && cpg != 16 && cpg != 32))
+      return fail(h, CLD_ERR_UNSUPPORTED, "the denoiser backward needs dims of 8 x {1,2,4,8,16,32} channels");
+  }
+  if (tb_total > CLD_TB_TOTAL_MAX) return fail(h, CLD_ERR_UNSUPPORTED, "time-bias width %d above %d", tb_total, CLD_TB_TOTAL_MAX);
+  if (td > 64) return fail(h, CLD_ERR_UNSUPPORTED, "the denoiser backward needs base_dim <= 64");
+  // 12 blocks x 4 + p0 p1 q0 q1 fA fB tmpR + gA gB gX gY + 2 x 2 (concat gradients) = 63 E, + the small per-row vectors
+  const size_t per_row = 63 * E + (size_t)tb_total + 64 + td + 4 * td + 4 * td + td + 2 * 256 + 1 + (size_t)c.horizon * c.latent_dim;
+  const size_t cap = (size_t)R;
+  CLD_CUDA_OK(h, cudaMalloc((void**)&st->arena, per_row * cap * sizeof(float)));
+  float* p = st->arena;
+  auto take = [&](size_t per) { float* q = p; p += per * cap; return q; };
+  for (int b = 0; b < 12; ++b) { st->blk[b].A0 = take(E); st->blk[b].B0 = take(E); st->blk[b].A1 = take(E); st->blk[b].OUT = take(E); }
+  st->p0 = take(E); st->p1 = take(E); st->q0 = take(E); st->q1 = take(E); st->fA = take(E); st->fB = take(E); st->tmpR = take(E);
+  st->gA = take(E); st->gB = take(E); st->gX = take(E); st->gY = take(E); st->gcat8 = take(2 * E); st->gcat10 = take(2 * E);
+  st->dtbias = take(tb_total); st->dtcm = take(64); st->emb = take(td); st->hid = take(4 * td); st->dpre1 = take(4 * td);
+  st->dpre2 = take(td); st->rp_g = take(256); st->rp_b = take(256); st->loss_row = take(1);
+  st->deps = take((size_t)c.horizon * c.latent_dim);
+  st->cap_rows = R;
+  st->fwd_valid = false;
+  return 0;
+}
+
+static const int kOff5[5] = {-2, -1, 0, 1, 2};
+static const int kOff3[5] = {-1, 0, 1, 0, 0};
+static const int kOff1[5] = {0, 0, 0, 0, 0};
+
+// forward convolution  out = conv(in) (+ bias)
+static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int Tin, float* out, int Tout,
+                    int Tj, int istride, int ostride, int ooff, const int* ioff, const float* bias, int R, cudaStream_t s) {
+  TGemm a;
+  a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin;
+  for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)(i < w.ntaps ? i : 0) * w.cin * w.cout; a.ioff[i] = i < w.ntaps ? ioff[i] : 0; }
+  a.ldw = w.cout; a.bias = bias; a.out = out; a.Tout = Tout; a.cout = w.cout; a.ntaps = w.ntaps;
+  a.istride = istride; a.ostride = ostride; a.ooff = ooff; a.Tj = Tj; a.R = R; a.accum = 0;
+  dim3 grid((R * Tj + GBM - 1) / GBM, (w.cout + GBN - 1) / GBN);
+  tgemm_kernel<false><<<grid, 256, 0, s>>>(a);
+  CLD_LAUNCH_OK(h, "tgemm_kernel<fwd>");
+  return 0;
+}
+
+// data gradient: out[r, j*ostride+ooff, 0:n_out) (+)= sum_i dout[r, j*istride+ioff[i], :] @ W[taps[i]]^T
+static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, const int* ioff, const float* dout, int Tdout,
+                      float* out, int Tout, int n_out, int Tj, int istride, int ostride, int ooff, int accum, int R, cudaStream_t s) {
+  TGemm a;
+  a.in0 = dout; a.c0 = w.cout; a.in1 = nullptr; a.c1 = 0; a.Tin = Tdout;
+  for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)taps[i < ntaps ? i : 0] * w.cin * w.cout; a.ioff[i] = i < ntaps ? ioff[i] : 0; }
+  a.ldw = w.cout; a.bias = nullptr; a.out = out; a.Tout = Tout; a.cout = n_out; a.ntaps = ntaps;
+  a.istride = istride; a.ostride = ostride; a.ooff = ooff; a.Tj = Tj; a.R = R; a.accum = accum;
+  dim3 grid((R * Tj + GBM - 1) / GBM, (n_out + GBN - 1) / GBN);
+  tgemm_kernel<true><<<grid, 256, 0, s>>>(a);
+  CLD_LAUNCH_OK(h, "tgemm_kernel<dgrad>");
+  return 0;
+}
+
+// weight gradient of one packed matrix [ntaps][cin][cout] -> partials in st->part; `splits_out` for the reduce
+static int conv_wgrad(CldHandle* h, int cin_total, int cout, int ntaps, const int* ioff, const float* in0, int c0, const float* in1,
+                      int c1, int Tin, const float* dout, int Tdout, int Tj, int istride, int ostride, int ooff, int R,
+                      int* splits_out, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  TWgrad a;
+  a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin; a.dout = dout; a.Tout = Tdout; a.cout = cout; a.ntaps = ntaps;
+  for (int i = 0; i < 5; ++i) a.ioff[i] = i < ntaps ? ioff[i] : 0;
+  a.istride = istride; a.ostride = ostride; a.ooff = ooff; a.Tj = Tj; a.R = R; a.part = st->part;
+  const int M = R * Tj;
+  const int tiles = ((cin_total + 63) / 64) * ((cout + 63) / 64) * ntaps;
+  int splits = (4 * h->num_sms + tiles - 1) / tiles;
+  const int max_by_m = (M + 255) / 256;
+  if (splits > max_by_m) splits = max_by_m;
+  const size_t wsz = (size_t)ntaps * cin_total * cout;
+  if ((size_t)splits * wsz > st->part_floats) splits = (int)(st->part_floats / wsz);
+  if (splits < 1) return fail(h, CLD_ERR_UNSUPPORTED, "weight-gradient scratch too small");
+  int chunk = (M + splits - 1) / splits;
+  chunk = (chunk + 15) / 16 * 16;
+  splits = (M + chunk - 1) / chunk;
+  a.splits = splits; a.chunk = chunk;
+  dim3 grid((cin_total + 63) / 64, (cout + 63) / 64, ntaps * splits);
+  twgrad_kernel<<<grid, 256, 0, s>>>(a);
+  CLD_LAUNCH_OK(h, "twgrad_kernel");
+  *splits_out = splits;
+  return 0;
+}
+
+static int wreduce(CldHandle* h, int splits, int ntaps, int cin, int cout, int co_off, int co_n, float* dst, int K, const int* ks,
+                   int transposed, cudaStream_t s) {
+  TKs k;
+  for (int i = 0; i < 5; ++i) k.k[i] = i < ntaps ? ks[i] : 0;
+  const int total = ntaps * cin * co_n;
+  twreduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(ts_of(h)->part, splits, ntaps, cin, cout, co_off, co_n, dst, K, k, transposed);
+  CLD_LAUNCH_OK(h, "twreduce_kernel");
+  return 0;
+}
+
+static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  int nblk = (M + 31) / 32;
+  if (nblk > COLSUM_BLOCKS) nblk = COLSUM_BLOCKS;
+  dim3 grid(nblk, (C + 255) / 256);
+  colsum_kernel<<<grid, 256, 0, s>>>(src, M, C, st->colpart);
+  CLD_LAUNCH_OK(h, "colsum_kernel");
+  colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(st->colpart, nblk, C, dst);
+  CLD_LAUNCH_OK(h, "colsum_final_kernel");
+  return 0;
+}
+
+static int slice(CldHandle* h, float* dst, const float* src, size_t M, int C, int ld, int off, int add, cudaStream_t s) {
+  const size_t n = M * C;
+  slice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n, C, ld, off, add);
+  CLD_LAUNCH_OK(h, "slice_kernel");
+  return 0;
+}
+
+int gn_mish_launch(CldHandle* h, const float* in, const GnW& n, const float* tbias, int tb_stride, const float* res, float* out, int T,
+                   int C, int R, cudaStream_t s);   // kernels_unet_fp32.cu
+
+static int block_fwd(CldHandle* h, int bi, const float* in0, int c0, const float* in1, int c1, int T, int R, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  const ResBlockW& rb = h->unet.rb[bi];
+  BlkStash& b = st->blk[bi];
+  b.in0 = in0; b.c0 = c0; b.in1 = in1; b.c1 = c1; b.T = T;
+  int rc;
+  if ((rc = conv_fwd(h, rb.c0, in0, c0, in1, c1, T, b.A0, T, T, 1, 1, 0, kOff5, rb.c0.b, R, s))) return rc;
+  if ((rc = gn_mish_launch(h, b.A0, rb.n0, h->tbias + rb.tb_off, h->unet.tb_total, nullptr, b.B0, T, rb.cout, R, s))) return rc;
+  if ((rc = conv_fwd(h, rb.c1, b.B0, rb.cout, nullptr, 0, T, b.A1, T, T, 1, 1, 0, kOff5, rb.c1.b, R, s))) return rc;
+  const float* res = in0;
+  if (rb.res.w) {
+    if ((rc = conv_fwd(h, rb.res, in0, c0, in1, c1, T, st->tmpR, T, T, 1, 1, 0, kOff1, rb.res.b, R, s))) return rc;
+    res = st->tmpR;
+  }
+  return gn_mish_launch(h, b.A1, rb.n1, nullptr, 0, res, b.OUT, T, rb.cout, R, s);
+}
+
+int unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R, cudaStream_t s) {
+  int rc;
+  if ((rc = train_prepare(h, R))) return rc;
+  TrainState* st = ts_of(h);
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  const int T = c.horizon, T2 = T / 2, T4 = T / 4;
+  const int d0 = c.dims[0], d1 = c.dims[1], d2 = c.dims[2], D = c.latent_dim;
+  st->fwd_valid = false;
+  if ((rc = unet_time_bias(h, cond, t, R, s))) return rc;      // -> h->tcm, h->tbias (kept for the backward)
+  BlkStash* b = st->blk;
+  if ((rc = block_fwd(h, 0, x, D, nullptr, 0, T, R, s))) return rc;
+  if ((rc = block_fwd(h, 1, b[0].OUT, d0, nullptr, 0, T, R, s))) return rc;
+  if ((rc = conv_fwd(h, u.down[0], b[1].OUT, d0, nullptr, 0, T, st->p0, T2, T2, 2, 1, 0, kOff3, u.down[0].b, R, s))) return rc;
+  if ((rc = block_fwd(h, 2, st->p0, d0, nullptr, 0, T2, R, s))) return rc;
+  if ((rc = block_fwd(h, 3, b[2].OUT, d1, nullptr, 0, T2, R, s))) return rc;
+  if ((rc = conv_fwd(h, u.down[1], b[3].OUT, d1, nullptr, 0, T2, st->p1, T4, T4, 2, 1, 0, kOff3, u.down[1].b, R, s))) return rc;
+  if ((rc = block_fwd(h, 4, st->p1, d1, nullptr, 0, T4, R, s))) return rc;
+  if ((rc = block_fwd(h, 5, b[4].OUT, d2, nullptr, 0, T4, R, s))) return rc;
+  if ((rc = block_fwd(h, 6, b[5].OUT, d2, nullptr, 0, T4, R, s))) return rc;
+  if ((rc = block_fwd(h, 7, b[6].OUT, d2, nullptr, 0, T4, R, s))) return rc;
+  if ((rc = block_fwd(h, 8, b[7].OUT, d2, b[5].OUT, d2, T4, R, s))) return rc;
+  if ((rc = block_fwd(h, 9, b[8].OUT, d1, nullptr, 0, T4, R, s))) return rc;
+  const int off_e[5] = {0, -1, 0, 0, 0}, off_o[5] = {1, 0, 0, 0, 0};
+  if ((rc = conv_fwd(h, u.up[0][0], b[9].OUT, d1, nullptr, 0, T4, st->q0, T2, T4, 1, 2, 0, off_e, u.up_b[0], R, s))) return rc;
+  if ((rc = conv_fwd(h, u.up[0][1], b[9].OUT, d1, nullptr, 0, T4, st->q0, T2, T4, 1, 2, 1, off_o, u.up_b[0], R, s))) return rc;
+  if ((rc = block_fwd(h, 10, st->q0, d1, b[3].OUT, d1, T2, R, s))) return rc;
+  if ((rc = block_fwd(h, 11, b[10].OUT, d0, nullptr, 0, T2, R, s))) return rc;
+  if ((rc = conv_fwd(h, u.up[1][0], b[11].OUT, d0, nullptr, 0, T2, st->q1, T, T2, 1, 2, 0, off_e, u.up_b[1], R, s))) return rc;
+  if ((rc = conv_fwd(h, u.up[1][1], b[11].OUT, d0, nullptr, 0, T2, st->q1, T, T2, 1, 2, 1, off_o, u.up_b[1], R, s))) return rc;
+  if ((rc = conv_fwd(h, u.fin0, st->q1, d0, nullptr, 0, T, st->fA, T, T, 1, 1, 0, kOff5, u.fin0.b, R, s))) return rc;
+  if ((rc = gn_mish_launch(h, st->fA, u.fin0n, nullptr, 0, nullptr, st->fB, T, d0, R, s))) return rc;
+  if ((rc = conv_fwd(h, u.fin1, st->fB, d0, nullptr, 0, T, eps, T, T, 1, 1, 0, kOff1, u.fin1.b, R, s))) return rc;
+  st->x = x; st->t = t; st->R = R; st->fwd_valid = true;
+  return 0;
+}
+
+// gradient of GroupNorm+Mish: dA = d(conv output); gamma / beta gradients -> grads; optional time-bias gradient slice
+static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float* dA, float* dgamma, float* dbeta, float* dtb,
+                  int T, int C, int R, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, st->rp_g, st->rp_b, dtb, h->unet.tb_total, T, C);
+  CLD_LAUNCH_OK(h, "gn_mish_bwd_kernel");
+  int rc;
+  if ((rc = colsum(h, st->rp_g, R, C, dgamma, s))) return rc;
+  return colsum(h, st->rp_b, R, C, dbeta, s);
+}
+
+static const int kK5[5] = {0, 1, 2, 3, 4}, kK1[5] = {0, 0, 0, 0, 0}, kK3[5] = {0, 1, 2, 0, 0};
+static const int kTap5[5] = {0, 1, 2, 3, 4};
+static const int kNeg5[5] = {2, 1, 0, -1, -2};
+
+// weight + bias gradient of a stride-1 convolution with `ntaps` (5 | 1) taps
+static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, const float* in0, int c0, const float* in1, int c1, int T,
+                            const float* dout, float* dw, float* db, int R, cudaStream_t s) {
+  int rc, splits;
+  if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s)))
+    return rc;
+  if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s))) return rc;
+  return colsum(h, dout, R * T, cout, db, s);
+}
+
+// backward of one residual block.  dOUT [R,T,cout] -> dIN [R,T,cin_total] (written), parameter gradients -> grads[...]
+static int block_bwd(CldHandle* h, int bi, const BlkIdx& ix, const float* dOUT, float* dIN, float* const* grads, int R, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  const ResBlockW& rb = h->unet.rb[bi];
+  const BlkStash& b = st->blk[bi];
+  const int T = b.T, C = rb.cout, cin = b.c0 + b.c1;
+  int rc;
+  // second Conv1dBlock
+  if ((rc = gn_bwd(h, b.A1, rb.n1, dOUT, st->gA, grads[ix.g1], grads[ix.b1], nullptr, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, C, C, 5, b.B0, C, nullptr, 0, T, st->gA, grads[ix.c1w], grads[ix.c1b], R, s))) return rc;
+  if ((rc = conv_dgrad(h, rb.c1, 5, kTap5, kNeg5, st->gA, T, st->gB, T, C, T, 1, 1, 0, 0, R, s))) return rc;
+  // first Conv1dBlock (+ time / cond bias)
+  if ((rc = gn_bwd(h, b.A0, rb.n0, st->gB, st->gA, grads[ix.g0], grads[ix.b0], st->dtbias + rb.tb_off, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, cin, C, 5, b.in0, b.c0, b.in1, b.c1, T, st->gA, grads[ix.c0w], grads[ix.c0b], R, s))) return rc;
+  if ((rc = conv_dgrad(h, rb.c0, 5, kTap5, kNeg5, st->gA, T, dIN, T, cin, T, 1, 1, 0, 0, R, s))) return rc;
+  // residual path
+  if (rb.res.w) {
+    if ((rc = conv_param_grads(h, cin, C, 1, b.in0, b.c0, b.in1, b.c1, T, dOUT, grads[ix.rw], grads[ix.rb], R, s))) return rc;
+    const int tap0[5] = {0, 0, 0, 0, 0};
+    if ((rc = conv_dgrad(h, rb.res, 1, tap0, kOff1, dOUT, T, dIN, T, cin, T, 1, 1, 0, 1, R, s))) return rc;
+  } else {
+    if ((rc = slice(h, dIN, dOUT, (size_t)R * T, C, C, 0, 1, s))) return rc;
+  }
+  return 0;
+}
+
+// backward of Downsample1d (Conv1d k3 s2 p1): in [R,T,C] -> out [R,T/2,C]
+static int down_bwd(CldHandle* h, const ConvW& w, const float* in, int T, const float* dout, float* din, float* dw, float* db, int R,
+                    cudaStream_t s) {
+  const int C = w.cout, Th = T / 2;
+  int rc, splits;
+  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s))) return rc;
+  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s))) return rc;
+  if ((rc = colsum(h, dout, R * Th, C, db, s))) return rc;
+  // forward: out[j] = sum_tap in[2j + tap - 1] W[tap].  even ti = 2m: tap 1, j = m;  odd ti = 2m + 1: tap 0 with j = m + 1, tap 2 with j = m
+  const int te[5] = {1, 0, 0, 0, 0}, oe[5] = {0, 0, 0, 0, 0};
+  const int to[5] = {0, 2, 0, 0, 0}, oo[5] = {1, 0, 0, 0, 0};
+  if ((rc = conv_dgrad(h, w, 1, te, oe, dout, Th, din, T, C, Th, 1, 2, 0, 0, R, s))) return rc;
+  return conv_dgrad(h, w, 2, to, oo, dout, Th, din, T, C, Th, 1, 2, 1, 0, R, s);
+}
+
+// backward of Upsample1d (ConvTranspose1d k4 s2 p1): in [R,T,C] -> out [R,2T,C]; phases packed as up[0] (even outputs: torch taps 1, 3
+// reading in[j], in[j-1]) and up[1] (odd outputs: torch taps 0, 2 reading in[j+1], in[j])
+static int up_bwd(CldHandle* h, const ConvW* up, const float* in, int T, const float* dout, float* din, float* dw, float* db, int R,
+                  cudaStream_t s) {
+  const int C = up[0].cout;
+  const int off_e[5] = {0, -1, 0, 0, 0}, off_o[5] = {1, 0, 0, 0, 0};
+  const int kte[5] = {1, 3, 0, 0, 0}, kto[5] = {0, 2, 0, 0, 0};
+  int rc, splits;
+  if ((rc = conv_wgrad(h, C, C, 2, off_e, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 0, R, &splits, s))) return rc;
+  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kte, 1, s))) return rc;
+  if ((rc = conv_wgrad(h, C, C, 2, off_o, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 1, R, &splits, s))) return rc;
+  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kto, 1, s))) return rc;
+  if ((rc = colsum(h, dout, R * 2 * T, C, db, s))) return rc;
+  // dIn[ti] = sum_ph sum_tap dOut[2 (ti - io_ph[tap]) + ph] W_ph[tap]^T
+  const int t01[5] = {0, 1, 0, 0, 0};
+  const int ie[5] = {0, 2, 0, 0, 0};          // phase 0: -2 * {0, -1} + 0
+  const int io[5] = {-1, 1, 0, 0, 0};         // phase 1: -2 * {1, 0} + 1
+  if ((rc = conv_dgrad(h, up[0], 2, t01, ie, dout, 2 * T, din, T, C, T, 2, 1, 0, 0, R, s))) return rc;
+  return conv_dgrad(h, up[1], 2, t01, io, dout, 2 * T, din, T, C, T, 2, 1, 0, 1, R, s);
+}
+
+int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, int n, float* dx_out, int R, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  if (!st || !st->fwd_valid || st->R != R)
+    return fail(h, CLD_ERR_STATE, "cld_unet_backward needs the cld_unet_train_forward of the same rows immediately before it");
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  const int T = c.horizon, T2 = T / 2, T4 = T / 4;
+  const int d0 = c.dims[0], d1 = c.dims[1], d2 = c.dims[2], D = c.latent_dim, td = c.base_dim, tdim = c.base_dim + c.cond_dim;
+  // ---- parameter indices in state-dict order (the order cld_load_unet consumes)
+  BlkIdx ix[12];
+  int i_down[2][2], i_up[2][2], i_fin[6];
+  {
+    const int order[12] = {0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 6, 7};   // exec index of the blocks in state-dict order
+    int idx = 4, k = 0;
+    auto blk = [&](int e) {
+      BlkIdx& b = ix[e];
+      b.tw = idx++; b.tb = idx++; b.c0w = idx++; b.c0b = idx++; b.g0 = idx++; b.b0 = idx++;
+      b.c1w = idx++; b.c1b = idx++; b.g1 = idx++; b.b1 = idx++;
+      if (u.rb[e].res.w) { b.rw = idx++; b.rb = idx++; } else b.rw = b.rb = -1;
+    };
+    for (int lvl = 0; lvl < 3; ++lvl) {
+      blk(order[k++]); blk(order[k++]);
+      if (lvl < 2) { i_down[lvl][0] = idx++; i_down[lvl][1] = idx++; }
+    }
+    for (int lvl = 0; lvl < 2; ++lvl) {
+      blk(order[k++]); blk(order[k++]);
+      i_up[lvl][0] = idx++; i_up[lvl][1] = idx++;
+    }
+    blk(order[k++]); blk(order[k++]);
+    for (int i = 0; i < 6; ++i) i_fin[i] = idx++;
+    if (idx != n) return fail(h, CLD_ERR_ARG, "cld_unet_backward: expected %d gradient tensors, got %d", idx, n);
+  }
+  int rc, splits;
+  const BlkStash* b = st->blk;
+  float *gX = st->gX, *gY = st->gY;
+  // ---- final_conv: Conv1d(1x1) <- Conv1dBlock
+  if ((rc = conv_param_grads(h, d0, D, 1, st->fB, d0, nullptr, 0, T, d_eps, grads[i_fin[4]], grads[i_fin[5]], R, s))) return rc;
+  {
+    const int tap0[5] = {0, 0, 0, 0, 0};
+    if ((rc = conv_dgrad(h, u.fin1, 1, tap0, kOff1, d_eps, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;
+  }
+  if ((rc = gn_bwd(h, st->fA, u.fin0n, gX, st->gA, grads[i_fin[2]], grads[i_fin[3]], nullptr, T, d0, R, s))) return rc;
+  if ((rc = conv_param_grads(h, d0, d0, 5, st->q1, d0, nullptr, 0, T, st->gA, grads[i_fin[0]], grads[i_fin[1]], R, s))) return rc;
+  if ((rc = conv_dgrad(h, u.fin0, 5, kTap5, kNeg5, st->gA, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;          // gX = d q1
+  // ---- ups.1: upsample, blocks 11, 10
+  if ((rc = up_bwd(h, u.up[1], b[11].OUT, T2, gX, gY, grads[i_up[1][0]], grads[i_up[1][1]], R, s))) return rc;      // gY = d o11
+  if ((rc = block_bwd(h, 11, ix[11], gY, gX, grads, R, s))) return rc;                                              // gX = d o10
+  if ((rc = block_bwd(h, 10, ix[10], gX, st->gcat10, grads, R, s))) return rc;                                      // (d q0 | d sk1)
+  if ((rc = slice(h, gX, st->gcat10, (size_t)R * T2, d1, 2 * d1, 0, 0, s))) return rc;                              // gX = d q0
+  // ---- ups.0: upsample, blocks 9, 8
+  if ((rc = up_bwd(h, u.up[0], b[9].OUT, T4, gX, gY, grads[i_up[0][0]], grads[i_up[0][1]], R, s))) return rc;       // gY = d o9
+  if ((rc = block_bwd(h, 9, ix[9], gY, gX, grads, R, s))) return rc;                                                // gX = d o8
+  if ((rc = block_bwd(h, 8, ix[8], gX, st->gcat8, grads, R, s))) return rc;                                         // (d o7 | d sk2)
+  if ((rc = slice(h, gX, st->gcat8, (size_t)R * T4, d2, 2 * d2, 0, 0, s))) return rc;                               // gX = d o7
+  // ---- mid blocks 7, 6
+  if ((rc = block_bwd(h, 7, ix[7], gX, gY, grads, R, s))) return rc;                                                // gY = d o6
+  if ((rc = block_bwd(h, 6, ix[6], gY, gX, grads, R, s))) return rc;                                                // gX = d o5 (mid part)
+  if ((rc = slice(h, gX, st->gcat8, (size_t)R * T4, d2, 2 * d2, d2, 1, s))) return rc;                              // + skip part
+  // ---- downs.2: blocks 5, 4
+  if ((rc = block_bwd(h, 5, ix[5], gX, gY, grads, R, s))) return rc;                                                // gY = d o4
+  if ((rc = block_bwd(h, 4, ix[4], gY, gX, grads, R, s))) return rc;                                                // gX = d p1
+  // ---- downs.1: downsample, blocks 3, 2
+  if ((rc = down_bwd(h, u.down[1], b[3].OUT, T2, gX, gY, grads[i_down[1][0]], grads[i_down[1][1]], R, s))) return rc;   // gY = d o3 (down part)
+  if ((rc = slice(h, gY, st->gcat10, (size_t)R * T2, d1, 2 * d1, d1, 1, s))) return rc;                             // + skip part
+  if ((rc = block_bwd(h, 3, ix[3], gY, gX, grads, R, s))) return rc;                                                // gX = d o2
+  if ((rc = block_bwd(h, 2, ix[2], gX, gY, grads, R, s))) return rc;                                                // gY = d p0
+  // ---- downs.0: downsample, blocks 1, 0
+  if ((rc = down_bwd(h, u.down[0], b[1].OUT, T, gY, gX, grads[i_down[0][0]], grads[i_down[0][1]], R, s))) return rc;    // gX = d o1
+  if ((rc = block_bwd(h, 1, ix[1], gX, gY, grads, R, s))) return rc;                                                // gY = d o0
+  if ((rc = block_bwd(h, 0, ix[0], gY, gX, grads, R, s))) return rc;                                                // gX = d x [R,T,4]
+  if (dx_out) CLD_CUDA_OK(h, cudaMemcpyAsync(dx_out, gX, (size_t)R * T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // ---- time / cond projections of the 12 blocks: tbias = tcm @ tb_w + tb_b  (tb_w packed [tdim][tb_total])
+  const int tbt = u.tb_total;
+  if ((rc = conv_wgrad(h, tdim, tbt, 1, kOff1, h->tcm, tdim, nullptr, 0, 1, st->dtbias, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
+  for (int e = 0; e < 12; ++e)
+    if ((rc = wreduce(h, splits, 1, tdim, tbt, u.rb[e].tb_off, u.rb[e].cout, grads[ix[e].tw], 1, kK1, 0, s))) return rc;
+  if ((rc = colsum(h, st->dtbias, R, tbt, st->tb_bgrad, s))) return rc;
+  for (int e = 0; e < 12; ++e)
+    CLD_CUDA_OK(h, cudaMemcpyAsync(grads[ix[e].tb], st->tb_bgrad + u.rb[e].tb_off, u.rb[e].cout * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+  // d(Mish(time embedding)) = dtbias @ tb_w[0:td, :]^T   (the cond half of tcm is an input, not a parameter)
+  {
+    ConvW tb; tb.w = u.tb_w; tb.cin = tdim; tb.cout = tbt; tb.ntaps = 1;
+    const int tap0[5] = {0, 0, 0, 0, 0};
+    if ((rc = conv_dgrad(h, tb, 1, tap0, kOff1, st->dtbias, 1, st->dtcm, 1, td, 1, 1, 1, 0, 0, R, s))) return rc;
+  }
+  time_mlp_bwd_kernel<<<R, 128, 0, s>>>(st->t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, st->dtcm, td, st->emb, st->hid, st->dpre1,
+                                        st->dpre2, td);
+  CLD_LAUNCH_OK(h, "time_mlp_bwd_kernel");
+  // Linear(d, 4d): weight [4d][d];  Linear(4d, d): weight [d][4d]
+  if ((rc = conv_wgrad(h, td, 4 * td, 1, kOff1, st->emb, td, nullptr, 0, 1, st->dpre1, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
+  if ((rc = wreduce(h, splits, 1, td, 4 * td, 0, 4 * td, grads[0], 1, kK1, 0, s))) return rc;
+  if ((rc = colsum(h, st->dpre1, R, 4 * td, grads[1], s))) return rc;
+  if ((rc = conv_wgrad(h, 4 * td, td, 1, kOff1, st->hid, 4 * td, nullptr, 0, 1, st->dpre2, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
+  if ((rc = wreduce(h, splits, 1, 4 * td, td, 0, td, grads[2], 1, kK1, 0, s))) return rc;
+  if ((rc = colsum(h, st->dpre2, R, td, grads[3], s))) return rc;
+  return 0;
+}
+
+static int upload_schedule(CldHandle* h, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  const Schedule& sc = h->sched;
+  if (!sc.loaded) return fail(h, CLD_ERR_STATE, "schedule not loaded");
+  const int n = h->cfg.n_timesteps;
+  CLD_CUDA_OK(h, cudaMemcpyAsync(st->sched_dev, sc.x_t_cof.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+  CLD_CUDA_OK(h, cudaMemcpyAsync(st->sched_dev + n, sc.noise_cof.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+  CLD_CUDA_OK(h, cudaMemcpyAsync(st->sched_dev + 2 * n, sc.logvar.data(), n * sizeof(float), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
+             const float* reward, float baseline, float clip, float* logp_new, float* loss_out, float* d_eps, int R, cudaStream_t s) {
+  int rc;
+  if ((rc = train_prepare(h, R))) return rc;
+  if ((rc = upload_schedule(h, s))) return rc;
+  TrainState* st = ts_of(h);
+  const int n = h->cfg.horizon * h->cfg.latent_dim;
+  ppo_head_kernel<<<R, 128, 0, s>>>(eps, x_t, x_tm1, t, st->sched_dev, h->cfg.n_timesteps, logp_old, reward, baseline, clip, logp_new,
+                                    st->loss_row, d_eps, n, R);
+  CLD_LAUNCH_OK(h, "ppo_head_kernel");
+  if (loss_out) {
+    sum_rows_kernel<<<1, 256, 0, s>>>(st->loss_row, R, loss_out);
+    CLD_LAUNCH_OK(h, "sum_rows_kernel");
+  }
+  return 0;
+}
+
+int mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps, int R, cudaStream_t s) {
+  int rc;
+  if ((rc = train_prepare(h, R))) return rc;
+  TrainState* st = ts_of(h);
+  const int n = h->cfg.horizon * h->cfg.latent_dim;
+  mse_head_kernel<<<R, 128, 0, s>>>(eps, noise, st->loss_row, d_eps, n, R);
+  CLD_LAUNCH_OK(h, "mse_head_kernel");
+  if (loss_out) {
+    sum_rows_kernel<<<1, 256, 0, s>>>(st->loss_row, R, loss_out);
+    CLD_LAUNCH_OK(h, "sum_rows_kernel");
+  }
+  return 0;
+}
+
+float* train_deps_buffer(CldHandle* h) { return ts_of(h) ? ts_of(h)->deps : nullptr; }
+
+int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+              int step, cudaStream_t s) {
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+  CLD_LAUNCH_OK(h, "adam_kernel");
+  return 0;
+}
+
+}  // namespace cld

@@ -162,6 +162,9 @@ class DmModel(nn.Module):
         self._decoder_sd = None
         self._decoder_mod = None          # weakref to the VAE's lstm_dec container (VaeModel.bind)
         self._loaded_sig = None
+        # denoiser training (sec. 8 f-2): fp32 engine with the activation stash, flat parameter / gradient vectors
+        self._train_eng, self._train_sig, self._train_gen, self._param_epoch = None, None, 0, 0
+        self._flat, self._flat_grad, self._flat_views = None, None, None
 
     def _create_dynamics(self):
         if str(self._dynamics_type) in ("Unicycle", "DynType.UNICYCLE"):
@@ -185,13 +188,14 @@ class DmModel(nn.Module):
     def invalidate(self):
         """Force a re-read of all parameters at the next call (normally not needed: see `_weights_signature`)."""
         self._engine_key = None
+        self._train_sig = None
 
     def _weights_signature(self):
         """The engine holds a packed SNAPSHOT of the parameters.  Every in-place change of a tensor (Module.load_state_dict
         at any level of the module tree -- Lightning's load_from_checkpoint recurses through _load_from_state_dict and never
         calls a child's load_state_dict --, optimizer steps, manual copy_) bumps its `_version`; identity covers `.data =`
         / re-assignment.  The engine is rebuilt whenever the signature differs from the one it was packed from."""
-        sig = [(id(p), p._version) for p in self.model.parameters()]
+        sig = [(id(p), p._version, p.data_ptr()) for p in self.model.parameters()] + [self._param_epoch]
         sig += [(id(b), b._version) for b in self.buffers()]
         dec = self._decoder_mod() if self._decoder_mod is not None else None
         if dec is not None:
@@ -413,13 +417,124 @@ class DmModel(nn.Module):
         mean = self.x_t_cof[t].reshape(shp) * xt - self.noise_cof[t].reshape(shp) * noise
         return mean, self.posterior_log_variance_clipped[t].reshape(shp)
 
-    @torch.no_grad()
+    def _grad_mode(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
+
     def log_prob(self, x_t, x_t_minus_1, aux_info, t):
-        """Forward value of DmModel.log_prob (dm_model.py:165-174); no autograd (PPO update is out of scope)."""
-        eps = self.denoise(x_t, aux_info, t)
+        """DmModel.log_prob (dm_model.py:165-174).  Under autograd (the PPO update, guide_dm_trainer.py:150-168) the denoiser
+        runs through `denoise_train`, whose backward is the analytic CUDA backward: `loss.backward(); opt.step()` of the
+        reference work unchanged.  Without grad it is the forward value on the sampling engine."""
+        if self._grad_mode():
+            eps = self.denoise_train(x_t, aux_info, t)
+        else:
+            with torch.no_grad():
+                eps = self.denoise(x_t, aux_info, t)
         mean, log_var = self.x_tminus1_mean_var(x_t, eps, t)
         sigma = (0.5 * log_var).exp()
         return torch.distributions.Normal(mean, sigma).log_prob(x_t_minus_1).mean(dim=(1, 2))
 
-    def compute_losses(self, aux_info, z0):
-        raise NotImplementedError("training of the denoiser is outside the sampling hot path (SURVEY.md sec. 8f-2)")
+    def q_sample(self, x_0, t, noise):
+        """dm_model.py:92-97."""
+        shp = (-1,) + (1,) * (x_0.dim() - 1)
+        return self.sqrt_alphas_cumprod[t].reshape(shp) * x_0 + self.sqrt_one_minus_alphas_cumprod[t].reshape(shp) * noise
+
+    def compute_losses(self, aux_info, z0, *, t=None, noise=None):
+        """DmModel.compute_losses (dm_model.py:83-90): MSE between the drawn noise and the denoiser's prediction at a random
+        step; differentiable w.r.t. the denoiser's parameters through `denoise_train`.  `t` / `noise` may be supplied (tests)."""
+        if t is None:
+            t = torch.randint(0, self.n_timesteps, (len(z0),), device=z0.device).long()
+        if noise is None:
+            noise = torch.randn_like(z0)
+        z_noisy = self.q_sample(z0, t, noise)
+        eps = self.denoise_train(z_noisy, aux_info, t) if self._grad_mode() else self.denoise(z_noisy, aux_info, t)
+        return torch.nn.functional.mse_loss(noise, eps)
+
+    # ------------------------------------------------------------------ denoiser training (SURVEY.md sec. 8 f-2)
+    def mark_parameters_changed(self):
+        """Call after changing parameters through raw pointers (the fused Adam kernel): tensor versions do not see that."""
+        self._param_epoch += 1
+
+    def train_engine(self, rows=1):
+        """fp32 engine that holds the training stash (forward activations + gradient scratch); weights re-packed in place whenever
+        the parameters changed (every optimizer step)."""
+        dev = self.betas.device
+        if dev.type != "cuda":
+            raise RuntimeError("cld_b200.DmModel runs only on a CUDA (B200) device; there is no CPU path")
+        from .engine import Engine
+        sig = self._weights_signature()
+        eng = self._train_eng
+        if eng is None or eng.max_rows < rows or eng.device != dev:
+            if eng is not None:
+                eng.close()
+            eng = self._train_eng = Engine(horizon=self.horizon, latent_dim=self.latent_size, cond_dim=self.cond_dim,
+                                           base_dim=self.base_dim, dims=self.model.dims[1:], hidden=self._hidden,
+                                           n_timesteps=self.n_timesteps, max_rows=max(int(rows), 128), precision="fp32",
+                                           dt=float(self.dt), acce_bound=self.dyn.acce_bound, vbound=self.dyn.vbound,
+                                           max_steer=self.dyn.max_steer, max_yawvel=self.dyn.max_yawvel,
+                                           norm_mean=self._norm[0], norm_std=self._norm[1], device=dev)
+            eng.set_schedule(dict(self.named_buffers()))
+            self._train_sig = None
+        if self._train_sig != sig:
+            eng.load_unet(self.model.state_dict())
+            self._train_sig = sig
+        return eng
+
+    def denoise_train(self, x, aux_info, t):
+        """eps = self.model(x, aux_info, t) as a node of the autograd graph (parameters and x are its inputs)."""
+        params = list(self.model.parameters())
+        return _UnetTrainFn.apply(self, x, aux_info['cond_feat'], t, *params)
+
+    def flatten_parameters(self):
+        """Re-seat the denoiser's parameters (and their .grad) as views of ONE flat fp32 vector each, so the fused Adam kernel
+        updates the model in a single launch and the backward writes straight into the optimizer's gradient vector.  Values,
+        names and state_dict are unchanged.  -> (flat_params, flat_grads)."""
+        params = list(self.model.parameters())
+        if self._flat is not None and all(p.data_ptr() == v.data_ptr() for p, v in zip(params, self._flat_views[0])):
+            return self._flat, self._flat_grad
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        flat, fgrad = torch.empty(n, device=dev, dtype=torch.float32), torch.zeros(n, device=dev, dtype=torch.float32)
+        pv, gv, off = [], [], 0
+        for p in params:
+            k = p.numel()
+            v = flat[off:off + k].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            g = fgrad[off:off + k].view(p.shape)
+            p.grad = g
+            pv.append(v); gv.append(g)
+            off += k
+        self._flat, self._flat_grad, self._flat_views = flat, fgrad, (pv, gv)
+        self.mark_parameters_changed()
+        return flat, fgrad
+
+    def ppo_minibatch_grad(self, x1, x0, cond_feat, t, log_p_old, reward, baseline, clip_eps=0.2):
+        """One minibatch of `ppo_update` (guide_dm_trainer.py:150-172) up to `opt.step()`, entirely inside the library: denoiser
+        forward, log-prob, clipped surrogate, analytic backward.  The gradients are WRITTEN into the flat gradient vector
+        (`flatten_parameters`).  -> (loss [1], log_p_new [R])."""
+        self.flatten_parameters()
+        eng = self.train_engine(x1.shape[0])
+        logp, loss = eng.ppo_grad(x1, x0, cond_feat, t, log_p_old, reward, baseline, self._flat_views[1], clip_eps)
+        return loss, logp
+
+
+class _UnetTrainFn(torch.autograd.Function):
+    """TemporalMapUnet.forward with the hand-written CUDA backward (csrc/kernels_unet_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, dm, x, cond, t, *params):
+        eng = dm.train_engine(x.shape[0])
+        eps = eng.unet_train_forward(x.detach(), cond.detach(), t)
+        dm._train_gen += 1
+        ctx.dm, ctx.eng, ctx.gen = dm, eng, dm._train_gen
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.need_dx = x.requires_grad
+        return eps
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        if ctx.gen != ctx.dm._train_gen:
+            raise RuntimeError("cld_b200: only the most recent denoise_train() call can be back-propagated (one activation stash)")
+        grads = [torch.empty(s, device=d_eps.device, dtype=torch.float32) for s in ctx.shapes]
+        dx = ctx.eng.unet_backward(d_eps.contiguous(), grads, want_dx=ctx.need_dx)
+        return (None, dx, None, None) + tuple(grads)

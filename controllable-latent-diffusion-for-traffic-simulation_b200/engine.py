@@ -215,6 +215,79 @@ class Engine:
                 lib.cld_unet_debug_stage(self._h, -1, C.c_void_p(0), R, self._stream())
         return (eps, dbg) if debug_stage is not None else eps
 
+    # ------------------------------------------------------------------ denoiser training
+    @_on_device
+    def unet_train_forward(self, x, cond, t):
+        """eps like `unet_forward` on the fp32 kernels; the handle keeps the activations for `unet_backward`."""
+        x, cond = _f32(x, self.device), _f32(cond, self.device)
+        t = t.to(self.device, torch.int64).contiguous()
+        eps = torch.empty_like(x)
+        self._train_keep = (x, cond, t)            # the backward reads x and t again
+        self._check(lib.cld_unet_train_forward(self._h, _ptr(x), _ptr(cond), _ptr(t), _ptr(eps), x.shape[0], self._stream()),
+                    "cld_unet_train_forward")
+        return eps
+
+    @staticmethod
+    def _grad_ptrs(grads):
+        for g in grads:
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise ValueError("gradient tensors must be contiguous fp32")
+        return (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+
+    @_on_device
+    def unet_backward(self, d_eps, grads, want_dx=False):
+        """d_eps [R,T,D] -> the parameter gradients, written into `grads` (state-dict order and shapes); -> dx or None."""
+        d_eps = _f32(d_eps, self.device)
+        dx = torch.empty_like(d_eps) if want_dx else None
+        self._check(lib.cld_unet_backward(self._h, _ptr(d_eps), self._grad_ptrs(grads), len(grads), _ptr(dx), d_eps.shape[0],
+                                          self._stream()), "cld_unet_backward")
+        return dx
+
+    @_on_device
+    def ppo_head(self, eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps=0.2, want_grad=True):
+        """-> (logp_new [R], loss [1], d_eps [R,T,D] or None): DmModel.log_prob's tail + the clipped surrogate and its gradient."""
+        eps, x_t, x_tm1 = _f32(eps, self.device), _f32(x_t, self.device), _f32(x_tm1, self.device)
+        logp_old, reward = _f32(logp_old, self.device), _f32(reward, self.device)
+        t = t.to(self.device, torch.int64).contiguous()
+        R = eps.shape[0]
+        logp, loss = torch.empty(R, device=self.device), torch.empty(1, device=self.device)
+        d_eps = torch.empty_like(eps) if want_grad else None
+        self._check(lib.cld_ppo_head(self._h, _ptr(eps), _ptr(x_t), _ptr(x_tm1), _ptr(t), _ptr(logp_old), _ptr(reward), float(baseline),
+                                     float(clip_eps), _ptr(logp), _ptr(loss), _ptr(d_eps), R, self._stream()), "cld_ppo_head")
+        return logp, loss, d_eps
+
+    @_on_device
+    def mse_head(self, eps, noise, want_grad=True):
+        eps, noise = _f32(eps, self.device), _f32(noise, self.device)
+        loss = torch.empty(1, device=self.device)
+        d_eps = torch.empty_like(eps) if want_grad else None
+        self._check(lib.cld_mse_head(self._h, _ptr(eps), _ptr(noise), _ptr(loss), _ptr(d_eps), eps.shape[0], self._stream()),
+                    "cld_mse_head")
+        return loss, d_eps
+
+    @_on_device
+    def ppo_grad(self, x_t, x_tm1, cond, t, logp_old, reward, baseline, grads, clip_eps=0.2):
+        """One minibatch of ppo_update up to `opt.step()`: -> (logp_new [R], loss [1]); the gradients land in `grads`."""
+        x_t, x_tm1, cond = _f32(x_t, self.device), _f32(x_tm1, self.device), _f32(cond, self.device)
+        logp_old, reward = _f32(logp_old, self.device), _f32(reward, self.device)
+        t = t.to(self.device, torch.int64).contiguous()
+        R = x_t.shape[0]
+        logp, loss = torch.empty(R, device=self.device), torch.empty(1, device=self.device)
+        self._check(lib.cld_ppo_grad(self._h, _ptr(x_t), _ptr(x_tm1), _ptr(cond), _ptr(t), _ptr(logp_old), _ptr(reward), float(baseline),
+                                     float(clip_eps), self._grad_ptrs(grads), len(grads), _ptr(logp), _ptr(loss), R, self._stream()),
+                    "cld_ppo_grad")
+        return logp, loss
+
+    @_on_device
+    def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """torch.optim.Adam on one flat fp32 vector (in place)."""
+        for v in (params, grads, exp_avg, exp_avg_sq):
+            if v.dtype != torch.float32 or not v.is_contiguous() or v.numel() != params.numel():
+                raise ValueError("adam_step needs four contiguous fp32 vectors of equal length")
+        self._check(lib.cld_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(lr),
+                                      float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), self._stream()),
+                    "cld_adam_step")
+
     @_on_device
     def posterior_step(self, x, eps, noise, t, t_next=-1, sampler="ddpm", want_mean=False):
         x, eps, noise = _f32(x, self.device), _f32(eps, self.device), _f32(noise, self.device)

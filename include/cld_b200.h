@@ -136,6 +136,37 @@ int cld_set_schedule(CldHandle* h, const float* x_t_cof, const float* noise_cof,
 int cld_unet_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t,
                      float* eps_out, int R, void* stream);
 
+/* ---- the PPO inner loop's denoiser update ----------------------------------------------------
+ * Replaces, for `loss.backward(); opt.step()` of GuideDMLightningModule.ppo_update (src/trainers/guide_dm_trainer.py:127-183):
+ * autograd through TemporalMapUnet (src/tbsim/models/temporal.py:122-180), DmModel.log_prob (models/dm/dm_model.py:165-174),
+ * the clipped surrogate (guide_dm_trainer.py:158-168) and torch.optim.Adam (guide_dm_trainer.py:59-65).  fp32.
+ *
+ * cld_unet_train_forward: same result as cld_unet_forward on the fp32 kernels, and keeps every activation the backward needs
+ *   in the handle (about 0.85 MB per row; allocated on first use, grows with R).
+ * cld_unet_backward: d_eps [R,T,D] = d(loss)/d(eps) -> the gradients of the 148 parameter tensors, WRITTEN (not accumulated) to
+ *   grads[i] in state-dict order and layout (Conv1d [cout][cin][k], ConvTranspose1d [cin][cout][k], Linear [out][in]);
+ *   dx_out [R,T,D] = d(loss)/d(x) or NULL.  Must directly follow the cld_unet_train_forward of the same rows (no other denoiser
+ *   call on this handle in between).  No atomics: a step is bit-reproducible. */
+int cld_unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps_out, int R, void* stream);
+int cld_unet_backward(CldHandle* h, const float* d_eps, float* const* grads, int n, float* dx_out, int R, void* stream);
+
+/* PPO head: logp_new[r] = mean_{T,D} Normal(x_t_cof[t] x_t - noise_cof[t] eps, exp(.5 logvar[t])).log_prob(x_tm1),
+ * loss = -(1/R) sum_r min(ratio A, clamp(ratio, 1-clip, 1+clip) A), ratio = exp(logp_new - logp_old), A = reward - baseline;
+ * d_eps_out [R,T,D] = d(loss)/d(eps).  logp_new_out [R], loss_out [1], d_eps_out may be NULL. */
+int cld_ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
+                 const float* reward, float baseline, float clip_eps, float* logp_new_out, float* loss_out, float* d_eps_out, int R,
+                 void* stream);
+/* F.mse_loss(noise, eps) of DmModel.compute_losses (models/dm/dm_model.py:83-90) and its gradient d_eps_out (may be NULL). */
+int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps_out, int R, void* stream);
+/* forward + PPO head + backward in one call (the body of one minibatch iteration of ppo_update up to `opt.step()`). */
+int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float* cond, const int64_t* t, const float* logp_old,
+                 const float* reward, float baseline, float clip_eps, float* const* grads, int n, float* logp_new_out, float* loss_out,
+                 int R, void* stream);
+/* torch.optim.Adam step (amsgrad off; weight_decay added to the gradient) on ONE flat fp32 vector of `numel` elements; `step`
+ * counts from 1.  The caller keeps the parameters of the model as views of that vector. */
+int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* Debug/verification hook: registers a tap; the NEXT cld_unet_forward calls copy the channels-last
  * activation [R,T',C] produced by stage `stage_index` (0..16: downs.0.0, downs.0.1, downs.0.2, ...,
  * mid_block1, mid_block2, ups.0.0, ..., ups.1.2, final_conv.0) into `out` (fp32).  out == NULL

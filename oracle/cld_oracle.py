@@ -655,3 +655,55 @@ def rasterize_agents(maps, agent_hist_pos, agent_mask, raster_from_agent):
     img[:, :, 0] = 0
     img[:, :, -1] = 0
     return torch.cat((img.reshape(b, t, h, w), maps), dim=1)
+
+
+# =====================================================================================================================
+# the PPO inner loop (src/trainers/guide_dm_trainer.py:127-183)
+# =====================================================================================================================
+def log_prob(unet_sd, sched, x_t, x_tm1, cond, t):
+    """DmModel.log_prob (models/dm/dm_model.py:165-174): per-row mean over (T, D) of Normal(mean, sigma).log_prob(x_{t-1})."""
+    eps = unet_forward(unet_sd, x_t, cond, t)
+    shp = (-1, 1, 1)
+    mean = sched['x_t_cof'][t].reshape(shp) * x_t - sched['noise_cof'][t].reshape(shp) * eps        # dm_model.py:158-161
+    sigma = (0.5 * sched['posterior_log_variance_clipped'][t].reshape(shp)).exp()
+    return torch.distributions.Normal(mean, sigma).log_prob(x_tm1).mean(dim=(1, 2))
+
+
+def ppo_loss(log_p_new, log_p_old, reward, baseline, clip_eps=0.2):
+    """guide_dm_trainer.py:155-168."""
+    advantage = reward - baseline
+    ratios = torch.exp(log_p_new - log_p_old)
+    surr1 = ratios * advantage
+    surr2 = torch.clamp(ratios, 1 - clip_eps, 1 + clip_eps) * advantage
+    return -torch.min(surr1, surr2).mean()
+
+
+def ppo_grads(unet_sd, sched, x1, x0, cond, t, log_p_old, reward, baseline, clip_eps=0.2):
+    """loss.backward() of one ppo_update minibatch through autograd: -> (loss, log_p_new, {name: grad})."""
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in unet_sd.items()}
+    with torch.enable_grad():
+        lp = log_prob(sd, sched, x1, x0, cond, t)
+        loss = ppo_loss(lp, log_p_old, reward, baseline, clip_eps)
+        grads = torch.autograd.grad(loss, list(sd.values()))
+    return loss.detach(), lp.detach(), dict(zip(sd.keys(), grads))
+
+
+def mse_grads(unet_sd, sched, z0, cond, t, noise):
+    """DmModel.compute_losses (dm_model.py:83-97) with given t / noise, and its parameter gradients."""
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in unet_sd.items()}
+    shp = (-1, 1, 1)
+    z_noisy = sched['sqrt_alphas_cumprod'][t].reshape(shp) * z0 + sched['sqrt_one_minus_alphas_cumprod'][t].reshape(shp) * noise
+    with torch.enable_grad():
+        loss = torch.nn.functional.mse_loss(noise, unet_forward(sd, z_noisy, cond, t))
+        grads = torch.autograd.grad(loss, list(sd.values()))
+    return loss.detach(), dict(zip(sd.keys(), grads))
+
+
+def adam_update(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """One torch.optim.Adam step (amsgrad off) on plain tensors, in float64: -> (p', m', v')."""
+    p, g, m, v = p.double(), g.double(), m.double(), v.double()
+    g = g + weight_decay * p
+    m = betas[0] * m + (1 - betas[0]) * g
+    v = betas[1] * v + (1 - betas[1]) * g * g
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    return p - (lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps), m, v

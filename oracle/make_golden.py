@@ -427,6 +427,96 @@ def raster_golden():
     print("raster golden written")
 
 
+
+def ppo_golden():
+    """one minibatch of the REAL `ppo_update` arithmetic (guide_dm_trainer.py:150-172: the reference's own
+    DmModel.log_prob, the surrogate lines, loss.backward(), torch.optim.Adam) and of DmModel.compute_losses' MSE
+    -> tests/golden/ppo.npz: inputs, log-probs, losses, per-tensor gradient norms / sums, sampled gradient and update values."""
+    RH.install()
+    dm, vae, algo = RH.build_models(n_timesteps=16)
+    names = [k for k, _ in dm.model.named_parameters()]
+    sched = O.make_schedule(16)
+    unet_sd = {k: v.detach().clone() for k, v in dm.model.state_dict().items()}
+    torch.manual_seed(2025)
+    R = 12
+    x1, cond = torch.randn(R, 52, 4), torch.randn(R, 256)
+    # The trainer calls log_prob at t = 0 (guide_dm_trainer.py:160), where posterior_log_variance_clipped = log(1e-20), i.e.
+    # sigma = 1e-10: (x0 - mean)^2 / (2 sigma^2) turns fp32 rounding of the mean (1e-7) into log-probs of -1e5 .. -1e6, so at t = 0
+    # NO two fp32 implementations (not even the reference run twice with different batch compositions) agree.  The arithmetic is
+    # pinned at t = 1 .. 15, where sigma is 0.02 .. 0.3; the t = 0 behaviour is covered by the tests as a property (finite or not,
+    # the same formula).
+    t = torch.tensor([1, 2, 3, 4, 5, 6, 8, 10, 12, 13, 14, 15])
+    with torch.no_grad():
+        eps = dm.model(x1, {'cond_feat': cond}, t)
+        mean = dm.x_t_cof[t].reshape(-1, 1, 1) * x1 - dm.noise_cof[t].reshape(-1, 1, 1) * eps
+        sigma = (0.5 * dm.posterior_log_variance_clipped[t]).exp().reshape(-1, 1, 1)
+    x0 = mean + sigma * torch.randn(R, 52, 4)
+    with torch.no_grad():
+        lp_now = dm.log_prob(x1, x0, {'cond_feat': cond}, t)
+    # old log-probs spread around the current ones so that ratios fall inside, above and below the clip range
+    log_p_old = lp_now + torch.tensor([0.0, 0.05, -0.05, 0.15, -0.15, 0.3, -0.3, 0.5, -0.5, 0.1, -0.1, 0.0])
+    reward = torch.randn(R) * 2 - 1
+    baseline = -0.8
+    for p in dm.model.parameters():
+        p.requires_grad_(True)
+    opt = torch.optim.Adam(dm.model.parameters(), lr=1e-4, weight_decay=1e-5)
+    # ---- the reference's lines (guide_dm_trainer.py:155-172)
+    advantage = reward - baseline
+    log_p_new = dm.log_prob(x1, x0, {'cond_feat': cond}, t=t)
+    ratios = torch.exp(log_p_new - log_p_old)
+    surr1 = ratios * advantage
+    surr2 = torch.clamp(ratios, 1 - 0.2, 1 + 0.2) * advantage
+    loss = -torch.min(surr1, surr2).mean()
+    opt.zero_grad()
+    loss.backward()
+    g_ref = {k: p.grad.detach().clone() for k, p in dm.model.named_parameters()}
+    before = {k: p.detach().clone() for k, p in dm.model.named_parameters()}
+    opt.step()
+    delta = {k: (p.detach() - before[k]) for k, p in dm.model.named_parameters()}
+    # ---- oracle == reference
+    loss_or, lp_or, g_or = O.ppo_grads(unet_sd, sched, x1, x0, cond, t, log_p_old, reward, baseline, 0.2)
+    check("ppo log_p_new (oracle vs reference)", lp_or, log_p_new.detach(), 1e-6)
+    check("ppo loss", loss_or.reshape(1), loss.detach().reshape(1), 1e-6)
+    worst = 0.0
+    for k in names:
+        worst = max(worst, rel(g_or[k].double(), g_ref[k].double()))
+    print("ppo parameter gradients: worst per-tensor rel %.3e over %d tensors" % (worst, len(names)))
+    assert worst < 1e-4
+    p1, _, _ = O.adam_update(before[names[7]], g_ref[names[7]], torch.zeros_like(before[names[7]]), torch.zeros_like(before[names[7]]),
+                             1, 1e-4, weight_decay=1e-5)
+    check("adam_update restatement vs torch.optim.Adam", (p1 - before[names[7]].double()).float(), delta[names[7]], 1e-3)
+    # ---- DM training loss (compute_losses with fixed t / noise)
+    dm2, _, _ = RH.build_models(n_timesteps=16)
+    torch.manual_seed(77)
+    z0, tq, nz = torch.randn(R, 52, 4), torch.randint(0, 16, (R,)), torch.randn(R, 52, 4)
+    z_noisy = dm2.q_sample(x_0=z0, t=tq, noise=nz)
+    mse = torch.nn.functional.mse_loss(nz, dm2.model(z_noisy, {'cond_feat': cond}, tq))
+    mse.backward()
+    gm_ref = {k: p.grad.detach().clone() for k, p in dm2.model.named_parameters()}
+    mse_or, gm_or = O.mse_grads(unet_sd, sched, z0, cond, tq, nz)
+    check("mse loss (oracle vs reference)", mse_or.reshape(1), mse.detach().reshape(1), 1e-6)
+    worst = max(rel(gm_or[k].double(), gm_ref[k].double()) for k in names)
+    print("mse parameter gradients: worst per-tensor rel %.3e" % worst)
+    assert worst < 1e-4
+    # ---- golden: norms / sums of every tensor, 48 sampled entries of every tensor (fixed generator)
+    gen = torch.Generator().manual_seed(5)
+    idx = {k: torch.randint(0, g_ref[k].numel(), (48,), generator=gen) for k in names}
+    pack = lambda d, f: np.stack([f(d[k]) for k in names])
+    np.savez_compressed(
+        os.path.join(GOLD, "ppo.npz"), x1=x1.numpy(), x0=x0.numpy(), cond=cond.numpy(), t=t.numpy(), log_p_old=log_p_old.numpy(),
+        reward=reward.numpy(), baseline=baseline, clip=0.2, lr=1e-4, weight_decay=1e-5, names=np.array(names),
+        log_p_new=log_p_new.detach().numpy(), loss=float(loss), ratios=ratios.detach().numpy(),
+        grad_norm=pack(g_ref, lambda v: v.double().norm().item()), grad_sum=pack(g_ref, lambda v: v.double().sum().item()),
+        grad_idx=np.stack([idx[k].numpy() for k in names]),
+        grad_samples=np.stack([g_ref[k].reshape(-1)[idx[k]].numpy() for k in names]),
+        delta_samples=np.stack([delta[k].reshape(-1)[idx[k]].numpy() for k in names]),
+        delta_norm=pack(delta, lambda v: v.double().norm().item()),
+        z0=z0.numpy(), tq=tq.numpy(), nz=nz.numpy(), mse=float(mse),
+        mse_grad_norm=pack(gm_ref, lambda v: v.double().norm().item()),
+        mse_grad_samples=np.stack([gm_ref[k].reshape(-1)[idx[k]].numpy() for k in names]))
+    print("ppo golden written: loss %.6f, ratios %s" % (float(loss), np.round(ratios.detach().numpy(), 3)))
+
+
 if __name__ == "__main__":
     if "--only-choose" in sys.argv:
         choose_golden()
@@ -436,5 +526,7 @@ if __name__ == "__main__":
         raster_golden()
     elif "--only-context" in sys.argv:
         context_golden()
+    elif "--only-ppo" in sys.argv:
+        ppo_golden()
     else:
         main()

@@ -221,3 +221,42 @@ def test_rasterize_agents_oracle_vs_reference_golden(gold):
                              torch.from_numpy(g["agent_hist_mask"]), torch.from_numpy(g["raster_from_agent"]))
     assert torch.equal(img, torch.from_numpy(g["image_x2"]).float() / 2)
     assert int((img[:, :31] == 1).sum()) == int(g["n_ego"]) and int((img[:, :31] == -1).sum()) == int(g["n_oth"])
+
+
+# ---------------------------------------------------------------------------------------------------- f-2 (PPO update)
+def test_ppo_oracle_vs_reference_golden(gold, models_cpu):
+    """O.log_prob / O.ppo_loss / autograd gradients against the REAL reference's ppo_update arithmetic (tests/golden/ppo.npz)."""
+    g = gold("ppo")
+    dm, _, _ = models_cpu(16)
+    sd = {k: v.detach() for k, v in dm.model.state_dict().items()}
+    names = [str(n) for n in g["names"]]
+    assert names == list(sd.keys())
+    tt = lambda k: torch.tensor(g[k])
+    loss, lp, grads = O.ppo_grads(sd, O.make_schedule(16), tt("x1"), tt("x0"), tt("cond"), tt("t"), tt("log_p_old"), tt("reward"),
+                                  float(g["baseline"]), float(g["clip"]))
+    assert ((lp - tt("log_p_new")).norm() / tt("log_p_new").norm()).item() < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    for i, k in enumerate(names):
+        want = float(g["grad_norm"][i])
+        assert abs(grads[k].double().norm().item() - want) <= 1e-4 * want + 1e-12, k
+        samp = grads[k].reshape(-1)[torch.tensor(g["grad_idx"][i])]
+        assert (samp - torch.tensor(g["grad_samples"][i])).abs().max().item() <= 1e-4 * want, k
+    # the clipped surrogate: rows outside the clip range on the side the minimum cuts off carry no gradient
+    r, adv = tt("ratios"), tt("reward") - float(g["baseline"])
+    cut = ((r > 1.2) & (adv > 0)) | ((r < 0.8) & (adv < 0))
+    assert cut.any() and (~cut).any()
+    # Adam restatement on one tensor against the reference's sampled update
+    k = names[7]
+    p = sd[k]
+    p1, _, _ = O.adam_update(p, grads[k], torch.zeros_like(p), torch.zeros_like(p), 1, float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    idx = torch.tensor(g["grad_idx"][7])
+    got = (p1 - p.double()).reshape(-1)[idx]
+    big = torch.tensor(g["grad_samples"][7]).abs() > 1e-6
+    assert (got[big] - torch.tensor(g["delta_samples"][7]).double()[big]).abs().max().item() < 2e-2 * float(g["lr"])
+
+
+def test_warmup_cosine_schedule():
+    """lr factor of configure_optimizers (guide_dm_trainer.py:67-75)."""
+    from cld_b200.trainer import warmup_cosine
+    assert warmup_cosine(0, 30) == 0.0 and abs(warmup_cosine(5, 30) - 0.5) < 1e-12 and abs(warmup_cosine(10, 30) - 1.0) < 1e-12
+    assert abs(warmup_cosine(20, 30) - 0.5) < 1e-12 and warmup_cosine(30, 30) < 1e-12
