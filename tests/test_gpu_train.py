@@ -211,15 +211,18 @@ def test_adam_kernel_vs_torch(dm16):
         ref.grad = gr.clone()
         opt.step()
         eng.adam_step(p, gr, m, v, step, 3e-4, (0.9, 0.999), 1e-8, 1e-2)
-        assert (p - ref.detach()).abs().max().item() < 2e-7
+        assert (p - ref.detach()).abs().max().item() < 1e-6          # a few ulp of |p| <= 4
     st = opt.state[ref]
     assert rel(m, st['exp_avg']) < 1e-6 and rel(v, st['exp_avg_sq']) < 1e-6
 
 
-def test_trainer_ppo_update_runs_and_modes_agree(models_cpu):
+def test_trainer_ppo_update_loop(models_cpu):
     """GuideDMTrainer (mirror of guide_dm_trainer.py:85-183): sampling steps fill the device replay buffer, ppo_update runs its
-    minibatches; the fused mode and the autograd mode produce the same losses and parameters.  PPO evaluates log_prob at t = 0
-    where sigma = 1e-10 (see oracle/make_golden.py:ppo_golden), so only agreement between the two modes is asserted on values."""
+    minibatches in both modes.  PPO evaluates log_prob at t = 0 where sigma = 1e-10 (oracle/make_golden.py:ppo_golden): an fp32
+    rounding difference of the posterior mean (fused multiply-add or not) moves log_p_new by 1e5, so ratios are 0, 1 or inf
+    depending on the last bit -- in the reference as well.  Values of the two modes are therefore NOT comparable here (their
+    agreement is asserted at well-conditioned steps in test_reference_lines_through_autograd_and_fused_step_agree); this test
+    checks the loop itself: buffer contents, update cadence, finite parameters, engine refresh."""
     from cld_b200 import default_algo_config, make_scenes
     from cld_b200.dm_model import DmModel
     from cld_b200.trainer import GuideDMTrainer
@@ -242,8 +245,12 @@ def test_trainer_ppo_update_runs_and_modes_agree(models_cpu):
         assert 'train/ppo_loss' in tr.log and tr.steps_since_update == 0
         tr.on_epoch_end()
         results.append((tr.log['train/ppo_loss'], torch.cat([p.detach().reshape(-1) for p in dm.model.parameters()]).clone()))
-    (l_f, p_f), (l_a, p_a) = results
-    assert np.isfinite(l_f) == np.isfinite(l_a)
-    if np.isfinite(l_f):
-        assert abs(l_f - l_a) <= 1e-3 * max(1.0, abs(l_a))
-    assert torch.isfinite(p_f).all() == torch.isfinite(p_a).all()
+        p_now = results[-1][1]
+        assert torch.isfinite(p_now).all()
+        torch.manual_seed(0)
+        p_init = torch.cat([p.detach().reshape(-1) for p in DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=16).model.parameters()])
+        moved = (p_now.cpu() - p_init).abs().max().item()
+        assert 0 < moved <= 4 * 3.2e-4                     # 2 epochs x 2 minibatches; an Adam step moves an entry by <= lr (1 - b1) / sqrt(1 - b2)
+        # the sampler picks up the updated weights (engine re-packed from the changed parameters)
+        out2 = dm(batch, aux, algo, use_device_rng=True, seed=77)
+        assert torch.isfinite(out2['pred_traj']).all()
