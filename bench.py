@@ -261,6 +261,60 @@ def context_encoder_rate(dev, agents=1024, iters=5, warmup=3):
     return out
 
 
+def ppo_update_rate(dev, skip_cpu, rows=128, iters=20, warmup=3):
+    """SURVEY.md sec. 8 f-2 beside the cfg4 line: one minibatch of ppo_update (guide_dm_trainer.py:150-172: denoiser forward,
+    log-prob, clipped surrogate, backward, Adam, weight re-pack) on `rows` replay rows (config.yaml:168), inputs resident in HBM;
+    CPU: the oracle's autograd restatement of the same minibatch on all host threads (1 warm-up + 1 timed)."""
+    import torch
+    from cld_b200 import default_algo_config
+    from cld_b200.dm_model import DmModel
+    from cld_b200.trainer import FusedAdam
+    torch.manual_seed(0)
+    dm = DmModel(default_algo_config(), {"image": (34, 224, 224)}, n_timesteps=16).to(dev)
+    for p in dm.model.parameters():
+        p.requires_grad_(True)
+    opt = FusedAdam(dm, lr=1e-4, weight_decay=1e-5)
+    g = torch.Generator(device=dev).manual_seed(5)
+    rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)    # noqa: E731
+    x1, x0, cond, lp_old, reward = rn(rows, 52, 4), rn(rows, 52, 4), rn(rows, 256), rn(rows), rn(rows)
+    t = torch.full((rows,), 3, dtype=torch.long, device=dev)
+
+    def step():
+        loss, _ = dm.ppo_minibatch_grad(x1, x0, cond, t, lp_old, reward, 0.0, 0.2)
+        opt.step()
+        return loss
+    for _ in range(warmup):
+        step()
+    eng = dm.train_engine(rows)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out = {"rows": rows, "ms_per_minibatch_update": ms, "updates_per_s": 1e3 / ms, "iters": iters, "dtype": "fp32 (CUDA cores)",
+           "gpu_launches_per_update": (eng.launch_count() - l0) // iters,
+           "algorithmic_gflop_per_update": 3 * 119.23e-3 * rows, "achieved_tflops": 3 * 119.23e6 * rows / (ms * 1e-3) / 1e12,
+           "ppo_update_s": "%.1f s for the reference's 10 epochs x 300 minibatches" % (3000 * ms * 1e-3)}
+    if not skip_cpu:
+        import time
+        import cld_oracle as O
+        sd = {k: v.detach().cpu() for k, v in dm.model.state_dict().items()}
+        args = [v.cpu() for v in (x1, x0, cond, t, lp_old, reward)]
+        sched = O.make_schedule(16)
+        torch.set_num_threads(os.cpu_count())
+        O.ppo_grads(sd, sched, *args, 0.0, 0.2)
+        t0 = time.perf_counter()
+        O.ppo_grads(sd, sched, *args, 0.0, 0.2)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"ms_per_minibatch_grad": dt * 1e3, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "oracle autograd of the same %d-row minibatch (forward + backward, no optimizer step)" % rows}
+    return out
+
+
 def hbm_kernel_rooflines(eng, R, T, A, scene, dev, iters=20):
     """K3 (posterior step) and K6 (indicators) alone at the rows of one launch: algorithmic bytes / CUDA-event time."""
     import torch
@@ -532,6 +586,9 @@ def main():
             del out
             torch.cuda.empty_cache()
             ctx = context_encoder_rate(dev)
+        ppo = None
+        if world == 1 and a.config == "cfg4":
+            ppo = ppo_update_rate(dev, a.skip_cpu)
         line = {
             "metric": "guided scenarios/sec (50-step DDIM)" if a.config in ("cfg1", "cfg2") else "guided scenarios/sec (%s)" % a.config,
             "value": value, "unit": "scenarios/s", "n_gpus": world,
@@ -543,6 +600,8 @@ def main():
                                                          "(cld_b200.staging.HostStager); results read back to pinned host memory every call"},
             "gpu_launches": launches, "clocks": clocks, "context_encoder": ctx, "lanes": n_lanes, "single_lane": single,
         }
+        if ppo is not None:
+            line["ppo_update"] = ppo
         if world > 1:
             line["all_gather"] = {"ms": gather_ms, "bytes_per_rank": R * (T * 7 + 1) * 4, "share_of_step": gather_ms / ms}
         print(json.dumps(line))

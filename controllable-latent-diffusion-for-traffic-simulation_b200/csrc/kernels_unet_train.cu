@@ -30,29 +30,33 @@ struct TGemm {
   int Tj; int R; int accum;
 };
 
-constexpr int GBM = 128, GBN = 64, GBK = 16;
+constexpr int GBN = 64, GBK = 16;
 
-template <bool TRANSB>
+// BM = 128 | 64 | 32 GEMM rows per CTA (256 threads, thread tile BM/16 x 4): a 128-row minibatch gives M = 1 664 .. 6 656 rows, i.e.
+// 13 .. 52 tiles of 128 -- the smaller tiles are what fills 148 SMs
+template <bool TRANSB, int BM>
 __global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
-  __shared__ float As[GBK][GBM + 4];
+  constexpr int RPT = BM / 16;                       // rows per thread
+  constexpr int ALOADS = (BM * 4 + 255) / 256;       // float4 loads of the A tile per thread
+  __shared__ __align__(16) float As[GBK][BM + 4];
   __shared__ __align__(16) float Bs[GBK][GBN + 4];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * GBN;
   const int M = a.R * a.Tj;
   const int cin = a.c0 + a.c1;
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[8][4];
+  float acc[RPT][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RPT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  int a_row[2], a_q[2], a_r[2], a_j[2];
+  int a_row[ALOADS], a_q[ALOADS], a_r[ALOADS], a_j[ALOADS];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < ALOADS; ++i) {
     const int idx = tid + i * 256;
     a_row[i] = idx >> 2; a_q[i] = idx & 3;
     const int m = m0 + a_row[i];
-    a_r[i] = (m < M) ? m / a.Tj : -1;
+    a_r[i] = (m < M && a_row[i] < BM) ? m / a.Tj : -1;
     a_j[i] = (m < M) ? m % a.Tj : 0;
   }
   const int kchunks = (cin + GBK - 1) / GBK;
@@ -61,17 +65,19 @@ __global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
     for (int kc = 0; kc < kchunks; ++kc) {
       const int ci0 = kc * GBK;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c = ci0 + a_q[i] * 4;
-        const int ti = a_j[i] * a.istride + a.ioff[tap];
-        if (a_r[i] >= 0 && c < cin && ti >= 0 && ti < a.Tin) {
-          const float* p = (c < a.c0) ? a.in0 + ((size_t)a_r[i] * a.Tin + ti) * a.c0 + c
-                                      : a.in1 + ((size_t)a_r[i] * a.Tin + ti) * a.c1 + (c - a.c0);
-          v = *reinterpret_cast<const float4*>(p);
+      for (int i = 0; i < ALOADS; ++i) {
+        if (a_row[i] < BM) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int c = ci0 + a_q[i] * 4;
+          const int ti = a_j[i] * a.istride + a.ioff[tap];
+          if (a_r[i] >= 0 && c < cin && ti >= 0 && ti < a.Tin) {
+            const float* p = (c < a.c0) ? a.in0 + ((size_t)a_r[i] * a.Tin + ti) * a.c0 + c
+                                        : a.in1 + ((size_t)a_r[i] * a.Tin + ti) * a.c1 + (c - a.c0);
+            v = *reinterpret_cast<const float4*>(p);
+          }
+          As[a_q[i] * 4 + 0][a_row[i]] = v.x; As[a_q[i] * 4 + 1][a_row[i]] = v.y;
+          As[a_q[i] * 4 + 2][a_row[i]] = v.z; As[a_q[i] * 4 + 3][a_row[i]] = v.w;
         }
-        As[a_q[i] * 4 + 0][a_row[i]] = v.x; As[a_q[i] * 4 + 1][a_row[i]] = v.y;
-        As[a_q[i] * 4 + 2][a_row[i]] = v.z; As[a_q[i] * 4 + 3][a_row[i]] = v.w;
       }
       if (!TRANSB) {
         const int b_k = tid >> 4, b_n = (tid & 15) * 4;
@@ -89,13 +95,23 @@ __global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < GBK; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+        float av[RPT];
+        if (RPT == 8) {
+          const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+          const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+          av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+          av[RPT - 4] = a1.x; av[RPT - 3] = a1.y; av[RPT - 2] = a1.z; av[RPT - 1] = a1.w;
+        } else if (RPT == 4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          av[0] = a0.x; av[1] = a0.y; av[RPT - 2] = a0.z; av[RPT - 1] = a0.w;
+        } else {
+          const float2 a0 = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+          av[0] = a0.x; av[RPT - 1] = a0.y;
+        }
         const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RPT; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
@@ -107,8 +123,8 @@ __global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + ty * 8 + i;
+    for (int i = 0; i < RPT; ++i) {
+      const int m = m0 + ty * RPT + i;
       if (m < M) {
         const int r = m / a.Tj, j = m % a.Tj;
         float4* op = reinterpret_cast<float4*>(a.out + ((size_t)r * a.Tout + j * a.ostride + a.ooff) * a.cout + n);
@@ -120,6 +136,17 @@ __global__ void __launch_bounds__(256) tgemm_kernel(TGemm a) {
   }
 }
 
+template <bool TRANSB>
+static int tgemm_launch(CldHandle* h, const TGemm& a, int n_out, cudaStream_t s) {
+  const int M = a.R * a.Tj, ny = (n_out + GBN - 1) / GBN;
+  const int want = 2 * h->num_sms;
+  if (((M + 127) / 128) * ny >= want) tgemm_kernel<TRANSB, 128><<<dim3((M + 127) / 128, ny), 256, 0, s>>>(a);
+  else if (((M + 63) / 64) * ny >= want) tgemm_kernel<TRANSB, 64><<<dim3((M + 63) / 64, ny), 256, 0, s>>>(a);
+  else tgemm_kernel<TRANSB, 32><<<dim3((M + 31) / 32, ny), 256, 0, s>>>(a);
+  CLD_LAUNCH_OK(h, TRANSB ? "tgemm_kernel<dgrad>" : "tgemm_kernel<fwd>");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dW[tap][ci][co] = sum_m in[m @ tap][ci] * dOut[m][co], M split over grid.z, partials reduced in fixed order
 // ------------------------------------------------------------------------------------------------
@@ -129,6 +156,7 @@ struct TWgrad {
   int ntaps; int ioff[5]; int istride, ostride, ooff;
   int Tj; int R;
   float* part;                  // [splits][ntaps][cin][cout]
+  float* bias_part;             // [splits][cout] column sums of dOut (the bias gradient), or nullptr
   int splits, chunk;            // chunk = rows of M per split (multiple of 16)
 };
 
@@ -148,6 +176,8 @@ __global__ void __launch_bounds__(256) twgrad_kernel(TWgrad a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool do_bias = a.bias_part && blockIdx.x == 0 && tap == 0;     // one CTA per (output-channel tile, split) also sums dOut
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int mb = m_lo; mb < m_hi; mb += 16) {
     const int m = mb + l_row;
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
@@ -165,6 +195,7 @@ __global__ void __launch_bounds__(256) twgrad_kernel(TWgrad a) {
     }
     *reinterpret_cast<float4*>(&As[l_row][l_c]) = va;
     *reinterpret_cast<float4*>(&Bs[l_row][l_c]) = vb;
+    if (do_bias) { bs.x += vb.x; bs.y += vb.y; bs.z += vb.z; bs.w += vb.w; }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -188,6 +219,16 @@ __global__ void __launch_bounds__(256) twgrad_kernel(TWgrad a) {
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
   }
+  if (do_bias) {                                       // 16 row-threads per column quad, summed in a fixed order
+    *reinterpret_cast<float4*>(&Bs[l_row][l_c]) = bs;
+    __syncthreads();
+    if (tid < 64 && co0 + tid < a.cout) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += Bs[r][tid];
+      a.bias_part[(size_t)split * a.cout + co0 + tid] = t;
+    }
+  }
 }
 
 // sum the split partials (fixed order) and write the gradient in the reference's parameter layout:
@@ -195,10 +236,19 @@ __global__ void __launch_bounds__(256) twgrad_kernel(TWgrad a) {
 // The columns [co_off, co_off + co_n) of the packed matrix are written (a slice for the concatenated time-bias projection).
 struct TKs { int k[5]; };
 __global__ void __launch_bounds__(256) twreduce_kernel(const float* __restrict__ part, int splits, int ntaps, int cin, int cout,
-                                                       int co_off, int co_n, float* __restrict__ dst, int K, TKs ks, int transposed) {
+                                                       int co_off, int co_n, float* __restrict__ dst, int K, TKs ks, int transposed,
+                                                       const float* __restrict__ bias_part, float* __restrict__ bias_dst) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int total = ntaps * cin * co_n;
-  if (idx >= total) return;
+  if (idx >= total) {
+    const int c = idx - total;
+    if (bias_dst && c < co_n) {
+      float s = 0.f;
+      for (int i = 0; i < splits; ++i) s += bias_part[(size_t)i * cout + co_off + c];
+      bias_dst[c] = s;
+    }
+    return;
+  }
   const int co = idx % co_n, ci = (idx / co_n) % cin, tap = idx / (co_n * cin);
   const size_t stride = (size_t)ntaps * cin * cout;
   const float* p = part + ((size_t)tap * cin + ci) * cout + co_off + co;
@@ -225,12 +275,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
   for (; m < M; m += st) s0 += src[(size_t)m * C + c];
   partial[(size_t)blockIdx.x * C + c] = (s0 + s1) + (s2 + s3);
 }
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dst) {
+// columns [0, split) go to dst0, [split, C) to dst1 (two gradient tensors from one pass)
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dst0,
+                                                           int split, float* __restrict__ dst1) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
   for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * C + c];
-  dst[c] = s;
+  if (c < split) dst0[c] = s; else dst1[c - split] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,11 +313,11 @@ __device__ __forceinline__ float mish_grad(float x) {
 //   x = conv output [R,T,C];  xh = (x - mean) rstd;  u = xh g + b;  y = mish(u) (+ ...)
 //   dU = dY mish'(u);  dg[c] += dU xh;  db[c] += dU;  dxh = dU g;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh))
 // One CTA per row, warp = group.  cpg divides 32, so a lane always meets the same channel: per-channel sums stay in registers.
-// Per-row partials (dg, db, and sum_t dY = d(time bias)) are written; colsum reduces them over the rows.
+// Per-row partials (rp [R][dg | db], and sum_t dY = d(time bias)) are written; one colsum reduces them over the rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ dy,
-                                                          float* __restrict__ dx, float* __restrict__ rp_g, float* __restrict__ rp_b,
+                                                          float* __restrict__ dx, float* __restrict__ rp,
                                                           float* __restrict__ dtb, int tb_stride, int T, int C) {
   const int r = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpg = C >> 3, n = T * cpg;
@@ -305,7 +357,7 @@ __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restric
     sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
   }
   if (lane < cpg) {
-    rp_g[(size_t)r * C + c] = sg; rp_b[(size_t)r * C + c] = sb;
+    rp[(size_t)r * 2 * C + c] = sg; rp[(size_t)r * 2 * C + C + c] = sb;      // [R][gamma | beta]
     if (dtb) dtb[(size_t)r * tb_stride + c] = sy;
   }
 #pragma unroll
@@ -473,9 +525,10 @@ struct TrainState {
   float *p0 = nullptr, *p1 = nullptr, *q0 = nullptr, *q1 = nullptr, *fA = nullptr, *fB = nullptr, *tmpR = nullptr;
   float *gA = nullptr, *gB = nullptr, *gX = nullptr, *gY = nullptr, *gcat8 = nullptr, *gcat10 = nullptr;
   float *dtbias = nullptr, *dtcm = nullptr, *emb = nullptr, *hid = nullptr, *dpre1 = nullptr, *dpre2 = nullptr;
-  float *rp_g = nullptr, *rp_b = nullptr, *loss_row = nullptr, *deps = nullptr;
+  float *rp = nullptr, *loss_row = nullptr, *deps = nullptr;
   float* part = nullptr;  size_t part_floats = 0;
   float* colpart = nullptr;
+  float* bias_part = nullptr;      // [MAX_SPLITS][256] split partials of a convolution's bias gradient
   float* tb_bgrad = nullptr;       // [tb_total] bias gradient of the concatenated time / cond projection
   float* sched_dev = nullptr;
   const float* x = nullptr;
@@ -492,6 +545,7 @@ void train_destroy(CldHandle* h) {
   if (st->arena) cudaFree(st->arena);
   if (st->part) cudaFree(st->part);
   if (st->colpart) cudaFree(st->colpart);
+  if (st->bias_part) cudaFree(st->bias_part);
   if (st->sched_dev) cudaFree(st->sched_dev);
   delete st;
   h->train = nullptr;
@@ -502,6 +556,7 @@ void train_invalidate(CldHandle* h) {
 }
 
 constexpr int COLSUM_BLOCKS = 128;
+constexpr int MAX_SPLITS = 1024;
 constexpr size_t PART_FLOATS = (size_t)6 << 20;
 
 static int train_prepare(CldHandle* h, int R) {
@@ -514,6 +569,7 @@ static int train_prepare(CldHandle* h, int R) {
     st->part_floats = PART_FLOATS;
     CLD_CUDA_OK(h, cudaMalloc((void**)&st->colpart, (size_t)(COLSUM_BLOCKS + 1) * CLD_TB_TOTAL_MAX * sizeof(float)));
     st->tb_bgrad = st->colpart + (size_t)COLSUM_BLOCKS * CLD_TB_TOTAL_MAX;
+    CLD_CUDA_OK(h, cudaMalloc((void**)&st->bias_part, (size_t)MAX_SPLITS * 256 * sizeof(float)));
     CLD_CUDA_OK(h, cudaMalloc((void**)&st->sched_dev, (size_t)3 * c.n_timesteps * sizeof(float)));
   }
   if (R <= st->cap_rows) return 0;
@@ -537,7 +593,7 @@ static int train_prepare(CldHandle* h, int R) {
   st->p0 = take(E); st->p1 = take(E); st->q0 = take(E); st->q1 = take(E); st->fA = take(E); st->fB = take(E); st->tmpR = take(E);
   st->gA = take(E); st->gB = take(E); st->gX = take(E); st->gY = take(E); st->gcat8 = take(2 * E); st->gcat10 = take(2 * E);
   st->dtbias = take(tb_total); st->dtcm = take(64); st->emb = take(td); st->hid = take(4 * td); st->dpre1 = take(4 * td);
-  st->dpre2 = take(td); st->rp_g = take(256); st->rp_b = take(256); st->loss_row = take(1);
+  st->dpre2 = take(td); st->rp = take(512); st->loss_row = take(1);
   st->deps = take((size_t)c.horizon * c.latent_dim);
   st->cap_rows = R;
   st->fwd_valid = false;
@@ -556,10 +612,7 @@ static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, cons
   for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)(i < w.ntaps ? i : 0) * w.cin * w.cout; a.ioff[i] = i < w.ntaps ? ioff[i] : 0; }
   a.ldw = w.cout; a.bias = bias; a.out = out; a.Tout = Tout; a.cout = w.cout; a.ntaps = w.ntaps;
   a.istride = istride; a.ostride = ostride; a.ooff = ooff; a.Tj = Tj; a.R = R; a.accum = 0;
-  dim3 grid((R * Tj + GBM - 1) / GBM, (w.cout + GBN - 1) / GBN);
-  tgemm_kernel<false><<<grid, 256, 0, s>>>(a);
-  CLD_LAUNCH_OK(h, "tgemm_kernel<fwd>");
-  return 0;
+  return tgemm_launch<false>(h, a, w.cout, s);
 }
 
 // data gradient: out[r, j*ostride+ooff, 0:n_out) (+)= sum_i dout[r, j*istride+ioff[i], :] @ W[taps[i]]^T
@@ -570,16 +623,13 @@ static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, 
   for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)taps[i < ntaps ? i : 0] * w.cin * w.cout; a.ioff[i] = i < ntaps ? ioff[i] : 0; }
   a.ldw = w.cout; a.bias = nullptr; a.out = out; a.Tout = Tout; a.cout = n_out; a.ntaps = ntaps;
   a.istride = istride; a.ostride = ostride; a.ooff = ooff; a.Tj = Tj; a.R = R; a.accum = accum;
-  dim3 grid((R * Tj + GBM - 1) / GBM, (n_out + GBN - 1) / GBN);
-  tgemm_kernel<true><<<grid, 256, 0, s>>>(a);
-  CLD_LAUNCH_OK(h, "tgemm_kernel<dgrad>");
-  return 0;
+  return tgemm_launch<true>(h, a, n_out, s);
 }
 
 // weight gradient of one packed matrix [ntaps][cin][cout] -> partials in st->part; `splits_out` for the reduce
 static int conv_wgrad(CldHandle* h, int cin_total, int cout, int ntaps, const int* ioff, const float* in0, int c0, const float* in1,
                       int c1, int Tin, const float* dout, int Tdout, int Tj, int istride, int ostride, int ooff, int R,
-                      int* splits_out, cudaStream_t s) {
+                      int* splits_out, cudaStream_t s, bool with_bias = false) {
   TrainState* st = ts_of(h);
   TWgrad a;
   a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin; a.dout = dout; a.Tout = Tdout; a.cout = cout; a.ntaps = ntaps;
@@ -592,7 +642,10 @@ static int conv_wgrad(CldHandle* h, int cin_total, int cout, int ntaps, const in
   if (splits > max_by_m) splits = max_by_m;
   const size_t wsz = (size_t)ntaps * cin_total * cout;
   if ((size_t)splits * wsz > st->part_floats) splits = (int)(st->part_floats / wsz);
+  if (splits > MAX_SPLITS) splits = MAX_SPLITS;
   if (splits < 1) return fail(h, CLD_ERR_UNSUPPORTED, "weight-gradient scratch too small");
+  if (with_bias && cout > 256) return fail(h, CLD_ERR_UNSUPPORTED, "fused bias gradient needs cout <= 256");
+  a.bias_part = with_bias ? st->bias_part : nullptr;
   int chunk = (M + splits - 1) / splits;
   chunk = (chunk + 15) / 16 * 16;
   splits = (M + chunk - 1) / chunk;
@@ -605,23 +658,24 @@ static int conv_wgrad(CldHandle* h, int cin_total, int cout, int ntaps, const in
 }
 
 static int wreduce(CldHandle* h, int splits, int ntaps, int cin, int cout, int co_off, int co_n, float* dst, int K, const int* ks,
-                   int transposed, cudaStream_t s) {
+                   int transposed, cudaStream_t s, float* bias_dst = nullptr) {
   TKs k;
   for (int i = 0; i < 5; ++i) k.k[i] = i < ntaps ? ks[i] : 0;
-  const int total = ntaps * cin * co_n;
-  twreduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(ts_of(h)->part, splits, ntaps, cin, cout, co_off, co_n, dst, K, k, transposed);
+  const int total = ntaps * cin * co_n + (bias_dst ? co_n : 0);
+  twreduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(ts_of(h)->part, splits, ntaps, cin, cout, co_off, co_n, dst, K, k, transposed,
+                                                      ts_of(h)->bias_part, bias_dst);
   CLD_LAUNCH_OK(h, "twreduce_kernel");
   return 0;
 }
 
-static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cudaStream_t s) {
+static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cudaStream_t s, int split = -1, float* dst1 = nullptr) {
   TrainState* st = ts_of(h);
   int nblk = (M + 31) / 32;
   if (nblk > COLSUM_BLOCKS) nblk = COLSUM_BLOCKS;
   dim3 grid(nblk, (C + 255) / 256);
   colsum_kernel<<<grid, 256, 0, s>>>(src, M, C, st->colpart);
   CLD_LAUNCH_OK(h, "colsum_kernel");
-  colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(st->colpart, nblk, C, dst);
+  colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(st->colpart, nblk, C, dst, split < 0 ? C : split, dst1);
   CLD_LAUNCH_OK(h, "colsum_final_kernel");
   return 0;
 }
@@ -694,11 +748,9 @@ int unet_train_forward(CldHandle* h, const float* x, const float* cond, const in
 static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float* dA, float* dgamma, float* dbeta, float* dtb,
                   int T, int C, int R, cudaStream_t s) {
   TrainState* st = ts_of(h);
-  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, st->rp_g, st->rp_b, dtb, h->unet.tb_total, T, C);
+  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, st->rp, dtb, h->unet.tb_total, T, C);
   CLD_LAUNCH_OK(h, "gn_mish_bwd_kernel");
-  int rc;
-  if ((rc = colsum(h, st->rp_g, R, C, dgamma, s))) return rc;
-  return colsum(h, st->rp_b, R, C, dbeta, s);
+  return colsum(h, st->rp, R, 2 * C, dgamma, s, C, dbeta);
 }
 
 static const int kK5[5] = {0, 1, 2, 3, 4}, kK1[5] = {0, 0, 0, 0, 0}, kK3[5] = {0, 1, 2, 0, 0};
@@ -709,10 +761,10 @@ static const int kNeg5[5] = {2, 1, 0, -1, -2};
 static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, const float* in0, int c0, const float* in1, int c1, int T,
                             const float* dout, float* dw, float* db, int R, cudaStream_t s) {
   int rc, splits;
-  if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s)))
+  if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s,
+                       true)))
     return rc;
-  if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s))) return rc;
-  return colsum(h, dout, R * T, cout, db, s);
+  return wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s, db);
 }
 
 // backward of one residual block.  dOUT [R,T,cout] -> dIN [R,T,cin_total] (written), parameter gradients -> grads[...]
@@ -746,9 +798,8 @@ static int down_bwd(CldHandle* h, const ConvW& w, const float* in, int T, const 
                     cudaStream_t s) {
   const int C = w.cout, Th = T / 2;
   int rc, splits;
-  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s))) return rc;
-  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s))) return rc;
-  if ((rc = colsum(h, dout, R * Th, C, db, s))) return rc;
+  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s, true))) return rc;
+  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s, db))) return rc;
   // forward: out[j] = sum_tap in[2j + tap - 1] W[tap].  even ti = 2m: tap 1, j = m;  odd ti = 2m + 1: tap 0 with j = m + 1, tap 2 with j = m
   const int te[5] = {1, 0, 0, 0, 0}, oe[5] = {0, 0, 0, 0, 0};
   const int to[5] = {0, 2, 0, 0, 0}, oo[5] = {1, 0, 0, 0, 0};
