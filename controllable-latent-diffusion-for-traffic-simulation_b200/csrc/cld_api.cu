@@ -66,6 +66,17 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, float* __restric
   dst[((size_t)tap * cin + ci) * ld + off + co] = v;
 }
 
+// dst[(tap*cout + co)*cin + ci] = src[co, ci, k(tap)]: the [N][K] (K contiguous) weight planes of the tensor-core training forward
+__global__ void pack_conv_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int K, int ntaps,
+                                   int k0, int k1, int k2, int k3, int k4) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = ntaps * cin * cout;
+  if (idx >= total) return;
+  int ci = idx % cin, co = (idx / cin) % cout, tap = idx / (cout * cin);
+  int ks[5] = {k0, k1, k2, k3, k4};
+  dst[idx] = src[((size_t)co * cin + ci) * K + ks[tap]];
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
@@ -94,6 +105,11 @@ static int pack_conv(CldHandle* h, ConvW* w, const float* src, const float* bias
   pack_conv_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->w, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4],
                                                        cout, 0, transposed);
   CLD_LAUNCH_OK(h, "pack_conv_kernel");
+  if (!transposed) {
+    if ((rc = dev_alloc(h, &w->wt, (size_t)ntaps * cin * cout))) return rc;
+    pack_conv_t_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->wt, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4]);
+    CLD_LAUNCH_OK(h, "pack_conv_t_kernel");
+  }
   if (bias) return copy_vec(h, &w->b, bias, cout, s);
   return 0;
 }
@@ -192,6 +208,7 @@ void cld_destroy(CldHandle* h) {
   tc_destroy(h);
   lstm_tc_destroy(h);
   train_destroy(h);
+  train_tc_destroy(h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_tvec) cudaEventDestroy(h->ev_tvec);
@@ -443,8 +460,14 @@ int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float
   return unet_train_backward(h, d_eps, grads, n, nullptr, R, s);
 }
 
-int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+int cld_train_set_precision(CldHandle* h, int tf32) {
+  if (!h) return CLD_ERR_ARG;
+  h->train_tf32 = tf32 != 0;
+  return CLD_OK;
+}
+
+int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int step, void* stream) {
   if (!h || !params || !grads || !exp_avg || !exp_avg_sq) return fail(h, CLD_ERR_ARG, "null argument");
   if (numel < 1 || step < 1) return fail(h, CLD_ERR_ARG, "numel and step must be positive");
   return adam_step(h, params, grads, exp_avg, exp_avg_sq, (size_t)numel, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);

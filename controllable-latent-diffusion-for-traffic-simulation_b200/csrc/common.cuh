@@ -20,6 +20,7 @@ namespace cld {
 // ------------------------------------------------------------------------------------------------
 struct ConvW {
   float* w = nullptr;   // fp32 [ntaps][cin][cout]
+  float* wt = nullptr;  // fp32 [ntaps][cout][cin]: B operand (K-major) of the tensor-core training forward (train_tc.cu)
   float* b = nullptr;   // [cout]
   int cin = 0, cout = 0, ntaps = 0;
 };
@@ -132,6 +133,8 @@ struct CldHandle {
   bool use_lstm_tc = false;
   // denoiser training state (opaque, owned by kernels_unet_train.cu): activation stash + gradient scratch, allocated on first use
   void* train = nullptr;
+  void* train_tc = nullptr;        // tensor-map cache of the tf32 tensor-core convolutions (train_tc.cu)
+  bool train_tf32 = false;         // cld_train_set_precision: stride-1 convolutions of the training step on the tensor pipe
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)
   bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false, env_map_exhaustive = false;
   int env_lstm_pf = 3;
@@ -182,9 +185,17 @@ int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, i
 int ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
              const float* reward, float baseline, float clip, float* logp_new, float* loss_out, float* d_eps, int R, cudaStream_t s);
 int mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps, int R, cudaStream_t s);
-int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, double wd,
               int step, cudaStream_t s);
 float* train_deps_buffer(CldHandle* h);
+// ---- train_tc.cu
+bool tfconv_supported(int c0, int c1, int N, int Tp);
+int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* w, int planes, int ntaps,
+                  const int* wtap, const int* toff, const float* bias, float* out, int N, int accum, int R, cudaStream_t s);
+bool tfwgrad_supported(int c0, int c1, int cout, int Tp, int R);
+int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* dout, int cout, int ntaps,
+                   const int* toff, float* part, size_t part_floats, int max_splits, int R, int* splits_out, cudaStream_t s);
+void train_tc_destroy(CldHandle* h);
 void train_destroy(CldHandle* h);
 void train_invalidate(CldHandle* h);     // the time / cond bias buffers the backward reads were overwritten
 // ---- kernels_step.cu

@@ -499,17 +499,17 @@ __global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__
 
 // torch.optim.Adam (no amsgrad; weight_decay added to the gradient), one flat parameter vector
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                                                   float bc1, float bc2_sqrt) {
+                                                   float* __restrict__ v, size_t n, float step_size, float w1, float b2, float w2, float eps,
+                                                   float wd, float bc2_sqrt) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float pi = p[i];
   const float gi = fmaf(wd, pi, g[i]);
-  const float mi = m[i] + (gi - m[i]) * (1.f - b1);               // torch: exp_avg.lerp_(grad, 1 - beta1)
-  const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float mi = m[i] + (gi - m[i]) * w1;                       // torch: exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = fmaf(b2, v[i], w2 * gi * gi);                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  p[i] = pi - (lr / bc1) * (mi / denom);
+  p[i] = pi - step_size * (mi / denom);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -607,6 +607,10 @@ static const int kOff1[5] = {0, 0, 0, 0, 0};
 // forward convolution  out = conv(in) (+ bias)
 static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int Tin, float* out, int Tout,
                     int Tj, int istride, int ostride, int ooff, const int* ioff, const float* bias, int R, cudaStream_t s) {
+  if (h->train_tf32 && w.wt && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tin && Tout == Tin && tfconv_supported(c0, c1, w.cout, Tin)) {
+    const int taps[5] = {0, 1, 2, 3, 4};
+    return tfconv_launch(h, in0, c0, in1, c1, Tin, w.wt, w.ntaps, w.ntaps, taps, ioff, bias, out, w.cout, 0, R, s);
+  }
   TGemm a;
   a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin;
   for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)(i < w.ntaps ? i : 0) * w.cin * w.cout; a.ioff[i] = i < w.ntaps ? ioff[i] : 0; }
@@ -618,6 +622,9 @@ static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, cons
 // data gradient: out[r, j*ostride+ooff, 0:n_out) (+)= sum_i dout[r, j*istride+ioff[i], :] @ W[taps[i]]^T
 static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, const int* ioff, const float* dout, int Tdout,
                       float* out, int Tout, int n_out, int Tj, int istride, int ostride, int ooff, int accum, int R, cudaStream_t s) {
+  if (h->train_tf32 && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tdout && Tout == Tdout && n_out == w.cin &&
+      tfconv_supported(w.cout, 0, n_out, Tdout))
+    return tfconv_launch(h, dout, w.cout, nullptr, 0, Tdout, w.w, w.ntaps, ntaps, taps, ioff, nullptr, out, n_out, accum, R, s);
   TGemm a;
   a.in0 = dout; a.c0 = w.cout; a.in1 = nullptr; a.c1 = 0; a.Tin = Tdout;
   for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)taps[i < ntaps ? i : 0] * w.cin * w.cout; a.ioff[i] = i < ntaps ? ioff[i] : 0; }
@@ -761,6 +768,14 @@ static const int kNeg5[5] = {2, 1, 0, -1, -2};
 static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, const float* in0, int c0, const float* in1, int c1, int T,
                             const float* dout, float* dw, float* db, int R, cudaStream_t s) {
   int rc, splits;
+  if (h->train_tf32 && tfwgrad_supported(c0, c1, cout, T, R)) {
+    TrainState* st = ts_of(h);
+    if ((rc = tfwgrad_launch(h, in0, c0, in1, c1, T, dout, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, st->part, st->part_floats, MAX_SPLITS, R,
+                             &splits, s)))
+      return rc;
+    if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s))) return rc;
+    return colsum(h, dout, R * T, cout, db, s);
+  }
   if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s,
                        true)))
     return rc;
@@ -971,11 +986,13 @@ int mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out
 
 float* train_deps_buffer(CldHandle* h) { return ts_of(h) ? ts_of(h)->deps : nullptr; }
 
-int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, double wd,
               int step, cudaStream_t s) {
-  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+  // the scalar factors in double, as torch's Python-side arithmetic computes them (1 - 0.999f evaluated in fp32 is off by 1.3e-5)
+  const float step_size = (float)(lr / (1.0 - pow(b1, (double)step)));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)step));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, step_size, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps,
+                                                          (float)wd, bc2_sqrt);
   CLD_LAUNCH_OK(h, "adam_kernel");
   return 0;
 }

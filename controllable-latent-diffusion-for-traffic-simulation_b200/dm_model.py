@@ -165,6 +165,7 @@ class DmModel(nn.Module):
         # denoiser training (sec. 8 f-2): fp32 engine with the activation stash, flat parameter / gradient vectors
         self._train_eng, self._train_sig, self._train_gen, self._param_epoch = None, None, 0, 0
         self._flat, self._flat_grad, self._flat_views = None, None, None
+        self.train_precision = "fp32"      # "tf32": the training step's stride-1 convolutions on the tensor pipe (Engine.set_train_precision)
 
     def _create_dynamics(self):
         if str(self._dynamics_type) in ("Unicycle", "DynType.UNICYCLE"):
@@ -477,6 +478,7 @@ class DmModel(nn.Module):
         if self._train_sig != sig:
             eng.load_unet(self.model.state_dict())
             self._train_sig = sig
+        eng.set_train_precision(self.train_precision)
         return eng
 
     def denoise_train(self, x, aux_info, t):

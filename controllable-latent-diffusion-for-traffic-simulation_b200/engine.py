@@ -216,6 +216,11 @@ class Engine:
         return (eps, dbg) if debug_stage is not None else eps
 
     # ------------------------------------------------------------------ denoiser training
+    def set_train_precision(self, mode):
+        """"fp32": every training GEMM on the CUDA cores (1e-4 parity mode); "tf32": the stride-1 convolutions (forward and data
+        gradient) on the tensor pipe (tcgen05 kind::tf32)."""
+        self._check(lib.cld_train_set_precision(self._h, {"fp32": 0, "tf32": 1}[mode]), "cld_train_set_precision")
+
     @_on_device
     def unet_train_forward(self, x, cond, t):
         """eps like `unet_forward` on the fp32 kernels; the handle keeps the activations for `unet_backward`."""

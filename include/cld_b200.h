@@ -162,10 +162,14 @@ int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss
 int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float* cond, const int64_t* t, const float* logp_old,
                  const float* reward, float baseline, float clip_eps, float* const* grads, int n, float* logp_new_out, float* loss_out,
                  int R, void* stream);
+/* tf32 != 0: the stride-1 convolutions of the training step (forward and data gradient) run on the tensor pipe (tcgen05 kind::tf32,
+ * fp32 operands read with 10 mantissa bits, fp32 accumulation); 0 (default): everything in fp32 on the CUDA cores (1e-4 parity mode). */
+int cld_train_set_precision(CldHandle* h, int tf32);
 /* torch.optim.Adam step (amsgrad off; weight_decay added to the gradient) on ONE flat fp32 vector of `numel` elements; `step`
- * counts from 1.  The caller keeps the parameters of the model as views of that vector. */
-int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+ * counts from 1; the hyper-parameters are doubles because torch derives its scalar factors (1 - beta, bias corrections) in double.
+ * The caller keeps the parameters of the model as views of that vector. */
+int cld_adam_step(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int step, void* stream);
 
 /* Debug/verification hook: registers a tap; the NEXT cld_unet_forward calls copy the channels-last
  * activation [R,T',C] produced by stage `stage_index` (0..16: downs.0.0, downs.0.1, downs.0.2, ...,

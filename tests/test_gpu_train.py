@@ -90,6 +90,39 @@ def test_backward_vs_oracle_autograd_every_tensor(dm16):
     print("worst parameter-gradient rel %.2e (%s), dx rel %.2e" % (max(errs.values()), max(errs, key=errs.get), rel(dx, want[-1])))
 
 
+def test_tf32_tensor_core_mode_vs_oracle(models_cpu):
+    """train_precision = "tf32": the stride-1 convolutions of the forward and of the data gradient run as tcgen05 kind::tf32 GEMMs
+    fed by 3-D TMA boxes of the fp32 activations (csrc/train_tc.cu).  10-bit mantissa products: 1e-2 budget (measured ~1e-3)."""
+    dm, _, _ = models_cpu(16)
+    dm = dm.cuda()
+    dm.train_precision = "tf32"
+    for R in (10, 37):                              # 37 rows: partial last box at every level (2, 4 and 9 rows per box)
+        torch.manual_seed(5 + R)
+        x, cond = torch.randn(R, 52, 4), torch.randn(R, 256)
+        t = torch.randint(0, 16, (R,))
+        d_eps = torch.randn(R, 52, 4)
+        sd = {k: v.requires_grad_(True) for k, v in cpu_sd(dm.model).items()}
+        xg = x.clone().requires_grad_(True)
+        eps_want = O.unet_forward(sd, xg, cond, t)
+        want = torch.autograd.grad((eps_want * d_eps).sum(), list(sd.values()) + [xg])
+        eng = dm.train_engine(R)
+        eps = eng.unet_train_forward(x.cuda(), cond.cuda(), t.cuda())
+        grads = [torch.empty_like(p) for p in dm.model.parameters()]
+        dx = eng.unet_backward(d_eps.cuda(), grads, want_dx=True)
+        e_eps = rel(eps, eps_want.detach())
+        errs = {k: rel(gr, w) for k, gr, w in zip(sd.keys(), grads, want[:-1])}
+        print("tf32 mode R=%d: rel(eps) %.2e, worst gradient rel %.2e (%s), dx %.2e" %
+              (R, e_eps, max(errs.values()), max(errs, key=errs.get), rel(dx, want[-1])))
+        assert e_eps < 1e-2
+        assert max(errs.values()) < 1e-2, {k: v for k, v in errs.items() if v >= 1e-2}
+        assert rel(dx, want[-1]) < 1e-2
+    # the fp32 mode is untouched by the switch
+    dm.train_precision = "fp32"
+    eng = dm.train_engine(10)
+    e32 = eng.unet_train_forward(x[:10].cuda(), cond[:10].cuda(), t[:10].cuda())
+    assert rel(e32, eps_want.detach()[:10]) < 2e-5
+
+
 def test_backward_horizon_104(models_cpu):
     """cfg3's horizon: T = 104 (levels of 104 / 52 / 26 slots)."""
     from cld_b200 import default_algo_config

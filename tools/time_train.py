@@ -1,5 +1,5 @@
 """Time one PPO minibatch update on the GPU: cld_ppo_grad + cld_adam_step + weight re-pack, R rows.
-usage: python tools/time_train.py [rows=128] [iters=20]"""
+usage: python tools/time_train.py [rows=128] [iters=20] [fp32|tf32]"""
 import os
 import sys
 import time
@@ -13,9 +13,11 @@ from cld_b200.trainer import FusedAdam                       # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+mode = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 algo = default_algo_config()
 torch.manual_seed(0)
 dm = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=16).cuda()
+dm.train_precision = mode
 for p in dm.model.parameters():
     p.requires_grad_(True)
 opt = FusedAdam(dm, lr=1e-4, weight_decay=1e-5)
@@ -44,5 +46,5 @@ torch.cuda.synchronize()
 w1 = time.perf_counter()
 ms = e0.elapsed_time(e1) / iters
 flop = 3 * 119.23e6 * R     # forward + data gradient + weight gradient
-print("rows %d: %.3f ms per PPO minibatch update (device), %.3f ms wall, %d launches per update, %.1f TFLOP/s fp32 (3 x forward FLOPs)"
-      % (R, ms, (w1 - w0) * 1e3 / iters, (eng.launch_count() - n0) // iters, flop / ms / 1e9))
+print("%s rows %d: %.3f ms per PPO minibatch update (device), %.3f ms wall, %d launches per update, %.1f TFLOP/s fp32 (3 x forward FLOPs)"
+      % (mode, R, ms, (w1 - w0) * 1e3 / iters, (eng.launch_count() - n0) // iters, flop / ms / 1e9))
