@@ -273,6 +273,7 @@ def ppo_update_rate(dev, skip_cpu, rows=128, iters=20, warmup=3):
     dm = DmModel(default_algo_config(), {"image": (34, 224, 224)}, n_timesteps=16).to(dev)
     for p in dm.model.parameters():
         p.requires_grad_(True)
+    dm.train_precision = "tf32"
     opt = FusedAdam(dm, lr=1e-4, weight_decay=1e-5)
     g = torch.Generator(device=dev).manual_seed(5)
     rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)    # noqa: E731
@@ -283,22 +284,28 @@ def ppo_update_rate(dev, skip_cpu, rows=128, iters=20, warmup=3):
         loss, _ = dm.ppo_minibatch_grad(x1, x0, cond, t, lp_old, reward, 0.0, 0.2)
         opt.step()
         return loss
-    for _ in range(warmup):
-        step()
-    eng = dm.train_engine(rows)
-    torch.cuda.synchronize()
-    l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out = {"rows": rows, "ms_per_minibatch_update": ms, "updates_per_s": 1e3 / ms, "iters": iters, "dtype": "fp32 (CUDA cores)",
-           "gpu_launches_per_update": (eng.launch_count() - l0) // iters,
+    def timed():
+        for _ in range(warmup):
+            step()
+        eng = dm.train_engine(rows)
+        torch.cuda.synchronize()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, (eng.launch_count() - l0) // iters
+    ms, launches = timed()
+    dm.train_precision = "fp32"
+    ms32, launches32 = timed()
+    out = {"rows": rows, "ms_per_minibatch_update": ms, "updates_per_s": 1e3 / ms, "iters": iters,
+           "dtype": "tf32 tensor-core convolutions (tcgen05 kind::tf32, fp32 accumulate), fp32 elsewhere",
+           "gpu_launches_per_update": launches,
            "algorithmic_gflop_per_update": 3 * 119.23e-3 * rows, "achieved_tflops": 3 * 119.23e6 * rows / (ms * 1e-3) / 1e12,
-           "ppo_update_s": "%.1f s for the reference's 10 epochs x 300 minibatches" % (3000 * ms * 1e-3)}
+           "ppo_update_s": "%.1f s for the reference's 10 epochs x 300 minibatches" % (3000 * ms * 1e-3),
+           "fp32_parity_mode": {"ms_per_minibatch_update": ms32, "gpu_launches_per_update": launches32, "dtype": "fp32 (CUDA cores)"}}
     if not skip_cpu:
         import time
         import cld_oracle as O

@@ -275,14 +275,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
   for (; m < M; m += st) s0 += src[(size_t)m * C + c];
   partial[(size_t)blockIdx.x * C + c] = (s0 + s1) + (s2 + s3);
 }
-// columns [0, split) go to dst0, [split, C) to dst1 (two gradient tensors from one pass)
+// columns [0, split) go to dst0, [split, 2 split) to dst1, [2 split, C) to dst2 (up to three gradient tensors from one pass); also
+// used directly on a [M, C] matrix of few rows (nblk = M)
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dst0,
-                                                           int split, float* __restrict__ dst1) {
+                                                           int split, float* __restrict__ dst1, float* __restrict__ dst2) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * C + c];
-  if (c < split) dst0[c] = s; else dst1[c - split] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 3 < nblk; b += 4) {
+    s0 += partial[(size_t)b * C + c]; s1 += partial[(size_t)(b + 1) * C + c];
+    s2 += partial[(size_t)(b + 2) * C + c]; s3 += partial[(size_t)(b + 3) * C + c];
+  }
+  for (; b < nblk; ++b) s0 += partial[(size_t)b * C + c];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (c < split) dst0[c] = s; else if (c < 2 * split) dst1[c - split] = s; else if (dst2) dst2[c - 2 * split] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +320,8 @@ __device__ __forceinline__ float mish_grad(float x) {
 //   x = conv output [R,T,C];  xh = (x - mean) rstd;  u = xh g + b;  y = mish(u) (+ ...)
 //   dU = dY mish'(u);  dg[c] += dU xh;  db[c] += dU;  dxh = dU g;  dx = rstd (dxh - mean(dxh) - xh mean(dxh xh))
 // One CTA per row, warp = group.  cpg divides 32, so a lane always meets the same channel: per-channel sums stay in registers.
-// Per-row partials (rp [R][dg | db], and sum_t dY = d(time bias)) are written; one colsum reduces them over the rows.
+// Per-row partials (rp [R][dg | db | sum_t dx = the bias gradient of the convolution in front], and sum_t dY = d(time bias)) are
+// written; one colsum reduces them over the rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ dy,
@@ -357,17 +365,22 @@ __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restric
     sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
   }
   if (lane < cpg) {
-    rp[(size_t)r * 2 * C + c] = sg; rp[(size_t)r * 2 * C + C + c] = sb;      // [R][gamma | beta]
+    rp[(size_t)r * 3 * C + c] = sg; rp[(size_t)r * 3 * C + C + c] = sb;      // [R][gamma | beta | conv bias]
     if (dtb) dtb[(size_t)r * tb_stride + c] = sy;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   const float m1 = s1 / (float)n, m2 = s2 / (float)n;
+  float sx = 0.f;                                     // sum_t dx of this lane's channel = the row's share of the conv bias gradient
   for (int e = lane; e < n; e += 32) {
     const int off = (e / cpg) * C + cl;
     const float xh = (xin[off] - mean) * rstd;
-    dxo[off] = rstd * (dxo[off] - m1 - xh * m2);
+    const float d = rstd * (dxo[off] - m1 - xh * m2);
+    dxo[off] = d;
+    sx += d;
   }
+  for (int o = 16; o >= cpg; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  if (lane < cpg) rp[(size_t)r * 3 * C + 2 * C + c] = sx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -584,7 +597,7 @@ static int train_prepare(CldHandle* h, int R) {
   if (tb_total > CLD_TB_TOTAL_MAX) return fail(h, CLD_ERR_UNSUPPORTED, "time-bias width %d above %d", tb_total, CLD_TB_TOTAL_MAX);
   if (td > 64) return fail(h, CLD_ERR_UNSUPPORTED, "the denoiser backward needs base_dim <= 64");
   // 12 blocks x 4 + p0 p1 q0 q1 fA fB tmpR + gA gB gX gY + 2 x 2 (concat gradients) = 63 E, + the small per-row vectors
-  const size_t per_row = 63 * E + (size_t)tb_total + 64 + td + 4 * td + 4 * td + td + 2 * 256 + 1 + (size_t)c.horizon * c.latent_dim;
+  const size_t per_row = 63 * E + (size_t)tb_total + 64 + td + 4 * td + 4 * td + td + 3 * 256 + 1 + (size_t)c.horizon * c.latent_dim;
   const size_t cap = (size_t)R;
   CLD_CUDA_OK(h, cudaMalloc((void**)&st->arena, per_row * cap * sizeof(float)));
   float* p = st->arena;
@@ -593,7 +606,7 @@ static int train_prepare(CldHandle* h, int R) {
   st->p0 = take(E); st->p1 = take(E); st->q0 = take(E); st->q1 = take(E); st->fA = take(E); st->fB = take(E); st->tmpR = take(E);
   st->gA = take(E); st->gB = take(E); st->gX = take(E); st->gY = take(E); st->gcat8 = take(2 * E); st->gcat10 = take(2 * E);
   st->dtbias = take(tb_total); st->dtcm = take(64); st->emb = take(td); st->hid = take(4 * td); st->dpre1 = take(4 * td);
-  st->dpre2 = take(td); st->rp = take(512); st->loss_row = take(1);
+  st->dpre2 = take(td); st->rp = take(768); st->loss_row = take(1);
   st->deps = take((size_t)c.horizon * c.latent_dim);
   st->cap_rows = R;
   st->fwd_valid = false;
@@ -622,7 +635,7 @@ static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, cons
 // data gradient: out[r, j*ostride+ooff, 0:n_out) (+)= sum_i dout[r, j*istride+ioff[i], :] @ W[taps[i]]^T
 static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, const int* ioff, const float* dout, int Tdout,
                       float* out, int Tout, int n_out, int Tj, int istride, int ostride, int ooff, int accum, int R, cudaStream_t s) {
-  if (h->train_tf32 && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tdout && Tout == Tdout && n_out == w.cin &&
+  if (h->train_tf32 && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tdout && Tout == Tdout && (n_out == w.cin || w.ntaps == 1) &&
       tfconv_supported(w.cout, 0, n_out, Tdout))
     return tfconv_launch(h, dout, w.cout, nullptr, 0, Tdout, w.w, w.ntaps, ntaps, taps, ioff, nullptr, out, n_out, accum, R, s);
   TGemm a;
@@ -675,14 +688,20 @@ static int wreduce(CldHandle* h, int splits, int ntaps, int cin, int cout, int c
   return 0;
 }
 
-static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cudaStream_t s, int split = -1, float* dst1 = nullptr) {
+static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cudaStream_t s, int split = -1, float* dst1 = nullptr,
+                  float* dst2 = nullptr) {
   TrainState* st = ts_of(h);
+  if (M <= 512) {                       // few rows (per-row partials of a minibatch): one pass
+    colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(src, M, C, dst, split < 0 ? C : split, dst1, dst2);
+    CLD_LAUNCH_OK(h, "colsum_final_kernel");
+    return 0;
+  }
   int nblk = (M + 31) / 32;
   if (nblk > COLSUM_BLOCKS) nblk = COLSUM_BLOCKS;
   dim3 grid(nblk, (C + 255) / 256);
   colsum_kernel<<<grid, 256, 0, s>>>(src, M, C, st->colpart);
   CLD_LAUNCH_OK(h, "colsum_kernel");
-  colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(st->colpart, nblk, C, dst, split < 0 ? C : split, dst1);
+  colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(st->colpart, nblk, C, dst, split < 0 ? C : split, dst1, dst2);
   CLD_LAUNCH_OK(h, "colsum_final_kernel");
   return 0;
 }
@@ -752,12 +771,12 @@ int unet_train_forward(CldHandle* h, const float* x, const float* cond, const in
 }
 
 // gradient of GroupNorm+Mish: dA = d(conv output); gamma / beta gradients -> grads; optional time-bias gradient slice
-static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float* dA, float* dgamma, float* dbeta, float* dtb,
-                  int T, int C, int R, cudaStream_t s) {
+static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float* dA, float* dgamma, float* dbeta, float* dconv_bias,
+                  float* dtb, int T, int C, int R, cudaStream_t s) {
   TrainState* st = ts_of(h);
   gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, st->rp, dtb, h->unet.tb_total, T, C);
   CLD_LAUNCH_OK(h, "gn_mish_bwd_kernel");
-  return colsum(h, st->rp, R, 2 * C, dgamma, s, C, dbeta);
+  return colsum(h, st->rp, R, 3 * C, dgamma, s, C, dbeta, dconv_bias);
 }
 
 static const int kK5[5] = {0, 1, 2, 3, 4}, kK1[5] = {0, 0, 0, 0, 0}, kK3[5] = {0, 1, 2, 0, 0};
@@ -768,16 +787,17 @@ static const int kNeg5[5] = {2, 1, 0, -1, -2};
 static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, const float* in0, int c0, const float* in1, int c1, int T,
                             const float* dout, float* dw, float* db, int R, cudaStream_t s) {
   int rc, splits;
+  // db == nullptr: the bias gradient came out of the GroupNorm backward that produced `dout`
   if (h->train_tf32 && tfwgrad_supported(c0, c1, cout, T, R)) {
     TrainState* st = ts_of(h);
     if ((rc = tfwgrad_launch(h, in0, c0, in1, c1, T, dout, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, st->part, st->part_floats, MAX_SPLITS, R,
                              &splits, s)))
       return rc;
     if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s))) return rc;
-    return colsum(h, dout, R * T, cout, db, s);
+    return db ? colsum(h, dout, R * T, cout, db, s) : 0;
   }
   if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s,
-                       true)))
+                       db != nullptr)))
     return rc;
   return wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s, db);
 }
@@ -790,12 +810,12 @@ static int block_bwd(CldHandle* h, int bi, const BlkIdx& ix, const float* dOUT, 
   const int T = b.T, C = rb.cout, cin = b.c0 + b.c1;
   int rc;
   // second Conv1dBlock
-  if ((rc = gn_bwd(h, b.A1, rb.n1, dOUT, st->gA, grads[ix.g1], grads[ix.b1], nullptr, T, C, R, s))) return rc;
-  if ((rc = conv_param_grads(h, C, C, 5, b.B0, C, nullptr, 0, T, st->gA, grads[ix.c1w], grads[ix.c1b], R, s))) return rc;
+  if ((rc = gn_bwd(h, b.A1, rb.n1, dOUT, st->gA, grads[ix.g1], grads[ix.b1], grads[ix.c1b], nullptr, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, C, C, 5, b.B0, C, nullptr, 0, T, st->gA, grads[ix.c1w], nullptr, R, s))) return rc;
   if ((rc = conv_dgrad(h, rb.c1, 5, kTap5, kNeg5, st->gA, T, st->gB, T, C, T, 1, 1, 0, 0, R, s))) return rc;
   // first Conv1dBlock (+ time / cond bias)
-  if ((rc = gn_bwd(h, b.A0, rb.n0, st->gB, st->gA, grads[ix.g0], grads[ix.b0], st->dtbias + rb.tb_off, T, C, R, s))) return rc;
-  if ((rc = conv_param_grads(h, cin, C, 5, b.in0, b.c0, b.in1, b.c1, T, st->gA, grads[ix.c0w], grads[ix.c0b], R, s))) return rc;
+  if ((rc = gn_bwd(h, b.A0, rb.n0, st->gB, st->gA, grads[ix.g0], grads[ix.b0], grads[ix.c0b], st->dtbias + rb.tb_off, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, cin, C, 5, b.in0, b.c0, b.in1, b.c1, T, st->gA, grads[ix.c0w], nullptr, R, s))) return rc;
   if ((rc = conv_dgrad(h, rb.c0, 5, kTap5, kNeg5, st->gA, T, dIN, T, cin, T, 1, 1, 0, 0, R, s))) return rc;
   // residual path
   if (rb.res.w) {
@@ -884,8 +904,8 @@ int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, i
     const int tap0[5] = {0, 0, 0, 0, 0};
     if ((rc = conv_dgrad(h, u.fin1, 1, tap0, kOff1, d_eps, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;
   }
-  if ((rc = gn_bwd(h, st->fA, u.fin0n, gX, st->gA, grads[i_fin[2]], grads[i_fin[3]], nullptr, T, d0, R, s))) return rc;
-  if ((rc = conv_param_grads(h, d0, d0, 5, st->q1, d0, nullptr, 0, T, st->gA, grads[i_fin[0]], grads[i_fin[1]], R, s))) return rc;
+  if ((rc = gn_bwd(h, st->fA, u.fin0n, gX, st->gA, grads[i_fin[2]], grads[i_fin[3]], grads[i_fin[1]], nullptr, T, d0, R, s))) return rc;
+  if ((rc = conv_param_grads(h, d0, d0, 5, st->q1, d0, nullptr, 0, T, st->gA, grads[i_fin[0]], nullptr, R, s))) return rc;
   if ((rc = conv_dgrad(h, u.fin0, 5, kTap5, kNeg5, st->gA, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;          // gX = d q1
   // ---- ups.1: upsample, blocks 11, 10
   if ((rc = up_bwd(h, u.up[1], b[11].OUT, T2, gX, gY, grads[i_up[1][0]], grads[i_up[1][1]], R, s))) return rc;      // gY = d o11

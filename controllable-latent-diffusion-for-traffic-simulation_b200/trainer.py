@@ -54,7 +54,7 @@ def warmup_cosine(epoch, total_epochs):
 
 class GuideDMTrainer:
     def __init__(self, dm, vae, algo_config, *, batch_size, learning_rate=1e-4, weight_decay=0.0, epochs=30, fused=True,
-                 ppo_epochs=10, clip_eps=0.2, buffer_max=None, sample_kw=None, generator=None):
+                 ppo_epochs=10, clip_eps=0.2, buffer_max=None, sample_kw=None, generator=None, train_precision="tf32"):
         self.dm, self.vae, self.algo_config = dm, vae, algo_config
         self.batch_size = int(batch_size)
         self.num_samp = int(algo_config.num_samp)
@@ -69,6 +69,8 @@ class GuideDMTrainer:
         self.sample_kw = dict(sample_kw or {})
         self.generator = generator
         self.log = {}
+        # "tf32": the training step's convolutions on the tensor pipe (tcgen05 kind::tf32, ~1e-3); "fp32": CUDA cores (1e-4 parity mode)
+        dm.train_precision = train_precision
         for p in dm.model.parameters():
             p.requires_grad_(True)
         if self.fused:
