@@ -77,6 +77,46 @@ __global__ void pack_conv_t_kernel(const float* __restrict__ src, float* __restr
   dst[idx] = src[((size_t)co * cin + ci) * K + ks[tap]];
 }
 
+// ---- fused re-pack: all pack / copy jobs of cld_load_unet in ONE launch (the weights change after every optimizer step)
+struct PackSrc { const float* p[160]; };
+constexpr int PACK_BLOCK_ELEMS = 2048;
+__global__ void __launch_bounds__(256) repack_all_kernel(const PackJob* __restrict__ jobs, int njobs, PackSrc src) {
+  int lo = 0, hi = njobs - 1;                       // last job whose first block is <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const float* __restrict__ s = src.p[j.src];
+  const int base = ((int)blockIdx.x - j.blk0) * PACK_BLOCK_ELEMS;
+  for (int idx = base + threadIdx.x; idx < min(j.total, base + PACK_BLOCK_ELEMS); idx += 256) {
+    if (j.kind == 2) { j.dst[idx] = s[idx]; continue; }
+    if (j.kind == 0) {
+      const int co = idx % j.cout, ci = (idx / j.cout) % j.cin, tap = idx / (j.cout * j.cin);
+      const int k = j.ks[tap];
+      const float v = j.transposed ? s[((size_t)ci * j.cout + co) * j.K + k] : s[((size_t)co * j.cin + ci) * j.K + k];
+      j.dst[((size_t)tap * j.cin + ci) * j.ld + j.off + co] = v;
+    } else {
+      const int ci = idx % j.cin, co = (idx / j.cin) % j.cout, tap = idx / (j.cout * j.cin);
+      j.dst[idx] = s[((size_t)co * j.cin + ci) * j.K + j.ks[tap]];
+    }
+  }
+}
+
+static void record_job(CldHandle* h, int kind, const float* src, float* dst, int cout, int cin, int K, int ntaps, const int* ks, int ld,
+                       int off, int transposed, int total) {
+  if (!h->pack_recording) return;
+  int si = -1;
+  for (int i = 0; i < h->pack_nsrc; ++i)
+    if (h->pack_src[i] == src) { si = i; break; }
+  if (si < 0) { h->pack_recording = false; h->pack_jobs.clear(); return; }      // a source outside the list: no fast path
+  PackJob j;
+  j.kind = kind; j.src = si; j.dst = dst; j.cout = cout; j.cin = cin; j.K = K; j.ntaps = ntaps;
+  for (int i = 0; i < 5; ++i) j.ks[i] = (ks && i < ntaps) ? ks[i] : 0;
+  j.ld = ld; j.off = off; j.transposed = transposed; j.total = total; j.blk0 = 0;
+  h->pack_jobs.push_back(j);
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
@@ -93,6 +133,7 @@ static int copy_vec(CldHandle* h, float** dst, const float* src, size_t n, cudaS
   int rc = dev_alloc(h, dst, n);
   if (rc) return rc;
   CLD_CUDA_OK(h, cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  record_job(h, 2, src, *dst, 0, 0, 0, 0, nullptr, 0, 0, 0, (int)n);
   return 0;
 }
 
@@ -105,10 +146,12 @@ static int pack_conv(CldHandle* h, ConvW* w, const float* src, const float* bias
   pack_conv_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->w, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4],
                                                        cout, 0, transposed);
   CLD_LAUNCH_OK(h, "pack_conv_kernel");
+  record_job(h, 0, src, w->w, cout, cin, K, ntaps, ks, cout, 0, transposed, total);
   if (!transposed) {
     if ((rc = dev_alloc(h, &w->wt, (size_t)ntaps * cin * cout))) return rc;
     pack_conv_t_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->wt, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4]);
     CLD_LAUNCH_OK(h, "pack_conv_t_kernel");
+    record_job(h, 1, src, w->wt, cout, cin, K, ntaps, ks, 0, 0, 0, total);
   }
   if (bias) return copy_vec(h, &w->b, bias, cout, s);
   return 0;
@@ -235,6 +278,22 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
   if (n != expect) return fail(h, CLD_ERR_ARG, "cld_load_unet: expected %d tensors, got %d", expect, n);
   int idx = 0, rc;
   UnetW& u = h->unet;
+  // ---- re-load of a loaded fp32 handle (every optimizer step of the PPO update): ONE launch instead of ~80 pack kernels + ~100 copies
+  if (u.loaded && !tc_enabled(h) && h->pack_jobs_dev && n <= 160) {
+    PackSrc src;
+    for (int i = 0; i < n; ++i) {
+      if (!p[i]) return fail(h, CLD_ERR_ARG, "cld_load_unet: tensor %d is null", i);
+      src.p[i] = p[i];
+    }
+    repack_all_kernel<<<h->pack_blocks, 256, 0, s>>>(h->pack_jobs_dev, (int)h->pack_jobs.size(), src);
+    CLD_LAUNCH_OK(h, "repack_all_kernel");
+    h->tvec_all_valid = false;
+    train_invalidate(h);
+    return CLD_OK;
+  }
+  h->pack_jobs.clear();
+  h->pack_recording = !tc_enabled(h) && n <= 160;
+  h->pack_src = p; h->pack_nsrc = n;
   auto chk = [&](int i, int64_t want) -> bool { return !numels || numels[i] == want; };
 #define NEXT(want)                                                                                        \
   (chk(idx, (int64_t)(want)) ? p[idx++]                                                                   \
@@ -277,6 +336,9 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
                                                            rb.tb_off, 0);
       CLD_LAUNCH_OK(h, "pack_conv_kernel");
       CLD_CUDA_OK(h, cudaMemcpyAsync(u.tb_b + rb.tb_off, tbv, bd.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      const int k1x[5] = {0, 0, 0, 0, 0};
+      record_job(h, 0, tw, u.tb_w, bd.cout, tdim, 1, 1, k1x, u.tb_total, rb.tb_off, 0, total);
+      record_job(h, 2, tbv, u.tb_b + rb.tb_off, 0, 0, 0, 0, nullptr, 0, 0, 0, bd.cout);
     }
     TAKE(c0w, bd.cout * bd.cin * 5) TAKE(c0b, bd.cout) TAKE(g0, bd.cout) TAKE(b0, bd.cout)
     TAKE(c1w, bd.cout * bd.cout * 5) TAKE(c1b, bd.cout) TAKE(g1, bd.cout) TAKE(b1, bd.cout)
@@ -332,6 +394,14 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
 #undef TAKE
 #undef NEXT
   if (tc_enabled(h) && (rc = tc_finalize(h, s))) return rc;
+  if (h->pack_recording && !h->pack_jobs.empty()) {
+    int blk = 0;
+    for (PackJob& j : h->pack_jobs) { j.blk0 = blk; blk += (j.total + PACK_BLOCK_ELEMS - 1) / PACK_BLOCK_ELEMS; }
+    h->pack_blocks = blk;
+    if ((rc = dev_alloc(h, &h->pack_jobs_dev, h->pack_jobs.size()))) return rc;
+    CLD_CUDA_OK(h, cudaMemcpyAsync(h->pack_jobs_dev, h->pack_jobs.data(), h->pack_jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, s));
+  }
+  h->pack_recording = false; h->pack_src = nullptr;
   CLD_CUDA_OK(h, cudaStreamSynchronize(s));
   u.loaded = true;
   h->tvec_all_valid = false;

@@ -73,6 +73,16 @@ struct Schedule {
 
 }  // namespace cld
 
+namespace cld {
+// one entry of the fused weight re-pack (cld_load_unet on a handle that is already loaded: every optimizer step of the PPO update)
+struct PackJob {
+  int kind;            // 0: conv [cout][cin][K] -> [tap][cin][ld] (+off); 1: -> [tap][cout][cin]; 2: flat copy
+  int src;             // index into the state-dict pointer list
+  float* dst;
+  int cout, cin, K, ntaps, ks[5], ld, off, transposed, total, blk0;
+};
+}  // namespace cld
+
 struct CldHandle {
   CldConfig cfg;
   int device = 0;
@@ -133,6 +143,13 @@ struct CldHandle {
   bool use_lstm_tc = false;
   // denoiser training state (opaque, owned by kernels_unet_train.cu): activation stash + gradient scratch, allocated on first use
   void* train = nullptr;
+  // fused re-pack: the jobs recorded during the first cld_load_unet, and their device copy
+  std::vector<cld::PackJob> pack_jobs;
+  cld::PackJob* pack_jobs_dev = nullptr;
+  int pack_blocks = 0;
+  bool pack_recording = false;
+  const float* const* pack_src = nullptr;
+  int pack_nsrc = 0;
   void* train_tc = nullptr;        // tensor-map cache of the tf32 tensor-core convolutions (train_tc.cu)
   bool train_tf32 = false;         // cld_train_set_precision: stride-1 convolutions of the training step on the tensor pipe
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)

@@ -292,6 +292,27 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   if (c < split) dst0[c] = s; else if (c < 2 * split) dst1[c - split] = s; else if (dst2) dst2[c - 2 * split] = s;
 }
 
+// few rows (the per-row partials of a minibatch): 32 columns x 8 row slices per CTA, slices added in a fixed order
+__global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restrict__ src, int M, int C, float* __restrict__ dst0, int split,
+                                                           float* __restrict__ dst1, float* __restrict__ dst2) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < C) {
+    const int per = (M + 7) >> 3, lo = part * per, hi = min(M, lo + per);
+    for (int m = lo; m < hi; ++m) s += src[(size_t)m * C + c];
+  }
+  red[part][cl] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    float t = red[0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][cl];
+    if (c < split) dst0[c] = t; else if (c < 2 * split) dst1[c - split] = t; else if (dst2) dst2[c - 2 * split] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // elementwise helpers
 // ------------------------------------------------------------------------------------------------
@@ -692,8 +713,8 @@ static int colsum(CldHandle* h, const float* src, int M, int C, float* dst, cuda
                   float* dst2 = nullptr) {
   TrainState* st = ts_of(h);
   if (M <= 512) {                       // few rows (per-row partials of a minibatch): one pass
-    colsum_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(src, M, C, dst, split < 0 ? C : split, dst1, dst2);
-    CLD_LAUNCH_OK(h, "colsum_final_kernel");
+    colsum_small_kernel<<<(C + 31) / 32, 256, 0, s>>>(src, M, C, dst, split < 0 ? C : split, dst1, dst2);
+    CLD_LAUNCH_OK(h, "colsum_small_kernel");
     return 0;
   }
   int nblk = (M + 31) / 32;

@@ -204,6 +204,12 @@ def test_reference_lines_through_autograd_and_fused_step_agree(models_cpu, gold)
         with torch.no_grad():
             want_eps = O.unet_forward(cpu_sd(dm.model), x1.cpu(), cond.cpu(), t.cpu())
         assert rel(eps_new, want_eps) < 2e-5
+        # ... and so does the training engine (re-load of a loaded handle = the fused one-launch re-pack), in both weight layouts
+        teng = dm.train_engine(x1.shape[0])
+        assert rel(teng.unet_forward(x1, cond, t), want_eps) < 2e-5
+        dm.train_precision = "tf32"
+        assert rel(dm.train_engine(x1.shape[0]).unet_train_forward(x1, cond, t), want_eps) < 1e-2
+        dm.train_precision = "fp32"
     # autograd node + torch Adam  ==  fused kernels.  The first Adam step is -lr g / (|g| + 1e-8): where |g| is near 1e-8 the last bits
     # of g (d_eps from torch's elementwise autograd vs the head kernel) move the update; measured 1.9e-3 of the update's norm
     worst = max(rel(a, b) for a, b in zip(*deltas))
