@@ -68,13 +68,13 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, float* __restric
 
 // dst[(tap*cout + co)*cin + ci] = src[co, ci, k(tap)]: the [N][K] (K contiguous) weight planes of the tensor-core training forward
 __global__ void pack_conv_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int K, int ntaps,
-                                   int k0, int k1, int k2, int k3, int k4) {
+                                   int k0, int k1, int k2, int k3, int k4, int transposed) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int total = ntaps * cin * cout;
   if (idx >= total) return;
   int ci = idx % cin, co = (idx / cin) % cout, tap = idx / (cout * cin);
   int ks[5] = {k0, k1, k2, k3, k4};
-  dst[idx] = src[((size_t)co * cin + ci) * K + ks[tap]];
+  dst[idx] = transposed ? src[((size_t)ci * cout + co) * K + ks[tap]] : src[((size_t)co * cin + ci) * K + ks[tap]];
 }
 
 // ---- fused re-pack: all pack / copy jobs of cld_load_unet in ONE launch (the weights change after every optimizer step)
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) repack_all_kernel(const PackJob* __restri
       j.dst[((size_t)tap * j.cin + ci) * j.ld + j.off + co] = v;
     } else {
       const int ci = idx % j.cin, co = (idx / j.cin) % j.cout, tap = idx / (j.cout * j.cin);
-      j.dst[idx] = s[((size_t)co * j.cin + ci) * j.K + j.ks[tap]];
+      j.dst[idx] = j.transposed ? s[((size_t)ci * j.cout + co) * j.K + j.ks[tap]] : s[((size_t)co * j.cin + ci) * j.K + j.ks[tap]];
     }
   }
 }
@@ -147,12 +147,10 @@ static int pack_conv(CldHandle* h, ConvW* w, const float* src, const float* bias
                                                        cout, 0, transposed);
   CLD_LAUNCH_OK(h, "pack_conv_kernel");
   record_job(h, 0, src, w->w, cout, cin, K, ntaps, ks, cout, 0, transposed, total);
-  if (!transposed) {
-    if ((rc = dev_alloc(h, &w->wt, (size_t)ntaps * cin * cout))) return rc;
-    pack_conv_t_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->wt, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4]);
-    CLD_LAUNCH_OK(h, "pack_conv_t_kernel");
-    record_job(h, 1, src, w->wt, cout, cin, K, ntaps, ks, 0, 0, 0, total);
-  }
+  if ((rc = dev_alloc(h, &w->wt, (size_t)ntaps * cin * cout))) return rc;
+  pack_conv_t_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, w->wt, cout, cin, K, ntaps, ks[0], ks[1], ks[2], ks[3], ks[4], transposed);
+  CLD_LAUNCH_OK(h, "pack_conv_t_kernel");
+  record_job(h, 1, src, w->wt, cout, cin, K, ntaps, ks, 0, 0, transposed, total);
   if (bias) return copy_vec(h, &w->b, bias, cout, s);
   return 0;
 }

@@ -207,11 +207,13 @@ int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t
 float* train_deps_buffer(CldHandle* h);
 // ---- train_tc.cu
 bool tfconv_supported(int c0, int c1, int N, int Tp);
-int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* w, int planes, int ntaps,
-                  const int* wtap, const int* toff, const float* bias, float* out, int N, int accum, int R, cudaStream_t s);
+int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Ta, int tstride, int Tp, const float* w, int planes,
+                  int ntaps, const int* wtap, const int* toff, const float* bias, float* out, int Tout, int ostride, int ooff, int N, int accum,
+                  int R, cudaStream_t s);
 bool tfwgrad_supported(int c0, int c1, int cout, int Tp, int R);
-int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* dout, int cout, int ntaps,
-                   const int* toff, float* part, size_t part_floats, int max_splits, int R, int* splits_out, cudaStream_t s);
+int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Ta, int a_stride, int Tp, const float* dout, int Td,
+                   int d_stride, int d_toff, int cout, int ntaps, const int* toff, float* part, size_t part_floats, int max_splits, int R,
+                   int* splits_out, cudaStream_t s);
 void train_tc_destroy(CldHandle* h);
 void train_destroy(CldHandle* h);
 void train_invalidate(CldHandle* h);     // the time / cond bias buffers the backward reads were overwritten

@@ -641,9 +641,9 @@ static const int kOff1[5] = {0, 0, 0, 0, 0};
 // forward convolution  out = conv(in) (+ bias)
 static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int Tin, float* out, int Tout,
                     int Tj, int istride, int ostride, int ooff, const int* ioff, const float* bias, int R, cudaStream_t s) {
-  if (h->train_tf32 && w.wt && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tin && Tout == Tin && tfconv_supported(c0, c1, w.cout, Tin)) {
+  if (h->train_tf32 && w.wt && tfconv_supported(c0, c1, w.cout, Tj)) {
     const int taps[5] = {0, 1, 2, 3, 4};
-    return tfconv_launch(h, in0, c0, in1, c1, Tin, w.wt, w.ntaps, w.ntaps, taps, ioff, bias, out, w.cout, 0, R, s);
+    return tfconv_launch(h, in0, c0, in1, c1, Tin, istride, Tj, w.wt, w.ntaps, w.ntaps, taps, ioff, bias, out, Tout, ostride, ooff, w.cout, 0, R, s);
   }
   TGemm a;
   a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin;
@@ -656,9 +656,9 @@ static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, cons
 // data gradient: out[r, j*ostride+ooff, 0:n_out) (+)= sum_i dout[r, j*istride+ioff[i], :] @ W[taps[i]]^T
 static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, const int* ioff, const float* dout, int Tdout,
                       float* out, int Tout, int n_out, int Tj, int istride, int ostride, int ooff, int accum, int R, cudaStream_t s) {
-  if (h->train_tf32 && istride == 1 && ostride == 1 && ooff == 0 && Tj == Tdout && Tout == Tdout && (n_out == w.cin || w.ntaps == 1) &&
-      tfconv_supported(w.cout, 0, n_out, Tdout))
-    return tfconv_launch(h, dout, w.cout, nullptr, 0, Tdout, w.w, w.ntaps, ntaps, taps, ioff, nullptr, out, n_out, accum, R, s);
+  if (h->train_tf32 && (n_out == w.cin || w.ntaps == 1) && tfconv_supported(w.cout, 0, n_out, Tj))
+    return tfconv_launch(h, dout, w.cout, nullptr, 0, Tdout, istride, Tj, w.w, w.ntaps, ntaps, taps, ioff, nullptr, out, Tout, ostride, ooff,
+                         n_out, accum, R, s);
   TGemm a;
   a.in0 = dout; a.c0 = w.cout; a.in1 = nullptr; a.c1 = 0; a.Tin = Tdout;
   for (int i = 0; i < 5; ++i) { a.w[i] = w.w + (size_t)taps[i < ntaps ? i : 0] * w.cin * w.cout; a.ioff[i] = i < ntaps ? ioff[i] : 0; }
@@ -670,8 +670,13 @@ static int conv_dgrad(CldHandle* h, const ConvW& w, int ntaps, const int* taps, 
 // weight gradient of one packed matrix [ntaps][cin][cout] -> partials in st->part; `splits_out` for the reduce
 static int conv_wgrad(CldHandle* h, int cin_total, int cout, int ntaps, const int* ioff, const float* in0, int c0, const float* in1,
                       int c1, int Tin, const float* dout, int Tdout, int Tj, int istride, int ostride, int ooff, int R,
-                      int* splits_out, cudaStream_t s, bool with_bias = false) {
+                      int* splits_out, cudaStream_t s, bool with_bias = false, bool* bias_in_part = nullptr) {
   TrainState* st = ts_of(h);
+  if (bias_in_part) *bias_in_part = false;
+  if (h->train_tf32 && tfwgrad_supported(c0, c1, cout, Tj, R))        // tensor pipe; the caller sums dOut's columns itself
+    return tfwgrad_launch(h, in0, c0, in1, c1, Tin, istride, Tj, dout, Tdout, ostride, ooff, cout, ntaps, ioff, st->part, st->part_floats,
+                          MAX_SPLITS, R, splits_out, s);
+  if (bias_in_part) *bias_in_part = with_bias;
   TWgrad a;
   a.in0 = in0; a.c0 = c0; a.in1 = in1; a.c1 = c1; a.Tin = Tin; a.dout = dout; a.Tout = Tdout; a.cout = cout; a.ntaps = ntaps;
   for (int i = 0; i < 5; ++i) a.ioff[i] = i < ntaps ? ioff[i] : 0;
@@ -809,18 +814,12 @@ static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, co
                             const float* dout, float* dw, float* db, int R, cudaStream_t s) {
   int rc, splits;
   // db == nullptr: the bias gradient came out of the GroupNorm backward that produced `dout`
-  if (h->train_tf32 && tfwgrad_supported(c0, c1, cout, T, R)) {
-    TrainState* st = ts_of(h);
-    if ((rc = tfwgrad_launch(h, in0, c0, in1, c1, T, dout, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, st->part, st->part_floats, MAX_SPLITS, R,
-                             &splits, s)))
-      return rc;
-    if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s))) return rc;
-    return db ? colsum(h, dout, R * T, cout, db, s) : 0;
-  }
+  bool bias_in_part;
   if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s,
-                       db != nullptr)))
+                       db != nullptr, &bias_in_part)))
     return rc;
-  return wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s, db);
+  if ((rc = wreduce(h, splits, ntaps, cin_total, cout, 0, cout, dw, ntaps, ntaps == 5 ? kK5 : kK1, 0, s, bias_in_part ? db : nullptr))) return rc;
+  return (db && !bias_in_part) ? colsum(h, dout, R * T, cout, db, s) : 0;
 }
 
 // backward of one residual block.  dOUT [R,T,cout] -> dIN [R,T,cin_total] (written), parameter gradients -> grads[...]
@@ -854,8 +853,10 @@ static int down_bwd(CldHandle* h, const ConvW& w, const float* in, int T, const 
                     cudaStream_t s) {
   const int C = w.cout, Th = T / 2;
   int rc, splits;
-  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s, true))) return rc;
-  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s, db))) return rc;
+  bool bias_in_part;
+  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s, true, &bias_in_part))) return rc;
+  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s, bias_in_part ? db : nullptr))) return rc;
+  if (!bias_in_part && (rc = colsum(h, dout, R * Th, C, db, s))) return rc;
   // forward: out[j] = sum_tap in[2j + tap - 1] W[tap].  even ti = 2m: tap 1, j = m;  odd ti = 2m + 1: tap 0 with j = m + 1, tap 2 with j = m
   const int te[5] = {1, 0, 0, 0, 0}, oe[5] = {0, 0, 0, 0, 0};
   const int to[5] = {0, 2, 0, 0, 0}, oo[5] = {1, 0, 0, 0, 0};

@@ -32,6 +32,7 @@ struct TfConv {
   int ntaps; int toff[5]; int wtap[5];
   int kb0, kb1;                 // 32-channel blocks of source 0 / source 1 (concatenated input)
   int Tp, rbox, R, N, BN;
+  int Tout, ostride, ooff;      // output tensor [R, Tout, N]; GEMM row (r, j) is written to slot j * ostride + ooff
   const float* bias; float* out; int accum;
 };
 
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf32_conv_kernel(const __grid_c
     const bool valid = m < rows_valid && r < P.R;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    float* op = P.out + ((size_t)r * P.Tp + t) * P.N + n0;
+    float* op = P.out + ((size_t)r * P.Tout + t * P.ostride + P.ooff) * P.N + n0;
     for (int c = 0; c < P.BN; c += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
@@ -162,6 +163,7 @@ struct TfWgrad {
   int ntaps; int toff[5];
   int c0, cin, cout;
   int Tp, rbox, R, nbox, bps, splits;
+  int d_toff;                   // time coordinate of dOut's first slot (the output phase of a transposed convolution)
   float* part;
 };
 
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf32_wgrad_kernel(const __grid_
           if (c < P.c0) tma_load_3d(dst + a * TW_COL, &tmA0, c, P.toff[tap], bx * P.rbox, bar_full + 8 * s);
           else tma_load_3d(dst + a * TW_COL, &tmA1, c - P.c0, P.toff[tap], bx * P.rbox, bar_full + 8 * s);
         }
-        tma_load_3d(dst + 4 * TW_COL, &tmD, co0, 0, bx * P.rbox, bar_full + 8 * s);
-        tma_load_3d(dst + 5 * TW_COL, &tmD, co0 + 32, 0, bx * P.rbox, bar_full + 8 * s);
+        tma_load_3d(dst + 4 * TW_COL, &tmD, co0, P.d_toff, bx * P.rbox, bar_full + 8 * s);
+        tma_load_3d(dst + 5 * TW_COL, &tmD, co0 + 32, P.d_toff, bx * P.rbox, bar_full + 8 * s);
       }
       __syncwarp();
       if (++s == TW_STAGES) { s = 0; ph ^= 1u; }
@@ -274,7 +276,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TfState {
   EncodeTiledFn enc = nullptr;
   bool attr_set = false, attr_set_w = false;
-  std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> maps;     // (base, d0, d1, d2, box1, box2, swizzle)
+  std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> maps;     // (base, d0, d1, d2, box1, box2, swizzle, stride1)
 };
 
 static TfState* tf_of(CldHandle* h) {
@@ -287,7 +289,9 @@ void train_tc_destroy(CldHandle* h) {
 }
 
 // 3-D fp32 tensor {d0 (contiguous), d1, d2}, box {32, b1, b2}, 128-byte swizzle, zero fill outside
-static int tf_map(CldHandle* h, const float* base, int d0, int d1, int d2, int b1, int b2, const CUtensorMap** out, bool atom32 = false) {
+// b1 = elements LOADED along dimension 1, taken every `es1`-th (traversal stride: the stride-2 convolutions)
+static int tf_map(CldHandle* h, const float* base, int d0, int d1, int d2, int b1, int b2, const CUtensorMap** out, bool atom32 = false,
+                  int es1 = 1) {
   TfState* st = tf_of(h);
   if (!st->enc) {
     void* fn = nullptr;
@@ -296,14 +300,14 @@ static int tf_map(CldHandle* h, const float* base, int d0, int d1, int d2, int b
       return fail(h, CLD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     st->enc = (EncodeTiledFn)fn;
   }
-  const auto key = std::make_tuple((const void*)base, d0, d1, d2, b1, b2, (int)atom32);
+  const auto key = std::make_tuple((const void*)base, d0, d1, d2, b1, b2, (int)atom32, es1);
   auto it = st->maps.find(key);
   if (it == st->maps.end()) {
     if (st->maps.size() > 4096) st->maps.clear();
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
     cuuint64_t strides[2] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)b1, (cuuint32_t)b2}, es[3] = {1, 1, 1};
+    cuuint32_t box[3] = {32, (cuuint32_t)(b1 * es1), (cuuint32_t)b2}, es[3] = {1, (cuuint32_t)es1, 1};
     const CUresult r = st->enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -319,9 +323,11 @@ bool tfconv_supported(int c0, int c1, int N, int Tp) {
   return c0 % 32 == 0 && c1 % 32 == 0 && c0 > 0 && N % 16 == 0 && N >= 16 && Tp >= 1 && Tp <= 128;
 }
 
-// out[r, t, 0:N) (+)= bias + sum_i  in[r, t + toff[i], :] @ W[wtap[i]]^T,   W plane = [N][K] (K = c0 + c1 contiguous), `planes` planes
-int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* w, int planes, int ntaps,
-                  const int* wtap, const int* toff, const float* bias, float* out, int N, int accum, int R, cudaStream_t s) {
+// out[r, j * ostride + ooff, 0:N) (+)= bias + sum_i  in[r, j * tstride + toff[i], :] @ W[wtap[i]]^T  for j in [0, Tp);
+// in = [R, Ta, c0 (+ c1)], out = [R, Tout, N], W plane = [N][K] (K = c0 + c1 contiguous), `planes` planes
+int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Ta, int tstride, int Tp, const float* w, int planes,
+                  int ntaps, const int* wtap, const int* toff, const float* bias, float* out, int Tout, int ostride, int ooff, int N, int accum,
+                  int R, cudaStream_t s) {
   TfState* st = tf_of(h);
   if (!st->attr_set) {
     CLD_CUDA_OK(h, cudaFuncSetAttribute(tf32_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
@@ -336,12 +342,12 @@ int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int 
   if (P.rbox > 256) P.rbox = 256;
   const int mtiles = (R + P.rbox - 1) / P.rbox;
   P.BN = (N % 64 == 0 && mtiles * (N / 64) >= 120) ? 64 : (N % 32 == 0 ? 32 : 16);
-  P.bias = bias; P.out = out; P.accum = accum;
+  P.bias = bias; P.out = out; P.accum = accum; P.Tout = Tout; P.ostride = ostride; P.ooff = ooff;
   const CUtensorMap *mA0, *mA1, *mW;
   int rc;
-  if ((rc = tf_map(h, in0, c0, Tp, R, Tp, P.rbox, &mA0))) return rc;
+  if ((rc = tf_map(h, in0, c0, Ta, R, Tp, P.rbox, &mA0, false, tstride))) return rc;
   mA1 = mA0;
-  if (c1 > 0 && (rc = tf_map(h, in1, c1, Tp, R, Tp, P.rbox, &mA1))) return rc;
+  if (c1 > 0 && (rc = tf_map(h, in1, c1, Ta, R, Tp, P.rbox, &mA1, false, tstride))) return rc;
   if ((rc = tf_map(h, w, c0 + c1, N, planes, P.BN, 1, &mW))) return rc;
   dim3 grid(mtiles, N / P.BN);
   tf32_conv_kernel<<<grid, TF_THREADS, TF_SMEM, s>>>(*mA0, *mA1, *mW, P);
@@ -360,9 +366,11 @@ bool tfwgrad_supported(int c0, int c1, int cout, int Tp, int R) {
   return c0 > 0 && c0 % 32 == 0 && c1 % 32 == 0 && cout % 64 == 0 && rb > 0 && rb <= R;
 }
 
-// partials of dW[tap][ci][co] (tap i reads in[r, t + toff[i], :]) -> part [splits][ntaps][cin][cout]; *splits_out for the reduce
-int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Tp, const float* dout, int cout, int ntaps,
-                   const int* toff, float* part, size_t part_floats, int max_splits, int R, int* splits_out, cudaStream_t s) {
+// partials of dW[tap][ci][co] = sum_{r, j < Tp} in[r, j * a_stride + toff[tap], ci] * dout[r, j * d_stride + d_toff, co]
+// (in = [R, Ta, c0 (+ c1)], dout = [R, Td, cout]) -> part [splits][ntaps][cin][cout]; *splits_out for the reduce
+int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int c1, int Ta, int a_stride, int Tp, const float* dout, int Td,
+                   int d_stride, int d_toff, int cout, int ntaps, const int* toff, float* part, size_t part_floats, int max_splits, int R,
+                   int* splits_out, cudaStream_t s) {
   TfState* st = tf_of(h);
   if (!st->attr_set_w) {
     CLD_CUDA_OK(h, cudaFuncSetAttribute(tf32_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
@@ -371,7 +379,7 @@ int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int
   TfWgrad P;
   P.ntaps = ntaps;
   for (int i = 0; i < 5; ++i) P.toff[i] = i < ntaps ? toff[i] : 0;
-  P.c0 = c0; P.cin = c0 + c1; P.cout = cout; P.Tp = Tp; P.R = R; P.part = part;
+  P.c0 = c0; P.cin = c0 + c1; P.cout = cout; P.Tp = Tp; P.R = R; P.part = part; P.d_toff = d_toff;
   P.rbox = tfwgrad_rbox(Tp);
   P.nbox = (R + P.rbox - 1) / P.rbox;
   const int tiles = ((P.cin + 127) / 128) * (cout / 64) * ntaps;
@@ -386,10 +394,10 @@ int tfwgrad_launch(CldHandle* h, const float* in0, int c0, const float* in1, int
   P.splits = splits;
   const CUtensorMap *mA0, *mA1, *mD;
   int rc;
-  if ((rc = tf_map(h, in0, c0, Tp, R, Tp, P.rbox, &mA0, true))) return rc;
+  if ((rc = tf_map(h, in0, c0, Ta, R, Tp, P.rbox, &mA0, true, a_stride))) return rc;
   mA1 = mA0;
-  if (c1 > 0 && (rc = tf_map(h, in1, c1, Tp, R, Tp, P.rbox, &mA1, true))) return rc;
-  if ((rc = tf_map(h, dout, cout, Tp, R, Tp, P.rbox, &mD, true))) return rc;
+  if (c1 > 0 && (rc = tf_map(h, in1, c1, Ta, R, Tp, P.rbox, &mA1, true, a_stride))) return rc;
+  if ((rc = tf_map(h, dout, cout, Td, R, Tp, P.rbox, &mD, true, d_stride))) return rc;
   dim3 grid((P.cin + 127) / 128, cout / 64, ntaps * splits);
   tf32_wgrad_kernel<<<grid, TF_THREADS, TW_SMEM, s>>>(*mA0, *mA1, *mD, P);
   CLD_LAUNCH_OK(h, "tf32_wgrad_kernel");
