@@ -284,6 +284,7 @@ def ppo_update_rate(dev, skip_cpu, rows=128, iters=20, warmup=3):
         loss, _ = dm.ppo_minibatch_grad(x1, x0, cond, t, lp_old, reward, 0.0, 0.2)
         opt.step()
         return loss
+
     def timed():
         for _ in range(warmup):
             step()
@@ -297,12 +298,23 @@ def ppo_update_rate(dev, skip_cpu, rows=128, iters=20, warmup=3):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters, (eng.launch_count() - l0) // iters
-    ms, launches = timed()
+    ms_eager, launches = timed()
+    # the same update captured as a CUDA graph (cld_b200.trainer.GraphedPPOStep: what GuideDMTrainer runs)
+    from cld_b200.trainer import GraphedPPOStep
+    gs = GraphedPPOStep(dm, opt, rows, 0.2, eager_calls=0)
+    for dst, src in zip(gs.buffers(), (x0, x1, lp_old, reward, cond)):
+        dst.copy_(src)
+    gs.t.copy_(t)
+    eager_step = step
+    step = lambda: gs(0.0)        # noqa: E731
+    ms, _ = timed()
+    step = eager_step
     dm.train_precision = "fp32"
     ms32, launches32 = timed()
     out = {"rows": rows, "ms_per_minibatch_update": ms, "updates_per_s": 1e3 / ms, "iters": iters,
            "dtype": "tf32 tensor-core convolutions (tcgen05 kind::tf32, fp32 accumulate), fp32 elsewhere",
-           "gpu_launches_per_update": launches,
+           "mode": "one CUDA-graph replay per update (forward, log-prob, surrogate, backward on two streams, Adam, weight re-pack)",
+           "gpu_launches_per_update": launches, "ms_per_minibatch_update_without_graph": ms_eager,
            "algorithmic_gflop_per_update": 3 * 119.23e-3 * rows, "achieved_tflops": 3 * 119.23e6 * rows / (ms * 1e-3) / 1e12,
            "ppo_update_s": "%.1f s for the reference's 10 epochs x 300 minibatches" % (3000 * ms * 1e-3),
            "fp32_parity_mode": {"ms_per_minibatch_update": ms32, "gpu_launches_per_update": launches32, "dtype": "fp32 (CUDA cores)"}}

@@ -24,7 +24,7 @@ def __getattr__(name):
     if name in ("ReplayBuffer", "ppo_surrogate"):
         from . import replay
         return getattr(replay, name)
-    if name in ("GuideDMTrainer", "FusedAdam", "warmup_cosine"):
+    if name in ("GuideDMTrainer", "FusedAdam", "GraphedPPOStep", "warmup_cosine"):
         from . import trainer
         return getattr(trainer, name)
     if name in ("GuidedDiffusionPolicy", "choose_action_from_guidance"):

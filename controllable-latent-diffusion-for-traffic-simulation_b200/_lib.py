@@ -18,7 +18,7 @@ EXPORTS = [
     "cld_set_schedule", "cld_unet_forward", "cld_unet_debug_stage", "cld_posterior_step", "cld_add_noise",
     "cld_decode_rollout", "cld_unicycle", "cld_indicators", "cld_guidance_step", "cld_sample",
     "cld_launch_count", "cld_profile_begin", "cld_profile_end", "cld_tc_selftest",
-    "cld_unet_train_forward", "cld_unet_backward", "cld_ppo_head", "cld_mse_head", "cld_ppo_grad", "cld_adam_step", "cld_train_set_precision",
+    "cld_unet_train_forward", "cld_unet_backward", "cld_ppo_head", "cld_mse_head", "cld_ppo_grad", "cld_adam_step", "cld_adam_step_dev", "cld_train_set_precision",
     "cld_context_create", "cld_context_destroy", "cld_context_last_error", "cld_context_load", "cld_context_forward", "cld_context_forward_history",
     "cld_context_launch_count", "cld_context_conv_flops",
 ]
@@ -75,11 +75,12 @@ def _load():
     f32 = C.c_float
     lib.cld_unet_train_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.cld_unet_backward.argtypes = [vp, vp, C.POINTER(vp), i32, vp, i32, vp]
-    lib.cld_ppo_head.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, i32, vp]
+    lib.cld_ppo_head.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp, f32, vp, vp, vp, i32, vp]
     lib.cld_mse_head.argtypes = [vp, vp, vp, vp, vp, i32, vp]
-    lib.cld_ppo_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, f32, C.POINTER(vp), i32, vp, vp, i32, vp]
+    lib.cld_ppo_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp, f32, C.POINTER(vp), i32, vp, vp, i32, vp]
     f64 = C.c_double
     lib.cld_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, f64, f64, f64, f64, f64, i32, vp]
+    lib.cld_adam_step_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int64, vp, vp, f64, f64, f64, f64, vp]
     lib.cld_train_set_precision.argtypes = [vp, i32]
     lib.cld_unet_debug_stage.argtypes = [vp, i32, vp, i32, vp]
     lib.cld_posterior_step.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]

@@ -205,6 +205,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   h->env_lstm_prof = getenv("CLD_LSTM_PROF") != nullptr;
   h->env_map_stats = getenv("CLD_MAP_STATS") != nullptr;
   h->env_map_exhaustive = getenv("CLD_MAP_EXHAUSTIVE") != nullptr;
+  h->env_train_serial = getenv("CLD_TRAIN_SERIAL") != nullptr;
   if (const char* e = getenv("CLD_LSTM_PF")) h->env_lstm_pf = atoi(e);
   const int T = cfg->horizon;
   const size_t MR = cfg->max_rows;
@@ -454,6 +455,7 @@ int cld_set_schedule(CldHandle* h, const float* x_t_cof, const float* noise_cof,
   auto opt = [&](std::vector<float>& v, const float* p) { if (p) v.assign(p, p + n); else v.assign(n, 0.f); };
   opt(sc.sqrt_recip, sqrt_recip); opt(sc.sqrt_recipm1, sqrt_recipm1); opt(sc.sqrt_acp, sqrt_acp); opt(sc.sqrt_1macp, sqrt_1macp);
   sc.loaded = true;
+  ++h->sched_version;
   return CLD_OK;
 }
 
@@ -497,12 +499,13 @@ int cld_unet_backward(CldHandle* h, const float* d_eps, float* const* grads, int
 }
 
 int cld_ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
-                 const float* reward, float baseline, float clip_eps, float* logp_new_out, float* loss_out, float* d_eps_out, int R,
-                 void* stream) {
+                 const float* reward, float baseline, const float* baseline_dev, float clip_eps, float* logp_new_out, float* loss_out,
+                 float* d_eps_out, int R, void* stream) {
   int rc = check_rows(h, R);
   if (rc) return rc;
   if (!eps || !x_t || !x_tm1 || !t || !logp_old || !reward) return fail(h, CLD_ERR_ARG, "null argument");
-  return ppo_head(h, eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps, logp_new_out, loss_out, d_eps_out, R, (cudaStream_t)stream);
+  return ppo_head(h, eps, x_t, x_tm1, t, logp_old, reward, baseline, baseline_dev, clip_eps, logp_new_out, loss_out, d_eps_out, R,
+                  (cudaStream_t)stream);
 }
 
 int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps_out, int R, void* stream) {
@@ -513,8 +516,8 @@ int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss
 }
 
 int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float* cond, const int64_t* t, const float* logp_old,
-                 const float* reward, float baseline, float clip_eps, float* const* grads, int n, float* logp_new_out, float* loss_out,
-                 int R, void* stream) {
+                 const float* reward, float baseline, const float* baseline_dev, float clip_eps, float* const* grads, int n,
+                 float* logp_new_out, float* loss_out, int R, void* stream) {
   int rc = check_rows(h, R);
   if (rc) return rc;
   if (!x_t || !x_tm1 || !cond || !t || !logp_old || !reward || !grads) return fail(h, CLD_ERR_ARG, "null argument");
@@ -522,10 +525,19 @@ int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = unet_train_forward(h, x_t, cond, t, h->ws_eps, R, s))) return rc;
   float* d_eps = train_deps_buffer(h);
-  if ((rc = ppo_head(h, h->ws_eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps, logp_new_out, loss_out, d_eps, R, s))) return rc;
+  if ((rc = ppo_head(h, h->ws_eps, x_t, x_tm1, t, logp_old, reward, baseline, baseline_dev, clip_eps, logp_new_out, loss_out, d_eps, R, s)))
+    return rc;
   for (int i = 0; i < n; ++i)
     if (!grads[i]) return fail(h, CLD_ERR_ARG, "gradient pointer %d is null", i);
   return unet_train_backward(h, d_eps, grads, n, nullptr, R, s);
+}
+
+int cld_adam_step_dev(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, const double* lr_dev,
+                      int64_t* step_dev, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+  if (!h || !params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return fail(h, CLD_ERR_ARG, "null argument");
+  if (numel < 1) return fail(h, CLD_ERR_ARG, "numel must be positive");
+  return adam_step_dev(h, params, grads, exp_avg, exp_avg_sq, (size_t)numel, lr_dev, (long long*)step_dev, beta1, beta2, eps, weight_decay,
+                       (cudaStream_t)stream);
 }
 
 int cld_train_set_precision(CldHandle* h, int tf32) {

@@ -143,6 +143,7 @@ struct CldHandle {
   bool use_lstm_tc = false;
   // denoiser training state (opaque, owned by kernels_unet_train.cu): activation stash + gradient scratch, allocated on first use
   void* train = nullptr;
+  unsigned long long sched_version = 0;   // bumped by cld_set_schedule
   // fused re-pack: the jobs recorded during the first cld_load_unet, and their device copy
   std::vector<cld::PackJob> pack_jobs;
   cld::PackJob* pack_jobs_dev = nullptr;
@@ -153,6 +154,7 @@ struct CldHandle {
   void* train_tc = nullptr;        // tensor-map cache of the tf32 tensor-core convolutions (train_tc.cu)
   bool train_tf32 = false;         // cld_train_set_precision: stride-1 convolutions of the training step on the tensor pipe
   // debug switches, read from the environment ONCE at cld_create (never inside the step path)
+  bool env_train_serial = false;   // CLD_TRAIN_SERIAL=1: parameter gradients on the caller's stream instead of the handle's second stream
   bool env_lstm_bwd_simt = false, env_guidance_nofork = false, env_lstm_prof = false, env_map_stats = false, env_map_exhaustive = false;
   int env_lstm_pf = 3;
 };
@@ -200,7 +202,10 @@ int gn_mish_launch(CldHandle* h, const float* in, const GnW& n, const float* tbi
 int unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R, cudaStream_t s);
 int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, int n, float* dx_out, int R, cudaStream_t s);
 int ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
-             const float* reward, float baseline, float clip, float* logp_new, float* loss_out, float* d_eps, int R, cudaStream_t s);
+             const float* reward, float baseline, const float* baseline_dev, float clip, float* logp_new, float* loss_out, float* d_eps, int R,
+             cudaStream_t s);
+int adam_step_dev(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, const double* lr_dev, long long* step_dev, double b1,
+                  double b2, double eps, double wd, cudaStream_t s);
 int mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps, int R, cudaStream_t s);
 int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, double lr, double b1, double b2, double eps, double wd,
               int step, cudaStream_t s);

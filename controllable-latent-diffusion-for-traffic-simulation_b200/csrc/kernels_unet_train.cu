@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(128) time_mlp_bwd_kernel(const int64_t* __rest
 __global__ void __launch_bounds__(128) ppo_head_kernel(const float* __restrict__ eps, const float* __restrict__ x_t,
                                                        const float* __restrict__ x_tm1, const int64_t* __restrict__ t,
                                                        const float* __restrict__ sched, int n_t, const float* __restrict__ logp_old,
-                                                       const float* __restrict__ reward, float baseline, float clip,
+                                                       const float* __restrict__ reward, float baseline,
+                                                       const float* __restrict__ baseline_dev, float clip,
                                                        float* __restrict__ logp_new, float* __restrict__ loss_row,
                                                        float* __restrict__ d_eps, int n, int R) {
   __shared__ float red[4];
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(128) ppo_head_kernel(const float* __restrict__
   __syncthreads();
   const float logp = ((red[0] + red[1]) + (red[2] + red[3])) / (float)n;
   const float ratio = expf(logp - logp_old[r]);
-  const float A = reward[r] - baseline;
+  const float A = reward[r] - (baseline_dev ? baseline_dev[0] : baseline);
   const float s1 = ratio * A, s2 = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip) * A;
   const bool inside = ratio >= 1.f - clip && ratio <= 1.f + clip;
   float gl = 0.f;                                   // d min(s1, s2) / d logp
@@ -534,9 +535,10 @@ __global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__
 // torch.optim.Adam (no amsgrad; weight_decay added to the gradient), one flat parameter vector
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, size_t n, float step_size, float w1, float b2, float w2, float eps,
-                                                   float wd, float bc2_sqrt) {
+                                                   float wd, float bc2_sqrt, const float* __restrict__ dyn) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
+  if (dyn) { step_size = dyn[0]; bc2_sqrt = dyn[1]; }
   const float pi = p[i];
   const float gi = fmaf(wd, pi, g[i]);
   const float mi = m[i] + (gi - m[i]) * w1;                       // torch: exp_avg.lerp_(grad, 1 - beta1)
@@ -544,6 +546,14 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] = pi - step_size * (mi / denom);
+}
+
+// step counter and learning rate live on the device (a CUDA graph of the update replays with changing step / lr): one thread
+// advances the step and derives the two scalars of this step in double, as torch does on the host
+__global__ void adam_tick_kernel(long long* __restrict__ step, const double* __restrict__ lr, double b1, double b2, float* __restrict__ dyn) {
+  const long long st = ++step[0];
+  dyn[0] = (float)(lr[0] / (1.0 - pow(b1, (double)st)));
+  dyn[1] = (float)sqrt(1.0 - pow(b2, (double)st));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -557,14 +567,27 @@ struct TrainState {
   float* arena = nullptr;
   BlkStash blk[12];
   float *p0 = nullptr, *p1 = nullptr, *q0 = nullptr, *q1 = nullptr, *fA = nullptr, *fB = nullptr, *tmpR = nullptr;
-  float *gA = nullptr, *gB = nullptr, *gX = nullptr, *gY = nullptr, *gcat8 = nullptr, *gcat10 = nullptr;
+  float *gB = nullptr, *gcat8 = nullptr, *gcat10 = nullptr;
+  // The parameter gradients (weight-gradient GEMMs, split reductions, column sums) run on a second stream beside the data-gradient
+  // chain.  What they read is never overwritten during a backward: every GroupNorm backward has its own dA / per-row partial buffers,
+  // every layer its own data-gradient buffer; the scratch they share (part, bias_part, colpart) is touched by that stream only.
+  static constexpr int MAX_UNITS = 26, MAX_GD = 20, N_EVENTS = 64;
+  float* gA_u[MAX_UNITS] = {nullptr};
+  float* rp_u[MAX_UNITS] = {nullptr};
+  float* gD[MAX_GD] = {nullptr};
+  int unit = 0, nd = 0;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t evs[N_EVENTS] = {nullptr};
+  unsigned ev_next = 0;
   float *dtbias = nullptr, *dtcm = nullptr, *emb = nullptr, *hid = nullptr, *dpre1 = nullptr, *dpre2 = nullptr;
-  float *rp = nullptr, *loss_row = nullptr, *deps = nullptr;
+  float *loss_row = nullptr, *deps = nullptr;
   float* part = nullptr;  size_t part_floats = 0;
   float* colpart = nullptr;
   float* bias_part = nullptr;      // [MAX_SPLITS][256] split partials of a convolution's bias gradient
   float* tb_bgrad = nullptr;       // [tb_total] bias gradient of the concatenated time / cond projection
   float* sched_dev = nullptr;
+  unsigned long long sched_version = ~0ull;     // h->sched_version the device copy was made from
+  float* adam_dyn = nullptr;                    // [2] step size, sqrt of the second bias correction (graph-replayable Adam)
   const float* x = nullptr;
   const int64_t* t = nullptr;
   int R = 0;
@@ -581,6 +604,10 @@ void train_destroy(CldHandle* h) {
   if (st->colpart) cudaFree(st->colpart);
   if (st->bias_part) cudaFree(st->bias_part);
   if (st->sched_dev) cudaFree(st->sched_dev);
+  if (st->adam_dyn) cudaFree(st->adam_dyn);
+  if (st->aux) cudaStreamDestroy(st->aux);
+  for (cudaEvent_t e : st->evs)
+    if (e) cudaEventDestroy(e);
   delete st;
   h->train = nullptr;
 }
@@ -604,7 +631,12 @@ static int train_prepare(CldHandle* h, int R) {
     CLD_CUDA_OK(h, cudaMalloc((void**)&st->colpart, (size_t)(COLSUM_BLOCKS + 1) * CLD_TB_TOTAL_MAX * sizeof(float)));
     st->tb_bgrad = st->colpart + (size_t)COLSUM_BLOCKS * CLD_TB_TOTAL_MAX;
     CLD_CUDA_OK(h, cudaMalloc((void**)&st->bias_part, (size_t)MAX_SPLITS * 256 * sizeof(float)));
+    if (!h->env_train_serial) {
+      CLD_CUDA_OK(h, cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+      for (cudaEvent_t& e : st->evs) CLD_CUDA_OK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     CLD_CUDA_OK(h, cudaMalloc((void**)&st->sched_dev, (size_t)3 * c.n_timesteps * sizeof(float)));
+    CLD_CUDA_OK(h, cudaMalloc((void**)&st->adam_dyn, 2 * sizeof(float)));
   }
   if (R <= st->cap_rows) return 0;
   if (st->arena) { cudaFree(st->arena); st->arena = nullptr; st->cap_rows = 0; }
@@ -617,17 +649,19 @@ static int train_prepare(CldHandle* h, int R) {
   }
   if (tb_total > CLD_TB_TOTAL_MAX) return fail(h, CLD_ERR_UNSUPPORTED, "time-bias width %d above %d", tb_total, CLD_TB_TOTAL_MAX);
   if (td > 64) return fail(h, CLD_ERR_UNSUPPORTED, "the denoiser backward needs base_dim <= 64");
-  // 12 blocks x 4 + p0 p1 q0 q1 fA fB tmpR + gA gB gX gY + 2 x 2 (concat gradients) = 63 E, + the small per-row vectors
-  const size_t per_row = 63 * E + (size_t)tb_total + 64 + td + 4 * td + 4 * td + td + 3 * 256 + 1 + (size_t)c.horizon * c.latent_dim;
+  // 12 blocks x 4 + p0 p1 q0 q1 fA fB tmpR + gB + 2 x 2 (concat gradients) = 60 E, + 26 dA + 20 data-gradient buffers, + the small per-row vectors
+  const size_t per_row = (60 + TrainState::MAX_UNITS + TrainState::MAX_GD) * E + (size_t)TrainState::MAX_UNITS * 768 + (size_t)tb_total + 64 + td + 4 * td + 4 * td + td + 1 + (size_t)c.horizon * c.latent_dim;
   const size_t cap = (size_t)R;
   CLD_CUDA_OK(h, cudaMalloc((void**)&st->arena, per_row * cap * sizeof(float)));
   float* p = st->arena;
   auto take = [&](size_t per) { float* q = p; p += per * cap; return q; };
   for (int b = 0; b < 12; ++b) { st->blk[b].A0 = take(E); st->blk[b].B0 = take(E); st->blk[b].A1 = take(E); st->blk[b].OUT = take(E); }
   st->p0 = take(E); st->p1 = take(E); st->q0 = take(E); st->q1 = take(E); st->fA = take(E); st->fB = take(E); st->tmpR = take(E);
-  st->gA = take(E); st->gB = take(E); st->gX = take(E); st->gY = take(E); st->gcat8 = take(2 * E); st->gcat10 = take(2 * E);
+  st->gB = take(E); st->gcat8 = take(2 * E); st->gcat10 = take(2 * E);
+  for (int i = 0; i < TrainState::MAX_UNITS; ++i) { st->gA_u[i] = take(E); st->rp_u[i] = take(768); }
+  for (int i = 0; i < TrainState::MAX_GD; ++i) st->gD[i] = take(E);
   st->dtbias = take(tb_total); st->dtcm = take(64); st->emb = take(td); st->hid = take(4 * td); st->dpre1 = take(4 * td);
-  st->dpre2 = take(td); st->rp = take(768); st->loss_row = take(1);
+  st->dpre2 = take(td); st->loss_row = take(1);
   st->deps = take((size_t)c.horizon * c.latent_dim);
   st->cap_rows = R;
   st->fwd_valid = false;
@@ -637,6 +671,24 @@ static int train_prepare(CldHandle* h, int R) {
 static const int kOff5[5] = {-2, -1, 0, 1, 2};
 static const int kOff3[5] = {-1, 0, 1, 0, 0};
 static const int kOff1[5] = {0, 0, 0, 0, 0};
+
+// the parameter-gradient stream, ordered after everything enqueued on `s` so far (or `s` itself under CLD_TRAIN_SERIAL=1)
+static cudaStream_t pg_stream(CldHandle* h, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  if (!st->aux) return s;
+  cudaEvent_t e = st->evs[st->ev_next++ % TrainState::N_EVENTS];
+  cudaEventRecord(e, s);
+  cudaStreamWaitEvent(st->aux, e, 0);
+  return st->aux;
+}
+// the caller's stream waits for the parameter-gradient stream
+static void pg_join(CldHandle* h, cudaStream_t s) {
+  TrainState* st = ts_of(h);
+  if (!st->aux) return;
+  cudaEvent_t e = st->evs[st->ev_next++ % TrainState::N_EVENTS];
+  cudaEventRecord(e, st->aux);
+  cudaStreamWaitEvent(s, e, 0);
+}
 
 // forward convolution  out = conv(in) (+ bias)
 static int conv_fwd(CldHandle* h, const ConvW& w, const float* in0, int c0, const float* in1, int c1, int Tin, float* out, int Tout,
@@ -797,12 +849,18 @@ int unet_train_forward(CldHandle* h, const float* x, const float* cond, const in
 }
 
 // gradient of GroupNorm+Mish: dA = d(conv output); gamma / beta gradients -> grads; optional time-bias gradient slice
-static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float* dA, float* dgamma, float* dbeta, float* dconv_bias,
+// *dA_out = this GroupNorm's own dA buffer (read later by the data gradient on `s` and by the weight gradient on the second stream)
+static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, float** dA_out, float* dgamma, float* dbeta, float* dconv_bias,
                   float* dtb, int T, int C, int R, cudaStream_t s) {
   TrainState* st = ts_of(h);
-  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, st->rp, dtb, h->unet.tb_total, T, C);
+  if (st->unit >= TrainState::MAX_UNITS) return fail(h, CLD_ERR_STATE, "internal: GroupNorm backward units exhausted");
+  float* dA = st->gA_u[st->unit];
+  float* rp = st->rp_u[st->unit];
+  ++st->unit;
+  *dA_out = dA;
+  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, rp, dtb, h->unet.tb_total, T, C);
   CLD_LAUNCH_OK(h, "gn_mish_bwd_kernel");
-  return colsum(h, st->rp, R, 3 * C, dgamma, s, C, dbeta, dconv_bias);
+  return colsum(h, rp, R, 3 * C, dgamma, pg_stream(h, s), C, dbeta, dconv_bias);
 }
 
 static const int kK5[5] = {0, 1, 2, 3, 4}, kK1[5] = {0, 0, 0, 0, 0}, kK3[5] = {0, 1, 2, 0, 0};
@@ -815,6 +873,7 @@ static int conv_param_grads(CldHandle* h, int cin_total, int cout, int ntaps, co
   int rc, splits;
   // db == nullptr: the bias gradient came out of the GroupNorm backward that produced `dout`
   bool bias_in_part;
+  s = pg_stream(h, s);
   if ((rc = conv_wgrad(h, cin_total, cout, ntaps, ntaps == 5 ? kOff5 : kOff1, in0, c0, in1, c1, T, dout, T, T, 1, 1, 0, R, &splits, s,
                        db != nullptr, &bias_in_part)))
     return rc;
@@ -830,13 +889,14 @@ static int block_bwd(CldHandle* h, int bi, const BlkIdx& ix, const float* dOUT, 
   const int T = b.T, C = rb.cout, cin = b.c0 + b.c1;
   int rc;
   // second Conv1dBlock
-  if ((rc = gn_bwd(h, b.A1, rb.n1, dOUT, st->gA, grads[ix.g1], grads[ix.b1], grads[ix.c1b], nullptr, T, C, R, s))) return rc;
-  if ((rc = conv_param_grads(h, C, C, 5, b.B0, C, nullptr, 0, T, st->gA, grads[ix.c1w], nullptr, R, s))) return rc;
-  if ((rc = conv_dgrad(h, rb.c1, 5, kTap5, kNeg5, st->gA, T, st->gB, T, C, T, 1, 1, 0, 0, R, s))) return rc;
+  float* gA;
+  if ((rc = gn_bwd(h, b.A1, rb.n1, dOUT, &gA, grads[ix.g1], grads[ix.b1], grads[ix.c1b], nullptr, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, C, C, 5, b.B0, C, nullptr, 0, T, gA, grads[ix.c1w], nullptr, R, s))) return rc;
+  if ((rc = conv_dgrad(h, rb.c1, 5, kTap5, kNeg5, gA, T, st->gB, T, C, T, 1, 1, 0, 0, R, s))) return rc;
   // first Conv1dBlock (+ time / cond bias)
-  if ((rc = gn_bwd(h, b.A0, rb.n0, st->gB, st->gA, grads[ix.g0], grads[ix.b0], grads[ix.c0b], st->dtbias + rb.tb_off, T, C, R, s))) return rc;
-  if ((rc = conv_param_grads(h, cin, C, 5, b.in0, b.c0, b.in1, b.c1, T, st->gA, grads[ix.c0w], nullptr, R, s))) return rc;
-  if ((rc = conv_dgrad(h, rb.c0, 5, kTap5, kNeg5, st->gA, T, dIN, T, cin, T, 1, 1, 0, 0, R, s))) return rc;
+  if ((rc = gn_bwd(h, b.A0, rb.n0, st->gB, &gA, grads[ix.g0], grads[ix.b0], grads[ix.c0b], st->dtbias + rb.tb_off, T, C, R, s))) return rc;
+  if ((rc = conv_param_grads(h, cin, C, 5, b.in0, b.c0, b.in1, b.c1, T, gA, grads[ix.c0w], nullptr, R, s))) return rc;
+  if ((rc = conv_dgrad(h, rb.c0, 5, kTap5, kNeg5, gA, T, dIN, T, cin, T, 1, 1, 0, 0, R, s))) return rc;
   // residual path
   if (rb.res.w) {
     if ((rc = conv_param_grads(h, cin, C, 1, b.in0, b.c0, b.in1, b.c1, T, dOUT, grads[ix.rw], grads[ix.rb], R, s))) return rc;
@@ -854,9 +914,10 @@ static int down_bwd(CldHandle* h, const ConvW& w, const float* in, int T, const 
   const int C = w.cout, Th = T / 2;
   int rc, splits;
   bool bias_in_part;
-  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, s, true, &bias_in_part))) return rc;
-  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, s, bias_in_part ? db : nullptr))) return rc;
-  if (!bias_in_part && (rc = colsum(h, dout, R * Th, C, db, s))) return rc;
+  cudaStream_t ps = pg_stream(h, s);
+  if ((rc = conv_wgrad(h, C, C, 3, kOff3, in, C, nullptr, 0, T, dout, Th, Th, 2, 1, 0, R, &splits, ps, true, &bias_in_part))) return rc;
+  if ((rc = wreduce(h, splits, 3, C, C, 0, C, dw, 3, kK3, 0, ps, bias_in_part ? db : nullptr))) return rc;
+  if (!bias_in_part && (rc = colsum(h, dout, R * Th, C, db, ps))) return rc;
   // forward: out[j] = sum_tap in[2j + tap - 1] W[tap].  even ti = 2m: tap 1, j = m;  odd ti = 2m + 1: tap 0 with j = m + 1, tap 2 with j = m
   const int te[5] = {1, 0, 0, 0, 0}, oe[5] = {0, 0, 0, 0, 0};
   const int to[5] = {0, 2, 0, 0, 0}, oo[5] = {1, 0, 0, 0, 0};
@@ -872,11 +933,12 @@ static int up_bwd(CldHandle* h, const ConvW* up, const float* in, int T, const f
   const int off_e[5] = {0, -1, 0, 0, 0}, off_o[5] = {1, 0, 0, 0, 0};
   const int kte[5] = {1, 3, 0, 0, 0}, kto[5] = {0, 2, 0, 0, 0};
   int rc, splits;
-  if ((rc = conv_wgrad(h, C, C, 2, off_e, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 0, R, &splits, s))) return rc;
-  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kte, 1, s))) return rc;
-  if ((rc = conv_wgrad(h, C, C, 2, off_o, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 1, R, &splits, s))) return rc;
-  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kto, 1, s))) return rc;
-  if ((rc = colsum(h, dout, R * 2 * T, C, db, s))) return rc;
+  cudaStream_t ps = pg_stream(h, s);
+  if ((rc = conv_wgrad(h, C, C, 2, off_e, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 0, R, &splits, ps))) return rc;
+  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kte, 1, ps))) return rc;
+  if ((rc = conv_wgrad(h, C, C, 2, off_o, in, C, nullptr, 0, T, dout, 2 * T, T, 1, 2, 1, R, &splits, ps))) return rc;
+  if ((rc = wreduce(h, splits, 2, C, C, 0, C, dw, 4, kto, 1, ps))) return rc;
+  if ((rc = colsum(h, dout, R * 2 * T, C, db, ps))) return rc;
   // dIn[ti] = sum_ph sum_tap dOut[2 (ti - io_ph[tap]) + ph] W_ph[tap]^T
   const int t01[5] = {0, 1, 0, 0, 0};
   const int ie[5] = {0, 2, 0, 0, 0};          // phase 0: -2 * {0, -1} + 0
@@ -919,68 +981,91 @@ int unet_train_backward(CldHandle* h, const float* d_eps, float* const* grads, i
   }
   int rc, splits;
   const BlkStash* b = st->blk;
-  float *gX = st->gX, *gY = st->gY;
+  st->unit = 0; st->nd = 0;
+  auto nb = [&]() -> float* { return st->gD[st->nd < TrainState::MAX_GD ? st->nd++ : TrainState::MAX_GD - 1]; };   // a fresh data-gradient buffer
+  float *g, *g2, *gA;
   // ---- final_conv: Conv1d(1x1) <- Conv1dBlock
   if ((rc = conv_param_grads(h, d0, D, 1, st->fB, d0, nullptr, 0, T, d_eps, grads[i_fin[4]], grads[i_fin[5]], R, s))) return rc;
+  g = nb();
   {
     const int tap0[5] = {0, 0, 0, 0, 0};
-    if ((rc = conv_dgrad(h, u.fin1, 1, tap0, kOff1, d_eps, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;
+    if ((rc = conv_dgrad(h, u.fin1, 1, tap0, kOff1, d_eps, T, g, T, d0, T, 1, 1, 0, 0, R, s))) return rc;
   }
-  if ((rc = gn_bwd(h, st->fA, u.fin0n, gX, st->gA, grads[i_fin[2]], grads[i_fin[3]], grads[i_fin[1]], nullptr, T, d0, R, s))) return rc;
-  if ((rc = conv_param_grads(h, d0, d0, 5, st->q1, d0, nullptr, 0, T, st->gA, grads[i_fin[0]], nullptr, R, s))) return rc;
-  if ((rc = conv_dgrad(h, u.fin0, 5, kTap5, kNeg5, st->gA, T, gX, T, d0, T, 1, 1, 0, 0, R, s))) return rc;          // gX = d q1
+  if ((rc = gn_bwd(h, st->fA, u.fin0n, g, &gA, grads[i_fin[2]], grads[i_fin[3]], grads[i_fin[1]], nullptr, T, d0, R, s))) return rc;
+  if ((rc = conv_param_grads(h, d0, d0, 5, st->q1, d0, nullptr, 0, T, gA, grads[i_fin[0]], nullptr, R, s))) return rc;
+  g = nb();
+  if ((rc = conv_dgrad(h, u.fin0, 5, kTap5, kNeg5, gA, T, g, T, d0, T, 1, 1, 0, 0, R, s))) return rc;               // g = d q1
   // ---- ups.1: upsample, blocks 11, 10
-  if ((rc = up_bwd(h, u.up[1], b[11].OUT, T2, gX, gY, grads[i_up[1][0]], grads[i_up[1][1]], R, s))) return rc;      // gY = d o11
-  if ((rc = block_bwd(h, 11, ix[11], gY, gX, grads, R, s))) return rc;                                              // gX = d o10
-  if ((rc = block_bwd(h, 10, ix[10], gX, st->gcat10, grads, R, s))) return rc;                                      // (d q0 | d sk1)
-  if ((rc = slice(h, gX, st->gcat10, (size_t)R * T2, d1, 2 * d1, 0, 0, s))) return rc;                              // gX = d q0
+  g2 = nb();
+  if ((rc = up_bwd(h, u.up[1], b[11].OUT, T2, g, g2, grads[i_up[1][0]], grads[i_up[1][1]], R, s))) return rc;       // g2 = d o11
+  g = nb();
+  if ((rc = block_bwd(h, 11, ix[11], g2, g, grads, R, s))) return rc;                                               // g = d o10
+  if ((rc = block_bwd(h, 10, ix[10], g, st->gcat10, grads, R, s))) return rc;                                       // (d q0 | d sk1)
+  g = nb();
+  if ((rc = slice(h, g, st->gcat10, (size_t)R * T2, d1, 2 * d1, 0, 0, s))) return rc;                               // g = d q0
   // ---- ups.0: upsample, blocks 9, 8
-  if ((rc = up_bwd(h, u.up[0], b[9].OUT, T4, gX, gY, grads[i_up[0][0]], grads[i_up[0][1]], R, s))) return rc;       // gY = d o9
-  if ((rc = block_bwd(h, 9, ix[9], gY, gX, grads, R, s))) return rc;                                                // gX = d o8
-  if ((rc = block_bwd(h, 8, ix[8], gX, st->gcat8, grads, R, s))) return rc;                                         // (d o7 | d sk2)
-  if ((rc = slice(h, gX, st->gcat8, (size_t)R * T4, d2, 2 * d2, 0, 0, s))) return rc;                               // gX = d o7
+  g2 = nb();
+  if ((rc = up_bwd(h, u.up[0], b[9].OUT, T4, g, g2, grads[i_up[0][0]], grads[i_up[0][1]], R, s))) return rc;        // g2 = d o9
+  g = nb();
+  if ((rc = block_bwd(h, 9, ix[9], g2, g, grads, R, s))) return rc;                                                 // g = d o8
+  if ((rc = block_bwd(h, 8, ix[8], g, st->gcat8, grads, R, s))) return rc;                                          // (d o7 | d sk2)
+  g = nb();
+  if ((rc = slice(h, g, st->gcat8, (size_t)R * T4, d2, 2 * d2, 0, 0, s))) return rc;                                // g = d o7
   // ---- mid blocks 7, 6
-  if ((rc = block_bwd(h, 7, ix[7], gX, gY, grads, R, s))) return rc;                                                // gY = d o6
-  if ((rc = block_bwd(h, 6, ix[6], gY, gX, grads, R, s))) return rc;                                                // gX = d o5 (mid part)
-  if ((rc = slice(h, gX, st->gcat8, (size_t)R * T4, d2, 2 * d2, d2, 1, s))) return rc;                              // + skip part
+  g2 = nb();
+  if ((rc = block_bwd(h, 7, ix[7], g, g2, grads, R, s))) return rc;                                                 // g2 = d o6
+  g = nb();
+  if ((rc = block_bwd(h, 6, ix[6], g2, g, grads, R, s))) return rc;                                                 // g = d o5 (mid part)
+  if ((rc = slice(h, g, st->gcat8, (size_t)R * T4, d2, 2 * d2, d2, 1, s))) return rc;                               // + skip part
   // ---- downs.2: blocks 5, 4
-  if ((rc = block_bwd(h, 5, ix[5], gX, gY, grads, R, s))) return rc;                                                // gY = d o4
-  if ((rc = block_bwd(h, 4, ix[4], gY, gX, grads, R, s))) return rc;                                                // gX = d p1
+  g2 = nb();
+  if ((rc = block_bwd(h, 5, ix[5], g, g2, grads, R, s))) return rc;                                                 // g2 = d o4
+  g = nb();
+  if ((rc = block_bwd(h, 4, ix[4], g2, g, grads, R, s))) return rc;                                                 // g = d p1
   // ---- downs.1: downsample, blocks 3, 2
-  if ((rc = down_bwd(h, u.down[1], b[3].OUT, T2, gX, gY, grads[i_down[1][0]], grads[i_down[1][1]], R, s))) return rc;   // gY = d o3 (down part)
-  if ((rc = slice(h, gY, st->gcat10, (size_t)R * T2, d1, 2 * d1, d1, 1, s))) return rc;                             // + skip part
-  if ((rc = block_bwd(h, 3, ix[3], gY, gX, grads, R, s))) return rc;                                                // gX = d o2
-  if ((rc = block_bwd(h, 2, ix[2], gX, gY, grads, R, s))) return rc;                                                // gY = d p0
+  g2 = nb();
+  if ((rc = down_bwd(h, u.down[1], b[3].OUT, T2, g, g2, grads[i_down[1][0]], grads[i_down[1][1]], R, s))) return rc;    // g2 = d o3 (down part)
+  if ((rc = slice(h, g2, st->gcat10, (size_t)R * T2, d1, 2 * d1, d1, 1, s))) return rc;                             // + skip part
+  g = nb();
+  if ((rc = block_bwd(h, 3, ix[3], g2, g, grads, R, s))) return rc;                                                 // g = d o2
+  g2 = nb();
+  if ((rc = block_bwd(h, 2, ix[2], g, g2, grads, R, s))) return rc;                                                 // g2 = d p0
   // ---- downs.0: downsample, blocks 1, 0
-  if ((rc = down_bwd(h, u.down[0], b[1].OUT, T, gY, gX, grads[i_down[0][0]], grads[i_down[0][1]], R, s))) return rc;    // gX = d o1
-  if ((rc = block_bwd(h, 1, ix[1], gX, gY, grads, R, s))) return rc;                                                // gY = d o0
-  if ((rc = block_bwd(h, 0, ix[0], gY, gX, grads, R, s))) return rc;                                                // gX = d x [R,T,4]
-  if (dx_out) CLD_CUDA_OK(h, cudaMemcpyAsync(dx_out, gX, (size_t)R * T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  // ---- time / cond projections of the 12 blocks: tbias = tcm @ tb_w + tb_b  (tb_w packed [tdim][tb_total])
+  g = nb();
+  if ((rc = down_bwd(h, u.down[0], b[1].OUT, T, g2, g, grads[i_down[0][0]], grads[i_down[0][1]], R, s))) return rc;     // g = d o1
+  g2 = nb();
+  if ((rc = block_bwd(h, 1, ix[1], g, g2, grads, R, s))) return rc;                                                 // g2 = d o0
+  g = nb();
+  if ((rc = block_bwd(h, 0, ix[0], g2, g, grads, R, s))) return rc;                                                 // g = d x [R,T,4]
+  if (dx_out) CLD_CUDA_OK(h, cudaMemcpyAsync(dx_out, g, (size_t)R * T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // ---- time / cond projections of the 12 blocks: tbias = tcm @ tb_w + tb_b  (tb_w packed [tdim][tb_total]); everything from here
+  //      on is parameter-gradient work: on the second stream, after the last GroupNorm backward has written its slice of dtbias
+  cudaStream_t ps = pg_stream(h, s);
   const int tbt = u.tb_total;
-  if ((rc = conv_wgrad(h, tdim, tbt, 1, kOff1, h->tcm, tdim, nullptr, 0, 1, st->dtbias, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
+  if ((rc = conv_wgrad(h, tdim, tbt, 1, kOff1, h->tcm, tdim, nullptr, 0, 1, st->dtbias, 1, 1, 1, 1, 0, R, &splits, ps))) return rc;
   for (int e = 0; e < 12; ++e)
-    if ((rc = wreduce(h, splits, 1, tdim, tbt, u.rb[e].tb_off, u.rb[e].cout, grads[ix[e].tw], 1, kK1, 0, s))) return rc;
-  if ((rc = colsum(h, st->dtbias, R, tbt, st->tb_bgrad, s))) return rc;
+    if ((rc = wreduce(h, splits, 1, tdim, tbt, u.rb[e].tb_off, u.rb[e].cout, grads[ix[e].tw], 1, kK1, 0, ps))) return rc;
+  if ((rc = colsum(h, st->dtbias, R, tbt, st->tb_bgrad, ps))) return rc;
   for (int e = 0; e < 12; ++e)
     CLD_CUDA_OK(h, cudaMemcpyAsync(grads[ix[e].tb], st->tb_bgrad + u.rb[e].tb_off, u.rb[e].cout * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s));
+                                   cudaMemcpyDeviceToDevice, ps));
   // d(Mish(time embedding)) = dtbias @ tb_w[0:td, :]^T   (the cond half of tcm is an input, not a parameter)
   {
     ConvW tb; tb.w = u.tb_w; tb.cin = tdim; tb.cout = tbt; tb.ntaps = 1;
     const int tap0[5] = {0, 0, 0, 0, 0};
-    if ((rc = conv_dgrad(h, tb, 1, tap0, kOff1, st->dtbias, 1, st->dtcm, 1, td, 1, 1, 1, 0, 0, R, s))) return rc;
+    if ((rc = conv_dgrad(h, tb, 1, tap0, kOff1, st->dtbias, 1, st->dtcm, 1, td, 1, 1, 1, 0, 0, R, ps))) return rc;
   }
-  time_mlp_bwd_kernel<<<R, 128, 0, s>>>(st->t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, st->dtcm, td, st->emb, st->hid, st->dpre1,
-                                        st->dpre2, td);
+  time_mlp_bwd_kernel<<<R, 128, 0, ps>>>(st->t, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, st->dtcm, td, st->emb, st->hid, st->dpre1,
+                                         st->dpre2, td);
   CLD_LAUNCH_OK(h, "time_mlp_bwd_kernel");
   // Linear(d, 4d): weight [4d][d];  Linear(4d, d): weight [d][4d]
-  if ((rc = conv_wgrad(h, td, 4 * td, 1, kOff1, st->emb, td, nullptr, 0, 1, st->dpre1, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
-  if ((rc = wreduce(h, splits, 1, td, 4 * td, 0, 4 * td, grads[0], 1, kK1, 0, s))) return rc;
-  if ((rc = colsum(h, st->dpre1, R, 4 * td, grads[1], s))) return rc;
-  if ((rc = conv_wgrad(h, 4 * td, td, 1, kOff1, st->hid, 4 * td, nullptr, 0, 1, st->dpre2, 1, 1, 1, 1, 0, R, &splits, s))) return rc;
-  if ((rc = wreduce(h, splits, 1, 4 * td, td, 0, td, grads[2], 1, kK1, 0, s))) return rc;
-  if ((rc = colsum(h, st->dpre2, R, td, grads[3], s))) return rc;
+  if ((rc = conv_wgrad(h, td, 4 * td, 1, kOff1, st->emb, td, nullptr, 0, 1, st->dpre1, 1, 1, 1, 1, 0, R, &splits, ps))) return rc;
+  if ((rc = wreduce(h, splits, 1, td, 4 * td, 0, 4 * td, grads[0], 1, kK1, 0, ps))) return rc;
+  if ((rc = colsum(h, st->dpre1, R, 4 * td, grads[1], ps))) return rc;
+  if ((rc = conv_wgrad(h, 4 * td, td, 1, kOff1, st->hid, 4 * td, nullptr, 0, 1, st->dpre2, 1, 1, 1, 1, 0, R, &splits, ps))) return rc;
+  if ((rc = wreduce(h, splits, 1, 4 * td, td, 0, td, grads[2], 1, kK1, 0, ps))) return rc;
+  if ((rc = colsum(h, st->dpre2, R, td, grads[3], ps))) return rc;
+  pg_join(h, s);                 // the gradients are complete in the caller's stream order
   return 0;
 }
 
@@ -996,13 +1081,17 @@ static int upload_schedule(CldHandle* h, cudaStream_t s) {
 }
 
 int ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
-             const float* reward, float baseline, float clip, float* logp_new, float* loss_out, float* d_eps, int R, cudaStream_t s) {
+             const float* reward, float baseline, const float* baseline_dev, float clip, float* logp_new, float* loss_out, float* d_eps, int R,
+             cudaStream_t s) {
   int rc;
   if ((rc = train_prepare(h, R))) return rc;
-  if ((rc = upload_schedule(h, s))) return rc;
+  if (ts_of(h)->sched_version != h->sched_version) {         // host -> device copy only when the schedule changed (never inside a CUDA graph)
+    if ((rc = upload_schedule(h, s))) return rc;
+    ts_of(h)->sched_version = h->sched_version;
+  }
   TrainState* st = ts_of(h);
   const int n = h->cfg.horizon * h->cfg.latent_dim;
-  ppo_head_kernel<<<R, 128, 0, s>>>(eps, x_t, x_tm1, t, st->sched_dev, h->cfg.n_timesteps, logp_old, reward, baseline, clip, logp_new,
+  ppo_head_kernel<<<R, 128, 0, s>>>(eps, x_t, x_tm1, t, st->sched_dev, h->cfg.n_timesteps, logp_old, reward, baseline, baseline_dev, clip, logp_new,
                                     st->loss_row, d_eps, n, R);
   CLD_LAUNCH_OK(h, "ppo_head_kernel");
   if (loss_out) {
@@ -1034,7 +1123,20 @@ int adam_step(CldHandle* h, float* p, const float* g, float* m, float* v, size_t
   const float step_size = (float)(lr / (1.0 - pow(b1, (double)step)));
   const float bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)step));
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, step_size, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps,
-                                                          (float)wd, bc2_sqrt);
+                                                          (float)wd, bc2_sqrt, nullptr);
+  CLD_LAUNCH_OK(h, "adam_kernel");
+  return 0;
+}
+
+int adam_step_dev(CldHandle* h, float* p, const float* g, float* m, float* v, size_t n, const double* lr_dev, long long* step_dev, double b1,
+                  double b2, double eps, double wd, cudaStream_t s) {
+  int rc;
+  if ((rc = train_prepare(h, 1))) return rc;
+  TrainState* st = ts_of(h);
+  adam_tick_kernel<<<1, 1, 0, s>>>(step_dev, lr_dev, b1, b2, st->adam_dyn);
+  CLD_LAUNCH_OK(h, "adam_tick_kernel");
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, 0.f, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps, (float)wd,
+                                                          1.f, st->adam_dyn);
   CLD_LAUNCH_OK(h, "adam_kernel");
   return 0;
 }

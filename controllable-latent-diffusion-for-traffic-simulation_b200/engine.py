@@ -249,7 +249,7 @@ class Engine:
         return dx
 
     @_on_device
-    def ppo_head(self, eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps=0.2, want_grad=True):
+    def ppo_head(self, eps, x_t, x_tm1, t, logp_old, reward, baseline, clip_eps=0.2, want_grad=True, baseline_dev=None):
         """-> (logp_new [R], loss [1], d_eps [R,T,D] or None): DmModel.log_prob's tail + the clipped surrogate and its gradient."""
         eps, x_t, x_tm1 = _f32(eps, self.device), _f32(x_t, self.device), _f32(x_tm1, self.device)
         logp_old, reward = _f32(logp_old, self.device), _f32(reward, self.device)
@@ -258,7 +258,7 @@ class Engine:
         logp, loss = torch.empty(R, device=self.device), torch.empty(1, device=self.device)
         d_eps = torch.empty_like(eps) if want_grad else None
         self._check(lib.cld_ppo_head(self._h, _ptr(eps), _ptr(x_t), _ptr(x_tm1), _ptr(t), _ptr(logp_old), _ptr(reward), float(baseline),
-                                     float(clip_eps), _ptr(logp), _ptr(loss), _ptr(d_eps), R, self._stream()), "cld_ppo_head")
+                                     _ptr(baseline_dev), float(clip_eps), _ptr(logp), _ptr(loss), _ptr(d_eps), R, self._stream()), "cld_ppo_head")
         return logp, loss, d_eps
 
     @_on_device
@@ -271,7 +271,7 @@ class Engine:
         return loss, d_eps
 
     @_on_device
-    def ppo_grad(self, x_t, x_tm1, cond, t, logp_old, reward, baseline, grads, clip_eps=0.2):
+    def ppo_grad(self, x_t, x_tm1, cond, t, logp_old, reward, baseline, grads, clip_eps=0.2, baseline_dev=None):
         """One minibatch of ppo_update up to `opt.step()`: -> (logp_new [R], loss [1]); the gradients land in `grads`."""
         x_t, x_tm1, cond = _f32(x_t, self.device), _f32(x_tm1, self.device), _f32(cond, self.device)
         logp_old, reward = _f32(logp_old, self.device), _f32(reward, self.device)
@@ -279,8 +279,8 @@ class Engine:
         R = x_t.shape[0]
         logp, loss = torch.empty(R, device=self.device), torch.empty(1, device=self.device)
         self._check(lib.cld_ppo_grad(self._h, _ptr(x_t), _ptr(x_tm1), _ptr(cond), _ptr(t), _ptr(logp_old), _ptr(reward), float(baseline),
-                                     float(clip_eps), self._grad_ptrs(grads), len(grads), _ptr(logp), _ptr(loss), R, self._stream()),
-                    "cld_ppo_grad")
+                                     _ptr(baseline_dev), float(clip_eps), self._grad_ptrs(grads), len(grads), _ptr(logp), _ptr(loss), R,
+                                     self._stream()), "cld_ppo_grad")
         return logp, loss
 
     @_on_device
@@ -292,6 +292,14 @@ class Engine:
         self._check(lib.cld_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), float(lr),
                                       float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), self._stream()),
                     "cld_adam_step")
+
+    @_on_device
+    def adam_step_dev(self, params, grads, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """Adam with the step counter (int64 [1], incremented by the call) and the learning rate (float64 [1]) on the device: replayable
+        inside a CUDA graph."""
+        self._check(lib.cld_adam_step_dev(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), _ptr(lr_dev),
+                                          _ptr(step_dev), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), self._stream()),
+                    "cld_adam_step_dev")
 
     @_on_device
     def posterior_step(self, x, eps, noise, t, t_next=-1, sampler="ddpm", want_mean=False):

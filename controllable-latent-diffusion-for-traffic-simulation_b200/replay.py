@@ -58,9 +58,14 @@ class ReplayBuffer:
         # without replacement, like random.sample
         return torch.randperm(self._size, device=self.device, generator=generator)[:batch_size]
 
-    def sample(self, batch_size, generator=None):
-        """-> (x0 [b,T,D], x1 [b,T,D], log_p_old [b], reward [b], cond_feat [b,C]) on the device."""
+    def sample(self, batch_size, generator=None, out=None):
+        """-> (x0 [b,T,D], x1 [b,T,D], log_p_old [b], reward [b], cond_feat [b,C]) on the device; `out`: five preallocated tensors to
+        gather into (the static inputs of a CUDA graph)."""
         idx = self._indices(batch_size, generator)
+        if out is not None:
+            for b, o in zip(self._bufs, out):
+                torch.index_select(b, 0, idx, out=o)
+            return tuple(out)
         return tuple(b.index_select(0, idx) for b in self._bufs)
 
     def sample_tuples(self, batch_size, generator=None):

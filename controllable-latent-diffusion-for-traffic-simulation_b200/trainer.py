@@ -43,6 +43,66 @@ class FusedAdam:
         self.dm.mark_parameters_changed()
 
 
+class GraphedPPOStep:
+    """One minibatch iteration of ppo_update -- cld_ppo_grad (forward, log-prob, surrogate, backward on two streams), cld_adam_step_dev
+    and the one-launch weight re-pack -- captured ONCE as a CUDA graph and replayed: at the 128-row minibatch the ~280 launches of an
+    update are bound by the host's launch rate, not by the GPU.  Inputs are copied into static buffers; the scalars that change between
+    replays (reward baseline, learning rate, Adam step) live in device memory.  The first `eager_calls` calls run un-captured (they
+    create the handle's scratch, tensor maps and kernel attributes); results are bit-identical to the un-captured path."""
+
+    def __init__(self, dm, opt, rows, clip_eps=0.2, eager_calls=2):
+        self.dm, self.opt, self.rows, self.clip, self.eager_left = dm, opt, int(rows), float(clip_eps), int(eager_calls)
+        dev = opt.flat.device
+        z = lambda *sh, dt=torch.float32: torch.zeros(*sh, device=dev, dtype=dt)      # noqa: E731
+        self.x0, self.x1 = z(rows, dm.horizon, dm.latent_size), z(rows, dm.horizon, dm.latent_size)
+        self.cond, self.t = z(rows, dm.cond_dim), z(rows, dt=torch.long)
+        self.log_p_old, self.reward = z(rows), z(rows)
+        self.baseline, self.lr, self.step = z(1), z(1, dt=torch.float64), z(1, dt=torch.long)
+        self.graph, self.loss, self.log_p = None, None, None
+        self._lr_host = self._base_host = None
+
+    def buffers(self):
+        """(x0, x1, log_p_old, reward, cond): sample the replay buffer straight into these (ReplayBuffer.sample(out=...))."""
+        return self.x0, self.x1, self.log_p_old, self.reward, self.cond
+
+    def _body(self, eng):
+        log_p, loss = eng.ppo_grad(self.x1, self.x0, self.cond, self.t, self.log_p_old, self.reward, 0.0, self.dm._flat_views[1], self.clip,
+                                   baseline_dev=self.baseline)
+        o = self.opt
+        eng.adam_step_dev(o.flat, o.grad, o.exp_avg, o.exp_avg_sq, self.lr, self.step, o.betas, o.eps, o.weight_decay)
+        eng.load_unet(self.dm.model.state_dict())          # loaded handle: the one-launch re-pack
+        return loss, log_p
+
+    def __call__(self, baseline, t=None):
+        """The static buffers hold the minibatch.  -> loss [1] (valid until the next call)."""
+        dm, o = self.dm, self.opt
+        if t is not None:
+            self.t.copy_(t)
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            loss, _ = dm.ppo_minibatch_grad(self.x1, self.x0, self.cond, self.t, self.log_p_old, self.reward, baseline, self.clip)
+            o.step()
+            return loss.clone()
+        if baseline != self._base_host:
+            self.baseline.fill_(baseline)
+            self._base_host = baseline
+        if o.lr != self._lr_host:
+            self.lr.fill_(o.lr)
+            self._lr_host = o.lr
+        if self.graph is None:
+            eng = dm.train_engine(self.rows)                 # weights current, precision set: nothing left to do at replay time
+            self.step.fill_(o.step_count)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.log_p = self._body(eng)
+        self.graph.replay()
+        o.step_count += 1
+        dm.mark_parameters_changed()                         # the sampling engine re-packs on its next use ...
+        dm._train_sig = dm._weights_signature()              # ... the training handle was re-packed inside the graph
+        return self.loss
+
+
 def warmup_cosine(epoch, total_epochs):
     """lr factor of guide_dm_trainer.py:67-75."""
     warm = total_epochs / 3
@@ -54,7 +114,7 @@ def warmup_cosine(epoch, total_epochs):
 
 class GuideDMTrainer:
     def __init__(self, dm, vae, algo_config, *, batch_size, learning_rate=1e-4, weight_decay=0.0, epochs=30, fused=True,
-                 ppo_epochs=10, clip_eps=0.2, buffer_max=None, sample_kw=None, generator=None, train_precision="tf32"):
+                 ppo_epochs=10, clip_eps=0.2, buffer_max=None, sample_kw=None, generator=None, train_precision="tf32", cuda_graph=True):
         self.dm, self.vae, self.algo_config = dm, vae, algo_config
         self.batch_size = int(batch_size)
         self.num_samp = int(algo_config.num_samp)
@@ -78,6 +138,8 @@ class GuideDMTrainer:
         else:
             self.optimizer = torch.optim.Adam(dm.model.parameters(), lr=learning_rate, weight_decay=weight_decay)
         self._base_lr = float(learning_rate)
+        self.cuda_graph = bool(cuda_graph) and self.fused
+        self._graphed = None
 
     # ---- configure_optimizers' LambdaLR, stepped once per epoch (guide_dm_trainer.py:76-83)
     def on_epoch_end(self):
@@ -116,8 +178,14 @@ class GuideDMTrainer:
         losses = []
         for _ in range(self.ppo_epochs):
             for _ in range(self.ppo_update_times):
-                x0, x1, log_p_old, reward, cond = self.replay_buffer.sample(self.ppo_mini_batch, self.generator)
                 baseline = self.replay_buffer.get_baseline()
+                if self.cuda_graph:
+                    if self._graphed is None:
+                        self._graphed = GraphedPPOStep(self.dm, self.optimizer, self.ppo_mini_batch, self.clip_eps)
+                    self.replay_buffer.sample(self.ppo_mini_batch, self.generator, out=self._graphed.buffers())
+                    losses.append(self._graphed(baseline).reshape(()).clone())      # t stays 0 (guide_dm_trainer.py:160)
+                    continue
+                x0, x1, log_p_old, reward, cond = self.replay_buffer.sample(self.ppo_mini_batch, self.generator)
                 t = torch.zeros(x0.shape[0], device=x0.device, dtype=torch.long)
                 losses.append(self.ppo_minibatch(x0, x1, log_p_old, reward, cond, t, baseline))
         return torch.stack(losses).mean()

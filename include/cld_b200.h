@@ -152,16 +152,22 @@ int cld_unet_backward(CldHandle* h, const float* d_eps, float* const* grads, int
 
 /* PPO head: logp_new[r] = mean_{T,D} Normal(x_t_cof[t] x_t - noise_cof[t] eps, exp(.5 logvar[t])).log_prob(x_tm1),
  * loss = -(1/R) sum_r min(ratio A, clamp(ratio, 1-clip, 1+clip) A), ratio = exp(logp_new - logp_old), A = reward - baseline;
- * d_eps_out [R,T,D] = d(loss)/d(eps).  logp_new_out [R], loss_out [1], d_eps_out may be NULL. */
+ * d_eps_out [R,T,D] = d(loss)/d(eps).  logp_new_out [R], loss_out [1], d_eps_out may be NULL.  baseline_dev (may be NULL): the baseline
+ * as ONE device float, read by the kernel instead of `baseline` -- for callers that replay the update as a CUDA graph. */
 int cld_ppo_head(CldHandle* h, const float* eps, const float* x_t, const float* x_tm1, const int64_t* t, const float* logp_old,
-                 const float* reward, float baseline, float clip_eps, float* logp_new_out, float* loss_out, float* d_eps_out, int R,
-                 void* stream);
+                 const float* reward, float baseline, const float* baseline_dev, float clip_eps, float* logp_new_out, float* loss_out,
+                 float* d_eps_out, int R, void* stream);
 /* F.mse_loss(noise, eps) of DmModel.compute_losses (models/dm/dm_model.py:83-90) and its gradient d_eps_out (may be NULL). */
 int cld_mse_head(CldHandle* h, const float* eps, const float* noise, float* loss_out, float* d_eps_out, int R, void* stream);
 /* forward + PPO head + backward in one call (the body of one minibatch iteration of ppo_update up to `opt.step()`). */
 int cld_ppo_grad(CldHandle* h, const float* x_t, const float* x_tm1, const float* cond, const int64_t* t, const float* logp_old,
-                 const float* reward, float baseline, float clip_eps, float* const* grads, int n, float* logp_new_out, float* loss_out,
-                 int R, void* stream);
+                 const float* reward, float baseline, const float* baseline_dev, float clip_eps, float* const* grads, int n,
+                 float* logp_new_out, float* loss_out, int R, void* stream);
+/* The same step with the step counter (int64, incremented by the call) and the learning rate (double) in DEVICE memory, so that a
+ * captured CUDA graph of the whole update (cld_ppo_grad + this + cld_load_unet on the loaded handle) can be replayed: no host-side
+ * scalar changes between replays. */
+int cld_adam_step_dev(CldHandle* h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel, const double* lr_dev,
+                      int64_t* step_dev, double beta1, double beta2, double eps, double weight_decay, void* stream);
 /* tf32 != 0: the stride-1 convolutions of the training step (forward and data gradient) run on the tensor pipe (tcgen05 kind::tf32,
  * fp32 operands read with 10 mantissa bits, fp32 accumulation); 0 (default): everything in fp32 on the CUDA cores (1e-4 parity mode). */
 int cld_train_set_precision(CldHandle* h, int tf32);

@@ -236,6 +236,40 @@ def test_compute_losses_mse_vs_reference_golden(dm16, gold):
     assert rel(d_eps, 2 * (eps - nz) / eps.numel()) < 1e-6
 
 
+def test_graph_replay_equals_eager_updates(models_cpu, gold):
+    """GraphedPPOStep (the update captured as a CUDA graph: two streams inside, device-side baseline / lr / step) reproduces the
+    parameters of the same sequence of un-captured updates bit for bit."""
+    from cld_b200.trainer import FusedAdam, GraphedPPOStep
+    g = gold("ppo")
+    finals = []
+    for use_graph in (False, True):
+        dm, _, _ = models_cpu(16)
+        dm = dm.cuda()
+        dm.train_precision = "tf32"
+        for p in dm.model.parameters():
+            p.requires_grad_(True)
+        opt = FusedAdam(dm, lr=1e-4, weight_decay=1e-5)
+        x1, x0, cond, t, lp_old, reward, baseline, clip = _ppo_inputs(g)
+        gs = GraphedPPOStep(dm, opt, x1.shape[0], clip) if use_graph else None
+        losses = []
+        for it in range(6):
+            xs = x1 + 0.01 * it                                   # a different minibatch every iteration
+            base = baseline + 0.1 * (it // 3)                     # the baseline and the learning rate change between replays
+            opt.lr = 1e-4 * (1.0 if it < 4 else 0.5)
+            if use_graph:
+                for dst, src in zip(gs.buffers(), (x0, xs, lp_old, reward, cond)):
+                    dst.copy_(src)
+                losses.append(float(gs(base, t)))
+            else:
+                loss, _ = dm.ppo_minibatch_grad(xs, x0, cond, t, lp_old, reward, base, clip)
+                opt.step()
+                losses.append(float(loss))
+        assert opt.step_count == 6
+        finals.append((losses, dm._flat.clone()))
+    assert finals[0][0] == finals[1][0], (finals[0][0], finals[1][0])
+    assert torch.equal(finals[0][1], finals[1][1])
+
+
 def test_adam_kernel_vs_torch(dm16):
     dm, _, _ = dm16
     eng = dm.train_engine(1)
