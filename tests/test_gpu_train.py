@@ -123,6 +123,28 @@ def test_tf32_tensor_core_mode_vs_oracle(models_cpu):
     assert rel(e32, eps_want.detach()[:10]) < 2e-5
 
 
+def test_backward_single_row_and_tf32_horizon_104(models_cpu):
+    """Edge shapes: ONE row in fp32 mode (every GEMM has a single partial tile; the tensor-pipe weight gradient needs whole boxes and
+    falls back per layer), and T = 104 on the tensor pipe (boxes of 1 / 2 / 4 rows)."""
+    from cld_b200 import default_algo_config
+    from cld_b200.dm_model import DmModel
+    for T, R, mode, tol in ((52, 1, "fp32", GRAD_TOL), (52, 3, "tf32", 1e-2), (104, 9, "tf32", 1e-2)):
+        algo = default_algo_config(horizon=T)
+        torch.manual_seed(0)
+        dm = DmModel(algo, {"image": (34, 224, 224)}, n_timesteps=16).cuda()
+        dm.train_precision = mode
+        torch.manual_seed(60 + R)
+        x, cond, t, d_eps = torch.randn(R, T, 4), torch.randn(R, 256), torch.randint(0, 16, (R,)), torch.randn(R, T, 4)
+        sd = {k: v.requires_grad_(True) for k, v in cpu_sd(dm.model).items()}
+        want = torch.autograd.grad((O.unet_forward(sd, x, cond, t) * d_eps).sum(), list(sd.values()))
+        eng = dm.train_engine(R)
+        eng.unet_train_forward(x.cuda(), cond.cuda(), t.cuda())
+        grads = [torch.empty_like(p) for p in dm.model.parameters()]
+        eng.unet_backward(d_eps.cuda(), grads)
+        worst = max(rel(gr, w) for gr, w in zip(grads, want))
+        assert worst < tol, (T, R, mode, worst)
+
+
 def test_backward_horizon_104(models_cpu):
     """cfg3's horizon: T = 104 (levels of 104 / 52 / 26 slots)."""
     from cld_b200 import default_algo_config
