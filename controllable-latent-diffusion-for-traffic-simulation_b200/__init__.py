@@ -27,6 +27,9 @@ def __getattr__(name):
     if name in ("GuideDMTrainer", "FusedAdam", "GraphedPPOStep", "warmup_cosine"):
         from . import trainer
         return getattr(trainer, name)
+    if name in ("SyntheticEnv", "closed_loop_rollout"):
+        from . import rollout
+        return getattr(rollout, name)
     if name in ("GuidedDiffusionPolicy", "choose_action_from_guidance"):
         from . import policy
         return getattr(policy, name)

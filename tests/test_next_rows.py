@@ -239,3 +239,73 @@ def test_test_step_mirror_feeds_realism_statistics(models_cpu):
     traj_d = vae.convert_action_to_state_and_action(vae.lstmvae.lstm_dec(out["pred_traj"], ad["cond_feat"]), ad["curr_states"], descaled_output=True)
     want_r = compute_reward(dm, traj_d.reshape(S * A, 1, 52, 6), bd).mean()
     assert torch.isfinite(r) and abs(r.item() - want_r.item()) <= 1e-5 * max(1.0, abs(want_r.item()))
+
+
+# ---------------------------------------------------------------------------------------------------- f-3: closed-loop driver
+class _StraightPolicy:
+    """Stub of policy.get_action: every agent keeps its speed along its heading (agent frame: +x)."""
+
+    def __init__(self, T, dt):
+        self.T, self.dt = T, dt
+
+    def get_action(self, obs, num_action_samples=1, step_index=0, sampler="ddpm", aux_info=None, **kw):
+        v = obs["curr_speed"]
+        tt = torch.arange(1, self.T + 1, device=v.device).float() * self.dt
+        pos = torch.stack([v[:, None] * tt[None, :], torch.zeros(v.shape[0], self.T, device=v.device)], -1)
+        return {"positions": pos, "yaws": torch.zeros(v.shape[0], self.T, 1, device=v.device)}, \
+            {"act_idx": torch.zeros(v.shape[0], dtype=torch.long), "guide_losses": {}}
+
+
+def test_closed_loop_driver_and_synthetic_env_frames():
+    """rollout.py:95-100 on the synthetic environment (CPU, stub policy): observations are agent-centric (the newest history point
+    is the origin, heading 0), the drivable raster of an agent's frame agrees with the world road, a constant-velocity plan moves
+    every agent along its own heading by v * dt per step, the loop replans every n_step_action steps until is_done."""
+    from cld_b200.rollout import SyntheticEnv, closed_loop_rollout
+    env = SyntheticEnv(2, 3, num_steps=25, n_step_action=10, seed=4, device="cpu")
+    p0, yaw0, v0 = env.pos.clone(), env.yaw.clone(), env.speed.clone()
+    obs = env.get_observation()
+    B = 6
+    assert obs["history_positions"].shape == (B, 31, 2) and obs["drivable_map"].shape == (B, 224, 224)
+    assert obs["history_positions"][:, -1].abs().max() < 1e-4 and obs["history_yaws"][:, -1].abs().max() < 1e-6
+    assert torch.allclose(obs["agent_from_world"] @ obs["world_from_agent"], torch.eye(3).expand(B, 3, 3), atol=1e-5)
+    # raster pixel of the agent's own position: (col 56, row 112); its drivable flag = the world road test at the agent
+    assert torch.equal(obs["drivable_map"][:, 112, 56], env.drivable_world(env.pos))
+    # the others' futures, mapped back to the world, are the other agents' plans
+    back = torch.einsum('bij,bstj->bsti', obs["world_from_agent"][:, :2, :2], obs["all_other_agents_future_positions"]) + \
+        obs["world_from_agent"][:, None, None, :2, 2]
+    assert torch.allclose(back[0, 0], env.plan_world[1], atol=1e-3) and torch.allclose(back[1, 0], env.plan_world[0], atol=1e-3)
+    recs = closed_loop_rollout(env, _StraightPolicy(env.T, env.dt), lambda o: None)
+    assert [r["steps_taken"] for r in recs] == [10, 10, 5] and env.is_done() and env.t == 25
+    want = p0 + torch.stack([torch.cos(yaw0), torch.sin(yaw0)], 1) * (v0 * 25 * env.dt)[:, None]
+    assert torch.allclose(env.pos, want, atol=1e-3) and torch.allclose(env.speed, v0, atol=1e-3) and torch.allclose(env.yaw, yaw0)
+    assert torch.equal(env.pos[v0 == 0], p0[v0 == 0])                       # parked agents (zero action) stay where they are
+    m = env.metrics()
+    assert m["steps"] == 25 and 0.0 <= m["offroad_rate"] <= 1.0 and 0.0 <= m["collision_rate"] <= 1.0
+
+
+@pytest.mark.gpu
+def test_closed_loop_rollout_with_the_guided_sampler(models_cpu):
+    """The same loop with GuidedDiffusionPolicy.get_action on the B200 sampler (bf16, guided, 4 samples per agent, scene-level
+    choice): runs to the end, replans 3 times, is deterministic under a fixed device-RNG seed, parked agents stay parked."""
+    from cld_b200.policy import GuidedDiffusionPolicy
+    from cld_b200.rollout import SyntheticEnv, closed_loop_rollout
+    dm, vae, algo = models_cpu(10, precision="bf16")
+    dm = dm.cuda()
+    vae = vae.cuda().bind(dm)
+    pol = GuidedDiffusionPolicy(dm, vae, algo, guidance=dict(agent_collision=50.0, map_collision=1.0))
+    torch.manual_seed(3)
+    cond = torch.randn(8, 256, device="cuda")
+    finals = []
+    for _ in range(2):
+        env = SyntheticEnv(2, 4, num_steps=30, n_step_action=10, seed=7)
+        parked = env.speed == 0
+        p0 = env.pos.clone()
+        recs = closed_loop_rollout(env, pol, lambda o: {"cond_feat": cond, "curr_states": env.curr_states()}, num_action_samples=4,
+                                   use_device_rng=True, seed=11)
+        assert len(recs) == 3 and env.t == 30 and all(r["act_idx"].shape == (8,) for r in recs)
+        assert set(recs[0]["guide_losses"]) == {"agent_collision", "map_collision"}
+        assert torch.isfinite(env.pos).all() and torch.equal(env.pos[parked], p0[parked])
+        # scene-level choice: the agents of a scene share the sample index
+        assert all((r["act_idx"].view(2, 4) == r["act_idx"].view(2, 4)[:, :1]).all() for r in recs)
+        finals.append(env.pos.clone())
+    assert torch.equal(finals[0], finals[1])
