@@ -422,6 +422,13 @@ def guidance_loss_scene(x6, scene, g):
         l = speed_limit_loss(x6, g['speed_limit_value'])
         per['speed_limit'] = l.detach()
         tot = tot + l.mean() * g['speed_limit']
+    if g.get('waypoint', 0.0) != 0.0:
+        wp = {k[3:]: scene[k] for k in ('wp_target', 'wp_mode', 'wp_time', 'wp_dist')}
+        l = waypoint_loss(x6, wp, g.get('min_target_time', 0.0))
+        act = wp['mode'] != 0                         # the reference passes the guided agents as `agt_mask`: the mean is over them
+        per['waypoint'] = l.detach()
+        if act.any():
+            tot = tot + l[act].mean() * g['waypoint']
     return tot, per
 
 
@@ -707,3 +714,71 @@ def adam_update(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay
     v = betas[1] * v + (1 - betas[1]) * g * g
     bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
     return p - (lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps), m, v
+
+
+# =====================================================================================================================
+# waypoint guidance terms -- TargetPosAtTimeLoss (guidance_loss.py:630-670) and the global-target
+# losses GlobalTargetPosAtTimeLoss (:930-1031) / GlobalTargetPosLoss (:1033-1135) with compute_progress_loss (:876-927).
+# The reference's forward() is (a) host logic that turns world targets into per-agent (local target, branch) and (b) one of
+# four per-agent formulas; `waypoint_plan` restates (a), `waypoint_loss` (b).
+#   mode 0  no loss (target time passed, or the agent has reached its target: have_reached_mask)
+#   mode 1  || p[t*] - g ||                                   TargetPosAtTimeLoss
+#   mode 2  relu(|| p[T-1] - g || - goal_dist)                compute_progress_loss with tgt_time
+#   mode 3  relu(goal_dist - (|| p[0] - g || - || p[T-1] - g ||))      compute_progress_loss without tgt_time
+#   mode 4  TargetPosLoss(g)                                   the "within reach" branch of GlobalTargetPosLoss
+# =====================================================================================================================
+def _tf_points(pts, mat):
+    """geometry_utils.transform_points_tensor for pts [B,K,2], mat [B,3,3]."""
+    return torch.einsum('bij,bkj->bki', mat[:, :2, :2], pts) + mat[:, None, :2, 2]
+
+
+def waypoint_plan(kind, target_pos, T, dt, *, target_time=None, global_t=0, urgency=None, pref_speed=None, min_progress_dist=0.5,
+                  target_tolerance=None, action_num=5, agent_from_world=None, world_from_agent=None, agent_hist=None,
+                  have_reached=None):
+    """-> dict(target [B,2] agent frame, mode [B] long, time [B] long, dist [B], have_reached [B] bool)."""
+    B = target_pos.shape[0]
+    zero_l, zero_f = torch.zeros(B, dtype=torch.long), torch.zeros(B)
+    if kind == 'target_pos_at_time':                       # target already in the agent frame
+        return dict(target=target_pos.float(), mode=torch.ones(B, dtype=torch.long), time=target_time.long(), dist=zero_f,
+                    have_reached=torch.zeros(B, dtype=torch.bool))
+    local = _tf_points(target_pos[:, None].float(), agent_from_world)[:, 0]
+    if kind == 'global_target_pos_at_time':
+        ltt = target_time.long() - int(global_t)
+        exact = (ltt < T) & (ltt >= 0)
+        prog = (~exact) & (ltt >= 0)
+        goal = ltt.float() * dt * pref_speed * (1.0 - urgency)
+        mode = torch.where(exact, torch.ones_like(ltt), torch.where(prog, torch.full_like(ltt, 2), zero_l))
+        time = torch.where(exact, ltt, zero_l)
+        dist = torch.where(prog, goal, zero_f)
+    elif kind == 'global_target_pos':
+        exact = local.norm(dim=-1) < T * dt * pref_speed
+        goal = torch.maximum(urgency * (T * dt * pref_speed), torch.tensor([min_progress_dist]))
+        mode = torch.where(exact, torch.full((B,), 4, dtype=torch.long), torch.full((B,), 3, dtype=torch.long))
+        time, dist = zero_l, torch.where(exact, zero_f, goal)
+    else:
+        raise ValueError(kind)
+    reached = have_reached.clone() if have_reached is not None else torch.zeros(B, dtype=torch.bool)
+    if target_tolerance is not None:
+        # guidance_loss.py:1019-1026 as written: agent_hist is [B,H,F]; `[:,0]` keeps the OLDEST of the last `action_num` history points,
+        # and [B,2] - [B,1,2] broadcasts to [B,B,2]: the minimum runs over ALL agents' positions (agent j near agent b's target counts)
+        hist_w = _tf_points(agent_hist[:, -action_num:, :2], world_from_agent)[:, 0]
+        reached |= (hist_w[None, :, :] - target_pos[:, None, :]).norm(dim=-1).min(dim=-1)[0] < target_tolerance
+        mode = torch.where(reached, zero_l, mode)
+    return dict(target=local, mode=mode, time=time, dist=dist, have_reached=reached)
+
+
+def waypoint_loss(x, wp, min_target_time=0.0):
+    """x [B,N,T,6] -> [B,N]."""
+    pos = x[..., :2]
+    B, N, T = pos.shape[:3]
+    tgt, mode = wp['target'].to(pos), wp['mode']
+    ar = torch.arange(B)
+    d_at = (pos[ar, :, wp['time'].clamp(0, T - 1)] - tgt[:, None]).norm(dim=-1)
+    d_first = (pos[:, :, 0] - tgt[:, None]).norm(dim=-1)
+    d_last = (pos[:, :, -1] - tgt[:, None]).norm(dim=-1)
+    gd = wp['dist'].to(pos)[:, None]
+    l_tp = target_pos_loss(x, tgt, min_target_time)
+    zero = torch.zeros_like(d_at)
+    m = lambda k: (mode == k)[:, None]                                          # noqa: E731
+    return torch.where(m(1), d_at, zero) + torch.where(m(2), torch.relu(d_last - gd), zero) + \
+        torch.where(m(3), torch.relu(gd - (d_first - d_last)), zero) + torch.where(m(4), l_tp, zero)

@@ -517,6 +517,76 @@ def ppo_golden():
     print("ppo golden written: loss %.6f, ratios %s" % (float(loss), np.round(ratios.detach().numpy(), 3)))
 
 
+
+def waypoint_golden():
+    """the REAL TargetPosAtTimeLoss / GlobalTargetPosAtTimeLoss / GlobalTargetPosLoss (guidance_loss.py:630-670,
+    930-1135) on one scene of 8 agents x 3 samples -> tests/golden/waypoint.npz (inputs, the reference's losses [B,N] and the
+    gradient of their sum w.r.t. the trajectories); the oracle's plan + formula must agree."""
+    RH.install()
+    from tbsim.utils import guidance_loss as GL
+    torch.manual_seed(31)
+    B, N, T, dt = 8, 3, 52, 0.1
+    v = torch.rand(B, 1, 1) * 8 + 1
+    tt = torch.arange(1, T + 1).float() * dt
+    x = torch.zeros(B, N, T, 6)
+    x[..., 0] = v * tt + 0.3 * torch.randn(B, N, 1).cumsum(0) * tt
+    x[..., 1] = 0.4 * torch.randn(B, N, 1) * tt + 0.05 * torch.randn(B, N, T).cumsum(-1)
+    yaw = (torch.rand(B) * 2 - 1) * 3.0
+    pos = (torch.rand(B, 2) * 2 - 1) * 40
+    c, s_ = torch.cos(yaw), torch.sin(yaw)
+    wfa = torch.zeros(B, 3, 3)
+    wfa[:, 0, 0], wfa[:, 0, 1], wfa[:, 0, 2] = c, -s_, pos[:, 0]
+    wfa[:, 1, 0], wfa[:, 1, 1], wfa[:, 1, 2] = s_, c, pos[:, 1]
+    wfa[:, 2, 2] = 1
+    afw = torch.linalg.inv(wfa)
+    hist = torch.zeros(B, 31, 8)
+    hist[:, :, 0] = -(torch.arange(30, -1, -1).float() * dt)[None, :] * v[:, 0]           # straight past along -x in the agent frame
+    batch = {'agent_from_world': afw, 'world_from_agent': wfa, 'agent_hist': hist}
+    # world targets: ahead of every agent at different ranges; agents 6, 7 are AT their target (reached within the tolerance)
+    rng = torch.tensor([6.0, 15.0, 30.0, 60.0, 90.0, 12.0, 0.5, 1.0])
+    lat = torch.tensor([1.0, -2.0, 3.0, -4.0, 2.0, 0.5, 0.2, -0.3])
+    tgt_local = torch.stack([rng, lat], 1)
+    tgt_world = O._tf_points(tgt_local[:, None], wfa)[:, 0]
+    out = dict(x=x.numpy(), world_from_agent=wfa.numpy(), agent_from_world=afw.numpy(), agent_hist=hist.numpy(),
+               target_world=tgt_world.numpy(), target_local=tgt_local.numpy(), T=T, dt=dt)
+    cases = {}
+    # (1) TargetPosAtTimeLoss: local targets, per-agent time steps
+    t_at = torch.tensor([3, 10, 25, 51, 40, 0, 7, 30])
+    cases['at_time'] = (GL.TargetPosAtTimeLoss(tgt_local, t_at), dict(kind='target_pos_at_time', target_pos=tgt_local, target_time=t_at))
+    # (2) GlobalTargetPosAtTimeLoss at global_t = 5: exact (time within the horizon), progress (beyond), passed (negative), reached
+    t_gl = torch.tensor([20, 40, 80, 150, 3, 56, 30, 200])
+    urg = torch.tensor([0.0, 0.3, 0.5, 0.8, 0.2, 0.1, 0.4, 0.6])
+    pref = torch.tensor([1.5, 2.0, 3.0, 4.0, 2.5, 1.0, 2.0, 3.5])
+    l2 = GL.GlobalTargetPosAtTimeLoss(tgt_world.numpy(), t_gl.numpy(), urg.numpy(), pref.numpy(), dt=dt, target_tolerance=4.5, action_num=5)
+    l2.global_t = 5
+    cases['global_at_time'] = (l2, dict(kind='global_target_pos_at_time', target_pos=tgt_world, target_time=t_gl, global_t=5, urgency=urg,
+                                        pref_speed=pref, target_tolerance=4.5, action_num=5))
+    # (3) GlobalTargetPosLoss: within reach -> TargetPosLoss, else progress; reached agents masked
+    l3 = GL.GlobalTargetPosLoss(tgt_world.numpy(), urg.numpy(), pref.numpy(), dt=dt, min_progress_dist=0.5, target_tolerance=4.5, action_num=5)
+    cases['global'] = (l3, dict(kind='global_target_pos', target_pos=tgt_world, urgency=urg, pref_speed=pref, min_progress_dist=0.5,
+                                target_tolerance=4.5, action_num=5))
+    w_samp = torch.rand(B, N) + 0.5                            # a non-uniform weighting so that every entry's gradient is exercised
+    for tag, (ref_loss, kw) in cases.items():
+        xr = x.clone().requires_grad_(True)
+        l_ref = ref_loss(xr, batch, agt_mask=None)
+        (g_ref,) = torch.autograd.grad((l_ref * w_samp).sum(), xr)
+        wp = O.waypoint_plan(T=T, dt=dt, agent_from_world=afw, world_from_agent=wfa, agent_hist=hist, **kw)
+        xo = x.clone().requires_grad_(True)
+        l_or = O.waypoint_loss(xo, wp)
+        (g_or,) = torch.autograd.grad((l_or * w_samp).sum(), xo)
+        check("waypoint %s: loss (oracle vs reference)" % tag, l_or.detach(), l_ref.detach(), 1e-6)
+        check("waypoint %s: d/dx" % tag, g_or, g_ref, 1e-6)
+        print("   modes", wp['mode'].tolist(), "reached", wp['have_reached'].long().tolist())
+        if hasattr(ref_loss, 'have_reached_mask') and ref_loss.have_reached_mask is not None:
+            assert torch.equal(ref_loss.have_reached_mask[:, 0], wp['have_reached'])
+        out.update({tag + '_loss': l_ref.detach().numpy(), tag + '_grad': g_ref.numpy(), tag + '_mode': wp['mode'].numpy(),
+                    tag + '_time': wp['time'].numpy(), tag + '_dist': wp['dist'].numpy(), tag + '_target': wp['target'].numpy()})
+    out.update(w_samp=w_samp.numpy(), t_at=t_at.numpy(), t_gl=t_gl.numpy(), urgency=urg.numpy(), pref_speed=pref.numpy(), global_t=5,
+               target_tolerance=4.5, action_num=5, min_progress_dist=0.5)
+    np.savez_compressed(os.path.join(GOLD, "waypoint.npz"), **out)
+    print("waypoint golden written")
+
+
 if __name__ == "__main__":
     if "--only-choose" in sys.argv:
         choose_golden()
@@ -528,5 +598,7 @@ if __name__ == "__main__":
         context_golden()
     elif "--only-ppo" in sys.argv:
         ppo_golden()
+    elif "--only-waypoint" in sys.argv:
+        waypoint_golden()
     else:
         main()
