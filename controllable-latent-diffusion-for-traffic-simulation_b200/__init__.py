@@ -27,6 +27,9 @@ def __getattr__(name):
     if name in ("GuideDMTrainer", "FusedAdam", "GraphedPPOStep", "warmup_cosine"):
         from . import trainer
         return getattr(trainer, name)
+    if name in ("TargetPosAtTime", "GlobalTargetPosAtTime", "GlobalTargetPos"):
+        from . import waypoints
+        return getattr(waypoints, name)
     if name in ("SyntheticEnv", "closed_loop_rollout"):
         from . import rollout
         return getattr(rollout, name)

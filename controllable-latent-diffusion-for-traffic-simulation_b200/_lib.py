@@ -41,7 +41,7 @@ class CldGuidanceConfig(C.Structure):
         ("num_points_l", C.c_int32), ("num_points_w", C.c_int32), ("speed_th", C.c_float),
         ("min_target_time", C.c_float), ("optimizer", C.c_int32), ("lr", C.c_float),
         ("w_target_speed", C.c_float), ("w_acc_limit", C.c_float), ("acc_limit", C.c_float),
-        ("w_speed_limit", C.c_float), ("speed_limit", C.c_float),
+        ("w_speed_limit", C.c_float), ("speed_limit", C.c_float), ("w_waypoint", C.c_float),
     ]
 
 
@@ -52,6 +52,7 @@ class CldScene(C.Structure):
         ("curr_speed", C.c_void_p), ("drivable_map", C.c_void_p), ("map_h", C.c_int32), ("map_w", C.c_int32),
         ("target_pos", C.c_void_p), ("others_pos", C.c_void_p), ("others_avail", C.c_void_p),
         ("num_others", C.c_int32), ("map_packed", C.c_int32), ("target_speed", C.c_void_p),
+        ("wp_target", C.c_void_p), ("wp_mode", C.c_void_p), ("wp_time", C.c_void_p), ("wp_dist", C.c_void_p), ("wp_weight", C.c_void_p),
     ]
 
 

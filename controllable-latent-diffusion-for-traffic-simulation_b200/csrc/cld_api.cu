@@ -231,7 +231,7 @@ int cld_create(const CldConfig* cfg, CldHandle** out) {
   if (!rc) rc = dev_alloc(h, &h->ws_dacc, MR * T);
   if (!rc) rc = dev_alloc(h, &h->map_work, MR * T + 8);
   if (!rc && cudaMemset(h->map_work, 0, 8 * sizeof(int)) != cudaSuccess) rc = fail(h, CLD_ERR_CUDA, "cudaMemset of the map work list failed");
-  if (!rc) rc = dev_alloc(h, &h->ws_loss, 6 * MR);
+  if (!rc) rc = dev_alloc(h, &h->ws_loss, 7 * MR);
   if (!rc) rc = dev_alloc(h, &h->ws_eps, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_mean, MR * T * cfg->latent_dim);
   if (!rc) rc = dev_alloc(h, &h->ws_x, MR * T * cfg->latent_dim);
@@ -669,6 +669,12 @@ int cld_sample(CldHandle* h, const float* x_init, const float* noises, uint64_t 
       if (sub.target_pos) sub.target_pos += a0 * 2;
       if (sub.others_pos) sub.others_pos += a0 * scene->num_others * T * 2;
       if (sub.others_avail) sub.others_avail += a0 * scene->num_others * T;
+      if (sub.target_speed) sub.target_speed += a0 * T;
+      if (sub.wp_target) sub.wp_target += a0 * 2;
+      if (sub.wp_mode) sub.wp_mode += a0;
+      if (sub.wp_time) sub.wp_time += a0;
+      if (sub.wp_dist) sub.wp_dist += a0;
+      if (sub.wp_weight) sub.wp_weight += a0;
       sc = &sub;
     }
     const float* condc = cond + (size_t)r0 * c.cond_dim;

@@ -20,10 +20,13 @@ __device__ __forceinline__ float clipg(float x, float lo, float hi) { return fmi
 struct LossArgs {
   const float* traj;     // [R,T,6]
   float* dtraj;          // [R,T,4]  d/d(x, y, v, yaw)
-  float* loss;           // [6,R] or nullptr: agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit
+  float* loss;           // [7,R] or nullptr: agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit, waypoint
   float* dacc;           // [R,T] d/d(acc) of the acc-limit term (acc = de-scaled action, not a function of the rollout) or nullptr
   const float *extent, *wfa, *rfa, *speed, *target, *tspeed;
   float w_ts, w_al, acc_limit, w_sl, speed_limit;
+  // waypoint terms (per agent): local target [B,2], mode [B] (0 none | 1 at-time | 2 final-distance hinge | 3 progress hinge | 4 TargetPosLoss),
+  // time step [B], goal distance [B], per-agent multiplier [B] (A / number of guided agents of the scene: the reference averages over them)
+  const float *wp_target, *wp_dist, *wp_w; const int *wp_mode, *wp_time; float w_wp;
   const uint8_t* dmap; int H, W, packed;   // packed: rows of (W + 7) / 8 bytes, pixel x = bit (x & 7) of byte x >> 3
   int S, A, N, T, R;
   float w_ac, w_mc, w_tp;
@@ -43,6 +46,44 @@ __device__ __forceinline__ float linspace_at(float lo, float hi, int n, int i) {
   if (n == 1) return lo;
   float step = (hi - lo) / (float)(n - 1);
   return (i < n / 2) ? lo + step * (float)i : hi - step * (float)(n - 1 - i);
+}
+
+// TargetPosLoss.forward (guidance_loss.py:693-712) for one (agent, sample) row by one warp, lanes over time: adds kk * d(loss)/d(x, y)
+// to dtraj [T,4] and returns the loss (all lanes).  tr = traj row [T,6].
+__device__ __forceinline__ float target_pos_term(const float* __restrict__ tr, float* __restrict__ dtraj, float tx, float ty, int t0, int T,
+                                                 int lane, float kk) {
+  const int Tn = T - t0;
+  float dmin = 3.4e38f;
+  for (int t = t0 + lane; t < T; t += 32) {
+    float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+    dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+  float Z = 0.f, E = 0.f;
+  for (int t = t0 + lane; t < T; t += 32) {
+    float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+    float d2 = dx * dx + dy * dy, d = sqrtf(d2);
+    float e = expf(-(d - dmin));
+    Z += e; E += e * d2;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    Z += __shfl_xor_sync(0xffffffffu, Z, o);
+    E += __shfl_xor_sync(0xffffffffu, E, o);
+  }
+  E /= Z;
+  if (kk != 0.f) {
+    const float k2 = kk / (float)Tn;
+    for (int t = t0 + lane; t < T; t += 32) {
+      float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
+      float d2 = dx * dx + dy * dy, d = sqrtf(d2);
+      float sw = expf(-(d - dmin)) / Z;
+      float f = 2.f * sw + ((d > 0.f) ? sw * (E - d2) / d : 0.f);
+      dtraj[t * 4] += k2 * f * dx; dtraj[t * 4 + 1] += k2 * f * dy;
+    }
+  }
+  return E / (float)Tn;
 }
 
 __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
@@ -161,49 +202,63 @@ __global__ void __launch_bounds__(512) guidance_loss_grad_kernel(LossArgs a) {
   // ---------------- target position (softmin-weighted squared distance): warp per agent ------------
   if (a.w_tp != 0.f && a.target) {
     const int t0 = (int)(a.min_target_time * (float)T);
-    const int Tn = T - t0;
     for (int i = i_lo + warp; i < i_hi; i += nwarps) {
       const int g = ag0 + i;
       const size_t row = (size_t)g * N + n;
-      const float tx = a.target[g * 2 + 0], ty = a.target[g * 2 + 1];
       // stationary agents were detached in place by the agent-collision term (guidance_loss.py:511-515)
       const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);
-      const float* tr = a.traj + (size_t)row * T * 6;
-      float dmin = 3.4e38f;
-      for (int t = t0 + lane; t < T; t += 32) {
-        float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
-        dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-      float Z = 0.f, E = 0.f;
-      for (int t = t0 + lane; t < T; t += 32) {
-        float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
-        float d2 = dx * dx + dy * dy, d = sqrtf(d2);
-        float e = expf(-(d - dmin));
-        Z += e; E += e * d2;
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        Z += __shfl_xor_sync(0xffffffffu, Z, o);
-        E += __shfl_xor_sync(0xffffffffu, E, o);
-      }
-      E /= Z;
-      if (lane == 0 && a.loss) a.loss[2 * (size_t)a.R + row] = E / (float)Tn;
-      if (has_grad) {
-        float kk = a.w_tp * inv_AN / (float)Tn;
-        for (int t = t0 + lane; t < T; t += 32) {
-          float dx = tr[t * 6] - tx, dy = tr[t * 6 + 1] - ty;
-          float d2 = dx * dx + dy * dy, d = sqrtf(d2);
-          float sw = expf(-(d - dmin)) / Z;
-          float f = 2.f * sw + ((d > 0.f) ? sw * (E - d2) / d : 0.f);
-          float* o = a.dtraj + ((size_t)row * T + t) * 4;
-          o[0] += kk * f * dx; o[1] += kk * f * dy;
-        }
-      }
+      const float l = target_pos_term(a.traj + (size_t)row * T * 6, a.dtraj + (size_t)row * T * 4, a.target[g * 2 + 0], a.target[g * 2 + 1], t0, T,
+                                      lane, has_grad ? a.w_tp * inv_AN : 0.f);
+      if (lane == 0 && a.loss) a.loss[2 * (size_t)a.R + row] = l;
     }
   } else if (a.loss) {
     for (int i = i_lo + tid; i < i_hi; i += nthr) a.loss[2 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
+  }
+  __syncthreads();       // the waypoint term touches other (row, step) entries of dtraj[..][0..1] than the lanes above
+
+  // ---------------- waypoint terms: warp per agent --------------------------------------------
+  //   TargetPosAtTimeLoss (guidance_loss.py:630-670), the exact / progress branches of GlobalTargetPosAtTimeLoss (:930-1031) and
+  //   GlobalTargetPosLoss (:1033-1135) with compute_progress_loss (:876-927); which branch an agent takes is host logic (wp_mode)
+  if (a.w_wp != 0.f && a.wp_mode) {
+    for (int i = i_lo + warp; i < i_hi; i += nwarps) {
+      const int g = ag0 + i;
+      const size_t row = (size_t)g * N + n;
+      const int mode = a.wp_mode[g];
+      const bool has_grad = !(a.w_ac != 0.f && agt[i * 8 + 3] == 0.f);
+      const float kk = has_grad ? a.w_wp * inv_AN * (a.wp_w ? a.wp_w[g] : 1.f) : 0.f;
+      const float* tr = a.traj + (size_t)row * T * 6;
+      float* dt_ = a.dtraj + (size_t)row * T * 4;
+      const float tx = a.wp_target[g * 2 + 0], ty = a.wp_target[g * 2 + 1];
+      float l = 0.f;
+      if (mode == 4) {
+        l = target_pos_term(tr, dt_, tx, ty, (int)(a.min_target_time * (float)T), T, lane, kk);
+      } else if (mode != 0 && lane == 0) {
+        const int ts = min(max(a.wp_time[g], 0), T - 1);
+        const float gd = a.wp_dist[g];
+        if (mode == 1) {
+          const float dx = tr[ts * 6] - tx, dy = tr[ts * 6 + 1] - ty, d = sqrtf(dx * dx + dy * dy);
+          l = d;
+          if (d > 0.f) { dt_[ts * 4] += kk * dx / d; dt_[ts * 4 + 1] += kk * dy / d; }
+        } else {
+          const float ex = tr[(T - 1) * 6] - tx, ey = tr[(T - 1) * 6 + 1] - ty, dl = sqrtf(ex * ex + ey * ey);
+          if (mode == 2) {
+            l = fmaxf(dl - gd, 0.f);
+            if (dl - gd > 0.f && dl > 0.f) { dt_[(T - 1) * 4] += kk * ex / dl; dt_[(T - 1) * 4 + 1] += kk * ey / dl; }
+          } else {
+            const float fx = tr[0] - tx, fy = tr[1] - ty, df = sqrtf(fx * fx + fy * fy);
+            const float e = gd - (df - dl);
+            l = fmaxf(e, 0.f);
+            if (e > 0.f) {
+              if (df > 0.f) { dt_[0] -= kk * fx / df; dt_[1] -= kk * fy / df; }
+              if (dl > 0.f) { dt_[(T - 1) * 4] += kk * ex / dl; dt_[(T - 1) * 4 + 1] += kk * ey / dl; }
+            }
+          }
+        }
+      }
+      if (lane == 0 && a.loss) a.loss[6 * (size_t)a.R + row] = l;
+    }
+  } else if (a.loss) {
+    for (int i = i_lo + tid; i < i_hi; i += nthr) a.loss[6 * (size_t)a.R + (size_t)(ag0 + i) * N + n] = 0.f;
   }
   __syncthreads();       // the terms below add to dtraj[..][2] of the same rows (different lanes <-> steps than above)
 
@@ -583,6 +638,9 @@ int guidance_loss_grad(CldHandle* h, const float* traj, const CldScene* sc, cons
   a.w_ac = g->w_agent_collision; a.w_mc = g->w_map_collision; a.w_tp = g->w_target_pos;
   a.tspeed = sc->target_speed; a.w_ts = g->w_target_speed; a.w_al = g->w_acc_limit; a.acc_limit = g->acc_limit;
   a.w_sl = g->w_speed_limit; a.speed_limit = g->speed_limit; a.dacc = a.w_al != 0.f ? dacc : nullptr;
+  a.w_wp = g->w_waypoint; a.wp_target = sc->wp_target; a.wp_mode = sc->wp_mode; a.wp_time = sc->wp_time; a.wp_dist = sc->wp_dist; a.wp_w = sc->wp_weight;
+  if (a.w_wp != 0.f && (!sc->wp_target || !sc->wp_mode || !sc->wp_time || !sc->wp_dist))
+    return fail(h, CLD_ERR_ARG, "waypoint guidance needs CldScene.wp_target / wp_mode / wp_time / wp_dist");
   if (a.w_ts != 0.f && !sc->target_speed) return fail(h, CLD_ERR_ARG, "target_speed guidance needs CldScene.target_speed");
   if (a.w_al != 0.f && !dacc) return fail(h, CLD_ERR_STATE, "internal: acc-limit guidance without a d(acc) buffer");
   a.work = h->map_work; a.assign = 0; a.exhaustive = h->env_map_exhaustive ? 1 : 0;

@@ -14,6 +14,7 @@ import torch.distributed as dist
 # data_batch / aux_info entries indexed by agent row (B = S*A, scene-major)
 PER_AGENT_KEYS = (
     "extent", "world_from_agent", "raster_from_agent", "curr_speed", "drivable_map", "drivable_map_bits", "scene_index", "target_pos", "target_speed",
+    "wp_target", "wp_mode", "wp_time", "wp_dist", "wp_weight",
     "all_other_agents_future_positions", "all_other_agents_future_availability", "history_positions",
     "history_yaws", "cond_feat", "curr_states", "image",
 )

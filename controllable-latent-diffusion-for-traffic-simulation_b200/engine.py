@@ -154,6 +154,10 @@ class Engine:
             "others": _f32(batch.get("all_other_agents_future_positions"), d),
             "avail": _u8(batch.get("all_other_agents_future_availability"), d),
             "tspeed": _f32(batch.get("target_speed"), d),
+            # waypoint guidance (cld_b200.waypoints.*.scene_entries): per-agent local target, branch, time step, goal distance, multiplier
+            "wp_target": _f32(batch.get("wp_target"), d), "wp_dist": _f32(batch.get("wp_dist"), d), "wp_weight": _f32(batch.get("wp_weight"), d),
+            "wp_mode": batch["wp_mode"].to(d, torch.int32).contiguous() if batch.get("wp_mode") is not None else None,
+            "wp_time": batch["wp_time"].to(d, torch.int32).contiguous() if batch.get("wp_time") is not None else None,
         }
         sc = CldScene()
         sc.num_scenes, sc.agents_per_scene, sc.num_samp = int(num_scenes), int(agents_per_scene), int(num_samp)
@@ -166,6 +170,8 @@ class Engine:
         sc.target_pos, sc.others_pos, sc.others_avail = _ptr(keep["target"]), _ptr(keep["others"]), _ptr(keep["avail"])
         sc.num_others = int(keep["others"].shape[1]) if keep["others"] is not None else 0
         sc.target_speed = _ptr(keep["tspeed"])
+        sc.wp_target, sc.wp_mode, sc.wp_time = _ptr(keep["wp_target"]), _ptr(keep["wp_mode"]), _ptr(keep["wp_time"])
+        sc.wp_dist, sc.wp_weight = _ptr(keep["wp_dist"]), _ptr(keep["wp_weight"])
         if keep["tspeed"] is not None and tuple(keep["tspeed"].shape[-1:]) != (self.T,):
             raise ValueError("target_speed must be [B, T=%d]" % self.T)
         if keep["others"] is not None and keep["others"].shape[2] != self.T:
@@ -191,6 +197,7 @@ class Engine:
         gc.w_target_speed = float(g.get("target_speed", 0.0))
         gc.w_acc_limit, gc.acc_limit = float(g.get("acc_limit", 0.0)), float(g.get("acc_limit_value", 0.0))
         gc.w_speed_limit, gc.speed_limit = float(g.get("speed_limit", 0.0)), float(g.get("speed_limit_value", 0.0))
+        gc.w_waypoint = float(g.get("waypoint", 0.0))
         return gc
 
     # ------------------------------------------------------------------ kernels
@@ -346,7 +353,7 @@ class Engine:
         R = z.shape[0]
         gc = self.make_guidance(guidance)
         z_out, grad = torch.empty_like(z), torch.empty_like(z)
-        loss = torch.empty(6, R, device=self.device)      # agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit
+        loss = torch.empty(7, R, device=self.device)      # agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit, waypoint
         self._check(lib.cld_guidance_step(self._h, _ptr(z), _ptr(cond), _ptr(curr), C.byref(scene), C.byref(gc),
                                           _ptr(z_out), _ptr(grad), _ptr(loss), R, self._stream()), "cld_guidance_step")
         return z_out, grad, loss

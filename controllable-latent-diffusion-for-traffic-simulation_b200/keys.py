@@ -17,7 +17,9 @@ def default_guidance(**over):
     g = dict(agent_collision=50.0, map_collision=1.0, target_pos=0.0, num_disks=2, buffer_dist=0.2, decay=0.9,
              num_points=(10, 10), speed_th=0.5, min_target_time=0.0, optimizer="adam", lr=0.3,
              # SURVEY.md sec. 8 f-4 (off by default): weights and limits of TargetSpeedLoss / AccLimitLoss / SpeedLimitLoss
-             target_speed=0.0, acc_limit=0.0, acc_limit_value=0.0, speed_limit=0.0, speed_limit_value=0.0)
+             target_speed=0.0, acc_limit=0.0, acc_limit_value=0.0, speed_limit=0.0, speed_limit_value=0.0,
+             # waypoint terms (cld_b200.waypoints: target_pos_at_time / global_target_pos_at_time / global_target_pos)
+             waypoint=0.0)
     g.update(over)
     return g
 

@@ -9,7 +9,7 @@ import torch
 from .keys import agents_per_scene as _agents_per_scene, default_guidance
 
 SCENE_LEVEL_TERMS = ("agent_collision",)      # + social_group / gpt* in the reference, which are not built
-LOSS_ROWS = ("agent_collision", "map_collision", "target_pos", "target_speed", "acc_limit", "speed_limit")
+LOSS_ROWS = ("agent_collision", "map_collision", "target_pos", "target_speed", "acc_limit", "speed_limit", "waypoint")
 
 
 def choose_action_from_guidance(guide_losses, agents_per_scene, scene_level):

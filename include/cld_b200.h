@@ -83,6 +83,8 @@ typedef struct {
   float acc_limit;
   float w_speed_limit;      /* SpeedLimitLoss   guidance_loss.py:1509-1538: mean_t max(|v_t| - speed_limit, 0)            */
   float speed_limit;
+  float w_waypoint;         /* waypoint terms selected per agent by CldScene.wp_mode (TargetPosAtTimeLoss guidance_loss.py:630-670; the
+                               branches of GlobalTargetPosAtTimeLoss :930-1031 / GlobalTargetPosLoss :1033-1135, compute_progress_loss :876-927) */
 } CldGuidanceConfig;
 
 /* Per-agent scene tensors (the reference's data_batch entries), B = S*A agent rows, scene-major. */
@@ -103,6 +105,14 @@ typedef struct {
   int32_t map_packed;               /* 0: drivable_map is [B,H,W] bytes; 1: bit-packed [B,H,(W+7)/8] bytes, pixel x = bit (x & 7) of
                                        byte x >> 3 (numpy.packbits(..., bitorder="little")): 8x fewer bytes to ship per scene      */
   const float* target_speed;        /* [B,T] target speed of every step (TargetSpeedLoss) or NULL */
+  /* waypoint guidance (w_waypoint != 0), per agent; the host decides the branch (cld_b200.waypoints mirrors the reference's forward()):
+   *   wp_mode 0 none | 1 ||p[wp_time] - g|| | 2 relu(||p[T-1] - g|| - wp_dist) | 3 relu(wp_dist - (||p[0] - g|| - ||p[T-1] - g||)) |
+   *           4 TargetPosLoss(g);   g = wp_target in the AGENT frame;   wp_weight = multiplier (A / guided agents of the scene) or NULL */
+  const float* wp_target;           /* [B,2] or NULL */
+  const int32_t* wp_mode;           /* [B]   or NULL */
+  const int32_t* wp_time;           /* [B]   or NULL */
+  const float* wp_dist;             /* [B]   or NULL */
+  const float* wp_weight;           /* [B]   or NULL */
 } CldScene;
 
 int cld_version(void);
@@ -219,7 +229,7 @@ int cld_indicators(CldHandle* h, const float* traj, const CldScene* scene, uint8
  * decoder = lstm_dec and transform = convert_action_to_state_and_action, one scene per reference
  * call: z_out = z_mean - lr*g/(|g|+1e-8) (Adam step 1) or z_mean - lr*g (SGD), g = dL/dz by an
  * analytic backward.  cond/curr are per ROW ([R,C], [R,4]).  grad_out [R,T,4] and
- * loss_out [6,R] (agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit per row) may be NULL. */
+ * loss_out [7,R] (agent_collision, map_collision, target_pos, target_speed, acc_limit, speed_limit, waypoint per row) may be NULL. */
 int cld_guidance_step(CldHandle* h, const float* z_mean, const float* cond, const float* curr,
                       const CldScene* scene, const CldGuidanceConfig* g, float* z_out,
                       float* grad_out, float* loss_out, int R, void* stream);

@@ -571,3 +571,55 @@ def test_ragged_scenes_equal_per_scene_calls(gpu_models):
     stats = failure_rate_compute(dm, out["traj"], bd)
     assert 0.0 <= stats["overall_failure_rate"] <= 1.0
     assert others.shape[0] == B
+
+
+def test_waypoint_guidance_terms_vs_oracle(gpu_models):
+    """TargetPosAtTimeLoss / GlobalTargetPosAtTimeLoss / GlobalTargetPosLoss through cld_guidance_step (analytic
+    gradient through the decoder) against the oracle's autograd; the oracle's formulas and cld_b200.waypoints' host logic are pinned to
+    the real reference classes by tests/test_oracle.py::test_waypoint_terms_vs_reference_golden.  2 scenes x 4 agents x 2 samples,
+    every branch (none / at-time / final-distance hinge / progress hinge / TargetPosLoss) and an agent that has arrived."""
+    from cld_b200.waypoints import GlobalTargetPos, GlobalTargetPosAtTime, TargetPosAtTime
+    dm, vae, algo = gpu_models(10)
+    S, A, N, T = 2, 4, 2, 52
+    aux, batch = make_scenes(S, A, seed=41, dense=True)
+    B = S * A
+    wfa = batch["world_from_agent"]
+    batch["agent_from_world"] = torch.linalg.inv(wfa)
+    hist = torch.zeros(B, 31, 8)
+    hist[:, :, 0] = -(torch.arange(30, -1, -1).float() * 0.1)[None, :] * aux["curr_states"][:, 2:3]
+    batch["agent_hist"] = hist
+    rng = torch.tensor([6.0, 15.0, 40.0, 90.0, 25.0, 0.3, 60.0, 12.0])
+    lat = torch.tensor([1.0, -2.0, 3.0, -4.0, 2.0, 0.1, -1.0, 0.5])
+    local = torch.stack([rng, lat], 1)
+    world = torch.einsum('bij,bj->bi', wfa[:, :2, :2], local) + wfa[:, :2, 2]
+    urg = torch.tensor([0.0, 0.3, 0.5, 0.8, 0.2, 0.1, 0.4, 0.6])
+    pref = torch.tensor([1.5, 2.0, 3.0, 4.0, 2.5, 1.0, 2.0, 3.5])
+    gat = GlobalTargetPosAtTime(world, torch.tensor([20, 40, 80, 150, 3, 56, 30, 200]), urg, pref, target_tolerance=2.0)
+    gat.update(5)
+    terms = {"at_time": TargetPosAtTime(local, torch.tensor([3, 10, 25, 51, 40, 0, 7, 30]), agents=torch.tensor([1, 1, 0, 1, 1, 1, 1, 0]).bool()),
+             "global_at_time": gat,
+             "global": GlobalTargetPos(world, urg, pref, min_progress_dist=0.5, target_tolerance=2.0)}
+    torch.manual_seed(12)
+    z = torch.randn(B * N, T, 4)
+    rep = lambda v: v.repeat_interleave(N, dim=0)        # noqa: E731
+    eng = dm.engine(B * N)
+    dec_sd = cpu_sd(vae.lstmvae.lstm_dec)
+    seen = set()
+    for tag, term in terms.items():
+        ent = term.scene_entries(batch, T, A)
+        seen |= set(ent["wp_mode"].tolist())
+        b2 = dict(batch, **ent)
+        g = dict(O.DEFAULT_GUIDANCE, agent_collision=0.0, map_collision=0.0, waypoint=2.0, optimizer="sgd", lr=1.0)
+        want_grad, per = O.guidance_grad(dec_sd, z, aux["cond_feat"], aux["curr_states"], b2, A, N, g)
+        assert want_grad.abs().sum() > 0
+        scene = eng.make_scene(b2, S, A, N)
+        z_out, grad, loss = eng.guidance_step(z.cuda(), rep(aux["cond_feat"]).cuda(), rep(aux["curr_states"]).cuda(), scene, g)
+        want_loss = torch.cat([p["waypoint"] for p in per]).reshape(-1)
+        assert rel(loss[6], want_loss) < 1e-4, tag
+        assert rel(grad, want_grad) < 1e-3, (tag, rel(grad, want_grad))
+        assert rel(z_out, z - want_grad) < 1e-4
+        # rows of agents without a waypoint carry no gradient
+        idle = rep(ent["wp_mode"] == 0)
+        assert grad.cpu()[idle].abs().max() == 0 if idle.any() else True
+    assert seen == {0, 1, 2, 3, 4}
+    assert terms["global"].have_reached.tolist() == [False] * 5 + [True] + [False] * 2

@@ -260,3 +260,44 @@ def test_warmup_cosine_schedule():
     from cld_b200.trainer import warmup_cosine
     assert warmup_cosine(0, 30) == 0.0 and abs(warmup_cosine(5, 30) - 0.5) < 1e-12 and abs(warmup_cosine(10, 30) - 1.0) < 1e-12
     assert abs(warmup_cosine(20, 30) - 0.5) < 1e-12 and warmup_cosine(30, 30) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------- f-4 (waypoint terms)
+def _waypoint_batch(g):
+    t = lambda k: torch.tensor(g[k])          # noqa: E731
+    return {"agent_from_world": t("agent_from_world"), "world_from_agent": t("world_from_agent"), "agent_hist": t("agent_hist")}
+
+
+def _waypoint_terms(g):
+    from cld_b200.waypoints import GlobalTargetPos, GlobalTargetPosAtTime, TargetPosAtTime
+    t = lambda k: torch.tensor(g[k])          # noqa: E731
+    tol, an = float(g["target_tolerance"]), int(g["action_num"])
+    gat = GlobalTargetPosAtTime(t("target_world"), t("t_gl"), t("urgency"), t("pref_speed"), dt=float(g["dt"]), target_tolerance=tol, action_num=an)
+    gat.update(int(g["global_t"]))
+    return {"at_time": TargetPosAtTime(t("target_local"), t("t_at")), "global_at_time": gat,
+            "global": GlobalTargetPos(t("target_world"), t("urgency"), t("pref_speed"), dt=float(g["dt"]),
+                                      min_progress_dist=float(g["min_progress_dist"]), target_tolerance=tol, action_num=an)}
+
+
+def test_waypoint_terms_vs_reference_golden(gold):
+    """Host logic of cld_b200.waypoints (branch per agent, local targets, goal distances, have_reached) and the oracle's four
+    formulas against the REAL TargetPosAtTimeLoss / GlobalTargetPosAtTimeLoss / GlobalTargetPosLoss (tests/golden/waypoint.npz)."""
+    g = gold("waypoint")
+    x = torch.tensor(g["x"])
+    B, N, T = x.shape[:3]
+    batch = _waypoint_batch(g)
+    for tag, term in _waypoint_terms(g).items():
+        ent = term.scene_entries(batch, T, B)
+        assert torch.equal(ent["wp_mode"], torch.tensor(g[tag + "_mode"])), tag
+        act = ent["wp_mode"] != 0
+        assert torch.allclose(ent["wp_target"][act], torch.tensor(g[tag + "_target"])[act], atol=1e-5)
+        assert torch.equal(ent["wp_time"][ent["wp_mode"] == 1], torch.tensor(g[tag + "_time"])[ent["wp_mode"] == 1])
+        assert torch.allclose(ent["wp_dist"], torch.tensor(g[tag + "_dist"]), atol=1e-5)
+        assert torch.allclose(ent["wp_weight"], act.float() * (B / act.sum()))
+        xo = x.clone().requires_grad_(True)
+        wp = {k[3:]: v for k, v in ent.items()}
+        l = O.waypoint_loss(xo, wp)
+        (gr,) = torch.autograd.grad((l * torch.tensor(g["w_samp"])).sum(), xo)
+        assert torch.allclose(l.detach(), torch.tensor(g[tag + "_loss"]), atol=1e-5, rtol=1e-5), tag
+        assert torch.allclose(gr, torch.tensor(g[tag + "_grad"]), atol=1e-5, rtol=1e-4), tag
+    assert set(g["global_at_time_mode"].tolist()) == {0, 1, 2} and set(g["global_mode"].tolist()) == {0, 3, 4}
