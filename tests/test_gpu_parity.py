@@ -331,7 +331,13 @@ def test_shards_chunks_and_lanes_equal_the_unsharded_batch(models_cpu, precision
     from cld_b200.engine import default_guidance
     S, A, N = 8, 4, 2
     aux, batch = make_scenes(S, A, seed=77, dense=True)
-    kw = dict(sampler="ddpm", guidance=default_guidance(), use_device_rng=True, seed=2024, want_indicators=True, agents_per_scene=A)
+    # per-agent guidance inputs as well (target speeds, waypoints): their rows must follow the agents through shards, chunks and lanes
+    from cld_b200.waypoints import TargetPosAtTime
+    torch.manual_seed(9)
+    batch["target_speed"] = (aux["curr_states"][:, 2:3] + torch.randn(S * A, 1)).clamp(min=0).repeat(1, 52)
+    batch.update(TargetPosAtTime(batch["target_pos"], torch.randint(5, 52, (S * A,)), agents=torch.rand(S * A) < 0.7).scene_entries(batch, 52, A))
+    guid = default_guidance(target_speed=2.0, waypoint=1.0)
+    kw = dict(sampler="ddpm", guidance=guid, use_device_rng=True, seed=2024, want_indicators=True, agents_per_scene=A)
 
     def build(**k):
         dm, vae, algo = models_cpu(10, precision=precision, **k)
@@ -363,8 +369,10 @@ def test_shards_chunks_and_lanes_equal_the_unsharded_batch(models_cpu, precision
     assert eng.max_rows == 2 * A * N
     scene = eng.make_scene(batch, S, A, N)
     o = eng.sample(x_init, aux["cond_feat"].cuda().repeat_interleave(N, 0), seed=2024, curr_rows=aux["curr_states"].cuda().repeat_interleave(N, 0),
-                   scene=scene, guidance=default_guidance(), sampler="ddpm", want_indicators=True)
+                   scene=scene, guidance=guid, sampler="ddpm", want_indicators=True)
     assert torch.equal(o["x0"], full["pred_traj"]) and torch.equal(o["traj"], full["traj"]) and torch.equal(o["coll"], full["coll"])
+    plain = dm(cu(batch), cu(aux), algo, x_init=x_init, **dict(kw, guidance=default_guidance()))
+    assert not torch.equal(plain["pred_traj"], full["pred_traj"])            # the per-agent terms do act
     # (iii) two lanes
     dm_l, algo_l = build(max_rows=S * A * N, lanes=2)
     lan = dm_l(cu(batch), cu(aux), algo_l, x_init=x_init, **kw)
