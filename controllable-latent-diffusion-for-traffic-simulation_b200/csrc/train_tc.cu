@@ -22,16 +22,17 @@ namespace cld {
 using namespace cld::tc;
 
 constexpr int TF_THREADS = 192;
-constexpr int TF_STAGES = 6;
+constexpr int TF_MAX_STAGES = 8;
 constexpr int TF_A_BYTES = 128 * 128;            // 128 GEMM rows x 32 fp32
-constexpr int TF_MAX_BN = 64;
-constexpr int TF_STAGE_BYTES = TF_A_BYTES + TF_MAX_BN * 128;
-constexpr int TF_SMEM = TF_STAGES * TF_STAGE_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
+constexpr int TF_MAX_BN = 256;
+constexpr int TF_DATA_BYTES = 192 * 1024;        // stage ring: stages x (A tile + BN x 128 B)
+constexpr int TF_SMEM = TF_DATA_BYTES + 1024 /* barriers */ + 1024 /* alignment slack */;
 
 struct TfConv {
   int ntaps; int toff[5]; int wtap[5];
   int kb0, kb1;                 // 32-channel blocks of source 0 / source 1 (concatenated input)
   int Tp, rbox, R, N, BN;
+  int stages, stage_bytes;      // ring depth (<= TF_MAX_STAGES) and bytes per stage (A tile + B tile)
   int Tout, ostride, ooff;      // output tensor [R, Tout, N]; GEMM row (r, j) is written to slot j * ostride + ooff
   const float* bias; float* out; int accum;
 };
@@ -55,16 +56,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf32_conv_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmW, const TfConv P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TF_STAGES * TF_STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TF_STAGES + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TF_DATA_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TF_MAX_STAGES + 2);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TF_STAGES, bar_acc = bar_empty + 8 * TF_STAGES;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TF_MAX_STAGES, bar_acc = bar_empty + 8 * TF_MAX_STAGES;
+  const int TF_STAGES = P.stages;
+  const uint32_t TF_STAGE_BYTES = (uint32_t)P.stage_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_valid = P.rbox * P.Tp;
   const uint32_t a_bytes = (uint32_t)rows_valid * 128u, b_bytes = (uint32_t)P.BN * 128u;
   const int r0 = blockIdx.x * P.rbox, n0 = blockIdx.y * P.BN;
   const int kbs = P.kb0 + P.kb1, n_st = P.ntaps * kbs;
-  const uint32_t tm_cols = P.BN <= 32 ? 32u : 64u;
+  const uint32_t tm_cols = P.BN <= 32 ? 32u : (P.BN <= 64 ? 64u : (P.BN <= 128 ? 128u : 256u));
   if (tid == 0) {
     for (int i = 0; i < TF_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
@@ -341,7 +344,14 @@ int tfconv_launch(CldHandle* h, const float* in0, int c0, const float* in1, int 
   if (P.rbox > R) P.rbox = R;
   if (P.rbox > 256) P.rbox = 256;
   const int mtiles = (R + P.rbox - 1) / P.rbox;
+  // N tile: the largest that still gives every SM a CTA (the A box is re-read once per N tile: large batches want wide tiles, the
+  // 128-row minibatch wants many CTAs)
   P.BN = (N % 64 == 0 && mtiles * (N / 64) >= 120) ? 64 : (N % 32 == 0 ? 32 : 16);
+  for (int bn = TF_MAX_BN; bn > 64; bn >>= 1)
+    if (N % bn == 0 && mtiles * (N / bn) >= h->num_sms) { P.BN = bn; break; }
+  P.stage_bytes = TF_A_BYTES + P.BN * 128;
+  P.stages = TF_DATA_BYTES / P.stage_bytes;
+  if (P.stages > TF_MAX_STAGES) P.stages = TF_MAX_STAGES;
   P.bias = bias; P.out = out; P.accum = accum; P.Tout = Tout; P.ostride = ostride; P.ooff = ooff;
   const CUtensorMap *mA0, *mA1, *mW;
   int rc;
