@@ -344,33 +344,77 @@ __device__ __forceinline__ float mish_grad(float x) {
 // Per-row partials (rp [R][dg | db | sum_t dx = the bias gradient of the convolution in front], and sum_t dY = d(time bias)) are
 // written; one colsum reduces them over the rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, const float* __restrict__ dy,
-                                                          float* __restrict__ dx, float* __restrict__ rp,
-                                                          float* __restrict__ dtb, int tb_stride, int T, int C) {
-  const int r = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// NW warps share a group (a 128-row minibatch is one CTA per row on 128 of 148 SMs: the per-warp loop of 13..26 dependent
+// load -> libm-Mish iterations is the kernel's latency; more warps per group shorten it).  Partial sums of the NW warps are combined
+// through shared memory in a fixed order.
+template <int NW>
+__device__ __forceinline__ float group_sum(float v, float* red, int g, int w, int lane) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[g * NW + w] = v;
+  __syncthreads();
+  float t = red[g * NW];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) t += red[g * NW + i];
+  return t;
+}
+
+// forward: GroupNorm(8) -> Mish -> (+ per-row channel bias | + residual), as gn_mish_fp32 (kernels_unet_fp32.cu) with NW warps per group
+template <int NW>
+__global__ void __launch_bounds__(256 * NW) gn_mish_fwd_mw_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const float* __restrict__ tbias,
+                                                                   int tb_stride, const float* __restrict__ res, float* __restrict__ out,
+                                                                   int T, int C) {
+  __shared__ float red[2][8 * NW];
+  const int r = blockIdx.x, wid = threadIdx.x >> 5, g = wid / NW, w = wid % NW, lane = threadIdx.x & 31;
+  const int cpg = C >> 3, n = T * cpg;
+  const float* xin = in + (size_t)r * T * C + g * cpg;
+  float s = 0.f;
+  for (int e = lane + 32 * w; e < n; e += 32 * NW) s += xin[(e / cpg) * C + (e % cpg)];
+  const float mean = group_sum<NW>(s, red[0], g, w, lane) / (float)n;
+  float v = 0.f;
+  for (int e = lane + 32 * w; e < n; e += 32 * NW) {
+    const float d = xin[(e / cpg) * C + (e % cpg)] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = 1.0f / sqrtf(group_sum<NW>(v, red[1], g, w, lane) / (float)n + 1e-5f);
+  for (int e = lane + 32 * w; e < n; e += 32 * NW) {
+    const int t = e / cpg, c = g * cpg + (e % cpg);
+    float y = (xin[t * C + (e % cpg)] - mean) * rstd * gamma[c] + beta[c];
+    y = mish_fwd(y);
+    if (tbias) y += tbias[(size_t)r * tb_stride + c];
+    if (res) y += res[((size_t)r * T + t) * C + c];
+    out[((size_t)r * T + t) * C + c] = y;
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256 * NW) gn_mish_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ dy,
+                                                                float* __restrict__ dx, float* __restrict__ rp,
+                                                                float* __restrict__ dtb, int tb_stride, int T, int C) {
+  __shared__ float red[4][8 * NW];
+  __shared__ float chan[4][8 * NW][32];             // per-warp per-channel partials of dgamma, dbeta, sum dY, sum dx
+  const int r = blockIdx.x, wid = threadIdx.x >> 5, g = wid / NW, w = wid % NW, lane = threadIdx.x & 31;
   const int cpg = C >> 3, n = T * cpg;
   const size_t base = (size_t)r * T * C + g * cpg;
   const float* xin = x + base;
   const float* dyin = dy + base;
   float* dxo = dx + base;
+  const int e0 = lane + 32 * w, es = 32 * NW;
   float s = 0.f;
-  for (int e = lane; e < n; e += 32) s += xin[(e / cpg) * C + (e % cpg)];
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)n;
+  for (int e = e0; e < n; e += es) s += xin[(e / cpg) * C + (e % cpg)];
+  const float mean = group_sum<NW>(s, red[0], g, w, lane) / (float)n;
   float v = 0.f;
-  for (int e = lane; e < n; e += 32) {
+  for (int e = e0; e < n; e += es) {
     const float d = xin[(e / cpg) * C + (e % cpg)] - mean;
     v = fmaf(d, d, v);
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const float rstd = 1.0f / sqrtf(v / (float)n + 1e-5f);
-  const int cl = lane % cpg, c = g * cpg + cl;        // this lane's channel (cpg | 32)
+  const float rstd = 1.0f / sqrtf(group_sum<NW>(v, red[1], g, w, lane) / (float)n + 1e-5f);
+  const int cl = lane % cpg, c = g * cpg + cl;        // this lane's channel (cpg | 32, and the warp stride 32 NW keeps it)
   const float gm = gamma[c], bt = beta[c];
   float sg = 0.f, sb = 0.f, sy = 0.f, s1 = 0.f, s2 = 0.f;
-  for (int e = lane; e < n; e += 32) {
+  for (int e = e0; e < n; e += es) {
     const int off = (e / cpg) * C + cl;
     const float xh = (xin[off] - mean) * rstd;
     const float u = fmaf(xh, gm, bt);
@@ -381,19 +425,22 @@ __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restric
     s1 += dxh; s2 = fmaf(dxh, xh, s2);
     dxo[off] = dxh;
   }
-  // per-channel sums: lanes with equal lane % cpg
+  // per-channel sums: lanes with equal lane % cpg, then the NW warps of the group
   for (int o = 16; o >= cpg; o >>= 1) {
     sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
   }
-  if (lane < cpg) {
-    rp[(size_t)r * 3 * C + c] = sg; rp[(size_t)r * 3 * C + C + c] = sb;      // [R][gamma | beta | conv bias]
-    if (dtb) dtb[(size_t)r * tb_stride + c] = sy;
-  }
+  if (lane < cpg) { chan[0][wid][lane] = sg; chan[1][wid][lane] = sb; chan[2][wid][lane] = sy; }
+  const float m1 = group_sum<NW>(s1, red[2], g, w, lane) / (float)n;        // (its __syncthreads also publishes chan[0..2])
+  const float m2 = group_sum<NW>(s2, red[3], g, w, lane) / (float)n;
+  if (w == 0 && lane < cpg) {
+    float tg = 0.f, tb = 0.f, ty = 0.f;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-  const float m1 = s1 / (float)n, m2 = s2 / (float)n;
+    for (int i = 0; i < NW; ++i) { tg += chan[0][g * NW + i][lane]; tb += chan[1][g * NW + i][lane]; ty += chan[2][g * NW + i][lane]; }
+    rp[(size_t)r * 3 * C + c] = tg; rp[(size_t)r * 3 * C + C + c] = tb;      // [R][gamma | beta | conv bias]
+    if (dtb) dtb[(size_t)r * tb_stride + c] = ty;
+  }
   float sx = 0.f;                                     // sum_t dx of this lane's channel = the row's share of the conv bias gradient
-  for (int e = lane; e < n; e += 32) {
+  for (int e = e0; e < n; e += es) {
     const int off = (e / cpg) * C + cl;
     const float xh = (xin[off] - mean) * rstd;
     const float d = rstd * (dxo[off] - m1 - xh * m2);
@@ -401,7 +448,14 @@ __global__ void __launch_bounds__(256) gn_mish_bwd_kernel(const float* __restric
     sx += d;
   }
   for (int o = 16; o >= cpg; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
-  if (lane < cpg) rp[(size_t)r * 3 * C + 2 * C + c] = sx;
+  if (lane < cpg) chan[3][wid][lane] = sx;
+  __syncthreads();
+  if (w == 0 && lane < cpg) {
+    float tx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) tx += chan[3][g * NW + i][lane];
+    rp[(size_t)r * 3 * C + 2 * C + c] = tx;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -791,8 +845,14 @@ static int slice(CldHandle* h, float* dst, const float* src, size_t M, int C, in
   return 0;
 }
 
-int gn_mish_launch(CldHandle* h, const float* in, const GnW& n, const float* tbias, int tb_stride, const float* res, float* out, int T,
-                   int C, int R, cudaStream_t s);   // kernels_unet_fp32.cu
+// warps per GroupNorm group in the training kernels: 2 while the batch leaves SMs idle (latency), 1 for large batches (occupancy)
+static int gn_mish_train(CldHandle* h, const float* in, const GnW& n, const float* tbias, int tb_stride, const float* res, float* out, int T,
+                          int C, int R, cudaStream_t s) {
+  if (R <= 2 * h->num_sms) gn_mish_fwd_mw_kernel<2><<<R, 512, 0, s>>>(in, n.g, n.b, tbias, tb_stride, res, out, T, C);
+  else gn_mish_fwd_mw_kernel<1><<<R, 256, 0, s>>>(in, n.g, n.b, tbias, tb_stride, res, out, T, C);
+  CLD_LAUNCH_OK(h, "gn_mish_fwd_mw_kernel");
+  return 0;
+}
 
 static int block_fwd(CldHandle* h, int bi, const float* in0, int c0, const float* in1, int c1, int T, int R, cudaStream_t s) {
   TrainState* st = ts_of(h);
@@ -801,14 +861,14 @@ static int block_fwd(CldHandle* h, int bi, const float* in0, int c0, const float
   b.in0 = in0; b.c0 = c0; b.in1 = in1; b.c1 = c1; b.T = T;
   int rc;
   if ((rc = conv_fwd(h, rb.c0, in0, c0, in1, c1, T, b.A0, T, T, 1, 1, 0, kOff5, rb.c0.b, R, s))) return rc;
-  if ((rc = gn_mish_launch(h, b.A0, rb.n0, h->tbias + rb.tb_off, h->unet.tb_total, nullptr, b.B0, T, rb.cout, R, s))) return rc;
+  if ((rc = gn_mish_train(h, b.A0, rb.n0, h->tbias + rb.tb_off, h->unet.tb_total, nullptr, b.B0, T, rb.cout, R, s))) return rc;
   if ((rc = conv_fwd(h, rb.c1, b.B0, rb.cout, nullptr, 0, T, b.A1, T, T, 1, 1, 0, kOff5, rb.c1.b, R, s))) return rc;
   const float* res = in0;
   if (rb.res.w) {
     if ((rc = conv_fwd(h, rb.res, in0, c0, in1, c1, T, st->tmpR, T, T, 1, 1, 0, kOff1, rb.res.b, R, s))) return rc;
     res = st->tmpR;
   }
-  return gn_mish_launch(h, b.A1, rb.n1, nullptr, 0, res, b.OUT, T, rb.cout, R, s);
+  return gn_mish_train(h, b.A1, rb.n1, nullptr, 0, res, b.OUT, T, rb.cout, R, s);
 }
 
 int unet_train_forward(CldHandle* h, const float* x, const float* cond, const int64_t* t, float* eps, int R, cudaStream_t s) {
@@ -842,7 +902,7 @@ int unet_train_forward(CldHandle* h, const float* x, const float* cond, const in
   if ((rc = conv_fwd(h, u.up[1][0], b[11].OUT, d0, nullptr, 0, T2, st->q1, T, T2, 1, 2, 0, off_e, u.up_b[1], R, s))) return rc;
   if ((rc = conv_fwd(h, u.up[1][1], b[11].OUT, d0, nullptr, 0, T2, st->q1, T, T2, 1, 2, 1, off_o, u.up_b[1], R, s))) return rc;
   if ((rc = conv_fwd(h, u.fin0, st->q1, d0, nullptr, 0, T, st->fA, T, T, 1, 1, 0, kOff5, u.fin0.b, R, s))) return rc;
-  if ((rc = gn_mish_launch(h, st->fA, u.fin0n, nullptr, 0, nullptr, st->fB, T, d0, R, s))) return rc;
+  if ((rc = gn_mish_train(h, st->fA, u.fin0n, nullptr, 0, nullptr, st->fB, T, d0, R, s))) return rc;
   if ((rc = conv_fwd(h, u.fin1, st->fB, d0, nullptr, 0, T, eps, T, T, 1, 1, 0, kOff1, u.fin1.b, R, s))) return rc;
   st->x = x; st->t = t; st->R = R; st->fwd_valid = true;
   return 0;
@@ -858,7 +918,8 @@ static int gn_bwd(CldHandle* h, const float* A, const GnW& n, const float* dY, f
   float* rp = st->rp_u[st->unit];
   ++st->unit;
   *dA_out = dA;
-  gn_mish_bwd_kernel<<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, rp, dtb, h->unet.tb_total, T, C);
+  if (R <= 2 * h->num_sms) gn_mish_bwd_kernel<2><<<R, 512, 0, s>>>(A, n.g, n.b, dY, dA, rp, dtb, h->unet.tb_total, T, C);
+  else gn_mish_bwd_kernel<1><<<R, 256, 0, s>>>(A, n.g, n.b, dY, dA, rp, dtb, h->unet.tb_total, T, C);
   CLD_LAUNCH_OK(h, "gn_mish_bwd_kernel");
   return colsum(h, rp, R, 3 * C, dgamma, pg_stream(h, s), C, dbeta, dconv_bias);
 }
