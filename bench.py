@@ -80,39 +80,49 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms 200` process,
+    started before the warm-up (its NVML start-up stays out of the timed region; a process spawned per sample stalled kernel launches
+    for tens of milliseconds), killed after; only the samples that arrived between `mark()` and `stop()` are used."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self.t0, self.proc = index, [], None, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 7:
-                    self.rows.append(f)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+                    self.rows.append((time.perf_counter(), f))
+        except Exception:
+            pass
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        self._stop_evt.set()
+        t1 = time.perf_counter()
+        time.sleep(0.25)                         # let the sample that covers the end of the region arrive
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=3)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [f for ts, f in self.rows if t0 <= ts <= t1 + 0.25] or [f for _, f in self.rows[-1:]]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "sm_max_mhz": float(rows[0][1]) if rows and rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
 
 
 def measured_peaks():
@@ -469,12 +479,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler_thread = ClockSampler(local) if rank == 0 else None
+    if sampler_thread:
+        sampler_thread.start()                  # one long-running nvidia-smi: started before the warm-up, sampled in the timed region
     for _ in range(a.warmup):
         hot_path(batch_d, aux_d, hist_d)
     barrier()
-    sampler_thread = ClockSampler(local) if rank == 0 else None
     if sampler_thread:
-        sampler_thread.start()
+        sampler_thread.mark()
     def count_launches():
         n = dm_run.launch_count() + (ce.launch_count() if ce is not None else 0)
         return n + (dm.launch_count() if dm_run is not dm else 0)
