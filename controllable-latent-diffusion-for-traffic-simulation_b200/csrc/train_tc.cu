@@ -119,24 +119,47 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf32_conv_kernel(const __grid_c
     const int q = warp & 3, m = q * 32 + lane;
     const int r = r0 + m / P.Tp, t = m % P.Tp;
     const bool valid = m < rows_valid && r < P.R;
+    float* op = P.out + ((size_t)r * P.Tout + t * P.ostride + P.ooff) * P.N + n0;
+    // accumulate mode (the residual 1x1 convolution's data gradient is added to the block's): the previous values do not depend on
+    // the MMAs -- up to 64 columns are fetched BEFORE the accumulator wait (read-modify-write behind the wait cost 27 us per launch)
+    float4 prev[16];
+    const bool pre = P.accum && P.BN <= 64;
+    if (pre && valid) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i * 4 < P.BN) prev[i] = *reinterpret_cast<const float4*>(op + i * 4);
+    }
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    float* op = P.out + ((size_t)r * P.Tout + t * P.ostride + P.ooff) * P.N + n0;
-    for (int c = 0; c < P.BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_wait_ld();
-      if (valid) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < P.BN; c0 += 64) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          if (P.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(P.bias + n0 + c + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c = c0 + cc;
+        if (c < P.BN) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+          float4 pv[4];
+          if (P.accum && !pre && valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pv[j] = *reinterpret_cast<const float4*>(op + c + 4 * j);
           }
-          float4* dp = reinterpret_cast<float4*>(op + c + j);
-          if (P.accum) { const float4 p = *dp; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-          *dp = o;
+          tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (P.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(P.bias + n0 + c + j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (P.accum) {
+                const float4 p = pre ? prev[(cc + j) >> 2] : pv[j >> 2];
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *reinterpret_cast<float4*>(op + c + j) = o;
+            }
+          }
         }
       }
     }
