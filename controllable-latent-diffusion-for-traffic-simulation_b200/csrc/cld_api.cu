@@ -318,6 +318,7 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
   }
   if ((rc = dev_alloc(h, &u.tb_w, (size_t)tdim * u.tb_total))) return rc;
   if ((rc = dev_alloc(h, &u.tb_b, u.tb_total))) return rc;
+  if ((rc = dev_alloc(h, &u.tb_wt, (size_t)tdim * u.tb_total))) return rc;
   // time-bias offsets follow EXECUTION order
   int exec_cout[12];
   for (int b = 0; b < 12; ++b) exec_cout[defs[b].exec] = defs[b].cout;
@@ -338,6 +339,9 @@ int cld_load_unet(CldHandle* h, const float* const* p, const int64_t* numels, in
       const int k1x[5] = {0, 0, 0, 0, 0};
       record_job(h, 0, tw, u.tb_w, bd.cout, tdim, 1, 1, k1x, u.tb_total, rb.tb_off, 0, total);
       record_job(h, 2, tbv, u.tb_b + rb.tb_off, 0, 0, 0, 0, nullptr, 0, 0, 0, bd.cout);
+      // torch's Linear weight [cout][tdim] IS the [N][K] plane the tensor-core training forward reads: rows tb_off .. tb_off + cout
+      CLD_CUDA_OK(h, cudaMemcpyAsync(u.tb_wt + (size_t)rb.tb_off * tdim, tw, (size_t)bd.cout * tdim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      record_job(h, 2, tw, u.tb_wt + (size_t)rb.tb_off * tdim, 0, 0, 0, 0, nullptr, 0, 0, 0, bd.cout * tdim);
     }
     TAKE(c0w, bd.cout * bd.cin * 5) TAKE(c0b, bd.cout) TAKE(g0, bd.cout) TAKE(b0, bd.cout)
     TAKE(c1w, bd.cout * bd.cout * 5) TAKE(c1b, bd.cout) TAKE(g1, bd.cout) TAKE(b1, bd.cout)

@@ -41,6 +41,7 @@ struct UnetW {
   float* freqs = nullptr;   // [d/2] sinusoid frequencies (diffuser_helpers.py:27-29)
   // concatenated per-block Linear(288->cout): packed [288][tb_total] + bias[tb_total]
   float* tb_w = nullptr;
+  float* tb_wt = nullptr;   // the same weights as [tb_total][tdim] (K contiguous): B operand of the tensor-core training forward
   float* tb_b = nullptr;
   int tb_total = 0;
   ResBlockW rb[12];     // downs.0.0 .. ups.1.1 in execution order
@@ -193,6 +194,7 @@ int unet_forward_fp32(CldHandle* h, const float* x, const float* cond, const int
                       int R, cudaStream_t s);
 int unet_stage_elems(const CldHandle* h, int stage);
 int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s);   // per-row t -> h->tcm, h->tbias
+int unet_time_cond(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s);   // only h->tcm = Mish([t_emb, cond])
 int unet_cond_bias(CldHandle* h, const float* cond, int R, cudaStream_t s);   // -> h->tbias (cond part + bias)
 int unet_time_vec(CldHandle* h, int t, cudaStream_t s);                        // -> h->tvec
 int unet_time_vec_to(CldHandle* h, int t, float* dst, cudaStream_t s);

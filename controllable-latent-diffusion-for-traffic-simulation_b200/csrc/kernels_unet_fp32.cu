@@ -246,12 +246,20 @@ static int tap(CldHandle* h, int stage, const float* buf, int R, cudaStream_t s)
 }
 
 // time / cond projections of all 12 blocks at once: tbias[R, tb_total] = Mish([t_emb, cond]) @ Wtb + btb
-int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s) {
+int unet_time_cond(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s) {
   const UnetW& u = h->unet;
   const CldConfig& c = h->cfg;
   train_invalidate(h);
   time_cond_mish<<<R, 128, 0, s>>>(t, cond, u.t1_w, u.t1_b, u.t2_w, u.t2_b, u.freqs, h->tcm, c.base_dim, c.cond_dim);
   CLD_LAUNCH_OK(h, "time_cond_mish");
+  return 0;
+}
+
+int unet_time_bias(CldHandle* h, const float* cond, const int64_t* t, int R, cudaStream_t s) {
+  const UnetW& u = h->unet;
+  const CldConfig& c = h->cfg;
+  int rc0 = unet_time_cond(h, cond, t, R, s);
+  if (rc0) return rc0;
   ConvW tb; tb.w = u.tb_w; tb.b = u.tb_b; tb.cin = c.base_dim + c.cond_dim; tb.cout = u.tb_total; tb.ntaps = 1;
   return launch_conv(h, tb, h->tcm, tb.cin, nullptr, 0, 1, h->tbias, 1, 1, 1, 1, 0, kOff1, tb.b, R, s);
 }

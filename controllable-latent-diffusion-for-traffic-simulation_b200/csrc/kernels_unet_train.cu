@@ -880,7 +880,14 @@ int unet_train_forward(CldHandle* h, const float* x, const float* cond, const in
   const int T = c.horizon, T2 = T / 2, T4 = T / 4;
   const int d0 = c.dims[0], d1 = c.dims[1], d2 = c.dims[2], D = c.latent_dim;
   st->fwd_valid = false;
-  if ((rc = unet_time_bias(h, cond, t, R, s))) return rc;      // -> h->tcm, h->tbias (kept for the backward)
+  // -> h->tcm, h->tbias (kept for the backward); the projection of all 12 blocks is one GEMM [R, 288] x [288, 1 792]
+  const int tdim = c.base_dim + c.cond_dim;
+  if (h->train_tf32 && u.tb_wt && tfconv_supported(tdim, 0, u.tb_total, 1)) {
+    if ((rc = unet_time_cond(h, cond, t, R, s))) return rc;
+    const int tap0[5] = {0, 0, 0, 0, 0};
+    if ((rc = tfconv_launch(h, h->tcm, tdim, nullptr, 0, 1, 1, 1, u.tb_wt, 1, 1, tap0, tap0, u.tb_b, h->tbias, 1, 1, 0, u.tb_total, 0, R, s)))
+      return rc;
+  } else if ((rc = unet_time_bias(h, cond, t, R, s))) return rc;
   BlkStash* b = st->blk;
   if ((rc = block_fwd(h, 0, x, D, nullptr, 0, T, R, s))) return rc;
   if ((rc = block_fwd(h, 1, b[0].OUT, d0, nullptr, 0, T, R, s))) return rc;
